@@ -1,0 +1,110 @@
+"""TEST INFRASTRUCTURE ONLY -- regenerates tests/golden/ from the reference itself.
+
+Run in the build container (needs /root/reference, read-only):
+
+    python -m oracle.gen_golden
+
+It executes the reference's own ``Utils.normalize_data``, ``Tracking.TrackBuffer.track``
+and ``TrackBuffer.estimate_posture`` (imported unmodified; patches listed in
+oracle/ref_harness.py) on seeded synthetic scenes from ``mmwave_msc_b200.synth`` and
+stores the per-frame decisions and states, plus the literal known-answer values of
+SURVEY.md section 8(c) recomputed from the reference's functions.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from mmwave_msc_b200 import synth  # noqa: E402
+from oracle import ref_harness as rh, trace_io  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# people walk in and out, clutter confined to a far corner: tracks time out and ids are re-issued
+CHURN = synth.SceneSpec(clutter_frac=0.02, leave_prob=0.5, enter_prob=0.5, clutter_box=(2.2, 2.5, 4.2, 4.5),
+                        people_min=2, people_max=4)
+
+# (name, scene_id, n_frames, spec, max_tracks)
+CASES = [
+    ("churn_s311", 311, 150, CHURN, None),
+    ("churn_s321", 321, 160, CHURN, None),
+    ("churn_s308", 308, 140, CHURN, None),
+    ("c1_s0", 0, 60, synth.SceneSpec(), None),
+    ("c1_s1", 1, 60, synth.SceneSpec(), None),
+    ("c1_s4", 4, 60, synth.SceneSpec(), None),
+    ("c1_s5", 5, 60, synth.SceneSpec(), None),
+    ("c1_s11", 11, 140, synth.SceneSpec(), None),
+    ("c1_s100_long", 100, 200, synth.SceneSpec(), None),
+    ("c1_s21_jitter", 21, 40, synth.SceneSpec(jitter_lattice=True), None),
+    ("c3_s7_dense", 7, 16, synth.SceneSpec.dense(), 10),
+]
+
+
+def known_answers() -> dict:
+    const, utils, tracking = rh.load_reference()
+    ka = {}
+    ka["altered_dist"] = float(utils.altered_EuclideanDist([0.1, 2.0, 1.0], [0.4, 2.5, 0.2]))
+    ka["transform"] = utils.point_transform_to_standard_axis(np.array([0.5, 3.0, -0.4, 0.1, 0.6, -0.08])).tolist()
+    ka["normalize"] = utils.normalize_data({"x": [.5, 1, 0], "y": [3, -1, 0], "z": [-.4, 0, 0],
+                                            "doppler": [.62, .1, .3], "peakVal": [120, 5, 7]}).tolist()
+    k = tracking.KalmanState(np.zeros(6))
+    k.predict(F=const.MOTION_MODEL.KF_F(0.1), Q=const.MOTION_MODEL.KF_Q_DISCR(0.1))
+    ka["predict_diagP_dt0.1"] = np.diag(k.P).tolist()
+    ka["Q_dt1"] = const.MOTION_MODEL.KF_Q_DISCR(1).tolist()
+    ka["F_dt0.25"] = const.MOTION_MODEL.KF_F(0.25).tolist()
+    ka["default_posture"] = np.asarray(const.MODEL_DEFAULT_POSTURE).tolist()
+    ka["constants"] = {n: getattr(const, n) for n in (
+        "S_HEIGHT", "S_TILT", "FB_FRAMES_BATCH", "DB_Z_WEIGHT", "DB_RANGE_WEIGHT", "DB_EPS", "DB_MIN_SAMPLES_MIN",
+        "TR_MAX_TRACKS", "TR_LIFETIME_DYNAMIC", "TR_LIFETIME_STATIC", "TR_VEL_THRES", "TR_GATE", "KF_R_STD",
+        "KF_Q_STD", "KF_P_INIT", "KF_GROUP_DISP_EST_INIT", "KF_ENABLE_EST", "KF_A_N", "KF_EST_POINTNUM",
+        "KF_SPREAD_LIM", "KF_A_SPR", "INTENSITY_MU", "INTENSITY_STD", "MODEL_MIN_INPUT")}
+    return ka
+
+
+def balltree_deviation(n_scenes: int = 24, n_frames: int = 30) -> dict:
+    """How often the shipped sklearn 'auto' (BallTree) labels differ from exact neighbourhoods."""
+    diff_calls = calls = diff_scenes = 0
+    for sid in range(200, 200 + n_scenes):
+        sc = synth.gen_scene(sid, n_frames)
+        a = rh.run_reference_scene(sc.frames, sc.dts(), dbscan_algorithm="auto")
+        b = rh.run_reference_scene(sc.frames, sc.dts(), dbscan_algorithm="brute")
+        sd = False
+        for ra, rb in zip(a, b):
+            if ra["labels"] is None or rb["labels"] is None:
+                sd |= (ra["labels"] is None) != (rb["labels"] is None)
+                continue
+            calls += 1
+            if len(ra["labels"]) != len(rb["labels"]) or not np.array_equal(ra["labels"], rb["labels"]):
+                diff_calls += 1
+                sd = True
+        same_end = ([t["id"] for t in a[-1]["tracks"]] == [t["id"] for t in b[-1]["tracks"]])
+        diff_scenes += int(sd or not same_end)
+    return {"scenes": n_scenes, "frames": n_frames, "dbscan_calls": calls, "calls_with_different_labels": diff_calls,
+            "scenes_with_any_difference": diff_scenes}
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    json.dump(known_answers(), open(os.path.join(GOLDEN, "known_answers.json"), "w"), indent=1)
+    for name, sid, nf, spec, mt in CASES:
+        sc = synth.gen_scene(sid, nf, spec)
+        recs = rh.run_reference_scene(sc.frames, sc.dts(), pose_fn=lambda x: np.zeros((len(x), 57)), max_tracks=mt)
+        d = trace_io.pack(sc.frames, sc.dts(), recs)
+        d["max_tracks"] = np.array(4 if mt is None else mt, np.int32)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **d)
+        print(name, "frames", nf, "tracks at end", len(recs[-1]["tracks"]), "next id", recs[-1]["next_track_id"],
+              "dbscan runs", int(d["labels_ran"].sum()))
+    if "--deviation" in sys.argv:
+        dev = balltree_deviation()
+        json.dump(dev, open(os.path.join(GOLDEN, "balltree_deviation.json"), "w"), indent=1)
+        print(dev)
+
+
+if __name__ == "__main__":
+    main()

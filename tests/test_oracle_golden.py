@@ -1,0 +1,106 @@
+"""The numpy oracle against (a) the known-answer values recomputed from the reference's
+own functions and (b) the golden traces recorded from the reference's own Tracking.py /
+Utils.py (oracle/gen_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+from oracle import mmw_oracle as mo, trace_io
+
+KA = json.load(open(os.path.join(GOLDEN, "known_answers.json")))
+FLOAT_TOL = 1e-9     # oracle vs reference, both float64: summation-order noise only
+
+
+def test_constants_match_reference():
+    c, cfg = KA["constants"], mo.OracleConfig()
+    assert (c["S_HEIGHT"], c["S_TILT"]) == (cfg.s_height, cfg.s_tilt_deg)
+    assert c["FB_FRAMES_BATCH"] == cfg.frames_batch
+    assert (c["DB_Z_WEIGHT"], c["DB_RANGE_WEIGHT"], c["DB_EPS"], c["DB_MIN_SAMPLES_MIN"]) == \
+        (cfg.db_z_weight, cfg.db_range_weight, cfg.db_eps, cfg.db_min_samples)
+    assert (c["TR_MAX_TRACKS"], c["TR_LIFETIME_DYNAMIC"], c["TR_LIFETIME_STATIC"], c["TR_VEL_THRES"], c["TR_GATE"]) == \
+        (cfg.tr_max_tracks, cfg.tr_lifetime_dynamic, cfg.tr_lifetime_static, cfg.tr_vel_thres, cfg.tr_gate)
+    assert (c["KF_Q_STD"], c["KF_P_INIT"], c["KF_GROUP_DISP_EST_INIT"], c["KF_ENABLE_EST"], c["KF_A_N"],
+            c["KF_EST_POINTNUM"], c["KF_A_SPR"]) == \
+        (cfg.kf_q_var, cfg.kf_p_init, cfg.kf_group_disp_init, cfg.kf_enable_est, cfg.kf_a_n, cfg.kf_est_pointnum,
+         cfg.kf_a_spr)
+    assert list(c["KF_SPREAD_LIM"]) == list(cfg.kf_spread_lim)
+    assert (c["INTENSITY_MU"], c["INTENSITY_STD"]) == (cfg.intensity_mu, cfg.intensity_std)
+    np.testing.assert_array_equal(KA["default_posture"], mo.MODEL_DEFAULT_POSTURE)
+
+
+def test_known_answers():
+    d = mo.pair_distance_matrix(np.array([[0.1, 2.0, 1.0], [0.4, 2.5, 0.2]]))
+    assert d[0, 1] == KA["altered_dist"] == d[1, 0]
+    world, keep = mo.normalize_points(np.array([[.5, 3, -.4, .62, 120], [1, -1, 0, .1, 5], [0, 0, 0, .3, 7]]))
+    assert keep.tolist() == [True, False, False]
+    np.testing.assert_allclose(world, np.array(KA["normalize"]), rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(mo.kf_Q(1.0), np.array(KA["Q_dt1"]))
+    np.testing.assert_array_equal(mo.kf_F(0.25), np.array(KA["F_dt0.25"]))
+    P = (mo.kf_F(0.1) @ (np.eye(9) * 0.1)) @ mo.kf_F(0.1).T + mo.kf_Q(0.1)
+    np.testing.assert_allclose(np.diag(P), KA["predict_diagP_dt0.1"], rtol=1e-15)
+
+
+def _run_oracle(g, max_tracks):
+    so = mo.SceneOracle(mo.OracleConfig(tr_max_tracks=max_tracks))
+    return [so.step(fr, dt) for fr, dt in zip(g["frames"], g["dts"])]
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_oracle_reproduces_reference_trace(case):
+    d = np.load(os.path.join(GOLDEN, case + ".npz"))
+    g = trace_io.unpack(d)
+    ora = _run_oracle(g, int(d["max_tracks"]))
+    for f, (a, b) in enumerate(zip(g["recs"], ora)):
+        ctx = "%s frame %d" % (case, f)
+        # decisions: bit-exact
+        assert a["M"] == b["M"], ctx
+        np.testing.assert_array_equal(a["assoc"], b["assoc"], err_msg=ctx)
+        assert (a["labels"] is None) == (b["labels"] is None), ctx
+        if a["labels"] is not None:
+            np.testing.assert_array_equal(a["labels"], b["labels"], err_msg=ctx)
+        np.testing.assert_array_equal(a["ring_counts"], b["ring_counts"][-len(a["ring_counts"]):] if len(
+            a["ring_counts"]) else b["ring_counts"], err_msg=ctx)
+        assert a["next_track_id"] == b["next_track_id"], ctx
+        assert [t["id"] for t in a["tracks"]] == [t["id"] for t in b["tracks"]], ctx
+        for ta, tb in zip(a["tracks"], b["tracks"]):
+            assert ta["lifetime"] == tb["lifetime"] and ta["N_est"] == tb["N_est"], ctx
+            assert ta["point_num"] == tb["point_num"] and ta["static"] == tb["static"], ctx
+            np.testing.assert_array_equal(ta["ring_counts"], tb["ring_counts"], err_msg=ctx)
+            for k in ("x", "P", "spread_est", "group_disp_est", "centroid", "min_vals", "max_vals"):
+                np.testing.assert_allclose(ta[k], tb[k], rtol=FLOAT_TOL, atol=FLOAT_TOL, err_msg=ctx + " " + k)
+        if a["features"] is not None:
+            np.testing.assert_allclose(a["features"], b["features"], rtol=0, atol=1e-12, err_msg=ctx)
+
+
+def test_dbscan_semantics_small():
+    """Border point reachable from two clusters takes the lower label; noise = -1; self counts."""
+    cfg = mo.OracleConfig(db_min_samples=4, db_eps=0.05)      # y = 0 -> weight 1, radius sqrt(.05) = 0.2236
+    pts = np.zeros((10, 8))
+    # index 0: border point between two 4-point groups (neighbourhood = itself + one core of each group = 3 < 4)
+    pts[:, 0] = [0.35, 0.0, 0.05, 0.1, 0.15, 0.55, 0.6, 0.65, 0.7, 5.0]
+    lab = mo.dbscan_labels(pts, cfg)
+    assert lab.tolist() == [0, 0, 0, 0, 0, 1, 1, 1, 1, -1]
+    # same cloud, groups swapped in index order: the border now goes to the group that is numbered first
+    pts[:, 0] = [0.35, 0.55, 0.6, 0.65, 0.7, 0.0, 0.05, 0.1, 0.15, 5.0]
+    assert mo.dbscan_labels(pts, cfg).tolist() == [0, 0, 0, 0, 0, 1, 1, 1, 1, -1]
+    # empty and singleton inputs
+    assert mo.dbscan_labels(np.zeros((0, 8)), cfg).shape == (0,)
+    assert mo.dbscan_labels(np.zeros((1, 8)), cfg).tolist() == [-1]
+
+
+def test_features_layout():
+    cfg = mo.OracleConfig()
+    cloud = np.zeros((70, 8))
+    cloud[:, 0] = np.linspace(1, -1, 70)
+    cloud[:, 7] = 100
+    tr = mo.Track(cloud, 0, cfg)
+    f = mo.pose_features(tr, cfg)
+    assert f.shape == (3, 8, 8, 5)
+    assert np.all(f[1:] == 0)                                  # absent ring frames stay zero (Utils.py:493)
+    x = f[0].reshape(64, 5)[:, 0]
+    assert np.all(np.diff(x) >= 0) and len(x) == 64            # cut to the first 64, sorted by x
+    f0 = mo.pose_features(tr, mo.OracleConfig(frames_batch=0))
+    assert f0.shape == (8, 8, 5)
