@@ -1,0 +1,238 @@
+/*
+ * mmw.h -- C ABI of libmmw.so: the B200-native (sm_100a) implementation of the per-frame
+ * radar perception path of AsteriosPar/mmWave_MSc, batched over S independent scenes.
+ *
+ * The reference has no FFI: its boundary for this path is the Python module API of
+ * src/Utils.py and src/Tracking.py.  Every entry point below names the reference
+ * interface it replaces (paths relative to the reference's src/).  The Python host layer
+ * in mmwave_msc_b200/ binds these with ctypes (mmwave_msc_b200/_lib.py) and mirrors the
+ * reference's names on top (mmwave_msc_b200/Tracking.py, Utils.py).
+ *
+ * Conventions: extern "C"; plain pointers and sizes; no exceptions cross the boundary;
+ * every function returns MMW_OK (0) or a negative mmw_status; mmw_last_error() gives the
+ * message of the last failure on the calling thread.  The caller owns every buffer it
+ * passes in; the context owns all device memory and one CUDA stream.  A context is not
+ * thread-safe; distinct contexts are independent.  There is no CPU fallback: without a
+ * CUDA device mmw_create fails with MMW_ERR_CUDA.
+ */
+#ifndef MMW_H
+#define MMW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMW_ABI_VERSION 1
+
+typedef enum mmw_status {
+    MMW_OK = 0,
+    MMW_ERR_INVALID = -1,      /* bad argument / configuration */
+    MMW_ERR_CUDA = -2,         /* CUDA runtime error (message in mmw_last_error) */
+    MMW_ERR_CAPACITY = -3,     /* batch larger than the capacity given to mmw_create */
+    MMW_ERR_STATE = -4         /* call order (e.g. pose requested before weights were loaded) */
+} mmw_status;
+
+/* Mirror of the reference's constants.py (file:line = constants.py). */
+typedef struct mmw_config {
+    double s_height;               /* S_HEIGHT :41 */
+    double s_tilt_deg;             /* S_TILT :42 */
+    double z_max;                  /* scene bound on z', Utils.py:424 (2.5) */
+    int32_t frames_batch;          /* FB_FRAMES_BATCH :66; rings hold frames_batch+1 frames (1..3) */
+    int32_t db_min_samples;        /* DB_MIN_SAMPLES_MIN :73 */
+    double db_z_weight;            /* DB_Z_WEIGHT :70 */
+    double db_range_weight;        /* DB_RANGE_WEIGHT :71 */
+    double db_eps;                 /* DB_EPS :72 */
+    int32_t tr_max_tracks;         /* TR_MAX_TRACKS :85 (only gates whether DBSCAN runs, Tracking.py:693-696) */
+    int32_t kf_enable_est;         /* KF_ENABLE_EST :100 */
+    double tr_lifetime_dynamic;    /* TR_LIFETIME_DYNAMIC :86 [s] */
+    double tr_lifetime_static;     /* TR_LIFETIME_STATIC :87 [s] */
+    double tr_vel_thres;           /* TR_VEL_THRES :88 */
+    double tr_gate;                /* TR_GATE :89 */
+    double kf_q_var;               /* KF_Q_STD :93, passed as a variance (:212) */
+    double kf_p_init;              /* KF_P_INIT :96 */
+    double kf_group_disp_init;     /* KF_GROUP_DISP_EST_INIT :97 */
+    double kf_a_n;                 /* KF_A_N :101 */
+    double kf_a_spr;               /* KF_A_SPR :104 */
+    double kf_spread_lim[6];       /* KF_SPREAD_LIM :103 */
+    int32_t kf_est_pointnum;       /* KF_EST_POINTNUM :102 */
+    int32_t reserved0;
+    double intensity_mu;           /* INTENSITY_MU :108 */
+    double intensity_std;          /* INTENSITY_STD :109 */
+    double x_nudge_thres;          /* 0.6, Tracking.py:397 */
+    double x_nudge_gain;           /* 0.4, Tracking.py:398 */
+    float default_posture[57];     /* MODEL_DEFAULT_POSTURE :112-172 */
+    float reserved1;
+} mmw_config;
+
+/* Fills *cfg with the reference's default constants. */
+int mmw_default_config(mmw_config* cfg);
+
+typedef struct mmw_ctx mmw_ctx;
+
+/* Pose network variants (train.py). */
+#define MMW_POSE_2D 0   /* define_CNN    train.py:33-68  : (8,8,5)   -> 57, used when frames_batch == 0 */
+#define MMW_POSE_3D 1   /* define_CNN_3D train.py:71-106 : (3,8,8,5) -> 57, used when frames_batch == 2 */
+
+/* mmw_step flags */
+#define MMW_STEP_POSE          0x1u   /* run estimate_posture after track (offline_main.py:60) */
+#define MMW_STEP_DEVICE_INPUT  0x2u   /* pts/offsets/dt are device pointers (already resident in HBM) */
+#define MMW_STEP_RECORD_LABELS 0x4u   /* keep the DBSCAN labels of this frame for mmw_get_labels */
+
+/* per-scene status bits (mmw_get_status) */
+#define MMW_SCENE_POINT_OVERFLOW 0x1u /* a frame had more points than max_points_per_frame (extra points dropped) */
+#define MMW_SCENE_TRACK_OVERFLOW 0x2u /* more tracks than the max_tracks capacity (extra clusters dropped) */
+
+/*
+ * One context = S independent scenes, each the state that offline_main.py:32-34 creates
+ * (TrackBuffer() + the global BatchedData() ring), resident on one GPU.
+ *   max_points_per_frame : capacity N_cap of one frame of one scene (e.g. 256; 1024 for the dense cfg)
+ *   max_tracks           : capacity T_cap of one scene's effective_tracks list (1..32).  The reference can
+ *                          exceed TR_MAX_TRACKS (Tracking.py:585-589, 703), so T_cap should be > tr_max_tracks.
+ */
+int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points_per_frame, int max_tracks,
+               mmw_ctx** out);
+int mmw_destroy(mmw_ctx* ctx);
+const char* mmw_last_error(void);
+int mmw_abi_version(void);
+
+/* Resets every scene to the state of a fresh TrackBuffer() + BatchedData() (Tracking.py:504-511, 38-41). */
+int mmw_reset(mmw_ctx* ctx);
+
+/*
+ * Loads the keypoint regressor's weights (replaces keras load_model, offline_main.py:33).
+ * blob = concatenation of Keras model.get_weights() flattened, fp32 (see mmwave_msc_b200/pose_weights.py).
+ */
+int mmw_load_pose_weights(mmw_ctx* ctx, int variant, const float* blob, size_t n_floats);
+
+/*
+ * One radar frame for every scene: the loop body of offline_main.py:45-60 --
+ *   Utils.normalize_data (Utils.py:342-434), TrackBuffer.track (Tracking.py:664-703) and, with
+ *   MMW_STEP_POSE, TrackBuffer.estimate_posture (Tracking.py:705-734).
+ *   pts     [sum N, 5] fp32 rows x, y, z, doppler, peakVal in the sensor frame (detObj of ReadDataIWR1443.py)
+ *   offsets [S+1]      int32 row offsets of each scene's points (ragged batch)
+ *   dt      [S]        fp64 seconds since the scene's previous frame (trackbuffer.dt, offline_main.py:45-49)
+ * Scenes whose frame is empty after the scene-bounds filter are skipped entirely, as offline_main.py:55 does.
+ * Asynchronous on the context's stream unless the inputs are pageable host memory.
+ */
+int mmw_step(mmw_ctx* ctx, const float* pts, const int32_t* offsets, const double* dt, uint32_t flags);
+
+/* Blocks until all work queued on the context's stream has finished. */
+int mmw_sync(mmw_ctx* ctx);
+/* The context's cudaStream_t (so a host framework can time it with events / order copies after it). */
+void* mmw_stream(mmw_ctx* ctx);
+
+/* One element of effective_tracks (Tracking.py ClusterTrack/KalmanState/PointCluster attributes). */
+typedef struct mmw_track_out {
+    int32_t id;                /* value of next_track_id when the track was spawned (Tracking.py:587-588) */
+    int32_t point_num;         /* cluster.point_num of the last associated cloud */
+    int32_t is_static;         /* cluster.status == STATIC (Tracking.py:132-136) */
+    int32_t ring_frames;       /* len(track.batch.buffer) */
+    int32_t ring_counts[3];    /* points kept per ring frame, oldest first (at most 64 each are stored) */
+    int32_t reserved;
+    double lifetime;           /* seconds since the last association (Tracking.py:400-407) */
+    double n_est;              /* N_est */
+    double x[9];               /* state.x */
+    double P[81];              /* state.P row-major */
+    double spread_est[6];
+    double group_disp_est[36];
+    double centroid[6];
+    double min_vals[6];
+    double max_vals[6];
+    float keypoints[57];       /* [x0..x18 | y0..y18 | z0..z18] (train.py:169-177) */
+    float reserved2;
+} mmw_track_out;
+
+/*
+ * Readback (host buffers).  tracks: [S * max_tracks] entries, scene s at tracks[s*max_tracks ..], in
+ * effective_tracks list order; n_tracks: [S].  Either pointer may be NULL.
+ */
+int mmw_get_tracks(mmw_ctx* ctx, mmw_track_out* tracks, int32_t* n_tracks);
+
+/* Compact per-scene summary for the hot loop's result read: n_tracks [S], next_track_id [S],
+ * M (points that survived the scene-bounds filter in the last frame) [S].  Any pointer may be NULL. */
+int mmw_get_scene_summary(mmw_ctx* ctx, int32_t* n_tracks, int32_t* next_track_id, int32_t* last_M);
+
+/* Per-point association of the last frame, the return value of TrackBuffer._calc_dist_fun
+ * (Tracking.py:530-574): assoc[offsets[s] + m] for m < M_s is the index in the pre-maintenance track list,
+ * -1 = unassigned (None).  Entries m >= M_s are -2.  assoc: [sum N] int32. */
+int mmw_get_point_assoc(mmw_ctx* ctx, int32_t* assoc, size_t n);
+
+/* DBSCAN labels of the last frame stepped with MMW_STEP_RECORD_LABELS: labels [S * 3 * max_points] int32
+ * (scene s at s*3*max_points, fused ring order oldest frame first, -1 noise); n_fused [S] = number of fused
+ * points clustered, or -1 when DBSCAN did not run for that scene (Tracking.py:693-697). */
+int mmw_get_labels(mmw_ctx* ctx, int32_t* labels, int32_t* n_fused);
+
+/* Per-scene overflow bits since creation/reset. */
+int mmw_get_status(mmw_ctx* ctx, uint32_t* flags);
+
+/* Sizes of the global unassigned ring (batch.buffer of offline_main.py:34): counts [S*3] oldest first,
+ * -1 for absent frames. */
+int mmw_get_ring_counts(mmw_ctx* ctx, int32_t* counts);
+
+/* BatchedData.pop_frame / clear on the global ring of one scene (preprocessing.py:263-264, Tracking.py:53-71). */
+int mmw_ring_pop(mmw_ctx* ctx, int scene);
+int mmw_ring_clear(mmw_ctx* ctx, int scene);
+
+/* Pose input/output of the last MMW_STEP_POSE frame: number of track rows, their (scene, list index) and the
+ * feature maps handed to the network, fp32 [(frames_batch+1) * 64 * 5] per row (format_single_frame,
+ * Utils.py:468-520).  feats/scene_idx/track_idx may be NULL; *n_rows is always written. */
+int mmw_get_pose_rows(mmw_ctx* ctx, int32_t* n_rows, int32_t* scene_idx, int32_t* track_idx, float* feats,
+                      size_t feats_capacity_floats);
+
+/* ---- stage-level entry points (stateless; host buffers; used by the known-answer tests) ---- */
+
+/* Utils.normalize_data (Utils.py:342-434) on a ragged batch: world [sum N, 8] fp64 rows
+ * x,y,z,vx,vy,vz,doppler,peakVal for every input point and keep [sum N] (1 = inside the scene bounds). */
+int mmw_preprocess(mmw_ctx* ctx, const float* pts, size_t n_points, double* world, uint8_t* keep);
+
+/* Utils.apply_DBscan (Utils.py:250-291) with exact epsilon-neighbourhoods on a ragged batch of clouds:
+ * xyz [sum B, 3] fp64, offsets [C+1]; labels [sum B] int32 with sklearn's numbering (-1 noise).
+ * Each cloud may have at most 3*max_points points.  eps <= 0 / min_samples <= 0 select the config values. */
+int mmw_dbscan(mmw_ctx* ctx, const double* xyz, const int32_t* offsets, int n_clouds, double eps, int min_samples,
+               int32_t* labels);
+
+/* filterpy KalmanFilter.predict as ClusterTrack.predict_state calls it (Tracking.py:372-385):
+ * x [n,9], P [n,81] updated in place with F(dt[i]), Q(dt[i]) of constants.py:195-215. */
+int mmw_kalman_predict(mmw_ctx* ctx, double* x, double* P, const double* dt, int n);
+
+/* filterpy KalmanFilter.update (Joseph form) as ClusterTrack.update_state calls it (Tracking.py:387-398),
+ * including the x[0] nudge: z [n,6], R [n,36], lifetime_is_zero [n]; x, P updated in place. */
+int mmw_kalman_update(mmw_ctx* ctx, double* x, double* P, const double* z, const double* R,
+                      const uint8_t* lifetime_is_zero, int n);
+
+/* Gate scores of TrackBuffer._calc_dist_fun (Tracking.py:545-572) for one scene: points [M,6] fp64,
+ * tracks given by hx [T,6] and C [T,36]; d2 [M,T] fp64 and assoc [M] int32 out. */
+int mmw_gate(mmw_ctx* ctx, const double* points, int M, const double* hx, const double* C, int T, double* d2,
+             int32_t* assoc);
+
+/* Keras model.predict (Tracking.py:732): feats [n, (frames_batch+1)*64*5] fp32 -> keypoints [n,57] fp32. */
+int mmw_pose(mmw_ctx* ctx, const float* feats, int n, float* keypoints);
+
+/* ---- device-side views for a host framework that owns the stream (bench / torch.distributed gather) ---- */
+
+/* Packs the per-scene results of the last frame into a caller-provided DEVICE buffer of
+ * S * max_tracks * MMW_RESULT_FLOATS fp32 (id, n_tracks, x[9], keypoints[57]), ready to be
+ * all-gathered across ranks.  Asynchronous on the context's stream. */
+#define MMW_RESULT_FLOATS 68
+int mmw_pack_results(mmw_ctx* ctx, float* device_out);
+
+/* Counters accumulated on the device since the last call (algorithmic-bytes bookkeeping):
+ * out[0]=frames stepped (scene-frames that ran), [1]=sum N, [2]=sum M, [3]=sum U (unassigned pushed),
+ * [4]=sum fused points clustered, [5]=sum tracks after the frame, [6]=sum min(A_j,64) ring rows written,
+ * [7]=pose rows. */
+int mmw_get_counters(mmw_ctx* ctx, uint64_t out[8], int reset);
+
+/* Selects the kernel used for the pose network's dense contraction: 1 = tcgen05 tensor-core path (default),
+ * 0 = CUDA-core fp32 path (kept for numerics comparison). */
+int mmw_set_dense_path(mmw_ctx* ctx, int use_tensor_cores);
+
+/* Number of kernels this library launched since creation (bench.py's gpu_launches). */
+uint64_t mmw_launch_count(mmw_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMW_H */

@@ -1,0 +1,188 @@
+// Warp-cooperative float64 linear algebra for the 6x6 / 9x9 tracker matrices.
+// One warp owns one track; matrices live in shared memory, lanes split the elements.
+#pragma once
+#include "mmw_internal.cuh"
+
+namespace mmw {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// Per-warp scratch (doubles): aug 72 | A 36 | B 36 | K 54 | M1 81 | M2 81 | v 16
+constexpr int kWsAug = 0, kWsA = 72, kWsB = 108, kWsK = 144, kWsM1 = 198, kWsM2 = 279, kWsV = 360;
+constexpr int kWarpScratch = 376;
+
+// Inverse and determinant of a 6x6 row-major matrix by Gauss-Jordan elimination with partial
+// pivoting (numpy.linalg.inv / det are LU with partial pivoting: Tracking.py:558-559, filterpy update).
+// A, Ainv: 36 doubles in shared memory (may not alias); aug: 72 doubles scratch.  Returns det(A).
+__device__ __forceinline__ double warp_inv6(const double* A, double* Ainv, double* aug, int lane) {
+    for (int e = lane; e < 72; e += 32) {
+        const int r = e / 12, c = e % 12;
+        aug[e] = c < 6 ? A[r * 6 + c] : (c - 6 == r ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    double det = 1.0;
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k) {
+        int p = k;
+        double best = fabs(aug[k * 12 + k]);
+        for (int r = k + 1; r < 6; ++r) {
+            const double v = fabs(aug[r * 12 + k]);
+            if (v > best) { best = v; p = r; }
+        }
+        if (p != k) {
+            if (lane < 12) {
+                const double a = aug[k * 12 + lane], b = aug[p * 12 + lane];
+                aug[k * 12 + lane] = b;
+                aug[p * 12 + lane] = a;
+            }
+            det = -det;
+        }
+        __syncwarp();
+        const double piv = aug[k * 12 + k];
+        det *= piv;
+        __syncwarp();
+        if (lane < 12) aug[k * 12 + lane] = aug[k * 12 + lane] / piv;
+        __syncwarp();
+        double nv[2];
+        int ne[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int idx = lane + 32 * t;
+            ne[t] = -1;
+            if (idx < 60) {
+                const int rr = idx / 12, c = idx % 12;
+                const int r = rr < k ? rr : rr + 1;
+                ne[t] = r * 12 + c;
+                nv[t] = aug[r * 12 + c] - aug[r * 12 + k] * aug[k * 12 + c];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+            if (ne[t] >= 0) aug[ne[t]] = nv[t];
+        __syncwarp();
+    }
+    for (int e = lane; e < 36; e += 32) Ainv[e] = aug[(e / 6) * 12 + 6 + (e % 6)];
+    __syncwarp();
+    return det;
+}
+
+// filterpy KalmanFilter.predict with F = KF_F(dt), Q = KF_Q_DISCR(dt) (constants.py:195-215):
+//   x = F x ;  P = (F P) F' + Q.  x: 9, P: 81 in shared memory; tmp: 81 doubles scratch.
+__device__ __forceinline__ void warp_kf_predict(double* x, double* P, double dt, double q_var, double* tmp,
+                                                int lane) {
+    const double h = 0.5 * (dt * dt);
+    double nx = 0.0;
+    if (lane < 9) {
+        nx = x[lane];
+        if (lane < 6) nx += dt * x[lane + 3];
+        if (lane < 3) nx += h * x[lane + 6];
+    }
+    for (int e = lane; e < 81; e += 32) {
+        const int i = e / 9, j = e % 9;
+        double v = P[e];
+        if (i < 6) v += dt * P[(i + 3) * 9 + j];
+        if (i < 3) v += h * P[(i + 6) * 9 + j];
+        tmp[e] = v;
+    }
+    __syncwarp();
+    if (lane < 9) x[lane] = nx;
+    const double dt2 = dt * dt, dt3 = dt2 * dt, dt4 = dt2 * dt2;
+    for (int e = lane; e < 81; e += 32) {
+        const int i = e / 9, j = e % 9;
+        double v = tmp[e];
+        if (j < 6) v += dt * tmp[i * 9 + j + 3];
+        if (j < 3) v += h * tmp[i * 9 + j + 6];
+        if (i / 3 == j / 3) {   // block_diag(Qw, Qw, Qw): blocks on state indices (0-2), (3-5), (6-8)  (Q10)
+            const int a = i % 3, b = j % 3, s = a + b;   // Qw[a][b] depends on a+b only
+            double qv;
+            if (s == 0) qv = 0.25 * dt4;
+            else if (s == 1) qv = 0.5 * dt3;
+            else if (s == 2) qv = (a == 1) ? dt2 : 0.5 * dt2;
+            else if (s == 3) qv = dt;
+            else qv = 1.0;
+            v += qv * q_var;
+        }
+        P[e] = v;
+    }
+    __syncwarp();
+}
+
+// filterpy KalmanFilter.update, Joseph form, H = [I6 0] (Tracking.py:387-393):
+//   y = z - x[:6]; S = P[:6,:6] + R; K = P[:, :6] S^-1; x += K y;
+//   P = (I-KH) P (I-KH)' + (K R) K'
+// then the x[0] nudge of Tracking.py:396-398 when `nudge` is set.
+// R: 36 doubles (shared).  ws: per-warp scratch of kWarpScratch doubles.
+__device__ __forceinline__ void warp_kf_update(double* x, double* P, const double* z, const double* R, bool nudge,
+                                               double nudge_thres, double nudge_gain, double* ws, int lane) {
+    double* S = ws + kWsA;
+    double* SI = ws + kWsB;
+    double* K = ws + kWsK;
+    double* M1 = ws + kWsM1;
+    double* M2 = ws + kWsM2;
+    double* v = ws + kWsV;
+    for (int e = lane; e < 36; e += 32) S[e] = P[(e / 6) * 9 + (e % 6)] + R[e];
+    if (lane < 6) v[lane] = z[lane] - x[lane];
+    __syncwarp();
+    warp_inv6(S, SI, ws + kWsAug, lane);
+    // K = P[:, :6] SI   (9x6)
+    for (int e = lane; e < 54; e += 32) {
+        const int i = e / 6, a = e % 6;
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) acc += P[i * 9 + b] * SI[b * 6 + a];
+        K[e] = acc;
+    }
+    __syncwarp();
+    // x += K y
+    if (lane < 9) {
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc += K[lane * 6 + a] * v[a];
+        x[lane] += acc;
+    }
+    // M1 = (I - K H) P : row i = P[i,:] - sum_{a<6} K[i][a] P[a,:]
+    for (int e = lane; e < 81; e += 32) {
+        const int i = e / 9, j = e % 9;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const double ikh = (k == i ? 1.0 : 0.0) - (k < 6 ? K[i * 6 + k] : 0.0);
+            acc += ikh * P[k * 9 + j];
+        }
+        M1[e] = acc;
+    }
+    // M2 = K R  (9x6) stored with stride 9 in M2[i*9 + a]
+    for (int e = lane; e < 54; e += 32) {
+        const int i = e / 6, a = e % 6;
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) acc += K[i * 6 + b] * R[b * 6 + a];
+        M2[i * 9 + a] = acc;
+    }
+    __syncwarp();
+    // P = M1 (I-KH)' + M2 K'
+    for (int e = lane; e < 81; e += 32) {
+        const int i = e / 9, j = e % 9;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const double ikh = (k == j ? 1.0 : 0.0) - (k < 6 ? K[j * 6 + k] : 0.0);
+            acc += M1[i * 9 + k] * ikh;
+        }
+        double acc2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc2 += M2[i * 9 + a] * K[j * 6 + a];
+        P[e] = acc + acc2;
+    }
+    __syncwarp();
+    if (nudge && lane == 0) {
+        // `abs(variance.any()) > 0.6` is abs(bool) > 0.6, i.e. true iff z[0] != x[0]  (Q12)
+        const double var = z[0] - x[0];
+        const double truth = (var != 0.0) ? 1.0 : 0.0;
+        if (truth > nudge_thres) x[0] += var * nudge_gain;
+    }
+    __syncwarp();
+}
+
+}  // namespace mmw

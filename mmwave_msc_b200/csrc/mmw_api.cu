@@ -1,0 +1,807 @@
+// C ABI of libmmw.so (include/mmw.h): context management, the per-frame step, readback, and the
+// stage-level entry points.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dbscan.cuh"
+#include "linalg.cuh"
+#include "mmw_internal.cuh"
+#include "pose.cuh"
+#include "pose_tc.cuh"
+
+using namespace mmw;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(MMW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+struct mmw_ctx {
+    mmw_config cfg;
+    DevConfig dc;
+    int device = 0, S = 0, ncap = 0, tcap = 0;
+    cudaStream_t stream = nullptr;
+    // resident state
+    TrackRec* d_tracks = nullptr;
+    SceneRec* d_scenes = nullptr;
+    float* d_track_ring = nullptr;
+    float* d_uring = nullptr;
+    float* d_keypoints = nullptr;
+    float* d_default_posture = nullptr;
+    int32_t* d_assoc = nullptr;
+    int32_t* d_labels = nullptr;
+    unsigned long long* d_counters = nullptr;
+    // input staging (host-input path)
+    float* d_pts = nullptr;
+    int32_t* d_offsets = nullptr;
+    double* d_dt = nullptr;
+    size_t pts_cap_rows = 0;
+    std::vector<int32_t> h_offsets;
+    // pose
+    int variant = -1;
+    bool has_weights = false;
+    int D = 0, Kf = 0, H = 0;
+    float* d_blob = nullptr;
+    const float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr, *wd1 = nullptr, *bd1 = nullptr,
+                *wd2 = nullptr, *bd2 = nullptr;
+    float *d_bn1s = nullptr, *d_bn1t = nullptr, *d_bn2s = nullptr, *d_bn2t = nullptr;
+    float* d_feats = nullptr;
+    int32_t *d_row_scene = nullptr, *d_row_track = nullptr, *d_row_slot = nullptr;
+    int* d_pose_total = nullptr;
+    float *d_act2 = nullptr, *d_act3 = nullptr, *d_pose_out = nullptr;
+    int pose_cap = 0;
+    PoseTc tc;              // tensor-core dense path (pose_tc.cu)
+    bool use_tc = true;
+    uint64_t launches = 0;
+};
+
+static void fill_devconfig(const mmw_config& c, int ncap, int tcap, DevConfig* d) {
+    const double ang = c.s_tilt_deg * (M_PI / 180.0);      // numpy.radians
+    d->cos_t = std::cos(ang);
+    d->sin_t = std::sin(ang);
+    d->s_height = c.s_height;
+    d->z_max = c.z_max;
+    d->db_z_weight = c.db_z_weight;
+    d->db_range_weight = c.db_range_weight;
+    d->db_eps = c.db_eps;
+    d->life_dyn = c.tr_lifetime_dynamic;
+    d->life_sta = c.tr_lifetime_static;
+    d->vel_thres = c.tr_vel_thres;
+    d->gate = c.tr_gate;
+    d->q_var = c.kf_q_var;
+    d->p_init = c.kf_p_init;
+    d->g_init = c.kf_group_disp_init;
+    d->a_n = c.kf_a_n;
+    d->a_spr = c.kf_a_spr;
+    for (int i = 0; i < 6; ++i) d->spread_lim[i] = c.kf_spread_lim[i];
+    d->int_mu = c.intensity_mu;
+    d->int_std = c.intensity_std;
+    d->nudge_thres = c.x_nudge_thres;
+    d->nudge_gain = c.x_nudge_gain;
+    d->db_min_samples = c.db_min_samples;
+    d->ring_size = c.frames_batch + 1;
+    d->tr_max_tracks = c.tr_max_tracks;
+    d->enable_est = c.kf_enable_est;
+    d->est_pointnum = c.kf_est_pointnum;
+    d->ncap = ncap;
+    d->tcap = tcap;
+}
+
+static const float kDefaultPosture[57] = {
+    0.0000f, -0.0007f, -0.0006f, -0.0038f, -0.1820f, -0.2540f, -0.2579f, 0.1830f, 0.2957f, 0.2940f,
+    -0.0805f, -0.1141f, -0.1232f, -0.1358f, 0.0796f, 0.1436f, 0.1558f, 0.1720f, -0.0007f, 0.7699f,
+    1.0906f, 1.4020f, 1.5513f, 1.2893f, 1.0360f, 0.7994f, 1.2865f, 1.0483f, 0.8117f, 0.7670f,
+    0.3428f, 0.0000f, -0.0746f, 0.7713f, 0.3706f, -0.0128f, -0.0796f, 1.3255f, 0.0752f, 0.0533f,
+    0.0203f, 0.0000f, 0.0496f, 0.1350f, 0.1303f, 0.0345f, 0.1277f, 0.1050f, 0.0392f, 0.0533f,
+    0.0786f, -0.0056f, 0.0346f, -0.0007f, 0.0683f, -0.0082f, 0.0312f};
+
+extern "C" {
+
+int mmw_abi_version(void) { return MMW_ABI_VERSION; }
+const char* mmw_last_error(void) { return g_err.c_str(); }
+
+int mmw_default_config(mmw_config* c) {
+    if (!c) return fail(MMW_ERR_INVALID, "cfg is NULL");
+    std::memset(c, 0, sizeof(*c));
+    c->s_height = 1.8; c->s_tilt_deg = -5; c->z_max = 2.5;
+    c->frames_batch = 2; c->db_min_samples = 35;
+    c->db_z_weight = 0.4; c->db_range_weight = 0.03; c->db_eps = 0.3;
+    c->tr_max_tracks = 4; c->kf_enable_est = 0;
+    c->tr_lifetime_dynamic = 3; c->tr_lifetime_static = 7; c->tr_vel_thres = 0.12; c->tr_gate = 4.5;
+    c->kf_q_var = 1; c->kf_p_init = 0.1; c->kf_group_disp_init = 0.1; c->kf_a_n = 0.9; c->kf_a_spr = 0.9;
+    const double lim[6] = {0.2, 0.2, 2, 1.2, 1.2, 0.2};
+    for (int i = 0; i < 6; ++i) c->kf_spread_lim[i] = lim[i];
+    c->kf_est_pointnum = 10;
+    c->intensity_mu = 27.0187; c->intensity_std = 70.351;
+    c->x_nudge_thres = 0.6; c->x_nudge_gain = 0.4;
+    std::memcpy(c->default_posture, kDefaultPosture, sizeof(kDefaultPosture));
+    return MMW_OK;
+}
+
+int mmw_destroy(mmw_ctx* x) {
+    if (!x) return MMW_OK;
+    cudaSetDevice(x->device);
+    if (x->stream) cudaStreamSynchronize(x->stream);
+    void* ptrs[] = {x->d_tracks, x->d_scenes, x->d_track_ring, x->d_uring, x->d_keypoints, x->d_default_posture,
+                    x->d_assoc, x->d_labels, x->d_counters, x->d_pts, x->d_offsets, x->d_dt, x->d_blob, x->d_bn1s,
+                    x->d_bn1t, x->d_bn2s, x->d_bn2t, x->d_feats, x->d_row_scene, x->d_row_track, x->d_row_slot,
+                    x->d_pose_total, x->d_act2, x->d_act3, x->d_pose_out};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    pose_tc_free(&x->tc);
+    if (x->stream) cudaStreamDestroy(x->stream);
+    delete x;
+    return MMW_OK;
+}
+
+int mmw_reset(mmw_ctx* x) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(x->device));
+    CK(cudaMemsetAsync(x->d_scenes, 0, sizeof(SceneRec) * x->S, x->stream));
+    CK(cudaMemsetAsync(x->d_tracks, 0, sizeof(TrackRec) * (size_t)x->S * x->tcap, x->stream));
+    CK(cudaMemsetAsync(x->d_counters, 0, sizeof(unsigned long long) * 8, x->stream));
+    CK(cudaMemsetAsync(x->d_assoc, 0xff, sizeof(int32_t) * (size_t)x->S * x->ncap, x->stream));
+    CK(cudaMemsetAsync(x->d_pose_total, 0, sizeof(int), x->stream));
+    return MMW_OK;
+}
+
+int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, int max_tracks, mmw_ctx** out) {
+    if (!cfg || !out) return fail(MMW_ERR_INVALID, "cfg/out is NULL");
+    if (n_scenes < 1 || max_points < 1 || max_tracks < 1 || max_tracks > kMaxTcap)
+        return fail(MMW_ERR_INVALID, "n_scenes >= 1, max_points >= 1, 1 <= max_tracks <= 32 required");
+    if (cfg->frames_batch < 0 || cfg->frames_batch > kRing - 1)
+        return fail(MMW_ERR_INVALID, "frames_batch must be 0..2");
+    if (cfg->db_min_samples < 1 || cfg->tr_max_tracks < 0)
+        return fail(MMW_ERR_INVALID, "db_min_samples >= 1 and tr_max_tracks >= 0 required");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(MMW_ERR_CUDA, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int smem = step_smem_bytes(max_points, max_tracks);
+    if ((size_t)smem > prop.sharedMemPerBlockOptin)
+        return fail(MMW_ERR_CAPACITY, "max_points/max_tracks need more shared memory than one CTA can have");
+    mmw_ctx* x = new (std::nothrow) mmw_ctx();
+    if (!x) return fail(MMW_ERR_INVALID, "out of host memory");
+    x->cfg = *cfg;
+    x->device = device; x->S = n_scenes; x->ncap = max_points; x->tcap = max_tracks;
+    fill_devconfig(*cfg, max_points, max_tracks, &x->dc);
+    const size_t S = n_scenes;
+#define ALLOC(p, bytes)                                                       \
+    do {                                                                      \
+        cudaError_t e__ = cudaMalloc((void**)&(p), (bytes));                  \
+        if (e__ != cudaSuccess) {                                             \
+            mmw_destroy(x);                                                   \
+            return fail(MMW_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e__)); \
+        }                                                                     \
+    } while (0)
+    if (cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete x;
+        return fail(MMW_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    ALLOC(x->d_tracks, sizeof(TrackRec) * S * max_tracks);
+    ALLOC(x->d_scenes, sizeof(SceneRec) * S);
+    ALLOC(x->d_track_ring, sizeof(float) * S * max_tracks * kRing * kFeatPts * kRawCols);
+    ALLOC(x->d_uring, sizeof(float) * S * kRing * max_points * kRawCols);
+    ALLOC(x->d_keypoints, sizeof(float) * S * max_tracks * kKp);
+    ALLOC(x->d_default_posture, sizeof(float) * kKp);
+    ALLOC(x->d_assoc, sizeof(int32_t) * S * max_points);
+    ALLOC(x->d_labels, sizeof(int32_t) * S * 3 * max_points);
+    ALLOC(x->d_counters, sizeof(unsigned long long) * 8);
+    ALLOC(x->d_offsets, sizeof(int32_t) * (S + 1));
+    ALLOC(x->d_dt, sizeof(double) * S);
+    ALLOC(x->d_pose_total, sizeof(int));
+    x->pose_cap = n_scenes * max_tracks;
+    ALLOC(x->d_row_scene, sizeof(int32_t) * x->pose_cap);
+    ALLOC(x->d_row_track, sizeof(int32_t) * x->pose_cap);
+    ALLOC(x->d_row_slot, sizeof(int32_t) * x->pose_cap);
+    ALLOC(x->d_feats, sizeof(float) * (size_t)x->pose_cap * kRing * kFeatPts * kRawCols);
+    ALLOC(x->d_pose_out, sizeof(float) * (size_t)x->pose_cap * kKp);
+#undef ALLOC
+    cudaMemcpy(x->d_default_posture, cfg->default_posture, sizeof(float) * kKp, cudaMemcpyHostToDevice);
+    cudaMemset(x->d_keypoints, 0, sizeof(float) * S * max_tracks * kKp);
+    int rc = mmw_reset(x);
+    if (rc != MMW_OK) { mmw_destroy(x); return rc; }
+    cudaStreamSynchronize(x->stream);
+    *out = x;
+    return MMW_OK;
+}
+
+int mmw_sync(mmw_ctx* x) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    return MMW_OK;
+}
+
+void* mmw_stream(mmw_ctx* x) { return x ? (void*)x->stream : nullptr; }
+uint64_t mmw_launch_count(mmw_ctx* x) { return x ? x->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+int mmw_load_pose_weights(mmw_ctx* x, int variant, const float* blob, size_t n) {
+    if (!x || !blob) return fail(MMW_ERR_INVALID, "ctx/blob is NULL");
+    if (variant != MMW_POSE_2D && variant != MMW_POSE_3D) return fail(MMW_ERR_INVALID, "unknown pose variant");
+    const int D = variant == MMW_POSE_3D ? 3 : 1;
+    if (D != x->dc.ring_size)
+        return fail(MMW_ERR_INVALID, "pose variant does not match frames_batch (2-D net needs frames_batch=0, "
+                                     "3-D net needs frames_batch=2; Utils.py:517-520)");
+    const int taps = D == 3 ? 27 : 9;
+    const int Kf = D * 64 * 32, H = D * 512;
+    const size_t sz[16] = {(size_t)taps * 5 * 16, 16, (size_t)taps * 16 * 32, 32, 32, 32, 32, 32,
+                           (size_t)Kf * H, (size_t)H, (size_t)H, (size_t)H, (size_t)H, (size_t)H,
+                           (size_t)H * kKp, (size_t)kKp};
+    size_t off[17];
+    off[0] = 0;
+    for (int i = 0; i < 16; ++i) off[i + 1] = off[i] + sz[i];
+    if (n != off[16]) return fail(MMW_ERR_INVALID, "weight blob has the wrong number of floats for this variant");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    if (x->d_blob) { cudaFree(x->d_blob); x->d_blob = nullptr; }
+    for (float** p : {&x->d_bn1s, &x->d_bn1t, &x->d_bn2s, &x->d_bn2t, &x->d_act2, &x->d_act3})
+        if (*p) { cudaFree(*p); *p = nullptr; }
+    CK(cudaMalloc((void**)&x->d_blob, sizeof(float) * n));
+    CK(cudaMemcpy(x->d_blob, blob, sizeof(float) * n, cudaMemcpyHostToDevice));
+    x->w1 = x->d_blob + off[0]; x->b1 = x->d_blob + off[1];
+    x->w2 = x->d_blob + off[2]; x->b2 = x->d_blob + off[3];
+    x->wd1 = x->d_blob + off[8]; x->bd1 = x->d_blob + off[9];
+    x->wd2 = x->d_blob + off[14]; x->bd2 = x->d_blob + off[15];
+    // BatchNorm at inference (Keras, eps = 1e-3): y = gamma (v - mean)/sqrt(var + eps) + beta = v*scale + shift
+    auto bn = [&](size_t g, int cnt, float** ds, float** dt) -> int {
+        std::vector<float> sc(cnt), sh(cnt);
+        for (int i = 0; i < cnt; ++i) {
+            const float gamma = blob[off[g] + i], beta = blob[off[g + 1] + i], mean = blob[off[g + 2] + i],
+                        var = blob[off[g + 3] + i];
+            const float s = gamma / std::sqrt(var + 1e-3f);
+            sc[i] = s;
+            sh[i] = beta - mean * s;
+        }
+        if (cudaMalloc((void**)ds, sizeof(float) * cnt) != cudaSuccess) return -1;
+        if (cudaMalloc((void**)dt, sizeof(float) * cnt) != cudaSuccess) return -1;
+        cudaMemcpy(*ds, sc.data(), sizeof(float) * cnt, cudaMemcpyHostToDevice);
+        cudaMemcpy(*dt, sh.data(), sizeof(float) * cnt, cudaMemcpyHostToDevice);
+        return 0;
+    };
+    if (bn(4, 32, &x->d_bn1s, &x->d_bn1t) || bn(10, H, &x->d_bn2s, &x->d_bn2t))
+        return fail(MMW_ERR_CUDA, "cudaMalloc failed for BatchNorm constants");
+    CK(cudaMalloc((void**)&x->d_act2, sizeof(float) * (size_t)x->pose_cap * Kf));
+    CK(cudaMalloc((void**)&x->d_act3, sizeof(float) * (size_t)x->pose_cap * H));
+    x->variant = variant; x->D = D; x->Kf = Kf; x->H = H;
+    int rc = pose_tc_init(&x->tc, blob + off[8], Kf, H, x->pose_cap, x->stream);
+    if (rc != 0) return fail(MMW_ERR_CUDA, std::string("tensor-core dense path init failed: ") + pose_tc_error());
+    x->has_weights = true;
+    return MMW_OK;
+}
+
+static int run_pose_net(mmw_ctx* x, float* keypoints_by_slot, int max_rows) {
+    ConvArgs ca{x->d_feats, x->w1, x->b1, x->w2, x->b2, x->d_bn1s, x->d_bn1t, x->d_act2, x->d_pose_total};
+    int grid = max_rows < 296 ? max_rows : 296;
+    CK(launch_conv(ca, x->D, grid, x->stream));
+    x->launches++;
+    FcArgs fa{x->d_act2, x->wd1, x->bd1, x->d_bn2s, x->d_bn2t, x->d_act3, x->d_pose_total, x->Kf, x->H};
+    if (x->use_tc && x->tc.ready) {
+        int nl = 0;
+        if (pose_tc_fc1(&x->tc, fa, max_rows, x->stream, &nl) != 0)
+            return fail(MMW_ERR_CUDA, std::string("tensor-core dense path: ") + pose_tc_error());
+        x->launches += nl;
+    } else {
+        CK(launch_fc1_simt(fa, max_rows, x->stream));
+        x->launches++;
+    }
+    Fc2Args f2{x->d_act3, x->wd2, x->bd2, x->d_pose_out, keypoints_by_slot, x->d_row_scene, x->d_row_slot,
+               x->d_pose_total, x->H, x->tcap};
+    grid = max_rows < 148 * 16 ? max_rows : 148 * 16;
+    CK(launch_fc2(f2, grid, x->stream));
+    x->launches++;
+    return MMW_OK;
+}
+
+int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double* dt, uint32_t flags) {
+    if (!x || !offsets || !dt) return fail(MMW_ERR_INVALID, "ctx/offsets/dt is NULL");
+    if ((flags & MMW_STEP_POSE) && !x->has_weights)
+        return fail(MMW_ERR_STATE, "MMW_STEP_POSE needs mmw_load_pose_weights first");
+    CK(cudaSetDevice(x->device));
+    StepArgs a;
+    a.cfg = x->dc;
+    if (flags & MMW_STEP_DEVICE_INPUT) {
+        if (!pts) return fail(MMW_ERR_INVALID, "pts is NULL");
+        a.pts = pts; a.offsets = offsets; a.dt = dt;
+    } else {
+        const size_t total = (size_t)offsets[x->S];
+        if (offsets[0] != 0) return fail(MMW_ERR_INVALID, "offsets[0] must be 0");
+        if (total > (size_t)x->S * x->ncap)
+            return fail(MMW_ERR_CAPACITY, "more points than n_scenes * max_points_per_frame");
+        if (total > 0 && !pts) return fail(MMW_ERR_INVALID, "pts is NULL");
+        if (total > x->pts_cap_rows) {
+            CK(cudaStreamSynchronize(x->stream));
+            if (x->d_pts) cudaFree(x->d_pts);
+            x->d_pts = nullptr;
+            const size_t cap = (size_t)x->S * x->ncap;
+            CK(cudaMalloc((void**)&x->d_pts, sizeof(float) * kRawCols * cap));
+            x->pts_cap_rows = cap;
+        }
+        if (total)
+            CK(cudaMemcpyAsync(x->d_pts, pts, sizeof(float) * kRawCols * total, cudaMemcpyHostToDevice, x->stream));
+        CK(cudaMemcpyAsync(x->d_offsets, offsets, sizeof(int32_t) * (x->S + 1), cudaMemcpyHostToDevice, x->stream));
+        CK(cudaMemcpyAsync(x->d_dt, dt, sizeof(double) * x->S, cudaMemcpyHostToDevice, x->stream));
+        x->h_offsets.assign(offsets, offsets + x->S + 1);
+        a.pts = x->d_pts; a.offsets = x->d_offsets; a.dt = x->d_dt;
+    }
+    a.tracks = x->d_tracks; a.scenes = x->d_scenes; a.track_ring = x->d_track_ring; a.uring = x->d_uring;
+    a.keypoints = x->d_keypoints; a.default_posture = x->d_default_posture; a.assoc_out = x->d_assoc;
+    a.labels_out = (flags & MMW_STEP_RECORD_LABELS) ? x->d_labels : nullptr;
+    a.counters = x->d_counters; a.n_scenes = x->S; a.flags = flags;
+    CK(launch_step(a, x->stream));
+    x->launches++;
+    if (flags & MMW_STEP_POSE) {
+        CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
+        PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, x->d_row_scene, x->d_row_track,
+                        x->d_row_slot};
+        CK(launch_pose_features(fa, x->S, x->stream));
+        x->launches += 2;
+        int rc = run_pose_net(x, x->d_keypoints, x->pose_cap);
+        if (rc != MMW_OK) return rc;
+    }
+    return MMW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int mmw_get_tracks(mmw_ctx* x, mmw_track_out* tracks, int32_t* n_tracks) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    std::vector<SceneRec> sc(x->S);
+    CK(cudaMemcpy(sc.data(), x->d_scenes, sizeof(SceneRec) * x->S, cudaMemcpyDeviceToHost));
+    if (n_tracks)
+        for (int s = 0; s < x->S; ++s) n_tracks[s] = sc[s].n_tracks;
+    if (!tracks) return MMW_OK;
+    std::vector<TrackRec> tr((size_t)x->S * x->tcap);
+    std::vector<float> kp((size_t)x->S * x->tcap * kKp);
+    CK(cudaMemcpy(tr.data(), x->d_tracks, sizeof(TrackRec) * tr.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(kp.data(), x->d_keypoints, sizeof(float) * kp.size(), cudaMemcpyDeviceToHost));
+    for (int s = 0; s < x->S; ++s) {
+        for (int k = 0; k < x->tcap; ++k) {
+            mmw_track_out& o = tracks[(size_t)s * x->tcap + k];
+            std::memset(&o, 0, sizeof(o));
+            if (k >= sc[s].n_tracks) { o.id = -1; continue; }
+            const TrackRec& t = tr[(size_t)s * x->tcap + k];
+            o.id = t.id; o.point_num = t.point_num; o.is_static = t.is_static; o.ring_frames = t.ring_n;
+            for (int f = 0; f < kRing; ++f)
+                o.ring_counts[f] = f < t.ring_n ? t.ring_cnt[(t.ring_head + f) % x->dc.ring_size] : -1;
+            o.lifetime = t.lifetime; o.n_est = t.n_est;
+            std::memcpy(o.x, t.x, sizeof(t.x)); std::memcpy(o.P, t.P, sizeof(t.P));
+            std::memcpy(o.spread_est, t.spread, sizeof(t.spread));
+            std::memcpy(o.group_disp_est, t.G, sizeof(t.G));
+            std::memcpy(o.centroid, t.centroid, sizeof(t.centroid));
+            std::memcpy(o.min_vals, t.minv, sizeof(t.minv)); std::memcpy(o.max_vals, t.maxv, sizeof(t.maxv));
+            std::memcpy(o.keypoints, &kp[((size_t)s * x->tcap + t.slot) * kKp], sizeof(float) * kKp);
+        }
+    }
+    return MMW_OK;
+}
+
+int mmw_get_scene_summary(mmw_ctx* x, int32_t* n_tracks, int32_t* next_id, int32_t* last_M) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(x->device));
+    std::vector<SceneRec> sc(x->S);
+    CK(cudaMemcpyAsync(sc.data(), x->d_scenes, sizeof(SceneRec) * x->S, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    for (int s = 0; s < x->S; ++s) {
+        if (n_tracks) n_tracks[s] = sc[s].n_tracks;
+        if (next_id) next_id[s] = sc[s].next_id;
+        if (last_M) last_M[s] = sc[s].last_M;
+    }
+    return MMW_OK;
+}
+
+int mmw_get_point_assoc(mmw_ctx* x, int32_t* assoc, size_t n) {
+    if (!x || !assoc) return fail(MMW_ERR_INVALID, "ctx/assoc is NULL");
+    if (n > (size_t)x->S * x->ncap) return fail(MMW_ERR_CAPACITY, "n exceeds n_scenes * max_points_per_frame");
+    CK(cudaSetDevice(x->device));
+    CK(cudaMemcpyAsync(assoc, x->d_assoc, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    return MMW_OK;
+}
+
+int mmw_get_labels(mmw_ctx* x, int32_t* labels, int32_t* n_fused) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    if (labels)
+        CK(cudaMemcpy(labels, x->d_labels, sizeof(int32_t) * (size_t)x->S * 3 * x->ncap, cudaMemcpyDeviceToHost));
+    if (n_fused) {
+        std::vector<SceneRec> sc(x->S);
+        CK(cudaMemcpy(sc.data(), x->d_scenes, sizeof(SceneRec) * x->S, cudaMemcpyDeviceToHost));
+        for (int s = 0; s < x->S; ++s) n_fused[s] = sc[s].last_ran ? sc[s].dbscan_n : -1;
+    }
+    return MMW_OK;
+}
+
+int mmw_get_status(mmw_ctx* x, uint32_t* flags) {
+    if (!x || !flags) return fail(MMW_ERR_INVALID, "ctx/flags is NULL");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    std::vector<SceneRec> sc(x->S);
+    CK(cudaMemcpy(sc.data(), x->d_scenes, sizeof(SceneRec) * x->S, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < x->S; ++s) flags[s] = sc[s].flags;
+    return MMW_OK;
+}
+
+int mmw_get_ring_counts(mmw_ctx* x, int32_t* counts) {
+    if (!x || !counts) return fail(MMW_ERR_INVALID, "ctx/counts is NULL");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    std::vector<SceneRec> sc(x->S);
+    CK(cudaMemcpy(sc.data(), x->d_scenes, sizeof(SceneRec) * x->S, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < x->S; ++s)
+        for (int f = 0; f < kRing; ++f)
+            counts[s * kRing + f] =
+                f < sc[s].ring_n ? sc[s].ring_cnt[(sc[s].ring_head + f) % x->dc.ring_size] : -1;
+    return MMW_OK;
+}
+
+static int ring_edit(mmw_ctx* x, int scene, bool clear) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    if (scene < 0 || scene >= x->S) return fail(MMW_ERR_INVALID, "scene out of range");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    SceneRec sc;
+    CK(cudaMemcpy(&sc, x->d_scenes + scene, sizeof(sc), cudaMemcpyDeviceToHost));
+    if (clear) {
+        sc.ring_n = 0; sc.ring_head = 0; sc.ring_cnt[0] = sc.ring_cnt[1] = sc.ring_cnt[2] = 0;
+    } else if (sc.ring_n > 0) {          // popleft (Tracking.py:66-71)
+        sc.ring_cnt[sc.ring_head] = 0;
+        sc.ring_head = (sc.ring_head + 1) % x->dc.ring_size;
+        sc.ring_n -= 1;
+    }
+    CK(cudaMemcpy(x->d_scenes + scene, &sc, sizeof(sc), cudaMemcpyHostToDevice));
+    return MMW_OK;
+}
+int mmw_ring_pop(mmw_ctx* x, int scene) { return ring_edit(x, scene, false); }
+int mmw_ring_clear(mmw_ctx* x, int scene) { return ring_edit(x, scene, true); }
+
+int mmw_get_pose_rows(mmw_ctx* x, int32_t* n_rows, int32_t* scene_idx, int32_t* track_idx, float* feats,
+                      size_t cap_floats) {
+    if (!x || !n_rows) return fail(MMW_ERR_INVALID, "ctx/n_rows is NULL");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    int n = 0;
+    CK(cudaMemcpy(&n, x->d_pose_total, sizeof(int), cudaMemcpyDeviceToHost));
+    *n_rows = n;
+    if (scene_idx) CK(cudaMemcpy(scene_idx, x->d_row_scene, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    if (track_idx) CK(cudaMemcpy(track_idx, x->d_row_track, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    if (feats) {
+        const size_t per = (size_t)x->dc.ring_size * kFeatPts * kRawCols;
+        if (cap_floats < per * n) return fail(MMW_ERR_CAPACITY, "feats buffer too small");
+        CK(cudaMemcpy(feats, x->d_feats, sizeof(float) * per * n, cudaMemcpyDeviceToHost));
+    }
+    return MMW_OK;
+}
+
+int mmw_get_counters(mmw_ctx* x, uint64_t out[8], int reset) {
+    if (!x || !out) return fail(MMW_ERR_INVALID, "ctx/out is NULL");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    unsigned long long h[8];
+    CK(cudaMemcpy(h, x->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) out[i] = h[i];
+    if (reset) CK(cudaMemset(x->d_counters, 0, sizeof(h)));
+    return MMW_OK;
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// stage-level kernels
+// ================================================================================================
+namespace mmw {
+
+__global__ void preprocess_kernel(DevConfig c, const float* pts, size_t n, double* world, uint8_t* keep) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = pts + i * kRawCols;
+    double w[6];
+    world_from_raw(c, p[0], p[1], p[2], p[3], w);
+    double* o = world + i * 8;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = w[k];
+    o[6] = (double)p[3];
+    o[7] = (double)p[4];
+    keep[i] = ((w[2] <= c.z_max) && (w[2] > 0.0) && (w[1] > 0.0)) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kStepThreads) dbscan_stage_kernel(DevConfig c, const double* xyz,
+                                                                    const int32_t* offsets, double eps, int min_samples,
+                                                                    int32_t* labels, int maxB) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* X = reinterpret_cast<double*>(smem);
+    double* Y = X + maxB;
+    double* Z = Y + maxB;
+    int* par = reinterpret_cast<int*>(Z + maxB);
+    int* cl = par + maxB;
+    int* scan = cl + maxB;
+    const int off = offsets[blockIdx.x];
+    const int B = offsets[blockIdx.x + 1] - off;
+    if (B <= 0) return;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        X[b] = xyz[(size_t)(off + b) * 3 + 0];
+        Y[b] = xyz[(size_t)(off + b) * 3 + 1];
+        Z[b] = xyz[(size_t)(off + b) * 3 + 2];
+    }
+    __syncthreads();
+    dbscan_block(c, X, Y, Z, B, eps, min_samples, par, cl, scan);
+    for (int b = threadIdx.x; b < B; b += blockDim.x) labels[off + b] = cl[b];
+}
+
+__global__ void kalman_predict_kernel(double* x, double* P, const double* dt, int n, double q_var) {
+    __shared__ double sx[4][9], sP[4][81], tmp[4][81];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + warp;
+    if (i >= n) return;
+    for (int e = lane; e < 81; e += 32) sP[warp][e] = P[(size_t)i * 81 + e];
+    if (lane < 9) sx[warp][lane] = x[(size_t)i * 9 + lane];
+    __syncwarp();
+    warp_kf_predict(sx[warp], sP[warp], dt[i], q_var, tmp[warp], lane);
+    for (int e = lane; e < 81; e += 32) P[(size_t)i * 81 + e] = sP[warp][e];
+    if (lane < 9) x[(size_t)i * 9 + lane] = sx[warp][lane];
+}
+
+__global__ void kalman_update_kernel(double* x, double* P, const double* z, const double* R, const uint8_t* life0,
+                                     int n, double thres, double gain) {
+    __shared__ double sx[4][9], sP[4][81], sz[4][6], sR[4][36], ws[4][kWarpScratch];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + warp;
+    if (i >= n) return;
+    for (int e = lane; e < 81; e += 32) sP[warp][e] = P[(size_t)i * 81 + e];
+    for (int e = lane; e < 36; e += 32) sR[warp][e] = R[(size_t)i * 36 + e];
+    if (lane < 9) sx[warp][lane] = x[(size_t)i * 9 + lane];
+    if (lane < 6) sz[warp][lane] = z[(size_t)i * 6 + lane];
+    __syncwarp();
+    warp_kf_update(sx[warp], sP[warp], sz[warp], sR[warp], life0[i] != 0, thres, gain, ws[warp], lane);
+    for (int e = lane; e < 81; e += 32) P[(size_t)i * 81 + e] = sP[warp][e];
+    if (lane < 9) x[(size_t)i * 9 + lane] = sx[warp][lane];
+}
+
+__global__ void __launch_bounds__(128) gate_stage_kernel(const double* pts, int M, const double* hx, const double* C,
+                                                         int T, double gate, double* d2, int32_t* assoc) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* cinv = reinterpret_cast<double*>(smem);          // [T][36]
+    double* logdet = cinv + (size_t)T * 36;                   // [T]
+    double* sC = logdet + T;                                  // [4][36]
+    double* aug = sC + 4 * 36;                                // [4][72]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < T; j += 4) {
+        for (int e = lane; e < 36; e += 32) sC[warp * 36 + e] = C[(size_t)j * 36 + e];
+        __syncwarp();
+        const double det = warp_inv6(sC + warp * 36, cinv + j * 36, aug + warp * 72, lane);
+        if (lane == 0) logdet[j] = log(fabs(det));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        double best = INFINITY;
+        int bj = -1;
+        for (int j = 0; j < T; ++j) {
+            double y[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) y[k] = pts[(size_t)i * 6 + k] - hx[j * 6 + k];
+            double q = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                double tb = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) tb += y[k] * cinv[j * 36 + k * 6 + b];
+                q += tb * y[b];
+            }
+            const double v = logdet[j] + q;
+            d2[(size_t)i * T + j] = v;
+            if (v < gate && v < best) { best = v; bj = j; }
+        }
+        assoc[i] = bj;
+    }
+}
+
+__global__ void pack_results_kernel(const SceneRec* scenes, const TrackRec* tracks, const float* keypoints, int S,
+                                    int tcap, float* out) {
+    const int idx = blockIdx.x;            // scene * tcap + k
+    const int s = idx / tcap, k = idx % tcap;
+    float* o = out + (size_t)idx * MMW_RESULT_FLOATS;
+    const int nt = scenes[s].n_tracks;
+    if (k >= nt) {
+        for (int e = threadIdx.x; e < MMW_RESULT_FLOATS; e += blockDim.x) o[e] = e == 0 ? -1.f : 0.f;
+        if (threadIdx.x == 0) o[1] = (float)nt;
+        return;
+    }
+    const TrackRec* t = tracks + (size_t)s * tcap + k;
+    for (int e = threadIdx.x; e < MMW_RESULT_FLOATS; e += blockDim.x) {
+        float v;
+        if (e == 0) v = (float)t->id;
+        else if (e == 1) v = (float)nt;
+        else if (e < 11) v = (float)t->x[e - 2];
+        else v = keypoints[((size_t)s * tcap + t->slot) * kKp + (e - 11)];
+        o[e] = v;
+    }
+}
+
+}  // namespace mmw
+
+extern "C" {
+
+int mmw_pack_results(mmw_ctx* x, float* device_out) {
+    if (!x || !device_out) return fail(MMW_ERR_INVALID, "ctx/device_out is NULL");
+    CK(cudaSetDevice(x->device));
+    pack_results_kernel<<<x->S * x->tcap, 64, 0, x->stream>>>(x->d_scenes, x->d_tracks, x->d_keypoints, x->S, x->tcap,
+                                                              device_out);
+    CK(cudaGetLastError());
+    x->launches++;
+    return MMW_OK;
+}
+
+int mmw_preprocess(mmw_ctx* x, const float* pts, size_t n, double* world, uint8_t* keep) {
+    if (!x || !world || !keep || (n && !pts)) return fail(MMW_ERR_INVALID, "NULL argument");
+    if (n == 0) return MMW_OK;
+    CK(cudaSetDevice(x->device));
+    float* dp; double* dw; uint8_t* dk;
+    CK(cudaMalloc((void**)&dp, n * kRawCols * sizeof(float)));
+    CK(cudaMalloc((void**)&dw, n * 8 * sizeof(double)));
+    CK(cudaMalloc((void**)&dk, n));
+    CK(cudaMemcpyAsync(dp, pts, n * kRawCols * sizeof(float), cudaMemcpyHostToDevice, x->stream));
+    preprocess_kernel<<<(unsigned)((n + 255) / 256), 256, 0, x->stream>>>(x->dc, dp, n, dw, dk);
+    CK(cudaGetLastError());
+    x->launches++;
+    CK(cudaMemcpyAsync(world, dw, n * 8 * sizeof(double), cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemcpyAsync(keep, dk, n, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    cudaFree(dp); cudaFree(dw); cudaFree(dk);
+    return MMW_OK;
+}
+
+int mmw_dbscan(mmw_ctx* x, const double* xyz, const int32_t* offsets, int n_clouds, double eps, int min_samples,
+               int32_t* labels) {
+    if (!x || !offsets || !labels || n_clouds < 0) return fail(MMW_ERR_INVALID, "NULL argument");
+    if (n_clouds == 0) return MMW_OK;
+    const size_t total = (size_t)offsets[n_clouds];
+    int maxB = 0;
+    for (int i = 0; i < n_clouds; ++i) {
+        const int b = offsets[i + 1] - offsets[i];
+        if (b < 0) return fail(MMW_ERR_INVALID, "offsets must be non-decreasing");
+        if (b > maxB) maxB = b;
+    }
+    if (maxB > 3 * x->ncap) return fail(MMW_ERR_CAPACITY, "a cloud has more than 3*max_points points");
+    if (total == 0) return MMW_OK;
+    if (!xyz) return fail(MMW_ERR_INVALID, "xyz is NULL");
+    if (eps <= 0) eps = x->cfg.db_eps;
+    if (min_samples <= 0) min_samples = x->cfg.db_min_samples;
+    CK(cudaSetDevice(x->device));
+    double* dx; int32_t *doff, *dl;
+    CK(cudaMalloc((void**)&dx, total * 3 * sizeof(double)));
+    CK(cudaMalloc((void**)&doff, (n_clouds + 1) * sizeof(int32_t)));
+    CK(cudaMalloc((void**)&dl, total * sizeof(int32_t)));
+    CK(cudaMemcpyAsync(dx, xyz, total * 3 * sizeof(double), cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(doff, offsets, (n_clouds + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, x->stream));
+    const size_t smem = (size_t)maxB * (3 * 8 + 2 * 4) + 64;
+    CK(cudaFuncSetAttribute(dbscan_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dbscan_stage_kernel<<<n_clouds, kStepThreads, smem, x->stream>>>(x->dc, dx, doff, eps, min_samples, dl, maxB);
+    CK(cudaGetLastError());
+    x->launches++;
+    CK(cudaMemcpyAsync(labels, dl, total * sizeof(int32_t), cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    cudaFree(dx); cudaFree(doff); cudaFree(dl);
+    return MMW_OK;
+}
+
+int mmw_kalman_predict(mmw_ctx* x, double* hx, double* hP, const double* dt, int n) {
+    if (!x || !hx || !hP || !dt || n < 0) return fail(MMW_ERR_INVALID, "NULL argument");
+    if (n == 0) return MMW_OK;
+    CK(cudaSetDevice(x->device));
+    double *dx, *dP, *ddt;
+    CK(cudaMalloc((void**)&dx, (size_t)n * 9 * 8));
+    CK(cudaMalloc((void**)&dP, (size_t)n * 81 * 8));
+    CK(cudaMalloc((void**)&ddt, (size_t)n * 8));
+    CK(cudaMemcpyAsync(dx, hx, (size_t)n * 9 * 8, cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(dP, hP, (size_t)n * 81 * 8, cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(ddt, dt, (size_t)n * 8, cudaMemcpyHostToDevice, x->stream));
+    kalman_predict_kernel<<<(n + 3) / 4, 128, 0, x->stream>>>(dx, dP, ddt, n, x->dc.q_var);
+    CK(cudaGetLastError());
+    x->launches++;
+    CK(cudaMemcpyAsync(hx, dx, (size_t)n * 9 * 8, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemcpyAsync(hP, dP, (size_t)n * 81 * 8, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    cudaFree(dx); cudaFree(dP); cudaFree(ddt);
+    return MMW_OK;
+}
+
+int mmw_kalman_update(mmw_ctx* x, double* hx, double* hP, const double* z, const double* R, const uint8_t* life0,
+                      int n) {
+    if (!x || !hx || !hP || !z || !R || !life0 || n < 0) return fail(MMW_ERR_INVALID, "NULL argument");
+    if (n == 0) return MMW_OK;
+    CK(cudaSetDevice(x->device));
+    double *dx, *dP, *dz, *dR; uint8_t* dl;
+    CK(cudaMalloc((void**)&dx, (size_t)n * 9 * 8));
+    CK(cudaMalloc((void**)&dP, (size_t)n * 81 * 8));
+    CK(cudaMalloc((void**)&dz, (size_t)n * 6 * 8));
+    CK(cudaMalloc((void**)&dR, (size_t)n * 36 * 8));
+    CK(cudaMalloc((void**)&dl, (size_t)n));
+    CK(cudaMemcpyAsync(dx, hx, (size_t)n * 9 * 8, cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(dP, hP, (size_t)n * 81 * 8, cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(dz, z, (size_t)n * 6 * 8, cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(dR, R, (size_t)n * 36 * 8, cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(dl, life0, (size_t)n, cudaMemcpyHostToDevice, x->stream));
+    kalman_update_kernel<<<(n + 3) / 4, 128, 0, x->stream>>>(dx, dP, dz, dR, dl, n, x->dc.nudge_thres,
+                                                             x->dc.nudge_gain);
+    CK(cudaGetLastError());
+    x->launches++;
+    CK(cudaMemcpyAsync(hx, dx, (size_t)n * 9 * 8, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemcpyAsync(hP, dP, (size_t)n * 81 * 8, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    cudaFree(dx); cudaFree(dP); cudaFree(dz); cudaFree(dR); cudaFree(dl);
+    return MMW_OK;
+}
+
+int mmw_gate(mmw_ctx* x, const double* points, int M, const double* hxv, const double* C, int T, double* d2,
+             int32_t* assoc) {
+    if (!x || !assoc || M < 0 || T < 0) return fail(MMW_ERR_INVALID, "NULL argument");
+    if (M == 0) return MMW_OK;
+    if (T > 0 && (!hxv || !C || !d2)) return fail(MMW_ERR_INVALID, "NULL argument");
+    if (!points) return fail(MMW_ERR_INVALID, "points is NULL");
+    CK(cudaSetDevice(x->device));
+    double *dp, *dh = nullptr, *dC = nullptr, *dd = nullptr; int32_t* da;
+    CK(cudaMalloc((void**)&dp, (size_t)M * 6 * 8));
+    CK(cudaMalloc((void**)&da, (size_t)M * 4));
+    CK(cudaMalloc((void**)&dh, (size_t)(T ? T : 1) * 6 * 8));
+    CK(cudaMalloc((void**)&dC, (size_t)(T ? T : 1) * 36 * 8));
+    CK(cudaMalloc((void**)&dd, (size_t)M * (T ? T : 1) * 8));
+    CK(cudaMemcpyAsync(dp, points, (size_t)M * 6 * 8, cudaMemcpyHostToDevice, x->stream));
+    if (T) {
+        CK(cudaMemcpyAsync(dh, hxv, (size_t)T * 6 * 8, cudaMemcpyHostToDevice, x->stream));
+        CK(cudaMemcpyAsync(dC, C, (size_t)T * 36 * 8, cudaMemcpyHostToDevice, x->stream));
+    }
+    const size_t smem = ((size_t)T * 37 + 4 * 36 + 4 * 72) * 8;
+    CK(cudaFuncSetAttribute(gate_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gate_stage_kernel<<<1, 128, smem, x->stream>>>(dp, M, dh, dC, T, x->dc.gate, dd, da);
+    CK(cudaGetLastError());
+    x->launches++;
+    if (T) CK(cudaMemcpyAsync(d2, dd, (size_t)M * T * 8, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemcpyAsync(assoc, da, (size_t)M * 4, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    cudaFree(dp); cudaFree(da); cudaFree(dh); cudaFree(dC); cudaFree(dd);
+    return MMW_OK;
+}
+
+int mmw_pose(mmw_ctx* x, const float* feats, int n, float* keypoints) {
+    if (!x || !feats || !keypoints || n < 0) return fail(MMW_ERR_INVALID, "NULL argument");
+    if (!x->has_weights) return fail(MMW_ERR_STATE, "mmw_pose needs mmw_load_pose_weights first");
+    if (n > x->pose_cap) return fail(MMW_ERR_CAPACITY, "n exceeds n_scenes * max_tracks");
+    if (n == 0) return MMW_OK;
+    CK(cudaSetDevice(x->device));
+    const size_t per = (size_t)x->dc.ring_size * kFeatPts * kRawCols;
+    CK(cudaMemcpyAsync(x->d_feats, feats, sizeof(float) * per * n, cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(x->d_pose_total, &n, sizeof(int), cudaMemcpyHostToDevice, x->stream));
+    CK(cudaStreamSynchronize(x->stream));     // &n is a stack variable
+    int rc = run_pose_net(x, nullptr, n);
+    if (rc != MMW_OK) return rc;
+    CK(cudaMemcpyAsync(keypoints, x->d_pose_out, sizeof(float) * kKp * n, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    return MMW_OK;
+}
+
+/* Test/bench hook: 0 = CUDA-core fp32 dense path, 1 = tcgen05 tensor-core dense path (default). */
+int mmw_set_dense_path(mmw_ctx* x, int use_tensor_cores) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    x->use_tc = use_tensor_cores != 0;
+    return MMW_OK;
+}
+
+}  // extern "C"

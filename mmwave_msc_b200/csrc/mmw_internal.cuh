@@ -1,0 +1,124 @@
+// Internal device-side data model of libmmw (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mmw.h"
+
+namespace mmw {
+
+constexpr int kRing = 3;          // max frames in a ring: FB_FRAMES_BATCH + 1 <= 3 (constants.py:66)
+constexpr int kFeatPts = 64;      // points kept per track ring frame (format_single_frame, Utils.py:505-510)
+constexpr int kRawCols = 5;       // x, y, z, doppler, peakVal (sensor frame, fp32)
+constexpr int kKp = 57;           // 19 joints x 3
+constexpr int kStepThreads = 128;
+constexpr int kStepWarps = kStepThreads / 32;
+constexpr int kMaxTcap = 32;
+
+// Derived constants handed to kernels by value.
+struct DevConfig {
+    double cos_t, sin_t, s_height, z_max;
+    double db_z_weight, db_range_weight, db_eps;
+    double life_dyn, life_sta, vel_thres, gate;
+    double q_var, p_init, g_init, a_n, a_spr;
+    double spread_lim[6];
+    double int_mu, int_std, nudge_thres, nudge_gain;
+    int db_min_samples, ring_size, tr_max_tracks, enable_est, est_pointnum;
+    int ncap, tcap;
+};
+
+// One element of a scene's effective_tracks list (ClusterTrack + KalmanState + PointCluster).
+// All decision arithmetic of the tracker is float64, like the reference.
+struct TrackRec {
+    double x[9];
+    double P[81];
+    double spread[6];
+    double G[36];          // group_disp_est
+    double centroid[6];
+    double minv[6];
+    double maxv[6];
+    double n_est;
+    double lifetime;
+    int32_t id;
+    int32_t point_num;
+    int32_t is_static;
+    int32_t slot;          // physical slot of this track's ring / keypoints inside the scene
+    int32_t ring_n;        // frames in the track ring
+    int32_t ring_head;     // physical index of the oldest frame
+    int32_t ring_cnt[kRing];   // stored rows per PHYSICAL frame (<= 64)
+    int32_t pad;
+};
+static_assert(sizeof(TrackRec) % 8 == 0, "TrackRec must be a whole number of doubles");
+constexpr int kTrackWords = sizeof(TrackRec) / 8;
+
+struct SceneRec {
+    int32_t n_tracks;
+    int32_t next_id;
+    int32_t ring_n;            // frames in the global unassigned ring
+    int32_t ring_head;         // physical index of the oldest frame
+    int32_t ring_cnt[kRing];   // points per PHYSICAL frame
+    uint32_t slot_mask;        // physical track slots in use
+    uint32_t flags;            // MMW_SCENE_* overflow bits
+    int32_t last_M;            // points surviving the bounds filter in the last frame
+    int32_t last_ran;          // 1 if the last frame ran track()
+    int32_t dbscan_n;          // fused points clustered in the last frame, -1 if DBSCAN did not run
+    int32_t pose_base;         // first pose row of this scene in the last pose batch
+    int32_t pad[3];
+};
+static_assert(sizeof(SceneRec) == 64, "SceneRec is one 64-byte record");
+
+struct StepArgs {
+    DevConfig cfg;
+    const float* pts;          // [sum N, 5]
+    const int32_t* offsets;    // [S+1]
+    const double* dt;          // [S]
+    TrackRec* tracks;          // [S][tcap]
+    SceneRec* scenes;          // [S]
+    float* track_ring;         // [S][tcap][kRing][64][5]
+    float* uring;              // [S][kRing][ncap][5]
+    float* keypoints;          // [S][tcap][57] by physical slot
+    const float* default_posture;  // [57]
+    int32_t* assoc_out;        // [sum N]
+    int32_t* labels_out;       // [S][3*ncap] or nullptr
+    unsigned long long* counters;  // [8]
+    int n_scenes;
+    uint32_t flags;
+};
+
+// ---- world-frame point from a raw sensor point (Utils.py:379-420) -----------------------------------
+// Written with explicit round-to-nearest multiplies/adds (no FMA contraction) so that the
+// scene-bounds predicates and the DBSCAN inputs are bit-identical to the float64 numpy oracle.
+__device__ __forceinline__ void world_yz(const DevConfig& c, double y, double z, double& yw, double& zw) {
+    yw = __dadd_rn(__dmul_rn(c.cos_t, y), __dmul_rn(-c.sin_t, z));
+    zw = __dadd_rn(__dadd_rn(__dmul_rn(c.sin_t, y), __dmul_rn(c.cos_t, z)), c.s_height);
+}
+
+__device__ __forceinline__ void world_from_raw(const DevConfig& c, float fx, float fy, float fz, float fd,
+                                               double w[6]) {
+    const double x = fx, y = fy, z = fz, d = fd;
+    const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+    double vx, vy, vz;
+    if (r == 0.0) {                       // Utils.py:387-390
+        vx = 0.0; vy = d; vz = 0.0;
+    } else {                              // Utils.py:400-402: (doppler * coord) / r
+        vx = __ddiv_rn(__dmul_rn(d, x), r);
+        vy = __ddiv_rn(__dmul_rn(d, y), r);
+        vz = __ddiv_rn(__dmul_rn(d, z), r);
+    }
+    w[0] = x;
+    world_yz(c, y, z, w[1], w[2]);
+    w[3] = vx;
+    w[4] = __dadd_rn(__dmul_rn(c.cos_t, vy), __dmul_rn(-c.sin_t, vz));
+    w[5] = __dadd_rn(__dmul_rn(c.sin_t, vy), __dmul_rn(c.cos_t, vz));
+}
+
+// altered_EuclideanDist(p, q) <= eps (Utils.py:242-247, compared as sklearn's radius query does)
+__device__ __forceinline__ bool eps_neighbour(const DevConfig& c, double x1, double y1, double z1, double x2,
+                                              double y2, double z2, double eps) {
+    const double w = __dsub_rn(1.0, __dmul_rn(__dmul_rn(__dadd_rn(y1, y2), 0.5), c.db_range_weight));
+    const double dx = __dsub_rn(x1, x2), dy = __dsub_rn(y1, y2), dz = __dsub_rn(z1, z2);
+    const double q = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)),
+                               __dmul_rn(c.db_z_weight, __dmul_rn(dz, dz)));
+    return __dmul_rn(w, q) <= eps;
+}
+
+}  // namespace mmw

@@ -1,0 +1,56 @@
+// Argument blocks of the pose-stage kernels (pose_kernels.cu, pose_tc.cu).
+#pragma once
+#include "mmw_internal.cuh"
+
+namespace mmw {
+
+struct PoseFeatArgs {
+    DevConfig cfg;
+    const SceneRec* scenes;
+    const TrackRec* tracks;
+    const float* track_ring;
+    float* feats;          // [rows][ring_size*64*5]
+    int32_t* row_scene;    // [rows]
+    int32_t* row_track;
+    int32_t* row_slot;
+};
+
+struct ConvArgs {
+    const float* feats;    // [rows][D*64*5]
+    const float *w1, *b1, *w2, *b2, *bn1_scale, *bn1_shift;
+    float* act2;           // [rows][D*64*32]  BN1(relu(conv2)), channels-last flatten order
+    const int* n_rows;     // device scalar
+};
+
+struct FcArgs {
+    const float* A;        // [rows][K]
+    const float* W;        // [K][H]
+    const float *bias, *bn_scale, *bn_shift;
+    float* out;            // [rows][H]
+    const int* n_rows;
+    int K, H;
+};
+
+struct Fc2Args {
+    const float* act3;     // [rows][H]
+    const float* W;        // [H][57]
+    const float* bias;
+    float* out;            // [rows][57]
+    float* keypoints;      // [S][tcap][57] by slot, or nullptr
+    const int32_t* row_scene;
+    const int32_t* row_slot;
+    const int* n_rows;
+    int H, tcap;
+};
+
+cudaError_t launch_pose_index(SceneRec* scenes, int S, int* pose_total, unsigned long long* counters,
+                              cudaStream_t st);
+cudaError_t launch_pose_features(const PoseFeatArgs& a, int S, cudaStream_t st);
+cudaError_t launch_conv(const ConvArgs& a, int D, int grid, cudaStream_t st);
+cudaError_t launch_fc1_simt(const FcArgs& a, int max_rows, cudaStream_t st);
+cudaError_t launch_fc2(const Fc2Args& a, int grid, cudaStream_t st);
+
+int step_smem_bytes(int ncap, int tcap);
+cudaError_t launch_step(const StepArgs& a, cudaStream_t stream);
+
+}  // namespace mmw

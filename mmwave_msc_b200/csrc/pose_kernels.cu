@@ -1,0 +1,309 @@
+// Pose stage: TrackBuffer.estimate_posture (Tracking.py:705-734).
+//   pose_index_kernel    compacts the tracks of all scenes that ran this frame into pose rows
+//   pose_feature_kernel  relative_coordinates + format_single_frame (Utils.py:437-520) per track
+//   conv_kernel          Conv(5->16)+ReLU, Conv(16->32)+ReLU, BatchNorm   (train.py:35-47 / 74-85)
+//   fc1 / fc2            Dense+ReLU+BatchNorm, Dense(57)                  (train.py:49-57 / 87-96)
+// The CUDA-core fp32 kernels in this file are the reference-exact path; the tensor-core (tcgen05) GEMM for the
+// dense contraction lives in pose_tc.cu and replaces fc1 when enabled.
+#include "mmw_internal.cuh"
+#include "pose.cuh"
+
+namespace mmw {
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) pose_index_kernel(SceneRec* scenes, int S, int* pose_total,
+                                                          unsigned long long* counters) {
+    __shared__ int wsum[32];
+    __shared__ int running;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < S; base += 1024) {
+        const int s = base + tid;
+        int v = 0;
+        if (s < S && scenes[s].last_ran) v = scenes[s].n_tracks;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int cw = wsum[w];
+            if (w < warp) before += cw;
+            tot += cw;
+        }
+        const int r0 = running;
+        if (s < S) scenes[s].pose_base = r0 + before + incl - v;
+        __syncthreads();
+        if (tid == 0) running = r0 + tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        *pose_total = running;
+        atomicAdd(&counters[7], (unsigned long long)running);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One warp per track.  Feature rows are relative to the CURRENT centroid for every ring frame (Q21),
+// intensity is normalised before padding so pads stay exactly 0, rows are sorted by x with the canonical
+// stable (x, row index) order, frames absent from the ring stay zero.
+__global__ void __launch_bounds__(128) pose_feature_kernel(PoseFeatArgs a) {
+    __shared__ double keys[4][kFeatPts];
+    __shared__ float vals[4][kFeatPts][kRawCols];
+    const int s = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const SceneRec sc = a.scenes[s];
+    if (!sc.last_ran) return;
+    const DevConfig& c = a.cfg;
+    const int nfr = c.ring_size;
+    for (int k = warp; k < sc.n_tracks; k += 4) {
+        const TrackRec* t = a.tracks + (size_t)s * c.tcap + k;
+        const int row = sc.pose_base + k;
+        const double cx = t->centroid[0], cy = t->centroid[1];
+        const int slot = t->slot, rn = t->ring_n, rh = t->ring_head;
+        if (lane == 0) {
+            a.row_scene[row] = s;
+            a.row_track[row] = k;
+            a.row_slot[row] = slot;
+        }
+        float* out = a.feats + (size_t)row * nfr * kFeatPts * kRawCols;
+        for (int f = 0; f < nfr; ++f) {
+            if (f >= rn) {
+                for (int e = lane; e < kFeatPts * kRawCols; e += 32) out[f * kFeatPts * kRawCols + e] = 0.f;
+                continue;
+            }
+            const int phys = (rh + f) % c.ring_size;
+            const int cnt = t->ring_cnt[phys];
+            const float* src = a.track_ring + (((size_t)s * c.tcap + slot) * kRing + phys) * (kFeatPts * kRawCols);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane + 32 * h;
+                double key = 0.0;
+                float v[kRawCols] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                if (i < cnt) {
+                    const float x = src[i * kRawCols + 0], y = src[i * kRawCols + 1], z = src[i * kRawCols + 2];
+                    const float d = src[i * kRawCols + 3], p = src[i * kRawCols + 4];
+                    double yw, zw;
+                    world_yz(c, (double)y, (double)z, yw, zw);
+                    key = __dsub_rn((double)x, cx);
+                    v[0] = (float)key;
+                    v[1] = (float)__dsub_rn(yw, cy);
+                    v[2] = (float)zw;
+                    v[3] = d;
+                    v[4] = (float)__ddiv_rn(__dsub_rn((double)p, c.int_mu), c.int_std);
+                }
+                keys[warp][i] = key;
+#pragma unroll
+                for (int q = 0; q < kRawCols; ++q) vals[warp][i][q] = v[q];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane + 32 * h;
+                const double key = keys[warp][i];
+                int rank = 0;
+                for (int q = 0; q < kFeatPts; ++q) {
+                    const double kq = keys[warp][q];
+                    rank += (kq < key || (kq == key && q < i)) ? 1 : 0;
+                }
+#pragma unroll
+                for (int q = 0; q < kRawCols; ++q)
+                    out[(f * kFeatPts + rank) * kRawCols + q] = vals[warp][i][q];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Conv stack, one CTA per pose row.  D = 1 (define_CNN, 8x8x5) or 3 (define_CNN_3D, 3x8x8x5).
+// 'same' zero padding, cross-correlation, channels-last; Dropout is identity at inference.
+template <int D>
+__global__ void __launch_bounds__(256) conv_kernel(ConvArgs a) {
+    constexpr int P = D * 64;                 // output positions
+    constexpr int TAPS = (D == 3 ? 27 : 9);
+    constexpr int A1S = 17;                   // padded row stride of act1 (bank conflicts)
+    extern __shared__ __align__(16) float sm[];
+    float* w2 = sm;                           // [TAPS][16][32]
+    float* w1 = w2 + TAPS * 16 * 32;          // [TAPS][5][16]
+    float* in = w1 + TAPS * 5 * 16;           // [P][5]
+    float* a1 = in + P * 5;                   // [P][A1S]
+    __shared__ int total;
+    if (threadIdx.x == 0) total = *a.n_rows;
+    for (int i = threadIdx.x; i < TAPS * 16 * 32; i += 256) w2[i] = a.w2[i];
+    for (int i = threadIdx.x; i < TAPS * 5 * 16; i += 256) w1[i] = a.w1[i];
+    __syncthreads();
+    for (int row = blockIdx.x; row < total; row += gridDim.x) {
+        const float* feat = a.feats + (size_t)row * P * 5;
+        for (int i = threadIdx.x; i < P * 5; i += 256) in[i] = feat[i];
+        __syncthreads();
+        // conv1: thread = (pos, 8 output channels)
+        for (int it = threadIdx.x; it < P * 2; it += 256) {
+            const int pos = it >> 1, c0 = (it & 1) * 8;
+            const int d = pos / 64, h = (pos / 8) % 8, w = pos % 8;
+            float acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = a.b1[c0 + q];
+            for (int tap = 0; tap < TAPS; ++tap) {
+                const int kd = (D == 3) ? tap / 9 - 1 : 0, kh = (tap / 3) % 3 - 1, kw = tap % 3 - 1;
+                const int dd = d + kd, hh = h + kh, ww = w + kw;
+                if (dd < 0 || dd >= D || hh < 0 || hh >= 8 || ww < 0 || ww >= 8) continue;
+                const float* ip = in + ((dd * 8 + hh) * 8 + ww) * 5;
+                const float* wp_ = w1 + tap * 5 * 16 + c0;
+#pragma unroll
+                for (int ci = 0; ci < 5; ++ci) {
+                    const float v = ip[ci];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[q] = fmaf(v, wp_[ci * 16 + q], acc[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a1[pos * A1S + c0 + q] = fmaxf(acc[q], 0.f);
+        }
+        __syncthreads();
+        // conv2 + ReLU + BatchNorm: thread = (pos, 8 output channels)
+        float* out = a.act2 + (size_t)row * P * 32;
+        for (int it = threadIdx.x; it < P * 4; it += 256) {
+            const int pos = it % P, c0 = (it / P) * 8;
+            const int d = pos / 64, h = (pos / 8) % 8, w = pos % 8;
+            float acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = a.b2[c0 + q];
+            for (int tap = 0; tap < TAPS; ++tap) {
+                const int kd = (D == 3) ? tap / 9 - 1 : 0, kh = (tap / 3) % 3 - 1, kw = tap % 3 - 1;
+                const int dd = d + kd, hh = h + kh, ww = w + kw;
+                if (dd < 0 || dd >= D || hh < 0 || hh >= 8 || ww < 0 || ww >= 8) continue;
+                const float* ip = a1 + ((dd * 8 + hh) * 8 + ww) * A1S;
+                const float* wp_ = w2 + tap * 16 * 32 + c0;
+#pragma unroll
+                for (int ci = 0; ci < 16; ++ci) {
+                    const float v = ip[ci];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[q] = fmaf(v, wp_[ci * 32 + q], acc[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                out[pos * 32 + c0 + q] = fmaf(fmaxf(acc[q], 0.f), a.bn1_scale[c0 + q], a.bn1_shift[c0 + q]);
+        }
+        __syncthreads();
+    }
+}
+
+size_t conv_smem_bytes(int D) {
+    const int P = D * 64, TAPS = (D == 3 ? 27 : 9);
+    return sizeof(float) * (size_t)(TAPS * 16 * 32 + TAPS * 5 * 16 + P * 5 + P * 17);
+}
+
+cudaError_t launch_conv(const ConvArgs& a, int D, int grid, cudaStream_t st) {
+    const size_t smem = conv_smem_bytes(D);
+    cudaError_t e;
+    if (D == 3) {
+        e = cudaFuncSetAttribute(conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        conv_kernel<3><<<grid, 256, smem, st>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        conv_kernel<1><<<grid, 256, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Dense 1 (CUDA-core fp32 path): out[n][H] = BN2(relu(A[n][K] W[K][H] + b)).  64x64 tile, 256 threads, 4x4 each.
+__global__ void __launch_bounds__(256) fc1_simt_kernel(FcArgs a) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int n = *a.n_rows;
+    const int m0 = blockIdx.y * 64, h0 = blockIdx.x * 64;
+    if (m0 >= n) return;
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < a.K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int r = i / 16, kk = i % 16;
+            As[kk][r] = (m0 + r < n) ? a.A[(size_t)(m0 + r) * a.K + k0 + kk] : 0.f;
+        }
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            const int kk = i / 64, cc = i % 64;
+            Bs[kk][cc] = a.W[(size_t)(k0 + kk) * a.H + h0 + cc];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= n) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int h = h0 + tx * 4 + j;
+            const float v = fmaxf(acc[i][j] + a.bias[h], 0.f);
+            a.out[(size_t)m * a.H + h] = fmaf(v, a.bn_scale[h], a.bn_shift[h]);
+        }
+    }
+}
+
+cudaError_t launch_fc1_simt(const FcArgs& a, int max_rows, cudaStream_t st) {
+    dim3 grid(a.H / 64, (max_rows + 63) / 64);
+    fc1_simt_kernel<<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// Dense 2: keypoints[n][57] = act3[n][H] W3[H][57] + b3; one CTA (64 threads) per row; also scatters the
+// result to the owning track's keypoint slot (Tracking.py:733-734).
+__global__ void __launch_bounds__(64) fc2_kernel(Fc2Args a) {
+    extern __shared__ float xrow[];
+    const int n = *a.n_rows;
+    for (int row = blockIdx.x; row < n; row += gridDim.x) {
+        for (int i = threadIdx.x; i < a.H; i += 64) xrow[i] = a.act3[(size_t)row * a.H + i];
+        __syncthreads();
+        if (threadIdx.x < kKp) {
+            float acc = 0.f;
+            for (int h = 0; h < a.H; ++h) acc = fmaf(xrow[h], a.W[(size_t)h * kKp + threadIdx.x], acc);
+            acc += a.bias[threadIdx.x];
+            a.out[(size_t)row * kKp + threadIdx.x] = acc;
+            if (a.keypoints != nullptr) {
+                const int s = a.row_scene[row], slot = a.row_slot[row];
+                a.keypoints[((size_t)s * a.tcap + slot) * kKp + threadIdx.x] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_fc2(const Fc2Args& a, int grid, cudaStream_t st) {
+    fc2_kernel<<<grid, 64, a.H * sizeof(float), st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pose_index(SceneRec* scenes, int S, int* pose_total, unsigned long long* counters,
+                              cudaStream_t st) {
+    pose_index_kernel<<<1, 1024, 0, st>>>(scenes, S, pose_total, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pose_features(const PoseFeatArgs& a, int S, cudaStream_t st) {
+    pose_feature_kernel<<<S, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace mmw

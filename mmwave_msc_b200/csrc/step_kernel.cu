@@ -1,0 +1,545 @@
+// The fused per-frame tracker step: one CTA per scene runs
+//   Utils.normalize_data (Utils.py:342-434) -> TrackBuffer.track (Tracking.py:664-703)
+// i.e. transform+bounds filter+ordered compaction, Kalman predict, Mahalanobis gating and association,
+// per-track cluster statistics and ring push, track maintenance, Kalman update, push of the unassigned
+// points into the scene's global ring, DBSCAN over the fused ring, and track spawning -- with every
+// intermediate in shared memory / registers.  HBM traffic per scene-frame is the raw points in, the track
+// records in and out, the ring rows written and the fused ring read when DBSCAN runs.
+#include "dbscan.cuh"
+#include "linalg.cuh"
+#include "mmw_internal.cuh"
+
+namespace mmw {
+
+struct SmemLayout {
+    // offsets in bytes into dynamic shared memory
+    int regionA;     // doubles: world cols [6][ncap] during association; X,Y,Z [3*ncap] each during DBSCAN
+    int craw;        // float [ncap*5] compacted raw points of this frame
+    int assoc;       // int [ncap]
+    int par;         // int [3*ncap]
+    int cl;          // int [3*ncap]
+    int tracks;      // TrackRec [tcap]
+    int cinv;        // double [tcap][36]
+    int hx;          // double [tcap][6]
+    int logdet;      // double [tcap]
+    int ws;          // double [warps][kWarpScratch]
+    int misc;        // ints
+    int total;
+};
+
+__host__ __device__ inline SmemLayout make_layout(int ncap, int tcap) {
+    SmemLayout L;
+    int o = 0;
+    L.regionA = o; o += 9 * ncap * 8;
+    L.tracks = o;  o += tcap * (int)sizeof(TrackRec);
+    L.cinv = o;    o += tcap * 36 * 8;
+    L.hx = o;      o += tcap * 6 * 8;
+    L.logdet = o;  o += tcap * 8;
+    L.ws = o;      o += kStepWarps * kWarpScratch * 8;
+    L.craw = o;    o += ncap * 5 * 4;
+    L.assoc = o;   o += ncap * 4;
+    L.par = o;     o += 3 * ncap * 4;
+    L.cl = o;      o += 3 * ncap * 4;
+    L.misc = o;    o += 128 * 4;
+    L.total = o;
+    return L;
+}
+
+int step_smem_bytes(int ncap, int tcap) { return make_layout(ncap, tcap).total; }
+
+// misc int slots
+enum { kM = 0, kNFree = 1, kU = 2, kUPhys = 3, kScan = 4 /* .. +kStepWarps+1 */, kOrder = 16 /* .. +32 */,
+       kFree = 48 /* .. +32 */ };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// Push the rows i (ascending) with sel(i) true into a ring frame of capacity `cap` rows.  One warp.
+// Returns the number of selected rows (may exceed cap; only the first cap are stored).
+template <class Sel>
+__device__ __forceinline__ int warp_push_rows(const float* craw, int M, float* dst, int cap, Sel sel, int lane) {
+    int base = 0;
+    for (int i0 = 0; i0 < M; i0 += 32) {
+        const int i = i0 + lane;
+        const bool f = i < M && sel(i);
+        const unsigned m = __ballot_sync(kFull, f);
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (f && pos < cap) {
+#pragma unroll
+            for (int k = 0; k < kRawCols; ++k) dst[pos * kRawCols + k] = craw[i * kRawCols + k];
+        }
+        base += __popc(m);
+    }
+    return base;
+}
+
+// PointCluster statistics (Tracking.py:120-136) of the rows selected by sel, from world columns wp[k][i].
+// All lanes return the same values.
+template <class Sel>
+__device__ __forceinline__ int warp_cluster_stats(const double* wp, int ncap, int M, Sel sel, int lane,
+                                                  double cen[6], double mn[6], double mx[6]) {
+    int n = 0;
+    double s[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { s[k] = 0.0; mn[k] = INFINITY; mx[k] = -INFINITY; }
+    for (int i = lane; i < M; i += 32) {
+        if (!sel(i)) continue;
+        ++n;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double v = wp[k * ncap + i];
+            s[k] += v;
+            mn[k] = fmin(mn[k], v);
+            mx[k] = fmax(mx[k], v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        s[k] = warp_sum(s[k]);
+        mn[k] = warp_min(mn[k]);
+        mx[k] = warp_max(mx[k]);
+        cen[k] = n > 0 ? s[k] / (double)n : 0.0;
+    }
+    return n;
+}
+
+__device__ __forceinline__ const float* uring_frame(const StepArgs& a, int s, int phys) {
+    return a.uring + ((size_t)s * kRing + phys) * (size_t)a.cfg.ncap * kRawCols;
+}
+
+__global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const DevConfig& c = a.cfg;
+    const int ncap = c.ncap, tcap = c.tcap;
+    const SmemLayout L = make_layout(ncap, tcap);
+    double* wp = reinterpret_cast<double*>(smem + L.regionA);
+    float* craw = reinterpret_cast<float*>(smem + L.craw);
+    int* assoc = reinterpret_cast<int*>(smem + L.assoc);
+    int* par = reinterpret_cast<int*>(smem + L.par);
+    int* cl = reinterpret_cast<int*>(smem + L.cl);
+    TrackRec* tr = reinterpret_cast<TrackRec*>(smem + L.tracks);
+    double* cinv = reinterpret_cast<double*>(smem + L.cinv);
+    double* hx = reinterpret_cast<double*>(smem + L.hx);
+    double* logdet = reinterpret_cast<double*>(smem + L.logdet);
+    double* wsall = reinterpret_cast<double*>(smem + L.ws);
+    int* misc = reinterpret_cast<int*>(smem + L.misc);
+
+    const int s = blockIdx.x;
+    if (s >= a.n_scenes) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* ws = wsall + warp * kWarpScratch;
+
+    SceneRec sc = a.scenes[s];           // every thread keeps a copy; thread 0 writes it back
+    const int off = a.offsets[s];
+    int N = a.offsets[s + 1] - off;
+    if (N > ncap) { N = ncap; sc.flags |= MMW_SCENE_POINT_OVERFLOW; }
+    const double dt = a.dt[s];
+
+    // ---- 1. load, transform, bounds filter, ordered compaction (Utils.py:379-432) ------------------
+    for (int i = tid; i < N * kRawCols; i += kStepThreads) craw[i] = a.pts[(size_t)off * kRawCols + i];
+    __syncthreads();
+    int M = 0;
+    for (int base = 0; base < N; base += kStepThreads) {
+        const int i = base + tid;
+        float r5[kRawCols];
+        double w[6];
+        bool keep = false;
+        if (i < N) {
+#pragma unroll
+            for (int k = 0; k < kRawCols; ++k) r5[k] = craw[i * kRawCols + k];
+            world_from_raw(c, r5[0], r5[1], r5[2], r5[3], w);
+            keep = (w[2] <= c.z_max) && (w[2] > 0.0) && (w[1] > 0.0);      // Utils.py:423-427
+        }
+        int tot;
+        const int pos = M + block_rank(keep, &tot, misc + kScan);   // syncs: all rows of this chunk are in registers
+        if (keep) {
+#pragma unroll
+            for (int k = 0; k < kRawCols; ++k) craw[pos * kRawCols + k] = r5[k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) wp[k * ncap + pos] = w[k];
+        }
+        M += tot;
+        __syncthreads();
+    }
+    for (int i = M + tid; i < N; i += kStepThreads) a.assoc_out[off + i] = -2;
+
+    sc.last_M = M;
+    sc.dbscan_n = -1;
+    if (M == 0) {                        // offline_main.py:55: the frame is skipped entirely (Q23)
+        if (tid == 0) {
+            sc.last_ran = 0;
+            a.scenes[s] = sc;
+            atomicAdd(&a.counters[1], (unsigned long long)N);
+        }
+        return;
+    }
+    sc.last_ran = 1;
+
+    // ---- 2. load this scene's track records -----------------------------------------------------------
+    const int T0 = sc.n_tracks;
+    {
+        const double* src = reinterpret_cast<const double*>(a.tracks + (size_t)s * tcap);
+        double* dst = reinterpret_cast<double*>(tr);
+        for (int i = tid; i < T0 * kTrackWords; i += kStepThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    // ---- 3. predict (Tracking.py:591-596, Q9) and gate matrices (Tracking.py:545-551) ---------------
+    for (int j = warp; j < T0; j += kStepWarps) {
+        TrackRec& t = tr[j];
+        warp_kf_predict(t.x, t.P, t.lifetime + dt, c.q_var, ws + kWsM1, lane);
+        double* C = ws + kWsA;
+        for (int e = lane; e < 36; e += 32) {
+            const int r = e / 6, q = e % 6;
+            double v = t.P[r * 9 + q];
+            if (r == q) { const double h = t.spread[r] / 2; v += h * h; }   // get_Rm (361-370)
+            C[e] = v + t.G[e];
+        }
+        if (lane < 6) hx[j * 6 + lane] = t.x[lane];
+        __syncwarp();
+        const double det = warp_inv6(C, cinv + j * 36, ws + kWsAug, lane);
+        if (lane == 0) logdet[j] = log(fabs(det));
+    }
+    __syncthreads();
+
+    // ---- 4. gating + association (Tracking.py:553-572, Q14) -------------------------------------------
+    for (int i = tid; i < M; i += kStepThreads) {
+        double p[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) p[k] = wp[k * ncap + i];
+        double best = INFINITY;
+        int bj = -1;
+        for (int j = 0; j < T0; ++j) {
+            double y[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) y[k] = p[k] - hx[j * 6 + k];
+            const double* Ci = cinv + j * 36;
+            double q = 0.0;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                double tb = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) tb += y[k] * Ci[k * 6 + b];
+                q += tb * y[b];
+            }
+            const double d2 = logdet[j] + q;
+            if (d2 < c.gate && d2 < best) { best = d2; bj = j; }
+        }
+        assoc[i] = bj;
+        a.assoc_out[off + i] = bj;
+    }
+    __syncthreads();
+
+    // ---- 5. per-track association (Tracking.py:648-653, 314-341) + unassigned push (Tracking.py:691) --
+    int U = 0, ring_rows = 0;
+    for (int g = warp; g <= T0; g += kStepWarps) {
+        if (g == T0) {
+            // BatchedData.add_frame(unassigned): drop the oldest frame when the ring is full
+            int phys;
+            if (sc.ring_n >= c.ring_size) { phys = sc.ring_head; }
+            else { phys = (sc.ring_head + sc.ring_n) % c.ring_size; }
+            float* dst = const_cast<float*>(uring_frame(a, s, phys));
+            const int u = warp_push_rows(craw, M, dst, ncap, [&](int i) { return assoc[i] < 0; }, lane);
+            if (lane == 0) { misc[kU] = u; misc[kUPhys] = phys; }
+            continue;
+        }
+        TrackRec& t = tr[g];
+        double cen[6], mn[6], mx[6];
+        auto sel = [&](int i) { return assoc[i] == g; };
+        const int n = warp_cluster_stats(wp, ncap, M, sel, lane, cen, mn, mx);
+        if (n == 0) {
+            if (lane == 0) t.lifetime += dt;                     // update_lifetime(dt) (400-407)
+            continue;
+        }
+        // dispersion matrix about the centroid (population covariance, _get_D 270-290)
+        double acc[21];
+#pragma unroll
+        for (int p = 0; p < 21; ++p) acc[p] = 0.0;
+        for (int i = lane; i < M; i += 32) {
+            if (!sel(i)) continue;
+            double d[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) d[k] = wp[k * ncap + i] - cen[k];
+            int p = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int q = r; q < 6; ++q) acc[p++] += d[r] * d[q];
+        }
+#pragma unroll
+        for (int p = 0; p < 21; ++p) acc[p] = warp_sum(acc[p]) / (double)n;
+        // ring push (first 64 associated rows in input order are what format_single_frame can see)
+        int phys;
+        if (t.ring_n >= c.ring_size) { phys = t.ring_head; }
+        else { phys = (t.ring_head + t.ring_n) % c.ring_size; }
+        float* dst = a.track_ring + (((size_t)s * tcap + t.slot) * kRing + phys) * (kFeatPts * kRawCols);
+        warp_push_rows(craw, M, dst, kFeatPts, sel, lane);
+        __syncwarp();
+        if (lane == 0) {
+            if (t.ring_n >= c.ring_size) t.ring_head = (t.ring_head + 1) % c.ring_size;
+            else t.ring_n += 1;
+            t.ring_cnt[phys] = n < kFeatPts ? n : kFeatPts;
+            t.lifetime = 0.0;
+            t.point_num = n;
+            t.is_static = sqrt(cen[3] * cen[3] + cen[4] * cen[4] + cen[5] * cen[5]) < c.vel_thres ? 1 : 0;
+            if (c.enable_est) {                                  // _estimate_point_num (232-244)
+                if ((double)n > t.n_est) t.n_est = (double)n;
+                else t.n_est = (1 - c.a_n) * t.n_est + c.a_n * (double)n;
+            } else {
+                t.n_est = (double)(n > c.est_pointnum ? n : c.est_pointnum);
+            }
+        }
+        if (lane < 6) {                                          // _estimate_measurement_spread (246-268)
+            const int m = lane;
+            t.centroid[m] = cen[m];
+            t.minv[m] = mn[m];
+            t.maxv[m] = mx[m];
+            double spread = mx[m] - mn[m];
+            if (n != 1) spread = spread * (double)(n + 1) / (double)(n - 1);
+            spread = fmin(2 * c.spread_lim[m], spread);
+            spread = fmax(c.spread_lim[m], spread);
+            if (spread > t.spread[m]) t.spread[m] = spread;
+            else t.spread[m] = (1.0 - c.a_spr) * t.spread[m] + c.a_spr * spread;
+        }
+        __syncwarp();
+        {                                                        // _estimate_group_disp_matrix (292-297)
+            const double al = (double)n / t.n_est;
+            for (int e = lane; e < 36; e += 32) {
+                int r = e / 6, q = e % 6;
+                if (r > q) { const int tmp = r; r = q; q = tmp; }
+                const int p = r * 6 - (r * (r - 1)) / 2 + (q - r);
+                double dv = 0.0;
+#pragma unroll
+                for (int pp = 0; pp < 21; ++pp) dv = (pp == p) ? acc[pp] : dv;
+                t.G[e] = (1 - al) * t.G[e] + al * dv;
+            }
+        }
+        if (lane == 0) ring_rows += (n < kFeatPts ? n : kFeatPts);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const int u = misc[kU], phys = misc[kUPhys];
+        U = u;
+        if (sc.ring_n >= c.ring_size) sc.ring_head = (sc.ring_head + 1) % c.ring_size;
+        else sc.ring_n += 1;
+        sc.ring_cnt[phys] = u;
+    }
+
+    // ---- 6. maintenance (Tracking.py:513-528, Q16): drop timed-out tracks, keep list order -----------
+    if (tid == 0) {
+        int nk = 0, nf = 0;
+        for (int k = 0; k < T0; ++k) {
+            const double lim = tr[k].is_static ? c.life_sta : c.life_dyn;
+            if (tr[k].lifetime > lim) misc[kFree + nf++] = tr[k].slot;     // INACTIVE: dropped from the list
+            else misc[kOrder + nk++] = k;
+        }
+        misc[kM] = nk;
+        misc[kNFree] = nf;
+    }
+    __syncthreads();
+    const int T1 = misc[kM];
+    for (int k = 0; k < misc[kNFree]; ++k) sc.slot_mask &= ~(1u << misc[kFree + k]);
+
+    // ---- 7. update every surviving track (Tracking.py:598-603, 387-398; Q11-Q13) ---------------------
+    for (int k = warp; k < T1; k += kStepWarps) {
+        TrackRec& t = tr[misc[kOrder + k]];
+        // _get_Rc (299-312): Rm/N + ((N_est - N)/((N_est - 1) N)) * group_disp_est
+        double* Rc = cinv + misc[kOrder + k] * 36;   // the gate matrices are dead by now: reuse as R storage
+        const double Nn = (double)t.point_num;
+        const double coef = (t.n_est - Nn) / ((t.n_est - 1.0) * Nn);
+        for (int e = lane; e < 36; e += 32) {
+            const int r = e / 6, q = e % 6;
+            double rm = 0.0;
+            if (r == q) { const double h = t.spread[r] / 2; rm = h * h; }
+            Rc[e] = rm / Nn + coef * t.G[e];
+        }
+        __syncwarp();
+        warp_kf_update(t.x, t.P, t.centroid, Rc, t.lifetime == 0.0, c.nudge_thres, c.nudge_gain, ws, lane);
+    }
+    __syncthreads();
+
+    // ---- 8. DBSCAN over the fused global ring (Tracking.py:693-700) -----------------------------------
+    int B = 0;
+    int fcnt[kRing], fphys[kRing];
+    for (int f = 0; f < kRing; ++f) {
+        fphys[f] = (sc.ring_head + f) % c.ring_size;
+        fcnt[f] = f < sc.ring_n ? sc.ring_cnt[fphys[f]] : 0;
+        B += fcnt[f];
+    }
+    int ncl = 0;
+    double* X = wp;
+    double* Y = wp + 3 * ncap;
+    double* Z = wp + 6 * ncap;
+    const bool run_db = B > 0 && T1 < c.tr_max_tracks;
+    if (run_db) {
+        // fused cloud, oldest frame first; world y/z recomputed from the raw rows (x is unchanged)
+        int b0 = 0;
+        for (int f = 0; f < kRing; ++f) {
+            const float* src = uring_frame(a, s, fphys[f]);
+            for (int i = tid; i < fcnt[f]; i += kStepThreads) {
+                const float x = src[i * kRawCols + 0], y = src[i * kRawCols + 1], z = src[i * kRawCols + 2];
+                double yw, zw;
+                world_yz(c, (double)y, (double)z, yw, zw);
+                X[b0 + i] = (double)x; Y[b0 + i] = yw; Z[b0 + i] = zw;
+            }
+            b0 += fcnt[f];
+        }
+        __syncthreads();
+        ncl = dbscan_block(c, X, Y, Z, B, c.db_eps, c.db_min_samples, par, cl, misc + kScan);
+        sc.dbscan_n = B;
+        if (a.labels_out != nullptr)
+            for (int b = tid; b < B; b += kStepThreads) a.labels_out[(size_t)s * 3 * ncap + b] = cl[b];
+    }
+
+    // ---- 9. spawn one track per cluster, in label order (Tracking.py:576-589, 210-230; Q7, Q20) ------
+    int T2 = T1;
+    if (ncl > 0) {
+        if (T1 + ncl > tcap) { ncl = tcap - T1; sc.flags |= MMW_SCENE_TRACK_OVERFLOW; }
+        // smem record indices not used by survivors, physical slots not in use (all threads compute the same)
+        unsigned used = 0;
+        for (int k = 0; k < T1; ++k) used |= 1u << misc[kOrder + k];
+        int newidx[kMaxTcap], newslot[kMaxTcap];
+        {
+            const unsigned capmask = tcap >= 32 ? 0xffffffffu : ((1u << tcap) - 1u);
+            unsigned fr = ~used & capmask, fs = ~sc.slot_mask & capmask;
+            for (int q = 0; q < ncl; ++q) {
+                newidx[q] = __ffs(fr) - 1; fr &= fr - 1;
+                newslot[q] = __ffs(fs) - 1; fs &= fs - 1;
+                sc.slot_mask |= 1u << newslot[q];
+            }
+        }
+        for (int q = warp; q < ncl; q += kStepWarps) {
+            TrackRec& t = tr[newidx[q]];
+            // cluster statistics over the 6 world columns, recomputed from the ring's raw rows
+            int n = 0;
+            double sacc[6], mn[6], mx[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { sacc[k] = 0.0; mn[k] = INFINITY; mx[k] = -INFINITY; }
+            int b0 = 0;
+            float* dst = a.track_ring + (((size_t)s * tcap + newslot[q]) * kRing + 0) * (kFeatPts * kRawCols);
+            int stored = 0;
+            for (int f = 0; f < kRing; ++f) {
+                const float* src = uring_frame(a, s, fphys[f]);
+                for (int i0 = 0; i0 < fcnt[f]; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool in = i < fcnt[f] && cl[b0 + i] == q;
+                    float r5[kRawCols];
+                    if (in) {
+#pragma unroll
+                        for (int k = 0; k < kRawCols; ++k) r5[k] = src[i * kRawCols + k];
+                        double w[6];
+                        world_from_raw(c, r5[0], r5[1], r5[2], r5[3], w);
+                        ++n;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) {
+                            sacc[k] += w[k]; mn[k] = fmin(mn[k], w[k]); mx[k] = fmax(mx[k], w[k]);
+                        }
+                    }
+                    const unsigned m = __ballot_sync(kFull, in);
+                    const int pos = stored + __popc(m & ((1u << lane) - 1u));
+                    if (in && pos < kFeatPts) {
+#pragma unroll
+                        for (int k = 0; k < kRawCols; ++k) dst[pos * kRawCols + k] = r5[k];
+                    }
+                    stored += __popc(m);
+                }
+                b0 += fcnt[f];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
+            double cen[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                cen[k] = warp_sum(sacc[k]) / (double)n;
+                mn[k] = warp_min(mn[k]);
+                mx[k] = warp_max(mx[k]);
+            }
+            for (int e = lane; e < 81; e += 32) t.P[e] = (e / 9 == e % 9) ? c.p_init : 0.0;
+            for (int e = lane; e < 36; e += 32) t.G[e] = (e / 6 == e % 6) ? c.g_init : 0.0;
+            if (lane < 9) t.x[lane] = 0.0;
+            __syncwarp();
+            if (lane < 6) {
+                t.x[lane] = cen[lane];
+                t.centroid[lane] = cen[lane];
+                t.minv[lane] = mn[lane];
+                t.maxv[lane] = mx[lane];
+                t.spread[lane] = 0.0;
+            }
+            if (lane == 0) {
+                t.n_est = 0.0;
+                t.lifetime = 0.0;
+                t.id = sc.next_id + q;
+                t.point_num = n;
+                t.is_static = sqrt(cen[3] * cen[3] + cen[4] * cen[4] + cen[5] * cen[5]) < c.vel_thres ? 1 : 0;
+                t.slot = newslot[q];
+                t.ring_n = 1;
+                t.ring_head = 0;
+                t.ring_cnt[0] = n < kFeatPts ? n : kFeatPts;
+                t.ring_cnt[1] = 0;
+                t.ring_cnt[2] = 0;
+                t.pad = 0;
+                misc[kOrder + T1 + q] = newidx[q];
+            }
+            // keypoints = MODEL_DEFAULT_POSTURE until the first inference (Tracking.py:221, Q25)
+            float* kp = a.keypoints + ((size_t)s * tcap + newslot[q]) * kKp;
+            for (int e = lane; e < kKp; e += 32) kp[e] = a.default_posture[e];
+        }
+        sc.next_id += ncl;
+        T2 = T1 + ncl;
+        sc.ring_n = 0;                   // batch.clear() (Tracking.py:699-700, Q8)
+        sc.ring_head = 0;
+        sc.ring_cnt[0] = sc.ring_cnt[1] = sc.ring_cnt[2] = 0;
+    }
+    __syncthreads();
+
+    // ---- 10. write back: track records in list order, scene record, counters ---------------------------
+    {
+        double* dstbase = reinterpret_cast<double*>(a.tracks + (size_t)s * tcap);
+        for (int i = tid; i < T2 * kTrackWords; i += kStepThreads) {
+            const int k = i / kTrackWords, wd = i % kTrackWords;
+            dstbase[i] = reinterpret_cast<const double*>(tr + misc[kOrder + k])[wd];
+        }
+    }
+    // ring rows written by all warps of this CTA
+    if (lane == 0 && ring_rows) atomicAdd(&a.counters[6], (unsigned long long)ring_rows);
+    if (tid == 0) {
+        sc.n_tracks = T2;
+        a.scenes[s] = sc;
+        atomicAdd(&a.counters[0], 1ull);
+        atomicAdd(&a.counters[1], (unsigned long long)N);
+        atomicAdd(&a.counters[2], (unsigned long long)M);
+        atomicAdd(&a.counters[3], (unsigned long long)U);
+        if (run_db) atomicAdd(&a.counters[4], (unsigned long long)B);
+        atomicAdd(&a.counters[5], (unsigned long long)T2);
+    }
+}
+
+cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
+    const int smem = step_smem_bytes(a.cfg.ncap, a.cfg.tcap);
+    static int configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    step_kernel<<<a.n_scenes, kStepThreads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace mmw

@@ -1,0 +1,258 @@
+"""Parity of the CUDA path (called through the C ABI, include/mmw.h) with the numpy oracle and with the
+golden traces recorded from the reference.  Decisions (filter, labels, gates, ids) are compared bit-exactly;
+float64 state to STATE_RTOL; joints to 1 mm."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+from helpers import KEYPOINT_ATOL, compare_frame, oracle_config
+from mmwave_msc_b200 import pose_weights as pw, synth
+from mmwave_msc_b200.batched import BatchedTracker, default_config
+from oracle import mmw_oracle as mo, trace_io
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- a1: preprocessing --------------------------------------------------------------------------------
+def test_preprocess_bit_exact():
+    rng = np.random.default_rng(1)
+    raw = np.concatenate([synth.gen_scene(3, 4).frames[k] for k in range(4)])
+    edge = np.array([[0, 0, 0, .3, 7],            # r == 0 (Utils.py:387-390)
+                     [1, -1, 0, .1, 5],           # fails y' > 0
+                     [.5, 3, -.4, .62, 120],      # survey known answer
+                     [0, 2, 0.8, 0, 1],           # near the z' <= 2.5 bound
+                     [0, 1, -2.5, 0, 1]], np.float32)
+    rnd = rng.normal(0, 3, size=(5000, 5)).astype(np.float32)
+    pts = np.concatenate([raw, edge, rnd]).astype(np.float32)
+    bt = BatchedTracker(1)
+    world, keep = bt.preprocess(pts)
+    ow, ok = mo.normalize_points(pts.astype(np.float64))
+    np.testing.assert_array_equal(keep, ok)
+    np.testing.assert_array_equal(world[keep], ow)          # bit-exact: same float64 operations, no FMA contraction
+
+
+# ---- a2/a3: DBSCAN ------------------------------------------------------------------------------------
+def test_dbscan_stage_matches_oracle():
+    rng = np.random.default_rng(2)
+    clouds = []
+    for n, k in ((0, 1), (1, 1), (34, 1), (35, 1), (90, 2), (400, 3), (600, 4), (768, 5)):
+        c = np.concatenate([rng.normal([rng.uniform(-2, 2), rng.uniform(1, 4), 1.0], [0.12, 0.12, 0.4],
+                                       size=(n // k if k else 0, 3)) for _ in range(k)] +
+                           [rng.uniform([-2.5, 0.3, 0], [2.5, 4.5, 2.5], size=(n - (n // k) * k, 3))]) if n else \
+            np.zeros((0, 3))
+        clouds.append(c)
+    # a cloud that mixes dense blobs and uniform clutter
+    clouds.append(np.concatenate([rng.normal([0, 2, 1], [0.12, 0.12, 0.4], size=(150, 3)),
+                                  rng.uniform([-2.5, 0.3, 0], [2.5, 4.5, 2.5], size=(300, 3))]))
+    bt = BatchedTracker(1, max_points=256)
+    got = bt.dbscan(clouds)
+    for c, g in zip(clouds, got):
+        pts8 = np.zeros((len(c), 8)); pts8[:, :3] = c
+        np.testing.assert_array_equal(g, mo.dbscan_labels(pts8))
+    # border/tie semantics on the hand-made cloud of the oracle test
+    p = np.zeros((10, 3)); p[:, 0] = [0.35, 0.55, 0.6, 0.65, 0.7, 0.0, 0.05, 0.1, 0.15, 5.0]
+    assert bt.dbscan([p], eps=0.05, min_samples=4)[0].tolist() == [0, 0, 0, 0, 0, 1, 1, 1, 1, -1]
+
+
+# ---- a6/a7: Kalman ------------------------------------------------------------------------------------
+def _rand_spd(rng, n, scale=0.1):
+    a = rng.normal(size=(n, n))
+    return scale * (a @ a.T / n + np.eye(n))
+
+
+def test_kalman_predict_update_stage():
+    rng = np.random.default_rng(3)
+    n = 37
+    x = rng.normal(size=(n, 9)); P = np.stack([_rand_spd(rng, 9) for _ in range(n)])
+    dt = rng.uniform(0.05, 3.5, size=n)
+    bt = BatchedTracker(1)
+    gx, gP = bt.kalman_predict(x, P, dt)
+    for i in range(n):
+        F, Q = mo.kf_F(dt[i]), mo.kf_Q(dt[i])
+        np.testing.assert_allclose(gx[i], F @ x[i], rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(gP[i], (F @ P[i]) @ F.T + Q, rtol=1e-13, atol=1e-15)
+    z = rng.normal(size=(n, 6)); R = np.stack([_rand_spd(rng, 6, 0.01) for _ in range(n)])
+    life0 = rng.integers(0, 2, size=n).astype(np.uint8)
+    ux, uP = bt.kalman_update(x, P, z, R, life0)
+    cfg = mo.OracleConfig()
+    for i in range(n):
+        t = mo.Track(np.zeros((1, 8)), 0, cfg)
+        t.x, t.P, t.centroid, t.lifetime = x[i].copy(), P[i].copy(), z[i], 0.0 if life0[i] else 0.5
+        t.Rc = lambda R_=R[i]: R_
+        t.update()
+        np.testing.assert_allclose(ux[i], t.x, rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(uP[i], t.P, rtol=1e-10, atol=1e-13)
+
+
+def test_gate_stage():
+    rng = np.random.default_rng(4)
+    T, M = 5, 300
+    hx = rng.normal(0, 1, size=(T, 6)); Cm = np.stack([_rand_spd(rng, 6, 0.3) for _ in range(T)])
+    pts = hx[rng.integers(0, T, size=M)] + rng.normal(0, 0.6, size=(M, 6))
+    bt = BatchedTracker(1)
+    d2, assoc = bt.gate(pts, hx, Cm)
+    ref = np.stack([np.log(abs(np.linalg.det(Cm[j]))) + np.einsum("ia,ab,ib->i", pts - hx[j], np.linalg.inv(Cm[j]),
+                                                                  pts - hx[j]) for j in range(T)], axis=1)
+    np.testing.assert_allclose(d2, ref, rtol=1e-11, atol=1e-12)
+    exp = mo.associate_from_scores(ref, 4.5)
+    margin = np.abs(ref - 4.5).min(axis=1)
+    assert np.array_equal(assoc[margin > 1e-9], exp[margin > 1e-9])
+    assert (assoc >= 0).sum() > 20 and (assoc < 0).sum() > 20
+
+
+# ---- a15/a16: pose CNN --------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [pw.VARIANT_3D, pw.VARIANT_2D])
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_pose_stage(variant, tensor_cores):
+    rng = np.random.default_rng(5)
+    fb = 2 if variant == pw.VARIANT_3D else 0
+    W = pw.make_pose_weights(variant)
+    n = 200
+    shape = (n, 3, 8, 8, 5) if fb == 2 else (n, 8, 8, 5)
+    feats = np.zeros((n, (fb + 1) * 64, 5), np.float32)
+    for i in range(n):                       # 20-64 real rows per frame + zero pads, like format_single_frame
+        for f in range(fb + 1):
+            k = int(rng.integers(20, 65))
+            rows = np.zeros((64, 5), np.float32)
+            rows[:k, 0] = rng.normal(0, 0.15, k); rows[:k, 1] = rng.normal(0, 0.15, k)
+            rows[:k, 2] = rng.normal(1.0, 0.4, k); rows[:k, 3] = rng.normal(0, 0.3, k)
+            rows[:k, 4] = (np.floor(rng.gamma(0.5, 54.0, k)) + 1 - 27.0187) / 70.351
+            feats[i, f * 64:(f + 1) * 64] = rows[np.argsort(rows[:, 0], kind="stable")]
+    feats = feats.reshape(shape)
+    bt = BatchedTracker(64, max_tracks=8, config=default_config(frames_batch=fb))
+    bt.load_pose_weights(W, variant)
+    bt.set_dense_path(tensor_cores)
+    got = bt.pose(feats)
+    ref = mo.pose_forward(W, feats, np.float64)
+    err = np.abs(got - ref).max()
+    assert err < (KEYPOINT_ATOL if tensor_cores else 1e-4), "max joint error %.3g m" % err
+    assert np.abs(ref).mean() > 0.05         # the comparison is not vacuous
+
+
+# ---- a11: full sequences, free-running ----------------------------------------------------------------
+def _run_sequence(scene_ids, n_frames, spec, cfg, weights=None, tensor_cores=True, max_points=256, max_tracks=8,
+                  every=1):
+    batches = synth.gen_batch(scene_ids, n_frames, spec)
+    ocfg = oracle_config(cfg)
+    oracles = [mo.SceneOracle(ocfg, pose_weights=weights, pose_dtype=np.float64) for _ in scene_ids]
+    bt = BatchedTracker(len(scene_ids), max_points=max_points, max_tracks=max_tracks, config=cfg)
+    if weights is not None:
+        bt.load_pose_weights(weights)
+        bt.set_dense_path(tensor_cores)
+    for f, b in enumerate(batches):
+        bt.step(b.points, b.offsets, b.dt, pose=weights is not None, record_labels=True)
+        recs = [o.step(b.points[b.offsets[s]:b.offsets[s + 1]], b.dt[s]) for s, o in enumerate(oracles)]
+        if f % every == 0 or f == n_frames - 1:
+            compare_frame(bt, recs, b.offsets, "frame %d" % f, labels=bt.labels(),
+                          check_keypoints=weights is not None,
+                          pose_rows=bt.pose_rows() if weights is not None else None)
+    assert not bt.status().any()
+    return bt
+
+
+def test_sequences_default_config_with_pose():
+    W = pw.make_pose_weights(pw.VARIANT_3D)
+    _run_sequence(list(range(12)), 45, synth.SceneSpec(), default_config(), weights=W)
+
+
+def test_sequences_churn_tracks_time_out_and_ids_reissued():
+    spec = synth.SceneSpec(clutter_frac=0.02, leave_prob=0.5, enter_prob=0.5, clutter_box=(2.2, 2.5, 4.2, 4.5),
+                           people_min=2, people_max=4)
+    bt = _run_sequence([304, 308, 311, 321], 150, spec, default_config())
+    _, nid, _ = bt.summary()
+    _, nt = bt.tracks()
+    assert (nid > nt).any()                   # at least one track was dropped
+
+
+def test_sequences_2d_net_frames_batch_0():
+    W = pw.make_pose_weights(pw.VARIANT_2D)
+    _run_sequence([1, 2, 5], 25, synth.SceneSpec(), default_config(frames_batch=0), weights=W)
+
+
+def test_sequence_dense_config_c3():
+    _run_sequence([7, 8], 10, synth.SceneSpec.dense(), default_config(tr_max_tracks=10), max_points=1024,
+                  max_tracks=16)
+
+
+def test_empty_and_ragged_frames():
+    """Scenes with no points at all, frames emptied by the filter (Q23), and a scene that only ever sees noise."""
+    cfg = default_config()
+    bt = BatchedTracker(4, config=cfg)
+    oracles = [mo.SceneOracle(oracle_config(cfg)) for _ in range(4)]
+    sc = synth.gen_scene(1, 12)
+    rng = np.random.default_rng(9)
+    for f in range(12):
+        parts = [sc.frames[f],
+                 np.zeros((0, 5), np.float32),                                             # empty input
+                 np.array([[1, -1, 0, .1, 5], [0, 0, 0, .2, 3]], np.float32),              # all filtered out
+                 rng.uniform([-2, 0.5, -1, -1, 1], [2, 4, 0.5, 1, 50], size=(int(rng.integers(1, 40)), 5)).astype(
+                     np.float32)]
+        if f % 5 == 4:
+            parts[0] = np.zeros((0, 5), np.float32)                                        # a dropped frame
+        offsets = np.zeros(5, np.int32); offsets[1:] = np.cumsum([len(p) for p in parts])
+        pts = np.concatenate(parts)
+        dt = np.full(4, 0.083)
+        bt.step(pts, offsets, dt, pose=False, record_labels=True)
+        recs = [o.step(p, 0.083) for o, p in zip(oracles, parts)]
+        compare_frame(bt, recs, offsets, "frame %d" % f, labels=bt.labels())
+
+
+# ---- golden traces recorded from the reference's own Tracking.py / Utils.py --------------------------
+@pytest.mark.parametrize("case", golden_cases())
+def test_against_reference_golden_trace(case):
+    d = np.load(os.path.join(GOLDEN, case + ".npz"))
+    g = trace_io.unpack(d)
+    mt = int(d["max_tracks"])
+    dense = max(len(f) for f in g["frames"]) > 256
+    bt = BatchedTracker(1, max_points=1024 if dense else 256, max_tracks=16 if dense else 8,
+                        config=default_config(tr_max_tracks=mt))
+    bt.load_pose_weights(pw.make_pose_weights(pw.VARIANT_3D))
+    for f, (fr, dt, rec) in enumerate(zip(g["frames"], g["dts"], g["recs"])):
+        offsets = np.array([0, len(fr)], np.int32)
+        want_pose = rec["features"] is not None
+        bt.step(fr, offsets, np.array([dt]), pose=want_pose, record_labels=True)
+        compare_frame(bt, [rec], offsets, "%s frame %d" % (case, f), labels=bt.labels(),
+                      pose_rows=bt.pose_rows() if want_pose else None)
+
+
+# ---- size-independent properties at the benchmark's full size ----------------------------------------
+def test_full_size_c2_permutation_and_determinism():
+    S, F = 1024, 6
+    ids = list(range(S))
+    batches = synth.gen_batch(ids, F)
+    W = pw.make_pose_weights(pw.VARIANT_3D)
+
+    def run(order):
+        bt = BatchedTracker(S)
+        bt.load_pose_weights(W)
+        for b in batches:
+            parts = [b.points[b.offsets[s]:b.offsets[s + 1]] for s in order]
+            offsets = np.zeros(S + 1, np.int32); offsets[1:] = np.cumsum([len(p) for p in parts])
+            bt.step(np.concatenate(parts), offsets, b.dt[order], pose=True)
+        tr, nt = bt.tracks()
+        return tr, nt, bt.status()
+
+    ident = np.arange(S)
+    perm = np.random.default_rng(0).permutation(S)
+    tr0, nt0, st0 = run(ident)
+    tr1, nt1, _ = run(ident)
+    trp, ntp, _ = run(perm)
+    assert not st0.any()
+    assert nt0.sum() > S                       # tracks exist
+    assert tr0.tobytes() == tr1.tobytes()      # run-to-run bit-identical
+    inv = np.argsort(perm)
+    assert np.array_equal(nt0, ntp[inv])
+    assert tr0.tobytes() == trp[inv].tobytes() # a scene's result does not depend on its place in the batch
+    # spot-check 8 scenes against the oracle
+    pick = [0, 17, 233, 511, 512, 640, 901, 1023]
+    oracles = {s: mo.SceneOracle(pose_weights=W) for s in pick}
+    for b in batches:
+        recs = {s: oracles[s].step(b.points[b.offsets[s]:b.offsets[s + 1]], b.dt[s]) for s in pick}
+    for s in pick:
+        assert nt0[s] == len(recs[s]["tracks"])
+        for k, t in enumerate(recs[s]["tracks"]):
+            assert tr0[s, k]["id"] == t["id"]
+            np.testing.assert_allclose(tr0[s, k]["x"], t["x"], rtol=1e-8, atol=1e-10)
+            np.testing.assert_allclose(tr0[s, k]["keypoints"], t["keypoints"], rtol=0, atol=KEYPOINT_ATOL)
