@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the per-frame radar perception path (cluster + track + pose) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one radar frame for every resident scene: Utils.normalize_data -> TrackBuffer.track ->
+TrackBuffer.estimate_posture of the reference (offline_main.py:45-60), S scenes at once per GPU.
+Workload = BASELINE config C2 per GPU (1024 concurrent synthetic IWR1443-shaped scenes, ~200 pts/frame, up to 4
+tracks each, reference default constants => the 3-frame 3-D pose net); with N GPUs the scenes are sharded
+1024 per GPU (N=8 is BASELINE config C5, 8192 scenes), no inter-GPU traffic in the hot loop, one NCCL
+all-gather of the packed results at the end.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SCENES_PER_GPU = 1024
+PRIME_FRAMES = 12          # untimed frames before warm-up so that tracks exist (start-up DBSCAN is not steady state)
+METRIC = "radar frames/sec (cluster+track+pose)"
+UNIT = "scene-frames/s"
+WORKLOAD = ("C2: %d concurrent synthetic IWR1443 scenes per GPU, ~200 pts/frame (U{160..240}), 1-4 people, "
+            "12 Hz cfg, reference default constants (FB_FRAMES_BATCH=2 -> 3x8x8x5 pose net)" % SCENES_PER_GPU)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "src": "measured (MEASURED_PEAKS.json; bf16 = sustained, kernel timed inside a long step)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+def algorithmic_bytes(cnt: np.ndarray, nfr: int) -> float:
+    """SURVEY.md section 8(d) per scene-frame formula summed from the device counters:
+    20 N + 4 M + 32 U + 32 Bf[dbscan ran] + sum_tracks (2*624 + 20 min(A_j,64) + nfr*64*20 + 228) + 8."""
+    frames, N, M, U, Bf, T, rows, pose = (float(x) for x in cnt)
+    return 20 * N + 4 * M + 32 * U + 32 * Bf + T * (2 * 624 + nfr * 64 * 20 + 228) + 20 * rows + 8 * frames
+
+
+def cpu_port_run(scene_ids, n_frames, with_pose=True):
+    """The oracle port (numpy restatement of the reference path) on the given scenes; returns scene-frames, seconds."""
+    from mmwave_msc_b200 import pose_weights as pw, synth
+    from oracle import mmw_oracle as mo
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+    W = pw.make_pose_weights(pw.VARIANT_3D) if with_pose else None
+    scenes = [synth.gen_scene(s, n_frames) for s in scene_ids]
+    t0 = time.perf_counter()
+    n = 0
+    for sc in scenes:
+        so = mo.SceneOracle(pose_weights=W, pose_dtype=np.float32)
+        for fr, dt in zip(sc.frames, sc.dts()):
+            so.step(fr, dt)
+            n += 1
+    return n, time.perf_counter() - t0
+
+
+def _cpu_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    return cpu_port_run(*args)
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the CPU implementation of the path (oracle port; the reference itself is pure Python
+    that cannot travel to this box) on all host cores, independent scenes per process."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    frames = 30
+    per_proc = 2
+    vals = []
+    for step in range(args.warmup + args.steps):
+        jobs = [([10_000 + step * 1000 + p * per_proc + i for i in range(per_proc)], frames, True) for p in range(procs)]
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
+        wall = max(r[1] for r in res)
+        if step >= args.warmup:
+            vals.append(sum(r[0] for r in res) / wall)
+    v = float(np.mean(vals)) if vals else 0.0
+    sample = "%d processes x %d scenes x %d frames per step (C2-shaped scenes, pose CNN in torch-CPU fp32)" % (
+        procs, per_proc, frames)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * procs * per_proc * frames / v if v else None,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--scenes", type=int, default=SCENES_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-path", default="tc", choices=["tc", "simt"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mmwave_msc_b200 import _lib, pose_weights as pw, synth
+    from mmwave_msc_b200.batched import BatchedTracker
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    S = args.scenes
+    W_, K = args.warmup, args.steps
+    n_frames = PRIME_FRAMES + 2 * (W_ + K) + K      # device-timed pass, e2e pass, per-kernel profile pass
+    ids = [rank * S + i for i in range(S)]
+    batches = synth.gen_batch(ids, n_frames)
+
+    bt = BatchedTracker(S, max_points=256, max_tracks=8, device=local)
+    weights = pw.make_pose_weights(pw.VARIANT_3D)
+    bt.load_pose_weights(weights)
+    bt.set_dense_path(args.dense_path == "tc")
+    stream = torch.cuda.ExternalStream(bt.stream, device=local)
+
+    # inputs resident in HBM for the device-timed pass; pinned host copies for the end-to-end pass
+    dev = []
+    for b in batches:
+        dev.append((torch.from_numpy(b.points).cuda(), torch.from_numpy(b.offsets).cuda(), torch.from_numpy(b.dt).cuda()))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_dev(f, pose=True):
+        p, o, d = dev[f]
+        bt.step_device(p.data_ptr(), o.data_ptr(), d.data_ptr(), p.shape[0], pose=pose)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    f = 0
+    for _ in range(PRIME_FRAMES):
+        step_dev(f); f += 1
+    for _ in range(W_):
+        step_dev(f); f += 1
+    bt.sync()
+    bt.counters(reset=True)
+    launches0 = bt.launch_count()
+
+    # ---- device-timed pass: K steps, inputs resident in HBM, L2 flushed between steps ----------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for k in range(K):
+        with torch.cuda.stream(stream):
+            flush.fill_(k & 0xff)            # evict L2 between timed iterations (not inside the timed interval)
+            ev[k][0].record(stream)
+        step_dev(f); f += 1
+        ev[k][1].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = float(step_ms.sum())
+    launches = bt.launch_count() - launches0
+    cnt = bt.counters(reset=True)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * S * K / (total_ms_max / 1e3)
+
+    # ---- end-to-end pass through the public API: pinned host inputs, result read back every step ----------
+    res_dev = torch.empty(S * bt.tcap * _lib.RESULT_FLOATS, dtype=torch.float32, device="cuda")
+    res_host = torch.empty(S * bt.tcap * _lib.RESULT_FLOATS, dtype=torch.float32).pin_memory()
+    pinned = []
+    for b in batches[f:f + W_ + K]:
+        pp = torch.from_numpy(b.points).pin_memory()
+        po = torch.from_numpy(b.offsets).pin_memory()
+        pd = torch.from_numpy(b.dt).pin_memory()
+        pinned.append((pp.numpy(), po.numpy(), pd.numpy()))
+
+    def step_e2e(i):
+        p, o, d = pinned[i]
+        bt.step(p, o, d, pose=True)
+        bt.pack_results(res_dev.data_ptr())
+        with torch.cuda.stream(stream):
+            res_host.copy_(res_dev, non_blocking=True)
+        bt.sync()
+        return p.nbytes + o.nbytes + d.nbytes
+
+    for i in range(W_):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = 0
+    for i in range(W_, W_ + K):
+        h2d += step_e2e(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    f += W_ + K
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * S * K / float(t.item())
+
+    # ---- per-kernel durations (CUDA events on the library's stream around every launch) --------------------
+    kern = bt.profile_kernels(lambda i: step_dev(f + i), K) if hasattr(bt, "profile_kernels") else {}
+
+    # ---- final result gather: the only collective of the path (NCCL all-gather over NVLink) ---------------
+    bt.pack_results(res_dev.data_ptr())
+    bt.sync()
+    if world > 1:
+        gathered = torch.empty(world * res_dev.numel(), dtype=torch.float32, device="cuda")
+        dist.all_gather_into_tensor(gathered, res_dev)
+        torch.cuda.synchronize()
+
+    if rank == 0:
+        pk = peaks()
+        nfr = 3
+        alg = algorithmic_bytes(cnt, nfr)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+            "ms_per_step": total_ms_max / K, "p50_ms_per_step": float(np.median(step_ms)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "scenes_per_gpu": S, "max_points": 256, "max_tracks": 8,
+                       "pose_net": "define_CNN_3D", "pose_dtype": "fp32 (CUDA-core) / bf16x3 split on tcgen05, fp32 accumulate",
+                       "dense_path": args.dense_path, "prime_frames": PRIME_FRAMES,
+                       "l2": "flushed between timed steps (256 MiB fill); per-step CUDA events on the library stream, "
+                             "flush excluded", "parallelism": "scenes sharded %d/GPU, no collective in the hot loop" % S},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // K),
+                    "d2h_bytes_per_step": int(res_host.numel() * 4)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "counters_per_step": {k: float(v) / K for k, v in zip(
+                ["scene_frames", "N", "M", "U", "Bf", "tracks", "ring_rows", "pose_rows"], cnt)},
+        }
+        out.update(rooflines(kern, cnt, K, alg, pk, total_ms / K))
+        if not args.no_cpu_baseline:
+            n, sec = cpu_port_run(range(50_000, 50_004), 60)
+            out["cpu_baseline"] = {"value": n / sec, "unit": UNIT, "cores": 1, "kind": "port",
+                                   "sample": "4 C2-shaped scenes x 60 frames, oracle port (numpy float64 + torch-CPU "
+                                             "fp32 pose net), one thread"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def rooflines(kern, cnt, K, alg_bytes, pk, step_ms):
+    """roofline of the dominant kernel + the tracker step kernel (HBM) and the dense GEMM (tensor)."""
+    out = {}
+    rows = float(cnt[7]) / K
+    fc1_flops = 2.0 * rows * 6144 * 1536
+    step_bytes = alg_bytes / K
+    if kern:
+        out["kernel_ms"] = kern
+        dom = max(kern, key=kern.get)
+        st = kern.get("step", None)
+        if st:
+            a = step_bytes / (st / 1e3) / 1e9
+            out["roofline_step"] = {"kernel": "step_kernel", "bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"],
+                                    "unit": "GB/s", "frac": a / pk["hbm_gbs"], "traffic": None,
+                                    "algorithmic_bytes_per_launch": step_bytes, "peak_src": pk["src"]}
+        g = kern.get("fc1", None)
+        if g:
+            a = fc1_flops / (g / 1e3) / 1e12
+            out["roofline_fc1"] = {"kernel": "fc1", "bound": "tensor", "achieved": a, "peak": pk["bf16_tflops"],
+                                   "unit": "TFLOP/s", "frac": a / pk["bf16_tflops"], "traffic": None,
+                                   "algorithmic_flops_per_launch": fc1_flops, "peak_src": pk["src"]}
+        out["roofline"] = dict(out["roofline_fc1"] if dom == "fc1" and g else out.get("roofline_step", {}))
+        out["roofline"]["dominant_kernel"] = dom
+    else:
+        a = step_bytes / (step_ms / 1e3) / 1e9
+        out["roofline"] = {"kernel": "whole step (no per-kernel timing)", "bound": "hbm", "achieved": a,
+                           "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": a / pk["hbm_gbs"], "traffic": None}
+    return out
+
+
+if __name__ == "__main__":
+    main()

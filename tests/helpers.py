@@ -4,9 +4,10 @@ import numpy as np
 from oracle import mmw_oracle as mo
 
 # float64 state on both sides; differences come from summation order and FMA contraction only.  The spec's
-# bar is 1e-4 relative on state; we hold the device to a much tighter one.
-STATE_RTOL = 1e-8
-STATE_ATOL = 1e-10
+# bar is 1e-4 relative on state; free-running sequences are held to 1e-6 (tiny differences are amplified by
+# the filter over hundreds of frames), single stage calls to 1e-11 (test_gpu_parity.py).
+STATE_RTOL = 1e-6
+STATE_ATOL = 1e-9
 KEYPOINT_ATOL = 1e-3        # 1 mm on joints (north_star)
 
 
