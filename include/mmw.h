@@ -229,6 +229,18 @@ int mmw_get_counters(mmw_ctx* ctx, uint64_t out[8], int reset);
  * 0 = CUDA-core fp32 path (kept for numerics comparison). */
 int mmw_set_dense_path(mmw_ctx* ctx, int use_tensor_cores);
 
+/* Per-kernel device time: while enabled, every launch of mmw_step is bracketed by CUDA events on the context's
+ * stream.  mmw_get_kernel_ms returns the accumulated milliseconds and launch counts per kernel class. */
+#define MMW_K_STEP 0           /* fused tracker step (normalize + track) */
+#define MMW_K_POSE_INDEX 1     /* pose row compaction */
+#define MMW_K_POSE_FEATURES 2  /* relative_coordinates + format_single_frame */
+#define MMW_K_CONV 3           /* conv1 + conv2 + BatchNorm */
+#define MMW_K_FC1 4            /* dense 1 (+ operand split when the tensor-core path is on) */
+#define MMW_K_FC2 5            /* dense 2 */
+#define MMW_N_KERNELS 8
+int mmw_profile(mmw_ctx* ctx, int enable);
+int mmw_get_kernel_ms(mmw_ctx* ctx, double* total_ms /*[MMW_N_KERNELS]*/, uint64_t* calls /*[MMW_N_KERNELS]*/);
+
 /* Number of kernels this library launched since creation (bench.py's gpu_launches). */
 uint64_t mmw_launch_count(mmw_ctx* ctx);
 

@@ -14,6 +14,7 @@ MMW_POSE_2D, MMW_POSE_3D = 0, 1
 STEP_POSE, STEP_DEVICE_INPUT, STEP_RECORD_LABELS = 0x1, 0x2, 0x4
 SCENE_POINT_OVERFLOW, SCENE_TRACK_OVERFLOW = 0x1, 0x2
 RESULT_FLOATS = 68
+KERNEL_NAMES = ["step", "pose_index", "pose_features", "conv", "fc1", "fc2", "k6", "k7"]
 
 
 class MmwError(RuntimeError):
@@ -92,6 +93,8 @@ SIGNATURES = {
     "mmw_pack_results": (C.c_int, [_p, _p]),
     "mmw_get_counters": (C.c_int, [_p, _p, C.c_int]),
     "mmw_set_dense_path": (C.c_int, [_p, C.c_int]),
+    "mmw_profile": (C.c_int, [_p, C.c_int]),
+    "mmw_get_kernel_ms": (C.c_int, [_p, _p, _p]),
     "mmw_launch_count": (C.c_uint64, [_p]),
 }
 

@@ -186,6 +186,17 @@ class BatchedTracker:
         _lib.check(self.lib.mmw_get_counters(self._h, _lib.ptr(out), 1 if reset else 0))
         return out
 
+    def profile_kernels(self, step_fn, n_steps: int) -> dict:
+        """Average device milliseconds per launch of each kernel class over n_steps calls of step_fn(i)
+        (CUDA events on the library's stream around every launch; not a profiler run)."""
+        _lib.check(self.lib.mmw_profile(self._h, 1))
+        for i in range(n_steps):
+            step_fn(i)
+        ms = np.zeros(8, np.float64); calls = np.zeros(8, np.uint64)
+        _lib.check(self.lib.mmw_get_kernel_ms(self._h, _lib.ptr(ms), _lib.ptr(calls)))
+        _lib.check(self.lib.mmw_profile(self._h, 0))
+        return {_lib.KERNEL_NAMES[i]: float(ms[i] / calls[i]) for i in range(8) if calls[i] > 0}
+
     def launch_count(self) -> int:
         return int(self.lib.mmw_launch_count(self._h))
 

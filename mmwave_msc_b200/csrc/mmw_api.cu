@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "dbscan.cuh"
@@ -66,7 +67,20 @@ struct mmw_ctx {
     PoseTc tc;              // tensor-core dense path (pose_tc.cu)
     bool use_tc = true;
     uint64_t launches = 0;
+    // per-kernel CUDA-event profiling (mmw_profile)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, int>> marks;   // event recorded BEFORE kernel `second` (-1 = end marker)
+    double kernel_ms[MMW_N_KERNELS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t kernel_calls[MMW_N_KERNELS] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+static void prof_mark(mmw_ctx* x, int next_kernel) {
+    if (!x->profiling) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, x->stream);
+    x->marks.emplace_back(e, next_kernel);
+}
 
 static void fill_devconfig(const mmw_config& c, int ncap, int tcap, DevConfig* d) {
     const double ang = c.s_tilt_deg * (M_PI / 180.0);      // numpy.radians
@@ -289,9 +303,11 @@ int mmw_load_pose_weights(mmw_ctx* x, int variant, const float* blob, size_t n) 
 static int run_pose_net(mmw_ctx* x, float* keypoints_by_slot, int max_rows) {
     ConvArgs ca{x->d_feats, x->w1, x->b1, x->w2, x->b2, x->d_bn1s, x->d_bn1t, x->d_act2, x->d_pose_total};
     int grid = max_rows < 296 ? max_rows : 296;
+    prof_mark(x, MMW_K_CONV);
     CK(launch_conv(ca, x->D, grid, x->stream));
     x->launches++;
     FcArgs fa{x->d_act2, x->wd1, x->bd1, x->d_bn2s, x->d_bn2t, x->d_act3, x->d_pose_total, x->Kf, x->H};
+    prof_mark(x, MMW_K_FC1);
     if (x->use_tc && x->tc.ready) {
         int nl = 0;
         if (pose_tc_fc1(&x->tc, fa, max_rows, x->stream, &nl) != 0)
@@ -303,9 +319,11 @@ static int run_pose_net(mmw_ctx* x, float* keypoints_by_slot, int max_rows) {
     }
     Fc2Args f2{x->d_act3, x->wd2, x->bd2, x->d_pose_out, keypoints_by_slot, x->d_row_scene, x->d_row_slot,
                x->d_pose_total, x->H, x->tcap};
-    grid = max_rows < 148 * 16 ? max_rows : 148 * 16;
+    grid = (max_rows + 7) / 8 < 148 * 4 ? (max_rows + 7) / 8 : 148 * 4;
+    prof_mark(x, MMW_K_FC2);
     CK(launch_fc2(f2, grid, x->stream));
     x->launches++;
+    prof_mark(x, -1);
     return MMW_OK;
 }
 
@@ -344,12 +362,16 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     a.keypoints = x->d_keypoints; a.default_posture = x->d_default_posture; a.assoc_out = x->d_assoc;
     a.labels_out = (flags & MMW_STEP_RECORD_LABELS) ? x->d_labels : nullptr;
     a.counters = x->d_counters; a.n_scenes = x->S; a.flags = flags;
+    prof_mark(x, MMW_K_STEP);
     CK(launch_step(a, x->stream));
     x->launches++;
+    prof_mark(x, -1);
     if (flags & MMW_STEP_POSE) {
+        prof_mark(x, MMW_K_POSE_INDEX);
         CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
         PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, x->d_row_scene, x->d_row_track,
                         x->d_row_slot};
+        prof_mark(x, MMW_K_POSE_FEATURES);
         CK(launch_pose_features(fa, x->S, x->stream));
         x->launches += 2;
         int rc = run_pose_net(x, x->d_keypoints, x->pose_cap);
@@ -794,6 +816,36 @@ int mmw_pose(mmw_ctx* x, const float* feats, int n, float* keypoints) {
     if (rc != MMW_OK) return rc;
     CK(cudaMemcpyAsync(keypoints, x->d_pose_out, sizeof(float) * kKp * n, cudaMemcpyDeviceToHost, x->stream));
     CK(cudaStreamSynchronize(x->stream));
+    return MMW_OK;
+}
+
+int mmw_profile(mmw_ctx* x, int enable) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    for (auto& m : x->marks) cudaEventDestroy(m.first);
+    x->marks.clear();
+    for (int i = 0; i < MMW_N_KERNELS; ++i) { x->kernel_ms[i] = 0; x->kernel_calls[i] = 0; }
+    x->profiling = enable != 0;
+    return MMW_OK;
+}
+
+int mmw_get_kernel_ms(mmw_ctx* x, double* total_ms, uint64_t* calls) {
+    if (!x || !total_ms || !calls) return fail(MMW_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    for (size_t i = 0; i + 1 < x->marks.size(); ++i) {
+        const int k = x->marks[i].second;
+        if (k < 0 || k >= MMW_N_KERNELS) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, x->marks[i].first, x->marks[i + 1].first) == cudaSuccess) {
+            x->kernel_ms[k] += ms;
+            x->kernel_calls[k] += 1;
+        }
+    }
+    for (auto& m : x->marks) cudaEventDestroy(m.first);
+    x->marks.clear();
+    for (int i = 0; i < MMW_N_KERNELS; ++i) { total_ms[i] = x->kernel_ms[i]; calls[i] = x->kernel_calls[i]; }
     return MMW_OK;
 }
 

@@ -268,22 +268,52 @@ cudaError_t launch_fc1_simt(const FcArgs& a, int max_rows, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// Dense 2: keypoints[n][57] = act3[n][H] W3[H][57] + b3; one CTA (64 threads) per row; also scatters the
-// result to the owning track's keypoint slot (Tracking.py:733-734).
-__global__ void __launch_bounds__(64) fc2_kernel(Fc2Args a) {
-    extern __shared__ float xrow[];
+// Dense 2: keypoints[n][57] = act3[n][H] W3[H][57] + b3.  One CTA = 8 rows; thread = (output o, K half); the
+// weight element is loaded once and used for the 8 rows staged in shared memory.  Also scatters the result to the
+// owning track's keypoint slot (Tracking.py:733-734).
+constexpr int kFc2Rows = 8;
+__global__ void __launch_bounds__(128) fc2_kernel(Fc2Args a) {
+    extern __shared__ float xs[];                 // [kFc2Rows][H]
+    __shared__ float part[kFc2Rows][64];
     const int n = *a.n_rows;
-    for (int row = blockIdx.x; row < n; row += gridDim.x) {
-        for (int i = threadIdx.x; i < a.H; i += 64) xrow[i] = a.act3[(size_t)row * a.H + i];
+    const int o = threadIdx.x & 63, half = threadIdx.x >> 6;
+    const int hlen = a.H / 2;
+    for (int r0 = blockIdx.x * kFc2Rows; r0 < n; r0 += gridDim.x * kFc2Rows) {
+        const int nr = min(kFc2Rows, n - r0);
+        for (int i = threadIdx.x; i < kFc2Rows * a.H; i += 128) {
+            const int r = i / a.H;
+            xs[i] = r < nr ? a.act3[(size_t)(r0 + r) * a.H + (i - r * a.H)] : 0.f;
+        }
         __syncthreads();
-        if (threadIdx.x < kKp) {
-            float acc = 0.f;
-            for (int h = 0; h < a.H; ++h) acc = fmaf(xrow[h], a.W[(size_t)h * kKp + threadIdx.x], acc);
-            acc += a.bias[threadIdx.x];
-            a.out[(size_t)row * kKp + threadIdx.x] = acc;
-            if (a.keypoints != nullptr) {
-                const int s = a.row_scene[row], slot = a.row_slot[row];
-                a.keypoints[((size_t)s * a.tcap + slot) * kKp + threadIdx.x] = acc;
+        float acc[kFc2Rows];
+#pragma unroll
+        for (int r = 0; r < kFc2Rows; ++r) acc[r] = 0.f;
+        if (o < kKp) {
+            const float* wp_ = a.W + (size_t)(half * hlen) * kKp + o;
+            const float* xp = xs + half * hlen;
+#pragma unroll 4
+            for (int h = 0; h < hlen; ++h) {
+                const float w = __ldg(wp_ + (size_t)h * kKp);
+#pragma unroll
+                for (int r = 0; r < kFc2Rows; ++r) acc[r] = fmaf(xp[r * a.H + h], w, acc[r]);
+            }
+        }
+        if (half == 1) {
+#pragma unroll
+            for (int r = 0; r < kFc2Rows; ++r) part[r][o] = acc[r];
+        }
+        __syncthreads();
+        if (half == 0 && o < kKp) {
+#pragma unroll
+            for (int r = 0; r < kFc2Rows; ++r) {
+                if (r >= nr) break;
+                const float v = (acc[r] + part[r][o]) + a.bias[o];
+                const int row = r0 + r;
+                a.out[(size_t)row * kKp + o] = v;
+                if (a.keypoints != nullptr) {
+                    const int s = a.row_scene[row], slot = a.row_slot[row];
+                    a.keypoints[((size_t)s * a.tcap + slot) * kKp + o] = v;
+                }
             }
         }
         __syncthreads();
@@ -291,7 +321,14 @@ __global__ void __launch_bounds__(64) fc2_kernel(Fc2Args a) {
 }
 
 cudaError_t launch_fc2(const Fc2Args& a, int grid, cudaStream_t st) {
-    fc2_kernel<<<grid, 64, a.H * sizeof(float), st>>>(a);
+    const size_t smem = (size_t)kFc2Rows * a.H * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    fc2_kernel<<<grid, 128, smem, st>>>(a);
     return cudaGetLastError();
 }
 
