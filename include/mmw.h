@@ -119,6 +119,15 @@ int mmw_load_pose_weights(mmw_ctx* ctx, int variant, const float* blob, size_t n
  */
 int mmw_step(mmw_ctx* ctx, const float* pts, const int32_t* offsets, const double* dt, uint32_t flags);
 
+/* TrackBuffer.estimate_posture (Tracking.py:705-734) alone, on the current state of every scene whose last
+ * frame ran: feature maps (relative_coordinates + format_single_frame, Utils.py:437-520) + the CNN. */
+int mmw_estimate_posture(mmw_ctx* ctx);
+
+/* Builds only the pose rows / feature maps of mmw_estimate_posture (readable with mmw_get_pose_rows) so that a
+ * caller-supplied model object can do the inference (Tracking.py:732), and stores its answer for one track. */
+int mmw_pose_features_only(mmw_ctx* ctx);
+int mmw_set_keypoints(mmw_ctx* ctx, int scene, int track_index, const float* keypoints57);
+
 /* Blocks until all work queued on the context's stream has finished. */
 int mmw_sync(mmw_ctx* ctx);
 /* The context's cudaStream_t (so a host framework can time it with events / order copies after it). */

@@ -73,6 +73,9 @@ SIGNATURES = {
     "mmw_reset": (C.c_int, [_p]),
     "mmw_load_pose_weights": (C.c_int, [_p, C.c_int, _p, C.c_size_t]),
     "mmw_step": (C.c_int, [_p, _p, _p, _p, C.c_uint32]),
+    "mmw_estimate_posture": (C.c_int, [_p]),
+    "mmw_pose_features_only": (C.c_int, [_p]),
+    "mmw_set_keypoints": (C.c_int, [_p, C.c_int, C.c_int, _p]),
     "mmw_sync": (C.c_int, [_p]),
     "mmw_stream": (_p, [_p]),
     "mmw_get_tracks": (C.c_int, [_p, _p, _p]),

@@ -120,6 +120,17 @@ class BatchedTracker:
         _lib.check(self.lib.mmw_step(self._h, C.c_void_p(points_ptr), C.c_void_p(offsets_ptr), C.c_void_p(dt_ptr),
                                      flags))
 
+    def estimate_posture(self):
+        """TrackBuffer.estimate_posture alone (needs load_pose_weights first)."""
+        _lib.check(self.lib.mmw_estimate_posture(self._h))
+
+    def pose_features_only(self):
+        _lib.check(self.lib.mmw_pose_features_only(self._h))
+
+    def set_keypoints(self, scene: int, track_index: int, kp: np.ndarray):
+        kp = np.ascontiguousarray(kp, dtype=np.float32).reshape(57)
+        _lib.check(self.lib.mmw_set_keypoints(self._h, int(scene), int(track_index), _lib.ptr(kp)))
+
     def sync(self):
         _lib.check(self.lib.mmw_sync(self._h))
 

@@ -366,17 +366,45 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     CK(launch_step(a, x->stream));
     x->launches++;
     prof_mark(x, -1);
-    if (flags & MMW_STEP_POSE) {
-        prof_mark(x, MMW_K_POSE_INDEX);
-        CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
-        PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, x->d_row_scene, x->d_row_track,
-                        x->d_row_slot};
-        prof_mark(x, MMW_K_POSE_FEATURES);
-        CK(launch_pose_features(fa, x->S, x->stream));
-        x->launches += 2;
-        int rc = run_pose_net(x, x->d_keypoints, x->pose_cap);
-        if (rc != MMW_OK) return rc;
-    }
+    if (flags & MMW_STEP_POSE) return mmw_estimate_posture(x);
+    return MMW_OK;
+}
+
+int mmw_estimate_posture(mmw_ctx* x) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    if (!x->has_weights) return fail(MMW_ERR_STATE, "estimate_posture needs mmw_load_pose_weights first");
+    CK(cudaSetDevice(x->device));
+    prof_mark(x, MMW_K_POSE_INDEX);
+    CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
+    PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, x->d_row_scene, x->d_row_track,
+                    x->d_row_slot};
+    prof_mark(x, MMW_K_POSE_FEATURES);
+    CK(launch_pose_features(fa, x->S, x->stream));
+    x->launches += 2;
+    return run_pose_net(x, x->d_keypoints, x->pose_cap);
+}
+
+int mmw_pose_features_only(mmw_ctx* x) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(x->device));
+    CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
+    PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, x->d_row_scene, x->d_row_track,
+                    x->d_row_slot};
+    CK(launch_pose_features(fa, x->S, x->stream));
+    x->launches += 2;
+    return MMW_OK;
+}
+
+int mmw_set_keypoints(mmw_ctx* x, int scene, int track_index, const float* kp57) {
+    if (!x || !kp57) return fail(MMW_ERR_INVALID, "NULL argument");
+    if (scene < 0 || scene >= x->S || track_index < 0 || track_index >= x->tcap)
+        return fail(MMW_ERR_INVALID, "scene/track out of range");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    TrackRec t;
+    CK(cudaMemcpy(&t, x->d_tracks + (size_t)scene * x->tcap + track_index, sizeof(t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(x->d_keypoints + ((size_t)scene * x->tcap + t.slot) * kKp, kp57, sizeof(float) * kKp,
+                  cudaMemcpyHostToDevice));
     return MMW_OK;
 }
 

@@ -89,8 +89,26 @@ def balltree_deviation(n_scenes: int = 24, n_frames: int = 30) -> dict:
             "scenes_with_any_difference": diff_scenes}
 
 
+def offline_manager_sequence() -> dict:
+    """What the reference's CSV reader (Utils.OfflineManager, Utils.py:53-177) hands out frame by frame,
+    including its read-buffer quirk: the frame that fills the 40-frame buffer is delivered with its first
+    row only (Utils.py:128-131) and the rest of that frame is dropped."""
+    import tempfile
+    const, utils, tracking = rh.load_reference()
+    sc = synth.gen_scene(2, 95)
+    d = tempfile.mkdtemp()
+    synth.write_reference_csv(sc, d, frames_per_file=40)
+    om = utils.OfflineManager(d)
+    seq = []
+    while not om.is_finished() and len(seq) < 400:
+        ok, fc, det = om.get_data()
+        seq.append([int(ok), int(fc), len(det["x"]) if ok else -1, int(det["posix"][0]) if ok else -1])
+    return {"scene": 2, "frames": 95, "frames_per_file": 40, "sequence": seq}
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    json.dump(offline_manager_sequence(), open(os.path.join(GOLDEN, "offline_manager_sequence.json"), "w"))
     json.dump(known_answers(), open(os.path.join(GOLDEN, "known_answers.json"), "w"), indent=1)
     for name, sid, nf, spec, mt in CASES:
         sc = synth.gen_scene(sid, nf, spec)

@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Summarise an ncu report (raw page) into a small markdown table:  python profiles/summarize_ncu.py rep.ncu-rep"""
+import csv
+import subprocess
+import sys
+
+METRICS = [
+    ("gpu__time_duration.sum", "time_us"),
+    ("dram__bytes_read.sum", "dram_rd_MB"),
+    ("dram__bytes_write.sum", "dram_wr_MB"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_%"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_%"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_%"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_%"),
+    ("launch__registers_per_thread", "regs"),
+    ("launch__occupancy_limit_shared_mem", "occ_lim_smem"),
+    ("launch__occupancy_limit_registers", "occ_lim_regs"),
+    ("smsp__inst_executed.sum", "warp_insts"),
+]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units = rows[0], rows[1]
+    ki = h.index("Kernel Name")
+    cols = [(h.index(m), n) for m, n in METRICS if m in h]
+    print("| kernel | " + " | ".join("%s [%s]" % (n, units[i]) if units[i] else n for i, n in cols) + " |")
+    print("|---|" + "---|" * len(cols))
+    for r in rows[2:]:
+        print("| %s | " % r[ki].split("(")[0][:40] + " | ".join(r[i] for i, _ in cols) + " |")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -62,3 +62,23 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_offline_manager_matches_reference_reader(tmp_path):
+    """The CSV replay reader hands out the same frames as the reference's OfflineManager did on the same log
+    (golden sequence recorded by oracle/gen_golden.py), including the dropped rows of every 40th frame."""
+    import json
+    import sys
+    import types
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "offline_manager_sequence.json")))
+    from mmwave_msc_b200 import synth
+    sc = synth.gen_scene(g["scene"], g["frames"])
+    synth.write_reference_csv(sc, str(tmp_path), frames_per_file=g["frames_per_file"])
+    # import Utils without touching the device: OfflineManager is pure host code
+    from mmwave_msc_b200 import Utils
+    om = Utils.OfflineManager(str(tmp_path))
+    seq = []
+    while not om.is_finished() and len(seq) < 400:
+        ok, fc, det = om.get_data()
+        seq.append([int(ok), int(fc), len(det["x"]) if ok else -1, int(det["posix"][0]) if ok else -1])
+    assert seq == g["sequence"]
