@@ -250,6 +250,10 @@ int mmw_set_dense_path(mmw_ctx* ctx, int use_tensor_cores);
 int mmw_profile(mmw_ctx* ctx, int enable);
 int mmw_get_kernel_ms(mmw_ctx* ctx, double* total_ms /*[MMW_N_KERNELS]*/, uint64_t* calls /*[MMW_N_KERNELS]*/);
 
+/* Debug: per-phase SM-cycle accounting inside the fused step kernel (thread 0 of every CTA).  Returns the
+ * cycles accumulated since the last call in out16 (may be NULL) and switches the accounting on/off. */
+int mmw_phase_clocks(mmw_ctx* ctx, int enable, uint64_t* out16);
+
 /* Number of kernels this library launched since creation (bench.py's gpu_launches). */
 uint64_t mmw_launch_count(mmw_ctx* ctx);
 

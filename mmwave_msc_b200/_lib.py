@@ -98,6 +98,7 @@ SIGNATURES = {
     "mmw_set_dense_path": (C.c_int, [_p, C.c_int]),
     "mmw_profile": (C.c_int, [_p, C.c_int]),
     "mmw_get_kernel_ms": (C.c_int, [_p, _p, _p]),
+    "mmw_phase_clocks": (C.c_int, [_p, C.c_int, _p]),
     "mmw_launch_count": (C.c_uint64, [_p]),
 }
 

@@ -272,3 +272,13 @@ class BatchedTracker:
         out = np.zeros((n, 57), np.float32)
         _lib.check(self.lib.mmw_pose(self._h, _lib.ptr(feats), n, _lib.ptr(out)))
         return out
+
+
+def _phase_clocks(self, enable: bool):
+    """Debug: cycles per phase of the fused step kernel accumulated since the last call (16 counters)."""
+    out = np.zeros(16, dtype=np.uint64)
+    _lib.check(self.lib.mmw_phase_clocks(self._h, 1 if enable else 0, _lib.ptr(out)))
+    return out
+
+
+BatchedTracker.phase_clocks = _phase_clocks

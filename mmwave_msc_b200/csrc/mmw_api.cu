@@ -45,6 +45,8 @@ struct mmw_ctx {
     int32_t* d_assoc = nullptr;
     int32_t* d_labels = nullptr;
     unsigned long long* d_counters = nullptr;
+    unsigned long long* d_phase = nullptr;
+    bool phase_clocks = false;
     // input staging (host-input path)
     float* d_pts = nullptr;
     int32_t* d_offsets = nullptr;
@@ -150,7 +152,7 @@ int mmw_destroy(mmw_ctx* x) {
     cudaSetDevice(x->device);
     if (x->stream) cudaStreamSynchronize(x->stream);
     void* ptrs[] = {x->d_tracks, x->d_scenes, x->d_track_ring, x->d_uring, x->d_keypoints, x->d_default_posture,
-                    x->d_assoc, x->d_labels, x->d_counters, x->d_pts, x->d_offsets, x->d_dt, x->d_blob, x->d_bn1s,
+                    x->d_assoc, x->d_labels, x->d_counters, x->d_phase, x->d_pts, x->d_offsets, x->d_dt, x->d_blob, x->d_bn1s,
                     x->d_bn1t, x->d_bn2s, x->d_bn2t, x->d_feats, x->d_row_scene, x->d_row_track, x->d_row_slot,
                     x->d_pose_total, x->d_act2, x->d_act3, x->d_pose_out};
     for (void* p : ptrs)
@@ -216,6 +218,7 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     ALLOC(x->d_assoc, sizeof(int32_t) * S * max_points);
     ALLOC(x->d_labels, sizeof(int32_t) * S * 3 * max_points);
     ALLOC(x->d_counters, sizeof(unsigned long long) * 8);
+    ALLOC(x->d_phase, sizeof(unsigned long long) * 16);
     ALLOC(x->d_offsets, sizeof(int32_t) * (S + 1));
     ALLOC(x->d_dt, sizeof(double) * S);
     ALLOC(x->d_pose_total, sizeof(int));
@@ -362,6 +365,7 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     a.keypoints = x->d_keypoints; a.default_posture = x->d_default_posture; a.assoc_out = x->d_assoc;
     a.labels_out = (flags & MMW_STEP_RECORD_LABELS) ? x->d_labels : nullptr;
     a.counters = x->d_counters; a.n_scenes = x->S; a.flags = flags;
+    a.phase_cycles = x->phase_clocks ? x->d_phase : nullptr;
     prof_mark(x, MMW_K_STEP);
     CK(launch_step(a, x->stream));
     x->launches++;
@@ -874,6 +878,20 @@ int mmw_get_kernel_ms(mmw_ctx* x, double* total_ms, uint64_t* calls) {
     for (auto& m : x->marks) cudaEventDestroy(m.first);
     x->marks.clear();
     for (int i = 0; i < MMW_N_KERNELS; ++i) { total_ms[i] = x->kernel_ms[i]; calls[i] = x->kernel_calls[i]; }
+    return MMW_OK;
+}
+
+int mmw_phase_clocks(mmw_ctx* x, int enable, uint64_t* out16) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    if (out16) {
+        unsigned long long h[16];
+        CK(cudaMemcpy(h, x->d_phase, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 16; ++i) out16[i] = h[i];
+    }
+    CK(cudaMemset(x->d_phase, 0, sizeof(unsigned long long) * 16));
+    x->phase_clocks = enable != 0;
     return MMW_OK;
 }
 

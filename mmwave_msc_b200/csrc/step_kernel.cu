@@ -122,7 +122,18 @@ __device__ __forceinline__ const float* uring_frame(const StepArgs& a, int s, in
     return a.uring + ((size_t)s * kRing + phys) * (size_t)a.cfg.ncap * kRawCols;
 }
 
+// Optional per-phase cycle accounting (thread 0 of every CTA, accumulated with one atomic per phase).
+#define PHASE_MARK(idx)                                                                  \
+    do {                                                                                 \
+        if (a.phase_cycles != nullptr && threadIdx.x == 0) {                             \
+            const long long now__ = clock64();                                           \
+            atomicAdd(&a.phase_cycles[idx], (unsigned long long)(now__ - phase_t0));     \
+            phase_t0 = now__;                                                            \
+        }                                                                                \
+    } while (0)
+
 __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constant__ StepArgs a) {
+    long long phase_t0 = clock64();
     extern __shared__ __align__(16) unsigned char smem[];
     const DevConfig& c = a.cfg;
     const int ncap = c.ncap, tcap = c.tcap;
@@ -190,6 +201,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
     }
     sc.last_ran = 1;
 
+    PHASE_MARK(1);
     // ---- 2. load this scene's track records -----------------------------------------------------------
     const int T0 = sc.n_tracks;
     {
@@ -199,6 +211,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
     }
     __syncthreads();
 
+    PHASE_MARK(2);
     // ---- 3. predict (Tracking.py:591-596, Q9) and gate matrices (Tracking.py:545-551) ---------------
     for (int j = warp; j < T0; j += kStepWarps) {
         TrackRec& t = tr[j];
@@ -217,6 +230,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
     }
     __syncthreads();
 
+    PHASE_MARK(3);
     // ---- 4. gating + association (Tracking.py:553-572, Q14) -------------------------------------------
     for (int i = tid; i < M; i += kStepThreads) {
         double p[6];
@@ -245,6 +259,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
     }
     __syncthreads();
 
+    PHASE_MARK(4);
     // ---- 5. per-track association (Tracking.py:648-653, 314-341) + unassigned push (Tracking.py:691) --
     int U = 0, ring_rows = 0;
     for (int g = warp; g <= T0; g += kStepWarps) {
@@ -341,6 +356,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
         sc.ring_cnt[phys] = u;
     }
 
+    PHASE_MARK(5);
     // ---- 6. maintenance (Tracking.py:513-528, Q16): drop timed-out tracks, keep list order -----------
     if (tid == 0) {
         int nk = 0, nf = 0;
@@ -356,6 +372,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
     const int T1 = misc[kM];
     for (int k = 0; k < misc[kNFree]; ++k) sc.slot_mask &= ~(1u << misc[kFree + k]);
 
+    PHASE_MARK(6);
     // ---- 7. update every surviving track (Tracking.py:598-603, 387-398; Q11-Q13) ---------------------
     for (int k = warp; k < T1; k += kStepWarps) {
         TrackRec& t = tr[misc[kOrder + k]];
@@ -374,6 +391,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
     }
     __syncthreads();
 
+    PHASE_MARK(7);
     // ---- 8. DBSCAN over the fused global ring (Tracking.py:693-700) -----------------------------------
     int B = 0;
     int fcnt[kRing], fphys[kRing];
@@ -407,6 +425,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
             for (int b = tid; b < B; b += kStepThreads) a.labels_out[(size_t)s * 3 * ncap + b] = cl[b];
     }
 
+    PHASE_MARK(8);
     // ---- 9. spawn one track per cluster, in label order (Tracking.py:576-589, 210-230; Q7, Q20) ------
     int T2 = T1;
     if (ncl > 0) {
@@ -508,6 +527,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
     }
     __syncthreads();
 
+    PHASE_MARK(9);
     // ---- 10. write back: track records in list order, scene record, counters ---------------------------
     {
         double* dstbase = reinterpret_cast<double*>(a.tracks + (size_t)s * tcap);
@@ -528,6 +548,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
         if (run_db) atomicAdd(&a.counters[4], (unsigned long long)B);
         atomicAdd(&a.counters[5], (unsigned long long)T2);
     }
+    PHASE_MARK(10);
 }
 
 cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
