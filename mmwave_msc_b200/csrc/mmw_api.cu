@@ -297,13 +297,34 @@ int mmw_load_pose_weights(mmw_ctx* x, int variant, const float* blob, size_t n) 
     CK(cudaMalloc((void**)&x->d_act2, sizeof(float) * (size_t)x->pose_cap * Kf));
     CK(cudaMalloc((void**)&x->d_act3, sizeof(float) * (size_t)x->pose_cap * H));
     x->variant = variant; x->D = D; x->Kf = Kf; x->H = H;
-    int rc = pose_tc_init(&x->tc, blob + off[8], Kf, H, x->pose_cap, x->stream);
+    int rc = pose_tc_init(&x->tc, blob, off, D, x->pose_cap);
     if (rc != 0) return fail(MMW_ERR_CUDA, std::string("tensor-core dense path init failed: ") + pose_tc_error());
     x->has_weights = true;
     return MMW_OK;
 }
 
 static int run_pose_net(mmw_ctx* x, float* keypoints_by_slot, int max_rows) {
+    if (x->use_tc && x->tc.ready) {
+        // tensor-core path: conv1 -> conv2 -> dense1 -> dense2, operands handed over as split bf16 (pose_tc.cu)
+        PoseTcRun r{x->d_pose_total, x->b1, x->b2, x->d_bn1s, x->d_bn1t, x->bd1, x->d_bn2s, x->d_bn2t, x->bd2,
+                    x->d_pose_out, keypoints_by_slot, x->d_row_scene, x->d_row_slot, x->tcap};
+        int nl = 0;
+        prof_mark(x, MMW_K_CONV);
+        if (pose_tc_conv(&x->tc, r, x->stream, &nl) != 0)
+            return fail(MMW_ERR_CUDA, std::string("tensor-core conv: ") + pose_tc_error());
+        x->launches += nl;
+        prof_mark(x, MMW_K_FC1);
+        if (pose_tc_fc1(&x->tc, r, max_rows, x->stream, &nl) != 0)
+            return fail(MMW_ERR_CUDA, std::string("tensor-core dense 1: ") + pose_tc_error());
+        x->launches += nl;
+        prof_mark(x, MMW_K_FC2);
+        if (pose_tc_fc2(&x->tc, r, max_rows, x->stream, &nl) != 0)
+            return fail(MMW_ERR_CUDA, std::string("tensor-core dense 2: ") + pose_tc_error());
+        x->launches += nl;
+        prof_mark(x, -1);
+        return MMW_OK;
+    }
+    // CUDA-core fp32 path (kept for numerics comparison)
     ConvArgs ca{x->d_feats, x->w1, x->b1, x->w2, x->b2, x->d_bn1s, x->d_bn1t, x->d_act2, x->d_pose_total};
     int grid = max_rows < 296 ? max_rows : 296;
     prof_mark(x, MMW_K_CONV);
@@ -311,15 +332,8 @@ static int run_pose_net(mmw_ctx* x, float* keypoints_by_slot, int max_rows) {
     x->launches++;
     FcArgs fa{x->d_act2, x->wd1, x->bd1, x->d_bn2s, x->d_bn2t, x->d_act3, x->d_pose_total, x->Kf, x->H};
     prof_mark(x, MMW_K_FC1);
-    if (x->use_tc && x->tc.ready) {
-        int nl = 0;
-        if (pose_tc_fc1(&x->tc, fa, max_rows, x->stream, &nl) != 0)
-            return fail(MMW_ERR_CUDA, std::string("tensor-core dense path: ") + pose_tc_error());
-        x->launches += nl;
-    } else {
-        CK(launch_fc1_simt(fa, max_rows, x->stream));
-        x->launches++;
-    }
+    CK(launch_fc1_simt(fa, max_rows, x->stream));
+    x->launches++;
     Fc2Args f2{x->d_act3, x->wd2, x->bd2, x->d_pose_out, keypoints_by_slot, x->d_row_scene, x->d_row_slot,
                x->d_pose_total, x->H, x->tcap};
     grid = (max_rows + 7) / 8 < 148 * 4 ? (max_rows + 7) / 8 : 148 * 4;
@@ -380,7 +394,8 @@ int mmw_estimate_posture(mmw_ctx* x) {
     CK(cudaSetDevice(x->device));
     prof_mark(x, MMW_K_POSE_INDEX);
     CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
-    PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, x->d_row_scene, x->d_row_track,
+    PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats,
+                    (x->use_tc && x->tc.ready) ? pose_tc_input(&x->tc) : nullptr, x->d_row_scene, x->d_row_track,
                     x->d_row_slot};
     prof_mark(x, MMW_K_POSE_FEATURES);
     CK(launch_pose_features(fa, x->S, x->stream));
@@ -392,8 +407,8 @@ int mmw_pose_features_only(mmw_ctx* x) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(x->device));
     CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
-    PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, x->d_row_scene, x->d_row_track,
-                    x->d_row_slot};
+    PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, nullptr, x->d_row_scene,
+                    x->d_row_track, x->d_row_slot};
     CK(launch_pose_features(fa, x->S, x->stream));
     x->launches += 2;
     return MMW_OK;
@@ -844,6 +859,11 @@ int mmw_pose(mmw_ctx* x, const float* feats, int n, float* keypoints) {
     CK(cudaMemcpyAsync(x->d_feats, feats, sizeof(float) * per * n, cudaMemcpyHostToDevice, x->stream));
     CK(cudaMemcpyAsync(x->d_pose_total, &n, sizeof(int), cudaMemcpyHostToDevice, x->stream));
     CK(cudaStreamSynchronize(x->stream));     // &n is a stack variable
+    if (x->use_tc && x->tc.ready) {
+        if (pose_tc_pack_input(&x->tc, x->d_feats, x->d_pose_total, x->stream) != 0)
+            return fail(MMW_ERR_CUDA, std::string("tensor-core input pack: ") + pose_tc_error());
+        x->launches++;
+    }
     int rc = run_pose_net(x, nullptr, n);
     if (rc != MMW_OK) return rc;
     CK(cudaMemcpyAsync(keypoints, x->d_pose_out, sizeof(float) * kKp * n, cudaMemcpyDeviceToHost, x->stream));

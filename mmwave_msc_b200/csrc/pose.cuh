@@ -1,5 +1,7 @@
 // Argument blocks of the pose-stage kernels (pose_kernels.cu, pose_tc.cu).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "mmw_internal.cuh"
 
 namespace mmw {
@@ -10,6 +12,7 @@ struct PoseFeatArgs {
     const TrackRec* tracks;
     const float* track_ring;
     float* feats;          // [rows][ring_size*64*5]
+    __nv_bfloat16* packed; // [rows][ring_size*64][16] = (hi c0..4,0,0,0 | lo c0..4,0,0,0) for the tensor-core convs, or nullptr
     int32_t* row_scene;    // [rows]
     int32_t* row_track;
     int32_t* row_slot;

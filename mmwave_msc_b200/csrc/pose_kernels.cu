@@ -72,9 +72,12 @@ __global__ void __launch_bounds__(128) pose_feature_kernel(PoseFeatArgs a) {
             a.row_slot[row] = slot;
         }
         float* out = a.feats + (size_t)row * nfr * kFeatPts * kRawCols;
+        uint4* pk = a.packed ? reinterpret_cast<uint4*>(a.packed + (size_t)row * nfr * kFeatPts * 16) : nullptr;
         for (int f = 0; f < nfr; ++f) {
             if (f >= rn) {
                 for (int e = lane; e < kFeatPts * kRawCols; e += 32) out[f * kFeatPts * kRawCols + e] = 0.f;
+                if (pk)
+                    for (int e = lane; e < kFeatPts * 2; e += 32) pk[f * kFeatPts * 2 + e] = make_uint4(0, 0, 0, 0);
                 continue;
             }
             const int phys = (rh + f) % c.ring_size;
@@ -114,6 +117,19 @@ __global__ void __launch_bounds__(128) pose_feature_kernel(PoseFeatArgs a) {
 #pragma unroll
                 for (int q = 0; q < kRawCols; ++q)
                     out[(f * kFeatPts + rank) * kRawCols + q] = vals[warp][i][q];
+                if (pk) {
+                    __align__(16) __nv_bfloat16 pv[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) pv[q] = __float2bfloat16_rn(0.f);
+#pragma unroll
+                    for (int q = 0; q < kRawCols; ++q) {
+                        const float x = vals[warp][i][q];
+                        pv[q] = __float2bfloat16_rn(x);
+                        pv[8 + q] = __float2bfloat16_rn(x - __bfloat162float(pv[q]));
+                    }
+                    pk[(f * kFeatPts + rank) * 2 + 0] = reinterpret_cast<const uint4*>(pv)[0];
+                    pk[(f * kFeatPts + rank) * 2 + 1] = reinterpret_cast<const uint4*>(pv)[1];
+                }
             }
             __syncwarp();
         }

@@ -1,17 +1,22 @@
-// Dense layer 1 of the pose network on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+// The pose network (train.py:33-106) on the 5th-generation tensor cores: tcgen05.mma + TMEM + TMA.
 //
-//   out[m][n] = BN2( relu( sum_k A[m][k] W[k][n] + bias[n] ) ),   A = BN1(relu(conv2)) flattened, K = D*64*32,
-//                                                                 N = D*512  (train.py:49-52 / 87-90)
+// Precision.  The network is fp32 in the reference (Keras default) and the joints must hold 1 mm.  A single bf16
+// or tf32 pass does not (14 mm / 2 mm worst case), so every fp32 operand is split into two
+// bf16 terms, a = a_hi + a_lo, w = w_hi + w_lo, and three products are accumulated in fp32 in TMEM:
+//     a_hi*w_hi + a_lo*w_hi + a_hi*w_lo            (the dropped a_lo*w_lo term is ~2^-16 relative)
 //
-// Precision: the network is fp32 in the reference (Keras default) and the joints must hold 1 mm.  A single bf16
-// or tf32 pass does not (14 mm / 2 mm worst case), so every operand is split into two bf16
-// terms, a = a_hi + a_lo, w = w_hi + w_lo, and three tensor-core products are accumulated in fp32 in TMEM:
-//   a_hi*w_hi + a_hi*w_lo + a_lo*w_hi          (the dropped a_lo*w_lo term is ~2^-16 relative)
+// Convolutions (conv_tc_kernel): TMA-im2col implicit GEMM.  Activations live in HBM channels-last with the hi and
+// lo halves interleaved per position, [row][d][h][w][hi c.. | lo c..], so ONE tensor-map box {C', 8, 8, 1, 1} at
+// coordinates (0, kw-1, kh-1, d+kd-1, row) is the im2col column block of tap (kd,kh,kw) for a whole 8x8 slice --
+// 'same' zero padding comes from TMA out-of-bounds fill.  An M=128 tile is two d-slices.  Per tap the B operand is
+// the K' x N' matrix [[W_hi | W_lo], [W_hi | 0]], so one MMA chain produces a*W_hi in columns [0,C) and a_hi*W_lo
+// in columns [C,2C); the epilogue adds the two halves, bias, ReLU (+ BatchNorm after conv2) and writes the next
+// layer's split operand directly.  No thread ever touches an operand byte.
 //
-// Kernel shape: one CTA per 128 x 256 output tile; warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM
-// allocation), warps 2-5 = epilogue (TMEM -> registers -> bias/ReLU/BatchNorm -> global).  Each pipeline stage
-// holds the four operand tiles of one K block {A_hi, A_lo, W_hi, W_lo} (loaded once, used by three MMAs per
-// 16-wide K step), so L2->SMEM traffic is 2/3 of what three independent GEMM passes would move.
+// Dense layers (gemm_tc_kernel): 128 x BN tiles, K blocks of 64 (SWIZZLE_128B); each pipeline stage holds the four
+// operand tiles {A_hi, A_lo, W_hi, W_lo} of one K block (loaded once, used by three MMAs per 16-wide K step).
+//
+// Warp roles in both kernels: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstring>
@@ -22,20 +27,6 @@
 
 namespace mmw {
 
-namespace tc {
-constexpr int BM = 128;            // UMMA M
-constexpr int BN = 256;            // UMMA N (TMEM columns, fp32)
-constexpr int BK = 64;             // K block = 128 bytes of bf16 = one SWIZZLE_128B atom row
-constexpr int UK = 16;             // UMMA K for 16-bit inputs
-constexpr int STAGES = 2;
-constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
-constexpr int B_BYTES = BN * BK * 2;                 // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int THREADS = 192;
-constexpr uint32_t TMEM_COLS = 256;
-}  // namespace tc
-
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -44,6 +35,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -60,6 +54,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
             "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -88,49 +90,259 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major operand tile in shared memory, rows of 128 bytes, SWIZZLE_128B (what the TMA wrote):
-// 8-row atoms are 1024 bytes apart (SBO); LBO is unused for swizzled K-major tiles; version = 1 (sm_100).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(COLS) : "memory");
+}
+
+// K-major operand tile in shared memory whose rows are exactly one swizzle span wide (SW bytes = 32, 64 or 128),
+// written by TMA with the matching swizzle: 8-row atoms are 8*SW bytes apart (SBO); LBO unused; version 1 (sm_100).
+template <int SW>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    constexpr uint64_t layout = SW == 128 ? 2 : (SW == 64 ? 4 : 6);
     uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fff);           // start address, bits [0,14)
-    d |= (uint64_t)0 << 16;                           // leading byte offset
-    d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;      // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                           // version
-    d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)(((8 * SW) >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
     return d;
 }
-
-// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N = 256, M = 128.
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(tc::BN >> 3) << 17) | ((uint32_t)(tc::BM >> 4) << 24);
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128.
+__device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-struct TcGemmArgs {
+__device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// =====================================================================================================
+// Convolution as TMA-im2col implicit GEMM
+// =====================================================================================================
+struct ConvTcArgs {
     const int* n_rows;
-    const float *bias, *bn_scale, *bn_shift;
-    float* out;
-    int K, H;
+    const float *bias, *bn_scale, *bn_shift;       // bn_* only for MODE 1
+    __nv_bfloat16* out0;                           // MODE 0: act1 packed [row][D][8][8][32]; MODE 1: A_hi [row][Kf]
+    __nv_bfloat16* out1;                           // MODE 1: A_lo [row][Kf]
+    int D, taps, rows_cap;
 };
 
-__global__ void __launch_bounds__(tc::THREADS, 1)
-fc1_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
-              const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
-              const TcGemmArgs a) {
-    using namespace tc;
+constexpr int kConvStages = 8;
+constexpr int kConvThreads = 192;
+
+template <int CK, int NOUT>
+constexpr int conv_smem_bytes_tc(int taps) {
+    return taps * NOUT * CK * 2 + kConvStages * 128 * CK * 2 + 1024 + 512;
+}
+
+// CK   = K' per tap = 2 * padded input channels (hi | lo): 16 for conv1, 32 for conv2
+// NOUT = MMA N     = 2 * output channels: 32 for conv1, 64 for conv2
+template <int CK, int NOUT, int MODE>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const ConvTcArgs a) {
+    constexpr int SW = CK * 2;                       // row bytes == swizzle span
+    constexpr int SLICE_BYTES = 64 * CK * 2;
+    constexpr int A_BYTES = 2 * SLICE_BYTES;
+    constexpr int B_TAP = NOUT * CK * 2;
+    constexpr int COUT = NOUT / 2;
+    constexpr uint32_t TCOLS = 2 * NOUT < 32 ? 32 : 2 * NOUT;      // two accumulator buffers
+    constexpr int NS = kConvStages;
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* sB = smem;
+    unsigned char* sA = smem + a.taps * B_TAP;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sA + NS * A_BYTES);
+    uint64_t* empty = full + NS;
+    uint64_t* tfull = empty + NS;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* bfull = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows = *a.n_rows;
+    const int D = a.D, taps = a.taps;
+    const int n_slices = rows * D;
+    const int n_tiles = (n_slices + 1) / 2;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        mbar_init(bfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(bfull, taps * B_TAP);
+            for (int t = 0; t < taps; ++t) tma_load_2d(sB + t * B_TAP, &map_b, bfull, 0, t * NOUT);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int tap = 0; tap < taps; ++tap, ++it) {
+                    const int s = it % NS;
+                    const uint32_t ph = (it / NS) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], A_BYTES);
+                    const int kd = D == 3 ? tap / 9 - 1 : 0, kh = (tap / 3) % 3 - 1, kw = tap % 3 - 1;
+#pragma unroll
+                    for (int sl = 0; sl < 2; ++sl) {
+                        const int L = 2 * tile + sl;
+                        const int row = L < n_slices ? L / D : a.rows_cap;      // past the end: fully out of bounds -> zeros
+                        const int d = L < n_slices ? L % D : 0;
+                        tma_load_5d(sA + s * A_BYTES + sl * SLICE_BYTES, &map_a, &full[s], 0, kw, kh, d + kd, row);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(NOUT);
+            mbar_wait(bfull, 0);
+            int it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+                const int buf = tl & 1;
+                mbar_wait(&tempty[buf], ((tl >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * NOUT);
+                for (int tap = 0; tap < taps; ++tap, ++it) {
+                    const int s = it % NS;
+                    const uint32_t ph = (it / NS) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = make_desc<SW>(smem_u32(sA + s * A_BYTES));
+                    const uint64_t db = make_desc<SW>(smem_u32(sB + tap * B_TAP));
+#pragma unroll
+                    for (int kk = 0; kk < CK / 16; ++kk)
+                        umma_bf16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (tap | kk) != 0);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tfull[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+            const int buf = tl & 1;
+            mbar_wait(&tfull[buf], (tl >> 1) & 1);
+            tc_fence_after();
+            const int m = q * 32 + lane;
+            const int L = 2 * tile + (m >> 6), pos = m & 63;
+            const bool valid = L < n_slices;
+            const int row = L / D, d = L % D;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NOUT);
+            float y[COUT];
+            {
+                uint32_t v[32];
+                tmem_ld32(taddr, v);
+                if (NOUT == 32) {
+#pragma unroll
+                    for (int c = 0; c < COUT; ++c) y[c] = __uint_as_float(v[c]) + __uint_as_float(v[COUT + c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) y[c % COUT] = __uint_as_float(v[c]);
+                    uint32_t v2[32];
+                    tmem_ld32(taddr + 32, v2);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) y[c % COUT] += __uint_as_float(v2[c]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);           // accumulator buffer may be overwritten
+            if (valid) {
+                __align__(16) __nv_bfloat16 hi[COUT], lo[COUT];
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) {
+                    float x = fmaxf(y[c] + __ldg(a.bias + c), 0.f);
+                    if (MODE == 1) x = fmaf(x, __ldg(a.bn_scale + c), __ldg(a.bn_shift + c));
+                    split2(x, hi[c], lo[c]);
+                }
+                const size_t p = ((size_t)row * D + d) * 64 + pos;
+                if (MODE == 0) {
+                    uint4* o = reinterpret_cast<uint4*>(a.out0 + p * (2 * COUT));
+#pragma unroll
+                    for (int i = 0; i < COUT / 8; ++i) o[i] = reinterpret_cast<const uint4*>(hi)[i];
+#pragma unroll
+                    for (int i = 0; i < COUT / 8; ++i) o[COUT / 8 + i] = reinterpret_cast<const uint4*>(lo)[i];
+                } else {
+                    uint4* oh = reinterpret_cast<uint4*>(a.out0 + p * COUT);
+                    uint4* ol = reinterpret_cast<uint4*>(a.out1 + p * COUT);
+#pragma unroll
+                    for (int i = 0; i < COUT / 8; ++i) {
+                        oh[i] = reinterpret_cast<const uint4*>(hi)[i];
+                        ol[i] = reinterpret_cast<const uint4*>(lo)[i];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TCOLS>(tmem_base);
+    }
+}
+
+// =====================================================================================================
+// Dense layers: split-bf16 GEMM, 128 x BN tiles
+// =====================================================================================================
+struct GemmTcArgs {
+    const int* n_rows;
+    const float *bias, *bn_scale, *bn_shift;
+    __nv_bfloat16 *out_hi, *out_lo;      // MODE 0: next layer's operand [row][N]
+    float* out;                          // MODE 1: [row][57]
+    float* keypoints;                    // MODE 1: scatter target or nullptr
+    const int32_t *row_scene, *row_slot;
+    int K, N, tcap;
+};
+
+constexpr int kGemmThreads = 192;
+constexpr int kBK = 64;
+template <int BN, int STAGES>
+constexpr int gemm_smem_bytes() { return STAGES * (2 * 128 * kBK * 2 + 2 * BN * kBK * 2) + 1024 + 256; }
+
+// MODE 0: out = split(BN(relu(acc + bias)))      MODE 1: out = acc + bias (first 57 columns), scattered to tracks
+template <int BN, int STAGES, int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+               const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
+               const GemmTcArgs a) {
+    constexpr int BM = 128, UK = 16;
+    constexpr int A_BYTES = BM * kBK * 2, B_BYTES = BN * kBK * 2;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
     const int rows = *a.n_rows;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    if (m0 >= rows) return;                                   // uniform per CTA
+    if (m0 >= rows) return;
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = a.K / BK;
+    const int nkb = a.K / kBK;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah) : "memory");
@@ -141,19 +353,13 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant_
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
-                     "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+    tc_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = *tmem_base_slot;
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
@@ -161,92 +367,106 @@ fc1_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant_
                 mbar_wait(&empty[s], ph ^ 1);
                 unsigned char* st = smem + s * STAGE_BYTES;
                 mbar_expect_tx(&full[s], STAGE_BYTES);
-                tma_load_2d(st, &map_ah, &full[s], kb * BK, m0);
-                tma_load_2d(st + A_BYTES, &map_al, &full[s], kb * BK, m0);
-                tma_load_2d(st + 2 * A_BYTES, &map_wh, &full[s], kb * BK, n0);
-                tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_wl, &full[s], kb * BK, n0);
+                tma_load_2d(st, &map_ah, &full[s], kb * kBK, m0);
+                tma_load_2d(st + A_BYTES, &map_al, &full[s], kb * kBK, m0);
+                tma_load_2d(st + 2 * A_BYTES, &map_wh, &full[s], kb * kBK, n0);
+                tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_wl, &full[s], kb * kBK, n0);
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            const uint32_t idesc = make_idesc();
+            const uint32_t idesc = make_idesc(BN);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&full[s], ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tc_fence_after();
                 const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t dah = make_desc_sw128(st), dal = make_desc_sw128(st + A_BYTES);
-                const uint64_t dwh = make_desc_sw128(st + 2 * A_BYTES), dwl = make_desc_sw128(st + 2 * A_BYTES + B_BYTES);
+                const uint64_t dah = make_desc<128>(st), dal = make_desc<128>(st + A_BYTES);
+                const uint64_t dwh = make_desc<128>(st + 2 * A_BYTES), dwl = make_desc<128>(st + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < BK / UK; ++kk) {
-                    const uint64_t adv = (uint64_t)((kk * UK * 2) >> 4);     // +32 bytes per K step inside the atom
+                for (int kk = 0; kk < kBK / UK; ++kk) {
+                    const uint64_t adv = (uint64_t)((kk * UK * 2) >> 4);
                     umma_bf16(tmem_d, dah + adv, dwh + adv, idesc, (kb | kk) != 0);
                     umma_bf16(tmem_d, dah + adv, dwl + adv, idesc, 1);
                     umma_bf16(tmem_d, dal + adv, dwh + adv, idesc, 1);
                 }
-                umma_commit(&empty[s]);                       // frees the stage when the MMAs above have read it
+                umma_commit(&empty[s]);
             }
-            umma_commit(tmem_full);                           // accumulator complete
+            umma_commit(tmem_full);
         }
     } else {
-        // ===== epilogue: 4 warps, each owns the TMEM lane quadrant (warp % 4) =====
         const int q = warp & 3;
         mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_fence_after();
         const int row = m0 + q * 32 + lane;
-        float* orow = a.out + (size_t)row * a.H + n0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (row < rows) {
+            if (row >= rows) continue;
+            if (MODE == 0) {
+                __align__(16) __nv_bfloat16 hi[32], lo[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    float* po = reinterpret_cast<float*>(&o);
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c0 + j;
+                    float x = fmaxf(__uint_as_float(v[j]) + __ldg(a.bias + n), 0.f);
+                    x = fmaf(x, __ldg(a.bn_scale + n), __ldg(a.bn_shift + n));
+                    split2(x, hi[j], lo[j]);
+                }
+                uint4* oh = reinterpret_cast<uint4*>(a.out_hi + (size_t)row * a.N + n0 + c0);
+                uint4* ol = reinterpret_cast<uint4*>(a.out_lo + (size_t)row * a.N + n0 + c0);
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int n = n0 + c0 + j + t;
-                        const float x = fmaxf(__uint_as_float(v[j + t]) + __ldg(a.bias + n), 0.f);
-                        po[t] = fmaf(x, __ldg(a.bn_scale + n), __ldg(a.bn_shift + n));
+                for (int i = 0; i < 4; ++i) {
+                    oh[i] = reinterpret_cast<const uint4*>(hi)[i];
+                    ol[i] = reinterpret_cast<const uint4*>(lo)[i];
+                }
+            } else {
+                const int s = a.keypoints ? a.row_scene[row] : 0, slot = a.keypoints ? a.row_slot[row] : 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c0 + j;
+                    if (n < kKp) {
+                        const float x = __uint_as_float(v[j]) + __ldg(a.bias + n);
+                        a.out[(size_t)row * kKp + n] = x;
+                        if (a.keypoints) a.keypoints[((size_t)s * a.tcap + slot) * kKp + n] = x;
                     }
-                    *reinterpret_cast<float4*>(orow + c0 + j) = o;
                 }
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+        tc_fence_after();
+        tmem_dealloc<TCOLS>(tmem_d);
     }
 }
 
-// fp32 -> (hi, lo) bf16 split of the activation matrix, rows < *n_rows only.
-__global__ void split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, const int* n_rows, int K) {
-    const size_t total = (size_t)(*n_rows) * K / 4;
+// fp32 feature maps [rows][P][5] -> packed bf16 [rows][P][16] = (hi c0..4, 0,0,0 | lo c0..4, 0,0,0)
+__global__ void pack_input_kernel(const float* __restrict__ feats, __nv_bfloat16* __restrict__ out, const int* n_rows,
+                                  int P) {
+    const size_t total = (size_t)(*n_rows) * P;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const float4 v = reinterpret_cast<const float4*>(src)[i];
-        const float f[4] = {v.x, v.y, v.z, v.w};
-        __nv_bfloat16 h[4], l[4];
+        __align__(16) __nv_bfloat16 v[16];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            h[t] = __float2bfloat16_rn(f[t]);
-            l[t] = __float2bfloat16_rn(f[t] - __bfloat162float(h[t]));
-        }
-        reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
-        reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+        for (int k = 0; k < 16; ++k) v[k] = __float2bfloat16_rn(0.f);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) split2(feats[i * 5 + k], v[k], v[8 + k]);
+        reinterpret_cast<uint4*>(out + i * 16)[0] = reinterpret_cast<const uint4*>(v)[0];
+        reinterpret_cast<uint4*>(out + i * 16)[1] = reinterpret_cast<const uint4*>(v)[1];
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
 struct TcImpl {
-    __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr, *w_hi = nullptr, *w_lo = nullptr;
-    CUtensorMap map_ah, map_al, map_wh, map_wl;
+    int D = 0, taps = 0, Kf = 0, H = 0, rows_cap = 0, rows_pad = 0;
+    __nv_bfloat16 *in_p = nullptr, *act1_p = nullptr;                 // packed activations
+    __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr;                   // dense-1 operand [rows_pad][Kf]
+    __nv_bfloat16 *h_hi = nullptr, *h_lo = nullptr;                   // dense-2 operand [rows_pad][H]
+    __nv_bfloat16 *w1b = nullptr, *w2b = nullptr;                     // conv B matrices [taps][NOUT][CK]
+    __nv_bfloat16 *wd1_hi = nullptr, *wd1_lo = nullptr, *wd2_hi = nullptr, *wd2_lo = nullptr;
+    CUtensorMap m_in, m_act1, m_w1b, m_w2b, m_ah, m_al, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l;
 };
 
 static std::string g_tc_err;
@@ -268,18 +488,35 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D bf16 tensor [rows][K] (K contiguous), box = [box_rows][BK], 128-byte swizzle.
-static int make_map(CUtensorMap* m, void* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+static CUtensorMapSwizzle swz(int bytes) {
+    return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// 2-D bf16 tensor [rows][K] (K contiguous), box [box_rows][box_k], swizzle span = box_k * 2 bytes.
+static int make_map_2d(CUtensorMap* m, void* base, uint64_t rows, uint64_t K, uint32_t box_rows, uint32_t box_k) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { g_tc_err = "cuTensorMapEncodeTiled not available"; return -1; }
     cuuint64_t dims[2] = {K, rows};
     cuuint64_t strides[1] = {K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)tc::BK, box_rows};
+    cuuint32_t box[2] = {box_k, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return -1; }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swz((int)box_k * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(2d) failed (" + std::to_string((int)r) + ")"; return -1; }
+    return 0;
+}
+
+// 5-D channels-last activation [rows][D][8][8][C] bf16, box {C, 8, 8, 1, 1}: one 8x8 slice of one tap.
+static int make_map_act(CUtensorMap* m, void* base, uint64_t rows, int D, int C) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { g_tc_err = "cuTensorMapEncodeTiled not available"; return -1; }
+    cuuint64_t dims[5] = {(cuuint64_t)C, 8, 8, (cuuint64_t)D, rows};
+    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * 8, (cuuint64_t)C * 2 * 64, (cuuint64_t)C * 2 * 64 * D};
+    cuuint32_t box[5] = {(cuuint32_t)C, 8, 8, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swz(C * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(5d) failed (" + std::to_string((int)r) + ")"; return -1; }
     return 0;
 }
 
@@ -297,60 +534,162 @@ static inline float bf2f(uint16_t h) {
     return f;
 }
 
-int pose_tc_init(PoseTc* t, const float* w_kh, int K, int H, int rows_cap, cudaStream_t) {
+template <class T>
+static bool dev_alloc(T** p, size_t bytes, bool zero = false) {
+    if (cudaMalloc((void**)p, bytes) != cudaSuccess) return false;
+    if (zero) cudaMemset(*p, 0, bytes);
+    return true;
+}
+static bool upload(__nv_bfloat16** d, const std::vector<uint16_t>& h) {
+    if (!dev_alloc(d, h.size() * 2)) return false;
+    return cudaMemcpy(*d, h.data(), h.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+// Conv B operand of one layer: [taps][2*cout][2*cinp] (K-major rows):
+//   n <  cout : k <  cinp -> w_hi[k][n]        k >= cinp -> w_hi[k-cinp][n]
+//   n >= cout : k <  cinp -> w_lo[k][n-cout]   k >= cinp -> 0
+// w is Keras layout [tap][cin][cout]; input channels are zero-padded from cin to cinp.
+static std::vector<uint16_t> conv_b(const float* w, int taps, int cin, int cinp, int cout) {
+    const int CK = 2 * cinp, NO = 2 * cout;
+    std::vector<uint16_t> b((size_t)taps * NO * CK, 0);
+    for (int t = 0; t < taps; ++t)
+        for (int n = 0; n < NO; ++n)
+            for (int k = 0; k < CK; ++k) {
+                const int ci = k % cinp, co = n % cout;
+                if (ci >= cin) continue;
+                const float wv = w[((size_t)t * cin + ci) * cout + co];
+                const uint16_t hi = f2bf(wv), lo = f2bf(wv - bf2f(hi));
+                uint16_t v = 0;
+                if (n < cout) v = hi;
+                else if (k < cinp) v = lo;
+                b[((size_t)t * NO + n) * CK + k] = v;
+            }
+    return b;
+}
+
+// Dense weight [K][N] (Keras in,out) -> K-major [Npad][K] hi / lo.
+static void dense_b(const float* w, int K, int N, int Npad, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+    hi.assign((size_t)Npad * K, 0);
+    lo.assign((size_t)Npad * K, 0);
+    for (int k = 0; k < K; ++k)
+        for (int n = 0; n < N; ++n) {
+            const float wv = w[(size_t)k * N + n];
+            const uint16_t h = f2bf(wv);
+            hi[(size_t)n * K + k] = h;
+            lo[(size_t)n * K + k] = f2bf(wv - bf2f(h));
+        }
+}
+
+int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int rows_cap) {
     pose_tc_free(t);
-    t->K = K; t->H = H; t->rows_cap = rows_cap;
-    if (K % tc::BK != 0 || H % tc::BN != 0) { g_tc_err = "K/H not tileable"; return -1; }
     TcImpl* im = new TcImpl();
     t->impl = im;
-    const size_t rows_pad = ((size_t)rows_cap + tc::BM - 1) / tc::BM * tc::BM;
-    const size_t an = rows_pad * K, wn = (size_t)H * K;
-    if (cudaMalloc((void**)&im->a_hi, an * 2) != cudaSuccess || cudaMalloc((void**)&im->a_lo, an * 2) != cudaSuccess ||
-        cudaMalloc((void**)&im->w_hi, wn * 2) != cudaSuccess || cudaMalloc((void**)&im->w_lo, wn * 2) != cudaSuccess) {
-        g_tc_err = "cudaMalloc failed";
+    im->D = D; im->taps = D == 3 ? 27 : 9; im->Kf = D * 64 * 32; im->H = D * 512; im->rows_cap = rows_cap;
+    im->rows_pad = (rows_cap + 127) / 128 * 128;
+    t->D = D; t->K = im->Kf; t->H = im->H; t->rows_cap = rows_cap;
+    const size_t R = im->rows_pad, P = (size_t)D * 64;
+    bool ok = dev_alloc(&im->in_p, R * P * 16 * 2, true) && dev_alloc(&im->act1_p, R * P * 32 * 2, true) &&
+              dev_alloc(&im->a_hi, R * im->Kf * 2, true) && dev_alloc(&im->a_lo, R * im->Kf * 2, true) &&
+              dev_alloc(&im->h_hi, R * im->H * 2, true) && dev_alloc(&im->h_lo, R * im->H * 2, true);
+    if (!ok) { g_tc_err = "cudaMalloc failed (activations)"; return -1; }
+    std::vector<uint16_t> hi, lo;
+    ok = upload(&im->w1b, conv_b(blob + off[0], im->taps, 5, 8, 16)) &&
+         upload(&im->w2b, conv_b(blob + off[2], im->taps, 16, 16, 32));
+    dense_b(blob + off[8], im->Kf, im->H, im->H, hi, lo);
+    ok = ok && upload(&im->wd1_hi, hi) && upload(&im->wd1_lo, lo);
+    dense_b(blob + off[14], im->H, kKp, 64, hi, lo);
+    ok = ok && upload(&im->wd2_hi, hi) && upload(&im->wd2_lo, lo);
+    if (!ok) { g_tc_err = "cudaMalloc/cudaMemcpy failed (weights)"; return -1; }
+    if (make_map_act(&im->m_in, im->in_p, R, D, 16) || make_map_act(&im->m_act1, im->act1_p, R, D, 32) ||
+        make_map_2d(&im->m_w1b, im->w1b, (uint64_t)im->taps * 32, 16, 32, 16) ||
+        make_map_2d(&im->m_w2b, im->w2b, (uint64_t)im->taps * 64, 32, 64, 32) ||
+        make_map_2d(&im->m_ah, im->a_hi, R, im->Kf, 128, 64) || make_map_2d(&im->m_al, im->a_lo, R, im->Kf, 128, 64) ||
+        make_map_2d(&im->m_w1h, im->wd1_hi, im->H, im->Kf, 256, 64) ||
+        make_map_2d(&im->m_w1l, im->wd1_lo, im->H, im->Kf, 256, 64) ||
+        make_map_2d(&im->m_hh, im->h_hi, R, im->H, 128, 64) || make_map_2d(&im->m_hl, im->h_lo, R, im->H, 128, 64) ||
+        make_map_2d(&im->m_w2h, im->wd2_hi, 64, im->H, 64, 64) || make_map_2d(&im->m_w2l, im->wd2_lo, 64, im->H, 64, 64))
         return -1;
-    }
-    cudaMemset(im->a_hi, 0, an * 2);
-    cudaMemset(im->a_lo, 0, an * 2);
-    // W is Keras (in, out) = [K][H]; the B operand wants it K-major per output column: [H][K]
-    std::vector<uint16_t> hi(wn), lo(wn);
-    for (int k = 0; k < K; ++k)
-        for (int h = 0; h < H; ++h) {
-            const float w = w_kh[(size_t)k * H + h];
-            const uint16_t bh = f2bf(w);
-            hi[(size_t)h * K + k] = bh;
-            lo[(size_t)h * K + k] = f2bf(w - bf2f(bh));
-        }
-    cudaMemcpy(im->w_hi, hi.data(), wn * 2, cudaMemcpyHostToDevice);
-    cudaMemcpy(im->w_lo, lo.data(), wn * 2, cudaMemcpyHostToDevice);
-    if (make_map(&im->map_ah, im->a_hi, rows_pad, K, tc::BM) || make_map(&im->map_al, im->a_lo, rows_pad, K, tc::BM) ||
-        make_map(&im->map_wh, im->w_hi, H, K, tc::BN) || make_map(&im->map_wl, im->w_lo, H, K, tc::BN))
-        return -1;
-    if (cudaFuncSetAttribute(fc1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES) != cudaSuccess) {
-        g_tc_err = "cudaFuncSetAttribute(fc1_tc_kernel) failed";
-        return -1;
-    }
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_tc_kernel<16, 32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 conv_smem_bytes_tc<16, 32>(27));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_tc_kernel<32, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 conv_smem_bytes_tc<32, 64>(27));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_kernel<256, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gemm_smem_bytes<256, 2>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_kernel<64, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gemm_smem_bytes<64, 4>());
+    if (e != cudaSuccess) { g_tc_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
     t->ready = true;
     return 0;
 }
 
-int pose_tc_fc1(PoseTc* t, const FcArgs& a, int max_rows, cudaStream_t st, int* n_launches) {
+__nv_bfloat16* pose_tc_input(PoseTc* t) {
+    TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
+    return im ? im->in_p : nullptr;
+}
+
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_tc_err = std::string(what) + ": " + cudaGetErrorString(e); return -1; }
+    return 0;
+}
+
+int pose_tc_pack_input(PoseTc* t, const float* feats, const int* n_rows, cudaStream_t st) {
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
-    split_bf16_kernel<<<148 * 8, 256, 0, st>>>(a.A, im->a_hi, im->a_lo, a.n_rows, a.K);
-    TcGemmArgs g{a.n_rows, a.bias, a.bn_scale, a.bn_shift, a.out, a.K, a.H};
-    dim3 grid(a.H / tc::BN, (max_rows + tc::BM - 1) / tc::BM);
-    fc1_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(im->map_ah, im->map_al, im->map_wh, im->map_wl, g);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
+    pack_input_kernel<<<148 * 4, 256, 0, st>>>(feats, im->in_p, n_rows, im->D * 64);
+    return check_launch("pack_input_kernel");
+}
+
+int pose_tc_conv(PoseTc* t, const PoseTcRun& r, cudaStream_t st, int* n_launches) {
+    TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
+    if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
+    ConvTcArgs c1{r.n_rows, r.b1, nullptr, nullptr, im->act1_p, nullptr, im->D, im->taps, im->rows_pad};
+    conv_tc_kernel<16, 32, 0><<<148, kConvThreads, conv_smem_bytes_tc<16, 32>(27), st>>>(im->m_in, im->m_w1b, c1);
+    if (check_launch("conv_tc_kernel<conv1>")) return -1;
+    ConvTcArgs c2{r.n_rows, r.b2, r.bn1_scale, r.bn1_shift, im->a_hi, im->a_lo, im->D, im->taps, im->rows_pad};
+    conv_tc_kernel<32, 64, 1><<<148, kConvThreads, conv_smem_bytes_tc<32, 64>(27), st>>>(im->m_act1, im->m_w2b, c2);
+    if (check_launch("conv_tc_kernel<conv2>")) return -1;
     if (n_launches) *n_launches = 2;
+    return 0;
+}
+
+int pose_tc_fc1(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, int* n_launches) {
+    TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
+    if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
+    GemmTcArgs g{r.n_rows, r.bd1, r.bn2_scale, r.bn2_shift, im->h_hi, im->h_lo, nullptr, nullptr, nullptr, nullptr,
+                 im->Kf, im->H, r.tcap};
+    dim3 grid(im->H / 256, (max_rows + 127) / 128);
+    gemm_tc_kernel<256, 2, 0><<<grid, kGemmThreads, gemm_smem_bytes<256, 2>(), st>>>(im->m_ah, im->m_al, im->m_w1h,
+                                                                                    im->m_w1l, g);
+    if (check_launch("gemm_tc_kernel<dense1>")) return -1;
+    if (n_launches) *n_launches = 1;
+    return 0;
+}
+
+int pose_tc_fc2(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, int* n_launches) {
+    TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
+    if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
+    GemmTcArgs g{r.n_rows, r.bd2, nullptr, nullptr, nullptr, nullptr, r.out, r.keypoints, r.row_scene, r.row_slot,
+                 im->H, 64, r.tcap};
+    dim3 grid(1, (max_rows + 127) / 128);
+    gemm_tc_kernel<64, 4, 1><<<grid, kGemmThreads, gemm_smem_bytes<64, 4>(), st>>>(im->m_hh, im->m_hl, im->m_w2h,
+                                                                                  im->m_w2l, g);
+    if (check_launch("gemm_tc_kernel<dense2>")) return -1;
+    if (n_launches) *n_launches = 1;
     return 0;
 }
 
 void pose_tc_free(PoseTc* t) {
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (im) {
-        for (void* p : {(void*)im->a_hi, (void*)im->a_lo, (void*)im->w_hi, (void*)im->w_lo})
+        for (void* p : {(void*)im->in_p, (void*)im->act1_p, (void*)im->a_hi, (void*)im->a_lo, (void*)im->h_hi,
+                        (void*)im->h_lo, (void*)im->w1b, (void*)im->w2b, (void*)im->wd1_hi, (void*)im->wd1_lo,
+                        (void*)im->wd2_hi, (void*)im->wd2_lo})
             if (p) cudaFree(p);
         delete im;
     }
