@@ -127,45 +127,66 @@ __device__ __forceinline__ void split2(float x, __nv_bfloat16& hi, __nv_bfloat16
 }
 
 // =====================================================================================================
-// Convolution as TMA-im2col implicit GEMM
+// Convolution as a shifted-window implicit GEMM
 // =====================================================================================================
+// First version (git history, profiles/r01_ncu_full_tma_im2col_conv.md): one TMA box per tap and slice (im2col by
+// tensor-map coordinates, zero padding by out-of-bounds fill).  Correct, but the TMA unit is row-rate bound on
+// 32/64-byte rows (~5 cycles per row, 27x re-read): 193 us + 200 us for conv1 + conv2 at ~1900 rows.
+//
+// Current version: per sample the activation slab is staged ONCE per kh in {-1,0,+1} into shared memory by four
+// producer warps (cp.async, 16 B each), zero-padded in d and w, in the un-swizzled UMMA core-matrix layout with
+// h as the row inside an 8-row atom:
+//        slab_kh[d' = 0..D+1][w'' = 0..9][chunk][h = 0..7][8 ch]     entry = act[d'-1][h + kh][w''-1]
+// With output rows ordered (d, w'', h) every tap (kd, kh, kw) is the SAME tile shifted by (1+kd)*10 + kw whole
+// atoms inside slab_kh -- so all 27 taps are tcgen05.mma instructions on shifted shared-memory descriptors, and
+// nobody copies im2col columns.  Output columns w'' = 0 and 9 are padding (discarded), i.e. 240 of the 256 MMA
+// rows per sample are computed and 192 kept.  The three kh slabs form a ring: slab_kh of the next sample is
+// refilled while the other two are still being multiplied.
 struct ConvTcArgs {
     const int* n_rows;
     const float *bias, *bn_scale, *bn_shift;       // bn_* only for MODE 1
+    const __nv_bfloat16* in;                       // packed input  [row][D][8][8][CK]  (hi | lo per position)
     __nv_bfloat16* out0;                           // MODE 0: act1 packed [row][D][8][8][32]; MODE 1: A_hi [row][Kf]
     __nv_bfloat16* out1;                           // MODE 1: A_lo [row][Kf]
-    int D, taps, rows_cap;
+    int D, taps;
 };
 
-constexpr int kConvStages = 8;
-constexpr int kConvThreads = 192;
+constexpr int kSlabThreads = 320;                  // warps 0-3 producers, 4 MMA, 5 weight loader, 6-9 epilogue
+constexpr int kSlabAtoms = 1 + 5 * 10 + 3;         // one guard atom in front, three behind (junk rows stay inside)
 
 template <int CK, int NOUT>
 constexpr int conv_smem_bytes_tc(int taps) {
-    return taps * NOUT * CK * 2 + kConvStages * 128 * CK * 2 + 1024 + 512;
+    return taps * NOUT * CK * 2 + 3 * kSlabAtoms * (CK / 8) * 128 + 1024 + 512;
+}
+
+__device__ __forceinline__ uint64_t make_desc_interleaved(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;     // K direction: distance between 8x16B core matrices
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;     // M direction: distance between 8-row groups
+    d |= (uint64_t)1 << 46;                         // version (sm_100); layout type 0 = no swizzle
+    return d;
 }
 
 // CK   = K' per tap = 2 * padded input channels (hi | lo): 16 for conv1, 32 for conv2
 // NOUT = MMA N     = 2 * output channels: 32 for conv1, 64 for conv2
 template <int CK, int NOUT, int MODE>
-__global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const ConvTcArgs a) {
-    constexpr int SW = CK * 2;                       // row bytes == swizzle span
-    constexpr int SLICE_BYTES = 64 * CK * 2;
-    constexpr int A_BYTES = 2 * SLICE_BYTES;
+__global__ void __launch_bounds__(kSlabThreads, 1)
+conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) {
+    constexpr int NCH = CK / 8;                      // 16-byte chunks per position
+    constexpr int ATOM = NCH * 128;                  // bytes of one 8-row atom
+    constexpr int SLAB_BYTES = kSlabAtoms * ATOM;
     constexpr int B_TAP = NOUT * CK * 2;
     constexpr int COUT = NOUT / 2;
-    constexpr uint32_t TCOLS = 2 * NOUT < 32 ? 32 : 2 * NOUT;      // two accumulator buffers
-    constexpr int NS = kConvStages;
+    constexpr uint32_t TCOLS = 4 * NOUT;             // 2 accumulator buffers x 2 M tiles
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* sB = smem;
-    unsigned char* sA = smem + a.taps * B_TAP;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sA + NS * A_BYTES);
-    uint64_t* empty = full + NS;
-    uint64_t* tfull = empty + NS;
+    unsigned char* slab = smem + a.taps * B_TAP;
+    uint64_t* sfull = reinterpret_cast<uint64_t*>(slab + 3 * SLAB_BYTES);
+    uint64_t* sempty = sfull + 3;
+    uint64_t* tfull = sempty + 3;
     uint64_t* tempty = tfull + 2;
     uint64_t* bfull = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
@@ -173,110 +194,133 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows = *a.n_rows;
     const int D = a.D, taps = a.taps;
-    const int n_slices = rows * D;
-    const int n_tiles = (n_slices + 1) / 2;
+    const int MT = D == 3 ? 2 : 1;
 
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    // static zero padding (d, w borders and the h rows a shifted copy never receives)
+    for (int i = threadIdx.x; i < 3 * SLAB_BYTES / 16; i += kSlabThreads)
+        reinterpret_cast<uint4*>(slab)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 4 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int c = 0; c < 3; ++c) { mbar_init(&sfull[c], 128); mbar_init(&sempty[c], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
         mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+    if (warp == 4) tmem_alloc<TCOLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp < 4) {
+        // ===== producers: global -> three h-shifted slabs =====
+        const int tid = threadIdx.x;
+        int n = 0;
+        for (int row = blockIdx.x; row < rows; row += gridDim.x, ++n) {
+            const __nv_bfloat16* src = a.in + (size_t)row * D * 64 * CK;
+            for (int c = 0; c < 3; ++c) {
+                const int kh = c - 1;
+                mbar_wait(&sempty[c], (uint32_t)((n & 1) ^ 1));
+                unsigned char* sl = slab + c * SLAB_BYTES;
+                for (int i = tid; i < D * 64 * NCH; i += 128) {
+                    const int chunk = i % NCH, pos = i / NCH;
+                    const int w = pos & 7, h = (pos >> 3) & 7, d = pos >> 6;
+                    const int hh = h - kh;
+                    if (hh < 0 || hh > 7) continue;
+                    unsigned char* dst = sl + (1 + (d + 1) * 10 + (w + 1)) * ATOM + chunk * 128 + hh * 16;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)),
+                                 "l"(src + (size_t)pos * CK + chunk * 8)
+                                 : "memory");
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&sfull[c]);
+            }
+        }
+    } else if (warp == 5) {
         if (lane == 0) {
             mbar_expect_tx(bfull, taps * B_TAP);
             for (int t = 0; t < taps; ++t) tma_load_2d(sB + t * B_TAP, &map_b, bfull, 0, t * NOUT);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int tap = 0; tap < taps; ++tap, ++it) {
-                    const int s = it % NS;
-                    const uint32_t ph = (it / NS) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], A_BYTES);
-                    const int kd = D == 3 ? tap / 9 - 1 : 0, kh = (tap / 3) % 3 - 1, kw = tap % 3 - 1;
-#pragma unroll
-                    for (int sl = 0; sl < 2; ++sl) {
-                        const int L = 2 * tile + sl;
-                        const int row = L < n_slices ? L / D : a.rows_cap;      // past the end: fully out of bounds -> zeros
-                        const int d = L < n_slices ? L % D : 0;
-                        tma_load_5d(sA + s * A_BYTES + sl * SLICE_BYTES, &map_a, &full[s], 0, kw, kh, d + kd, row);
-                    }
-                }
-            }
         }
-    } else if (warp == 1) {
+    } else if (warp == 4) {
+        // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = make_idesc(NOUT);
             mbar_wait(bfull, 0);
-            int it = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-                const int buf = tl & 1;
-                mbar_wait(&tempty[buf], ((tl >> 1) & 1) ^ 1);
+            int n = 0;
+            for (int row = blockIdx.x; row < rows; row += gridDim.x, ++n) {
+                const int buf = n & 1;
+                mbar_wait(&tempty[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * NOUT);
-                for (int tap = 0; tap < taps; ++tap, ++it) {
-                    const int s = it % NS;
-                    const uint32_t ph = (it / NS) & 1;
-                    mbar_wait(&full[s], ph);
+                for (int c = 0; c < 3; ++c) {
+                    mbar_wait(&sfull[c], (uint32_t)(n & 1));
                     tc_fence_after();
-                    const uint64_t da = make_desc<SW>(smem_u32(sA + s * A_BYTES));
-                    const uint64_t db = make_desc<SW>(smem_u32(sB + tap * B_TAP));
+                    const uint32_t sl = smem_u32(slab + c * SLAB_BYTES);
+                    for (int kd = (D == 3 ? -1 : 0); kd <= (D == 3 ? 1 : 0); ++kd) {
+                        for (int kw = -1; kw <= 1; ++kw) {
+                            const int tap = D == 3 ? ((kd + 1) * 3 + c) * 3 + (kw + 1) : c * 3 + (kw + 1);
+                            const bool first = c == 0 && kd == (D == 3 ? -1 : 0) && kw == -1;
+                            const uint64_t db = make_desc<CK * 2>(smem_u32(sB + tap * B_TAP));
+                            for (int mt = 0; mt < MT; ++mt) {
+                                const uint32_t aaddr = sl + (uint32_t)((1 + mt * 16 + (1 + kd) * 10 + kw) * ATOM);
+                                const uint32_t tmem_d = tmem_base + (uint32_t)((buf * 2 + mt) * NOUT);
 #pragma unroll
-                    for (int kk = 0; kk < CK / 16; ++kk)
-                        umma_bf16(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (tap | kk) != 0);
-                    umma_commit(&empty[s]);
+                                for (int kk = 0; kk < CK / 16; ++kk)
+                                    umma_bf16(tmem_d, make_desc_interleaved(aaddr + kk * 256, 128, ATOM),
+                                              db + (uint64_t)(kk * 2), idesc, !(first && kk == 0));
+                            }
+                        }
+                    }
+                    umma_commit(&sempty[c]);          // slab_kh may be refilled for the next sample
                 }
                 umma_commit(&tfull[buf]);
             }
         }
     } else {
+        // ===== epilogue: warps 6-9, TMEM lane quadrant = warp % 4 =====
         const int q = warp & 3;
-        int tl = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-            const int buf = tl & 1;
-            mbar_wait(&tfull[buf], (tl >> 1) & 1);
+        int n = 0;
+        for (int row = blockIdx.x; row < rows; row += gridDim.x, ++n) {
+            const int buf = n & 1;
+            mbar_wait(&tfull[buf], (uint32_t)((n >> 1) & 1));
             tc_fence_after();
-            const int m = q * 32 + lane;
-            const int L = 2 * tile + (m >> 6), pos = m & 63;
-            const bool valid = L < n_slices;
-            const int row = L / D, d = L % D;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NOUT);
-            float y[COUT];
-            {
+            float y[2][COUT];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                if (mt >= MT) break;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + mt) * NOUT);
                 uint32_t v[32];
                 tmem_ld32(taddr, v);
                 if (NOUT == 32) {
 #pragma unroll
-                    for (int c = 0; c < COUT; ++c) y[c] = __uint_as_float(v[c]) + __uint_as_float(v[COUT + c]);
+                    for (int c = 0; c < COUT; ++c) y[mt][c] = __uint_as_float(v[c]) + __uint_as_float(v[COUT + c]);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) y[c % COUT] = __uint_as_float(v[c]);
-                    uint32_t v2[32];
-                    tmem_ld32(taddr + 32, v2);
+                    for (int c = 0; c < 32; ++c) y[mt][c % COUT] = __uint_as_float(v[c]);
+                    tmem_ld32(taddr + 32, v);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) y[c % COUT] += __uint_as_float(v2[c]);
+                    for (int c = 0; c < 32; ++c) y[mt][c % COUT] += __uint_as_float(v[c]);
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);           // accumulator buffer may be overwritten
-            if (valid) {
+            if (lane == 0) mbar_arrive(&tempty[buf]);           // accumulators are in registers now
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                if (mt >= MT) break;
+                const int m = q * 32 + lane;
+                const int aidx = mt * 16 + (m >> 3), hh = m & 7;
+                const int d = aidx / 10, w2 = aidx % 10;
+                if (d >= D || w2 < 1 || w2 > 8) continue;       // padding columns / junk rows
                 __align__(16) __nv_bfloat16 hi[COUT], lo[COUT];
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) {
-                    float x = fmaxf(y[c] + __ldg(a.bias + c), 0.f);
+                    float x = fmaxf(y[mt][c] + __ldg(a.bias + c), 0.f);
                     if (MODE == 1) x = fmaf(x, __ldg(a.bn_scale + c), __ldg(a.bn_shift + c));
                     split2(x, hi[c], lo[c]);
                 }
-                const size_t p = ((size_t)row * D + d) * 64 + pos;
+                const size_t p = ((size_t)row * D + d) * 64 + hh * 8 + (w2 - 1);
                 if (MODE == 0) {
                     uint4* o = reinterpret_cast<uint4*>(a.out0 + p * (2 * COUT));
 #pragma unroll
@@ -297,7 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 4) {
         tc_fence_after();
         tmem_dealloc<TCOLS>(tmem_base);
     }
@@ -600,8 +644,7 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
     dense_b(blob + off[14], im->H, kKp, 64, hi, lo);
     ok = ok && upload(&im->wd2_hi, hi) && upload(&im->wd2_lo, lo);
     if (!ok) { g_tc_err = "cudaMalloc/cudaMemcpy failed (weights)"; return -1; }
-    if (make_map_act(&im->m_in, im->in_p, R, D, 16) || make_map_act(&im->m_act1, im->act1_p, R, D, 32) ||
-        make_map_2d(&im->m_w1b, im->w1b, (uint64_t)im->taps * 32, 16, 32, 16) ||
+    if (make_map_2d(&im->m_w1b, im->w1b, (uint64_t)im->taps * 32, 16, 32, 16) ||
         make_map_2d(&im->m_w2b, im->w2b, (uint64_t)im->taps * 64, 32, 64, 32) ||
         make_map_2d(&im->m_ah, im->a_hi, R, im->Kf, 128, 64) || make_map_2d(&im->m_al, im->a_lo, R, im->Kf, 128, 64) ||
         make_map_2d(&im->m_w1h, im->wd1_hi, im->H, im->Kf, 256, 64) ||
@@ -611,10 +654,10 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
         return -1;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_tc_kernel<16, 32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(conv_slab_kernel<16, 32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  conv_smem_bytes_tc<16, 32>(27));
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_tc_kernel<32, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(conv_slab_kernel<32, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  conv_smem_bytes_tc<32, 64>(27));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_kernel<256, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -648,12 +691,12 @@ int pose_tc_pack_input(PoseTc* t, const float* feats, const int* n_rows, cudaStr
 int pose_tc_conv(PoseTc* t, const PoseTcRun& r, cudaStream_t st, int* n_launches) {
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
-    ConvTcArgs c1{r.n_rows, r.b1, nullptr, nullptr, im->act1_p, nullptr, im->D, im->taps, im->rows_pad};
-    conv_tc_kernel<16, 32, 0><<<148, kConvThreads, conv_smem_bytes_tc<16, 32>(27), st>>>(im->m_in, im->m_w1b, c1);
-    if (check_launch("conv_tc_kernel<conv1>")) return -1;
-    ConvTcArgs c2{r.n_rows, r.b2, r.bn1_scale, r.bn1_shift, im->a_hi, im->a_lo, im->D, im->taps, im->rows_pad};
-    conv_tc_kernel<32, 64, 1><<<148, kConvThreads, conv_smem_bytes_tc<32, 64>(27), st>>>(im->m_act1, im->m_w2b, c2);
-    if (check_launch("conv_tc_kernel<conv2>")) return -1;
+    ConvTcArgs c1{r.n_rows, r.b1, nullptr, nullptr, im->in_p, im->act1_p, nullptr, im->D, im->taps};
+    conv_slab_kernel<16, 32, 0><<<148, kSlabThreads, conv_smem_bytes_tc<16, 32>(27), st>>>(im->m_w1b, c1);
+    if (check_launch("conv_slab_kernel<conv1>")) return -1;
+    ConvTcArgs c2{r.n_rows, r.b2, r.bn1_scale, r.bn1_shift, im->act1_p, im->a_hi, im->a_lo, im->D, im->taps};
+    conv_slab_kernel<32, 64, 1><<<148, kSlabThreads, conv_smem_bytes_tc<32, 64>(27), st>>>(im->m_w2b, c2);
+    if (check_launch("conv_slab_kernel<conv2>")) return -1;
     if (n_launches) *n_launches = 2;
     return 0;
 }
