@@ -228,6 +228,16 @@ int mmw_pose(mmw_ctx* ctx, const float* feats, int n, float* keypoints);
 #define MMW_RESULT_FLOATS 68
 int mmw_pack_results(mmw_ctx* ctx, float* device_out);
 
+/* Pipelined result read-back for the hot loop: packs the results of the frames queued so far (same layout as
+ * mmw_pack_results) and downloads them into host_out (pinned memory recommended; S * max_tracks *
+ * MMW_RESULT_FLOATS fp32) on a side stream, without blocking the host.  *slot receives the id (0/1) to pass to
+ * mmw_wait_results, which blocks until that download has finished.  Together with mmw_step on pinned host inputs
+ * (uploaded on another side stream into double-buffered staging) the upload of frame k+1, the kernels of frame k
+ * and the download of frame k-1 overlap.  Host input buffers must stay unchanged until the next-but-one
+ * mmw_step or mmw_sync. */
+int mmw_read_results_async(mmw_ctx* ctx, float* host_out, int* slot);
+int mmw_wait_results(mmw_ctx* ctx, int slot);
+
 /* Counters accumulated on the device since the last call (algorithmic-bytes bookkeeping):
  * out[0]=frames stepped (scene-frames that ran), [1]=sum N, [2]=sum M, [3]=sum U (unassigned pushed),
  * [4]=sum fused points clustered, [5]=sum tracks after the frame, [6]=sum min(A_j,64) ring rows written,

@@ -94,6 +94,8 @@ SIGNATURES = {
     "mmw_gate": (C.c_int, [_p, _p, C.c_int, _p, _p, C.c_int, _p, _p]),
     "mmw_pose": (C.c_int, [_p, _p, C.c_int, _p]),
     "mmw_pack_results": (C.c_int, [_p, _p]),
+    "mmw_read_results_async": (C.c_int, [_p, _p, C.POINTER(C.c_int)]),
+    "mmw_wait_results": (C.c_int, [_p, C.c_int]),
     "mmw_get_counters": (C.c_int, [_p, _p, C.c_int]),
     "mmw_set_dense_path": (C.c_int, [_p, C.c_int]),
     "mmw_profile": (C.c_int, [_p, C.c_int]),

@@ -131,6 +131,18 @@ class BatchedTracker:
         kp = np.ascontiguousarray(kp, dtype=np.float32).reshape(57)
         _lib.check(self.lib.mmw_set_keypoints(self._h, int(scene), int(track_index), _lib.ptr(kp)))
 
+    def read_results_async(self, host_out: np.ndarray) -> int:
+        """Queues pack + download of the current results into ``host_out`` (float32, S*max_tracks*68, ideally
+        pinned) without blocking; returns the slot to hand to ``wait_results``."""
+        if host_out.dtype != np.float32 or host_out.size != self.S * self.tcap * _lib.RESULT_FLOATS:
+            raise ValueError("host_out must be float32 with S*max_tracks*%d elements" % _lib.RESULT_FLOATS)
+        slot = C.c_int(0)
+        _lib.check(self.lib.mmw_read_results_async(self._h, _lib.ptr(host_out), C.byref(slot)))
+        return slot.value
+
+    def wait_results(self, slot: int):
+        _lib.check(self.lib.mmw_wait_results(self._h, int(slot)))
+
     def sync(self):
         _lib.check(self.lib.mmw_sync(self._h))
 

@@ -47,11 +47,16 @@ struct mmw_ctx {
     unsigned long long* d_counters = nullptr;
     unsigned long long* d_phase = nullptr;
     bool phase_clocks = false;
-    // input staging (host-input path)
-    float* d_pts = nullptr;
-    int32_t* d_offsets = nullptr;
-    double* d_dt = nullptr;
-    size_t pts_cap_rows = 0;
+    // input staging (host-input path): double-buffered, copied on a side stream so that the upload of frame k+1
+    // overlaps the kernels of frame k
+    float* d_pts2[2] = {nullptr, nullptr};
+    int32_t* d_offsets2[2] = {nullptr, nullptr};
+    double* d_dt2[2] = {nullptr, nullptr};
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+    cudaEvent_t packed[2] = {nullptr, nullptr}, results_done[2] = {nullptr, nullptr};
+    float* d_results[2] = {nullptr, nullptr};
+    unsigned stage_idx = 0, result_idx = 0;
     std::vector<int32_t> h_offsets;
     // pose
     int variant = -1;
@@ -152,12 +157,18 @@ int mmw_destroy(mmw_ctx* x) {
     cudaSetDevice(x->device);
     if (x->stream) cudaStreamSynchronize(x->stream);
     void* ptrs[] = {x->d_tracks, x->d_scenes, x->d_track_ring, x->d_uring, x->d_keypoints, x->d_default_posture,
-                    x->d_assoc, x->d_labels, x->d_counters, x->d_phase, x->d_pts, x->d_offsets, x->d_dt, x->d_blob, x->d_bn1s,
+                    x->d_assoc, x->d_labels, x->d_counters, x->d_phase, x->d_pts2[0], x->d_pts2[1], x->d_offsets2[0],
+                    x->d_offsets2[1], x->d_dt2[0], x->d_dt2[1], x->d_results[0], x->d_results[1], x->d_blob, x->d_bn1s,
                     x->d_bn1t, x->d_bn2s, x->d_bn2t, x->d_feats, x->d_row_scene, x->d_row_track, x->d_row_slot,
                     x->d_pose_total, x->d_act2, x->d_act3, x->d_pose_out};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     pose_tc_free(&x->tc);
+    for (int i = 0; i < 2; ++i)
+        for (cudaEvent_t e : {x->h2d_done[i], x->stage_free[i], x->packed[i], x->results_done[i]})
+            if (e) cudaEventDestroy(e);
+    if (x->h2d_stream) cudaStreamDestroy(x->h2d_stream);
+    if (x->d2h_stream) cudaStreamDestroy(x->d2h_stream);
     if (x->stream) cudaStreamDestroy(x->stream);
     delete x;
     return MMW_OK;
@@ -219,8 +230,24 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     ALLOC(x->d_labels, sizeof(int32_t) * S * 3 * max_points);
     ALLOC(x->d_counters, sizeof(unsigned long long) * 8);
     ALLOC(x->d_phase, sizeof(unsigned long long) * 16);
-    ALLOC(x->d_offsets, sizeof(int32_t) * (S + 1));
-    ALLOC(x->d_dt, sizeof(double) * S);
+    for (int i = 0; i < 2; ++i) {
+        ALLOC(x->d_pts2[i], sizeof(float) * kRawCols * S * max_points);
+        ALLOC(x->d_offsets2[i], sizeof(int32_t) * (S + 1));
+        ALLOC(x->d_dt2[i], sizeof(double) * S);
+        ALLOC(x->d_results[i], sizeof(float) * S * max_tracks * MMW_RESULT_FLOATS);
+        if (cudaEventCreateWithFlags(&x->h2d_done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x->stage_free[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x->packed[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x->results_done[i], cudaEventDisableTiming) != cudaSuccess) {
+            mmw_destroy(x);
+            return fail(MMW_ERR_CUDA, "cudaEventCreate failed");
+        }
+    }
+    if (cudaStreamCreateWithFlags(&x->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&x->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        mmw_destroy(x);
+        return fail(MMW_ERR_CUDA, "cudaStreamCreate failed");
+    }
     ALLOC(x->d_pose_total, sizeof(int));
     x->pose_cap = n_scenes * max_tracks;
     ALLOC(x->d_row_scene, sizeof(int32_t) * x->pose_cap);
@@ -241,7 +268,9 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
 int mmw_sync(mmw_ctx* x) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->h2d_stream));
     CK(cudaStreamSynchronize(x->stream));
+    CK(cudaStreamSynchronize(x->d2h_stream));
     return MMW_OK;
 }
 
@@ -351,6 +380,7 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     CK(cudaSetDevice(x->device));
     StepArgs a;
     a.cfg = x->dc;
+    int host_stage = -1;
     if (flags & MMW_STEP_DEVICE_INPUT) {
         if (!pts) return fail(MMW_ERR_INVALID, "pts is NULL");
         a.pts = pts; a.offsets = offsets; a.dt = dt;
@@ -360,20 +390,20 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
         if (total > (size_t)x->S * x->ncap)
             return fail(MMW_ERR_CAPACITY, "more points than n_scenes * max_points_per_frame");
         if (total > 0 && !pts) return fail(MMW_ERR_INVALID, "pts is NULL");
-        if (total > x->pts_cap_rows) {
-            CK(cudaStreamSynchronize(x->stream));
-            if (x->d_pts) cudaFree(x->d_pts);
-            x->d_pts = nullptr;
-            const size_t cap = (size_t)x->S * x->ncap;
-            CK(cudaMalloc((void**)&x->d_pts, sizeof(float) * kRawCols * cap));
-            x->pts_cap_rows = cap;
-        }
+        const int k = (int)(x->stage_idx++ & 1u);
+        // the staging buffer is free once the step kernel that last read it has run
+        CK(cudaStreamWaitEvent(x->h2d_stream, x->stage_free[k], 0));
         if (total)
-            CK(cudaMemcpyAsync(x->d_pts, pts, sizeof(float) * kRawCols * total, cudaMemcpyHostToDevice, x->stream));
-        CK(cudaMemcpyAsync(x->d_offsets, offsets, sizeof(int32_t) * (x->S + 1), cudaMemcpyHostToDevice, x->stream));
-        CK(cudaMemcpyAsync(x->d_dt, dt, sizeof(double) * x->S, cudaMemcpyHostToDevice, x->stream));
+            CK(cudaMemcpyAsync(x->d_pts2[k], pts, sizeof(float) * kRawCols * total, cudaMemcpyHostToDevice,
+                               x->h2d_stream));
+        CK(cudaMemcpyAsync(x->d_offsets2[k], offsets, sizeof(int32_t) * (x->S + 1), cudaMemcpyHostToDevice,
+                           x->h2d_stream));
+        CK(cudaMemcpyAsync(x->d_dt2[k], dt, sizeof(double) * x->S, cudaMemcpyHostToDevice, x->h2d_stream));
+        CK(cudaEventRecord(x->h2d_done[k], x->h2d_stream));
+        CK(cudaStreamWaitEvent(x->stream, x->h2d_done[k], 0));
         x->h_offsets.assign(offsets, offsets + x->S + 1);
-        a.pts = x->d_pts; a.offsets = x->d_offsets; a.dt = x->d_dt;
+        a.pts = x->d_pts2[k]; a.offsets = x->d_offsets2[k]; a.dt = x->d_dt2[k];
+        host_stage = k;
     }
     a.tracks = x->d_tracks; a.scenes = x->d_scenes; a.track_ring = x->d_track_ring; a.uring = x->d_uring;
     a.keypoints = x->d_keypoints; a.default_posture = x->d_default_posture; a.assoc_out = x->d_assoc;
@@ -383,6 +413,7 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     prof_mark(x, MMW_K_STEP);
     CK(launch_step(a, x->stream));
     x->launches++;
+    if (host_stage >= 0) CK(cudaEventRecord(x->stage_free[host_stage], x->stream));
     prof_mark(x, -1);
     if (flags & MMW_STEP_POSE) return mmw_estimate_posture(x);
     return MMW_OK;
@@ -715,6 +746,31 @@ int mmw_pack_results(mmw_ctx* x, float* device_out) {
                                                               device_out);
     CK(cudaGetLastError());
     x->launches++;
+    return MMW_OK;
+}
+
+int mmw_read_results_async(mmw_ctx* x, float* host_out, int* slot) {
+    if (!x || !host_out) return fail(MMW_ERR_INVALID, "ctx/host_out is NULL");
+    CK(cudaSetDevice(x->device));
+    const int r = (int)(x->result_idx++ & 1u);
+    CK(cudaStreamWaitEvent(x->stream, x->results_done[r], 0));     // previous download of this buffer finished
+    pack_results_kernel<<<x->S * x->tcap, 64, 0, x->stream>>>(x->d_scenes, x->d_tracks, x->d_keypoints, x->S, x->tcap,
+                                                              x->d_results[r]);
+    CK(cudaGetLastError());
+    x->launches++;
+    CK(cudaEventRecord(x->packed[r], x->stream));
+    CK(cudaStreamWaitEvent(x->d2h_stream, x->packed[r], 0));
+    CK(cudaMemcpyAsync(host_out, x->d_results[r], sizeof(float) * (size_t)x->S * x->tcap * MMW_RESULT_FLOATS,
+                       cudaMemcpyDeviceToHost, x->d2h_stream));
+    CK(cudaEventRecord(x->results_done[r], x->d2h_stream));
+    if (slot) *slot = r;
+    return MMW_OK;
+}
+
+int mmw_wait_results(mmw_ctx* x, int slot) {
+    if (!x || slot < 0 || slot > 1) return fail(MMW_ERR_INVALID, "bad ctx/slot");
+    CK(cudaSetDevice(x->device));
+    CK(cudaEventSynchronize(x->results_done[slot]));
     return MMW_OK;
 }
 

@@ -170,7 +170,7 @@ __device__ __forceinline__ uint64_t make_desc_interleaved(uint32_t saddr, uint32
 
 // CK   = K' per tap = 2 * padded input channels (hi | lo): 16 for conv1, 32 for conv2
 // NOUT = MMA N     = 2 * output channels: 32 for conv1, 64 for conv2
-template <int CK, int NOUT, int MODE>
+template <int CK, int NOUT, int MODE, int D>
 __global__ void __launch_bounds__(kSlabThreads, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) {
     constexpr int NCH = CK / 8;                      // 16-byte chunks per position
@@ -193,8 +193,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows = *a.n_rows;
-    const int D = a.D, taps = a.taps;
-    const int MT = D == 3 ? 2 : 1;
+    constexpr int taps = D == 3 ? 27 : 9;
+    constexpr int MT = D == 3 ? 2 : 1;                // M tiles of 128 rows per sample
 
     // static zero padding (d, w borders and the h rows a shifted copy never receives)
     for (int i = threadIdx.x; i < 3 * SLAB_BYTES / 16; i += kSlabThreads)
@@ -202,8 +202,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 4 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int c = 0; c < 3; ++c) { mbar_init(&sfull[c], 128); mbar_init(&sempty[c], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        for (int c = 0; c < 3; ++c) { mbar_init(&sfull[c], 128); mbar_init(&sempty[c], MT); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], MT); mbar_init(&tempty[b], 4); }
         mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -214,67 +214,94 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // ===== producers: global -> three h-shifted slabs =====
+        // ===== producers: global -> registers (one sample ahead) -> three h-shifted slabs =====
+        // The sample is read from HBM/L2 once; the three kh copies are shared-memory stores of the same
+        // registers, issued as soon as the MMA issuers release the corresponding slab.
+        constexpr int ITEMS = D * 64 * NCH / 128;            // 16-byte chunks per thread per sample
         const int tid = threadIdx.x;
+        int dstoff[ITEMS], hsrc[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const int i = tid + 128 * j;
+            const int chunk = i % NCH, pos = i / NCH;
+            const int w = pos & 7, h = (pos >> 3) & 7, d = pos >> 6;
+            dstoff[j] = (1 + (d + 1) * 10 + (w + 1)) * ATOM + chunk * 128;
+            hsrc[j] = h;
+        }
+        uint4 cur[ITEMS], nxt[ITEMS];
+        auto load_row = [&](int row, uint4 (&r)[ITEMS]) {
+            const uint4* src = reinterpret_cast<const uint4*>(a.in + (size_t)row * D * 64 * CK);
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) r[j] = __ldg(src + tid + 128 * j);
+        };
+        if ((int)blockIdx.x < rows) load_row(blockIdx.x, cur);
         int n = 0;
         for (int row = blockIdx.x; row < rows; row += gridDim.x, ++n) {
-            const __nv_bfloat16* src = a.in + (size_t)row * D * 64 * CK;
+            const int next = row + gridDim.x;
+            if (next < rows) load_row(next, nxt);
+#pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const int kh = c - 1;
                 mbar_wait(&sempty[c], (uint32_t)((n & 1) ^ 1));
                 unsigned char* sl = slab + c * SLAB_BYTES;
-                for (int i = tid; i < D * 64 * NCH; i += 128) {
-                    const int chunk = i % NCH, pos = i / NCH;
-                    const int w = pos & 7, h = (pos >> 3) & 7, d = pos >> 6;
-                    const int hh = h - kh;
-                    if (hh < 0 || hh > 7) continue;
-                    unsigned char* dst = sl + (1 + (d + 1) * 10 + (w + 1)) * ATOM + chunk * 128 + hh * 16;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)),
-                                 "l"(src + (size_t)pos * CK + chunk * 8)
-                                 : "memory");
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j) {
+                    const int hh = hsrc[j] - kh;
+                    if (hh >= 0 && hh <= 7) *reinterpret_cast<uint4*>(sl + dstoff[j] + hh * 16) = cur[j];
                 }
-                asm volatile("cp.async.wait_all;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&sfull[c]);
             }
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) cur[j] = nxt[j];
         }
-    } else if (warp == 5) {
+    } else if (warp == 4 || warp == 5) {
+        // ===== MMA issuers: warp 4 owns M tile 0, warp 5 loads the weights and owns M tile 1 (3-D net) =====
+        // Every operand address is slab/weight base + a compile-time constant, so one MMA costs two 64-bit adds.
+        const int mt = warp - 4;
         if (lane == 0) {
-            mbar_expect_tx(bfull, taps * B_TAP);
-            for (int t = 0; t < taps; ++t) tma_load_2d(sB + t * B_TAP, &map_b, bfull, 0, t * NOUT);
-        }
-    } else if (warp == 4) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(NOUT);
-            mbar_wait(bfull, 0);
-            int n = 0;
-            for (int row = blockIdx.x; row < rows; row += gridDim.x, ++n) {
-                const int buf = n & 1;
-                mbar_wait(&tempty[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
-                tc_fence_after();
-                for (int c = 0; c < 3; ++c) {
-                    mbar_wait(&sfull[c], (uint32_t)(n & 1));
+            if (warp == 5) {
+                mbar_expect_tx(bfull, taps * B_TAP);
+                for (int t = 0; t < taps; ++t) tma_load_2d(sB + t * B_TAP, &map_b, bfull, 0, t * NOUT);
+            }
+            if (mt < MT) {
+                constexpr uint32_t idesc = make_idesc(NOUT);
+                const uint64_t db0 = make_desc<CK * 2>(smem_u32(sB));
+                uint64_t da0[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    da0[c] = make_desc_interleaved(smem_u32(slab + c * SLAB_BYTES) + (uint32_t)((1 + mt * 16) * ATOM), 128,
+                                                   ATOM);
+                mbar_wait(bfull, 0);
+                int n = 0;
+                for (int row = blockIdx.x; row < rows; row += gridDim.x, ++n) {
+                    const int buf = n & 1;
+                    mbar_wait(&tempty[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
                     tc_fence_after();
-                    const uint32_t sl = smem_u32(slab + c * SLAB_BYTES);
-                    for (int kd = (D == 3 ? -1 : 0); kd <= (D == 3 ? 1 : 0); ++kd) {
-                        for (int kw = -1; kw <= 1; ++kw) {
-                            const int tap = D == 3 ? ((kd + 1) * 3 + c) * 3 + (kw + 1) : c * 3 + (kw + 1);
-                            const bool first = c == 0 && kd == (D == 3 ? -1 : 0) && kw == -1;
-                            const uint64_t db = make_desc<CK * 2>(smem_u32(sB + tap * B_TAP));
-                            for (int mt = 0; mt < MT; ++mt) {
-                                const uint32_t aaddr = sl + (uint32_t)((1 + mt * 16 + (1 + kd) * 10 + kw) * ATOM);
-                                const uint32_t tmem_d = tmem_base + (uint32_t)((buf * 2 + mt) * NOUT);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)((buf * 2 + mt) * NOUT);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        mbar_wait(&sfull[c], (uint32_t)(n & 1));
+                        tc_fence_after();
+#pragma unroll
+                        for (int kdi = 0; kdi < (D == 3 ? 3 : 1); ++kdi) {
+#pragma unroll
+                            for (int kwi = 0; kwi < 3; ++kwi) {
+                                const int kd = D == 3 ? kdi - 1 : 0, kw = kwi - 1;
+                                const int tap = D == 3 ? (kdi * 3 + c) * 3 + kwi : c * 3 + kwi;
+                                const bool first = c == 0 && kdi == 0 && kwi == 0;
+                                const int aoff = ((1 + kd) * 10 + kw) * ATOM;        // whole atoms: tap = tile shift
 #pragma unroll
                                 for (int kk = 0; kk < CK / 16; ++kk)
-                                    umma_bf16(tmem_d, make_desc_interleaved(aaddr + kk * 256, 128, ATOM),
-                                              db + (uint64_t)(kk * 2), idesc, !(first && kk == 0));
+                                    umma_bf16(tmem_d, da0[c] + (uint64_t)((aoff + kk * 256) >> 4),
+                                              db0 + (uint64_t)((tap * B_TAP + kk * 32) >> 4), idesc,
+                                              (first && kk == 0) ? 0u : 1u);
                             }
                         }
+                        umma_commit(&sempty[c]);      // slab_kh may be refilled once both issuers are done with it
                     }
-                    umma_commit(&sempty[c]);          // slab_kh may be refilled for the next sample
+                    umma_commit(&tfull[buf]);
                 }
-                umma_commit(&tfull[buf]);
             }
         }
     } else {
@@ -374,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     constexpr int BM = 128, UK = 16;
     constexpr int A_BYTES = BM * kBK * 2, B_BYTES = BN * kBK * 2;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    constexpr uint32_t TCOLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TCOLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // power of two
     const int rows = *a.n_rows;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     if (m0 >= rows) return;
@@ -647,21 +674,25 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
     if (make_map_2d(&im->m_w1b, im->w1b, (uint64_t)im->taps * 32, 16, 32, 16) ||
         make_map_2d(&im->m_w2b, im->w2b, (uint64_t)im->taps * 64, 32, 64, 32) ||
         make_map_2d(&im->m_ah, im->a_hi, R, im->Kf, 128, 64) || make_map_2d(&im->m_al, im->a_lo, R, im->Kf, 128, 64) ||
-        make_map_2d(&im->m_w1h, im->wd1_hi, im->H, im->Kf, 256, 64) ||
-        make_map_2d(&im->m_w1l, im->wd1_lo, im->H, im->Kf, 256, 64) ||
+        make_map_2d(&im->m_w1h, im->wd1_hi, im->H, im->Kf, im->H % 192 == 0 ? 192 : 256, 64) ||
+        make_map_2d(&im->m_w1l, im->wd1_lo, im->H, im->Kf, im->H % 192 == 0 ? 192 : 256, 64) ||
         make_map_2d(&im->m_hh, im->h_hi, R, im->H, 128, 64) || make_map_2d(&im->m_hl, im->h_lo, R, im->H, 128, 64) ||
         make_map_2d(&im->m_w2h, im->wd2_hi, 64, im->H, 64, 64) || make_map_2d(&im->m_w2l, im->wd2_lo, 64, im->H, 64, 64))
         return -1;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_slab_kernel<16, 32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 conv_smem_bytes_tc<16, 32>(27));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_slab_kernel<32, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 conv_smem_bytes_tc<32, 64>(27));
+    auto set_smem = [&](const void* fn, int bytes) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    set_smem((const void*)conv_slab_kernel<16, 32, 0, 3>, conv_smem_bytes_tc<16, 32>(27));
+    set_smem((const void*)conv_slab_kernel<32, 64, 1, 3>, conv_smem_bytes_tc<32, 64>(27));
+    set_smem((const void*)conv_slab_kernel<16, 32, 0, 1>, conv_smem_bytes_tc<16, 32>(9));
+    set_smem((const void*)conv_slab_kernel<32, 64, 1, 1>, conv_smem_bytes_tc<32, 64>(9));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_kernel<256, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  gemm_smem_bytes<256, 2>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_kernel<192, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gemm_smem_bytes<192, 2>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_kernel<64, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  gemm_smem_bytes<64, 4>());
@@ -692,10 +723,16 @@ int pose_tc_conv(PoseTc* t, const PoseTcRun& r, cudaStream_t st, int* n_launches
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
     ConvTcArgs c1{r.n_rows, r.b1, nullptr, nullptr, im->in_p, im->act1_p, nullptr, im->D, im->taps};
-    conv_slab_kernel<16, 32, 0><<<148, kSlabThreads, conv_smem_bytes_tc<16, 32>(27), st>>>(im->m_w1b, c1);
+    if (im->D == 3)
+        conv_slab_kernel<16, 32, 0, 3><<<148, kSlabThreads, conv_smem_bytes_tc<16, 32>(27), st>>>(im->m_w1b, c1);
+    else
+        conv_slab_kernel<16, 32, 0, 1><<<148, kSlabThreads, conv_smem_bytes_tc<16, 32>(9), st>>>(im->m_w1b, c1);
     if (check_launch("conv_slab_kernel<conv1>")) return -1;
     ConvTcArgs c2{r.n_rows, r.b2, r.bn1_scale, r.bn1_shift, im->act1_p, im->a_hi, im->a_lo, im->D, im->taps};
-    conv_slab_kernel<32, 64, 1><<<148, kSlabThreads, conv_smem_bytes_tc<32, 64>(27), st>>>(im->m_w2b, c2);
+    if (im->D == 3)
+        conv_slab_kernel<32, 64, 1, 3><<<148, kSlabThreads, conv_smem_bytes_tc<32, 64>(27), st>>>(im->m_w2b, c2);
+    else
+        conv_slab_kernel<32, 64, 1, 1><<<148, kSlabThreads, conv_smem_bytes_tc<32, 64>(9), st>>>(im->m_w2b, c2);
     if (check_launch("conv_slab_kernel<conv2>")) return -1;
     if (n_launches) *n_launches = 2;
     return 0;
@@ -706,9 +743,17 @@ int pose_tc_fc1(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
     GemmTcArgs g{r.n_rows, r.bd1, r.bn2_scale, r.bn2_shift, im->h_hi, im->h_lo, nullptr, nullptr, nullptr, nullptr,
                  im->Kf, im->H, r.tcap};
-    dim3 grid(im->H / 256, (max_rows + 127) / 128);
-    gemm_tc_kernel<256, 2, 0><<<grid, kGemmThreads, gemm_smem_bytes<256, 2>(), st>>>(im->m_ah, im->m_al, im->m_w1h,
-                                                                                    im->m_w1l, g);
+    // 128 x 192 tiles when they divide N: 1536/192 = 8 column tiles, i.e. 120 CTAs for ~1900 rows instead of 90
+    // CTAs of 128 x 256 on 148 SMs (one wave either way, 25 % less work per CTA)
+    if (im->H % 192 == 0) {
+        dim3 grid(im->H / 192, (max_rows + 127) / 128);
+        gemm_tc_kernel<192, 2, 0><<<grid, kGemmThreads, gemm_smem_bytes<192, 2>(), st>>>(im->m_ah, im->m_al, im->m_w1h,
+                                                                                        im->m_w1l, g);
+    } else {
+        dim3 grid(im->H / 256, (max_rows + 127) / 128);
+        gemm_tc_kernel<256, 2, 0><<<grid, kGemmThreads, gemm_smem_bytes<256, 2>(), st>>>(im->m_ah, im->m_al, im->m_w1h,
+                                                                                        im->m_w1l, g);
+    }
     if (check_launch("gemm_tc_kernel<dense1>")) return -1;
     if (n_launches) *n_launches = 1;
     return 0;
