@@ -12,7 +12,7 @@ struct PoseFeatArgs {
     const TrackRec* tracks;
     const float* track_ring;
     float* feats;          // [rows][ring_size*64*5]
-    __nv_bfloat16* packed; // [rows][ring_size*64][16] = (hi c0..4,0,0,0 | lo c0..4,0,0,0) for the tensor-core convs, or nullptr
+    __nv_bfloat16* packed; // tensor-core conv input [rows][D][8 w][2 chunks: hi|lo][8 h][8 ch] (pose_tc.cu), or nullptr
     int32_t* row_scene;    // [rows]
     int32_t* row_track;
     int32_t* row_slot;

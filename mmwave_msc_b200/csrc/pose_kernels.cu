@@ -127,8 +127,10 @@ __global__ void __launch_bounds__(128) pose_feature_kernel(PoseFeatArgs a) {
                         pv[q] = __float2bfloat16_rn(x);
                         pv[8 + q] = __float2bfloat16_rn(x - __bfloat162float(pv[q]));
                     }
-                    pk[(f * kFeatPts + rank) * 2 + 0] = reinterpret_cast<const uint4*>(pv)[0];
-                    pk[(f * kFeatPts + rank) * 2 + 1] = reinterpret_cast<const uint4*>(pv)[1];
+                    // slab order of the tensor-core convs: [row][d = f][w][chunk][h][8]  (pose_tc.cu)
+                    const int ph = rank >> 3, pw_ = rank & 7;
+                    pk[((f * 8 + pw_) * 2 + 0) * 8 + ph] = reinterpret_cast<const uint4*>(pv)[0];
+                    pk[((f * 8 + pw_) * 2 + 1) * 8 + ph] = reinterpret_cast<const uint4*>(pv)[1];
                 }
             }
             __syncwarp();

@@ -151,12 +151,17 @@ struct ConvTcArgs {
     int D, taps;
 };
 
-constexpr int kSlabThreads = 320;                  // warps 0-3 producers, 4 MMA, 5 weight loader, 6-9 epilogue
+constexpr int kSlabThreads = 320;                  // warps 0-3 producers, 4-5 MMA issuers, 6-9 epilogue
 constexpr int kSlabAtoms = 1 + 5 * 10 + 3;         // one guard atom in front, three behind (junk rows stay inside)
+
+// Slab ring depth: the (sample, kh) uses form one sequence u = 3*n + c that cycles through NSLAB buffers, so the
+// producers run up to NSLAB-1 uses ahead of the tensor core.
+template <int CK>
+__host__ __device__ constexpr int slab_ring() { return CK == 16 ? 8 : 4; }
 
 template <int CK, int NOUT>
 constexpr int conv_smem_bytes_tc(int taps) {
-    return taps * NOUT * CK * 2 + 3 * kSlabAtoms * (CK / 8) * 128 + 1024 + 512;
+    return taps * NOUT * CK * 2 + slab_ring<CK>() * kSlabAtoms * (CK / 8) * 128 + 1024 + 1024;
 }
 
 __device__ __forceinline__ uint64_t make_desc_interleaved(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -168,6 +173,10 @@ __device__ __forceinline__ uint64_t make_desc_interleaved(uint32_t saddr, uint32
     return d;
 }
 
+// Activations in HBM are stored in the slab's own order, [row][d][w][chunk][h][8 ch] (16-byte chunk = 8 bf16 of
+// the hi|lo channel vector of one position), so the producers' global reads are fully coalesced and their
+// shared-memory stores are bank-conflict free (8 consecutive lanes = the 128 contiguous bytes of one core matrix).
+//
 // CK   = K' per tap = 2 * padded input channels (hi | lo): 16 for conv1, 32 for conv2
 // NOUT = MMA N     = 2 * output channels: 32 for conv1, 64 for conv2
 template <int CK, int NOUT, int MODE, int D>
@@ -176,33 +185,40 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
     constexpr int NCH = CK / 8;                      // 16-byte chunks per position
     constexpr int ATOM = NCH * 128;                  // bytes of one 8-row atom
     constexpr int SLAB_BYTES = kSlabAtoms * ATOM;
+    constexpr int NSLAB = slab_ring<CK>();
     constexpr int B_TAP = NOUT * CK * 2;
     constexpr int COUT = NOUT / 2;
     constexpr uint32_t TCOLS = 4 * NOUT;             // 2 accumulator buffers x 2 M tiles
+    constexpr int taps = D == 3 ? 27 : 9;
+    constexpr int MT = D == 3 ? 2 : 1;               // M tiles of 128 rows per sample
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* sB = smem;
-    unsigned char* slab = smem + a.taps * B_TAP;
-    uint64_t* sfull = reinterpret_cast<uint64_t*>(slab + 3 * SLAB_BYTES);
-    uint64_t* sempty = sfull + 3;
-    uint64_t* tfull = sempty + 3;
+    unsigned char* slab = smem + taps * B_TAP;
+    uint64_t* sfull = reinterpret_cast<uint64_t*>(slab + NSLAB * SLAB_BYTES);
+    uint64_t* sempty = sfull + NSLAB;
+    uint64_t* tfull = sempty + NSLAB;
     uint64_t* tempty = tfull + 2;
     uint64_t* bfull = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+    float* sconst = reinterpret_cast<float*>(tmem_slot + 2);      // bias | bn_scale | bn_shift, COUT each
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows = *a.n_rows;
-    constexpr int taps = D == 3 ? 27 : 9;
-    constexpr int MT = D == 3 ? 2 : 1;                // M tiles of 128 rows per sample
 
     // static zero padding (d, w borders and the h rows a shifted copy never receives)
-    for (int i = threadIdx.x; i < 3 * SLAB_BYTES / 16; i += kSlabThreads)
+    for (int i = threadIdx.x; i < NSLAB * SLAB_BYTES / 16; i += kSlabThreads)
         reinterpret_cast<uint4*>(slab)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < COUT) {
+        sconst[threadIdx.x] = a.bias[threadIdx.x];
+        sconst[COUT + threadIdx.x] = MODE == 1 ? a.bn_scale[threadIdx.x] : 1.f;
+        sconst[2 * COUT + threadIdx.x] = MODE == 1 ? a.bn_shift[threadIdx.x] : 0.f;
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 4 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int c = 0; c < 3; ++c) { mbar_init(&sfull[c], 128); mbar_init(&sempty[c], MT); }
+        for (int c = 0; c < NSLAB; ++c) { mbar_init(&sfull[c], 128); mbar_init(&sempty[c], MT); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], MT); mbar_init(&tempty[b], 4); }
         mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -214,43 +230,47 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // ===== producers: global -> registers (one sample ahead) -> three h-shifted slabs =====
-        // The sample is read from HBM/L2 once; the three kh copies are shared-memory stores of the same
-        // registers, issued as soon as the MMA issuers release the corresponding slab.
+        // ===== producers: global -> registers (one sample ahead) -> the three h-shifted slabs of the sample =====
         constexpr int ITEMS = D * 64 * NCH / 128;            // 16-byte chunks per thread per sample
         const int tid = threadIdx.x;
-        int dstoff[ITEMS], hsrc[ITEMS];
+        int dstoff[ITEMS];
+        const int hsrc = tid & 7;                            // 128 % 8 == 0: every item of a thread has the same h
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             const int i = tid + 128 * j;
-            const int chunk = i % NCH, pos = i / NCH;
-            const int w = pos & 7, h = (pos >> 3) & 7, d = pos >> 6;
+            const int chunk = (i >> 3) % NCH, w = (i / (8 * NCH)) & 7, d = i / (64 * NCH);
             dstoff[j] = (1 + (d + 1) * 10 + (w + 1)) * ATOM + chunk * 128;
-            hsrc[j] = h;
         }
         uint4 cur[ITEMS], nxt[ITEMS];
         auto load_row = [&](int row, uint4 (&r)[ITEMS]) {
-            const uint4* src = reinterpret_cast<const uint4*>(a.in + (size_t)row * D * 64 * CK);
+            const uint4* src = reinterpret_cast<const uint4*>(a.in) + (size_t)row * (D * 64 * NCH);
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) r[j] = __ldg(src + tid + 128 * j);
         };
         if ((int)blockIdx.x < rows) load_row(blockIdx.x, cur);
-        int n = 0;
-        for (int row = blockIdx.x; row < rows; row += gridDim.x, ++n) {
+        int u = 0;
+        for (int row = blockIdx.x; row < rows; row += gridDim.x) {
             const int next = row + gridDim.x;
             if (next < rows) load_row(next, nxt);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int kh = c - 1;
-                mbar_wait(&sempty[c], (uint32_t)((n & 1) ^ 1));
-                unsigned char* sl = slab + c * SLAB_BYTES;
+            for (int c = 0; c < 3; ++c, ++u) {
+                const int slot = u % NSLAB;
+                mbar_wait(&sempty[slot], (uint32_t)(((u / NSLAB) & 1) ^ 1));
+                unsigned char* sl = slab + slot * SLAB_BYTES;
+                const int hh = hsrc - (c - 1);               // this slab serves kh = c - 1: row h feeds output h - kh
+                if (hh >= 0 && hh <= 7) {
 #pragma unroll
-                for (int j = 0; j < ITEMS; ++j) {
-                    const int hh = hsrc[j] - kh;
-                    if (hh >= 0 && hh <= 7) *reinterpret_cast<uint4*>(sl + dstoff[j] + hh * 16) = cur[j];
+                    for (int j = 0; j < ITEMS; ++j) *reinterpret_cast<uint4*>(sl + dstoff[j] + hh * 16) = cur[j];
+                }
+                // the h row this copy never receives must be zero: it may hold the previous use's data
+                const int hz = c == 0 ? 0 : (c == 2 ? 7 : -1);
+                if (hz >= 0 && hsrc == hz) {
+#pragma unroll
+                    for (int j = 0; j < ITEMS; ++j)
+                        *reinterpret_cast<uint4*>(sl + dstoff[j] + hz * 16) = make_uint4(0, 0, 0, 0);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&sfull[c]);
+                mbar_arrive(&sfull[slot]);
             }
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) cur[j] = nxt[j];
@@ -267,22 +287,20 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
             if (mt < MT) {
                 constexpr uint32_t idesc = make_idesc(NOUT);
                 const uint64_t db0 = make_desc<CK * 2>(smem_u32(sB));
-                uint64_t da0[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    da0[c] = make_desc_interleaved(smem_u32(slab + c * SLAB_BYTES) + (uint32_t)((1 + mt * 16) * ATOM), 128,
-                                                   ATOM);
+                const uint64_t da00 = make_desc_interleaved(smem_u32(slab) + (uint32_t)((1 + mt * 16) * ATOM), 128, ATOM);
                 mbar_wait(bfull, 0);
-                int n = 0;
+                int n = 0, u = 0;
                 for (int row = blockIdx.x; row < rows; row += gridDim.x, ++n) {
                     const int buf = n & 1;
                     mbar_wait(&tempty[buf], (uint32_t)(((n >> 1) & 1) ^ 1));
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)((buf * 2 + mt) * NOUT);
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        mbar_wait(&sfull[c], (uint32_t)(n & 1));
+                    for (int c = 0; c < 3; ++c, ++u) {
+                        const int slot = u % NSLAB;
+                        mbar_wait(&sfull[slot], (uint32_t)((u / NSLAB) & 1));
                         tc_fence_after();
+                        const uint64_t da0 = da00 + (uint64_t)((slot * SLAB_BYTES) >> 4);
 #pragma unroll
                         for (int kdi = 0; kdi < (D == 3 ? 3 : 1); ++kdi) {
 #pragma unroll
@@ -293,12 +311,12 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
                                 const int aoff = ((1 + kd) * 10 + kw) * ATOM;        // whole atoms: tap = tile shift
 #pragma unroll
                                 for (int kk = 0; kk < CK / 16; ++kk)
-                                    umma_bf16(tmem_d, da0[c] + (uint64_t)((aoff + kk * 256) >> 4),
+                                    umma_bf16(tmem_d, da0 + (uint64_t)((aoff + kk * 256) >> 4),
                                               db0 + (uint64_t)((tap * B_TAP + kk * 32) >> 4), idesc,
                                               (first && kk == 0) ? 0u : 1u);
                             }
                         }
-                        umma_commit(&sempty[c]);      // slab_kh may be refilled once both issuers are done with it
+                        umma_commit(&sempty[slot]);   // the slab may be refilled once both issuers are done with it
                     }
                     umma_commit(&tfull[buf]);
                 }
@@ -343,18 +361,21 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
                 __align__(16) __nv_bfloat16 hi[COUT], lo[COUT];
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) {
-                    float x = fmaxf(y[mt][c] + __ldg(a.bias + c), 0.f);
-                    if (MODE == 1) x = fmaf(x, __ldg(a.bn_scale + c), __ldg(a.bn_shift + c));
+                    float x = fmaxf(y[mt][c] + sconst[c], 0.f);
+                    if (MODE == 1) x = fmaf(x, sconst[COUT + c], sconst[2 * COUT + c]);
                     split2(x, hi[c], lo[c]);
                 }
-                const size_t p = ((size_t)row * D + d) * 64 + hh * 8 + (w2 - 1);
                 if (MODE == 0) {
-                    uint4* o = reinterpret_cast<uint4*>(a.out0 + p * (2 * COUT));
+                    // next conv's input, slab order [row][d][w][chunk][h][8]: chunks = hi[0:8] hi[8:16] lo[0:8] lo[8:16]
+                    uint4* o = reinterpret_cast<uint4*>(a.out0) +
+                               ((((size_t)row * D + d) * 8 + (w2 - 1)) * (2 * COUT / 8)) * 8 + hh;
 #pragma unroll
-                    for (int i = 0; i < COUT / 8; ++i) o[i] = reinterpret_cast<const uint4*>(hi)[i];
+                    for (int i = 0; i < COUT / 8; ++i) o[i * 8] = reinterpret_cast<const uint4*>(hi)[i];
 #pragma unroll
-                    for (int i = 0; i < COUT / 8; ++i) o[COUT / 8 + i] = reinterpret_cast<const uint4*>(lo)[i];
+                    for (int i = 0; i < COUT / 8; ++i) o[(COUT / 8 + i) * 8] = reinterpret_cast<const uint4*>(lo)[i];
                 } else {
+                    // dense-1 operand: Keras Flatten order (d, h, w, c)
+                    const size_t p = ((size_t)row * D + d) * 64 + hh * 8 + (w2 - 1);
                     uint4* oh = reinterpret_cast<uint4*>(a.out0 + p * COUT);
                     uint4* ol = reinterpret_cast<uint4*>(a.out1 + p * COUT);
 #pragma unroll
@@ -514,7 +535,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     }
 }
 
-// fp32 feature maps [rows][P][5] -> packed bf16 [rows][P][16] = (hi c0..4, 0,0,0 | lo c0..4, 0,0,0)
+// fp32 feature maps [rows][D*64][5] (position = (d, h, w)) -> packed bf16 in slab order [rows][D][8 w][2][8 h][8]:
+// chunk 0 = (hi c0..4, 0,0,0), chunk 1 = (lo c0..4, 0,0,0)
 __global__ void pack_input_kernel(const float* __restrict__ feats, __nv_bfloat16* __restrict__ out, const int* n_rows,
                                   int P) {
     const size_t total = (size_t)(*n_rows) * P;
@@ -524,8 +546,11 @@ __global__ void pack_input_kernel(const float* __restrict__ feats, __nv_bfloat16
         for (int k = 0; k < 16; ++k) v[k] = __float2bfloat16_rn(0.f);
 #pragma unroll
         for (int k = 0; k < 5; ++k) split2(feats[i * 5 + k], v[k], v[8 + k]);
-        reinterpret_cast<uint4*>(out + i * 16)[0] = reinterpret_cast<const uint4*>(v)[0];
-        reinterpret_cast<uint4*>(out + i * 16)[1] = reinterpret_cast<const uint4*>(v)[1];
+        const size_t slice = i / 64;                       // row * D + d
+        const int pos = (int)(i % 64), h = pos >> 3, w = pos & 7;
+        uint4* o = reinterpret_cast<uint4*>(out) + ((slice * 8 + w) * 2) * 8 + h;
+        o[0] = reinterpret_cast<const uint4*>(v)[0];
+        o[8] = reinterpret_cast<const uint4*>(v)[1];
     }
 }
 
