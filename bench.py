@@ -181,9 +181,12 @@ def main():
         reference_arm(args, rank, world)
         return
 
+    # the contract is ONE JSON line on stdout: keep NCCL's own banner/debug output off stdout
+    os.environ["NCCL_DEBUG"] = os.environ.get("MMW_NCCL_DEBUG", "WARN")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
-    from mmwave_msc_b200 import _lib, pose_weights as pw, synth
+    from mmwave_msc_b200 import _lib, pose_weights as pw, sharding, synth
     from mmwave_msc_b200.batched import BatchedTracker
 
     if not torch.cuda.is_available():
@@ -194,7 +197,7 @@ def main():
     S = args.scenes
     W_, K = args.warmup, args.steps
     n_frames = PRIME_FRAMES + 2 * (W_ + K) + K      # device-timed pass, e2e pass, per-kernel profile pass
-    ids = [rank * S + i for i in range(S)]
+    ids = sharding.shard_scene_ids(world * S, world, rank)      # contiguous block of scenes per GPU
     batches = synth.gen_batch(ids, n_frames)
 
     bt = BatchedTracker(S, max_points=256, max_tracks=8, device=local)
@@ -302,9 +305,9 @@ def main():
     bt.pack_results(res_dev.data_ptr())
     bt.sync()
     if world > 1:
-        gathered = torch.empty(world * res_dev.numel(), dtype=torch.float32, device="cuda")
-        dist.all_gather_into_tensor(gathered, res_dev)
+        gathered = sharding.gather_results(res_dev, world * S, bt.tcap * _lib.RESULT_FLOATS)
         torch.cuda.synchronize()
+        assert gathered.numel() == world * res_dev.numel()
 
     if rank == 0:
         pk = peaks()

@@ -11,58 +11,51 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kWsAug = 0, kWsA = 72, kWsB = 108, kWsK = 144, kWsM1 = 198, kWsM2 = 279, kWsV = 360;
 constexpr int kWarpScratch = 376;
 
+__device__ __forceinline__ double shfl_d(double v, int src) {
+    return __shfl_sync(kFull, v, src);
+}
+
 // Inverse and determinant of a 6x6 row-major matrix by Gauss-Jordan elimination with partial
 // pivoting (numpy.linalg.inv / det are LU with partial pivoting: Tracking.py:558-559, filterpy update).
-// A, Ainv: 36 doubles in shared memory (may not alias); aug: 72 doubles scratch.  Returns det(A).
-__device__ __forceinline__ double warp_inv6(const double* A, double* Ainv, double* aug, int lane) {
-    for (int e = lane; e < 72; e += 32) {
-        const int r = e / 12, c = e % 12;
-        aug[e] = c < 6 ? A[r * 6 + c] : (c - 6 == r ? 1.0 : 0.0);
-    }
-    __syncwarp();
+// Lane l < 12 keeps column l of the augmented matrix [A | I] in six registers; pivot search, row swap and the
+// multipliers travel by warp shuffle, so there is no shared-memory round trip or __syncwarp inside the six
+// elimination steps.  A, Ainv: 36 doubles in shared memory (may not alias).  `aug` is unused (kept for the
+// callers' scratch layout).  Returns det(A); every lane returns the same value.
+__device__ __forceinline__ double warp_inv6(const double* A, double* Ainv, double* /*aug*/, int lane) {
+    const int col = lane < 12 ? lane : 11;          // lanes >= 12 shadow lane 11 (results discarded)
+    double r[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r[i] = col < 6 ? A[i * 6 + col] : (col - 6 == i ? 1.0 : 0.0);
     double det = 1.0;
-#pragma unroll 1
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
+        // partial pivoting on column k (held by lane k): first row of maximum magnitude, like LAPACK's idamax
         int p = k;
-        double best = fabs(aug[k * 12 + k]);
-        for (int r = k + 1; r < 6; ++r) {
-            const double v = fabs(aug[r * 12 + k]);
-            if (v > best) { best = v; p = r; }
+        double best = fabs(r[k]);
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            const double v = fabs(r[i]);
+            if (v > best) { best = v; p = i; }
         }
-        if (p != k) {
-            if (lane < 12) {
-                const double a = aug[k * 12 + lane], b = aug[p * 12 + lane];
-                aug[k * 12 + lane] = b;
-                aug[p * 12 + lane] = a;
-            }
-            det = -det;
-        }
-        __syncwarp();
-        const double piv = aug[k * 12 + k];
+        p = __shfl_sync(kFull, p, k);
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i)
+            if (p == i) { const double t = r[k]; r[k] = r[i]; r[i] = t; }
+        if (p != k) det = -det;
+        const double piv = shfl_d(r[k], k);
         det *= piv;
-        __syncwarp();
-        if (lane < 12) aug[k * 12 + lane] = aug[k * 12 + lane] / piv;
-        __syncwarp();
-        double nv[2];
-        int ne[2];
+        r[k] = r[k] / piv;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int idx = lane + 32 * t;
-            ne[t] = -1;
-            if (idx < 60) {
-                const int rr = idx / 12, c = idx % 12;
-                const int r = rr < k ? rr : rr + 1;
-                ne[t] = r * 12 + c;
-                nv[t] = aug[r * 12 + c] - aug[r * 12 + k] * aug[k * 12 + c];
-            }
+        for (int i = 0; i < 6; ++i) {
+            if (i == k) continue;
+            const double f = shfl_d(r[i], k);       // multiplier = column k's entry of row i (before the update)
+            r[i] -= f * r[k];
         }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < 2; ++t)
-            if (ne[t] >= 0) aug[ne[t]] = nv[t];
-        __syncwarp();
     }
-    for (int e = lane; e < 36; e += 32) Ainv[e] = aug[(e / 6) * 12 + 6 + (e % 6)];
+    if (lane >= 6 && lane < 12) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Ainv[i * 6 + (lane - 6)] = r[i];
+    }
     __syncwarp();
     return det;
 }

@@ -45,9 +45,9 @@ struct TrackRec {
     int32_t ring_n;        // frames in the track ring
     int32_t ring_head;     // physical index of the oldest frame
     int32_t ring_cnt[kRing];   // stored rows per PHYSICAL frame (<= 64)
-    int32_t pad;
+    int32_t pad[3];            // record = 1264 bytes = 79 x 16 (moved with 16-byte cp.async)
 };
-static_assert(sizeof(TrackRec) % 8 == 0, "TrackRec must be a whole number of doubles");
+static_assert(sizeof(TrackRec) % 16 == 0, "TrackRec must be a whole number of 16-byte chunks");
 constexpr int kTrackWords = sizeof(TrackRec) / 8;
 
 struct SceneRec {

@@ -161,6 +161,29 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
     if (N > ncap) { N = ncap; sc.flags |= MMW_SCENE_POINT_OVERFLOW; }
     const double dt = a.dt[s];
 
+    // Issued first, consumed later: this scene's track records (cp.async -> shared memory, waited for in step 2)
+    // and the ring frames DBSCAN will read (L2 prefetch), so their DRAM latency overlaps the point phase.
+    const int T0 = sc.n_tracks;
+    {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.tracks + (size_t)s * tcap);
+        unsigned char* dst = reinterpret_cast<unsigned char*>(tr);
+#ifndef MMW_NO_CPASYNC
+        for (int i = tid; i < T0 * (int)(sizeof(TrackRec) / 16); i += kStepThreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i * 16)),
+                         "l"(src + i * 16)
+                         : "memory");
+#else
+        (void)src; (void)dst;
+#endif
+        for (int f = 0; f < sc.ring_n; ++f) {
+            const int phys = (sc.ring_head + f) % c.ring_size;
+            const char* fr = reinterpret_cast<const char*>(uring_frame(a, s, phys));
+            const int lines = (sc.ring_cnt[phys] * kRawCols * 4 + 127) / 128;
+            for (int i = tid; i < lines; i += kStepThreads)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(fr + i * 128));
+        }
+    }
+
     // ---- 1. load, transform, bounds filter, ordered compaction (Utils.py:379-432) ------------------
     for (int i = tid; i < N * kRawCols; i += kStepThreads) craw[i] = a.pts[(size_t)off * kRawCols + i];
     __syncthreads();
@@ -192,6 +215,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
     sc.last_M = M;
     sc.dbscan_n = -1;
     if (M == 0) {                        // offline_main.py:55: the frame is skipped entirely (Q23)
+        asm volatile("cp.async.wait_all;" ::: "memory");
         if (tid == 0) {
             sc.last_ran = 0;
             a.scenes[s] = sc;
@@ -203,12 +227,15 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
 
     PHASE_MARK(1);
     // ---- 2. load this scene's track records -----------------------------------------------------------
-    const int T0 = sc.n_tracks;
+#ifndef MMW_NO_CPASYNC
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#else
     {
         const double* src = reinterpret_cast<const double*>(a.tracks + (size_t)s * tcap);
         double* dst = reinterpret_cast<double*>(tr);
         for (int i = tid; i < T0 * kTrackWords; i += kStepThreads) dst[i] = src[i];
     }
+#endif
     __syncthreads();
 
     PHASE_MARK(2);
@@ -512,7 +539,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
                 t.ring_cnt[0] = n < kFeatPts ? n : kFeatPts;
                 t.ring_cnt[1] = 0;
                 t.ring_cnt[2] = 0;
-                t.pad = 0;
+                t.pad[0] = t.pad[1] = t.pad[2] = 0;
                 misc[kOrder + T1 + q] = newidx[q];
             }
             // keypoints = MODEL_DEFAULT_POSTURE until the first inference (Tracking.py:221, Q25)

@@ -256,3 +256,42 @@ def test_full_size_c2_permutation_and_determinism():
             assert tr0[s, k]["id"] == t["id"]
             np.testing.assert_allclose(tr0[s, k]["x"], t["x"], rtol=1e-8, atol=1e-10)
             np.testing.assert_allclose(tr0[s, k]["keypoints"], t["keypoints"], rtol=0, atol=KEYPOINT_ATOL)
+
+
+# ---- pipelined host path: side-stream upload + asynchronous packed-result download -----------------
+def test_pipelined_results_match_blocking_readback():
+    import torch
+    S, F = 64, 10
+    batches = synth.gen_batch(list(range(S)), F)
+    W = pw.make_pose_weights(pw.VARIANT_3D)
+    bt = BatchedTracker(S)
+    bt.load_pose_weights(W)
+    ref = BatchedTracker(S)
+    ref.load_pose_weights(W)
+    host = [torch.empty(S * bt.tcap * 68, dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+    pinned = []
+    for b in batches:                      # the API keeps reading the caller's buffers until the copy has run
+        pinned.append((torch.from_numpy(b.points).pin_memory().numpy(), torch.from_numpy(b.offsets).pin_memory().numpy(),
+                       torch.from_numpy(b.dt).pin_memory().numpy()))
+    prev = None
+    snaps = []
+    for f, (p, o, d) in enumerate(pinned):
+        bt.step(p, o, d, pose=True)
+        slot = bt.read_results_async(host[f & 1])
+        if prev is not None:
+            bt.wait_results(prev[0])
+            snaps.append(host[prev[1]].copy())
+        prev = (slot, f & 1)
+    bt.wait_results(prev[0])
+    snaps.append(host[prev[1]].copy())
+    for f, b in enumerate(batches):
+        ref.step(b.points, b.offsets, b.dt, pose=True)
+        tr, nt = ref.tracks()
+        got = snaps[f].reshape(S, bt.tcap, 68)
+        for s in range(S):
+            assert int(got[s, 0, 1]) == nt[s]
+            for k in range(nt[s]):
+                assert int(got[s, k, 0]) == tr[s, k]["id"]
+                np.testing.assert_array_equal(got[s, k, 2:11], tr[s, k]["x"].astype(np.float32))
+                np.testing.assert_array_equal(got[s, k, 11:], tr[s, k]["keypoints"])
+            assert np.all(got[s, nt[s]:, 0] == -1)
