@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=SCENES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense-path", default="tc", choices=["tc", "simt"])
+    ap.add_argument("--no-l2-flush", action="store_true", help="diagnostic only: keep L2 warm between timed steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -238,7 +239,8 @@ def main():
     barrier()
     for k in range(K):
         with torch.cuda.stream(stream):
-            flush.fill_(k & 0xff)            # evict L2 between timed iterations (not inside the timed interval)
+            if not args.no_l2_flush:
+                flush.fill_(k & 0xff)        # evict L2 between timed iterations (not inside the timed interval)
             ev[k][0].record(stream)
         step_dev(f); f += 1
         ev[k][1].record(stream)
@@ -320,8 +322,9 @@ def main():
             "config": {"workload": WORKLOAD, "scenes_per_gpu": S, "max_points": 256, "max_tracks": 8,
                        "pose_net": "define_CNN_3D", "pose_dtype": "fp32 (CUDA-core) / bf16x3 split on tcgen05, fp32 accumulate",
                        "dense_path": args.dense_path, "prime_frames": PRIME_FRAMES,
-                       "l2": "flushed between timed steps (256 MiB fill); per-step CUDA events on the library stream, "
-                             "flush excluded", "parallelism": "scenes sharded %d/GPU, no collective in the hot loop" % S},
+                       "l2": ("NOT flushed (diagnostic run)" if args.no_l2_flush else
+                              "flushed between timed steps (256 MiB fill); per-step CUDA events on the library stream, "
+                              "flush excluded"), "parallelism": "scenes sharded %d/GPU, no collective in the hot loop" % S},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // K),
                     "d2h_bytes_per_step": int(res_host.numel() * 4)},
             "gpu_launches": int(launches),

@@ -263,6 +263,8 @@ int mmw_get_kernel_ms(mmw_ctx* ctx, double* total_ms /*[MMW_N_KERNELS]*/, uint64
 /* Debug: per-phase SM-cycle accounting inside the fused step kernel (thread 0 of every CTA).  Returns the
  * cycles accumulated since the last call in out16 (may be NULL) and switches the accounting on/off. */
 int mmw_phase_clocks(mmw_ctx* ctx, int enable, uint64_t* out16);
+/* Debug: SM cycles the step kernel spent on each scene in the last frame stepped with the accounting on. */
+int mmw_scene_cycles(mmw_ctx* ctx, uint64_t* out /*[S]*/);
 
 /* Number of kernels this library launched since creation (bench.py's gpu_launches). */
 uint64_t mmw_launch_count(mmw_ctx* ctx);

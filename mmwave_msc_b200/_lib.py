@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmw.so")
+LIB_PATH = os.environ.get("MMW_LIB", os.path.join(_HERE, "libmmw.so"))   # MMW_LIB: alternative build (profiling experiments)
 
 MMW_POSE_2D, MMW_POSE_3D = 0, 1
 STEP_POSE, STEP_DEVICE_INPUT, STEP_RECORD_LABELS = 0x1, 0x2, 0x4
@@ -101,6 +101,7 @@ SIGNATURES = {
     "mmw_profile": (C.c_int, [_p, C.c_int]),
     "mmw_get_kernel_ms": (C.c_int, [_p, _p, _p]),
     "mmw_phase_clocks": (C.c_int, [_p, C.c_int, _p]),
+    "mmw_scene_cycles": (C.c_int, [_p, _p]),
     "mmw_launch_count": (C.c_uint64, [_p]),
 }
 

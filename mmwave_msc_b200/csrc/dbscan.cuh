@@ -52,39 +52,99 @@ __device__ __forceinline__ int block_rank(bool flag, int* total, int* s_scan) {
     return before + __popc(m & ((1u << lane) - 1u));
 }
 
-// X, Y, Z: B doubles each (shared).  par, cl: B ints each (shared).  On return cl[b] is the label of b.
+// Neighbour predicates ------------------------------------------------------------------------------------
+// Exact: float64 world coordinates in shared memory (stage-level entry point mmw_dbscan).
+struct NbExact {
+    const DevConfig& c;
+    const double *X, *Y, *Z;
+    double eps;
+    __device__ __forceinline__ bool operator()(int b, int q) const {
+        return eps_neighbour(c, X[b], Y[b], Z[b], X[q], Y[q], Z[q], eps);
+    }
+};
+
+// Screened: the fused step keeps the world coordinates of the ring points rounded to fp32 in shared memory and
+// evaluates the predicate in fp32 first (FP32 pipe, 4-cycle ops); only pairs whose fp32 distance falls inside a
+// guard band around eps -- wider than any fp32 rounding could move it -- are re-evaluated exactly in float64 from
+// the raw ring rows.  Decisions are therefore identical to the exact predicate, at a fraction of the FP64 work
+// (the FP64/XU pipe is what bounds this kernel, profiles/).
+struct NbScreened {
+    const DevConfig& c;
+    const float *Xf, *Yf, *Zf;        // shared memory, B floats each
+    const float* frame[kRing];        // raw rows of the ring frames, oldest first (global)
+    int start[kRing + 1];             // first fused index of each frame
+    double eps;
+    float lo, hi, rw, zw;
+    __device__ __forceinline__ void world(int b, double& x, double& y, double& z) const {
+        const int f = (b >= start[1] ? 1 : 0) + (b >= start[2] ? 1 : 0);
+        const float* r = frame[f] + (size_t)(b - start[f]) * kRawCols;
+        x = (double)r[0];
+        world_yz(c, (double)r[1], (double)r[2], y, z);
+    }
+    __device__ __forceinline__ bool operator()(int b, int q) const {
+        const float yb = Yf[b], yq = Yf[q];
+        const float w = 1.f - 0.5f * (yb + yq) * rw;
+        const float dx = Xf[b] - Xf[q], dy = yb - yq, dz = Zf[b] - Zf[q];
+        const float d = w * (dx * dx + dy * dy + zw * (dz * dz));
+        if (d > hi) return false;
+        if (d < lo) return true;
+        double x1, y1, z1, x2, y2, z2;                  // inside the guard band (or not finite): decide exactly
+        world(b, x1, y1, z1);
+        world(q, x2, y2, z2);
+        return eps_neighbour(c, x1, y1, z1, x2, y2, z2, eps);
+    }
+};
+
+// par, cl: B ints each (shared).  On return cl[b] is the label of b.
 // Returns the number of clusters (uniform over the block).
-__device__ inline int dbscan_block(const DevConfig& c, const double* X, const double* Y, const double* Z, int B,
-                                   double eps, int min_samples, int* par, int* cl, int* s_scan) {
+// Calls fn(b, q) for every unordered pair q < b < B, the B(B-1)/2 pairs split evenly over the block.
+template <class Fn>
+__device__ __forceinline__ void for_pairs(int B, Fn fn) {
+    const int nt = blockDim.x;
+    const int P = B * (B - 1) / 2;
+    const int chunk = (P + nt - 1) / nt;
+    int p = threadIdx.x * chunk;
+    const int pend = min(P, p + chunk);
+    if (p >= pend) return;
+    // pair index p <-> (b, q), q < b:  p = b(b-1)/2 + q
+    int b = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+    while (b * (b - 1) / 2 > p) --b;
+    while ((b + 1) * b / 2 <= p) ++b;
+    int q = p - b * (b - 1) / 2;
+    for (; p < pend; ++p) {
+        fn(b, q);
+        if (++q == b) { ++b; q = 0; }
+    }
+}
+
+constexpr int kPairSweepMax = 160;    // above this many fused points the count switches to early-exit rows
+
+template <class Nb>
+__device__ inline int dbscan_block(const Nb& nb, int B, int min_samples, int* par, int* cl, int* s_scan) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    // Neighbour counts.  The predicate is symmetric, so each unordered pair is evaluated once and the B(B-1)/2
-    // pairs are split evenly over the whole block (integer shared-memory atomics: order-independent, so the
-    // counts are deterministic).  Steady state is ~90 noise points = 4005 pairs = 32 per thread instead of one
-    // 90-long loop per point.
-    for (int b = tid; b < B; b += nt) par[b] = 1;                      // a point is its own neighbour
-    __syncthreads();
-    {
-        const int P = B * (B - 1) / 2;
-        const int chunk = (P + nt - 1) / nt;
-        int p = tid * chunk;
-        const int pend = min(P, p + chunk);
-        if (p < pend) {
-            // pair index p <-> (b, q), q < b:  p = b(b-1)/2 + q
-            int b = (int)((1.0 + sqrt(1.0 + 8.0 * (double)p)) * 0.5);
-            while (b * (b - 1) / 2 > p) --b;
-            while ((b + 1) * b / 2 <= p) ++b;
-            int q = p - b * (b - 1) / 2;
-            double x = X[b], y = Y[b], z = Z[b];
-            for (; p < pend; ++p) {
-                if (eps_neighbour(c, x, y, z, X[q], Y[q], Z[q], eps)) {
-                    atomicAdd(&par[b], 1);
-                    atomicAdd(&par[q], 1);
-                }
-                if (++q == b) {
-                    ++b; q = 0;
-                    if (b < B) { x = X[b]; y = Y[b]; z = Z[b]; }
-                }
-            }
+    // 1. neighbour counts (only "count >= min_samples" matters).
+    //    Small clouds (the steady-state noise residue, ~90 points): every unordered pair once, spread evenly over
+    //    the block, combined with integer shared-memory atomics (order-independent => deterministic).
+    //    Large clouds (a person walked in: hundreds of points, mostly one dense blob): one row per work item with
+    //    early exit at min_samples -- a blob point is decided after ~40 predicates instead of B -- rows handed out
+    //    through a shared-memory queue so the few full-length noise rows do not pile up on one thread.
+    if (B <= kPairSweepMax) {
+        for (int b = tid; b < B; b += nt) par[b] = 1;                  // a point is its own neighbour
+        __syncthreads();
+        for_pairs(B, [&](int b, int q) {
+            if (nb(b, q)) { atomicAdd(&par[b], 1); atomicAdd(&par[q], 1); }
+        });
+    } else {
+        int* queue = s_scan + 6;
+        if (tid == 0) *queue = 0;
+        __syncthreads();
+        while (true) {
+            const int b = atomicAdd(queue, 1);
+            if (b >= B) break;
+            int cnt = 1;
+            for (int q = 0; q < B && cnt < min_samples; ++q)
+                if (q != b && nb(b, q)) ++cnt;
+            par[b] = cnt;
         }
     }
     __syncthreads();
@@ -100,13 +160,16 @@ __device__ inline int dbscan_block(const DevConfig& c, const double* X, const do
         __syncthreads();
         return 0;
     }
-    // connected components over core points
+    // 2. connected components over core points (par[x] >= 0 <=> x is core, stable under the unions).  Pairs that
+    //    are already in one component are skipped BEFORE the predicate is evaluated: inside a dense blob almost
+    //    every pair is.
     for (int b = tid; b < B; b += nt) {
         if (((volatile int*)par)[b] < 0) continue;
-        const double x = X[b], y = Y[b], z = Z[b];
+        int rb = uf_find(par, b);
         for (int q = 0; q < b; ++q) {
             if (((volatile int*)par)[q] < 0) continue;
-            if (eps_neighbour(c, x, y, z, X[q], Y[q], Z[q], eps)) uf_unite(par, b, q);
+            if (uf_find(par, q) == rb) continue;
+            if (nb(b, q)) { uf_unite(par, b, q); rb = uf_find(par, b); }
         }
     }
     __syncthreads();
@@ -128,19 +191,18 @@ __device__ inline int dbscan_block(const DevConfig& c, const double* X, const do
         if (r >= 0) cl[b] = par[r];
     }
     __syncthreads();
-    // border points: lowest-numbered cluster with a core point within eps
+    // 3. border points: lowest-numbered cluster with a core point within eps (cl[q] >= 0 <=> q is core here;
+    //    cores of clusters that cannot improve the current best are skipped without evaluating the predicate)
     for (int b = tid; b < B; b += nt) {
         if (cl[b] >= 0) continue;
-        const double x = X[b], y = Y[b], z = Z[b];
         int best = 0x7fffffff;
         for (int q = 0; q < B; ++q) {
             const int lq = cl[q];
-            if (lq >= 0 && lq < best && eps_neighbour(c, x, y, z, X[q], Y[q], Z[q], eps)) best = lq;
+            if (lq >= 0 && lq < best && nb(b, q)) best = lq;
         }
         par[b] = best == 0x7fffffff ? -1 : best;
     }
     __syncthreads();
-    // NB: cl[q] >= 0 meant "core" during the pass above; merge border labels only now.
     for (int b = tid; b < B; b += nt)
         if (cl[b] < 0) cl[b] = par[b];
     __syncthreads();

@@ -7,9 +7,9 @@ namespace mmw {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// Per-warp scratch (doubles): aug 72 | A 36 | B 36 | K 54 | M1 81 | M2 81 | v 16
-constexpr int kWsAug = 0, kWsA = 72, kWsB = 108, kWsK = 144, kWsM1 = 198, kWsM2 = 279, kWsV = 360;
-constexpr int kWarpScratch = 376;
+// Per-warp scratch (doubles): A 36 | B 36 | K 54 | M1 81 | v 8.  M2 = K R (9x6) reuses A|B once S and S^-1 are dead.
+constexpr int kWsAug = 0, kWsA = 0, kWsB = 36, kWsK = 72, kWsM1 = 126, kWsM2 = 0, kWsV = 207;
+constexpr int kWarpScratch = 216;
 
 __device__ __forceinline__ double shfl_d(double v, int src) {
     return __shfl_sync(kFull, v, src);
@@ -145,13 +145,14 @@ __device__ __forceinline__ void warp_kf_update(double* x, double* P, const doubl
         }
         M1[e] = acc;
     }
-    // M2 = K R  (9x6) stored with stride 9 in M2[i*9 + a]
+    __syncwarp();                                   // every lane is done with SI before M2 overwrites A|B
+    // M2 = K R  (9x6)
     for (int e = lane; e < 54; e += 32) {
         const int i = e / 6, a = e % 6;
         double acc = 0.0;
 #pragma unroll
         for (int b = 0; b < 6; ++b) acc += K[i * 6 + b] * R[b * 6 + a];
-        M2[i * 9 + a] = acc;
+        M2[e] = acc;
     }
     __syncwarp();
     // P = M1 (I-KH)' + M2 K'
@@ -165,7 +166,7 @@ __device__ __forceinline__ void warp_kf_update(double* x, double* P, const doubl
         }
         double acc2 = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) acc2 += M2[i * 9 + a] * K[j * 6 + a];
+        for (int a = 0; a < 6; ++a) acc2 += M2[i * 6 + a] * K[j * 6 + a];
         P[e] = acc + acc2;
     }
     __syncwarp();

@@ -229,7 +229,7 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     ALLOC(x->d_assoc, sizeof(int32_t) * S * max_points);
     ALLOC(x->d_labels, sizeof(int32_t) * S * 3 * max_points);
     ALLOC(x->d_counters, sizeof(unsigned long long) * 8);
-    ALLOC(x->d_phase, sizeof(unsigned long long) * 16);
+    ALLOC(x->d_phase, sizeof(unsigned long long) * (16 + S));
     for (int i = 0; i < 2; ++i) {
         ALLOC(x->d_pts2[i], sizeof(float) * kRawCols * S * max_points);
         ALLOC(x->d_offsets2[i], sizeof(int32_t) * (S + 1));
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(kStepThreads) dbscan_stage_kernel(DevConfig c,
         Z[b] = xyz[(size_t)(off + b) * 3 + 2];
     }
     __syncthreads();
-    dbscan_block(c, X, Y, Z, B, eps, min_samples, par, cl, scan);
+    dbscan_block(NbExact{c, X, Y, Z, eps}, B, min_samples, par, cl, scan);
     for (int b = threadIdx.x; b < B; b += blockDim.x) labels[off + b] = cl[b];
 }
 
@@ -954,6 +954,14 @@ int mmw_get_kernel_ms(mmw_ctx* x, double* total_ms, uint64_t* calls) {
     for (auto& m : x->marks) cudaEventDestroy(m.first);
     x->marks.clear();
     for (int i = 0; i < MMW_N_KERNELS; ++i) { total_ms[i] = x->kernel_ms[i]; calls[i] = x->kernel_calls[i]; }
+    return MMW_OK;
+}
+
+int mmw_scene_cycles(mmw_ctx* x, uint64_t* out /*[S]*/) {
+    if (!x || !out) return fail(MMW_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    CK(cudaMemcpy(out, x->d_phase + 16, sizeof(unsigned long long) * x->S, cudaMemcpyDeviceToHost));
     return MMW_OK;
 }
 

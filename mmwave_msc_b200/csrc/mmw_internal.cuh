@@ -80,7 +80,7 @@ struct StepArgs {
     int32_t* assoc_out;        // [sum N]
     int32_t* labels_out;       // [S][3*ncap] or nullptr
     unsigned long long* counters;  // [8]
-    unsigned long long* phase_cycles;  // [16] or nullptr: cycles per phase of step_kernel (debug)
+    unsigned long long* phase_cycles;  // [16 + S] or nullptr: cycles per phase of step_kernel, then cycles per scene (debug)
     int n_scenes;
     uint32_t flags;
 };

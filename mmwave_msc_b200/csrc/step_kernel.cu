@@ -12,34 +12,42 @@
 namespace mmw {
 
 struct SmemLayout {
-    // offsets in bytes into dynamic shared memory
-    int regionA;     // doubles: world cols [6][ncap] during association; X,Y,Z [3*ncap] each during DBSCAN
+    // offsets in bytes into dynamic shared memory (kept under 32 KB at N_cap 256 / T_cap 8: 7 CTAs per SM, so the
+    // 1024 scenes of the C2 workload are resident in a single wave)
+    int vel;         // double [3][ncap]: world-frame velocity columns of the compacted frame (sqrt/div: kept);
+                     //   positions are recomputed from craw on use (x is the raw x; y', z' cost 4 mul + 3 add)
     int craw;        // float [ncap*5] compacted raw points of this frame
-    int assoc;       // int [ncap]
-    int par;         // int [3*ncap]
-    int cl;          // int [3*ncap]
+    int assoc;       // uint8 [ncap]: track index per compacted point, 255 = unassigned
+    int dbf;         // float [3][3*ncap]: fp32 world coordinates of the fused ring during DBSCAN; aliases
+                     //   vel|craw|assoc, which are dead by then
     int tracks;      // TrackRec [tcap]
     int cinv;        // double [tcap][36]
     int hx;          // double [tcap][6]
     int logdet;      // double [tcap]
     int ws;          // double [warps][kWarpScratch]
+    int par, cl;     // int [3*ncap] each: alias ws (dead during DBSCAN/spawn) when they fit, else their own space
     int misc;        // ints
     int total;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int ncap, int tcap) {
     SmemLayout L;
+    const int n4 = (ncap + 3) & ~3;
     int o = 0;
-    L.regionA = o; o += 9 * ncap * 8;
+    L.vel = o;     o += 3 * n4 * 8;
+    L.craw = o;    o += n4 * 5 * 4;
+    L.assoc = o;   o += n4;
+    L.dbf = 0;
+    if (o < 36 * n4) o = 36 * n4;                       // (never: 24 + 20 + 1 = 45 bytes per point)
+    o = (o + 15) & ~15;
     L.tracks = o;  o += tcap * (int)sizeof(TrackRec);
     L.cinv = o;    o += tcap * 36 * 8;
     L.hx = o;      o += tcap * 6 * 8;
-    L.logdet = o;  o += tcap * 8;
-    L.ws = o;      o += kStepWarps * kWarpScratch * 8;
-    L.craw = o;    o += ncap * 5 * 4;
-    L.assoc = o;   o += ncap * 4;
-    L.par = o;     o += 3 * ncap * 4;
-    L.cl = o;      o += 3 * ncap * 4;
+    L.logdet = o;  o += ((tcap + 1) & ~1) * 8;
+    L.ws = o;
+    const int wsb = kStepWarps * kWarpScratch * 8, dbb = 2 * 3 * n4 * 4;
+    o += wsb > dbb ? wsb : dbb;
+    L.par = L.ws;  L.cl = L.ws + 3 * n4 * 4;
     L.misc = o;    o += 128 * 4;
     L.total = o;
     return L;
@@ -88,8 +96,8 @@ __device__ __forceinline__ int warp_push_rows(const float* craw, int M, float* d
 
 // PointCluster statistics (Tracking.py:120-136) of the rows selected by sel, from world columns wp[k][i].
 // All lanes return the same values.
-template <class Sel>
-__device__ __forceinline__ int warp_cluster_stats(const double* wp, int ncap, int M, Sel sel, int lane,
+template <class Sel, class LoadW>
+__device__ __forceinline__ int warp_cluster_stats(LoadW load_w, int M, Sel sel, int lane,
                                                   double cen[6], double mn[6], double mx[6]) {
     int n = 0;
     double s[6];
@@ -98,9 +106,11 @@ __device__ __forceinline__ int warp_cluster_stats(const double* wp, int ncap, in
     for (int i = lane; i < M; i += 32) {
         if (!sel(i)) continue;
         ++n;
+        double w[6];
+        load_w(i, w);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            const double v = wp[k * ncap + i];
+            const double v = w[k];
             s[k] += v;
             mn[k] = fmin(mn[k], v);
             mx[k] = fmax(mx[k], v);
@@ -132,15 +142,25 @@ __device__ __forceinline__ const float* uring_frame(const StepArgs& a, int s, in
         }                                                                                \
     } while (0)
 
-__global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constant__ StepArgs a) {
+#ifndef MMW_STEP_MINBLOCKS
+#define MMW_STEP_MINBLOCKS 7
+#endif
+__global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(const __grid_constant__ StepArgs a) {
     long long phase_t0 = clock64();
+    const long long kernel_t0 = phase_t0;
     extern __shared__ __align__(16) unsigned char smem[];
     const DevConfig& c = a.cfg;
     const int ncap = c.ncap, tcap = c.tcap;
     const SmemLayout L = make_layout(ncap, tcap);
-    double* wp = reinterpret_cast<double*>(smem + L.regionA);
+    double* vel = reinterpret_cast<double*>(smem + L.vel);
     float* craw = reinterpret_cast<float*>(smem + L.craw);
-    int* assoc = reinterpret_cast<int*>(smem + L.assoc);
+    uint8_t* assoc = smem + L.assoc;
+    // world-frame 6-vector of compacted point i: positions recomputed (bit-identical to step 1), velocities stored
+    auto load_w = [&](int i, double (&w)[6]) {
+        w[0] = (double)craw[i * kRawCols + 0];
+        world_yz(c, (double)craw[i * kRawCols + 1], (double)craw[i * kRawCols + 2], w[1], w[2]);
+        w[3] = vel[i]; w[4] = vel[ncap + i]; w[5] = vel[2 * ncap + i];
+    };
     int* par = reinterpret_cast<int*>(smem + L.par);
     int* cl = reinterpret_cast<int*>(smem + L.cl);
     TrackRec* tr = reinterpret_cast<TrackRec*>(smem + L.tracks);
@@ -205,7 +225,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
 #pragma unroll
             for (int k = 0; k < kRawCols; ++k) craw[pos * kRawCols + k] = r5[k];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) wp[k * ncap + pos] = w[k];
+            for (int k = 0; k < 3; ++k) vel[k * ncap + pos] = w[3 + k];
         }
         M += tot;
         __syncthreads();
@@ -261,8 +281,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
     // ---- 4. gating + association (Tracking.py:553-572, Q14) -------------------------------------------
     for (int i = tid; i < M; i += kStepThreads) {
         double p[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) p[k] = wp[k * ncap + i];
+        load_w(i, p);
         double best = INFINITY;
         int bj = -1;
         for (int j = 0; j < T0; ++j) {
@@ -281,7 +300,7 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
             const double d2 = logdet[j] + q;
             if (d2 < c.gate && d2 < best) { best = d2; bj = j; }
         }
-        assoc[i] = bj;
+        assoc[i] = (uint8_t)(bj < 0 ? 255 : bj);
         a.assoc_out[off + i] = bj;
     }
     __syncthreads();
@@ -296,14 +315,14 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
             if (sc.ring_n >= c.ring_size) { phys = sc.ring_head; }
             else { phys = (sc.ring_head + sc.ring_n) % c.ring_size; }
             float* dst = const_cast<float*>(uring_frame(a, s, phys));
-            const int u = warp_push_rows(craw, M, dst, ncap, [&](int i) { return assoc[i] < 0; }, lane);
+            const int u = warp_push_rows(craw, M, dst, ncap, [&](int i) { return assoc[i] == 255; }, lane);
             if (lane == 0) { misc[kU] = u; misc[kUPhys] = phys; }
             continue;
         }
         TrackRec& t = tr[g];
         double cen[6], mn[6], mx[6];
         auto sel = [&](int i) { return assoc[i] == g; };
-        const int n = warp_cluster_stats(wp, ncap, M, sel, lane, cen, mn, mx);
+        const int n = warp_cluster_stats(load_w, M, sel, lane, cen, mn, mx);
         if (n == 0) {
             if (lane == 0) t.lifetime += dt;                     // update_lifetime(dt) (400-407)
             continue;
@@ -315,8 +334,9 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
         for (int i = lane; i < M; i += 32) {
             if (!sel(i)) continue;
             double d[6];
+            load_w(i, d);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) d[k] = wp[k * ncap + i] - cen[k];
+            for (int k = 0; k < 6; ++k) d[k] -= cen[k];
             int p = 0;
 #pragma unroll
             for (int r = 0; r < 6; ++r)
@@ -428,25 +448,36 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
         B += fcnt[f];
     }
     int ncl = 0;
-    double* X = wp;
-    double* Y = wp + 3 * ncap;
-    double* Z = wp + 6 * ncap;
     const bool run_db = B > 0 && T1 < c.tr_max_tracks;
     if (run_db) {
-        // fused cloud, oldest frame first; world y/z recomputed from the raw rows (x is unchanged)
+        // fused cloud, oldest frame first; world y/z recomputed in float64 from the raw rows (x is unchanged) and
+        // kept in shared memory rounded to fp32 for the screened predicate (dbscan.cuh)
+        float* Xf = reinterpret_cast<float*>(smem + L.dbf);
+        float* Yf = Xf + 3 * ncap;
+        float* Zf = Yf + 3 * ncap;
+        NbScreened nb{c, Xf, Yf, Zf, {nullptr, nullptr, nullptr}, {0, 0, 0, 0}, c.db_eps, 0.f, 0.f,
+                      (float)c.db_range_weight, (float)c.db_z_weight};
+        const float band = 1e-3f * (float)c.db_eps + 1e-4f;
+        nb.lo = (float)c.db_eps - band;
+        nb.hi = (float)c.db_eps + band;
         int b0 = 0;
         for (int f = 0; f < kRing; ++f) {
             const float* src = uring_frame(a, s, fphys[f]);
+            nb.frame[f] = src;
+            nb.start[f] = b0;
             for (int i = tid; i < fcnt[f]; i += kStepThreads) {
                 const float x = src[i * kRawCols + 0], y = src[i * kRawCols + 1], z = src[i * kRawCols + 2];
                 double yw, zw;
                 world_yz(c, (double)y, (double)z, yw, zw);
-                X[b0 + i] = (double)x; Y[b0 + i] = yw; Z[b0 + i] = zw;
+                Xf[b0 + i] = x; Yf[b0 + i] = (float)yw; Zf[b0 + i] = (float)zw;
             }
             b0 += fcnt[f];
         }
+        nb.start[kRing] = b0;
         __syncthreads();
-        ncl = dbscan_block(c, X, Y, Z, B, c.db_eps, c.db_min_samples, par, cl, misc + kScan);
+        PHASE_MARK(11);
+        ncl = dbscan_block(nb, B, c.db_min_samples, par, cl, misc + kScan);
+        PHASE_MARK(12);
         sc.dbscan_n = B;
         if (a.labels_out != nullptr)
             for (int b = tid; b < B; b += kStepThreads) a.labels_out[(size_t)s * 3 * ncap + b] = cl[b];
@@ -576,6 +607,8 @@ __global__ void __launch_bounds__(kStepThreads) step_kernel(const __grid_constan
         atomicAdd(&a.counters[5], (unsigned long long)T2);
     }
     PHASE_MARK(10);
+    if (a.phase_cycles != nullptr && threadIdx.x == 0)
+        a.phase_cycles[16 + blockIdx.x] = (unsigned long long)(clock64() - kernel_t0);   // last frame's cycles of this scene
 }
 
 cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
@@ -583,6 +616,9 @@ cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
     static int configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         configured = smem;
     }

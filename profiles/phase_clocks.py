@@ -1,15 +1,51 @@
-import sys; sys.path.insert(0,'.')
-import numpy as np, torch
+#!/usr/bin/env python
+"""Cycles per phase of the fused tracker step (thread 0 of every CTA, mmw_phase_clocks), C2 workload.
+First with the tracker alone (state stays in L2 between steps), then with the pose network between steps
+(its ~300 MB of scratch traffic evicts the tracker state, like in the real pipeline)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
 from mmwave_msc_b200 import synth, pose_weights as pw
 from mmwave_msc_b200.batched import BatchedTracker
-S=1024; F=30
+
+S, F = 1024, 40
 b = synth.gen_batch(range(S), F)
+names = ["load+filter", "load tracks", "predict+gatemat", "gate", "assoc stats", "maintain", "update", "dbscan",
+         "spawn", "writeback"]
+for pose in (False, True):
+    bt = BatchedTracker(S)
+    if pose:
+        bt.load_pose_weights(pw.make_pose_weights(pw.VARIANT_3D))
+    for f in range(20):
+        bt.step(b[f].points, b[f].offsets, b[f].dt, pose=pose)
+    bt.sync(); bt.phase_clocks(True)
+    for f in range(20, 40):
+        bt.step(b[f].points, b[f].offsets, b[f].dt, pose=pose)
+    pc = bt.phase_clocks(False).astype(float)
+    tot = pc[1:11].sum() + pc[11] + pc[12]
+    print("== pose between steps: %s" % pose)
+    for i, n in enumerate(names):
+        print("%-16s %8.0f cyc/scene-frame %5.1f%%" % (n, pc[i + 1] / (S * 20), 100 * pc[i + 1] / tot))
+    print("total cycles per scene-frame %.0f" % (tot / (S * 20)))
+    print("  inside dbscan: ring load %.0f, dbscan_block %.0f, tail %.0f  (cyc/scene-frame; tail = pc[8])" % (
+        pc[11] / (S * 20), pc[12] / (S * 20), pc[8] / (S * 20)))
+
+# distribution of per-scene cycles in one frame (the kernel ends when the slowest scene does)
+import ctypes
+from mmwave_msc_b200 import _lib
 bt = BatchedTracker(S)
-for f in range(20): bt.step(b[f].points, b[f].offsets, b[f].dt, pose=False)
+for f in range(25):
+    bt.step(b[f].points, b[f].offsets, b[f].dt, pose=False)
 bt.sync(); bt.phase_clocks(True)
-for f in range(20,30): bt.step(b[f].points, b[f].offsets, b[f].dt, pose=False)
-pc = bt.phase_clocks(False).astype(float)
-names=["load+filter","load tracks","predict+gatemat","gate","assoc stats","maintain","update","dbscan","spawn","writeback"]
-tot=pc[1:11].sum()
-for i,n in enumerate(names): print("%-16s %8.0f cyc/scene-frame %5.1f%%"%(n, pc[i+1]/(S*10), 100*pc[i+1]/tot))
-print("total cycles per scene-frame", tot/(S*10))
+bt.step(b[25].points, b[25].offsets, b[25].dt, pose=False)
+cyc = np.zeros(S, np.uint64)
+_lib.check(bt.lib.mmw_scene_cycles(bt._h, _lib.ptr(cyc)))
+bt.phase_clocks(False)
+cyc = cyc.astype(float)
+n, nid, m = bt.summary()
+rc = bt.ring_counts(); fused = np.where(rc > 0, rc, 0).sum(1)
+print("per-scene cycles: mean %.0f  p50 %.0f  p90 %.0f  p99 %.0f  max %.0f" % (cyc.mean(), np.percentile(cyc, 50),
+      np.percentile(cyc, 90), np.percentile(cyc, 99), cyc.max()))
+worst = np.argsort(-cyc)[:8]
+for w in worst:
+    print("  scene %4d cycles %7.0f tracks %d ring(after) %s M %d" % (w, cyc[w], n[w], rc[w].tolist(), m[w]))
