@@ -256,6 +256,7 @@ int mmw_set_dense_path(mmw_ctx* ctx, int use_tensor_cores);
 #define MMW_K_CONV 3           /* conv1 + conv2 + BatchNorm */
 #define MMW_K_FC1 4            /* dense 1 (+ operand split when the tensor-core path is on) */
 #define MMW_K_FC2 5            /* dense 2 */
+#define MMW_K_DBSCAN_BIG 6     /* union / border / spawn of the few scenes per frame in which clusters form */
 #define MMW_N_KERNELS 8
 int mmw_profile(mmw_ctx* ctx, int enable);
 int mmw_get_kernel_ms(mmw_ctx* ctx, double* total_ms /*[MMW_N_KERNELS]*/, uint64_t* calls /*[MMW_N_KERNELS]*/);
@@ -264,7 +265,7 @@ int mmw_get_kernel_ms(mmw_ctx* ctx, double* total_ms /*[MMW_N_KERNELS]*/, uint64
  * cycles accumulated since the last call in out16 (may be NULL) and switches the accounting on/off. */
 int mmw_phase_clocks(mmw_ctx* ctx, int enable, uint64_t* out16);
 /* Debug: SM cycles the step kernel spent on each scene in the last frame stepped with the accounting on. */
-int mmw_scene_cycles(mmw_ctx* ctx, uint64_t* out /*[S]*/);
+int mmw_scene_cycles(mmw_ctx* ctx, uint64_t* out /*[3*S]: cycles, then start and end %globaltimer ns per scene*/);
 
 /* Number of kernels this library launched since creation (bench.py's gpu_launches). */
 uint64_t mmw_launch_count(mmw_ctx* ctx);

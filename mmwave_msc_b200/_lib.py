@@ -14,7 +14,7 @@ MMW_POSE_2D, MMW_POSE_3D = 0, 1
 STEP_POSE, STEP_DEVICE_INPUT, STEP_RECORD_LABELS = 0x1, 0x2, 0x4
 SCENE_POINT_OVERFLOW, SCENE_TRACK_OVERFLOW = 0x1, 0x2
 RESULT_FLOATS = 68
-KERNEL_NAMES = ["step", "pose_index", "pose_features", "conv", "fc1", "fc2", "k6", "k7"]
+KERNEL_NAMES = ["step", "pose_index", "pose_features", "conv", "fc1", "fc2", "dbscan_big", "k7"]
 
 
 class MmwError(RuntimeError):

@@ -14,10 +14,15 @@
 
 namespace mmw {
 
-__device__ __forceinline__ int uf_find(volatile int* par, int i) {
+// Find with path halving.  Parents only ever decrease (roots are hooked under smaller roots), so shortening a path
+// with atomicMin(parent, grandparent) can never undo a concurrent hook -- a plain store could.  Without it the
+// min-index hooking degenerates into linked lists and every find in a dense 100-point blob walks ~100 links.
+__device__ __forceinline__ int uf_find(int* par, int i) {
     while (true) {
-        const int p = par[i];
+        const int p = ((volatile int*)par)[i];
         if (p == i) return i;
+        const int gp = ((volatile int*)par)[p];
+        if (gp != p) atomicMin(&par[i], gp);
         i = p;
     }
 }
@@ -61,6 +66,7 @@ struct NbExact {
     __device__ __forceinline__ bool operator()(int b, int q) const {
         return eps_neighbour(c, X[b], Y[b], Z[b], X[q], Y[q], Z[q], eps);
     }
+    __device__ __forceinline__ const NbExact& hot() const { return *this; }
 };
 
 // Screened: the fused step keeps the world coordinates of the ring points rounded to fp32 in shared memory and
@@ -81,73 +87,89 @@ struct NbScreened {
         x = (double)r[0];
         world_yz(c, (double)r[1], (double)r[2], y, z);
     }
-    __device__ __forceinline__ bool operator()(int b, int q) const {
-        const float yb = Yf[b], yq = Yf[q];
-        const float w = 1.f - 0.5f * (yb + yq) * rw;
-        const float dx = Xf[b] - Xf[q], dy = yb - yq, dz = Zf[b] - Zf[q];
-        const float d = w * (dx * dx + dy * dy + zw * (dz * dz));
-        if (d > hi) return false;
-        if (d < lo) return true;
-        double x1, y1, z1, x2, y2, z2;                  // inside the guard band (or not finite): decide exactly
+    // out of line on purpose: its float64 registers must not be live across the fp32 hot loop
+    __device__ __noinline__ bool exact(int b, int q) const {
+        double x1, y1, z1, x2, y2, z2;
         world(b, x1, y1, z1);
         world(q, x2, y2, z2);
         return eps_neighbour(c, x1, y1, z1, x2, y2, z2, eps);
     }
+    // The part of the predicate that runs for every pair, as a small by-value functor: seven scalars that stay in
+    // registers (the full struct has indexed arrays and lives in local memory -- going through it cost ~300 cycles
+    // per pair in LDL traffic).
+    struct Hot {
+        const float *X, *Y, *Z;
+        float lo, hi, rw, zw;
+        const NbScreened* full;
+        __device__ __forceinline__ bool operator()(int b, int q) const {
+            const float yb = Y[b], yq = Y[q];
+            const float w = 1.f - 0.5f * (yb + yq) * rw;
+            const float dx = X[b] - X[q], dy = yb - yq, dz = Z[b] - Z[q];
+            const float d = w * (dx * dx + dy * dy + zw * (dz * dz));
+            if (d > hi) return false;
+            if (d < lo) return true;
+            return full->exact(b, q);                   // inside the guard band (or not finite): decide exactly
+        }
+    };
+    __device__ __forceinline__ Hot hot() const { return Hot{Xf, Yf, Zf, lo, hi, rw, zw, this}; }
 };
 
 // par, cl: B ints each (shared).  On return cl[b] is the label of b.
 // Returns the number of clusters (uniform over the block).
-// Calls fn(b, q) for every unordered pair q < b < B, the B(B-1)/2 pairs split evenly over the block.
+// Sweep over all unordered pairs q < b < B in warp tiles: a warp owns a chunk of 32 consecutive q (one per lane) and
+// walks the rows b above it, so one row step evaluates 32 pairs, the row side of a result is combined with a warp
+// ballot / shuffle and the column side stays in a lane register.  fn(b, q, live) is called by all 32 lanes
+// (live = this lane's pair exists).
 template <class Fn>
-__device__ __forceinline__ void for_pairs(int B, Fn fn) {
-    const int nt = blockDim.x;
-    const int P = B * (B - 1) / 2;
-    const int chunk = (P + nt - 1) / nt;
-    int p = threadIdx.x * chunk;
-    const int pend = min(P, p + chunk);
-    if (p >= pend) return;
-    // pair index p <-> (b, q), q < b:  p = b(b-1)/2 + q
-    int b = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-    while (b * (b - 1) / 2 > p) --b;
-    while ((b + 1) * b / 2 <= p) ++b;
-    int q = p - b * (b - 1) / 2;
-    for (; p < pend; ++p) {
-        fn(b, q);
-        if (++q == b) { ++b; q = 0; }
+__device__ __forceinline__ void for_pair_tiles(int B, Fn fn) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nchunk = (B + 31) >> 5;
+    // every warp visits every chunk and takes the rows b = first + warp, first + warp + nw, ... : the work of a
+    // chunk (long for low j, short for high j) is split evenly instead of landing on one warp
+    for (int j = 0; j < nchunk; ++j) {
+        const int q = (j << 5) + lane;
+        for (int b = (j << 5) + 1 + warp; b < B; b += nw) fn(b, q, q < b && q < B);
     }
 }
 
-constexpr int kPairSweepMax = 160;    // above this many fused points the count switches to early-exit rows
+constexpr unsigned kFullMask = 0xffffffffu;
 
 template <class Nb>
-__device__ inline int dbscan_block(const Nb& nb, int B, int min_samples, int* par, int* cl, int* s_scan) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    // 1. neighbour counts (only "count >= min_samples" matters).
-    //    Small clouds (the steady-state noise residue, ~90 points): every unordered pair once, spread evenly over
-    //    the block, combined with integer shared-memory atomics (order-independent => deterministic).
-    //    Large clouds (a person walked in: hundreds of points, mostly one dense blob): one row per work item with
-    //    early exit at min_samples -- a blob point is decided after ~40 predicates instead of B -- rows handed out
-    //    through a shared-memory queue so the few full-length noise rows do not pile up on one thread.
-    if (B <= kPairSweepMax) {
-        for (int b = tid; b < B; b += nt) par[b] = 1;                  // a point is its own neighbour
-        __syncthreads();
-        for_pairs(B, [&](int b, int q) {
-            if (nb(b, q)) { atomicAdd(&par[b], 1); atomicAdd(&par[q], 1); }
-        });
-    } else {
-        int* queue = s_scan + 6;
-        if (tid == 0) *queue = 0;
-        __syncthreads();
-        while (true) {
-            const int b = atomicAdd(queue, 1);
-            if (b >= B) break;
-            int cnt = 1;
-            for (int q = 0; q < B && cnt < min_samples; ++q)
-                if (q != b && nb(b, q)) ++cnt;
-            par[b] = cnt;
+// stop_if_core: return -1 right after the counts when any core point exists (the caller hands the scene to
+// dbscan_big_kernel: clusters form in a couple of scenes per frame and the remaining sweeps would make that CTA
+// the one the whole step kernel waits for).
+__device__ inline int dbscan_block(const Nb& nb_full, int B, int min_samples, int* par, int* cl, int* s_scan,
+                                   unsigned long long* dbg = nullptr, bool stop_if_core = false) {
+    const auto nb = nb_full.hot();
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    long long dbg_t = clock64();
+    auto stamp = [&](int k) {
+        if (dbg != nullptr && tid == 0) {
+            const long long now = clock64();
+            atomicAdd(&dbg[k], (unsigned long long)(now - dbg_t));
+            dbg_t = now;
         }
+    };
+    // 1. neighbour counts: |{q : d(p,q) <= eps}| including p.  One integer atomic per (row, chunk) with a hit and
+    //    one per lane and chunk -- order-independent, so the counts (and everything below) are deterministic.
+    for (int b = tid; b < B; b += nt) par[b] = 1;                      // a point is its own neighbour
+    __syncthreads();
+    {
+        int cq = 0, qprev = -1;
+        for_pair_tiles(B, [&](int b, int q, bool live) {
+            if (q != qprev) {                                           // new chunk: flush this lane's column count
+                if (cq) atomicAdd(&par[qprev], cq);
+                cq = 0; qprev = q;
+            }
+            const bool hit = live && nb(b, q);
+            const unsigned m = __ballot_sync(kFullMask, hit);
+            cq += hit ? 1 : 0;
+            if (lane == 0 && m) atomicAdd(&par[b], __popc(m));
+        });
+        if (cq) atomicAdd(&par[qprev], cq);
     }
     __syncthreads();
+    stamp(13);
     int anycore = 0;
     for (int b = tid; b < B; b += nt) {
         const bool core = par[b] >= min_samples;
@@ -160,19 +182,18 @@ __device__ inline int dbscan_block(const Nb& nb, int B, int min_samples, int* pa
         __syncthreads();
         return 0;
     }
+    if (stop_if_core) return -1;
     // 2. connected components over core points (par[x] >= 0 <=> x is core, stable under the unions).  Pairs that
     //    are already in one component are skipped BEFORE the predicate is evaluated: inside a dense blob almost
     //    every pair is.
-    for (int b = tid; b < B; b += nt) {
-        if (((volatile int*)par)[b] < 0) continue;
-        int rb = uf_find(par, b);
-        for (int q = 0; q < b; ++q) {
-            if (((volatile int*)par)[q] < 0) continue;
-            if (uf_find(par, q) == rb) continue;
-            if (nb(b, q)) { uf_unite(par, b, q); rb = uf_find(par, b); }
-        }
-    }
+    for_pair_tiles(B, [&](int b, int q, bool live) {
+        if (((volatile int*)par)[b] < 0) return;                        // uniform over the warp
+        if (!live || ((volatile int*)par)[q] < 0) return;
+        if (uf_find(par, q) == uf_find(par, b)) return;
+        if (nb(b, q)) uf_unite(par, b, q);
+    });
     __syncthreads();
+    stamp(14);
     for (int b = tid; b < B; b += nt) cl[b] = par[b] >= 0 ? uf_find(par, b) : -1;
     __syncthreads();
     // rank of each root among the roots, ascending index
@@ -191,20 +212,28 @@ __device__ inline int dbscan_block(const Nb& nb, int B, int min_samples, int* pa
         if (r >= 0) cl[b] = par[r];
     }
     __syncthreads();
-    // 3. border points: lowest-numbered cluster with a core point within eps (cl[q] >= 0 <=> q is core here;
-    //    cores of clusters that cannot improve the current best are skipped without evaluating the predicate)
-    for (int b = tid; b < B; b += nt) {
-        if (cl[b] >= 0) continue;
-        int best = 0x7fffffff;
-        for (int q = 0; q < B; ++q) {
-            const int lq = cl[q];
-            if (lq >= 0 && lq < best && nb(b, q)) best = lq;
+    stamp(15);
+    // 3. border points: lowest-numbered cluster with a core point within eps (cl[x] >= 0 <=> x is core here)
+    for (int b = tid; b < B; b += nt)
+        if (cl[b] < 0) par[b] = 0x7fffffff;
+    __syncthreads();
+    for_pair_tiles(B, [&](int b, int q, bool live) {
+        const int lb = cl[b];                                           // uniform over the warp
+        const int lq = live ? cl[q] : lb;
+        const bool mixed = live && ((lb >= 0) != (lq >= 0));
+        const bool hit = mixed && nb(b, q);
+        if (lb >= 0) {                                                  // core row: label flows to non-core lanes
+            if (hit) atomicMin(&par[q], lb);
+        } else {                                                        // non-core row: min label of the core lanes
+            int v = hit ? lq : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(kFullMask, v, o));
+            if (lane == 0 && v != 0x7fffffff) atomicMin(&par[b], v);
         }
-        par[b] = best == 0x7fffffff ? -1 : best;
-    }
+    });
     __syncthreads();
     for (int b = tid; b < B; b += nt)
-        if (cl[b] < 0) cl[b] = par[b];
+        if (cl[b] < 0) cl[b] = par[b] == 0x7fffffff ? -1 : par[b];
     __syncthreads();
     return ncl;
 }

@@ -47,6 +47,7 @@ struct mmw_ctx {
     unsigned long long* d_counters = nullptr;
     unsigned long long* d_phase = nullptr;
     bool phase_clocks = false;
+    int32_t* d_defer = nullptr;      // [1 + S]: counter, then the work list of dbscan_big_kernel
     // input staging (host-input path): double-buffered, copied on a side stream so that the upload of frame k+1
     // overlaps the kernels of frame k
     float* d_pts2[2] = {nullptr, nullptr};
@@ -157,7 +158,7 @@ int mmw_destroy(mmw_ctx* x) {
     cudaSetDevice(x->device);
     if (x->stream) cudaStreamSynchronize(x->stream);
     void* ptrs[] = {x->d_tracks, x->d_scenes, x->d_track_ring, x->d_uring, x->d_keypoints, x->d_default_posture,
-                    x->d_assoc, x->d_labels, x->d_counters, x->d_phase, x->d_pts2[0], x->d_pts2[1], x->d_offsets2[0],
+                    x->d_assoc, x->d_labels, x->d_counters, x->d_phase, x->d_defer, x->d_pts2[0], x->d_pts2[1], x->d_offsets2[0],
                     x->d_offsets2[1], x->d_dt2[0], x->d_dt2[1], x->d_results[0], x->d_results[1], x->d_blob, x->d_bn1s,
                     x->d_bn1t, x->d_bn2s, x->d_bn2t, x->d_feats, x->d_row_scene, x->d_row_track, x->d_row_slot,
                     x->d_pose_total, x->d_act2, x->d_act3, x->d_pose_out};
@@ -229,7 +230,8 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     ALLOC(x->d_assoc, sizeof(int32_t) * S * max_points);
     ALLOC(x->d_labels, sizeof(int32_t) * S * 3 * max_points);
     ALLOC(x->d_counters, sizeof(unsigned long long) * 8);
-    ALLOC(x->d_phase, sizeof(unsigned long long) * (16 + S));
+    ALLOC(x->d_phase, sizeof(unsigned long long) * (16 + 3 * S));
+    ALLOC(x->d_defer, sizeof(int32_t) * (1 + S));
     for (int i = 0; i < 2; ++i) {
         ALLOC(x->d_pts2[i], sizeof(float) * kRawCols * S * max_points);
         ALLOC(x->d_offsets2[i], sizeof(int32_t) * (S + 1));
@@ -410,9 +412,13 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     a.labels_out = (flags & MMW_STEP_RECORD_LABELS) ? x->d_labels : nullptr;
     a.counters = x->d_counters; a.n_scenes = x->S; a.flags = flags;
     a.phase_cycles = x->phase_clocks ? x->d_phase : nullptr;
+    a.defer_count = x->d_defer;
+    a.defer_list = x->d_defer + 1;
     prof_mark(x, MMW_K_STEP);
     CK(launch_step(a, x->stream));
-    x->launches++;
+    prof_mark(x, MMW_K_DBSCAN_BIG);
+    CK(launch_dbscan_big(a, x->stream));
+    x->launches += 2;          // step_kernel + dbscan_big_kernel
     if (host_stage >= 0) CK(cudaEventRecord(x->stage_free[host_stage], x->stream));
     prof_mark(x, -1);
     if (flags & MMW_STEP_POSE) return mmw_estimate_posture(x);
@@ -961,7 +967,7 @@ int mmw_scene_cycles(mmw_ctx* x, uint64_t* out /*[S]*/) {
     if (!x || !out) return fail(MMW_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(x->device));
     CK(cudaStreamSynchronize(x->stream));
-    CK(cudaMemcpy(out, x->d_phase + 16, sizeof(unsigned long long) * x->S, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, x->d_phase + 16, sizeof(unsigned long long) * 3 * x->S, cudaMemcpyDeviceToHost));
     return MMW_OK;
 }
 

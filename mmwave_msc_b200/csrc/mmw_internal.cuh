@@ -81,9 +81,12 @@ struct StepArgs {
     int32_t* labels_out;       // [S][3*ncap] or nullptr
     unsigned long long* counters;  // [8]
     unsigned long long* phase_cycles;  // [16 + S] or nullptr: cycles per phase of step_kernel, then cycles per scene (debug)
+    int32_t* defer_list;       // [S] scenes whose DBSCAN + spawn is left to dbscan_big_kernel, or nullptr
+    int32_t* defer_count;      // device counter of defer_list (zeroed before every step)
     int n_scenes;
     uint32_t flags;
 };
+constexpr int kDeferPoints = 160;     // fused clouds larger than this go to dbscan_big_kernel
 
 // ---- world-frame point from a raw sensor point (Utils.py:379-420) -----------------------------------
 // Written with explicit round-to-nearest multiplies/adds (no FMA contraction) so that the

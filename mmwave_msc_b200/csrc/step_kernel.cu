@@ -132,6 +132,117 @@ __device__ __forceinline__ const float* uring_frame(const StepArgs& a, int s, in
     return a.uring + ((size_t)s * kRing + phys) * (size_t)a.cfg.ncap * kRawCols;
 }
 
+// One warp turns DBSCAN cluster q of the fused ring into a fresh track (ClusterTrack.__init__, Tracking.py:210-230
+// over PointCluster(cluster), :120-136): statistics over the 6 world columns recomputed from the ring's raw rows,
+// state x = [centroid, 0, 0, 0], P = KF_P_INIT*I, group dispersion = KF_GROUP_DISP_EST_INIT*I, ring = [first 64
+// cluster rows in fused order], keypoints = MODEL_DEFAULT_POSTURE.  `t` may live in shared or global memory.
+__device__ __forceinline__ void spawn_track(const StepArgs& a, int s, TrackRec& t, int q, int slot, int track_id,
+                                            const int* cl, const int* fcnt, const int* fphys, int lane) {
+    const DevConfig& c = a.cfg;
+    const int tcap = c.tcap;
+    int n = 0;
+    double sacc[6], mn[6], mx[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { sacc[k] = 0.0; mn[k] = INFINITY; mx[k] = -INFINITY; }
+    int b0 = 0;
+    float* dst = a.track_ring + (((size_t)s * tcap + slot) * kRing + 0) * (kFeatPts * kRawCols);
+    int stored = 0;
+    for (int f = 0; f < kRing; ++f) {
+        const float* src = uring_frame(a, s, fphys[f]);
+        for (int i0 = 0; i0 < fcnt[f]; i0 += 32) {
+            const int i = i0 + lane;
+            const bool in = i < fcnt[f] && cl[b0 + i] == q;
+            float r5[kRawCols];
+            if (in) {
+#pragma unroll
+                for (int k = 0; k < kRawCols; ++k) r5[k] = src[i * kRawCols + k];
+                double w[6];
+                world_from_raw(c, r5[0], r5[1], r5[2], r5[3], w);
+                ++n;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    sacc[k] += w[k]; mn[k] = fmin(mn[k], w[k]); mx[k] = fmax(mx[k], w[k]);
+                }
+            }
+            const unsigned m = __ballot_sync(kFull, in);
+            const int pos = stored + __popc(m & ((1u << lane) - 1u));
+            if (in && pos < kFeatPts) {
+#pragma unroll
+                for (int k = 0; k < kRawCols; ++k) dst[pos * kRawCols + k] = r5[k];
+            }
+            stored += __popc(m);
+        }
+        b0 += fcnt[f];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
+    double cen[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        cen[k] = warp_sum(sacc[k]) / (double)n;
+        mn[k] = warp_min(mn[k]);
+        mx[k] = warp_max(mx[k]);
+    }
+    for (int e = lane; e < 81; e += 32) t.P[e] = (e / 9 == e % 9) ? c.p_init : 0.0;
+    for (int e = lane; e < 36; e += 32) t.G[e] = (e / 6 == e % 6) ? c.g_init : 0.0;
+    if (lane >= 6 && lane < 9) t.x[lane] = 0.0;
+    if (lane < 6) {
+        t.x[lane] = cen[lane];
+        t.centroid[lane] = cen[lane];
+        t.minv[lane] = mn[lane];
+        t.maxv[lane] = mx[lane];
+        t.spread[lane] = 0.0;
+    }
+    if (lane == 0) {
+        t.n_est = 0.0;
+        t.lifetime = 0.0;
+        t.id = track_id;
+        t.point_num = n;
+        t.is_static = sqrt(cen[3] * cen[3] + cen[4] * cen[4] + cen[5] * cen[5]) < c.vel_thres ? 1 : 0;
+        t.slot = slot;
+        t.ring_n = 1;
+        t.ring_head = 0;
+        t.ring_cnt[0] = n < kFeatPts ? n : kFeatPts;
+        t.ring_cnt[1] = 0;
+        t.ring_cnt[2] = 0;
+        t.pad[0] = t.pad[1] = t.pad[2] = 0;
+    }
+    // keypoints = MODEL_DEFAULT_POSTURE until the first inference (Tracking.py:221, Q25)
+    float* kp = a.keypoints + ((size_t)s * tcap + slot) * kKp;
+    for (int e = lane; e < kKp; e += 32) kp[e] = a.default_posture[e];
+}
+
+// fp32 world coordinates of the fused ring (oldest frame first) into shared memory + the screened predicate over
+// them (dbscan.cuh).  Block-cooperative; ends with __syncthreads().
+__device__ __forceinline__ NbScreened load_fused_ring(const StepArgs& a, int s, const int* fcnt, const int* fphys,
+                                                      float* Xf, int stride) {
+    const DevConfig& c = a.cfg;
+    float* Yf = Xf + stride;
+    float* Zf = Yf + stride;
+    NbScreened nb{c, Xf, Yf, Zf, {nullptr, nullptr, nullptr}, {0, 0, 0, 0}, c.db_eps, 0.f, 0.f,
+                  (float)c.db_range_weight, (float)c.db_z_weight};
+    const float band = 1e-3f * (float)c.db_eps + 1e-4f;
+    nb.lo = (float)c.db_eps - band;
+    nb.hi = (float)c.db_eps + band;
+    int b0 = 0;
+    for (int f = 0; f < kRing; ++f) {
+        const float* src = uring_frame(a, s, fphys[f]);
+        nb.frame[f] = src;
+        nb.start[f] = b0;
+        for (int i = threadIdx.x; i < fcnt[f]; i += blockDim.x) {
+            const float x = src[i * kRawCols + 0], y = src[i * kRawCols + 1], z = src[i * kRawCols + 2];
+            double yw, zw;
+            world_yz(c, (double)y, (double)z, yw, zw);
+            Xf[b0 + i] = x; Yf[b0 + i] = (float)yw; Zf[b0 + i] = (float)zw;
+        }
+        b0 += fcnt[f];
+    }
+    nb.start[kRing] = b0;
+    __syncthreads();
+    return nb;
+}
+
+
 // Optional per-phase cycle accounting (thread 0 of every CTA, accumulated with one atomic per phase).
 #define PHASE_MARK(idx)                                                                  \
     do {                                                                                 \
@@ -148,6 +259,11 @@ __device__ __forceinline__ const float* uring_frame(const StepArgs& a, int s, in
 __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(const __grid_constant__ StepArgs a) {
     long long phase_t0 = clock64();
     const long long kernel_t0 = phase_t0;
+    if (a.phase_cycles != nullptr && threadIdx.x == 0) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        a.phase_cycles[16 + gridDim.x + blockIdx.x] = ns;
+    }
     extern __shared__ __align__(16) unsigned char smem[];
     const DevConfig& c = a.cfg;
     const int ncap = c.ncap, tcap = c.tcap;
@@ -449,37 +565,26 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     }
     int ncl = 0;
     const bool run_db = B > 0 && T1 < c.tr_max_tracks;
-    if (run_db) {
-        // fused cloud, oldest frame first; world y/z recomputed in float64 from the raw rows (x is unchanged) and
-        // kept in shared memory rounded to fp32 for the screened predicate (dbscan.cuh)
-        float* Xf = reinterpret_cast<float*>(smem + L.dbf);
-        float* Yf = Xf + 3 * ncap;
-        float* Zf = Yf + 3 * ncap;
-        NbScreened nb{c, Xf, Yf, Zf, {nullptr, nullptr, nullptr}, {0, 0, 0, 0}, c.db_eps, 0.f, 0.f,
-                      (float)c.db_range_weight, (float)c.db_z_weight};
-        const float band = 1e-3f * (float)c.db_eps + 1e-4f;
-        nb.lo = (float)c.db_eps - band;
-        nb.hi = (float)c.db_eps + band;
-        int b0 = 0;
-        for (int f = 0; f < kRing; ++f) {
-            const float* src = uring_frame(a, s, fphys[f]);
-            nb.frame[f] = src;
-            nb.start[f] = b0;
-            for (int i = tid; i < fcnt[f]; i += kStepThreads) {
-                const float x = src[i * kRawCols + 0], y = src[i * kRawCols + 1], z = src[i * kRawCols + 2];
-                double yw, zw;
-                world_yz(c, (double)y, (double)z, yw, zw);
-                Xf[b0 + i] = x; Yf[b0 + i] = (float)yw; Zf[b0 + i] = (float)zw;
-            }
-            b0 += fcnt[f];
-        }
-        nb.start[kRing] = b0;
-        __syncthreads();
-        PHASE_MARK(11);
-        ncl = dbscan_block(nb, B, c.db_min_samples, par, cl, misc + kScan);
-        PHASE_MARK(12);
+    // Big fused clouds (someone walked in: hundreds of points) are rare -- a couple of scenes per frame -- but cost
+    // several times a normal scene-frame and would set this kernel's duration.  They are handed to
+    // dbscan_big_kernel (1024 threads per scene) through a work list; everything else is clustered right here.
+    const bool defer = run_db && a.defer_list != nullptr && B > kDeferPoints;
+    bool deferred_late = false;
+    if (defer) {
+        if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
         sc.dbscan_n = B;
-        if (a.labels_out != nullptr)
+    } else if (run_db) {
+        NbScreened nb = load_fused_ring(a, s, fcnt, fphys, reinterpret_cast<float*>(smem + L.dbf), 3 * ncap);
+        PHASE_MARK(11);
+        ncl = dbscan_block(nb, B, c.db_min_samples, par, cl, misc + kScan, a.phase_cycles, a.defer_list != nullptr);
+        PHASE_MARK(12);
+        if (ncl < 0) {                   // clusters exist: union / border / spawn happen in dbscan_big_kernel
+            if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
+            ncl = 0;
+            deferred_late = true;
+        }
+        sc.dbscan_n = B;
+        if (a.labels_out != nullptr && !deferred_late)
             for (int b = tid; b < B; b += kStepThreads) a.labels_out[(size_t)s * 3 * ncap + b] = cl[b];
     }
 
@@ -502,80 +607,8 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
             }
         }
         for (int q = warp; q < ncl; q += kStepWarps) {
-            TrackRec& t = tr[newidx[q]];
-            // cluster statistics over the 6 world columns, recomputed from the ring's raw rows
-            int n = 0;
-            double sacc[6], mn[6], mx[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { sacc[k] = 0.0; mn[k] = INFINITY; mx[k] = -INFINITY; }
-            int b0 = 0;
-            float* dst = a.track_ring + (((size_t)s * tcap + newslot[q]) * kRing + 0) * (kFeatPts * kRawCols);
-            int stored = 0;
-            for (int f = 0; f < kRing; ++f) {
-                const float* src = uring_frame(a, s, fphys[f]);
-                for (int i0 = 0; i0 < fcnt[f]; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool in = i < fcnt[f] && cl[b0 + i] == q;
-                    float r5[kRawCols];
-                    if (in) {
-#pragma unroll
-                        for (int k = 0; k < kRawCols; ++k) r5[k] = src[i * kRawCols + k];
-                        double w[6];
-                        world_from_raw(c, r5[0], r5[1], r5[2], r5[3], w);
-                        ++n;
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) {
-                            sacc[k] += w[k]; mn[k] = fmin(mn[k], w[k]); mx[k] = fmax(mx[k], w[k]);
-                        }
-                    }
-                    const unsigned m = __ballot_sync(kFull, in);
-                    const int pos = stored + __popc(m & ((1u << lane) - 1u));
-                    if (in && pos < kFeatPts) {
-#pragma unroll
-                        for (int k = 0; k < kRawCols; ++k) dst[pos * kRawCols + k] = r5[k];
-                    }
-                    stored += __popc(m);
-                }
-                b0 += fcnt[f];
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
-            double cen[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                cen[k] = warp_sum(sacc[k]) / (double)n;
-                mn[k] = warp_min(mn[k]);
-                mx[k] = warp_max(mx[k]);
-            }
-            for (int e = lane; e < 81; e += 32) t.P[e] = (e / 9 == e % 9) ? c.p_init : 0.0;
-            for (int e = lane; e < 36; e += 32) t.G[e] = (e / 6 == e % 6) ? c.g_init : 0.0;
-            if (lane < 9) t.x[lane] = 0.0;
-            __syncwarp();
-            if (lane < 6) {
-                t.x[lane] = cen[lane];
-                t.centroid[lane] = cen[lane];
-                t.minv[lane] = mn[lane];
-                t.maxv[lane] = mx[lane];
-                t.spread[lane] = 0.0;
-            }
-            if (lane == 0) {
-                t.n_est = 0.0;
-                t.lifetime = 0.0;
-                t.id = sc.next_id + q;
-                t.point_num = n;
-                t.is_static = sqrt(cen[3] * cen[3] + cen[4] * cen[4] + cen[5] * cen[5]) < c.vel_thres ? 1 : 0;
-                t.slot = newslot[q];
-                t.ring_n = 1;
-                t.ring_head = 0;
-                t.ring_cnt[0] = n < kFeatPts ? n : kFeatPts;
-                t.ring_cnt[1] = 0;
-                t.ring_cnt[2] = 0;
-                t.pad[0] = t.pad[1] = t.pad[2] = 0;
-                misc[kOrder + T1 + q] = newidx[q];
-            }
-            // keypoints = MODEL_DEFAULT_POSTURE until the first inference (Tracking.py:221, Q25)
-            float* kp = a.keypoints + ((size_t)s * tcap + newslot[q]) * kKp;
-            for (int e = lane; e < kKp; e += 32) kp[e] = a.default_posture[e];
+            spawn_track(a, s, tr[newidx[q]], q, newslot[q], sc.next_id + q, cl, fcnt, fphys, lane);
+            if (lane == 0) misc[kOrder + T1 + q] = newidx[q];
         }
         sc.next_id += ncl;
         T2 = T1 + ncl;
@@ -609,6 +642,66 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     PHASE_MARK(10);
     if (a.phase_cycles != nullptr && threadIdx.x == 0)
         a.phase_cycles[16 + blockIdx.x] = (unsigned long long)(clock64() - kernel_t0);   // last frame's cycles of this scene
+    if (a.phase_cycles != nullptr && threadIdx.x == 0) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        a.phase_cycles[16 + 2 * gridDim.x + blockIdx.x] = ns;
+    }
+}
+
+// DBSCAN + spawn for the scenes the step kernel deferred (fused cloud > kDeferPoints): same device functions, one
+// CTA of 1024 threads per scene, new tracks written straight to the scene's list in global memory.
+constexpr int kBigThreads = 1024;
+__global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid_constant__ StepArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const DevConfig& c = a.cfg;
+    const int ncap = c.ncap, tcap = c.tcap;
+    float* Xf = reinterpret_cast<float*>(smem);
+    int* par = reinterpret_cast<int*>(smem + 36 * ncap);
+    int* cl = par + 3 * ncap;
+    int* scan = cl + 3 * ncap;                               // 64 ints
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_defer = *a.defer_count;
+    for (int it = blockIdx.x; it < n_defer; it += gridDim.x) {
+        const int s = a.defer_list[it];
+        SceneRec sc = a.scenes[s];
+        const int T1 = sc.n_tracks;
+        int B = 0;
+        int fcnt[kRing], fphys[kRing];
+        for (int f = 0; f < kRing; ++f) {
+            fphys[f] = (sc.ring_head + f) % c.ring_size;
+            fcnt[f] = f < sc.ring_n ? sc.ring_cnt[fphys[f]] : 0;
+            B += fcnt[f];
+        }
+        NbScreened nb = load_fused_ring(a, s, fcnt, fphys, Xf, 3 * ncap);
+        int ncl = dbscan_block(nb, B, c.db_min_samples, par, cl, scan);
+        if (a.labels_out != nullptr)
+            for (int b = tid; b < B; b += kBigThreads) a.labels_out[(size_t)s * 3 * ncap + b] = cl[b];
+        if (ncl > 0) {
+            if (T1 + ncl > tcap) { ncl = tcap - T1; sc.flags |= MMW_SCENE_TRACK_OVERFLOW; }
+            int newslot[kMaxTcap];
+            {
+                const unsigned capmask = tcap >= 32 ? 0xffffffffu : ((1u << tcap) - 1u);
+                unsigned fs = ~sc.slot_mask & capmask;
+                for (int q = 0; q < ncl; ++q) {
+                    newslot[q] = __ffs(fs) - 1; fs &= fs - 1;
+                    sc.slot_mask |= 1u << newslot[q];
+                }
+            }
+            for (int q = warp; q < ncl; q += kBigThreads / 32)
+                spawn_track(a, s, a.tracks[(size_t)s * tcap + T1 + q], q, newslot[q], sc.next_id + q, cl, fcnt, fphys,
+                            lane);
+            sc.next_id += ncl;
+            sc.n_tracks = T1 + ncl;
+            sc.ring_n = 0;               // batch.clear() (Tracking.py:699-700, Q8)
+            sc.ring_head = 0;
+            sc.ring_cnt[0] = sc.ring_cnt[1] = sc.ring_cnt[2] = 0;
+            if (tid == 0) atomicAdd(&a.counters[5], (unsigned long long)ncl);
+        }
+        __syncthreads();
+        if (tid == 0) a.scenes[s] = sc;
+        __syncthreads();
+    }
 }
 
 cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
@@ -622,7 +715,25 @@ cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         configured = smem;
     }
+    if (a.defer_count != nullptr) {
+        cudaError_t e = cudaMemsetAsync(a.defer_count, 0, sizeof(int32_t), stream);
+        if (e != cudaSuccess) return e;
+    }
     step_kernel<<<a.n_scenes, kStepThreads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dbscan_big(const StepArgs& a, cudaStream_t stream) {
+    if (a.defer_count == nullptr) return cudaSuccess;
+    cudaError_t e;
+    const int big_smem = 36 * a.cfg.ncap + 2 * 3 * a.cfg.ncap * 4 + 64 * 4;
+    static int big_configured = 0;
+    if (big_smem > big_configured) {
+        e = cudaFuncSetAttribute(dbscan_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem);
+        if (e != cudaSuccess) return e;
+        big_configured = big_smem;
+    }
+    dbscan_big_kernel<<<16, kBigThreads, big_smem, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -38,10 +38,16 @@ for f in range(25):
     bt.step(b[f].points, b[f].offsets, b[f].dt, pose=False)
 bt.sync(); bt.phase_clocks(True)
 bt.step(b[25].points, b[25].offsets, b[25].dt, pose=False)
-cyc = np.zeros(S, np.uint64)
-_lib.check(bt.lib.mmw_scene_cycles(bt._h, _lib.ptr(cyc)))
+raw = np.zeros(3 * S, np.uint64)
+_lib.check(bt.lib.mmw_scene_cycles(bt._h, _lib.ptr(raw)))
 bt.phase_clocks(False)
-cyc = cyc.astype(float)
+cyc = raw[:S].astype(float)
+t0 = raw[S:2 * S].astype(np.int64); t1 = raw[2 * S:].astype(np.int64)
+base = t0.min()
+print("CTA start offsets [us]: p50 %.1f p90 %.1f max %.1f | CTA end offsets [us]: p50 %.1f p90 %.1f max %.1f | CTA duration [us]: p50 %.1f max %.1f" % (
+    np.percentile(t0 - base, 50) / 1e3, np.percentile(t0 - base, 90) / 1e3, (t0 - base).max() / 1e3,
+    np.percentile(t1 - base, 50) / 1e3, np.percentile(t1 - base, 90) / 1e3, (t1 - base).max() / 1e3,
+    np.percentile(t1 - t0, 50) / 1e3, (t1 - t0).max() / 1e3))
 n, nid, m = bt.summary()
 rc = bt.ring_counts(); fused = np.where(rc > 0, rc, 0).sum(1)
 print("per-scene cycles: mean %.0f  p50 %.0f  p90 %.0f  p99 %.0f  max %.0f" % (cyc.mean(), np.percentile(cyc, 50),
@@ -49,3 +55,18 @@ print("per-scene cycles: mean %.0f  p50 %.0f  p90 %.0f  p99 %.0f  max %.0f" % (c
 worst = np.argsort(-cyc)[:8]
 for w in worst:
     print("  scene %4d cycles %7.0f tracks %d ring(after) %s M %d" % (w, cyc[w], n[w], rc[w].tolist(), m[w]))
+
+# phase breakdown of the slowest scene alone (same frames replayed in a 1-scene context)
+w = int(worst[0])
+b1 = synth.gen_batch([w], 26)
+bt1 = BatchedTracker(1)
+for f in range(25):
+    bt1.step(b1[f].points, b1[f].offsets, b1[f].dt, pose=False)
+bt1.sync(); bt1.phase_clocks(True)
+bt1.step(b1[25].points, b1[25].offsets, b1[25].dt, pose=False, record_labels=True)
+pc = bt1.phase_clocks(False).astype(float)
+lab, nf = bt1.labels()
+print("slowest scene %d: fused points %d, clusters %d" % (w, nf[0], lab[0, :max(nf[0], 0)].max() + 1 if nf[0] > 0 else 0))
+for i, nme in enumerate(names):
+    print("   %-16s %8.0f" % (nme, pc[i + 1]))
+print("   ring load %.0f dbscan_block %.0f  [count %.0f | union %.0f | find+rank+relabel %.0f | border = rest]" % (pc[11], pc[12], pc[13], pc[14], pc[15]))
