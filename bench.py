@@ -343,12 +343,31 @@ def main():
         dist.destroy_process_group()
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of each kernel from the committed ncu --set full capture (profiles/r01_traffic.json,
+    written by profiles/summarize_ncu.py --traffic), or {} when absent."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 def rooflines(kern, cnt, K, alg_bytes, pk, step_ms):
-    """roofline of the dominant kernel + the tracker step kernel (HBM) and the dense GEMM (tensor)."""
+    """roofline of the dominant kernel (by CUDA-event time inside the step), plus the two that are always reported:
+    the fused tracker step (HBM bound by construction) and the dense-1 GEMM (tensor bound).
+
+    tracker step: algorithmic bytes = SURVEY 8(d) without the pose terms,
+        20 N + 4 M + 32 U + 32 Bf[dbscan ran] + sum_tracks 2*624 + 20 * ring rows written + 8 per scene-frame
+      (fp32-storage convention of the survey; the device keeps track records in float64, i.e. moves 2x of that term)
+    dense 1: algorithmic FLOPs = 2 * rows * 6144 * 1536 (the fp32 layer); the tensor cores execute 3x that
+      (bf16x3 split), reported separately as `executed`."""
     out = {}
-    rows = float(cnt[7]) / K
+    frames, N, M, U, Bf, T, ring_rows, rows_total = (float(x) for x in cnt)
+    rows = rows_total / K
     fc1_flops = 2.0 * rows * 6144 * 1536
-    step_bytes = alg_bytes / K
+    step_bytes = (20 * N + 4 * M + 32 * U + 32 * Bf + T * 2 * 624 + 20 * ring_rows + 8 * frames) / K
+    traffic = ncu_traffic()
     if kern:
         out["kernel_ms"] = kern
         dom = max(kern, key=kern.get)
@@ -356,16 +375,23 @@ def rooflines(kern, cnt, K, alg_bytes, pk, step_ms):
         if st:
             a = step_bytes / (st / 1e3) / 1e9
             out["roofline_step"] = {"kernel": "step_kernel", "bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"],
-                                    "unit": "GB/s", "frac": a / pk["hbm_gbs"], "traffic": None,
-                                    "algorithmic_bytes_per_launch": step_bytes, "peak_src": pk["src"]}
+                                    "unit": "GB/s", "frac": a / pk["hbm_gbs"], "traffic": traffic.get("step_kernel"),
+                                    "algorithmic_bytes_per_launch": step_bytes, "peak_src": pk["src"],
+                                    "note": "latency/issue-bound, not HBM-bound: see DESIGN.md section 4 and profiles/"}
         g = kern.get("fc1", None)
         if g:
             a = fc1_flops / (g / 1e3) / 1e12
-            out["roofline_fc1"] = {"kernel": "fc1", "bound": "tensor", "achieved": a, "peak": pk["bf16_tflops"],
-                                   "unit": "TFLOP/s", "frac": a / pk["bf16_tflops"], "traffic": None,
-                                   "algorithmic_flops_per_launch": fc1_flops, "peak_src": pk["src"]}
+            out["roofline_fc1"] = {"kernel": "gemm_tc_kernel<192,2,0> (dense 1)", "bound": "tensor", "achieved": a,
+                                   "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": a / pk["bf16_tflops"],
+                                   "traffic": traffic.get("gemm_tc_kernel_dense1"),
+                                   "algorithmic_flops_per_launch": fc1_flops, "executed_tflops": 3 * a,
+                                   "executed_frac": 3 * a / pk["bf16_tflops"], "peak_src": pk["src"],
+                                   "note": "fp32-accurate layer as 3 bf16 MMA passes (hi*hi + hi*lo + lo*hi): "
+                                           "`achieved` counts the layer's FLOPs once, `executed` what the tensor "
+                                           "pipe ran"}
         out["roofline"] = dict(out["roofline_fc1"] if dom == "fc1" and g else out.get("roofline_step", {}))
         out["roofline"]["dominant_kernel"] = dom
+        out["algorithmic_bytes_per_step_whole_path"] = alg_bytes / K
     else:
         a = step_bytes / (step_ms / 1e3) / 1e9
         out["roofline"] = {"kernel": "whole step (no per-kernel timing)", "bound": "hbm", "achieved": a,

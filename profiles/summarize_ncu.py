@@ -31,5 +31,28 @@ def main(path):
         print("| %s | " % r[ki].split("(")[0][:40] + " | ".join(r[i] for i, _ in cols) + " |")
 
 
+def traffic(path):
+    """{kernel: dram bytes per launch} (mean over the captured launches) as JSON on stdout."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units = rows[0], rows[1]
+    ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = {}
+    for r in rows[2:]:
+        name = r[ki]
+        key = ("step_kernel" if "step_kernel" in name else "gemm_tc_kernel_dense1" if "gemm_tc_kernel<192" in name or
+               "gemm_tc_kernel<256" in name else "gemm_tc_kernel_dense2" if "gemm_tc_kernel<64" in name else
+               "conv_slab_conv1" if "conv_slab_kernel<16" in name else "conv_slab_conv2" if "conv_slab_kernel<32" in name
+               else name.split("(")[0])
+        b = float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
+        acc.setdefault(key, []).append(b)
+    print(json.dumps({k: sum(v) / len(v) for k, v in acc.items()}, indent=1))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if sys.argv[1] == "--traffic":
+        traffic(sys.argv[2])
+    else:
+        main(sys.argv[1])
