@@ -19,6 +19,7 @@
 // Warp roles in both kernels: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -535,6 +536,148 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     }
 }
 
+// ---- dense 1 with 2-CTA clusters and TMA multicast ---------------------------------------------------------
+// The plain kernel above is L2-bandwidth bound: 120 CTAs x 96 K blocks x 80 KB = 0.92 GB through L2 per call.  Two
+// CTAs that own vertically adjacent 128-row tiles need the SAME W tile, so they form a cluster (1,2,1): each loads
+// half of the W rows and multicasts them into both CTAs' shared memory (A stays private).  Per CTA and K block
+// that is 32 KB (A) + 24 KB (W) instead of 80 KB.  A stage may be refilled only when BOTH CTAs' MMAs have read it,
+// so tcgen05.commit arrives on the empty barrier of both CTAs (count 2).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+        "%4}], [%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                     "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                       const __grid_constant__ CUtensorMap map_wh_half, const __grid_constant__ CUtensorMap map_wl_half,
+                       const GemmTcArgs a) {
+    constexpr int BM = 128, UK = 16;
+    constexpr int A_BYTES = BM * kBK * 2, B_BYTES = BN * kBK * 2, BH_BYTES = B_BYTES / 2;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t TCOLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    const int rows = *a.n_rows;
+    if ((int)(blockIdx.y & ~1u) * BM >= rows) return;          // the whole cluster is past the last row
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const uint32_t rank = cluster_ctarank();
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = a.K / kBK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh_half) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl_half) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                          // both CTAs' barriers exist before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                unsigned char* st = smem + s * STAGE_BYTES;
+                mbar_expect_tx(&full[s], STAGE_BYTES);           // own A + both halves of W (one arrives from the peer)
+                tma_load_2d(st, &map_ah, &full[s], kb * kBK, m0);
+                tma_load_2d(st + A_BYTES, &map_al, &full[s], kb * kBK, m0);
+                tma_load_2d_mc(st + 2 * A_BYTES + rank * BH_BYTES, &map_wh_half, &full[s], kb * kBK,
+                               n0 + (int)rank * (BN / 2), (uint16_t)3);
+                tma_load_2d_mc(st + 2 * A_BYTES + B_BYTES + rank * BH_BYTES, &map_wl_half, &full[s], kb * kBK,
+                               n0 + (int)rank * (BN / 2), (uint16_t)3);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t dah = make_desc<128>(st), dal = make_desc<128>(st + A_BYTES);
+                const uint64_t dwh = make_desc<128>(st + 2 * A_BYTES), dwl = make_desc<128>(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < kBK / UK; ++kk) {
+                    const uint64_t adv = (uint64_t)((kk * UK * 2) >> 4);
+                    umma_bf16(tmem_d, dah + adv, dwh + adv, idesc, (kb | kk) != 0);
+                    umma_bf16(tmem_d, dah + adv, dwl + adv, idesc, 1);
+                    umma_bf16(tmem_d, dal + adv, dwh + adv, idesc, 1);
+                }
+                umma_commit_mc(&empty[s], (uint16_t)3);          // frees the stage in BOTH CTAs' view
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (row >= rows) continue;
+            __align__(16) __nv_bfloat16 hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = n0 + c0 + j;
+                float x = fmaxf(__uint_as_float(v[j]) + __ldg(a.bias + n), 0.f);
+                x = fmaf(x, __ldg(a.bn_scale + n), __ldg(a.bn_shift + n));
+                split2(x, hi[j], lo[j]);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(a.out_hi + (size_t)row * a.N + n0 + c0);
+            uint4* ol = reinterpret_cast<uint4*>(a.out_lo + (size_t)row * a.N + n0 + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                oh[i] = reinterpret_cast<const uint4*>(hi)[i];
+                ol[i] = reinterpret_cast<const uint4*>(lo)[i];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                          // the peer may still arrive on / write to this CTA
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TCOLS>(tmem_d);
+    }
+}
+
 // fp32 feature maps [rows][D*64][5] (position = (d, h, w)) -> packed bf16 in slab order [rows][D][8 w][2][8 h][8]:
 // chunk 0 = (hi c0..4, 0,0,0), chunk 1 = (lo c0..4, 0,0,0)
 __global__ void pack_input_kernel(const float* __restrict__ feats, __nv_bfloat16* __restrict__ out, const int* n_rows,
@@ -562,7 +705,8 @@ struct TcImpl {
     __nv_bfloat16 *h_hi = nullptr, *h_lo = nullptr;                   // dense-2 operand [rows_pad][H]
     __nv_bfloat16 *w1b = nullptr, *w2b = nullptr;                     // conv B matrices [taps][NOUT][CK]
     __nv_bfloat16 *wd1_hi = nullptr, *wd1_lo = nullptr, *wd2_hi = nullptr, *wd2_lo = nullptr;
-    CUtensorMap m_in, m_act1, m_w1b, m_w2b, m_ah, m_al, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l;
+    CUtensorMap m_in, m_act1, m_w1b, m_w2b, m_ah, m_al, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l, m_w1h_half, m_w1l_half;
+    bool cluster = false;
 };
 
 static std::string g_tc_err;
@@ -701,6 +845,8 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
         make_map_2d(&im->m_ah, im->a_hi, R, im->Kf, 128, 64) || make_map_2d(&im->m_al, im->a_lo, R, im->Kf, 128, 64) ||
         make_map_2d(&im->m_w1h, im->wd1_hi, im->H, im->Kf, im->H % 192 == 0 ? 192 : 256, 64) ||
         make_map_2d(&im->m_w1l, im->wd1_lo, im->H, im->Kf, im->H % 192 == 0 ? 192 : 256, 64) ||
+        (im->H % 192 == 0 && (make_map_2d(&im->m_w1h_half, im->wd1_hi, im->H, im->Kf, 96, 64) ||
+                              make_map_2d(&im->m_w1l_half, im->wd1_lo, im->H, im->Kf, 96, 64))) ||
         make_map_2d(&im->m_hh, im->h_hi, R, im->H, 128, 64) || make_map_2d(&im->m_hl, im->h_lo, R, im->H, 128, 64) ||
         make_map_2d(&im->m_w2h, im->wd2_hi, 64, im->H, 64, 64) || make_map_2d(&im->m_w2l, im->wd2_lo, 64, im->H, 64, 64))
         return -1;
@@ -718,6 +864,16 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_kernel<192, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  gemm_smem_bytes<192, 2>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_cluster_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 gemm_smem_bytes<192, 2>());
+    {
+        // Measured: no gain (108 vs 110 us).  The kernel is bound by what each SM can ingest from L2 (~64 B/clk: 80 KB
+        // per K block against 1152 MMA cycles), and multicast does not reduce the bytes landing in an SM's shared
+        // memory -- only cta_group::2 (B tile split across the pair) would.  Kept for experiments, off by default.
+        const char* env = getenv("MMW_FC1_CLUSTER");
+        im->cluster = im->H % 192 == 0 && env && env[0] == '1';
+    }
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_kernel<64, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  gemm_smem_bytes<64, 4>());
@@ -770,7 +926,20 @@ int pose_tc_fc1(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
                  im->Kf, im->H, r.tcap};
     // 128 x 192 tiles when they divide N: 1536/192 = 8 column tiles, i.e. 120 CTAs for ~1900 rows instead of 90
     // CTAs of 128 x 256 on 148 SMs (one wave either way, 25 % less work per CTA)
-    if (im->H % 192 == 0) {
+    if (im->cluster) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(im->H / 192, (((max_rows + 127) / 128) + 1) & ~1);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = gemm_smem_bytes<192, 2>();
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_cluster_kernel<192, 2>, im->m_ah, im->m_al, im->m_w1h_half,
+                                            im->m_w1l_half, g);
+        if (le != cudaSuccess) { g_tc_err = std::string("cudaLaunchKernelEx(dense1 cluster): ") + cudaGetErrorString(le); return -1; }
+    } else if (im->H % 192 == 0) {
         dim3 grid(im->H / 192, (max_rows + 127) / 128);
         gemm_tc_kernel<192, 2, 0><<<grid, kGemmThreads, gemm_smem_bytes<192, 2>(), st>>>(im->m_ah, im->m_al, im->m_w1h,
                                                                                         im->m_w1l, g);
