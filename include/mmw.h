@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MMW_ABI_VERSION 1
+#define MMW_ABI_VERSION 2
 
 typedef enum mmw_status {
     MMW_OK = 0,
@@ -65,6 +65,11 @@ typedef struct mmw_config {
     double x_nudge_gain;           /* 0.4, Tracking.py:398 */
     float default_posture[57];     /* MODEL_DEFAULT_POSTURE :112-172 */
     float reserved1;
+    /* smart-window projection (the step right after the path: Utils.py:180-219, Visualizer.py:14-29) */
+    double m_x, m_y, m_z;          /* M_X, M_Y, M_Z :31-33: the sensitive object behind the window */
+    double fade_size_max;          /* V_SCREEN_FADE_SIZE_MAX :50 */
+    double fade_size_min;          /* V_SCREEN_FADE_SIZE_MIN :51 */
+    double fade_weight;            /* V_SCREEN_FADE_WEIGHT :52 */
 } mmw_config;
 
 /* Fills *cfg with the reference's default constants. */
@@ -223,9 +228,13 @@ int mmw_pose(mmw_ctx* ctx, const float* feats, int n, float* keypoints);
 /* ---- device-side views for a host framework that owns the stream (bench / torch.distributed gather) ---- */
 
 /* Packs the per-scene results of the last frame into a caller-provided DEVICE buffer of
- * S * max_tracks * MMW_RESULT_FLOATS fp32 (id, n_tracks, x[9], keypoints[57]), ready to be
- * all-gathered across ranks.  Asynchronous on the context's stream. */
-#define MMW_RESULT_FLOATS 68
+ * S * max_tracks * MMW_RESULT_FLOATS fp32, ready to be all-gathered across ranks.  Record layout:
+ *   [0] id (-1 = no track)  [1] n_tracks of the scene  [2..10] state.x  [11..67] keypoints
+ *   [68] [69] centre (x, z) of the track's fade square on the smart window = calc_projection_points(
+ *        x[0] + kp[3], x[1] + kp[41], kp[22])  (Visualizer.py:16-20, Utils.py:180-219)
+ *   [70] side of the fade square (Visualizer.py:21-28)   [71] 0
+ * Asynchronous on the context's stream. */
+#define MMW_RESULT_FLOATS 72
 int mmw_pack_results(mmw_ctx* ctx, float* device_out);
 
 /* Pipelined result read-back for the hot loop: packs the results of the frames queued so far (same layout as

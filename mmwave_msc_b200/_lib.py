@@ -13,7 +13,8 @@ LIB_PATH = os.environ.get("MMW_LIB", os.path.join(_HERE, "libmmw.so"))   # MMW_L
 MMW_POSE_2D, MMW_POSE_3D = 0, 1
 STEP_POSE, STEP_DEVICE_INPUT, STEP_RECORD_LABELS = 0x1, 0x2, 0x4
 SCENE_POINT_OVERFLOW, SCENE_TRACK_OVERFLOW = 0x1, 0x2
-RESULT_FLOATS = 68
+RESULT_FLOATS = 72
+ABI_VERSION = 2            # MMW_ABI_VERSION of include/mmw.h this binding was written against
 KERNEL_NAMES = ["step", "pose_index", "pose_features", "conv", "fc1", "fc2", "dbscan_big", "k7"]
 
 
@@ -36,6 +37,8 @@ class Config(C.Structure):
         ("intensity_mu", C.c_double), ("intensity_std", C.c_double),
         ("x_nudge_thres", C.c_double), ("x_nudge_gain", C.c_double),
         ("default_posture", C.c_float * 57), ("reserved1", C.c_float),
+        ("m_x", C.c_double), ("m_y", C.c_double), ("m_z", C.c_double),
+        ("fade_size_max", C.c_double), ("fade_size_min", C.c_double), ("fade_weight", C.c_double),
     ]
 
 
@@ -121,6 +124,9 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
+    if lib.mmw_abi_version() != ABI_VERSION:   # a stale libmmw.so would mis-read the config struct: fail loudly
+        raise MmwError("libmmw.so at %s has ABI version %d, this binding needs %d -- rebuild it"
+                       % (LIB_PATH, lib.mmw_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

@@ -49,7 +49,11 @@ def config_from_constants(const) -> _lib.Config:
         kf_p_init=float(const.KF_P_INIT), kf_group_disp_init=float(const.KF_GROUP_DISP_EST_INIT),
         kf_a_n=float(const.KF_A_N), kf_a_spr=float(const.KF_A_SPR), kf_spread_lim=list(const.KF_SPREAD_LIM),
         kf_est_pointnum=int(const.KF_EST_POINTNUM), intensity_mu=float(const.INTENSITY_MU),
-        intensity_std=float(const.INTENSITY_STD), default_posture=list(np.asarray(const.MODEL_DEFAULT_POSTURE)))
+        intensity_std=float(const.INTENSITY_STD), default_posture=list(np.asarray(const.MODEL_DEFAULT_POSTURE)),
+        m_x=float(getattr(const, "M_X", 0.32)), m_y=float(getattr(const, "M_Y", -0.6)),
+        m_z=float(getattr(const, "M_Z", 1.3)), fade_size_max=float(getattr(const, "V_SCREEN_FADE_SIZE_MAX", 0.3)),
+        fade_size_min=float(getattr(const, "V_SCREEN_FADE_SIZE_MIN", 0.2)),
+        fade_weight=float(getattr(const, "V_SCREEN_FADE_WEIGHT", 0.08)))
 
 
 class BatchedTracker:

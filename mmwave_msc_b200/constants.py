@@ -8,6 +8,14 @@ by tests/test_abi_cpu.py through tests/golden/known_answers.json).
 """
 import numpy as np
 
+# smart window: sensitive object and fade-square sizing (constants.py:31-33, 50-54)
+M_X = 0.32
+M_Y = -0.6
+M_Z = 1.3
+V_SCREEN_FADE_SIZE_MAX = 0.3
+V_SCREEN_FADE_SIZE_MIN = 0.2
+V_SCREEN_FADE_WEIGHT = 0.08
+
 # sensor pose (constants.py:41-42)
 S_HEIGHT = 1.8
 S_TILT = -5

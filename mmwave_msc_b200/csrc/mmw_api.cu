@@ -150,6 +150,8 @@ int mmw_default_config(mmw_config* c) {
     c->intensity_mu = 27.0187; c->intensity_std = 70.351;
     c->x_nudge_thres = 0.6; c->x_nudge_gain = 0.4;
     std::memcpy(c->default_posture, kDefaultPosture, sizeof(kDefaultPosture));
+    c->m_x = 0.32; c->m_y = -0.6; c->m_z = 1.3;
+    c->fade_size_max = 0.3; c->fade_size_min = 0.2; c->fade_weight = 0.08;
     return MMW_OK;
 }
 
@@ -719,8 +721,19 @@ __global__ void __launch_bounds__(128) gate_stage_kernel(const double* pts, int 
     }
 }
 
+struct FadeCfg { double m_x, m_y, m_z, smax, smin, weight; };
+
+// calc_projection_points (Utils.py:180-219): where the line from the point to the sensitive object (M_X, M_Y, M_Z)
+// crosses the window plane y = 0.
+__device__ __forceinline__ void projection_point(const FadeCfg& f, double xo, double yo, double zo, double& xp,
+                                                 double& zp) {
+    const double xd = xo - f.m_x, yd = yo - f.m_y, zd = zo - f.m_z;
+    xp = (xd == 0.0) ? xo : (-f.m_y / (yd / xd)) + f.m_x;
+    zp = (zd == 0.0) ? zo : (-f.m_y / (yd / zd)) + f.m_z;
+}
+
 __global__ void pack_results_kernel(const SceneRec* scenes, const TrackRec* tracks, const float* keypoints, int S,
-                                    int tcap, float* out) {
+                                    int tcap, float* out, FadeCfg fade) {
     const int idx = blockIdx.x;            // scene * tcap + k
     const int s = idx / tcap, k = idx % tcap;
     float* o = out + (size_t)idx * MMW_RESULT_FLOATS;
@@ -731,13 +744,21 @@ __global__ void pack_results_kernel(const SceneRec* scenes, const TrackRec* trac
         return;
     }
     const TrackRec* t = tracks + (size_t)s * tcap + k;
-    for (int e = threadIdx.x; e < MMW_RESULT_FLOATS; e += blockDim.x) {
+    const float* kp = keypoints + ((size_t)s * tcap + t->slot) * kKp;
+    for (int e = threadIdx.x; e < 68; e += blockDim.x) {
         float v;
         if (e == 0) v = (float)t->id;
         else if (e == 1) v = (float)nt;
         else if (e < 11) v = (float)t->x[e - 2];
-        else v = keypoints[((size_t)s * tcap + t->slot) * kKp + (e - 11)];
+        else v = kp[e - 11];
         o[e] = v;
+    }
+    if (threadIdx.x == 0) {
+        // calc_fade_square (Visualizer.py:14-29), float64 like the reference
+        double cx, cz;
+        projection_point(fade, t->x[0] + (double)kp[3], t->x[1] + (double)kp[41], (double)kp[22], cx, cz);
+        const double size = fmax(fade.smin, fmin(fade.smax, fade.smax - (t->x[1] + (double)kp[12]) * fade.weight));
+        o[68] = (float)cx; o[69] = (float)cz; o[70] = (float)size; o[71] = 0.f;
     }
 }
 
@@ -748,8 +769,9 @@ extern "C" {
 int mmw_pack_results(mmw_ctx* x, float* device_out) {
     if (!x || !device_out) return fail(MMW_ERR_INVALID, "ctx/device_out is NULL");
     CK(cudaSetDevice(x->device));
+    const FadeCfg fc{x->cfg.m_x, x->cfg.m_y, x->cfg.m_z, x->cfg.fade_size_max, x->cfg.fade_size_min, x->cfg.fade_weight};
     pack_results_kernel<<<x->S * x->tcap, 64, 0, x->stream>>>(x->d_scenes, x->d_tracks, x->d_keypoints, x->S, x->tcap,
-                                                              device_out);
+                                                              device_out, fc);
     CK(cudaGetLastError());
     x->launches++;
     return MMW_OK;
@@ -760,8 +782,9 @@ int mmw_read_results_async(mmw_ctx* x, float* host_out, int* slot) {
     CK(cudaSetDevice(x->device));
     const int r = (int)(x->result_idx++ & 1u);
     CK(cudaStreamWaitEvent(x->stream, x->results_done[r], 0));     // previous download of this buffer finished
+    const FadeCfg fc{x->cfg.m_x, x->cfg.m_y, x->cfg.m_z, x->cfg.fade_size_max, x->cfg.fade_size_min, x->cfg.fade_weight};
     pack_results_kernel<<<x->S * x->tcap, 64, 0, x->stream>>>(x->d_scenes, x->d_tracks, x->d_keypoints, x->S, x->tcap,
-                                                              x->d_results[r]);
+                                                              x->d_results[r], fc);
     CK(cudaGetLastError());
     x->launches++;
     CK(cudaEventRecord(x->packed[r], x->stream));

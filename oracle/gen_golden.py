@@ -59,6 +59,11 @@ def known_answers() -> dict:
     ka["Q_dt1"] = const.MOTION_MODEL.KF_Q_DISCR(1).tolist()
     ka["F_dt0.25"] = const.MOTION_MODEL.KF_F(0.25).tolist()
     ka["default_posture"] = np.asarray(const.MODEL_DEFAULT_POSTURE).tolist()
+    # row f-2: the reference's own calc_projection_points (Utils.py:180-219); the second input has x_dist == z_dist == 0
+    pin = [[1.2, 3.4, 1.1], [0.32, 2.0, 1.3], [-0.7, 1.5, 0.4]]
+    ka["projection_points"] = {"inputs": pin, "outputs": [list(map(float, utils.calc_projection_points(*q))) for q in pin]}
+    ka["window_constants"] = {n: getattr(const, n) for n in (
+        "M_X", "M_Y", "M_Z", "V_SCREEN_FADE_SIZE_MAX", "V_SCREEN_FADE_SIZE_MIN", "V_SCREEN_FADE_WEIGHT")}
     ka["constants"] = {n: getattr(const, n) for n in (
         "S_HEIGHT", "S_TILT", "FB_FRAMES_BATCH", "DB_Z_WEIGHT", "DB_RANGE_WEIGHT", "DB_EPS", "DB_MIN_SAMPLES_MIN",
         "TR_MAX_TRACKS", "TR_LIFETIME_DYNAMIC", "TR_LIFETIME_STATIC", "TR_VEL_THRES", "TR_GATE", "KF_R_STD",

@@ -378,6 +378,27 @@ def pose_forward(weights: Sequence[np.ndarray], feats: np.ndarray, dtype=np.floa
 
 
 # ----------------------------------------------------------------------------
+# "next" row f-2: smart-window projection of a track (Utils.py:180-219, Visualizer.py:14-29)
+# ----------------------------------------------------------------------------
+def projection_point(x_origin, y_origin, z_origin, m=(0.32, -0.6, 1.3)):
+    """Utils.calc_projection_points (Utils.py:180-219) with M_X, M_Y, M_Z of constants.py:31-33."""
+    x_dist, y_dist, z_dist = x_origin - m[0], y_origin - m[1], z_origin - m[2]
+    x_proj = x_origin if x_dist == 0 else -m[1] / (y_dist / x_dist) + m[0]
+    z_proj = z_origin if z_dist == 0 else -m[1] / (y_dist / z_dist) + m[2]
+    return x_proj, z_proj
+
+
+def fade_square(x, keypoints, m=(0.32, -0.6, 1.3), size_max=0.3, size_min=0.2, weight=0.08):
+    """Visualizer.calc_fade_square (Visualizer.py:14-29): centre and side of the opaque square.  Restated from the
+    source (Visualizer.py cannot be imported here: matplotlib / pyqtgraph are absent), so only its
+    calc_projection_points part is pinned by a golden value."""
+    kp = np.asarray(keypoints, dtype=np.float64)
+    center = projection_point(x[0] + kp[3], x[1] + kp[41], kp[22], m)
+    size = max(size_min, min(size_max, size_max - (x[1] + kp[12]) * weight))
+    return center, size
+
+
+# ----------------------------------------------------------------------------
 # a11  one scene: TrackBuffer.track + estimate_posture under the offline_main loop
 # ----------------------------------------------------------------------------
 class SceneOracle:

@@ -24,7 +24,8 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "libmmw.so does not export %s" % s
     assert sorted(_lib.SIGNATURES) == syms, "ctypes SIGNATURES and include/mmw.h disagree"
-    assert lib.mmw_abi_version() == 1
+    want = int(re.search(r"#define MMW_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "mmw.h")).read()).group(1))
+    assert lib.mmw_abi_version() == want == _lib.ABI_VERSION
 
 
 def test_default_config_matches_reference_constants():

@@ -8,7 +8,7 @@ import pytest
 
 from conftest import GOLDEN, golden_cases
 from helpers import KEYPOINT_ATOL, compare_frame, oracle_config
-from mmwave_msc_b200 import pose_weights as pw, synth
+from mmwave_msc_b200 import _lib, pose_weights as pw, synth
 from mmwave_msc_b200.batched import BatchedTracker, default_config
 from oracle import mmw_oracle as mo, trace_io
 
@@ -268,7 +268,7 @@ def test_pipelined_results_match_blocking_readback():
     bt.load_pose_weights(W)
     ref = BatchedTracker(S)
     ref.load_pose_weights(W)
-    host = [torch.empty(S * bt.tcap * 68, dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+    host = [torch.empty(S * bt.tcap * _lib.RESULT_FLOATS, dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
     pinned = []
     for b in batches:                      # the API keeps reading the caller's buffers until the copy has run
         pinned.append((torch.from_numpy(b.points).pin_memory().numpy(), torch.from_numpy(b.offsets).pin_memory().numpy(),
@@ -287,11 +287,14 @@ def test_pipelined_results_match_blocking_readback():
     for f, b in enumerate(batches):
         ref.step(b.points, b.offsets, b.dt, pose=True)
         tr, nt = ref.tracks()
-        got = snaps[f].reshape(S, bt.tcap, 68)
+        got = snaps[f].reshape(S, bt.tcap, _lib.RESULT_FLOATS)
         for s in range(S):
             assert int(got[s, 0, 1]) == nt[s]
             for k in range(nt[s]):
                 assert int(got[s, k, 0]) == tr[s, k]["id"]
                 np.testing.assert_array_equal(got[s, k, 2:11], tr[s, k]["x"].astype(np.float32))
-                np.testing.assert_array_equal(got[s, k, 11:], tr[s, k]["keypoints"])
+                np.testing.assert_array_equal(got[s, k, 11:68], tr[s, k]["keypoints"])
+                # row f-2: fade square of the smart window, float64 on both sides, stored as fp32
+                (cx, cz), size = mo.fade_square(tr[s, k]["x"], tr[s, k]["keypoints"])
+                np.testing.assert_array_equal(got[s, k, 68:71], np.array([cx, cz, size]).astype(np.float32))
             assert np.all(got[s, nt[s]:, 0] == -1)

@@ -43,6 +43,24 @@ def test_known_answers():
     np.testing.assert_allclose(np.diag(P), KA["predict_diagP_dt0.1"], rtol=1e-15)
 
 
+def test_projection_points_match_reference():
+    """Row f-2: oracle restatement of Utils.calc_projection_points against the reference's own outputs."""
+    pp = KA["projection_points"]
+    for q, want in zip(pp["inputs"], pp["outputs"]):
+        assert list(mo.projection_point(*q)) == want
+    wc = KA["window_constants"]
+    from mmwave_msc_b200 import constants as c
+    assert (c.M_X, c.M_Y, c.M_Z) == (wc["M_X"], wc["M_Y"], wc["M_Z"])
+    assert (c.V_SCREEN_FADE_SIZE_MAX, c.V_SCREEN_FADE_SIZE_MIN, c.V_SCREEN_FADE_WEIGHT) == \
+        (wc["V_SCREEN_FADE_SIZE_MAX"], wc["V_SCREEN_FADE_SIZE_MIN"], wc["V_SCREEN_FADE_WEIGHT"])
+    # calc_fade_square (Visualizer.py:14-29) on the default posture: clamp active on both sides
+    kp = np.asarray(KA["default_posture"])
+    (cx, cz), size = mo.fade_square(np.array([0.5, 0.2, 1.0]), kp)
+    assert size == 0.3 - (0.2 + kp[12]) * 0.08 or size in (0.2, 0.3)
+    assert mo.fade_square(np.array([0.5, 9.0, 1.0]), kp)[1] == 0.2
+    assert mo.fade_square(np.array([0.5, -9.0, 1.0]), kp)[1] == 0.3
+
+
 def _run_oracle(g, max_tracks):
     so = mo.SceneOracle(mo.OracleConfig(tr_max_tracks=max_tracks))
     return [so.step(fr, dt) for fr, dt in zip(g["frames"], g["dts"])]
