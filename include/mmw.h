@@ -225,6 +225,17 @@ int mmw_gate(mmw_ctx* ctx, const double* points, int M, const double* hx, const 
 /* Keras model.predict (Tracking.py:732): feats [n, (frames_batch+1)*64*5] fp32 -> keypoints [n,57] fp32. */
 int mmw_pose(mmw_ctx* ctx, const float* feats, int n, float* keypoints);
 
+/* ---- dataset-builder mode ---- */
+
+/* What preprocessing.preprocess_dataset (preprocessing.py:185-216) writes after a frame, for every scene at once:
+ * valid[s] = 1 iff the scene's last frame ran track(), track 0 exists, was associated in that frame (lifetime == 0)
+ * and has points in its ring; then rows[s] is the (192, 5) float64 block of
+ * Utils.format_batched_frames(Utils.relative_coordinates(ring frames, centroid)) (Utils.py:523-548, 437-465): ring
+ * frames newest first, [x - cx, y - cy, z, doppler, peakVal], first 64 rows per frame, zero padded, unsorted; and
+ * centroid[s] = track 0's cluster centroid[:2] (preprocessing.py:209-213).  rows of invalid scenes are zero.
+ * Host pointers: rows [S][192][5], valid [S], centroid [S][2] (may be NULL).  Synchronous. */
+int mmw_export_track0(mmw_ctx* ctx, double* rows, int32_t* valid, double* centroid);
+
 /* ---- device-side views for a host framework that owns the stream (bench / torch.distributed gather) ---- */
 
 /* Packs the per-scene results of the last frame into a caller-provided DEVICE buffer of
@@ -275,6 +286,11 @@ int mmw_get_kernel_ms(mmw_ctx* ctx, double* total_ms /*[MMW_N_KERNELS]*/, uint64
 int mmw_phase_clocks(mmw_ctx* ctx, int enable, uint64_t* out16);
 /* Debug: SM cycles the step kernel spent on each scene in the last frame stepped with the accounting on. */
 int mmw_scene_cycles(mmw_ctx* ctx, uint64_t* out /*[3*S]: cycles, then start and end %globaltimer ns per scene*/);
+
+/* Debug: cycles of dbscan_big_kernel (thread 0 of each CTA, summed over the deferred scenes) since the last call, while
+ * mmw_phase_clocks is on: [0] ring load [1] labels+spawn+write-back [2] scenes [3] counts [4] unions [5] rank+relabel
+ * [6] border sweep [7] fused points. */
+int mmw_dbscan_big_clocks(mmw_ctx* ctx, uint64_t* out8);
 
 /* Number of kernels this library launched since creation (bench.py's gpu_launches). */
 uint64_t mmw_launch_count(mmw_ctx* ctx);

@@ -96,6 +96,7 @@ SIGNATURES = {
     "mmw_kalman_update": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int]),
     "mmw_gate": (C.c_int, [_p, _p, C.c_int, _p, _p, C.c_int, _p, _p]),
     "mmw_pose": (C.c_int, [_p, _p, C.c_int, _p]),
+    "mmw_export_track0": (C.c_int, [_p, _p, _p, _p]),
     "mmw_pack_results": (C.c_int, [_p, _p]),
     "mmw_read_results_async": (C.c_int, [_p, _p, C.POINTER(C.c_int)]),
     "mmw_wait_results": (C.c_int, [_p, C.c_int]),
@@ -105,6 +106,7 @@ SIGNATURES = {
     "mmw_get_kernel_ms": (C.c_int, [_p, _p, _p]),
     "mmw_phase_clocks": (C.c_int, [_p, C.c_int, _p]),
     "mmw_scene_cycles": (C.c_int, [_p, _p]),
+    "mmw_dbscan_big_clocks": (C.c_int, [_p, _p]),
     "mmw_launch_count": (C.c_uint64, [_p]),
 }
 

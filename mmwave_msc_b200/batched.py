@@ -227,6 +227,15 @@ class BatchedTracker:
     def launch_count(self) -> int:
         return int(self.lib.mmw_launch_count(self._h))
 
+    def export_track0(self):
+        """Dataset-builder export (preprocessing.py:185-216): (rows [S,192,5] float64, valid [S] bool,
+        centroid [S,2]) of track 0 of every scene after the last step."""
+        rows = np.zeros((self.S, 192, 5), np.float64)
+        valid = np.zeros(self.S, np.int32)
+        cen = np.zeros((self.S, 2), np.float64)
+        _lib.check(self.lib.mmw_export_track0(self._h, _lib.ptr(rows), _lib.ptr(valid), _lib.ptr(cen)))
+        return rows, valid.astype(bool), cen
+
     def pack_results(self, device_ptr: int):
         _lib.check(self.lib.mmw_pack_results(self._h, C.c_void_p(device_ptr)))
 

@@ -139,7 +139,8 @@ template <class Nb>
 // dbscan_big_kernel: clusters form in a couple of scenes per frame and the remaining sweeps would make that CTA
 // the one the whole step kernel waits for).
 __device__ inline int dbscan_block(const Nb& nb_full, int B, int min_samples, int* par, int* cl, int* s_scan,
-                                   unsigned long long* dbg = nullptr, bool stop_if_core = false) {
+                                   unsigned long long* dbg = nullptr, bool stop_if_core = false,
+                                   bool dbg_border = false) {
     const auto nb = nb_full.hot();
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     long long dbg_t = clock64();
@@ -235,6 +236,174 @@ __device__ inline int dbscan_block(const Nb& nb_full, int B, int min_samples, in
     for (int b = tid; b < B; b += nt)
         if (cl[b] < 0) cl[b] = par[b] == 0x7fffffff ? -1 : par[b];
     __syncthreads();
+    if (dbg_border) stamp(16);
+    return ncl;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same DBSCAN on an explicit adjacency bit matrix (dbscan_big_kernel).  The pair sweeps above evaluate the
+// predicate up to three times per pair and are chained through shared-memory atomics; for the handful of scenes per
+// frame in which clusters actually form that chain IS the kernel's duration.  Here the predicate is evaluated once
+// per ordered pair into adj[b][w] (bit j of word w = point 32 w + j is within eps of b, b included), after which
+// every phase is "one warp per row, one lane per bit, a loop over the W words of the row":
+//   counts -> popc;  components -> min-label propagation over core neighbours + pointer jumping until stable
+//   (labels only decrease and stay inside the component, so the fixed point is the smallest core index = the root
+//   dbscan_inner's ascending scan starts the cluster from);  cluster ids -> popc of the root bit mask;  border points
+//   -> min cluster id over core neighbours.  No atomics, results independent of scheduling.
+// adj: B * ceil(B/32) words; cm, rm: ceil(B/32) words each (shared).  Requires B <= blockDim.x * 32.
+__device__ inline int dbscan_bits_block(const NbScreened& nbf, int B, int min_samples, unsigned* adj, unsigned* cm,
+                                        unsigned* rm, int* par, int* cl, unsigned long long* dbg = nullptr) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int W = (B + 31) >> 5;
+    long long dbg_t = clock64();
+    auto stamp = [&](int k) {
+        if (dbg != nullptr && tid == 0) {
+            const long long now = clock64();
+            atomicAdd(&dbg[k], (unsigned long long)(now - dbg_t));
+            dbg_t = now;
+        }
+    };
+    // 1. adjacency rows and neighbour counts.  Four words of a row are in flight at once; the fp32 screen decides
+    //    almost every pair, the few inside the guard band are settled exactly afterwards (same decisions as
+    //    NbScreened::Hot, see there).
+    {
+        const float *X = nbf.Xf, *Y = nbf.Yf, *Z = nbf.Zf;
+        const float lo = nbf.lo, hi = nbf.hi, rw = nbf.rw, zw = nbf.zw;
+        for (int b = warp; b < B; b += nw) {
+            const float xb = X[b], yb = Y[b], zb = Z[b];
+            int cnt = 0;
+            for (int w0 = 0; w0 < W; w0 += 4) {
+                float d[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = ((w0 + u) << 5) + lane;
+                    const bool live = q < B;                              // q < B implies w0 + u < W
+                    const float xq = live ? X[q] : 0.f, yq = live ? Y[q] : 0.f, zq = live ? Z[q] : 0.f;
+                    const float wgt = 1.f - 0.5f * (yb + yq) * rw;
+                    const float dx = xb - xq, dy = yb - yq, dz = zb - zq;
+                    d[u] = live ? wgt * (dx * dx + dy * dy + zw * (dz * dz)) : INFINITY;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int w = w0 + u;
+                    if (w >= W) break;                                    // uniform over the warp
+                    const int q = (w << 5) + lane;
+                    bool hit = d[u] < lo;
+                    const bool unsure = q < B && !(d[u] > hi) && !hit;    // inside the band, or not finite
+                    if (__any_sync(kFullMask, unsure)) {
+                        if (unsure) hit = nbf.exact(b, q);
+                    }
+                    const unsigned m = __ballot_sync(kFullMask, hit);
+                    if (lane == 0) adj[b * W + w] = m;
+                    cnt += __popc(m);
+                }
+            }
+            if (lane == 0) par[b] = cnt >= min_samples ? b : -1;       // core points start as their own label
+        }
+    }
+    __syncthreads();
+    for (int w = warp; w < W; w += nw) {
+        const int b = (w << 5) + lane;
+        const unsigned m = __ballot_sync(kFullMask, b < B && par[b] >= 0);
+        if (lane == 0) cm[w] = m;
+    }
+    __syncthreads();
+    stamp(13);
+    int anycore = 0;
+    for (int w = tid; w < W; w += nt) anycore |= cm[w] != 0u;
+    if (!__syncthreads_or(anycore)) {
+        for (int b = tid; b < B; b += nt) cl[b] = -1;
+        __syncthreads();
+        return 0;
+    }
+    // 2. components of the core-core graph.  First hop straight from the bit rows (lowest core neighbour; final
+    //    already when the component is a clique, the usual person-sized blob), then min-label propagation +
+    //    pointer jumping until nothing changes.
+    for (int b = warp; b < B; b += nw) {
+        if (par[b] < 0) continue;                                        // uniform over the warp; par[b] is only
+        int m = 0x7fffffff;                                              // written by this warp in this loop
+        for (int w = lane; w < W; w += 32) {
+            const unsigned bits = adj[b * W + w] & cm[w];
+            if (bits) m = min(m, (w << 5) + __ffs(bits) - 1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
+        if (lane == 0) par[b] = m;                                       // m <= b: b is its own neighbour
+    }
+    __syncthreads();
+    while (true) {
+        for (int b = tid; b < B; b += nt) {                              // pointer jumping (parents only decrease)
+            int l = ((volatile int*)par)[b];
+            if (l < 0) continue;
+            while (true) {
+                const int p = ((volatile int*)par)[l];
+                if (p == l) break;
+                l = p;
+            }
+            if (l < ((volatile int*)par)[b]) atomicMin(&par[b], l);
+        }
+        __syncthreads();
+        int changed = 0;
+        for (int b = warp; b < B; b += nw) {
+            const int cur = ((volatile int*)par)[b];
+            if (cur < 0) continue;                                       // uniform over the warp
+            int m = cur;
+            for (int w0 = 0; w0 < W; w0 += 4) {
+                unsigned bits[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) bits[u] = w0 + u < W ? (adj[b * W + w0 + u] & cm[w0 + u]) : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if ((bits[u] >> lane) & 1u) m = min(m, ((volatile int*)par)[((w0 + u) << 5) + lane]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
+            if (m < cur) {
+                if (lane == 0) atomicMin(&par[b], m);
+                changed = 1;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    stamp(14);
+    // 3. cluster ids: rank of the root among the roots, ascending index
+    for (int w = warp; w < W; w += nw) {
+        const int b = (w << 5) + lane;
+        const unsigned m = __ballot_sync(kFullMask, b < B && par[b] == b);
+        if (lane == 0) rm[w] = m;
+    }
+    __syncthreads();
+    int ncl = 0;
+    for (int w = 0; w < W; ++w) ncl += __popc(rm[w]);
+    for (int b = tid; b < B; b += nt) {
+        const int r = par[b];
+        int id = -1;
+        if (r >= 0) {
+            id = __popc(rm[r >> 5] & ((1u << (r & 31)) - 1u));
+            for (int w = 0; w < (r >> 5); ++w) id += __popc(rm[w]);
+        }
+        cl[b] = id;
+    }
+    __syncthreads();
+    stamp(15);
+    // 4. border points: lowest-numbered cluster with a core point within eps (only labels of core points are read)
+    for (int b = warp; b < B; b += nw) {
+        if (par[b] >= 0) continue;                                       // uniform over the warp
+        int m = 0x7fffffff;
+        for (int w0 = 0; w0 < W; w0 += 4) {
+            unsigned bits[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) bits[u] = w0 + u < W ? (adj[b * W + w0 + u] & cm[w0 + u]) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((bits[u] >> lane) & 1u) m = min(m, cl[((w0 + u) << 5) + lane]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
+        if (lane == 0 && m != 0x7fffffff) cl[b] = m;
+    }
+    __syncthreads();
+    stamp(16);
     return ncl;
 }
 

@@ -2,6 +2,7 @@
 // stage-level entry points.  No torch types, no exceptions across the boundary, no CPU fallback.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -47,7 +48,8 @@ struct mmw_ctx {
     unsigned long long* d_counters = nullptr;
     unsigned long long* d_phase = nullptr;
     bool phase_clocks = false;
-    int32_t* d_defer = nullptr;      // [1 + S]: counter, then the work list of dbscan_big_kernel
+    int32_t* d_defer = nullptr;      // [1 + S + S]: counter, the work list of dbscan_big_kernel, pose rows per scene
+    bool fold_pose_index = true;     // pose-row scan inside pose_feature_kernel (S <= 4096) instead of pose_index_kernel
     // input staging (host-input path): double-buffered, copied on a side stream so that the upload of frame k+1
     // overlaps the kernels of frame k
     float* d_pts2[2] = {nullptr, nullptr};
@@ -57,6 +59,8 @@ struct mmw_ctx {
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
     cudaEvent_t packed[2] = {nullptr, nullptr}, results_done[2] = {nullptr, nullptr};
     float* d_results[2] = {nullptr, nullptr};
+    double* d_export = nullptr;      // [S][192*5 + 2] rows + centroid of mmw_export_track0 (allocated on first use)
+    int32_t* d_export_valid = nullptr;
     unsigned stage_idx = 0, result_idx = 0;
     std::vector<int32_t> h_offsets;
     // pose
@@ -159,7 +163,7 @@ int mmw_destroy(mmw_ctx* x) {
     if (!x) return MMW_OK;
     cudaSetDevice(x->device);
     if (x->stream) cudaStreamSynchronize(x->stream);
-    void* ptrs[] = {x->d_tracks, x->d_scenes, x->d_track_ring, x->d_uring, x->d_keypoints, x->d_default_posture,
+    void* ptrs[] = {x->d_export, x->d_export_valid, x->d_tracks, x->d_scenes, x->d_track_ring, x->d_uring, x->d_keypoints, x->d_default_posture,
                     x->d_assoc, x->d_labels, x->d_counters, x->d_phase, x->d_defer, x->d_pts2[0], x->d_pts2[1], x->d_offsets2[0],
                     x->d_offsets2[1], x->d_dt2[0], x->d_dt2[1], x->d_results[0], x->d_results[1], x->d_blob, x->d_bn1s,
                     x->d_bn1t, x->d_bn2s, x->d_bn2t, x->d_feats, x->d_row_scene, x->d_row_track, x->d_row_slot,
@@ -185,6 +189,7 @@ int mmw_reset(mmw_ctx* x) {
     CK(cudaMemsetAsync(x->d_counters, 0, sizeof(unsigned long long) * 8, x->stream));
     CK(cudaMemsetAsync(x->d_assoc, 0xff, sizeof(int32_t) * (size_t)x->S * x->ncap, x->stream));
     CK(cudaMemsetAsync(x->d_pose_total, 0, sizeof(int), x->stream));
+    CK(cudaMemsetAsync(x->d_defer, 0, sizeof(int32_t) * (1 + 2 * (size_t)x->S), x->stream));
     return MMW_OK;
 }
 
@@ -232,8 +237,12 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     ALLOC(x->d_assoc, sizeof(int32_t) * S * max_points);
     ALLOC(x->d_labels, sizeof(int32_t) * S * 3 * max_points);
     ALLOC(x->d_counters, sizeof(unsigned long long) * 8);
-    ALLOC(x->d_phase, sizeof(unsigned long long) * (16 + 3 * S));
-    ALLOC(x->d_defer, sizeof(int32_t) * (1 + S));
+    ALLOC(x->d_phase, sizeof(unsigned long long) * (16 + 3 * S + 16));
+    ALLOC(x->d_defer, sizeof(int32_t) * (1 + 2 * S));
+    {
+        const char* env = getenv("MMW_POSE_INDEX_FOLD");
+        x->fold_pose_index = S <= 4096 && !(env && env[0] == '0');
+    }
     for (int i = 0; i < 2; ++i) {
         ALLOC(x->d_pts2[i], sizeof(float) * kRawCols * S * max_points);
         ALLOC(x->d_offsets2[i], sizeof(int32_t) * (S + 1));
@@ -416,6 +425,7 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     a.phase_cycles = x->phase_clocks ? x->d_phase : nullptr;
     a.defer_count = x->d_defer;
     a.defer_list = x->d_defer + 1;
+    a.pose_cnt = x->d_defer + 1 + x->S;
     prof_mark(x, MMW_K_STEP);
     CK(launch_step(a, x->stream));
     prof_mark(x, MMW_K_DBSCAN_BIG);
@@ -431,25 +441,33 @@ int mmw_estimate_posture(mmw_ctx* x) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     if (!x->has_weights) return fail(MMW_ERR_STATE, "estimate_posture needs mmw_load_pose_weights first");
     CK(cudaSetDevice(x->device));
-    prof_mark(x, MMW_K_POSE_INDEX);
-    CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
+    if (!x->fold_pose_index) {
+        prof_mark(x, MMW_K_POSE_INDEX);
+        CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
+        x->launches++;
+    }
     PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats,
                     (x->use_tc && x->tc.ready) ? pose_tc_input(&x->tc) : nullptr, x->d_row_scene, x->d_row_track,
-                    x->d_row_slot};
+                    x->d_row_slot, x->fold_pose_index ? x->d_defer + 1 + x->S : nullptr, x->d_pose_total, x->d_counters,
+                    x->S};
     prof_mark(x, MMW_K_POSE_FEATURES);
     CK(launch_pose_features(fa, x->S, x->stream));
-    x->launches += 2;
+    x->launches++;
     return run_pose_net(x, x->d_keypoints, x->pose_cap);
 }
 
 int mmw_pose_features_only(mmw_ctx* x) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(x->device));
-    CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
+    if (!x->fold_pose_index) {
+        CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
+        x->launches++;
+    }
     PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, nullptr, x->d_row_scene,
-                    x->d_row_track, x->d_row_slot};
+                    x->d_row_track, x->d_row_slot, x->fold_pose_index ? x->d_defer + 1 + x->S : nullptr, x->d_pose_total,
+                    x->d_counters, x->S};
     CK(launch_pose_features(fa, x->S, x->stream));
-    x->launches += 2;
+    x->launches++;
     return MMW_OK;
 }
 
@@ -732,6 +750,46 @@ __device__ __forceinline__ void projection_point(const FadeCfg& f, double xo, do
     zp = (zd == 0.0) ? zo : (-f.m_y / (yd / zd)) + f.m_z;
 }
 
+// Dataset-builder export of track 0 (preprocessing.py:185-216; Utils.relative_coordinates :437-465 and
+// format_batched_frames :523-548): ring frames newest first, [x - cx, y - cy, z, doppler, peakVal] of the first 64
+// rows per frame in float64, zero padded, unsorted, raw intensity.  One CTA of 64 threads per scene.
+constexpr int kExportRows = kRing * kFeatPts;               // the reference always writes three frames (Utils.py:526)
+__global__ void __launch_bounds__(kFeatPts) export_track0_kernel(DevConfig c, const SceneRec* scenes,
+                                                                 const TrackRec* tracks, const float* track_ring,
+                                                                 double* out, int32_t* valid) {
+    const int s = blockIdx.x, i = threadIdx.x;
+    const SceneRec sc = scenes[s];
+    const TrackRec* t = tracks + (size_t)s * c.tcap;
+    double* o = out + (size_t)s * (kExportRows * kRawCols + 2);
+    bool ok = sc.last_ran && sc.n_tracks > 0 && t->lifetime == 0.0;
+    int total = 0;
+    if (ok)
+        for (int f = 0; f < t->ring_n; ++f) total += t->ring_cnt[(t->ring_head + f) % c.ring_size];
+    ok = ok && total > 0;
+    if (i == 0) valid[s] = ok ? 1 : 0;
+    if (!ok) return;
+    const double cx = t->centroid[0], cy = t->centroid[1];
+    if (i == 0) { o[kExportRows * kRawCols] = cx; o[kExportRows * kRawCols + 1] = cy; }
+    for (int k = 0; k < kRing; ++k) {
+        double v[kRawCols] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (k < t->ring_n) {
+            const int phys = (t->ring_head + t->ring_n - 1 - k) % c.ring_size;          // newest frame first
+            if (i < t->ring_cnt[phys]) {
+                const float* r = track_ring + ((((size_t)s * c.tcap + t->slot) * kRing + phys) * kFeatPts + i) * kRawCols;
+                double yw, zw;
+                world_yz(c, (double)r[1], (double)r[2], yw, zw);
+                v[0] = __dsub_rn((double)r[0], cx);
+                v[1] = __dsub_rn(yw, cy);
+                v[2] = zw;
+                v[3] = (double)r[3];
+                v[4] = (double)r[4];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kRawCols; ++q) o[(k * kFeatPts + i) * kRawCols + q] = v[q];
+    }
+}
+
 __global__ void pack_results_kernel(const SceneRec* scenes, const TrackRec* tracks, const float* keypoints, int S,
                                     int tcap, float* out, FadeCfg fade) {
     const int idx = blockIdx.x;            // scene * tcap + k
@@ -765,6 +823,34 @@ __global__ void pack_results_kernel(const SceneRec* scenes, const TrackRec* trac
 }  // namespace mmw
 
 extern "C" {
+
+int mmw_export_track0(mmw_ctx* x, double* rows, int32_t* valid, double* centroid) {
+    if (!x || !rows || !valid) return fail(MMW_ERR_INVALID, "ctx/rows/valid is NULL");
+    CK(cudaSetDevice(x->device));
+    const size_t per = (size_t)kExportRows * kRawCols + 2;
+    if (!x->d_export) {
+        CK(cudaMalloc((void**)&x->d_export, sizeof(double) * per * x->S));
+        CK(cudaMalloc((void**)&x->d_export_valid, sizeof(int32_t) * x->S));
+    }
+    export_track0_kernel<<<x->S, kFeatPts, 0, x->stream>>>(x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_export,
+                                                         x->d_export_valid);
+    CK(cudaGetLastError());
+    x->launches++;
+    std::vector<double> h(per * x->S);
+    CK(cudaMemcpyAsync(valid, x->d_export_valid, sizeof(int32_t) * x->S, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemcpyAsync(h.data(), x->d_export, sizeof(double) * per * x->S, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    for (int s = 0; s < x->S; ++s) {                               // blocks of invalid scenes are undefined on the device
+        double* r = rows + (size_t)s * kExportRows * kRawCols;
+        if (valid[s]) std::memcpy(r, h.data() + per * s, sizeof(double) * kExportRows * kRawCols);
+        else std::memset(r, 0, sizeof(double) * kExportRows * kRawCols);
+        if (centroid) {
+            centroid[2 * s] = valid[s] ? h[per * s + kExportRows * kRawCols] : 0.0;
+            centroid[2 * s + 1] = valid[s] ? h[per * s + kExportRows * kRawCols + 1] : 0.0;
+        }
+    }
+    return MMW_OK;
+}
 
 int mmw_pack_results(mmw_ctx* x, float* device_out) {
     if (!x || !device_out) return fail(MMW_ERR_INVALID, "ctx/device_out is NULL");
@@ -991,6 +1077,17 @@ int mmw_scene_cycles(mmw_ctx* x, uint64_t* out /*[S]*/) {
     CK(cudaSetDevice(x->device));
     CK(cudaStreamSynchronize(x->stream));
     CK(cudaMemcpy(out, x->d_phase + 16, sizeof(unsigned long long) * 3 * x->S, cudaMemcpyDeviceToHost));
+    return MMW_OK;
+}
+
+int mmw_dbscan_big_clocks(mmw_ctx* x, uint64_t* out8) {
+    if (!x || !out8) return fail(MMW_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    unsigned long long h[8];
+    CK(cudaMemcpy(h, x->d_phase + 16 + 3 * x->S, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) out8[i] = h[i];
+    CK(cudaMemset(x->d_phase + 16 + 3 * x->S, 0, sizeof(h)));
     return MMW_OK;
 }
 

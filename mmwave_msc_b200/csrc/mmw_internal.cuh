@@ -83,6 +83,7 @@ struct StepArgs {
     unsigned long long* phase_cycles;  // [16 + S] or nullptr: cycles per phase of step_kernel, then cycles per scene (debug)
     int32_t* defer_list;       // [S] scenes whose DBSCAN + spawn is left to dbscan_big_kernel, or nullptr
     int32_t* defer_count;      // device counter of defer_list (zeroed before every step)
+    int32_t* pose_cnt;         // [S] tracks of the scene if the frame ran track(), else 0: the pose-row scan reads this
     int n_scenes;
     uint32_t flags;
 };

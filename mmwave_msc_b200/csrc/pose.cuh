@@ -16,6 +16,12 @@ struct PoseFeatArgs {
     int32_t* row_scene;    // [rows]
     int32_t* row_track;
     int32_t* row_slot;
+    // Pose-row scan folded into this kernel (pose_cnt != nullptr): CTA s sums pose_cnt[0..s) itself and the CTA of
+    // the last scene publishes the row total, so no separate scan kernel sits between the tracker and the features.
+    const int32_t* pose_cnt;   // [S] or nullptr (then SceneRec::pose_base from pose_index_kernel is used)
+    int* pose_total;
+    unsigned long long* counters;
+    int n_scenes;
 };
 
 struct ConvArgs {

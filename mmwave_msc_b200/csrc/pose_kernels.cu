@@ -58,12 +58,32 @@ __global__ void __launch_bounds__(128) pose_feature_kernel(PoseFeatArgs a) {
     const int s = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const SceneRec sc = a.scenes[s];
+    int pose_base = sc.pose_base;
+    if (a.pose_cnt != nullptr) {
+        // exclusive scan value of this scene: every CTA adds up the (at most S) counts in front of it; the order of
+        // the integer additions does not matter, so the row layout is the same as pose_index_kernel's
+        __shared__ int wpart[4];
+        int part = 0;
+        for (int i = threadIdx.x; i < s; i += 128) part += __ldg(a.pose_cnt + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) wpart[warp] = part;
+        __syncthreads();
+        pose_base = wpart[0] + wpart[1] + wpart[2] + wpart[3];
+        if (threadIdx.x == 0) {
+            if (s == a.n_scenes - 1) {
+                const int total = pose_base + (sc.last_ran ? sc.n_tracks : 0);
+                *a.pose_total = total;
+                atomicAdd(&a.counters[7], (unsigned long long)total);
+            }
+        }
+    }
     if (!sc.last_ran) return;
     const DevConfig& c = a.cfg;
     const int nfr = c.ring_size;
     for (int k = warp; k < sc.n_tracks; k += 4) {
         const TrackRec* t = a.tracks + (size_t)s * c.tcap + k;
-        const int row = sc.pose_base + k;
+        const int row = pose_base + k;
         const double cx = t->centroid[0], cy = t->centroid[1];
         const int slot = t->slot, rn = t->ring_n, rh = t->ring_head;
         if (lane == 0) {
@@ -357,6 +377,13 @@ cudaError_t launch_pose_index(SceneRec* scenes, int S, int* pose_total, unsigned
 }
 
 cudaError_t launch_pose_features(const PoseFeatArgs& a, int S, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {          // same shared-memory carve-out as its neighbours in the step (no SM reconfiguration)
+        cudaError_t e = cudaFuncSetAttribute(pose_feature_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
     pose_feature_kernel<<<S, 128, 0, st>>>(a);
     return cudaGetLastError();
 }

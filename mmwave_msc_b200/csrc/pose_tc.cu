@@ -19,6 +19,7 @@
 // Warp roles in both kernels: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -407,12 +408,13 @@ struct GemmTcArgs {
     float* keypoints;                    // MODE 1: scatter target or nullptr
     const int32_t *row_scene, *row_slot;
     int K, N, tcap;
+    int dbg;                             // timing experiments only (MMW_GEMM_DBG): 1 = no TMA loads, 2 = no MMAs
 };
 
 constexpr int kGemmThreads = 192;
 constexpr int kBK = 64;
 template <int BN, int STAGES>
-constexpr int gemm_smem_bytes() { return STAGES * (2 * 128 * kBK * 2 + 2 * BN * kBK * 2) + 1024 + 256; }
+constexpr int gemm_smem_bytes() { return STAGES * (2 * 128 * kBK * 2 + 2 * BN * kBK * 2) + 1024 + 256 + 3 * BN * 4; }
 
 // MODE 0: out = split(BN(relu(acc + bias)))      MODE 1: out = acc + bias (first 57 columns), scattered to tracks
 template <int BN, int STAGES, int MODE>
@@ -425,7 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr uint32_t TCOLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // power of two
     const int rows = *a.n_rows;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * BM, n0 = MODE == 1 ? 0 : blockIdx.x * BN;
     if (m0 >= rows) return;
 
     extern __shared__ unsigned char smem_raw[];
@@ -459,11 +461,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 unsigned char* st = smem + s * STAGE_BYTES;
+                if (a.dbg & 1) { mbar_arrive(&full[s]); continue; }
                 mbar_expect_tx(&full[s], STAGE_BYTES);
-                tma_load_2d(st, &map_ah, &full[s], kb * kBK, m0);
-                tma_load_2d(st + A_BYTES, &map_al, &full[s], kb * kBK, m0);
-                tma_load_2d(st + 2 * A_BYTES, &map_wh, &full[s], kb * kBK, n0);
-                tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_wl, &full[s], kb * kBK, n0);
+                const int k0 = kb * kBK;
+                tma_load_2d(st, &map_ah, &full[s], k0, m0);
+                tma_load_2d(st + A_BYTES, &map_al, &full[s], k0, m0);
+                tma_load_2d(st + 2 * A_BYTES, &map_wh, &full[s], k0, n0);
+                tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_wl, &full[s], k0, n0);
             }
         }
     } else if (warp == 1) {
@@ -479,6 +483,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                 const uint64_t dwh = make_desc<128>(st + 2 * A_BYTES), dwl = make_desc<128>(st + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < kBK / UK; ++kk) {
+                    if (a.dbg & 2) break;
                     const uint64_t adv = (uint64_t)((kk * UK * 2) >> 4);
                     umma_bf16(tmem_d, dah + adv, dwh + adv, idesc, (kb | kk) != 0);
                     umma_bf16(tmem_d, dah + adv, dwl + adv, idesc, 1);
@@ -490,6 +495,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         }
     } else {
         const int q = warp & 3;
+        // bias / BatchNorm constants of this column tile into shared memory while the main loop runs
+        float* sconst = reinterpret_cast<float*>(tmem_slot + 2);
+        if (MODE == 0) {
+            for (int i = threadIdx.x - 64; i < BN; i += 128) {
+                sconst[i] = __ldg(a.bias + n0 + i);
+                sconst[BN + i] = __ldg(a.bn_scale + n0 + i);
+                sconst[2 * BN + i] = __ldg(a.bn_shift + n0 + i);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const int row = m0 + q * 32 + lane;
@@ -502,9 +517,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                 __align__(16) __nv_bfloat16 hi[32], lo[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c0 + j;
-                    float x = fmaxf(__uint_as_float(v[j]) + __ldg(a.bias + n), 0.f);
-                    x = fmaf(x, __ldg(a.bn_scale + n), __ldg(a.bn_shift + n));
+                    float x = fmaxf(__uint_as_float(v[j]) + sconst[c0 + j], 0.f);
+                    x = fmaf(x, sconst[BN + c0 + j], sconst[2 * BN + c0 + j]);
                     split2(x, hi[j], lo[j]);
                 }
                 uint4* oh = reinterpret_cast<uint4*>(a.out_hi + (size_t)row * a.N + n0 + c0);
@@ -515,15 +529,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                     ol[i] = reinterpret_cast<const uint4*>(lo)[i];
                 }
             } else {
-                const int s = a.keypoints ? a.row_scene[row] : 0, slot = a.keypoints ? a.row_slot[row] : 0;
+                // dense 2: the 57 outputs of a row go through shared memory (the pipeline stages are idle now) so that
+                // the global writes below are coalesced; lane-per-row scalar stores cost 32 sectors per instruction
+                float* stg = reinterpret_cast<float*>(smem);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c0 + j;
-                    if (n < kKp) {
-                        const float x = __uint_as_float(v[j]) + __ldg(a.bias + n);
-                        a.out[(size_t)row * kKp + n] = x;
-                        if (a.keypoints) a.keypoints[((size_t)s * a.tcap + slot) * kKp + n] = x;
-                    }
+                    const int n = c0 + j;
+                    if (n < kKp) stg[(q * 32 + lane) * kKp + n] = __uint_as_float(v[j]) + __ldg(a.bias + n);
+                }
+            }
+        }
+        if (MODE == 1) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");                     // the four epilogue warps
+            const float* stg = reinterpret_cast<const float*>(smem);
+            const int nrow = min(BM, rows - m0), et = threadIdx.x - 64;
+            float* o = a.out + (size_t)m0 * kKp;                               // rows m0.. are contiguous in out
+            for (int i = et; i < nrow * kKp; i += 128) o[i] = stg[i];
+            if (a.keypoints) {
+                for (int r = q; r < nrow; r += 4) {
+                    float* kp = a.keypoints + ((size_t)a.row_scene[m0 + r] * a.tcap + a.row_slot[m0 + r]) * kKp;
+                    for (int n = lane; n < kKp; n += 32) kp[n] = stg[r * kKp + n];
                 }
             }
         }
@@ -536,12 +561,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     }
 }
 
-// ---- dense 1 with 2-CTA clusters and TMA multicast ---------------------------------------------------------
-// The plain kernel above is L2-bandwidth bound: 120 CTAs x 96 K blocks x 80 KB = 0.92 GB through L2 per call.  Two
-// CTAs that own vertically adjacent 128-row tiles need the SAME W tile, so they form a cluster (1,2,1): each loads
-// half of the W rows and multicasts them into both CTAs' shared memory (A stays private).  Per CTA and K block
-// that is 32 KB (A) + 24 KB (W) instead of 80 KB.  A stage may be refilled only when BOTH CTAs' MMAs have read it,
-// so tcgen05.commit arrives on the empty barrier of both CTAs (count 2).
+// ---- dense 1 on CTA pairs: tcgen05.mma.cta_group::2 ----------------------------------------------------------
+// The single-CTA kernel above keeps only two 80 KB stages in flight, so every K block pays the HBM/L2 round trip
+// (per K block: (latency + 80 KB transfer + 1152 MMA cycles) / 2 stages ~ 1950 cycles against 1152 of tensor work).
+// A CTA pair (two SMs of one TPC, cluster (2,1,1)) runs ONE 256 x BN MMA per K step: each CTA stages its own 128
+// rows of A and only HALF of the W tile (BN/2 rows), the tensor cores exchange the halves.  A stage shrinks to
+// 32 KB (A) + 24 KB (W) = 56 KB, so four stages fit and the loads run ~3 K blocks ahead of the tensor core.
+//   * both CTAs issue their own TMA loads, all of which complete on the LEADER's full barrier (cta_group::2 form of
+//     cp.async.bulk.tensor, barrier address mapped into the leader with mapa)
+//   * the leader's elected thread issues every MMA; tcgen05.commit multicasts the "stage free" / "accumulator
+//     ready" arrivals to the barriers of both CTAs
+//   * each CTA's epilogue warps read the CTA's own TMEM (its 128 rows x BN columns)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -551,33 +581,75 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                               uint16_t mask) {
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// dst in this CTA's shared memory, completion bytes on `bar_cluster` (a shared::cluster address, the leader's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
-        "%4}], [%2], %5;" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
                      "r"(smem_u32(bar)), "h"(mask)
                  : "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(COLS) : "memory");
+}
+// kind::f16 instruction descriptor of the pair MMA: M = 256 (128 rows per CTA)
+__device__ __forceinline__ constexpr uint32_t make_idesc_pair(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+constexpr int gemm_pair_smem_bytes() {
+    return STAGES * (2 * 128 * kBK * 2 + 2 * (BN / 2) * kBK * 2) + 1024 + 256 + 3 * BN * 4;
 }
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
-                       const __grid_constant__ CUtensorMap map_wh_half, const __grid_constant__ CUtensorMap map_wl_half,
-                       const GemmTcArgs a) {
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                    const __grid_constant__ CUtensorMap map_wh_half, const __grid_constant__ CUtensorMap map_wl_half,
+                    const GemmTcArgs a) {
     constexpr int BM = 128, UK = 16;
-    constexpr int A_BYTES = BM * kBK * 2, B_BYTES = BN * kBK * 2, BH_BYTES = B_BYTES / 2;
-    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr int A_BYTES = BM * kBK * 2, BH_BYTES = (BN / 2) * kBK * 2;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;              // per CTA
     constexpr uint32_t TCOLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    __shared__ unsigned long long ts[8];                       // MMW_GEMM_DBG=4: %globaltimer at the phase boundaries
+    auto mark = [&](int i) {
+        if (a.dbg & 4) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ts[i] = t; }
+    };
+    if (threadIdx.x == 0) mark(0);
     const int rows = *a.n_rows;
-    if ((int)(blockIdx.y & ~1u) * BM >= rows) return;          // the whole cluster is past the last row
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const uint32_t rank = cluster_ctarank();
+    // grid = (M tiles rounded up to even, N tiles), cluster (2,1,1): a kernel that uses cta_group::2 must pair its CTAs
+    // along x (the driver rejects any other cluster shape as "cluster misconfiguration")
+    if ((int)(blockIdx.x & ~1u) * BM >= rows) return;          // the whole pair is past the last row
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const uint32_t rank = cluster_ctarank();                   // 0 = leader (issues the MMAs, owns the full barriers)
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -593,36 +665,41 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh_half) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl_half) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+    if (warp == 1) tmem_alloc_pair<TCOLS>(tmem_slot);          // the same warp of both CTAs, collectively
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                                          // both CTAs' barriers exist before any remote arrive
+    cluster_sync_all();                                        // both CTAs' barriers exist before any remote arrive
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    if (threadIdx.x == 0) mark(1);
 
     if (warp == 0) {
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
+                mbar_wait(&empty[s], ph ^ 1);                  // own copy: the commit below arrives in both CTAs
                 unsigned char* st = smem + s * STAGE_BYTES;
-                mbar_expect_tx(&full[s], STAGE_BYTES);           // own A + both halves of W (one arrives from the peer)
-                tma_load_2d(st, &map_ah, &full[s], kb * kBK, m0);
-                tma_load_2d(st + A_BYTES, &map_al, &full[s], kb * kBK, m0);
-                tma_load_2d_mc(st + 2 * A_BYTES + rank * BH_BYTES, &map_wh_half, &full[s], kb * kBK,
-                               n0 + (int)rank * (BN / 2), (uint16_t)3);
-                tma_load_2d_mc(st + 2 * A_BYTES + B_BYTES + rank * BH_BYTES, &map_wl_half, &full[s], kb * kBK,
-                               n0 + (int)rank * (BN / 2), (uint16_t)3);
+                const uint32_t bar = mapa_shared(smem_u32(&full[s]), 0);
+                if (a.dbg & 1) {
+                    if (rank == 0) mbar_arrive(&full[s]);
+                    continue;
+                }
+                if (rank == 0) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);       // the bytes of both CTAs
+                tma_load_2d_pair(st, &map_ah, bar, kb * kBK, m0);
+                tma_load_2d_pair(st + A_BYTES, &map_al, bar, kb * kBK, m0);
+                tma_load_2d_pair(st + 2 * A_BYTES, &map_wh_half, bar, kb * kBK, n0 + (int)rank * (BN / 2));
+                tma_load_2d_pair(st + 2 * A_BYTES + BH_BYTES, &map_wl_half, bar, kb * kBK, n0 + (int)rank * (BN / 2));
             }
+            mark(2);
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(BN);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_pair(BN);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
@@ -630,22 +707,33 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
                 tc_fence_after();
                 const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
                 const uint64_t dah = make_desc<128>(st), dal = make_desc<128>(st + A_BYTES);
-                const uint64_t dwh = make_desc<128>(st + 2 * A_BYTES), dwl = make_desc<128>(st + 2 * A_BYTES + B_BYTES);
+                const uint64_t dwh = make_desc<128>(st + 2 * A_BYTES), dwl = make_desc<128>(st + 2 * A_BYTES + BH_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < kBK / UK; ++kk) {
+                    if (a.dbg & 2) break;
                     const uint64_t adv = (uint64_t)((kk * UK * 2) >> 4);
-                    umma_bf16(tmem_d, dah + adv, dwh + adv, idesc, (kb | kk) != 0);
-                    umma_bf16(tmem_d, dah + adv, dwl + adv, idesc, 1);
-                    umma_bf16(tmem_d, dal + adv, dwh + adv, idesc, 1);
+                    umma_bf16_pair(tmem_d, dah + adv, dwh + adv, idesc, (kb | kk) != 0);
+                    umma_bf16_pair(tmem_d, dah + adv, dwl + adv, idesc, 1);
+                    umma_bf16_pair(tmem_d, dal + adv, dwh + adv, idesc, 1);
                 }
-                umma_commit_mc(&empty[s], (uint16_t)3);          // frees the stage in BOTH CTAs' view
+                umma_commit_pair(&empty[s], (uint16_t)3);      // frees the stage in BOTH CTAs
             }
-            umma_commit(tmem_full);
+            umma_commit_pair(tmem_full, (uint16_t)3);          // both epilogues may read their accumulators
+            mark(3);
         }
     } else {
         const int q = warp & 3;
+        // bias / BatchNorm constants of this column tile into shared memory while the main loop runs
+        float* sconst = reinterpret_cast<float*>(tmem_slot + 2);
+        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+            sconst[i] = __ldg(a.bias + n0 + i);
+            sconst[BN + i] = __ldg(a.bn_scale + n0 + i);
+            sconst[2 * BN + i] = __ldg(a.bn_shift + n0 + i);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) mark(4);
         const int row = m0 + q * 32 + lane;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -655,9 +743,8 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             __align__(16) __nv_bfloat16 hi[32], lo[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const int n = n0 + c0 + j;
-                float x = fmaxf(__uint_as_float(v[j]) + __ldg(a.bias + n), 0.f);
-                x = fmaf(x, __ldg(a.bn_scale + n), __ldg(a.bn_shift + n));
+                float x = fmaxf(__uint_as_float(v[j]) + sconst[c0 + j], 0.f);
+                x = fmaf(x, sconst[BN + c0 + j], sconst[2 * BN + c0 + j]);
                 split2(x, hi[j], lo[j]);
             }
             uint4* oh = reinterpret_cast<uint4*>(a.out_hi + (size_t)row * a.N + n0 + c0);
@@ -669,12 +756,21 @@ gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_
             }
         }
     }
+    if (threadIdx.x == 64) mark(5);
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                                          // the peer may still arrive on / write to this CTA
+    if (threadIdx.x == 0) mark(6);
+    cluster_sync_all();                                        // the peer may still arrive on / read from this CTA
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<TCOLS>(tmem_d);
+        tmem_dealloc_pair<TCOLS>(tmem_d);
+    }
+    if ((a.dbg & 4) && threadIdx.x == 0 && (blockIdx.x < 2 || blockIdx.x == 15) && (blockIdx.y == 0 || blockIdx.y == 7)) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        printf("[pair %d,%d] t0 %llu | prologue %llu | tma issued %llu | mma issued %llu | acc ready %llu | epilogue %llu | "
+               "sync %llu | end %llu (ns since t0)\n", (int)blockIdx.x, (int)blockIdx.y, ts[0], ts[1] - ts[0],
+               ts[2] - ts[0], ts[3] - ts[0], ts[4] - ts[0], ts[5] - ts[0], ts[6] - ts[0], t - ts[0]);
     }
 }
 
@@ -706,7 +802,8 @@ struct TcImpl {
     __nv_bfloat16 *w1b = nullptr, *w2b = nullptr;                     // conv B matrices [taps][NOUT][CK]
     __nv_bfloat16 *wd1_hi = nullptr, *wd1_lo = nullptr, *wd2_hi = nullptr, *wd2_lo = nullptr;
     CUtensorMap m_in, m_act1, m_w1b, m_w2b, m_ah, m_al, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l, m_w1h_half, m_w1l_half;
-    bool cluster = false;
+    int dbg = 0;
+    int pair = 0;                                                     // dense 1 on CTA pairs (cta_group::2): stages, 0 = off
 };
 
 static std::string g_tc_err;
@@ -831,6 +928,7 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
     bool ok = dev_alloc(&im->in_p, R * P * 16 * 2, true) && dev_alloc(&im->act1_p, R * P * 32 * 2, true) &&
               dev_alloc(&im->a_hi, R * im->Kf * 2, true) && dev_alloc(&im->a_lo, R * im->Kf * 2, true) &&
               dev_alloc(&im->h_hi, R * im->H * 2, true) && dev_alloc(&im->h_lo, R * im->H * 2, true);
+    { const char* env = getenv("MMW_GEMM_DBG"); im->dbg = env ? atoi(env) : 0; }
     if (!ok) { g_tc_err = "cudaMalloc failed (activations)"; return -1; }
     std::vector<uint16_t> hi, lo;
     ok = upload(&im->w1b, conv_b(blob + off[0], im->taps, 5, 8, 16)) &&
@@ -845,38 +943,70 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
         make_map_2d(&im->m_ah, im->a_hi, R, im->Kf, 128, 64) || make_map_2d(&im->m_al, im->a_lo, R, im->Kf, 128, 64) ||
         make_map_2d(&im->m_w1h, im->wd1_hi, im->H, im->Kf, im->H % 192 == 0 ? 192 : 256, 64) ||
         make_map_2d(&im->m_w1l, im->wd1_lo, im->H, im->Kf, im->H % 192 == 0 ? 192 : 256, 64) ||
-        (im->H % 192 == 0 && (make_map_2d(&im->m_w1h_half, im->wd1_hi, im->H, im->Kf, 96, 64) ||
-                              make_map_2d(&im->m_w1l_half, im->wd1_lo, im->H, im->Kf, 96, 64))) ||
+        make_map_2d(&im->m_w1h_half, im->wd1_hi, im->H, im->Kf, im->H % 192 == 0 ? 96 : 128, 64) ||
+        make_map_2d(&im->m_w1l_half, im->wd1_lo, im->H, im->Kf, im->H % 192 == 0 ? 96 : 128, 64) ||
         make_map_2d(&im->m_hh, im->h_hi, R, im->H, 128, 64) || make_map_2d(&im->m_hl, im->h_lo, R, im->H, 128, 64) ||
         make_map_2d(&im->m_w2h, im->wd2_hi, 64, im->H, 64, 64) || make_map_2d(&im->m_w2l, im->wd2_lo, 64, im->H, 64, 64))
         return -1;
     cudaError_t e = cudaSuccess;
     auto set_smem = [&](const void* fn, int bytes) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        // every kernel of the step asks for the same (maximum) shared-memory carve-out, so the SMs are not
+        // reconfigured at each of the seven kernel boundaries of a step
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     };
     set_smem((const void*)conv_slab_kernel<16, 32, 0, 3>, conv_smem_bytes_tc<16, 32>(27));
     set_smem((const void*)conv_slab_kernel<32, 64, 1, 3>, conv_smem_bytes_tc<32, 64>(27));
     set_smem((const void*)conv_slab_kernel<16, 32, 0, 1>, conv_smem_bytes_tc<16, 32>(9));
     set_smem((const void*)conv_slab_kernel<32, 64, 1, 1>, conv_smem_bytes_tc<32, 64>(9));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gemm_tc_kernel<256, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 gemm_smem_bytes<256, 2>());
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gemm_tc_kernel<192, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 gemm_smem_bytes<192, 2>());
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gemm_tc_cluster_kernel<192, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 gemm_smem_bytes<192, 2>());
+    set_smem((const void*)gemm_tc_kernel<256, 2, 0>, gemm_smem_bytes<256, 2>());
+    set_smem((const void*)gemm_tc_kernel<192, 2, 0>, gemm_smem_bytes<192, 2>());
     {
-        // Measured: no gain (108 vs 110 us).  The kernel is bound by what each SM can ingest from L2 (~64 B/clk: 80 KB
-        // per K block against 1152 MMA cycles), and multicast does not reduce the bytes landing in an SM's shared
-        // memory -- only cta_group::2 (B tile split across the pair) would.  Kept for experiments, off by default.
-        const char* env = getenv("MMW_FC1_CLUSTER");
-        im->cluster = im->H % 192 == 0 && env && env[0] == '1';
+        // Dense 1 on CTA pairs: deepest pipeline the device accepts for a 2-CTA cluster of this kernel (asked of the
+        // driver, not assumed), else the single-CTA kernel.  MMW_FC1_PAIR=0 forces the single-CTA kernel (the
+        // comparison point of the measurement in DESIGN.md), MMW_FC1_PAIR=<n> caps the stage count.
+        const char* env = getenv("MMW_FC1_PAIR");
+        const int cap = env ? atoi(env) : 99;
+        const bool verbose = getenv("MMW_VERBOSE") != nullptr;
+        const bool n192 = im->H % 192 == 0;
+        auto clusters = [&](const void* fn, int bytes) -> int {
+            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess ||
+                cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
+                cudaGetLastError();
+                return -1;
+            }
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(2, 8);
+            cfg.blockDim = dim3(kGemmThreads);
+            cfg.dynamicSmemBytes = bytes;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+            return n;
+        };
+        struct Cand { int stages; const void* fn; int bytes; };
+        // four stages were measured too: no faster than three (the main loop already runs at the tensor-core floor)
+        const Cand c192[] = {{3, (const void*)gemm_tc_pair_kernel<192, 3>, gemm_pair_smem_bytes<192, 3>()},
+                             {2, (const void*)gemm_tc_pair_kernel<192, 2>, gemm_pair_smem_bytes<192, 2>()}};
+        const Cand c256[] = {{3, (const void*)gemm_tc_pair_kernel<256, 3>, gemm_pair_smem_bytes<256, 3>()},
+                             {2, (const void*)gemm_tc_pair_kernel<256, 2>, gemm_pair_smem_bytes<256, 2>()}};
+        im->pair = 0;
+        for (const Cand& c : (n192 ? c192 : c256)) {
+            if (c.stages > cap) continue;
+            const int n = clusters(c.fn, c.bytes);
+            if (verbose)
+                fprintf(stderr, "[mmw] dense 1 pair kernel BN=%d stages=%d smem=%d: %d active clusters\n", n192 ? 192 : 256,
+                        c.stages, c.bytes, n);
+            if (n > 0) { im->pair = c.stages; break; }
+        }
+        if (verbose) fprintf(stderr, "[mmw] dense 1: %s\n", im->pair ? "cta_group::2 pair kernel" : "single-CTA kernel");
     }
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gemm_tc_kernel<64, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 gemm_smem_bytes<64, 4>());
+    set_smem((const void*)gemm_tc_kernel<64, 4, 1>, gemm_smem_bytes<64, 4>());
     if (e != cudaSuccess) { g_tc_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
     t->ready = true;
     return 0;
@@ -923,22 +1053,34 @@ int pose_tc_fc1(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
     GemmTcArgs g{r.n_rows, r.bd1, r.bn2_scale, r.bn2_shift, im->h_hi, im->h_lo, nullptr, nullptr, nullptr, nullptr,
-                 im->Kf, im->H, r.tcap};
+                 im->Kf, im->H, r.tcap, im->dbg};
     // 128 x 192 tiles when they divide N: 1536/192 = 8 column tiles, i.e. 120 CTAs for ~1900 rows instead of 90
     // CTAs of 128 x 256 on 148 SMs (one wave either way, 25 % less work per CTA)
-    if (im->cluster) {
+    if (im->pair) {
+        const bool n192 = im->H % 192 == 0;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(im->H / 192, (((max_rows + 127) / 128) + 1) & ~1);
+        cfg.gridDim = dim3((((max_rows + 127) / 128) + 1) & ~1, im->H / (n192 ? 192 : 256));
         cfg.blockDim = dim3(kGemmThreads);
-        cfg.dynamicSmemBytes = gemm_smem_bytes<192, 2>();
         cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_cluster_kernel<192, 2>, im->m_ah, im->m_al, im->m_w1h_half,
-                                            im->m_w1l_half, g);
-        if (le != cudaSuccess) { g_tc_err = std::string("cudaLaunchKernelEx(dense1 cluster): ") + cudaGetErrorString(le); return -1; }
+        cudaError_t le;
+        if (n192 && im->pair == 3) {
+            cfg.dynamicSmemBytes = gemm_pair_smem_bytes<192, 3>();
+            le = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<192, 3>, im->m_ah, im->m_al, im->m_w1h_half, im->m_w1l_half, g);
+        } else if (n192) {
+            cfg.dynamicSmemBytes = gemm_pair_smem_bytes<192, 2>();
+            le = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<192, 2>, im->m_ah, im->m_al, im->m_w1h_half, im->m_w1l_half, g);
+        } else if (im->pair == 3) {
+            cfg.dynamicSmemBytes = gemm_pair_smem_bytes<256, 3>();
+            le = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<256, 3>, im->m_ah, im->m_al, im->m_w1h_half, im->m_w1l_half, g);
+        } else {
+            cfg.dynamicSmemBytes = gemm_pair_smem_bytes<256, 2>();
+            le = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<256, 2>, im->m_ah, im->m_al, im->m_w1h_half, im->m_w1l_half, g);
+        }
+        if (le != cudaSuccess) { g_tc_err = std::string("cudaLaunchKernelEx(dense1 pair): ") + cudaGetErrorString(le); return -1; }
     } else if (im->H % 192 == 0) {
         dim3 grid(im->H / 192, (max_rows + 127) / 128);
         gemm_tc_kernel<192, 2, 0><<<grid, kGemmThreads, gemm_smem_bytes<192, 2>(), st>>>(im->m_ah, im->m_al, im->m_w1h,
@@ -957,7 +1099,7 @@ int pose_tc_fc2(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
     GemmTcArgs g{r.n_rows, r.bd2, nullptr, nullptr, nullptr, nullptr, r.out, r.keypoints, r.row_scene, r.row_slot,
-                 im->H, 64, r.tcap};
+                 im->H, 64, r.tcap, im->dbg};
     dim3 grid(1, (max_rows + 127) / 128);
     gemm_tc_kernel<64, 4, 1><<<grid, kGemmThreads, gemm_smem_bytes<64, 4>(), st>>>(im->m_hh, im->m_hl, im->m_w2h,
                                                                                   im->m_w2l, g);

@@ -137,7 +137,9 @@ __device__ __forceinline__ const float* uring_frame(const StepArgs& a, int s, in
 // state x = [centroid, 0, 0, 0], P = KF_P_INIT*I, group dispersion = KF_GROUP_DISP_EST_INIT*I, ring = [first 64
 // cluster rows in fused order], keypoints = MODEL_DEFAULT_POSTURE.  `t` may live in shared or global memory.
 __device__ __forceinline__ void spawn_track(const StepArgs& a, int s, TrackRec& t, int q, int slot, int track_id,
-                                            const int* cl, const int* fcnt, const int* fphys, int lane) {
+                                            const int* cl, const int* fcnt, const int* fphys, int lane,
+                                            const float* rawc = nullptr /* fused raw rows in shared memory */,
+                                            const double* w6 = nullptr /* their world 6-vectors, precomputed */) {
     const DevConfig& c = a.cfg;
     const int tcap = c.tcap;
     int n = 0;
@@ -148,7 +150,7 @@ __device__ __forceinline__ void spawn_track(const StepArgs& a, int s, TrackRec& 
     float* dst = a.track_ring + (((size_t)s * tcap + slot) * kRing + 0) * (kFeatPts * kRawCols);
     int stored = 0;
     for (int f = 0; f < kRing; ++f) {
-        const float* src = uring_frame(a, s, fphys[f]);
+        const float* src = rawc != nullptr ? rawc + (size_t)b0 * kRawCols : uring_frame(a, s, fphys[f]);
         for (int i0 = 0; i0 < fcnt[f]; i0 += 32) {
             const int i = i0 + lane;
             const bool in = i < fcnt[f] && cl[b0 + i] == q;
@@ -157,7 +159,12 @@ __device__ __forceinline__ void spawn_track(const StepArgs& a, int s, TrackRec& 
 #pragma unroll
                 for (int k = 0; k < kRawCols; ++k) r5[k] = src[i * kRawCols + k];
                 double w[6];
-                world_from_raw(c, r5[0], r5[1], r5[2], r5[3], w);
+                if (w6 != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) w[k] = w6[(size_t)(b0 + i) * 6 + k];
+                } else {
+                    world_from_raw(c, r5[0], r5[1], r5[2], r5[3], w);
+                }
                 ++n;
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
@@ -215,7 +222,7 @@ __device__ __forceinline__ void spawn_track(const StepArgs& a, int s, TrackRec& 
 // fp32 world coordinates of the fused ring (oldest frame first) into shared memory + the screened predicate over
 // them (dbscan.cuh).  Block-cooperative; ends with __syncthreads().
 __device__ __forceinline__ NbScreened load_fused_ring(const StepArgs& a, int s, const int* fcnt, const int* fphys,
-                                                      float* Xf, int stride) {
+                                                      float* Xf, int stride, float* rawc = nullptr) {
     const DevConfig& c = a.cfg;
     float* Yf = Xf + stride;
     float* Zf = Yf + stride;
@@ -234,6 +241,10 @@ __device__ __forceinline__ NbScreened load_fused_ring(const StepArgs& a, int s, 
             double yw, zw;
             world_yz(c, (double)y, (double)z, yw, zw);
             Xf[b0 + i] = x; Yf[b0 + i] = (float)yw; Zf[b0 + i] = (float)zw;
+            if (rawc != nullptr) {
+                float* r = rawc + (size_t)(b0 + i) * kRawCols;
+                r[0] = x; r[1] = y; r[2] = z; r[3] = src[i * kRawCols + 3]; r[4] = src[i * kRawCols + 4];
+            }
         }
         b0 += fcnt[f];
     }
@@ -355,6 +366,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         if (tid == 0) {
             sc.last_ran = 0;
             a.scenes[s] = sc;
+            a.pose_cnt[s] = 0;
             atomicAdd(&a.counters[1], (unsigned long long)N);
         }
         return;
@@ -632,6 +644,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     if (tid == 0) {
         sc.n_tracks = T2;
         a.scenes[s] = sc;
+        a.pose_cnt[s] = T2;
         atomicAdd(&a.counters[0], 1ull);
         atomicAdd(&a.counters[1], (unsigned long long)N);
         atomicAdd(&a.counters[2], (unsigned long long)M);
@@ -651,7 +664,15 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
 
 // DBSCAN + spawn for the scenes the step kernel deferred (fused cloud > kDeferPoints): same device functions, one
 // CTA of 1024 threads per scene, new tracks written straight to the scene's list in global memory.
-constexpr int kBigThreads = 1024;
+constexpr int kBigThreads = 512;
+constexpr int kBitsMaxB = 768;        // adjacency bit matrix of up to 768 x 768 (72 KB of shared memory)
+__host__ __device__ inline int big_bits_cap(int ncap) { return 3 * ncap < kBitsMaxB ? 3 * ncap : kBitsMaxB; }
+// shared-memory layout of dbscan_big_kernel: Xf|Yf|Zf, par, cl, scan, adj, cm, rm, raw rows, (8-byte aligned) w6
+__host__ __device__ inline int big_w6_offset(int ncap) {
+    const int cap = big_bits_cap(ncap), w = (cap + 31) / 32;
+    const int o = 36 * ncap + 2 * 3 * ncap * 4 + 64 * 4 + (cap * w + 2 * w) * 4 + cap * kRawCols * 4;
+    return (o + 7) & ~7;
+}
 __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const DevConfig& c = a.cfg;
@@ -660,8 +681,26 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
     int* par = reinterpret_cast<int*>(smem + 36 * ncap);
     int* cl = par + 3 * ncap;
     int* scan = cl + 3 * ncap;                               // 64 ints
+    // bit-matrix DBSCAN (dbscan.cuh) for fused clouds of up to kBitsMaxB points; larger ones (dense configurations
+    // with > 256 points per frame) take the pair-sweep version
+    const int bits_cap = big_bits_cap(ncap), bits_w = (bits_cap + 31) >> 5;
+    unsigned* adj = reinterpret_cast<unsigned*>(scan + 64);
+    unsigned* cm = adj + (size_t)bits_cap * bits_w;
+    unsigned* rm = cm + bits_w;
+    float* rawc = reinterpret_cast<float*>(rm + bits_w);     // bits_cap raw rows
+    double* w6 = reinterpret_cast<double*>(smem + big_w6_offset(ncap));   // bits_cap world 6-vectors
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_defer = *a.defer_count;
+    // debug accounting (mmw_dbscan_big_clocks): cycles of thread 0 per part, summed over the deferred scenes
+    unsigned long long* dbg = a.phase_cycles != nullptr ? a.phase_cycles + 16 + 3 * a.n_scenes : nullptr;
+    long long dbg_t = clock64();
+    auto stamp = [&](int k) {
+        if (dbg != nullptr && tid == 0) {
+            const long long now = clock64();
+            atomicAdd(&dbg[k], (unsigned long long)(now - dbg_t));
+            dbg_t = now;
+        }
+    };
     for (int it = blockIdx.x; it < n_defer; it += gridDim.x) {
         const int s = a.defer_list[it];
         SceneRec sc = a.scenes[s];
@@ -673,8 +712,13 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
             fcnt[f] = f < sc.ring_n ? sc.ring_cnt[fphys[f]] : 0;
             B += fcnt[f];
         }
-        NbScreened nb = load_fused_ring(a, s, fcnt, fphys, Xf, 3 * ncap);
-        int ncl = dbscan_block(nb, B, c.db_min_samples, par, cl, scan);
+        const bool bits = B <= bits_cap;
+        NbScreened nb = load_fused_ring(a, s, fcnt, fphys, Xf, 3 * ncap, bits ? rawc : nullptr);
+        stamp(0);
+        int ncl = bits ? dbscan_bits_block(nb, B, c.db_min_samples, adj, cm, rm, par, cl, dbg != nullptr ? dbg - 10 : nullptr)
+                       : dbscan_block(nb, B, c.db_min_samples, par, cl, scan, dbg != nullptr ? dbg - 10 : nullptr, false,
+                                      true);
+        if (dbg != nullptr && tid == 0) dbg_t = clock64();
         if (a.labels_out != nullptr)
             for (int b = tid; b < B; b += kBigThreads) a.labels_out[(size_t)s * 3 * ncap + b] = cl[b];
         if (ncl > 0) {
@@ -688,9 +732,20 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
                     sc.slot_mask |= 1u << newslot[q];
                 }
             }
+            if (bits) {                  // world coordinates and velocities of the clustered points, all threads
+                for (int b = tid; b < B; b += kBigThreads)
+                    if (cl[b] >= 0) {
+                        const float* r = rawc + (size_t)b * kRawCols;
+                        double w[6];
+                        world_from_raw(c, r[0], r[1], r[2], r[3], w);
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) w6[(size_t)b * 6 + k] = w[k];
+                    }
+                __syncthreads();
+            }
             for (int q = warp; q < ncl; q += kBigThreads / 32)
                 spawn_track(a, s, a.tracks[(size_t)s * tcap + T1 + q], q, newslot[q], sc.next_id + q, cl, fcnt, fphys,
-                            lane);
+                            lane, bits ? rawc : nullptr, bits ? w6 : nullptr);
             sc.next_id += ncl;
             sc.n_tracks = T1 + ncl;
             sc.ring_n = 0;               // batch.clear() (Tracking.py:699-700, Q8)
@@ -699,8 +754,10 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
             if (tid == 0) atomicAdd(&a.counters[5], (unsigned long long)ncl);
         }
         __syncthreads();
-        if (tid == 0) a.scenes[s] = sc;
+        if (tid == 0) { a.scenes[s] = sc; a.pose_cnt[s] = sc.n_tracks; }
         __syncthreads();
+        stamp(1);
+        if (dbg != nullptr && tid == 0) { atomicAdd(&dbg[2], 1ull); atomicAdd(&dbg[7], (unsigned long long)B); }
     }
 }
 
@@ -726,10 +783,13 @@ cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
 cudaError_t launch_dbscan_big(const StepArgs& a, cudaStream_t stream) {
     if (a.defer_count == nullptr) return cudaSuccess;
     cudaError_t e;
-    const int big_smem = 36 * a.cfg.ncap + 2 * 3 * a.cfg.ncap * 4 + 64 * 4;
+    const int big_smem = big_w6_offset(a.cfg.ncap) + big_bits_cap(a.cfg.ncap) * 6 * 8;
     static int big_configured = 0;
     if (big_smem > big_configured) {
         e = cudaFuncSetAttribute(dbscan_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(dbscan_big_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         big_configured = big_smem;
     }

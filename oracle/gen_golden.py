@@ -111,8 +111,33 @@ def offline_manager_sequence() -> dict:
     return {"scene": 2, "frames": 95, "frames_per_file": 40, "sequence": seq}
 
 
+EXPORT_CASES = [("c1_s4", 4, 30, None), ("churn_s308", None, 140, None)]
+
+
+def track0_export_golden() -> dict:
+    """Row f-3: the dataset-builder export of the reference (its own relative_coordinates + format_batched_frames
+    under the loop body of preprocessing.py:185-216) on the frames of two committed traces."""
+    out = {}
+    for name, _, nf, mt in EXPORT_CASES:
+        g = trace_io.unpack(np.load(os.path.join(GOLDEN, name + ".npz")))
+        frames, dts = g["frames"][:nf], g["dts"][:nf]
+        recs = rh.run_reference_scene(frames, dts, pose_fn=None, max_tracks=mt, export0=True)
+        valid = np.array([r["export0"] is not None for r in recs], bool)
+        out[name + "_frames"] = np.array(nf, np.int32)
+        out[name + "_valid"] = valid
+        out[name + "_rows"] = (np.stack([r["export0"][0] for r in recs if r["export0"] is not None])
+                               if valid.any() else np.zeros((0, 192, 5)))
+        out[name + "_centroid"] = (np.stack([r["export0"][1] for r in recs if r["export0"] is not None])
+                                   if valid.any() else np.zeros((0, 2)))
+        print("export0", name, "frames", nf, "valid", int(valid.sum()))
+    return out
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--export0-only" in sys.argv:
+        np.savez_compressed(os.path.join(GOLDEN, "track0_export.npz"), **track0_export_golden())
+        return
     json.dump(offline_manager_sequence(), open(os.path.join(GOLDEN, "offline_manager_sequence.json"), "w"))
     json.dump(known_answers(), open(os.path.join(GOLDEN, "known_answers.json"), "w"), indent=1)
     for name, sid, nf, spec, mt in CASES:
@@ -123,6 +148,7 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **d)
         print(name, "frames", nf, "tracks at end", len(recs[-1]["tracks"]), "next id", recs[-1]["next_track_id"],
               "dbscan runs", int(d["labels_ran"].sum()))
+    np.savez_compressed(os.path.join(GOLDEN, "track0_export.npz"), **track0_export_golden())
     if "--deviation" in sys.argv:
         dev = balltree_deviation()
         json.dump(dev, open(os.path.join(GOLDEN, "balltree_deviation.json"), "w"), indent=1)

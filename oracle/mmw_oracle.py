@@ -399,6 +399,29 @@ def fade_square(x, keypoints, m=(0.32, -0.6, 1.3), size_max=0.3, size_min=0.2, w
 
 
 # ----------------------------------------------------------------------------
+# "next" row f-3: dataset-builder export of track 0 (preprocessing.py:185-216, Utils.py:523-548)
+# ----------------------------------------------------------------------------
+def track0_export(scene: "SceneOracle"):
+    """What preprocess_dataset writes for a frame that ran track(): None unless track 0 exists, was seen in this
+    frame (lifetime == 0) and has points in its ring (preprocessing.py:185-196); else the (192, 5) block of
+    format_batched_frames(relative_coordinates(ring frames, centroid)) -- ring frames newest first, columns
+    [x - cx, y - cy, z, doppler, peakVal], first 64 rows per frame, zero padded, unsorted, raw intensity
+    (Utils.py:523-548, 437-465) -- and the centroid[:2] appended to the centroid log (preprocessing.py:209-213)."""
+    if not scene.tracks:
+        return None
+    t0 = scene.tracks[0]
+    if t0.lifetime != 0 or sum(len(f) for f in t0.ring.frames) == 0:
+        return None
+    out = np.zeros((3 * 64, 5))
+    cx, cy = t0.centroid[0], t0.centroid[1]
+    for k, cloud in enumerate(reversed(t0.ring.frames)):
+        rel = cloud - np.array([cx, cy, 0, 0, 0, 0, 0, 0])
+        sel = rel[:, [0, 1, 2, 6, 7]][:64]
+        out[k * 64:k * 64 + len(sel)] = sel
+    return out, np.array([cx, cy])
+
+
+# ----------------------------------------------------------------------------
 # a11  one scene: TrackBuffer.track + estimate_posture under the offline_main loop
 # ----------------------------------------------------------------------------
 class SceneOracle:

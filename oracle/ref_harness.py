@@ -125,7 +125,7 @@ class _ModelAdapter:
 
 def run_reference_scene(frames: List[np.ndarray], dts: np.ndarray, pose_fn=None,
                         dbscan_algorithm: str = "brute", stable_sort: bool = True,
-                        max_tracks: Optional[int] = None) -> List[dict]:
+                        max_tracks: Optional[int] = None, export0: bool = False) -> List[dict]:
     """Run the offline_main.py loop body (offline_main.py:45-60) on one scene.
 
     Returns one record per frame with the decisions and states after the frame.
@@ -163,6 +163,17 @@ def run_reference_scene(frames: List[np.ndarray], dts: np.ndarray, pose_fn=None,
                 if model is not None:
                     model.last_input = None
                     tb.estimate_posture(model)
+            if export0:
+                # the body of preprocess_dataset's frame loop (preprocessing.py:185-216), calling the reference's own
+                # relative_coordinates / format_batched_frames (preprocessing.py itself runs at import and needs
+                # wakepy + the authors' dataset, so its loop body is restated here around the reference's functions)
+                rec["export0"] = None
+                if ran and len(tb.effective_tracks) > 0:
+                    t0 = tb.effective_tracks[0]
+                    if t0.lifetime == 0 and len(t0.batch.effective_data) > 0:
+                        fr = utils.relative_coordinates(list(t0.batch.buffer), t0.cluster.centroid)
+                        rec["export0"] = (np.array(utils.format_batched_frames(fr), dtype=np.float64),
+                                          np.array(t0.cluster.centroid[:2], dtype=np.float64))
             rec["ran"] = ran
             rec["assoc"] = assoc_log[n_as0].copy() if len(assoc_log) > n_as0 else np.zeros(0, np.int32)
             rec["labels"] = pr.labels_log[n_lab0].copy() if len(pr.labels_log) > n_lab0 else None

@@ -31,4 +31,5 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    """Per-scene traces of the reference (trace_io format); track0_export.npz holds the dataset-builder blocks."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f != "track0_export.npz")

@@ -61,6 +61,29 @@ def test_projection_points_match_reference():
     assert mo.fade_square(np.array([0.5, -9.0, 1.0]), kp)[1] == 0.3
 
 
+@pytest.mark.parametrize("name", ["c1_s4", "churn_s308"])
+def test_track0_export_matches_reference(name):
+    """Row f-3: oracle.track0_export against the reference's own relative_coordinates + format_batched_frames run
+    under the loop body of preprocessing.py:185-216 (tests/golden/track0_export.npz, oracle/gen_golden.py)."""
+    ex = np.load(os.path.join(GOLDEN, "track0_export.npz"))
+    g = trace_io.unpack(np.load(os.path.join(GOLDEN, name + ".npz")))
+    nf = int(ex[name + "_frames"])
+    so = mo.SceneOracle()
+    k = 0
+    for f in range(nf):
+        rec = so.step(g["frames"][f], g["dts"][f])
+        got = mo.track0_export(so) if rec["ran"] else None
+        assert (got is not None) == bool(ex[name + "_valid"][f]), "frame %d" % f
+        if got is not None:
+            np.testing.assert_allclose(got[0], ex[name + "_rows"][k], rtol=0, atol=FLOAT_TOL)
+            np.testing.assert_allclose(got[1], ex[name + "_centroid"][k], rtol=0, atol=FLOAT_TOL)
+            # everything but the two centroid-relative columns is copied, not computed: exact
+            np.testing.assert_array_equal(got[0][:, 2:], ex[name + "_rows"][k][:, 2:])
+            k += 1
+    assert k == len(ex[name + "_rows"])
+    assert not ex[name + "_valid"].all() or name == "c1_s4"      # the churn case covers invalid frames
+
+
 def _run_oracle(g, max_tracks):
     so = mo.SceneOracle(mo.OracleConfig(tr_max_tracks=max_tracks))
     return [so.step(fr, dt) for fr, dt in zip(g["frames"], g["dts"])]
