@@ -382,7 +382,8 @@ def rooflines(kern, cnt, K, alg_bytes, pk, step_ms):
         g = kern.get("fc1", None)
         if g:
             a = fc1_flops / (g / 1e3) / 1e12
-            out["roofline_fc1"] = {"kernel": "gemm_tc_kernel<192,2,0> (dense 1)", "bound": "tensor", "achieved": a,
+            out["roofline_fc1"] = {"kernel": "gemm_tc_pair_kernel<192,3> (dense 1, tcgen05 cta_group::2)", "bound": "tensor",
+                                   "achieved": a,
                                    "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": a / pk["bf16_tflops"],
                                    "traffic": traffic.get("gemm_tc_kernel_dense1"),
                                    "algorithmic_flops_per_launch": fc1_flops, "executed_tflops": 3 * a,
@@ -390,7 +391,25 @@ def rooflines(kern, cnt, K, alg_bytes, pk, step_ms):
                                    "note": "fp32-accurate layer as 3 bf16 MMA passes (hi*hi + hi*lo + lo*hi): "
                                            "`achieved` counts the layer's FLOPs once, `executed` what the tensor "
                                            "pipe ran"}
-        out["roofline"] = dict(out["roofline_fc1"] if dom == "fc1" and g else out.get("roofline_step", {}))
+        cv = kern.get("conv", None)
+        if cv:
+            # both convolutions of the 3-D net (two launches, timed together): algorithmic FLOPs of the fp32 layers;
+            # `executed` = what the MMAs issued (hi/lo split incl. its zero block, 5 -> 8 padded input channels,
+            # 256 MMA rows per sample of which 192 are kept)
+            conv_flops = 2.0 * rows * (192 * 135 * 16 + 192 * 432 * 32)
+            conv_exec = 2.0 * rows * 27 * 256 * (32 * 16 + 64 * 32)
+            a = conv_flops / (cv / 1e3) / 1e12
+            out["roofline_conv"] = {"kernel": "conv_slab_kernel<16,32,0,3> + conv_slab_kernel<32,64,1,3> (conv 1 + conv 2)",
+                                    "bound": "tensor", "achieved": a, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                                    "frac": a / pk["bf16_tflops"], "traffic": traffic.get("conv_slab_conv2"),
+                                    "algorithmic_flops_per_launch": conv_flops,
+                                    "executed_tflops": conv_exec / (cv / 1e3) / 1e12,
+                                    "executed_frac": conv_exec / (cv / 1e3) / 1e12 / pk["bf16_tflops"],
+                                    "peak_src": pk["src"],
+                                    "note": "shifted-window implicit GEMM, N = 32 / 64 per MMA: bound by the A-operand "
+                                            "shared-memory reads of small-N MMAs, not by the tensor pipe (DESIGN.md 4)"}
+        by = {"fc1": "roofline_fc1", "conv": "roofline_conv", "step": "roofline_step"}
+        out["roofline"] = dict(out.get(by.get(dom, "roofline_step"), out.get("roofline_step", {})))
         out["roofline"]["dominant_kernel"] = dom
         out["algorithmic_bytes_per_step_whole_path"] = alg_bytes / K
     else:

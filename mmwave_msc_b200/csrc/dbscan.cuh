@@ -250,6 +250,84 @@ __device__ inline int dbscan_block(const Nb& nb_full, int B, int min_samples, in
 //   (labels only decrease and stay inside the component, so the fixed point is the smallest core index = the root
 //   dbscan_inner's ascending scan starts the cluster from);  cluster ids -> popc of the root bit mask;  border points
 //   -> min cluster id over core neighbours.  No atomics, results independent of scheduling.
+// Phases 2 and 3 of the bit-matrix DBSCAN, shared by dbscan_bits_block (rows of all points) and
+// dbscan_finish_core_rows (rows of the core points only): components of the core-core graph and cluster ids.
+// On entry par[b] = b for core points and -1 otherwise, cm = core bit mask, adj rows valid for every core point.
+// On return cl[b] = cluster id of core point b (-1 for the others) and the number of clusters is returned.
+__device__ inline int bits_components_and_ids(int B, int W, const unsigned* adj, const unsigned* cm, unsigned* rm,
+                                              int* par, int* cl) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    // 2. components of the core-core graph.  First hop straight from the bit rows (lowest core neighbour; final
+    //    already when the component is a clique, the usual person-sized blob), then min-label propagation +
+    //    pointer jumping until nothing changes.
+    for (int b = warp; b < B; b += nw) {
+        if (par[b] < 0) continue;                                        // uniform over the warp; par[b] is only
+        int m = 0x7fffffff;                                              // written by this warp in this loop
+        for (int w = lane; w < W; w += 32) {
+            const unsigned bits = adj[b * W + w] & cm[w];
+            if (bits) m = min(m, (w << 5) + __ffs(bits) - 1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
+        if (lane == 0) par[b] = m;                                       // m <= b: b is its own neighbour
+    }
+    __syncthreads();
+    while (true) {
+        for (int b = tid; b < B; b += nt) {                              // pointer jumping (parents only decrease)
+            int l = ((volatile int*)par)[b];
+            if (l < 0) continue;
+            while (true) {
+                const int p = ((volatile int*)par)[l];
+                if (p == l) break;
+                l = p;
+            }
+            if (l < ((volatile int*)par)[b]) atomicMin(&par[b], l);
+        }
+        __syncthreads();
+        int changed = 0;
+        for (int b = warp; b < B; b += nw) {
+            const int cur = ((volatile int*)par)[b];
+            if (cur < 0) continue;                                       // uniform over the warp
+            int m = cur;
+            for (int w0 = 0; w0 < W; w0 += 4) {
+                unsigned bits[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) bits[u] = w0 + u < W ? (adj[b * W + w0 + u] & cm[w0 + u]) : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if ((bits[u] >> lane) & 1u) m = min(m, ((volatile int*)par)[((w0 + u) << 5) + lane]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
+            if (m < cur) {
+                if (lane == 0) atomicMin(&par[b], m);
+                changed = 1;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    // 3. cluster ids: rank of the root among the roots, ascending index
+    for (int w = warp; w < W; w += nw) {
+        const int b = (w << 5) + lane;
+        const unsigned m = __ballot_sync(kFullMask, b < B && par[b] == b);
+        if (lane == 0) rm[w] = m;
+    }
+    __syncthreads();
+    int ncl = 0;
+    for (int w = 0; w < W; ++w) ncl += __popc(rm[w]);
+    for (int b = tid; b < B; b += nt) {
+        const int r = par[b];
+        int id = -1;
+        if (r >= 0) {
+            id = __popc(rm[r >> 5] & ((1u << (r & 31)) - 1u));
+            for (int w = 0; w < (r >> 5); ++w) id += __popc(rm[w]);
+        }
+        cl[b] = id;
+    }
+    __syncthreads();
+    return ncl;
+}
+
 // adj: B * ceil(B/32) words; cm, rm: ceil(B/32) words each (shared).  Requires B <= blockDim.x * 32.
 __device__ inline int dbscan_bits_block(const NbScreened& nbf, int B, int min_samples, unsigned* adj, unsigned* cm,
                                         unsigned* rm, int* par, int* cl, unsigned long long* dbg = nullptr) {
@@ -316,75 +394,7 @@ __device__ inline int dbscan_bits_block(const NbScreened& nbf, int B, int min_sa
         __syncthreads();
         return 0;
     }
-    // 2. components of the core-core graph.  First hop straight from the bit rows (lowest core neighbour; final
-    //    already when the component is a clique, the usual person-sized blob), then min-label propagation +
-    //    pointer jumping until nothing changes.
-    for (int b = warp; b < B; b += nw) {
-        if (par[b] < 0) continue;                                        // uniform over the warp; par[b] is only
-        int m = 0x7fffffff;                                              // written by this warp in this loop
-        for (int w = lane; w < W; w += 32) {
-            const unsigned bits = adj[b * W + w] & cm[w];
-            if (bits) m = min(m, (w << 5) + __ffs(bits) - 1);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
-        if (lane == 0) par[b] = m;                                       // m <= b: b is its own neighbour
-    }
-    __syncthreads();
-    while (true) {
-        for (int b = tid; b < B; b += nt) {                              // pointer jumping (parents only decrease)
-            int l = ((volatile int*)par)[b];
-            if (l < 0) continue;
-            while (true) {
-                const int p = ((volatile int*)par)[l];
-                if (p == l) break;
-                l = p;
-            }
-            if (l < ((volatile int*)par)[b]) atomicMin(&par[b], l);
-        }
-        __syncthreads();
-        int changed = 0;
-        for (int b = warp; b < B; b += nw) {
-            const int cur = ((volatile int*)par)[b];
-            if (cur < 0) continue;                                       // uniform over the warp
-            int m = cur;
-            for (int w0 = 0; w0 < W; w0 += 4) {
-                unsigned bits[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) bits[u] = w0 + u < W ? (adj[b * W + w0 + u] & cm[w0 + u]) : 0u;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if ((bits[u] >> lane) & 1u) m = min(m, ((volatile int*)par)[((w0 + u) << 5) + lane]);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
-            if (m < cur) {
-                if (lane == 0) atomicMin(&par[b], m);
-                changed = 1;
-            }
-        }
-        if (!__syncthreads_or(changed)) break;
-    }
-    stamp(14);
-    // 3. cluster ids: rank of the root among the roots, ascending index
-    for (int w = warp; w < W; w += nw) {
-        const int b = (w << 5) + lane;
-        const unsigned m = __ballot_sync(kFullMask, b < B && par[b] == b);
-        if (lane == 0) rm[w] = m;
-    }
-    __syncthreads();
-    int ncl = 0;
-    for (int w = 0; w < W; ++w) ncl += __popc(rm[w]);
-    for (int b = tid; b < B; b += nt) {
-        const int r = par[b];
-        int id = -1;
-        if (r >= 0) {
-            id = __popc(rm[r >> 5] & ((1u << (r & 31)) - 1u));
-            for (int w = 0; w < (r >> 5); ++w) id += __popc(rm[w]);
-        }
-        cl[b] = id;
-    }
-    __syncthreads();
+    const int ncl = bits_components_and_ids(B, W, adj, cm, rm, par, cl);
     stamp(15);
     // 4. border points: lowest-numbered cluster with a core point within eps (only labels of core points are read)
     for (int b = warp; b < B; b += nw) {
@@ -404,6 +414,52 @@ __device__ inline int dbscan_bits_block(const NbScreened& nbf, int B, int min_sa
     }
     __syncthreads();
     stamp(16);
+    return ncl;
+}
+
+// The step kernel's continuation for the few scenes per frame in which a cluster forms (fused cloud <= kDeferPoints):
+// dbscan_block(stop_if_core) has left par[b] = b for core points and -1 otherwise.  Only the rows of CORE points are
+// evaluated (core-core edges for the components, core-border edges for the border labels -- the predicate is
+// symmetric), so a person-sized blob of ~60 core points among ~150 costs 60 x 5 warp ballots.  Same labels as
+// dbscan_block / dbscan_bits_block.  adj: B * ceil(B/32) words, cm / rm: ceil(B/32) words (shared).
+template <class Nb>
+__device__ inline int dbscan_finish_core_rows(const Nb& nb_full, int B, unsigned* adj, unsigned* cm, unsigned* rm,
+                                              int* par, int* cl) {
+    const auto nb = nb_full.hot();
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int W = (B + 31) >> 5;
+    for (int w = warp; w < W; w += nw) {
+        const int b = (w << 5) + lane;
+        const unsigned m = __ballot_sync(kFullMask, b < B && par[b] >= 0);
+        if (lane == 0) cm[w] = m;
+    }
+    for (int b = warp; b < B; b += nw) {
+        if (par[b] < 0) continue;                                        // uniform over the warp
+        for (int w = 0; w < W; ++w) {
+            const int q = (w << 5) + lane;
+            const bool hit = q < B && (q == b || nb(b, q));
+            const unsigned m = __ballot_sync(kFullMask, hit);
+            if (lane == 0) adj[b * W + w] = m;
+        }
+    }
+    __syncthreads();
+    const int ncl = bits_components_and_ids(B, W, adj, cm, rm, par, cl);
+    // border points: every core row pushes its cluster id to its non-core neighbours; the minimum wins
+    for (int b = tid; b < B; b += nt)
+        if (cl[b] < 0) par[b] = 0x7fffffff;
+    __syncthreads();
+    for (int b = warp; b < B; b += nw) {
+        const int lb = cl[b];
+        if (lb < 0) continue;                                            // uniform over the warp
+        for (int w = 0; w < W; ++w) {
+            const unsigned bits = adj[b * W + w] & ~cm[w];
+            if ((bits >> lane) & 1u) atomicMin(&par[(w << 5) + lane], lb);
+        }
+    }
+    __syncthreads();
+    for (int b = tid; b < B; b += nt)
+        if (cl[b] < 0) cl[b] = par[b] == 0x7fffffff ? -1 : par[b];
+    __syncthreads();
     return ncl;
 }
 

@@ -431,10 +431,13 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     prof_mark(x, MMW_K_DBSCAN_BIG);
     CK(launch_dbscan_big(a, x->stream));
     x->launches += 2;          // step_kernel + dbscan_big_kernel
-    if (host_stage >= 0) CK(cudaEventRecord(x->stage_free[host_stage], x->stream));
     prof_mark(x, -1);
-    if (flags & MMW_STEP_POSE) return mmw_estimate_posture(x);
-    return MMW_OK;
+    int rc = MMW_OK;
+    if (flags & MMW_STEP_POSE) rc = mmw_estimate_posture(x);
+    // the staging buffer is free once step_kernel has read it; recorded after the last launch of the step so that no
+    // event sits between two kernels of the chain (it would undo their programmatic dependent launch)
+    if (host_stage >= 0) CK(cudaEventRecord(x->stage_free[host_stage], x->stream));
+    return rc;
 }
 
 int mmw_estimate_posture(mmw_ctx* x) {

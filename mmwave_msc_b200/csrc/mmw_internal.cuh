@@ -1,5 +1,7 @@
 // Internal device-side data model of libmmw (see DESIGN.md "Data layout in HBM").
 #pragma once
+#include <cstdlib>
+#include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/mmw.h"
@@ -88,6 +90,47 @@ struct StepArgs {
     uint32_t flags;
 };
 constexpr int kDeferPoints = 160;     // fused clouds larger than this go to dbscan_big_kernel
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------
+// The seven kernels of a step run back to back on one stream.  Each is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, does the part of its prologue that needs nothing from its
+// predecessor (barrier init, TMEM allocation, shared-memory zero fill, tensor-map prefetch), then
+// pdl_wait() -- the predecessor grid has completed and its writes are visible -- and only then
+// pdl_launch_dependents(), so that whenever a kernel's CTAs start, the kernel TWO places upstream has completed.
+// Launch latency and prologues overlap the predecessor's tail instead of sitting between kernels.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* env = getenv("MMW_PDL");
+        on = (env && env[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+
+// kernel<<<grid, block, smem, st>>>(args...) with the PDL attribute (and an optional cluster shape)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              dim3 cluster, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (cluster.x * cluster.y * cluster.z > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster.x; at[n].val.clusterDim.y = cluster.y; at[n].val.clusterDim.z = cluster.z;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at; cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- world-frame point from a raw sensor point (Utils.py:379-420) -----------------------------------
 // Written with explicit round-to-nearest multiplies/adds (no FMA contraction) so that the

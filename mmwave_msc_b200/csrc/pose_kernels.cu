@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(128) pose_feature_kernel(PoseFeatArgs a) {
     __shared__ float vals[4][kFeatPts][kRawCols];
     const int s = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();                          // the tracker kernels have completed
+    pdl_launch_dependents();
     const SceneRec sc = a.scenes[s];
     int pose_base = sc.pose_base;
     if (a.pose_cnt != nullptr) {
@@ -384,8 +386,7 @@ cudaError_t launch_pose_features(const PoseFeatArgs& a, int S, cudaStream_t st) 
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    pose_feature_kernel<<<S, 128, 0, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(pose_feature_kernel, dim3(S), dim3(128), 0, st, dim3(1, 1, 1), a);
 }
 
 }  // namespace mmw

@@ -207,7 +207,6 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
     float* sconst = reinterpret_cast<float*>(tmem_slot + 2);      // bias | bn_scale | bn_shift, COUT each
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rows = *a.n_rows;
 
     // static zero padding (d, w borders and the h rows a shifted copy never receives)
     for (int i = threadIdx.x; i < NSLAB * SLAB_BYTES / 16; i += kSlabThreads)
@@ -224,12 +223,19 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], MT); mbar_init(&tempty[b], 4); }
         mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the layer's weights do not depend on the previous kernel: fetch them before the PDL wait below
+        mbar_expect_tx(bfull, taps * B_TAP);
+        for (int t = 0; t < taps; ++t) tma_load_2d(sB + t * B_TAP, &map_b, bfull, 0, t * NOUT);
     }
     if (warp == 4) tmem_alloc<TCOLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above overlapped the previous kernel's tail (PDL); its activations and the row count are read below
+    pdl_wait();
+    pdl_launch_dependents();
+    const int rows = *a.n_rows;
 
     if (warp < 4) {
         // ===== producers: global -> registers (one sample ahead) -> the three h-shifted slabs of the sample =====
@@ -282,10 +288,6 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
         // Every operand address is slab/weight base + a compile-time constant, so one MMA costs two 64-bit adds.
         const int mt = warp - 4;
         if (lane == 0) {
-            if (warp == 5) {
-                mbar_expect_tx(bfull, taps * B_TAP);
-                for (int t = 0; t < taps; ++t) tma_load_2d(sB + t * B_TAP, &map_b, bfull, 0, t * NOUT);
-            }
             if (mt < MT) {
                 constexpr uint32_t idesc = make_idesc(NOUT);
                 const uint64_t db0 = make_desc<CK * 2>(smem_u32(sB));
@@ -426,7 +428,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     constexpr int A_BYTES = BM * kBK * 2, B_BYTES = BN * kBK * 2;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr uint32_t TCOLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // power of two
-    const int rows = *a.n_rows;
+    // The row count was written by the feature kernel, at least two kernels upstream: under the PDL discipline
+    // (mmw_internal.cuh) that grid had completed before this one could start, so it may be read before pdl_wait()
+    // -- which lets the CTAs past the last row leave without holding shared memory while they wait.
+    const int rows = __ldcg(a.n_rows);
     const int m0 = blockIdx.y * BM, n0 = MODE == 1 ? 0 : blockIdx.x * BN;
     if (m0 >= rows) return;
 
@@ -453,6 +458,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    pdl_wait();                          // the previous layer's activations are complete and visible
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -644,7 +651,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
         if (a.dbg & 4) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ts[i] = t; }
     };
     if (threadIdx.x == 0) mark(0);
-    const int rows = *a.n_rows;
+    const int rows = __ldcg(a.n_rows);                         // safe before pdl_wait(): see gemm_tc_kernel
     // grid = (M tiles rounded up to even, N tiles), cluster (2,1,1): a kernel that uses cta_group::2 must pair its CTAs
     // along x (the driver rejects any other cluster shape as "cluster misconfiguration")
     if ((int)(blockIdx.x & ~1u) * BM >= rows) return;          // the whole pair is past the last row
@@ -675,6 +682,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
     cluster_sync_all();                                        // both CTAs' barriers exist before any remote arrive
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    pdl_wait();                                                // conv2's output (A_hi / A_lo) is complete and visible
+    pdl_launch_dependents();
     if (threadIdx.x == 0) mark(1);
 
     if (warp == 0) {
@@ -1034,17 +1043,23 @@ int pose_tc_conv(PoseTc* t, const PoseTcRun& r, cudaStream_t st, int* n_launches
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
     ConvTcArgs c1{r.n_rows, r.b1, nullptr, nullptr, im->in_p, im->act1_p, nullptr, im->D, im->taps};
+    const dim3 one(1, 1, 1);
+    cudaError_t le;
     if (im->D == 3)
-        conv_slab_kernel<16, 32, 0, 3><<<148, kSlabThreads, conv_smem_bytes_tc<16, 32>(27), st>>>(im->m_w1b, c1);
+        le = launch_pdl(conv_slab_kernel<16, 32, 0, 3>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<16, 32>(27), st, one,
+                        im->m_w1b, c1);
     else
-        conv_slab_kernel<16, 32, 0, 1><<<148, kSlabThreads, conv_smem_bytes_tc<16, 32>(9), st>>>(im->m_w1b, c1);
-    if (check_launch("conv_slab_kernel<conv1>")) return -1;
+        le = launch_pdl(conv_slab_kernel<16, 32, 0, 1>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<16, 32>(9), st, one,
+                        im->m_w1b, c1);
+    if (le != cudaSuccess) { g_tc_err = std::string("conv_slab_kernel<conv1>: ") + cudaGetErrorString(le); return -1; }
     ConvTcArgs c2{r.n_rows, r.b2, r.bn1_scale, r.bn1_shift, im->act1_p, im->a_hi, im->a_lo, im->D, im->taps};
     if (im->D == 3)
-        conv_slab_kernel<32, 64, 1, 3><<<148, kSlabThreads, conv_smem_bytes_tc<32, 64>(27), st>>>(im->m_w2b, c2);
+        le = launch_pdl(conv_slab_kernel<32, 64, 1, 3>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<32, 64>(27), st, one,
+                        im->m_w2b, c2);
     else
-        conv_slab_kernel<32, 64, 1, 1><<<148, kSlabThreads, conv_smem_bytes_tc<32, 64>(9), st>>>(im->m_w2b, c2);
-    if (check_launch("conv_slab_kernel<conv2>")) return -1;
+        le = launch_pdl(conv_slab_kernel<32, 64, 1, 1>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<32, 64>(9), st, one,
+                        im->m_w2b, c2);
+    if (le != cudaSuccess) { g_tc_err = std::string("conv_slab_kernel<conv2>: ") + cudaGetErrorString(le); return -1; }
     if (n_launches) *n_launches = 2;
     return 0;
 }
@@ -1056,41 +1071,30 @@ int pose_tc_fc1(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
                  im->Kf, im->H, r.tcap, im->dbg};
     // 128 x 192 tiles when they divide N: 1536/192 = 8 column tiles, i.e. 120 CTAs for ~1900 rows instead of 90
     // CTAs of 128 x 256 on 148 SMs (one wave either way, 25 % less work per CTA)
+    cudaError_t le;
     if (im->pair) {
         const bool n192 = im->H % 192 == 0;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((((max_rows + 127) / 128) + 1) & ~1, im->H / (n192 ? 192 : 256));
-        cfg.blockDim = dim3(kGemmThreads);
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t le;
-        if (n192 && im->pair == 3) {
-            cfg.dynamicSmemBytes = gemm_pair_smem_bytes<192, 3>();
-            le = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<192, 3>, im->m_ah, im->m_al, im->m_w1h_half, im->m_w1l_half, g);
-        } else if (n192) {
-            cfg.dynamicSmemBytes = gemm_pair_smem_bytes<192, 2>();
-            le = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<192, 2>, im->m_ah, im->m_al, im->m_w1h_half, im->m_w1l_half, g);
-        } else if (im->pair == 3) {
-            cfg.dynamicSmemBytes = gemm_pair_smem_bytes<256, 3>();
-            le = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<256, 3>, im->m_ah, im->m_al, im->m_w1h_half, im->m_w1l_half, g);
-        } else {
-            cfg.dynamicSmemBytes = gemm_pair_smem_bytes<256, 2>();
-            le = cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<256, 2>, im->m_ah, im->m_al, im->m_w1h_half, im->m_w1l_half, g);
-        }
-        if (le != cudaSuccess) { g_tc_err = std::string("cudaLaunchKernelEx(dense1 pair): ") + cudaGetErrorString(le); return -1; }
+        const dim3 grid((((max_rows + 127) / 128) + 1) & ~1, im->H / (n192 ? 192 : 256)), blk(kGemmThreads), cl(2, 1, 1);
+        if (n192 && im->pair == 3)
+            le = launch_pdl(gemm_tc_pair_kernel<192, 3>, grid, blk, gemm_pair_smem_bytes<192, 3>(), st, cl, im->m_ah,
+                            im->m_al, im->m_w1h_half, im->m_w1l_half, g);
+        else if (n192)
+            le = launch_pdl(gemm_tc_pair_kernel<192, 2>, grid, blk, gemm_pair_smem_bytes<192, 2>(), st, cl, im->m_ah,
+                            im->m_al, im->m_w1h_half, im->m_w1l_half, g);
+        else if (im->pair == 3)
+            le = launch_pdl(gemm_tc_pair_kernel<256, 3>, grid, blk, gemm_pair_smem_bytes<256, 3>(), st, cl, im->m_ah,
+                            im->m_al, im->m_w1h_half, im->m_w1l_half, g);
+        else
+            le = launch_pdl(gemm_tc_pair_kernel<256, 2>, grid, blk, gemm_pair_smem_bytes<256, 2>(), st, cl, im->m_ah,
+                            im->m_al, im->m_w1h_half, im->m_w1l_half, g);
     } else if (im->H % 192 == 0) {
-        dim3 grid(im->H / 192, (max_rows + 127) / 128);
-        gemm_tc_kernel<192, 2, 0><<<grid, kGemmThreads, gemm_smem_bytes<192, 2>(), st>>>(im->m_ah, im->m_al, im->m_w1h,
-                                                                                        im->m_w1l, g);
+        le = launch_pdl(gemm_tc_kernel<192, 2, 0>, dim3(im->H / 192, (max_rows + 127) / 128), dim3(kGemmThreads),
+                        gemm_smem_bytes<192, 2>(), st, dim3(1, 1, 1), im->m_ah, im->m_al, im->m_w1h, im->m_w1l, g);
     } else {
-        dim3 grid(im->H / 256, (max_rows + 127) / 128);
-        gemm_tc_kernel<256, 2, 0><<<grid, kGemmThreads, gemm_smem_bytes<256, 2>(), st>>>(im->m_ah, im->m_al, im->m_w1h,
-                                                                                        im->m_w1l, g);
+        le = launch_pdl(gemm_tc_kernel<256, 2, 0>, dim3(im->H / 256, (max_rows + 127) / 128), dim3(kGemmThreads),
+                        gemm_smem_bytes<256, 2>(), st, dim3(1, 1, 1), im->m_ah, im->m_al, im->m_w1h, im->m_w1l, g);
     }
-    if (check_launch("gemm_tc_kernel<dense1>")) return -1;
+    if (le != cudaSuccess) { g_tc_err = std::string("dense 1 launch: ") + cudaGetErrorString(le); return -1; }
     if (n_launches) *n_launches = 1;
     return 0;
 }
@@ -1100,10 +1104,10 @@ int pose_tc_fc2(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
     GemmTcArgs g{r.n_rows, r.bd2, nullptr, nullptr, nullptr, nullptr, r.out, r.keypoints, r.row_scene, r.row_slot,
                  im->H, 64, r.tcap, im->dbg};
-    dim3 grid(1, (max_rows + 127) / 128);
-    gemm_tc_kernel<64, 4, 1><<<grid, kGemmThreads, gemm_smem_bytes<64, 4>(), st>>>(im->m_hh, im->m_hl, im->m_w2h,
-                                                                                  im->m_w2l, g);
-    if (check_launch("gemm_tc_kernel<dense2>")) return -1;
+    const cudaError_t le = launch_pdl(gemm_tc_kernel<64, 4, 1>, dim3(1, (max_rows + 127) / 128), dim3(kGemmThreads),
+                                      gemm_smem_bytes<64, 4>(), st, dim3(1, 1, 1), im->m_hh, im->m_hl, im->m_w2h,
+                                      im->m_w2l, g);
+    if (le != cudaSuccess) { g_tc_err = std::string("dense 2 launch: ") + cudaGetErrorString(le); return -1; }
     if (n_launches) *n_launches = 1;
     return 0;
 }

@@ -586,14 +586,27 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
         sc.dbscan_n = B;
     } else if (run_db) {
-        NbScreened nb = load_fused_ring(a, s, fcnt, fphys, reinterpret_cast<float*>(smem + L.dbf), 3 * ncap);
+        // with the work list on, clouds that get here have at most kDeferPoints points: the fp32 coordinate columns
+        // are packed that tightly, which leaves room behind them for the bit rows of dbscan_finish_core_rows
+        const int dstride = a.defer_list != nullptr ? kDeferPoints : 3 * ncap;
+        NbScreened nb = load_fused_ring(a, s, fcnt, fphys, reinterpret_cast<float*>(smem + L.dbf), dstride);
         PHASE_MARK(11);
         ncl = dbscan_block(nb, B, c.db_min_samples, par, cl, misc + kScan, a.phase_cycles, a.defer_list != nullptr);
         PHASE_MARK(12);
-        if (ncl < 0) {                   // clusters exist: union / border / spawn happen in dbscan_big_kernel
-            if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
-            ncl = 0;
-            deferred_late = true;
+        if (ncl < 0) {
+            // A cluster forms in this scene (a couple of scenes per frame).  Components, border labels and the spawn
+            // are finished right here from the bit rows of the core points (a few thousand cycles, inside the tail
+            // the kernel has anyway); only if the rows do not fit is the scene handed to dbscan_big_kernel.
+            const int W = (B + 31) >> 5;
+            const int bits_off = L.dbf + 3 * dstride * 4;
+            if (bits_off + (B * W + 2 * W) * 4 <= L.tracks) {
+                unsigned* adj = reinterpret_cast<unsigned*>(smem + bits_off);
+                ncl = dbscan_finish_core_rows(nb, B, adj, adj + B * W, adj + B * W + W, par, cl);
+            } else {
+                if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
+                ncl = 0;
+                deferred_late = true;
+            }
         }
         sc.dbscan_n = B;
         if (a.labels_out != nullptr && !deferred_late)
@@ -631,6 +644,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     __syncthreads();
 
     PHASE_MARK(9);
+    pdl_launch_dependents();             // late on purpose: dbscan_big's CTAs would otherwise sit on 16 SMs for the whole step
     // ---- 10. write back: track records in list order, scene record, counters ---------------------------
     {
         double* dstbase = reinterpret_cast<double*>(a.tracks + (size_t)s * tcap);
@@ -690,6 +704,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
     float* rawc = reinterpret_cast<float*>(rm + bits_w);     // bits_cap raw rows
     double* w6 = reinterpret_cast<double*>(smem + big_w6_offset(ncap));   // bits_cap world 6-vectors
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();                          // step_kernel has completed: work list, scene and track records are final
+    pdl_launch_dependents();
     const int n_defer = *a.defer_count;
     // debug accounting (mmw_dbscan_big_clocks): cycles of thread 0 per part, summed over the deferred scenes
     unsigned long long* dbg = a.phase_cycles != nullptr ? a.phase_cycles + 16 + 3 * a.n_scenes : nullptr;
@@ -793,8 +809,7 @@ cudaError_t launch_dbscan_big(const StepArgs& a, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         big_configured = big_smem;
     }
-    dbscan_big_kernel<<<16, kBigThreads, big_smem, stream>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(dbscan_big_kernel, dim3(16), dim3(kBigThreads), big_smem, stream, dim3(1, 1, 1), a);
 }
 
 }  // namespace mmw

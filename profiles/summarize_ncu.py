@@ -43,7 +43,7 @@ def traffic(path):
     for r in rows[2:]:
         name = r[ki]
         key = ("step_kernel" if "step_kernel" in name else "gemm_tc_kernel_dense1" if "gemm_tc_kernel<192" in name or
-               "gemm_tc_kernel<256" in name else "gemm_tc_kernel_dense2" if "gemm_tc_kernel<64" in name else
+               "gemm_tc_kernel<256" in name or "gemm_tc_pair_kernel" in name else "gemm_tc_kernel_dense2" if "gemm_tc_kernel<64" in name else
                "conv_slab_conv1" if "conv_slab_kernel<16" in name else "conv_slab_conv2" if "conv_slab_kernel<32" in name
                else name.split("(")[0])
         b = float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
