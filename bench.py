@@ -354,6 +354,18 @@ def ncu_traffic():
         return {}
 
 
+def issue_roofline(step_ms, traffic):
+    """Second roofline of the tracker step: warp instructions per launch (ncu, profiles/r01_traffic.json key
+    step_kernel_warp_insts, ~30 k per scene-frame of dependent float64 work) against the issue rate of the chip."""
+    wi = traffic.get("step_kernel_warp_insts")
+    if not wi:
+        return None
+    peak = 148 * 4 * 1.965e9            # warp instructions per second at the maximum SM clock
+    ach = wi / (step_ms / 1e3)
+    return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": ach / peak,
+            "warp_insts_per_launch": wi}
+
+
 def rooflines(kern, cnt, K, alg_bytes, pk, step_ms):
     """roofline of the dominant kernel (by CUDA-event time inside the step), plus the two that are always reported:
     the fused tracker step (HBM bound by construction) and the dense-1 GEMM (tensor bound).
@@ -378,6 +390,9 @@ def rooflines(kern, cnt, K, alg_bytes, pk, step_ms):
             out["roofline_step"] = {"kernel": "step_kernel", "bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"],
                                     "unit": "GB/s", "frac": a / pk["hbm_gbs"], "traffic": traffic.get("step_kernel"),
                                     "algorithmic_bytes_per_launch": step_bytes, "peak_src": pk["src"],
+                                    # what actually bounds it: warp-instruction issue (ncu smsp__inst_executed.sum of the
+                                    # committed capture / (SMs x 4 schedulers x SM clock))
+                                    "issue": issue_roofline(st, traffic),
                                     "note": "latency/issue-bound, not HBM-bound: see DESIGN.md section 4 and profiles/"}
         g = kern.get("fc1", None)
         if g:

@@ -250,8 +250,7 @@ __device__ inline int dbscan_block(const Nb& nb_full, int B, int min_samples, in
 //   (labels only decrease and stay inside the component, so the fixed point is the smallest core index = the root
 //   dbscan_inner's ascending scan starts the cluster from);  cluster ids -> popc of the root bit mask;  border points
 //   -> min cluster id over core neighbours.  No atomics, results independent of scheduling.
-// Phases 2 and 3 of the bit-matrix DBSCAN, shared by dbscan_bits_block (rows of all points) and
-// dbscan_finish_core_rows (rows of the core points only): components of the core-core graph and cluster ids.
+// Phases 2 and 3 of the bit-matrix DBSCAN, used by dbscan_bits_block: components of the core-core graph and cluster ids.
 // On entry par[b] = b for core points and -1 otherwise, cm = core bit mask, adj rows valid for every core point.
 // On return cl[b] = cluster id of core point b (-1 for the others) and the number of clusters is returned.
 __device__ inline int bits_components_and_ids(int B, int W, const unsigned* adj, const unsigned* cm, unsigned* rm,
@@ -414,52 +413,6 @@ __device__ inline int dbscan_bits_block(const NbScreened& nbf, int B, int min_sa
     }
     __syncthreads();
     stamp(16);
-    return ncl;
-}
-
-// The step kernel's continuation for the few scenes per frame in which a cluster forms (fused cloud <= kDeferPoints):
-// dbscan_block(stop_if_core) has left par[b] = b for core points and -1 otherwise.  Only the rows of CORE points are
-// evaluated (core-core edges for the components, core-border edges for the border labels -- the predicate is
-// symmetric), so a person-sized blob of ~60 core points among ~150 costs 60 x 5 warp ballots.  Same labels as
-// dbscan_block / dbscan_bits_block.  adj: B * ceil(B/32) words, cm / rm: ceil(B/32) words (shared).
-template <class Nb>
-__device__ inline int dbscan_finish_core_rows(const Nb& nb_full, int B, unsigned* adj, unsigned* cm, unsigned* rm,
-                                              int* par, int* cl) {
-    const auto nb = nb_full.hot();
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    const int W = (B + 31) >> 5;
-    for (int w = warp; w < W; w += nw) {
-        const int b = (w << 5) + lane;
-        const unsigned m = __ballot_sync(kFullMask, b < B && par[b] >= 0);
-        if (lane == 0) cm[w] = m;
-    }
-    for (int b = warp; b < B; b += nw) {
-        if (par[b] < 0) continue;                                        // uniform over the warp
-        for (int w = 0; w < W; ++w) {
-            const int q = (w << 5) + lane;
-            const bool hit = q < B && (q == b || nb(b, q));
-            const unsigned m = __ballot_sync(kFullMask, hit);
-            if (lane == 0) adj[b * W + w] = m;
-        }
-    }
-    __syncthreads();
-    const int ncl = bits_components_and_ids(B, W, adj, cm, rm, par, cl);
-    // border points: every core row pushes its cluster id to its non-core neighbours; the minimum wins
-    for (int b = tid; b < B; b += nt)
-        if (cl[b] < 0) par[b] = 0x7fffffff;
-    __syncthreads();
-    for (int b = warp; b < B; b += nw) {
-        const int lb = cl[b];
-        if (lb < 0) continue;                                            // uniform over the warp
-        for (int w = 0; w < W; ++w) {
-            const unsigned bits = adj[b * W + w] & ~cm[w];
-            if ((bits >> lane) & 1u) atomicMin(&par[(w << 5) + lane], lb);
-        }
-    }
-    __syncthreads();
-    for (int b = tid; b < B; b += nt)
-        if (cl[b] < 0) cl[b] = par[b] == 0x7fffffff ? -1 : par[b];
-    __syncthreads();
     return ncl;
 }
 

@@ -151,6 +151,8 @@ struct ConvTcArgs {
     __nv_bfloat16* out0;                           // MODE 0: act1 packed [row][D][8][8][32]; MODE 1: A_hi [row][Kf]
     __nv_bfloat16* out1;                           // MODE 1: A_lo [row][Kf]
     int D, taps;
+    int dbg;                                       // timing experiments only (MMW_GEMM_DBG): 8 = producers idle,
+                                                   // 16 = no MMAs, 32 = no epilogue stores
 };
 
 constexpr int kSlabThreads = 320;                  // warps 0-3 producers, 4-5 MMA issuers, 6-9 epilogue
@@ -255,18 +257,18 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) r[j] = __ldg(src + tid + 128 * j);
         };
-        if ((int)blockIdx.x < rows) load_row(blockIdx.x, cur);
+        if ((int)blockIdx.x < rows && !(a.dbg & 8)) load_row(blockIdx.x, cur);
         int u = 0;
         for (int row = blockIdx.x; row < rows; row += gridDim.x) {
             const int next = row + gridDim.x;
-            if (next < rows) load_row(next, nxt);
+            if (next < rows && !(a.dbg & 8)) load_row(next, nxt);
 #pragma unroll
             for (int c = 0; c < 3; ++c, ++u) {
                 const int slot = u % NSLAB;
                 mbar_wait(&sempty[slot], (uint32_t)(((u / NSLAB) & 1) ^ 1));
                 unsigned char* sl = slab + slot * SLAB_BYTES;
                 const int hh = hsrc - (c - 1);               // this slab serves kh = c - 1: row h feeds output h - kh
-                if (hh >= 0 && hh <= 7) {
+                if (hh >= 0 && hh <= 7 && !(a.dbg & 8)) {
 #pragma unroll
                     for (int j = 0; j < ITEMS; ++j) *reinterpret_cast<uint4*>(sl + dstoff[j] + hh * 16) = cur[j];
                 }
@@ -315,7 +317,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
                                 const int aoff = ((1 + kd) * 10 + kw) * ATOM;        // whole atoms: tap = tile shift
 #pragma unroll
                                 for (int kk = 0; kk < CK / 16; ++kk)
-                                    umma_bf16(tmem_d, da0 + (uint64_t)((aoff + kk * 256) >> 4),
+                                    if (!(a.dbg & 16)) umma_bf16(tmem_d, da0 + (uint64_t)((aoff + kk * 256) >> 4),
                                               db0 + (uint64_t)((tap * B_TAP + kk * 32) >> 4), idesc,
                                               (first && kk == 0) ? 0u : 1u);
                             }
@@ -361,7 +363,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
                 const int m = q * 32 + lane;
                 const int aidx = mt * 16 + (m >> 3), hh = m & 7;
                 const int d = aidx / 10, w2 = aidx % 10;
-                if (d >= D || w2 < 1 || w2 > 8) continue;       // padding columns / junk rows
+                if (d >= D || w2 < 1 || w2 > 8 || (a.dbg & 32)) continue;       // padding columns / junk rows
                 __align__(16) __nv_bfloat16 hi[COUT], lo[COUT];
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) {
@@ -1042,7 +1044,7 @@ int pose_tc_pack_input(PoseTc* t, const float* feats, const int* n_rows, cudaStr
 int pose_tc_conv(PoseTc* t, const PoseTcRun& r, cudaStream_t st, int* n_launches) {
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
-    ConvTcArgs c1{r.n_rows, r.b1, nullptr, nullptr, im->in_p, im->act1_p, nullptr, im->D, im->taps};
+    ConvTcArgs c1{r.n_rows, r.b1, nullptr, nullptr, im->in_p, im->act1_p, nullptr, im->D, im->taps, im->dbg};
     const dim3 one(1, 1, 1);
     cudaError_t le;
     if (im->D == 3)
@@ -1052,7 +1054,7 @@ int pose_tc_conv(PoseTc* t, const PoseTcRun& r, cudaStream_t st, int* n_launches
         le = launch_pdl(conv_slab_kernel<16, 32, 0, 1>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<16, 32>(9), st, one,
                         im->m_w1b, c1);
     if (le != cudaSuccess) { g_tc_err = std::string("conv_slab_kernel<conv1>: ") + cudaGetErrorString(le); return -1; }
-    ConvTcArgs c2{r.n_rows, r.b2, r.bn1_scale, r.bn1_shift, im->act1_p, im->a_hi, im->a_lo, im->D, im->taps};
+    ConvTcArgs c2{r.n_rows, r.b2, r.bn1_scale, r.bn1_shift, im->act1_p, im->a_hi, im->a_lo, im->D, im->taps, im->dbg};
     if (im->D == 3)
         le = launch_pdl(conv_slab_kernel<32, 64, 1, 3>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<32, 64>(27), st, one,
                         im->m_w2b, c2);

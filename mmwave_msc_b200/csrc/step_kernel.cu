@@ -586,27 +586,18 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
         sc.dbscan_n = B;
     } else if (run_db) {
-        // with the work list on, clouds that get here have at most kDeferPoints points: the fp32 coordinate columns
-        // are packed that tightly, which leaves room behind them for the bit rows of dbscan_finish_core_rows
-        const int dstride = a.defer_list != nullptr ? kDeferPoints : 3 * ncap;
-        NbScreened nb = load_fused_ring(a, s, fcnt, fphys, reinterpret_cast<float*>(smem + L.dbf), dstride);
+        NbScreened nb = load_fused_ring(a, s, fcnt, fphys, reinterpret_cast<float*>(smem + L.dbf), 3 * ncap);
         PHASE_MARK(11);
         ncl = dbscan_block(nb, B, c.db_min_samples, par, cl, misc + kScan, a.phase_cycles, a.defer_list != nullptr);
         PHASE_MARK(12);
         if (ncl < 0) {
-            // A cluster forms in this scene (a couple of scenes per frame).  Components, border labels and the spawn
-            // are finished right here from the bit rows of the core points (a few thousand cycles, inside the tail
-            // the kernel has anyway); only if the rows do not fit is the scene handed to dbscan_big_kernel.
-            const int W = (B + 31) >> 5;
-            const int bits_off = L.dbf + 3 * dstride * 4;
-            if (bits_off + (B * W + 2 * W) * 4 <= L.tracks) {
-                unsigned* adj = reinterpret_cast<unsigned*>(smem + bits_off);
-                ncl = dbscan_finish_core_rows(nb, B, adj, adj + B * W, adj + B * W + W, par, cl);
-            } else {
-                if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
-                ncl = 0;
-                deferred_late = true;
-            }
+            // A cluster forms in this scene (a couple of scenes per frame): components, border labels and the spawn
+            // happen in dbscan_big_kernel.  Finishing them here from the bit rows of the core points was measured:
+            // correct, but those CTAs (4 warps sharing an SM with 6 other CTAs) then end 35 us after all others and
+            // the step kernel goes from 72 to 107 us -- the separate 512-thread kernel costs 29 us.
+            if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
+            ncl = 0;
+            deferred_late = true;
         }
         sc.dbscan_n = B;
         if (a.labels_out != nullptr && !deferred_late)

@@ -48,7 +48,13 @@ def traffic(path):
                else name.split("(")[0])
         b = float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
         acc.setdefault(key, []).append(b)
-    print(json.dumps({k: sum(v) / len(v) for k, v in acc.items()}, indent=1))
+    res = {k: sum(v) / len(v) for k, v in acc.items()}
+    if "smsp__inst_executed.sum" in h:                 # warp instructions of the tracker step (bench.py issue roofline)
+        ii = h.index("smsp__inst_executed.sum")
+        wi = [float(r[ii]) for r in rows[2:] if "step_kernel" in r[ki]]
+        if wi:
+            res["step_kernel_warp_insts"] = sum(wi) / len(wi)
+    print(json.dumps(res, indent=1))
 
 
 if __name__ == "__main__":
