@@ -793,33 +793,35 @@ __global__ void __launch_bounds__(kFeatPts) export_track0_kernel(DevConfig c, co
     }
 }
 
-__global__ void pack_results_kernel(const SceneRec* scenes, const TrackRec* tracks, const float* keypoints, int S,
-                                    int tcap, float* out, FadeCfg fade) {
-    const int idx = blockIdx.x;            // scene * tcap + k
-    const int s = idx / tcap, k = idx % tcap;
-    float* o = out + (size_t)idx * MMW_RESULT_FLOATS;
+// One CTA per scene, one warp per record (8192 one-record CTAs cost 8 us of launch and tail on the main stream).
+__global__ void __launch_bounds__(256) pack_results_kernel(const SceneRec* scenes, const TrackRec* tracks,
+                                                           const float* keypoints, int S, int tcap, float* out,
+                                                           FadeCfg fade) {
+    const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int nt = scenes[s].n_tracks;
-    if (k >= nt) {
-        for (int e = threadIdx.x; e < MMW_RESULT_FLOATS; e += blockDim.x) o[e] = e == 0 ? -1.f : 0.f;
-        if (threadIdx.x == 0) o[1] = (float)nt;
-        return;
-    }
-    const TrackRec* t = tracks + (size_t)s * tcap + k;
-    const float* kp = keypoints + ((size_t)s * tcap + t->slot) * kKp;
-    for (int e = threadIdx.x; e < 68; e += blockDim.x) {
-        float v;
-        if (e == 0) v = (float)t->id;
-        else if (e == 1) v = (float)nt;
-        else if (e < 11) v = (float)t->x[e - 2];
-        else v = kp[e - 11];
-        o[e] = v;
-    }
-    if (threadIdx.x == 0) {
-        // calc_fade_square (Visualizer.py:14-29), float64 like the reference
-        double cx, cz;
-        projection_point(fade, t->x[0] + (double)kp[3], t->x[1] + (double)kp[41], (double)kp[22], cx, cz);
-        const double size = fmax(fade.smin, fmin(fade.smax, fade.smax - (t->x[1] + (double)kp[12]) * fade.weight));
-        o[68] = (float)cx; o[69] = (float)cz; o[70] = (float)size; o[71] = 0.f;
+    for (int k = warp; k < tcap; k += nw) {
+        float* o = out + ((size_t)s * tcap + k) * MMW_RESULT_FLOATS;
+        if (k >= nt) {
+            for (int e = lane; e < MMW_RESULT_FLOATS; e += 32) o[e] = e == 0 ? -1.f : (e == 1 ? (float)nt : 0.f);
+            continue;
+        }
+        const TrackRec* t = tracks + (size_t)s * tcap + k;
+        const float* kp = keypoints + ((size_t)s * tcap + t->slot) * kKp;
+        for (int e = lane; e < 68; e += 32) {
+            float v;
+            if (e == 0) v = (float)t->id;
+            else if (e == 1) v = (float)nt;
+            else if (e < 11) v = (float)t->x[e - 2];
+            else v = kp[e - 11];
+            o[e] = v;
+        }
+        if (lane == 0) {
+            // calc_fade_square (Visualizer.py:14-29), float64 like the reference
+            double cx, cz;
+            projection_point(fade, t->x[0] + (double)kp[3], t->x[1] + (double)kp[41], (double)kp[22], cx, cz);
+            const double size = fmax(fade.smin, fmin(fade.smax, fade.smax - (t->x[1] + (double)kp[12]) * fade.weight));
+            o[68] = (float)cx; o[69] = (float)cz; o[70] = (float)size; o[71] = 0.f;
+        }
     }
 }
 
@@ -859,7 +861,7 @@ int mmw_pack_results(mmw_ctx* x, float* device_out) {
     if (!x || !device_out) return fail(MMW_ERR_INVALID, "ctx/device_out is NULL");
     CK(cudaSetDevice(x->device));
     const FadeCfg fc{x->cfg.m_x, x->cfg.m_y, x->cfg.m_z, x->cfg.fade_size_max, x->cfg.fade_size_min, x->cfg.fade_weight};
-    pack_results_kernel<<<x->S * x->tcap, 64, 0, x->stream>>>(x->d_scenes, x->d_tracks, x->d_keypoints, x->S, x->tcap,
+    pack_results_kernel<<<x->S, 256, 0, x->stream>>>(x->d_scenes, x->d_tracks, x->d_keypoints, x->S, x->tcap,
                                                               device_out, fc);
     CK(cudaGetLastError());
     x->launches++;
@@ -872,7 +874,7 @@ int mmw_read_results_async(mmw_ctx* x, float* host_out, int* slot) {
     const int r = (int)(x->result_idx++ & 1u);
     CK(cudaStreamWaitEvent(x->stream, x->results_done[r], 0));     // previous download of this buffer finished
     const FadeCfg fc{x->cfg.m_x, x->cfg.m_y, x->cfg.m_z, x->cfg.fade_size_max, x->cfg.fade_size_min, x->cfg.fade_weight};
-    pack_results_kernel<<<x->S * x->tcap, 64, 0, x->stream>>>(x->d_scenes, x->d_tracks, x->d_keypoints, x->S, x->tcap,
+    pack_results_kernel<<<x->S, 256, 0, x->stream>>>(x->d_scenes, x->d_tracks, x->d_keypoints, x->S, x->tcap,
                                                               x->d_results[r], fc);
     CK(cudaGetLastError());
     x->launches++;

@@ -5,18 +5,18 @@
 // bf16 terms, a = a_hi + a_lo, w = w_hi + w_lo, and three products are accumulated in fp32 in TMEM:
 //     a_hi*w_hi + a_lo*w_hi + a_hi*w_lo            (the dropped a_lo*w_lo term is ~2^-16 relative)
 //
-// Convolutions (conv_tc_kernel): TMA-im2col implicit GEMM.  Activations live in HBM channels-last with the hi and
-// lo halves interleaved per position, [row][d][h][w][hi c.. | lo c..], so ONE tensor-map box {C', 8, 8, 1, 1} at
-// coordinates (0, kw-1, kh-1, d+kd-1, row) is the im2col column block of tap (kd,kh,kw) for a whole 8x8 slice --
-// 'same' zero padding comes from TMA out-of-bounds fill.  An M=128 tile is two d-slices.  Per tap the B operand is
-// the K' x N' matrix [[W_hi | W_lo], [W_hi | 0]], so one MMA chain produces a*W_hi in columns [0,C) and a_hi*W_lo
-// in columns [C,2C); the epilogue adds the two halves, bias, ReLU (+ BatchNorm after conv2) and writes the next
-// layer's split operand directly.  No thread ever touches an operand byte.
+// Convolutions (conv_slab_kernel): shifted-window implicit GEMM -- every tap is a tcgen05.mma on a shifted
+// shared-memory descriptor of a slab staged once per sample and kh (details at the kernel).  Per tap the B operand is
+// the K' x N' matrix [[W_hi | W_lo], [W_hi | 0]], so one MMA chain produces a*W_hi in columns [0,C) and a_hi*W_lo in
+// columns [C,2C); the epilogue adds the two halves, bias, ReLU (+ BatchNorm after conv2) and writes the next layer's
+// split operand directly.
 //
-// Dense layers (gemm_tc_kernel): 128 x BN tiles, K blocks of 64 (SWIZZLE_128B); each pipeline stage holds the four
-// operand tiles {A_hi, A_lo, W_hi, W_lo} of one K block (loaded once, used by three MMAs per 16-wide K step).
+// Dense layers: 128 x BN tiles (gemm_tc_kernel) or 256 x BN tiles on CTA pairs (gemm_tc_pair_kernel,
+// tcgen05.mma.cta_group::2), K blocks of 64 (SWIZZLE_128B); each pipeline stage holds the four operand tiles
+// {A_hi, A_lo, W_hi, W_lo} of one K block (loaded once by TMA, used by three MMAs per 16-wide K step).
 //
-// Warp roles in both kernels: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue.
+// Warp roles in the dense kernels: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue.
+// All kernels are links of the step's programmatic-dependent-launch chain (mmw_internal.cuh).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdio>
@@ -56,14 +56,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
             "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
-        "[%2];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -812,7 +804,7 @@ struct TcImpl {
     __nv_bfloat16 *h_hi = nullptr, *h_lo = nullptr;                   // dense-2 operand [rows_pad][H]
     __nv_bfloat16 *w1b = nullptr, *w2b = nullptr;                     // conv B matrices [taps][NOUT][CK]
     __nv_bfloat16 *wd1_hi = nullptr, *wd1_lo = nullptr, *wd2_hi = nullptr, *wd2_lo = nullptr;
-    CUtensorMap m_in, m_act1, m_w1b, m_w2b, m_ah, m_al, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l, m_w1h_half, m_w1l_half;
+    CUtensorMap m_w1b, m_w2b, m_ah, m_al, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l, m_w1h_half, m_w1l_half;
     int dbg = 0;
     int pair = 0;                                                     // dense 1 on CTA pairs (cta_group::2): stages, 0 = off
 };
@@ -851,20 +843,6 @@ static int make_map_2d(CUtensorMap* m, void* base, uint64_t rows, uint64_t K, ui
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swz((int)box_k * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(2d) failed (" + std::to_string((int)r) + ")"; return -1; }
-    return 0;
-}
-
-// 5-D channels-last activation [rows][D][8][8][C] bf16, box {C, 8, 8, 1, 1}: one 8x8 slice of one tap.
-static int make_map_act(CUtensorMap* m, void* base, uint64_t rows, int D, int C) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) { g_tc_err = "cuTensorMapEncodeTiled not available"; return -1; }
-    cuuint64_t dims[5] = {(cuuint64_t)C, 8, 8, (cuuint64_t)D, rows};
-    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * 8, (cuuint64_t)C * 2 * 64, (cuuint64_t)C * 2 * 64 * D};
-    cuuint32_t box[5] = {(cuuint32_t)C, 8, 8, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swz(C * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled(5d) failed (" + std::to_string((int)r) + ")"; return -1; }
     return 0;
 }
 

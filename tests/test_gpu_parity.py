@@ -298,3 +298,48 @@ def test_pipelined_results_match_blocking_readback():
                 (cx, cz), size = mo.fade_square(tr[s, k]["x"], tr[s, k]["keypoints"])
                 np.testing.assert_array_equal(got[s, k, 68:71], np.array([cx, cz, size]).astype(np.float32))
             assert np.all(got[s, nt[s]:, 0] == -1)
+
+
+# ---- alternative code paths selected by environment switches give the same results -------------------------
+def _run_with_env(env, S=48, F=14):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        batches = synth.gen_batch(list(range(100, 100 + S)), F)
+        bt = BatchedTracker(S)                                  # MMW_POSE_INDEX_FOLD is read at creation,
+        bt.load_pose_weights(pw.make_pose_weights(pw.VARIANT_3D))   # MMW_FC1_PAIR when the weights are loaded
+        for b in batches:
+            bt.step(b.points, b.offsets, b.dt, pose=True)
+        tr, nt = bt.tracks()
+        si, ti, feats = bt.pose_rows()
+        return tr, nt, si, ti, feats
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_pose_row_scan_folded_vs_separate_kernel():
+    """The pose-row scan inside pose_feature_kernel (default, S <= 4096) and pose_index_kernel (S > 4096) lay the
+    rows out identically."""
+    a = _run_with_env({"MMW_POSE_INDEX_FOLD": "1"})
+    b = _run_with_env({"MMW_POSE_INDEX_FOLD": "0"})
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[2], b[2])
+    np.testing.assert_array_equal(a[3], b[3])
+    np.testing.assert_array_equal(a[4], b[4])
+    for name in ("id", "x", "P", "keypoints"):
+        np.testing.assert_array_equal(a[0][name], b[0][name])
+
+
+def test_dense1_cta_pair_vs_single_cta_kernel():
+    """tcgen05.mma.cta_group::2 (default) and the single-CTA dense-1 kernel accumulate the same bf16x3 products in
+    fp32: joints agree far inside the 1 mm bar."""
+    a = _run_with_env({"MMW_FC1_PAIR": "3"})
+    b = _run_with_env({"MMW_FC1_PAIR": "0"})
+    np.testing.assert_array_equal(a[1], b[1])
+    assert a[1].sum() > 40
+    for s in range(len(a[1])):
+        np.testing.assert_allclose(a[0]["keypoints"][s, :a[1][s]], b[0]["keypoints"][s, :b[1][s]], rtol=0, atol=2e-5)
