@@ -106,6 +106,15 @@ int mmw_abi_version(void);
 /* Resets every scene to the state of a fresh TrackBuffer() + BatchedData() (Tracking.py:504-511, 38-41). */
 int mmw_reset(mmw_ctx* ctx);
 
+/* Checkpoint / resume of the tracker state of all scenes (track records, rings, keypoints, id counters): what a
+ * replay needs to continue bit-identically in this or another context created with the same n_scenes,
+ * max_points_per_frame, max_tracks and frames_batch (e.g. on another GPU).  mmw_state_size() = bytes of the blob;
+ * dump / restore take a HOST buffer of at least that size and are synchronous.  The reference has no equivalent
+ * (its state lives in Python objects for the length of the process); pose weights are not part of the blob. */
+size_t mmw_state_size(mmw_ctx* ctx);
+int mmw_state_dump(mmw_ctx* ctx, void* host_blob, size_t bytes);
+int mmw_state_restore(mmw_ctx* ctx, const void* host_blob, size_t bytes);
+
 /*
  * Loads the keypoint regressor's weights (replaces keras load_model, offline_main.py:33).
  * blob = concatenation of Keras model.get_weights() flattened, fp32 (see mmwave_msc_b200/pose_weights.py).
@@ -224,6 +233,23 @@ int mmw_gate(mmw_ctx* ctx, const double* points, int M, const double* hx, const 
 
 /* Keras model.predict (Tracking.py:732): feats [n, (frames_batch+1)*64*5] fp32 -> keypoints [n,57] fp32. */
 int mmw_pose(mmw_ctx* ctx, const float* feats, int n, float* keypoints);
+
+/* ---- sensor wire format ---- */
+
+/* Decodes n framed xWR14xx UART packets (each starts with the magic word 02 01 04 03 06 05 08 07) into the ragged
+ * fp32 point batch mmw_step takes: what ReadIWR14xx.read (ReadDataIWR1443.py:88-201) extracts from one packet --
+ * header, the first TLV if numDetectedObj > 0 and its type is 1 (detected points), objects as six little-endian
+ * 16-bit two's-complement words (rangeIdx, dopplerIdx, peakVal, x, y, z), the dopplerIdx correction of :167-175 with
+ * the int16 semantics of the reference's numpy 1.26, x y z / 2^xyzQFormat, doppler = dopplerIdx * doppler_res.
+ * Finding the packets in a byte stream (magic-word search, waiting for totalPacketLen bytes) stays with the caller.
+ *   packets, packet_offsets[n+1]  concatenated packet bytes and their boundaries (host)
+ *   points [max_points_total][5]  x y z doppler peakVal (host); point_offsets[n+1]; frame_numbers[n];
+ *   data_ok[n] = the reference's dataOK (0: no object, other TLV type, truncated or bad magic -> no points)
+ * PARITY UNPINNED: the reference decoder cannot run under numpy >= 2; the oracle
+ * (oracle/tlv_oracle.py) restates it.  Synchronous. */
+int mmw_decode_tlv(mmw_ctx* ctx, const uint8_t* packets, const int64_t* packet_offsets, int n_packets,
+                   double num_doppler_bins, double doppler_res, float* points, size_t max_points_total,
+                   int32_t* point_offsets, int32_t* frame_numbers, int32_t* data_ok);
 
 /* ---- dataset-builder mode ---- */
 

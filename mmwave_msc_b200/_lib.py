@@ -74,6 +74,9 @@ SIGNATURES = {
     "mmw_create": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
     "mmw_destroy": (C.c_int, [_p]),
     "mmw_reset": (C.c_int, [_p]),
+    "mmw_state_size": (C.c_size_t, [_p]),
+    "mmw_state_dump": (C.c_int, [_p, _p, C.c_size_t]),
+    "mmw_state_restore": (C.c_int, [_p, _p, C.c_size_t]),
     "mmw_load_pose_weights": (C.c_int, [_p, C.c_int, _p, C.c_size_t]),
     "mmw_step": (C.c_int, [_p, _p, _p, _p, C.c_uint32]),
     "mmw_estimate_posture": (C.c_int, [_p]),
@@ -96,6 +99,7 @@ SIGNATURES = {
     "mmw_kalman_update": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int]),
     "mmw_gate": (C.c_int, [_p, _p, C.c_int, _p, _p, C.c_int, _p, _p]),
     "mmw_pose": (C.c_int, [_p, _p, C.c_int, _p]),
+    "mmw_decode_tlv": (C.c_int, [_p, _p, _p, C.c_int, C.c_double, C.c_double, _p, C.c_size_t, _p, _p, _p]),
     "mmw_export_track0": (C.c_int, [_p, _p, _p, _p]),
     "mmw_pack_results": (C.c_int, [_p, _p]),
     "mmw_read_results_async": (C.c_int, [_p, _p, C.POINTER(C.c_int)]),

@@ -227,6 +227,34 @@ class BatchedTracker:
     def launch_count(self) -> int:
         return int(self.lib.mmw_launch_count(self._h))
 
+    def decode_tlv(self, packets, num_doppler_bins: float, doppler_res: float):
+        """Framed xWR14xx UART packets (list of bytes) -> (points (sum N, 5) float32, offsets (n+1,) int32,
+        frame_numbers (n,), data_ok (n,) bool): ReadIWR14xx.read's decode of each packet (ReadDataIWR1443.py:88-201),
+        in the ragged layout step() takes."""
+        n = len(packets)
+        offs = np.zeros(n + 1, np.int64)
+        offs[1:] = np.cumsum([len(p) for p in packets])
+        blob = np.frombuffer(b"".join(packets), dtype=np.uint8) if offs[-1] else np.zeros(1, np.uint8)
+        cap = int(max(0, (int(offs[-1]) - 48 * n) // 12 + n))          # 12 bytes per object after the headers
+        points = np.zeros((max(cap, 1), 5), np.float32)
+        poff = np.zeros(n + 1, np.int32)
+        frames = np.zeros(max(n, 1), np.int32)
+        ok = np.zeros(max(n, 1), np.int32)
+        _lib.check(self.lib.mmw_decode_tlv(self._h, _lib.ptr(np.ascontiguousarray(blob)), _lib.ptr(offs), n,
+                                           float(num_doppler_bins), float(doppler_res), _lib.ptr(points),
+                                           points.shape[0], _lib.ptr(poff), _lib.ptr(frames), _lib.ptr(ok)))
+        return points[:poff[-1]], poff, frames[:n], ok[:n].astype(bool)
+
+    def state_dump(self) -> np.ndarray:
+        """Tracker state of all scenes as one uint8 blob (mmw_state_dump): checkpoint of a replay."""
+        blob = np.zeros(int(self.lib.mmw_state_size(self._h)), np.uint8)
+        _lib.check(self.lib.mmw_state_dump(self._h, _lib.ptr(blob), blob.size))
+        return blob
+
+    def state_restore(self, blob: np.ndarray):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        _lib.check(self.lib.mmw_state_restore(self._h, _lib.ptr(blob), blob.size))
+
     def export_track0(self):
         """Dataset-builder export (preprocessing.py:185-216): (rows [S,192,5] float64, valid [S] bool,
         centroid [S,2]) of track 0 of every scene after the last step."""

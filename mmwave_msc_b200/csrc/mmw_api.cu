@@ -1,5 +1,6 @@
 // C ABI of libmmw.so (include/mmw.h): context management, the per-frame step, readback, and the
 // stage-level entry points.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -190,6 +191,71 @@ int mmw_reset(mmw_ctx* x) {
     CK(cudaMemsetAsync(x->d_assoc, 0xff, sizeof(int32_t) * (size_t)x->S * x->ncap, x->stream));
     CK(cudaMemsetAsync(x->d_pose_total, 0, sizeof(int), x->stream));
     CK(cudaMemsetAsync(x->d_defer, 0, sizeof(int32_t) * (1 + 2 * (size_t)x->S), x->stream));
+    return MMW_OK;
+}
+
+// ---- checkpoint / resume -------------------------------------------------------------------------
+namespace {
+struct StateHeader {
+    uint32_t magic, abi;
+    int32_t S, ncap, tcap, ring_size;
+    uint64_t bytes;
+};
+constexpr uint32_t kStateMagic = 0x4d4d5753u;   // "MMWS"
+struct StatePart { void* dev; size_t bytes; };
+std::vector<StatePart> state_parts(mmw_ctx* x) {
+    const size_t S = x->S;
+    return {{x->d_scenes, sizeof(SceneRec) * S},
+            {x->d_tracks, sizeof(TrackRec) * S * x->tcap},
+            {x->d_track_ring, sizeof(float) * S * x->tcap * kRing * kFeatPts * kRawCols},
+            {x->d_uring, sizeof(float) * S * kRing * x->ncap * kRawCols},
+            {x->d_keypoints, sizeof(float) * S * x->tcap * kKp},
+            {x->d_defer + 1 + S, sizeof(int32_t) * S}};                 // pose rows per scene of the last frame
+}
+}  // namespace
+
+size_t mmw_state_size(mmw_ctx* x) {
+    if (!x) return 0;
+    size_t n = sizeof(StateHeader);
+    for (const StatePart& p : state_parts(x)) n += p.bytes;
+    return n;
+}
+
+int mmw_state_dump(mmw_ctx* x, void* host_blob, size_t bytes) {
+    if (!x || !host_blob) return fail(MMW_ERR_INVALID, "ctx/host_blob is NULL");
+    const size_t need = mmw_state_size(x);
+    if (bytes < need) return fail(MMW_ERR_CAPACITY, "state blob buffer is smaller than mmw_state_size()");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    StateHeader h{kStateMagic, MMW_ABI_VERSION, x->S, x->ncap, x->tcap, x->dc.ring_size, (uint64_t)need};
+    unsigned char* o = static_cast<unsigned char*>(host_blob);
+    std::memcpy(o, &h, sizeof(h));
+    o += sizeof(h);
+    for (const StatePart& p : state_parts(x)) {
+        CK(cudaMemcpy(o, p.dev, p.bytes, cudaMemcpyDeviceToHost));
+        o += p.bytes;
+    }
+    return MMW_OK;
+}
+
+int mmw_state_restore(mmw_ctx* x, const void* host_blob, size_t bytes) {
+    if (!x || !host_blob) return fail(MMW_ERR_INVALID, "ctx/host_blob is NULL");
+    StateHeader h;
+    if (bytes < sizeof(h)) return fail(MMW_ERR_INVALID, "state blob is truncated");
+    std::memcpy(&h, host_blob, sizeof(h));
+    if (h.magic != kStateMagic || h.abi != MMW_ABI_VERSION)
+        return fail(MMW_ERR_INVALID, "not a state blob of this library version");
+    if (h.S != x->S || h.ncap != x->ncap || h.tcap != x->tcap || h.ring_size != x->dc.ring_size)
+        return fail(MMW_ERR_INVALID, "state blob was taken from a context of another shape "
+                                     "(n_scenes / max_points_per_frame / max_tracks / frames_batch)");
+    if (h.bytes != mmw_state_size(x) || bytes < h.bytes) return fail(MMW_ERR_INVALID, "state blob is truncated");
+    CK(cudaSetDevice(x->device));
+    CK(mmw_sync(x) == MMW_OK ? cudaSuccess : cudaErrorUnknown);
+    const unsigned char* o = static_cast<const unsigned char*>(host_blob) + sizeof(h);
+    for (const StatePart& p : state_parts(x)) {
+        CK(cudaMemcpy(p.dev, o, p.bytes, cudaMemcpyHostToDevice));
+        o += p.bytes;
+    }
     return MMW_OK;
 }
 
@@ -753,6 +819,64 @@ __device__ __forceinline__ void projection_point(const FadeCfg& f, double xo, do
     zp = (zd == 0.0) ? zo : (-f.m_y / (yd / zd)) + f.m_z;
 }
 
+// ---- UART TLV packets -> fp32 point rows (ReadDataIWR1443.py:88-201) ------------------------------------
+constexpr int kTlvHeader = 36;
+__device__ __forceinline__ uint32_t rd_u32(const uint8_t* p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ int rd_i16(const uint8_t* p) { return (int)(int16_t)((uint16_t)p[0] | ((uint16_t)p[1] << 8)); }
+
+// Number of objects a packet yields (0 when the reference would return dataOK = 0) and its frame number.
+__device__ __forceinline__ int tlv_packet_objects(const uint8_t* p, long long len, int* frame) {
+    const uint8_t magic[8] = {2, 1, 4, 3, 6, 5, 8, 7};
+    *frame = 0;
+    if (len < kTlvHeader) return 0;
+    for (int i = 0; i < 8; ++i)
+        if (p[i] != magic[i]) return 0;
+    const uint32_t total = rd_u32(p + 12);
+    if ((unsigned long long)len < total) return 0;                       // incomplete packet (:81-83)
+    *frame = (int)rd_u32(p + 20);
+    if (rd_u32(p + 28) == 0) return 0;                                   // numDetectedObj (:106)
+    if (len < kTlvHeader + 12) return 0;
+    if (rd_u32(p + kTlvHeader) != 1u) return 0;                          // MMWDEMO_UART_MSG_DETECTED_POINTS (:115)
+    const int n_obj = (int)((uint32_t)p[kTlvHeader + 8] | ((uint32_t)p[kTlvHeader + 9] << 8));
+    if (len < kTlvHeader + 12 + 12LL * n_obj) return 0;
+    return n_obj;
+}
+
+__global__ void tlv_count_kernel(const uint8_t* bytes, const long long* off, int n, int32_t* counts, int32_t* frames) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int fr;
+    counts[i] = tlv_packet_objects(bytes + off[i], off[i + 1] - off[i], &fr);
+    frames[i] = fr;
+}
+
+// One warp per packet, one lane per object (12 bytes in, 20 bytes out).
+__global__ void __launch_bounds__(256) tlv_decode_kernel(const uint8_t* bytes, const long long* off, int n,
+                                                         const int32_t* point_off, double half_bins_m1,
+                                                         double doppler_res, float* points) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const int n_obj = point_off[w + 1] - point_off[w];
+    if (n_obj == 0) return;
+    const uint8_t* p = bytes + off[w];
+    const int q = (int)((uint32_t)p[kTlvHeader + 10] | ((uint32_t)p[kTlvHeader + 11] << 8));
+    const double scale = exp2((double)q);                                // 2 ** xyzQFormat (:126-128)
+    const uint8_t* body = p + kTlvHeader + 12;
+    float* o = points + (size_t)point_off[w] * kRawCols;
+    for (int j = lane; j < n_obj; j += 32) {
+        const uint8_t* b = body + 12 * j;
+        int dop = rd_i16(b + 2);
+        if ((double)dop > half_bins_m1) dop = (int)(int16_t)(dop - 65535);   // :167-175 on int16 data (numpy 1.26 wrap)
+        o[j * kRawCols + 0] = (float)((double)rd_i16(b + 6) / scale);
+        o[j * kRawCols + 1] = (float)((double)rd_i16(b + 8) / scale);
+        o[j * kRawCols + 2] = (float)((double)rd_i16(b + 10) / scale);
+        o[j * kRawCols + 3] = (float)((double)dop * doppler_res);
+        o[j * kRawCols + 4] = (float)rd_i16(b + 4);
+    }
+}
+
 // Dataset-builder export of track 0 (preprocessing.py:185-216; Utils.relative_coordinates :437-465 and
 // format_batched_frames :523-548): ring frames newest first, [x - cx, y - cy, z, doppler, peakVal] of the first 64
 // rows per frame in float64, zero padded, unsorted, raw intensity.  One CTA of 64 threads per scene.
@@ -828,6 +952,60 @@ __global__ void __launch_bounds__(256) pack_results_kernel(const SceneRec* scene
 }  // namespace mmw
 
 extern "C" {
+
+int mmw_decode_tlv(mmw_ctx* x, const uint8_t* packets, const int64_t* packet_offsets, int n, double num_doppler_bins,
+                   double doppler_res, float* points, size_t max_points_total, int32_t* point_offsets,
+                   int32_t* frame_numbers, int32_t* data_ok) {
+    if (!x || !packet_offsets || !point_offsets || !frame_numbers || !data_ok)
+        return fail(MMW_ERR_INVALID, "NULL argument");
+    if (n < 0 || packet_offsets[0] != 0) return fail(MMW_ERR_INVALID, "n_packets >= 0 and packet_offsets[0] == 0 required");
+    point_offsets[0] = 0;
+    if (n == 0) return MMW_OK;
+    const size_t nbytes = (size_t)packet_offsets[n];
+    if (nbytes && !packets) return fail(MMW_ERR_INVALID, "packets is NULL");
+    CK(cudaSetDevice(x->device));
+    uint8_t* d_bytes = nullptr; long long* d_off = nullptr; int32_t *d_cnt = nullptr, *d_fr = nullptr, *d_poff = nullptr;
+    float* d_pts = nullptr;
+    auto cleanup = [&]() { for (void* p : {(void*)d_bytes, (void*)d_off, (void*)d_cnt, (void*)d_fr, (void*)d_poff, (void*)d_pts}) if (p) cudaFree(p); };
+#define TLV_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); return fail(MMW_ERR_CUDA, std::string(#expr ": ") + cudaGetErrorString(e__)); } } while (0)
+    TLV_CK(cudaMalloc((void**)&d_bytes, nbytes ? nbytes : 1));
+    TLV_CK(cudaMalloc((void**)&d_off, sizeof(long long) * (n + 1)));
+    TLV_CK(cudaMalloc((void**)&d_cnt, sizeof(int32_t) * n));
+    TLV_CK(cudaMalloc((void**)&d_fr, sizeof(int32_t) * n));
+    TLV_CK(cudaMalloc((void**)&d_poff, sizeof(int32_t) * (n + 1)));
+    TLV_CK(cudaMemcpyAsync(d_bytes, packets, nbytes, cudaMemcpyHostToDevice, x->stream));
+    TLV_CK(cudaMemcpyAsync(d_off, packet_offsets, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, x->stream));
+    tlv_count_kernel<<<(n + 255) / 256, 256, 0, x->stream>>>(d_bytes, d_off, n, d_cnt, d_fr);
+    TLV_CK(cudaGetLastError());
+    std::vector<int32_t> cnt(n);
+    TLV_CK(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, x->stream));
+    TLV_CK(cudaMemcpyAsync(frame_numbers, d_fr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, x->stream));
+    TLV_CK(cudaStreamSynchronize(x->stream));
+    x->launches++;
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        data_ok[i] = cnt[i] > 0 ? 1 : 0;
+        total += (size_t)cnt[i];
+        if (total > (size_t)INT32_MAX) { cleanup(); return fail(MMW_ERR_CAPACITY, "more than 2^31 points"); }
+        point_offsets[i + 1] = (int32_t)total;
+    }
+    if (total > max_points_total) { cleanup(); return fail(MMW_ERR_CAPACITY, "points buffer too small for the decoded packets"); }
+    if (total > 0) {
+        if (!points) { cleanup(); return fail(MMW_ERR_INVALID, "points is NULL"); }
+        TLV_CK(cudaMalloc((void**)&d_pts, sizeof(float) * kRawCols * total));
+        TLV_CK(cudaMemcpyAsync(d_poff, point_offsets, sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice, x->stream));
+        const long long threads = 32LL * n;
+        tlv_decode_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, x->stream>>>(
+            d_bytes, d_off, n, d_poff, num_doppler_bins / 2 - 1, doppler_res, d_pts);
+        TLV_CK(cudaGetLastError());
+        x->launches++;
+        TLV_CK(cudaMemcpyAsync(points, d_pts, sizeof(float) * kRawCols * total, cudaMemcpyDeviceToHost, x->stream));
+        TLV_CK(cudaStreamSynchronize(x->stream));
+    }
+#undef TLV_CK
+    cleanup();
+    return MMW_OK;
+}
 
 int mmw_export_track0(mmw_ctx* x, double* rows, int32_t* valid, double* centroid) {
     if (!x || !rows || !valid) return fail(MMW_ERR_INVALID, "ctx/rows/valid is NULL");

@@ -343,3 +343,32 @@ def test_dense1_cta_pair_vs_single_cta_kernel():
     assert a[1].sum() > 40
     for s in range(len(a[1])):
         np.testing.assert_allclose(a[0]["keypoints"][s, :a[1][s]], b[0]["keypoints"][s, :b[1][s]], rtol=0, atol=2e-5)
+
+
+# ---- checkpoint / resume -----------------------------------------------------------------------------------
+def test_state_dump_restore_continues_bit_identically():
+    S, F0, F1 = 40, 20, 12
+    batches = synth.gen_batch(list(range(300, 300 + S)), F0 + F1)
+    W = pw.make_pose_weights(pw.VARIANT_3D)
+    a = BatchedTracker(S)
+    a.load_pose_weights(W)
+    for b in batches[:F0]:
+        a.step(b.points, b.offsets, b.dt, pose=True)
+    blob = a.state_dump()
+    c = BatchedTracker(S)                       # a fresh context resumes from the blob
+    c.load_pose_weights(W)
+    c.state_restore(blob)
+    for b in batches[F0:]:
+        a.step(b.points, b.offsets, b.dt, pose=True)
+        c.step(b.points, b.offsets, b.dt, pose=True)
+        np.testing.assert_array_equal(a.point_assoc(), c.point_assoc())
+    ta, na = a.tracks()
+    tc_, nc = c.tracks()
+    np.testing.assert_array_equal(na, nc)
+    assert na.sum() > 40
+    assert ta.tobytes() == tc_.tobytes()
+    np.testing.assert_array_equal(a.ring_counts(), c.ring_counts())
+    # a blob of another shape is refused
+    d = BatchedTracker(S + 1)
+    with pytest.raises(_lib.MmwError):
+        d.state_restore(blob)
