@@ -268,25 +268,20 @@ __device__ inline int bits_components_and_ids(int B, int W, const unsigned* adj,
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
+        __syncwarp();                                                    // every lane has read par[b] above
         if (lane == 0) par[b] = m;                                       // m <= b: b is its own neighbour
     }
     __syncthreads();
+    // Race-free by construction: a propagation pass reads the labels in par and writes the new ones to cl, the
+    // pointer-jumping pass reads cl (chains strictly decrease until a fixed point) and writes par.
     while (true) {
-        for (int b = tid; b < B; b += nt) {                              // pointer jumping (parents only decrease)
-            int l = ((volatile int*)par)[b];
-            if (l < 0) continue;
-            while (true) {
-                const int p = ((volatile int*)par)[l];
-                if (p == l) break;
-                l = p;
-            }
-            if (l < ((volatile int*)par)[b]) atomicMin(&par[b], l);
-        }
-        __syncthreads();
         int changed = 0;
         for (int b = warp; b < B; b += nw) {
-            const int cur = ((volatile int*)par)[b];
-            if (cur < 0) continue;                                       // uniform over the warp
+            const int cur = par[b];
+            if (cur < 0) {                                               // uniform over the warp
+                if (lane == 0) cl[b] = -1;
+                continue;
+            }
             int m = cur;
             for (int w0 = 0; w0 < W; w0 += 4) {
                 unsigned bits[4];
@@ -294,14 +289,23 @@ __device__ inline int bits_components_and_ids(int B, int W, const unsigned* adj,
                 for (int u = 0; u < 4; ++u) bits[u] = w0 + u < W ? (adj[b * W + w0 + u] & cm[w0 + u]) : 0u;
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if ((bits[u] >> lane) & 1u) m = min(m, ((volatile int*)par)[((w0 + u) << 5) + lane]);
+                    if ((bits[u] >> lane) & 1u) m = min(m, par[((w0 + u) << 5) + lane]);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
-            if (m < cur) {
-                if (lane == 0) atomicMin(&par[b], m);
-                changed = 1;
+            if (lane == 0) cl[b] = m;
+            changed |= m < cur ? 1 : 0;
+        }
+        __syncthreads();
+        for (int b = tid; b < B; b += nt) {
+            int l = cl[b];
+            if (l < 0) continue;
+            while (true) {
+                const int p = cl[l];
+                if (p == l) break;
+                l = p;
             }
+            par[b] = l;
         }
         if (!__syncthreads_or(changed)) break;
     }

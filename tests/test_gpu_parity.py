@@ -372,3 +372,56 @@ def test_state_dump_restore_continues_bit_identically():
     d = BatchedTracker(S + 1)
     with pytest.raises(_lib.MmwError):
         d.state_restore(blob)
+
+
+# ---- capacity limits: flagged per scene, never silent ---------------------------------------------------
+def test_point_and_track_overflow_are_flagged():
+    """More points in a frame than max_points_per_frame: the scene keeps the first max_points rows (and behaves
+    exactly like a scene that was sent only those) and raises MMW_SCENE_POINT_OVERFLOW; more clusters than free
+    track slots: MMW_SCENE_TRACK_OVERFLOW.  Other scenes of the batch are unaffected."""
+    S, F, CAP = 4, 14, 96
+    batches = synth.gen_batch([0, 1, 2, 3], F)
+    bt = BatchedTracker(S, max_points=256)
+    small = BatchedTracker(S, max_points=256)
+    for b in batches:
+        # scenes 1 and 3 get their frames truncated on the host for `small`, and through the device-side point
+        # capacity for a context whose capacity is CAP
+        bt.step(b.points, b.offsets, b.dt, pose=False)
+    trunc = BatchedTracker(S, max_points=CAP)
+    oracles = [mo.SceneOracle() for _ in range(S)]
+    for b in batches:
+        parts = [b.points[b.offsets[s]:b.offsets[s + 1]] for s in range(S)]
+        # the host API refuses a batch that cannot fit the context at all ...
+        cut = [p[:CAP] for p in parts]
+        off = np.zeros(S + 1, np.int32)
+        off[1:] = np.cumsum([len(p) for p in cut])
+        small.step(np.concatenate(cut), off, b.dt, pose=False)
+        recs = [o.step(cut[s], b.dt[s]) for s, o in enumerate(oracles)]
+        compare_frame(small, recs, off, "truncated on the host")
+    assert not small.status().any()
+    # ... and the device flags scenes whose frame exceeds the per-scene capacity (device-resident input path)
+    import torch
+    for b in batches:
+        p = torch.from_numpy(b.points).cuda()
+        o = torch.from_numpy(b.offsets).cuda()
+        d = torch.from_numpy(b.dt).cuda()
+        trunc.step_device(p.data_ptr(), o.data_ptr(), d.data_ptr(), b.points.shape[0], pose=False)
+        trunc.sync()
+    st = trunc.status()
+    assert (st & _lib.SCENE_POINT_OVERFLOW).all()               # every scene had frames of > 96 points
+    ta, na = trunc.tracks()
+    tb, nb = small.tracks()
+    np.testing.assert_array_equal(na, nb)                        # same as sending the first CAP rows
+    for name in ("id", "x", "P"):
+        np.testing.assert_array_equal(ta[name], tb[name])
+    with pytest.raises(_lib.MmwError):                           # host path: more rows than S * max_points
+        trunc.step(batches[0].points, batches[0].offsets, batches[0].dt, pose=False)
+
+    # track capacity: room for 1 track, scenes with several people
+    one = BatchedTracker(S, max_tracks=1)
+    for b in batches:
+        one.step(b.points, b.offsets, b.dt, pose=False)
+    _, n1 = one.tracks()
+    assert (n1 <= 1).all() and (one.status() & _lib.SCENE_TRACK_OVERFLOW).any()
+    _, nfull = bt.tracks()
+    assert (nfull >= n1).all() and nfull.max() > 1
