@@ -197,7 +197,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     S = args.scenes
     W_, K = args.warmup, args.steps
-    n_frames = PRIME_FRAMES + 2 * (W_ + K) + K      # device-timed pass, e2e pass, per-kernel profile pass
+    LAT_FRAMES = 12
+    n_frames = PRIME_FRAMES + 2 * (W_ + K) + K + LAT_FRAMES   # device-timed, e2e, latency and per-kernel profile passes
     ids = sharding.shard_scene_ids(world * S, world, rank)      # contiguous block of scenes per GPU
     batches = synth.gen_batch(ids, n_frames)
 
@@ -301,6 +302,40 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * S * K / float(t.item())
 
+    # ---- per-frame latency, host enqueue -> results in host memory, NOT pipelined -------------
+    lat = []
+    for i in range(LAT_FRAMES):
+        b = batches[f + i]
+        hp = (torch.from_numpy(b.points).pin_memory().numpy(), torch.from_numpy(b.offsets).pin_memory().numpy(),
+              torch.from_numpy(b.dt).pin_memory().numpy())
+        bt.sync()
+        t0 = time.perf_counter()
+        bt.step(*hp, pose=True)
+        bt.wait_results(bt.read_results_async(res_np[0]))
+        lat.append((time.perf_counter() - t0) * 1e3)
+    f += LAT_FRAMES
+    latency = {"p50_ms_step_device": float(np.median(step_ms)),
+               "p50_ms_host_enqueue_to_results": float(np.median(lat[2:])),
+               "note": "one frame of all %d scenes of this GPU; the second figure includes the upload from pinned "
+                       "memory, the kernels, the result pack and its download, nothing overlapped" % S}
+    if rank == 0:
+        # C1: a single scene, what one live 12 Hz sensor would see
+        one = BatchedTracker(1, max_points=256, max_tracks=8, device=local)
+        one.load_pose_weights(weights)
+        ob = synth.gen_batch([10_000], 40)
+        r1 = torch.empty(one.tcap * _lib.RESULT_FLOATS, dtype=torch.float32).pin_memory().numpy()
+        l1 = []
+        for b in ob:
+            hp = (torch.from_numpy(b.points).pin_memory().numpy(), torch.from_numpy(b.offsets).pin_memory().numpy(),
+                  torch.from_numpy(b.dt).pin_memory().numpy())
+            one.sync()
+            t0 = time.perf_counter()
+            one.step(*hp, pose=True)
+            one.wait_results(one.read_results_async(r1))
+            l1.append((time.perf_counter() - t0) * 1e3)
+        latency["p50_ms_single_scene_host_enqueue_to_results"] = float(np.median(l1[10:]))
+        one.close()
+
     # ---- per-kernel durations (CUDA events on the library's stream around every launch) --------------------
     kern = bt.profile_kernels(lambda i: step_dev(f + i), K) if hasattr(bt, "profile_kernels") else {}
 
@@ -329,6 +364,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // K),
                     "d2h_bytes_per_step": int(res_host.numel() * 4)},
             "gpu_launches": int(launches),
+            "latency": latency,
             "clocks": clocks,
             "counters_per_step": {k: float(v) / K for k, v in zip(
                 ["scene_frames", "N", "M", "U", "Bf", "tracks", "ring_rows", "pose_rows"], cnt)},

@@ -81,9 +81,10 @@ struct NbScreened {
     int start[kRing + 1];             // first fused index of each frame
     double eps;
     float lo, hi, rw, zw;
+    const float* rawc;                // the same raw rows in fused order in shared memory, or nullptr (dbscan_big_kernel)
     __device__ __forceinline__ void world(int b, double& x, double& y, double& z) const {
         const int f = (b >= start[1] ? 1 : 0) + (b >= start[2] ? 1 : 0);
-        const float* r = frame[f] + (size_t)(b - start[f]) * kRawCols;
+        const float* r = rawc != nullptr ? rawc + (size_t)b * kRawCols : frame[f] + (size_t)(b - start[f]) * kRawCols;
         x = (double)r[0];
         world_yz(c, (double)r[1], (double)r[2], y, z);
     }
@@ -153,6 +154,8 @@ __device__ inline int dbscan_block(const Nb& nb_full, int B, int min_samples, in
     };
     // 1. neighbour counts: |{q : d(p,q) <= eps}| including p.  One integer atomic per (row, chunk) with a hit and
     //    one per lane and chunk -- order-independent, so the counts (and everything below) are deterministic.
+    //    (Register-resident 32 x 32 tiles of the upper triangle, as in dbscan_bits_block, were measured here too:
+    //    slower with the step kernel's four warps -- 18.9 k against 15.4 k cycles per scene-frame.)
     for (int b = tid; b < B; b += nt) par[b] = 1;                      // a point is its own neighbour
     __syncthreads();
     {
@@ -254,8 +257,16 @@ __device__ inline int dbscan_block(const Nb& nb_full, int B, int min_samples, in
 // On entry par[b] = b for core points and -1 otherwise, cm = core bit mask, adj rows valid for every core point.
 // On return cl[b] = cluster id of core point b (-1 for the others) and the number of clusters is returned.
 __device__ inline int bits_components_and_ids(int B, int W, const unsigned* adj, const unsigned* cm, unsigned* rm,
-                                              int* par, int* cl) {
+                                              int* par, int* cl, unsigned long long* dbg = nullptr) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    long long dbg_t = clock64();
+    auto stamp = [&](int k) {                                            // debug accounting (mmw_dbscan_big_clocks)
+        if (dbg != nullptr && tid == 0) {
+            const long long now = clock64();
+            atomicAdd(&dbg[k], (unsigned long long)(now - dbg_t));
+            dbg_t = now;
+        }
+    };
     // 2. components of the core-core graph.  First hop straight from the bit rows (lowest core neighbour; final
     //    already when the component is a clique, the usual person-sized blob), then min-label propagation +
     //    pointer jumping until nothing changes.
@@ -272,6 +283,22 @@ __device__ inline int bits_components_and_ids(int B, int W, const unsigned* adj,
         if (lane == 0) par[b] = m;                                       // m <= b: b is its own neighbour
     }
     __syncthreads();
+    stamp(18);
+    // The usual case is ONE person-sized blob: every core point is adjacent to the lowest core point L, the hop above
+    // has labelled them all L and nothing is left to propagate.
+    {
+        int L = -1;
+        for (int w = 0; w < W && L < 0; ++w)
+            if (cm[w]) L = (w << 5) + __ffs(cm[w]) - 1;
+        int star = 1;
+        for (int b = tid; b < B; b += nt) star &= (par[b] < 0 || par[b] == L) ? 1 : 0;
+        star = __syncthreads_and(star);
+        stamp(19);
+        if (star) {
+            if (dbg != nullptr && tid == 0) atomicAdd(&dbg[22], 1ull);
+            goto labelled;
+        }
+    }
     // Race-free by construction: a propagation pass reads the labels in par and writes the new ones to cl, the
     // pointer-jumping pass reads cl (chains strictly decrease until a fixed point) and writes par.
     while (true) {
@@ -283,13 +310,10 @@ __device__ inline int bits_components_and_ids(int B, int W, const unsigned* adj,
                 continue;
             }
             int m = cur;
-            for (int w0 = 0; w0 < W; w0 += 4) {
-                unsigned bits[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) bits[u] = w0 + u < W ? (adj[b * W + w0 + u] & cm[w0 + u]) : 0u;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if ((bits[u] >> lane) & 1u) m = min(m, par[((w0 + u) << 5) + lane]);
+#pragma unroll 2
+            for (int w = 0; w < W; ++w) {
+                const unsigned bits = adj[b * W + w] & cm[w];
+                if ((bits >> lane) & 1u) m = min(m, par[(w << 5) + lane]);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
@@ -307,8 +331,11 @@ __device__ inline int bits_components_and_ids(int B, int W, const unsigned* adj,
             }
             par[b] = l;
         }
+        if (dbg != nullptr && tid == 0) atomicAdd(&dbg[23], 1ull);          // propagation passes
         if (!__syncthreads_or(changed)) break;
     }
+    stamp(20);
+labelled:
     // 3. cluster ids: rank of the root among the roots, ascending index
     for (int w = warp; w < W; w += nw) {
         const int b = (w << 5) + lane;
@@ -344,43 +371,47 @@ __device__ inline int dbscan_bits_block(const NbScreened& nbf, int B, int min_sa
             dbg_t = now;
         }
     };
-    // 1. adjacency rows and neighbour counts.  Four words of a row are in flight at once; the fp32 screen decides
-    //    almost every pair, the few inside the guard band are settled exactly afterwards (same decisions as
-    //    NbScreened::Hot, see there).
+    // 1. adjacency rows, by 32 x 32 tiles of the upper triangle (the predicate is symmetric): a warp owns tile (I, J),
+    //    I <= J; lane = column q of word J with its coordinates in registers, the 32 rows b of block I are broadcast
+    //    from shared memory.  A row step gives word adj[b][J] by ballot; each lane collects its own hits over the rows,
+    //    which is the transposed word adj[q][I].  The fp32 screen decides almost every pair, the few inside the guard
+    //    band are settled exactly (same decisions as NbScreened::Hot, see there).
     {
         const float *X = nbf.Xf, *Y = nbf.Yf, *Z = nbf.Zf;
         const float lo = nbf.lo, hi = nbf.hi, rw = nbf.rw, zw = nbf.zw;
-        for (int b = warp; b < B; b += nw) {
-            const float xb = X[b], yb = Y[b], zb = Z[b];
-            int cnt = 0;
-            for (int w0 = 0; w0 < W; w0 += 4) {
-                float d[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int q = ((w0 + u) << 5) + lane;
-                    const bool live = q < B;                              // q < B implies w0 + u < W
-                    const float xq = live ? X[q] : 0.f, yq = live ? Y[q] : 0.f, zq = live ? Z[q] : 0.f;
-                    const float wgt = 1.f - 0.5f * (yb + yq) * rw;
-                    const float dx = xb - xq, dy = yb - yq, dz = zb - zq;
-                    d[u] = live ? wgt * (dx * dx + dy * dy + zw * (dz * dz)) : INFINITY;
+        const int ntiles = W * (W + 1) / 2;
+        for (int t = warp; t < ntiles; t += nw) {
+            int I = 0, rem = t;
+            while (rem >= W - I) { rem -= W - I; ++I; }
+            const int J = I + rem;
+            const int q = (J << 5) + lane;
+            const bool qlive = q < B;
+            const float xq = qlive ? X[q] : 0.f, yq = qlive ? Y[q] : 0.f, zq = qlive ? Z[q] : 0.f;
+            const int b0 = I << 5, bn = min(32, B - b0);
+            unsigned tb = 0;
+            for (int r = 0; r < bn; ++r) {
+                const int b = b0 + r;
+                const float yb = Y[b];
+                const float wgt = 1.f - 0.5f * (yb + yq) * rw;
+                const float dx = X[b] - xq, dy = yb - yq, dz = Z[b] - zq;
+                const float d = wgt * (dx * dx + dy * dy + zw * (dz * dz));
+                bool hit = qlive && (d < lo || q == b);
+                const bool unsure = qlive && !(d > hi) && !hit;           // inside the band, or not finite
+                if (__any_sync(kFullMask, unsure)) {
+                    if (unsure) hit = nbf.exact(b, q);
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int w = w0 + u;
-                    if (w >= W) break;                                    // uniform over the warp
-                    const int q = (w << 5) + lane;
-                    bool hit = d[u] < lo;
-                    const bool unsure = q < B && !(d[u] > hi) && !hit;    // inside the band, or not finite
-                    if (__any_sync(kFullMask, unsure)) {
-                        if (unsure) hit = nbf.exact(b, q);
-                    }
-                    const unsigned m = __ballot_sync(kFullMask, hit);
-                    if (lane == 0) adj[b * W + w] = m;
-                    cnt += __popc(m);
-                }
+                const unsigned m = __ballot_sync(kFullMask, hit);
+                if (lane == 0) adj[b * W + J] = m;
+                tb |= (hit ? 1u : 0u) << r;
             }
-            if (lane == 0) par[b] = cnt >= min_samples ? b : -1;       // core points start as their own label
+            if (I != J && qlive) adj[q * W + I] = tb;
         }
+    }
+    __syncthreads();
+    for (int b = tid; b < B; b += nt) {                                // neighbour counts -> core points
+        int cnt = 0;
+        for (int w = 0; w < W; ++w) cnt += __popc(adj[b * W + w]);
+        par[b] = cnt >= min_samples ? b : -1;                          // core points start as their own label
     }
     __syncthreads();
     for (int w = warp; w < W; w += nw) {
@@ -397,19 +428,16 @@ __device__ inline int dbscan_bits_block(const NbScreened& nbf, int B, int min_sa
         __syncthreads();
         return 0;
     }
-    const int ncl = bits_components_and_ids(B, W, adj, cm, rm, par, cl);
+    const int ncl = bits_components_and_ids(B, W, adj, cm, rm, par, cl, dbg);
     stamp(15);
     // 4. border points: lowest-numbered cluster with a core point within eps (only labels of core points are read)
     for (int b = warp; b < B; b += nw) {
         if (par[b] >= 0) continue;                                       // uniform over the warp
         int m = 0x7fffffff;
-        for (int w0 = 0; w0 < W; w0 += 4) {
-            unsigned bits[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) bits[u] = w0 + u < W ? (adj[b * W + w0 + u] & cm[w0 + u]) : 0u;
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if ((bits[u] >> lane) & 1u) m = min(m, cl[((w0 + u) << 5) + lane]);
+#pragma unroll 2
+        for (int w = 0; w < W; ++w) {
+            const unsigned bits = adj[b * W + w] & cm[w];
+            if ((bits >> lane) & 1u) m = min(m, cl[(w << 5) + lane]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));

@@ -1263,13 +1263,13 @@ int mmw_scene_cycles(mmw_ctx* x, uint64_t* out /*[S]*/) {
     return MMW_OK;
 }
 
-int mmw_dbscan_big_clocks(mmw_ctx* x, uint64_t* out8) {
+int mmw_dbscan_big_clocks(mmw_ctx* x, uint64_t* out8 /*[16]*/) {
     if (!x || !out8) return fail(MMW_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(x->device));
     CK(cudaStreamSynchronize(x->stream));
-    unsigned long long h[8];
+    unsigned long long h[16];
     CK(cudaMemcpy(h, x->d_phase + 16 + 3 * x->S, sizeof(h), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 8; ++i) out8[i] = h[i];
+    for (int i = 0; i < 16; ++i) out8[i] = h[i];
     CK(cudaMemset(x->d_phase + 16 + 3 * x->S, 0, sizeof(h)));
     return MMW_OK;
 }

@@ -227,7 +227,7 @@ __device__ __forceinline__ NbScreened load_fused_ring(const StepArgs& a, int s, 
     float* Yf = Xf + stride;
     float* Zf = Yf + stride;
     NbScreened nb{c, Xf, Yf, Zf, {nullptr, nullptr, nullptr}, {0, 0, 0, 0}, c.db_eps, 0.f, 0.f,
-                  (float)c.db_range_weight, (float)c.db_z_weight};
+                  (float)c.db_range_weight, (float)c.db_z_weight, rawc};
     const float band = 1e-3f * (float)c.db_eps + 1e-4f;
     nb.lo = (float)c.db_eps - band;
     nb.hi = (float)c.db_eps + band;
