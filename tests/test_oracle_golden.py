@@ -132,6 +132,35 @@ def test_dbscan_semantics_small():
     assert mo.dbscan_labels(np.zeros((1, 8)), cfg).tolist() == [-1]
 
 
+def test_dbscan_oracle_against_sklearn_on_random_clouds():
+    """The oracle's labelling against the DBSCAN the reference itself calls (scikit-learn, installed in this image;
+    Utils.py:272-278) with exact neighbourhoods (algorithm="brute") and the reference's metric formula
+    (Utils.py:242-247), on clouds small and dense enough for several clusters, border ties and noise."""
+    from sklearn.cluster import DBSCAN
+    cfg = mo.OracleConfig(db_min_samples=5, db_eps=0.02)
+
+    def metric(p1, p2):
+        w = 1 - ((p1[1] + p2[1]) / 2) * cfg.db_range_weight
+        return w * ((p1[0] - p2[0]) ** 2 + (p1[1] - p2[1]) ** 2 + cfg.db_z_weight * ((p1[2] - p2[2]) ** 2))
+
+    rng = np.random.default_rng(11)
+    seen_border_choice = 0
+    for trial in range(12):
+        k = int(rng.integers(2, 6))
+        centres = rng.uniform([-1, 1, 0.5], [1, 3, 1.5], size=(k, 3))
+        pts = np.zeros((140, 8))
+        own = rng.integers(0, k, size=140)
+        pts[:, :3] = centres[own] + rng.normal(0, 0.09, size=(140, 3))
+        pts[:20, :3] = rng.uniform([-1.5, 0.5, 0], [1.5, 3.5, 2], size=(20, 3))     # clutter
+        pts[:, :3] = np.round(pts[:, :3] * 512) / 512                               # sensor lattice: exact ties occur
+        want = DBSCAN(eps=cfg.db_eps, min_samples=cfg.db_min_samples, metric=metric,
+                      algorithm="brute").fit_predict(pts[:, :3])
+        got = mo.dbscan_labels(pts, cfg)
+        np.testing.assert_array_equal(got, want, err_msg="trial %d" % trial)
+        seen_border_choice += int(want.max() >= 1)
+    assert seen_border_choice >= 6                   # most trials have at least two clusters
+
+
 def test_features_layout():
     cfg = mo.OracleConfig()
     cloud = np.zeros((70, 8))
