@@ -49,7 +49,7 @@ struct mmw_ctx {
     unsigned long long* d_counters = nullptr;
     unsigned long long* d_phase = nullptr;
     bool phase_clocks = false;
-    int32_t* d_defer = nullptr;      // [1 + S + S]: counter, the work list of dbscan_big_kernel, pose rows per scene
+    int32_t* d_defer = nullptr;      // [2 + S + S]: counter, the work list of dbscan_big_kernel, pose rows per scene, finished-CTA ticket
     bool fold_pose_index = true;     // pose-row scan inside pose_feature_kernel (S <= 4096) instead of pose_index_kernel
     // input staging (host-input path): double-buffered, copied on a side stream so that the upload of frame k+1
     // overlaps the kernels of frame k
@@ -190,7 +190,7 @@ int mmw_reset(mmw_ctx* x) {
     CK(cudaMemsetAsync(x->d_counters, 0, sizeof(unsigned long long) * 8, x->stream));
     CK(cudaMemsetAsync(x->d_assoc, 0xff, sizeof(int32_t) * (size_t)x->S * x->ncap, x->stream));
     CK(cudaMemsetAsync(x->d_pose_total, 0, sizeof(int), x->stream));
-    CK(cudaMemsetAsync(x->d_defer, 0, sizeof(int32_t) * (1 + 2 * (size_t)x->S), x->stream));
+    CK(cudaMemsetAsync(x->d_defer, 0, sizeof(int32_t) * (2 + 2 * (size_t)x->S), x->stream));
     return MMW_OK;
 }
 
@@ -304,7 +304,7 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     ALLOC(x->d_labels, sizeof(int32_t) * S * 3 * max_points);
     ALLOC(x->d_counters, sizeof(unsigned long long) * 8);
     ALLOC(x->d_phase, sizeof(unsigned long long) * (16 + 3 * S + 16));
-    ALLOC(x->d_defer, sizeof(int32_t) * (1 + 2 * S));
+    ALLOC(x->d_defer, sizeof(int32_t) * (2 + 2 * S));
     {
         const char* env = getenv("MMW_POSE_INDEX_FOLD");
         x->fold_pose_index = S <= 4096 && !(env && env[0] == '0');
@@ -490,6 +490,7 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     a.counters = x->d_counters; a.n_scenes = x->S; a.flags = flags;
     a.phase_cycles = x->phase_clocks ? x->d_phase : nullptr;
     a.defer_count = x->d_defer;
+    a.defer_done = x->d_defer + 1 + 2 * x->S;
     a.defer_list = x->d_defer + 1;
     a.pose_cnt = x->d_defer + 1 + x->S;
     prof_mark(x, MMW_K_STEP);

@@ -84,7 +84,8 @@ struct StepArgs {
     unsigned long long* counters;  // [8]
     unsigned long long* phase_cycles;  // [16 + S] or nullptr: cycles per phase of step_kernel, then cycles per scene (debug)
     int32_t* defer_list;       // [S] scenes whose DBSCAN + spawn is left to dbscan_big_kernel, or nullptr
-    int32_t* defer_count;      // device counter of defer_list (zeroed before every step)
+    int32_t* defer_count;      // device counter of defer_list; dbscan_big_kernel's last CTA zeroes it for the next step
+    int32_t* defer_done;       // CTAs of dbscan_big_kernel that have finished (ticket for that reset)
     int32_t* pose_cnt;         // [S] tracks of the scene if the frame ran track(), else 0: the pose-row scan reads this
     int n_scenes;
     uint32_t flags;

@@ -766,6 +766,16 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
         stamp(1);
         if (dbg != nullptr && tid == 0) { atomicAdd(&dbg[2], 1ull); atomicAdd(&dbg[7], (unsigned long long)B); }
     }
+    // every CTA read the work-list length when it started; the last one to finish empties the list for the next step
+    // (no memset node between the steps)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(a.defer_done, 1) == (int)gridDim.x - 1) {
+            *a.defer_count = 0;
+            *a.defer_done = 0;
+        }
+    }
 }
 
 cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
@@ -778,10 +788,6 @@ cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         configured = smem;
-    }
-    if (a.defer_count != nullptr) {
-        cudaError_t e = cudaMemsetAsync(a.defer_count, 0, sizeof(int32_t), stream);
-        if (e != cudaSuccess) return e;
     }
     step_kernel<<<a.n_scenes, kStepThreads, smem, stream>>>(a);
     return cudaGetLastError();
