@@ -314,9 +314,8 @@ int mmw_phase_clocks(mmw_ctx* ctx, int enable, uint64_t* out16);
 int mmw_scene_cycles(mmw_ctx* ctx, uint64_t* out /*[3*S]: cycles, then start and end %globaltimer ns per scene*/);
 
 /* Debug: cycles of dbscan_big_kernel (thread 0 of each CTA, summed over the deferred scenes) since the last call, while
- * mmw_phase_clocks is on: [0] ring load [1] labels+spawn+write-back [2] scenes [3] counts [4] unions [5] rank+relabel
- * [6] border sweep [7] fused points [8] first hop [9] single-blob check [10] propagation loop [12] scenes that took the
- * single-blob shortcut [13] propagation passes.  out16: 16 values. */
+ * mmw_phase_clocks is on: [0] ring load [1] labels+spawn+write-back [2] scenes [3] adjacency + counts [5] components
+ * [6] border points [7] fused points; the rest is reserved.  out16: 16 values. */
 int mmw_dbscan_big_clocks(mmw_ctx* ctx, uint64_t* out16);
 
 /* Number of kernels this library launched since creation (bench.py's gpu_launches). */

@@ -247,122 +247,23 @@ __device__ inline int dbscan_block(const Nb& nb_full, int B, int min_samples, in
 // The same DBSCAN on an explicit adjacency bit matrix (dbscan_big_kernel).  The pair sweeps above evaluate the
 // predicate up to three times per pair and are chained through shared-memory atomics; for the handful of scenes per
 // frame in which clusters actually form that chain IS the kernel's duration.  Here the predicate is evaluated once
-// per ordered pair into adj[b][w] (bit j of word w = point 32 w + j is within eps of b, b included), after which
-// every phase is "one warp per row, one lane per bit, a loop over the W words of the row":
-//   counts -> popc;  components -> min-label propagation over core neighbours + pointer jumping until stable
-//   (labels only decrease and stay inside the component, so the fixed point is the smallest core index = the root
-//   dbscan_inner's ascending scan starts the cluster from);  cluster ids -> popc of the root bit mask;  border points
-//   -> min cluster id over core neighbours.  No atomics, results independent of scheduling.
-// Phases 2 and 3 of the bit-matrix DBSCAN, used by dbscan_bits_block: components of the core-core graph and cluster ids.
-// On entry par[b] = b for core points and -1 otherwise, cm = core bit mask, adj rows valid for every core point.
-// On return cl[b] = cluster id of core point b (-1 for the others) and the number of clusters is returned.
-__device__ inline int bits_components_and_ids(int B, int W, const unsigned* adj, const unsigned* cm, unsigned* rm,
-                                              int* par, int* cl, unsigned long long* dbg = nullptr) {
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    long long dbg_t = clock64();
-    auto stamp = [&](int k) {                                            // debug accounting (mmw_dbscan_big_clocks)
-        if (dbg != nullptr && tid == 0) {
-            const long long now = clock64();
-            atomicAdd(&dbg[k], (unsigned long long)(now - dbg_t));
-            dbg_t = now;
-        }
-    };
-    // 2. components of the core-core graph.  First hop straight from the bit rows (lowest core neighbour; final
-    //    already when the component is a clique, the usual person-sized blob), then min-label propagation +
-    //    pointer jumping until nothing changes.
-    for (int b = warp; b < B; b += nw) {
-        if (par[b] < 0) continue;                                        // uniform over the warp; par[b] is only
-        int m = 0x7fffffff;                                              // written by this warp in this loop
-        for (int w = lane; w < W; w += 32) {
-            const unsigned bits = adj[b * W + w] & cm[w];
-            if (bits) m = min(m, (w << 5) + __ffs(bits) - 1);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
-        __syncwarp();                                                    // every lane has read par[b] above
-        if (lane == 0) par[b] = m;                                       // m <= b: b is its own neighbour
-    }
-    __syncthreads();
-    stamp(18);
-    // The usual case is ONE person-sized blob: every core point is adjacent to the lowest core point L, the hop above
-    // has labelled them all L and nothing is left to propagate.
-    {
-        int L = -1;
-        for (int w = 0; w < W && L < 0; ++w)
-            if (cm[w]) L = (w << 5) + __ffs(cm[w]) - 1;
-        int star = 1;
-        for (int b = tid; b < B; b += nt) star &= (par[b] < 0 || par[b] == L) ? 1 : 0;
-        star = __syncthreads_and(star);
-        stamp(19);
-        if (star) {
-            if (dbg != nullptr && tid == 0) atomicAdd(&dbg[22], 1ull);
-            goto labelled;
-        }
-    }
-    // Race-free by construction: a propagation pass reads the labels in par and writes the new ones to cl, the
-    // pointer-jumping pass reads cl (chains strictly decrease until a fixed point) and writes par.
-    while (true) {
-        int changed = 0;
-        for (int b = warp; b < B; b += nw) {
-            const int cur = par[b];
-            if (cur < 0) {                                               // uniform over the warp
-                if (lane == 0) cl[b] = -1;
-                continue;
-            }
-            int m = cur;
-#pragma unroll 2
-            for (int w = 0; w < W; ++w) {
-                const unsigned bits = adj[b * W + w] & cm[w];
-                if ((bits >> lane) & 1u) m = min(m, par[(w << 5) + lane]);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
-            if (lane == 0) cl[b] = m;
-            changed |= m < cur ? 1 : 0;
-        }
-        __syncthreads();
-        for (int b = tid; b < B; b += nt) {
-            int l = cl[b];
-            if (l < 0) continue;
-            while (true) {
-                const int p = cl[l];
-                if (p == l) break;
-                l = p;
-            }
-            par[b] = l;
-        }
-        if (dbg != nullptr && tid == 0) atomicAdd(&dbg[23], 1ull);          // propagation passes
-        if (!__syncthreads_or(changed)) break;
-    }
-    stamp(20);
-labelled:
-    // 3. cluster ids: rank of the root among the roots, ascending index
-    for (int w = warp; w < W; w += nw) {
-        const int b = (w << 5) + lane;
-        const unsigned m = __ballot_sync(kFullMask, b < B && par[b] == b);
-        if (lane == 0) rm[w] = m;
-    }
-    __syncthreads();
-    int ncl = 0;
-    for (int w = 0; w < W; ++w) ncl += __popc(rm[w]);
-    for (int b = tid; b < B; b += nt) {
-        const int r = par[b];
-        int id = -1;
-        if (r >= 0) {
-            id = __popc(rm[r >> 5] & ((1u << (r & 31)) - 1u));
-            for (int w = 0; w < (r >> 5); ++w) id += __popc(rm[w]);
-        }
-        cl[b] = id;
-    }
-    __syncthreads();
-    return ncl;
-}
+// per unordered pair into adj[b][w] (bit j of word w = point 32 w + j is within eps of b, b included), and everything
+// after that is word-wide bit arithmetic:
+//   counts      popc of a row; core mask cm by ballot
+//   components  frontier expansion on bit masks: start from the lowest core point not yet visited -- the point
+//               dbscan_inner's ascending scan starts a cluster from, so clusters come out in canonical order --
+//               and OR the core rows of the frontier into the component until it stops growing (a person-sized blob
+//               is a near-clique: two rounds)
+//   border      a non-core point takes the first (= lowest-numbered) cluster whose mask meets its row
+// Results are independent of scheduling (integer ORs only).  Shared memory: adj B * W words, cm W words,
+// ws (4 + kMaxCompMasks) * W words, W = ceil(B / 32).  Requires B <= blockDim.x * 32 and W <= blockDim.x.
+constexpr int kMaxCompMasks = 32;      // clusters whose masks are kept for the border step (more: row-pull fallback)
 
-// adj: B * ceil(B/32) words; cm, rm: ceil(B/32) words each (shared).  Requires B <= blockDim.x * 32.
 __device__ inline int dbscan_bits_block(const NbScreened& nbf, int B, int min_samples, unsigned* adj, unsigned* cm,
-                                        unsigned* rm, int* par, int* cl, unsigned long long* dbg = nullptr) {
+                                        unsigned* ws, int* /*par*/, int* cl, unsigned long long* dbg = nullptr) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     const int W = (B + 31) >> 5;
+    unsigned *visited = ws, *comp = ws + W, *front = ws + 2 * W, *next = ws + 3 * W, *cmask = ws + 4 * W;
     long long dbg_t = clock64();
     auto stamp = [&](int k) {
         if (dbg != nullptr && tid == 0) {
@@ -408,40 +309,83 @@ __device__ inline int dbscan_bits_block(const NbScreened& nbf, int B, int min_sa
         }
     }
     __syncthreads();
-    for (int b = tid; b < B; b += nt) {                                // neighbour counts -> core points
-        int cnt = 0;
-        for (int w = 0; w < W; ++w) cnt += __popc(adj[b * W + w]);
-        par[b] = cnt >= min_samples ? b : -1;                          // core points start as their own label
-    }
-    __syncthreads();
+    // neighbour counts -> core mask (one warp per word of points)
     for (int w = warp; w < W; w += nw) {
         const int b = (w << 5) + lane;
-        const unsigned m = __ballot_sync(kFullMask, b < B && par[b] >= 0);
-        if (lane == 0) cm[w] = m;
+        int cnt = 0;
+        if (b < B)
+            for (int ww = 0; ww < W; ++ww) cnt += __popc(adj[b * W + ww]);
+        const unsigned m = __ballot_sync(kFullMask, b < B && cnt >= min_samples);
+        if (lane == 0) { cm[w] = m; visited[w] = 0u; next[w] = 0u; }
     }
+    for (int b = tid; b < B; b += nt) cl[b] = -1;
     __syncthreads();
     stamp(13);
-    int anycore = 0;
-    for (int w = tid; w < W; w += nt) anycore |= cm[w] != 0u;
-    if (!__syncthreads_or(anycore)) {
-        for (int b = tid; b < B; b += nt) cl[b] = -1;
-        __syncthreads();
-        return 0;
-    }
-    const int ncl = bits_components_and_ids(B, W, adj, cm, rm, par, cl, dbg);
-    stamp(15);
-    // 4. border points: lowest-numbered cluster with a core point within eps (only labels of core points are read)
-    for (int b = warp; b < B; b += nw) {
-        if (par[b] >= 0) continue;                                       // uniform over the warp
-        int m = 0x7fffffff;
-#pragma unroll 2
+    // 2. components of the core-core graph, in ascending order of their lowest core point
+    int ncl = 0;
+    while (true) {
+        int L = -1;
         for (int w = 0; w < W; ++w) {
-            const unsigned bits = adj[b * W + w] & cm[w];
-            if ((bits >> lane) & 1u) m = min(m, cl[(w << 5) + lane]);
+            const unsigned u = cm[w] & ~visited[w];
+            if (u) { L = (w << 5) + __ffs(u) - 1; break; }
         }
+        if (L < 0) break;                                               // uniform over the block
+        if (tid < W) comp[tid] = front[tid] = tid == (L >> 5) ? 1u << (L & 31) : 0u;
+        __syncthreads();
+        while (true) {
+            for (int b0 = warp << 5; b0 < B; b0 += nt) {
+                const int b = b0 + lane;
+                const bool in_front = b < B && ((front[b >> 5] >> (b & 31)) & 1u);
+                if (!__any_sync(kFullMask, in_front)) continue;
+                for (int w = 0; w < W; ++w) {
+                    const unsigned v = __reduce_or_sync(kFullMask, in_front ? (adj[b * W + w] & cm[w]) : 0u);
+                    if (lane == 0 && v) atomicOr(&next[w], v);
+                }
+            }
+            __syncthreads();
+            int grew = 0;
+            if (tid < W) {
+                const unsigned fresh = next[tid] & ~comp[tid];
+                comp[tid] |= fresh;
+                front[tid] = fresh;
+                next[tid] = 0u;
+                grew = fresh != 0u;
+            }
+            if (!__syncthreads_or(grew)) break;
+        }
+        for (int b = tid; b < B; b += nt)
+            if ((comp[b >> 5] >> (b & 31)) & 1u) cl[b] = ncl;
+        if (tid < W) {
+            visited[tid] |= comp[tid];
+            if (ncl < kMaxCompMasks) cmask[ncl * W + tid] = comp[tid];
+        }
+        ++ncl;
+        __syncthreads();
+    }
+    stamp(15);
+    // 3. border points: lowest-numbered cluster with a core point within eps
+    if (ncl <= kMaxCompMasks) {
+        for (int b = tid; b < B; b += nt) {
+            if ((cm[b >> 5] >> (b & 31)) & 1u) continue;
+            for (int k = 0; k < ncl; ++k) {
+                unsigned any = 0u;
+                for (int w = 0; w < W; ++w) any |= adj[b * W + w] & cmask[k * W + w];
+                if (any) { cl[b] = k; break; }
+            }
+        }
+    } else {                           // more clusters than kept masks: pull the minimum id over the core neighbours
+        for (int b = warp; b < B; b += nw) {
+            if ((cm[b >> 5] >> (b & 31)) & 1u) continue;                 // uniform over the warp
+            int m = 0x7fffffff;
+            for (int w = 0; w < W; ++w) {
+                const unsigned bits = adj[b * W + w] & cm[w];
+                if ((bits >> lane) & 1u) m = min(m, cl[(w << 5) + lane]);
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
-        if (lane == 0 && m != 0x7fffffff) cl[b] = m;
+            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(kFullMask, m, o));
+            __syncwarp();
+            if (lane == 0 && m != 0x7fffffff) cl[b] = m;
+        }
     }
     __syncthreads();
     stamp(16);

@@ -672,10 +672,11 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
 constexpr int kBigThreads = 512;
 constexpr int kBitsMaxB = 768;        // adjacency bit matrix of up to 768 x 768 (72 KB of shared memory)
 __host__ __device__ inline int big_bits_cap(int ncap) { return 3 * ncap < kBitsMaxB ? 3 * ncap : kBitsMaxB; }
-// shared-memory layout of dbscan_big_kernel: Xf|Yf|Zf, par, cl, scan, adj, cm, rm, raw rows, (8-byte aligned) w6
+// shared-memory layout of dbscan_big_kernel: Xf|Yf|Zf, par, cl, scan, adj, cm, ws, raw rows, (8-byte aligned) w6
+constexpr int kBigWsWords = 4 + kMaxCompMasks;    // per-word scratch rows of dbscan_bits_block
 __host__ __device__ inline int big_w6_offset(int ncap) {
     const int cap = big_bits_cap(ncap), w = (cap + 31) / 32;
-    const int o = 36 * ncap + 2 * 3 * ncap * 4 + 64 * 4 + (cap * w + 2 * w) * 4 + cap * kRawCols * 4;
+    const int o = 36 * ncap + 2 * 3 * ncap * 4 + 64 * 4 + (cap * w + (1 + kBigWsWords) * w) * 4 + cap * kRawCols * 4;
     return (o + 7) & ~7;
 }
 __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid_constant__ StepArgs a) {
@@ -691,8 +692,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
     const int bits_cap = big_bits_cap(ncap), bits_w = (bits_cap + 31) >> 5;
     unsigned* adj = reinterpret_cast<unsigned*>(scan + 64);
     unsigned* cm = adj + (size_t)bits_cap * bits_w;
-    unsigned* rm = cm + bits_w;
-    float* rawc = reinterpret_cast<float*>(rm + bits_w);     // bits_cap raw rows
+    unsigned* bws = cm + bits_w;                             // kBigWsWords rows of bits_w words
+    float* rawc = reinterpret_cast<float*>(bws + kBigWsWords * bits_w);     // bits_cap raw rows
     double* w6 = reinterpret_cast<double*>(smem + big_w6_offset(ncap));   // bits_cap world 6-vectors
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_wait();                          // step_kernel has completed: work list, scene and track records are final
@@ -722,7 +723,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
         const bool bits = B <= bits_cap;
         NbScreened nb = load_fused_ring(a, s, fcnt, fphys, Xf, 3 * ncap, bits ? rawc : nullptr);
         stamp(0);
-        int ncl = bits ? dbscan_bits_block(nb, B, c.db_min_samples, adj, cm, rm, par, cl, dbg != nullptr ? dbg - 10 : nullptr)
+        int ncl = bits ? dbscan_bits_block(nb, B, c.db_min_samples, adj, cm, bws, par, cl, dbg != nullptr ? dbg - 10 : nullptr)
                        : dbscan_block(nb, B, c.db_min_samples, par, cl, scan, dbg != nullptr ? dbg - 10 : nullptr, false,
                                       true);
         if (dbg != nullptr && tid == 0) dbg_t = clock64();

@@ -21,10 +21,8 @@ bt.phase_clocks(False)
 o = out.astype(float)
 n = max(o[2], 1)
 print("deferred scenes in 20 frames: %d (%.1f per frame), mean fused points %.0f" % (o[2], o[2] / 20, o[7] / n))
-for name, k in (("ring load", 0), ("counts", 3), ("unions", 4), ("rank+relabel", 5), ("border sweep", 6),
+for name, k in (("ring load", 0), ("adjacency + counts", 3), ("components (mask frontier)", 5), ("border points", 6),
                 ("labels+spawn+write-back", 1)):
     print("%-26s %8.0f cycles per deferred scene" % (name, o[k] / n))
-print("  inside rank+relabel: first hop %.0f, single-blob check %.0f, propagation loop %.0f cycles; %d of %d scenes took "
-      "the single-blob shortcut, %.1f propagation passes per scene" % (o[8] / n, o[9] / n, o[10] / n, o[12], o[2], o[13] / n))
 print("total %.0f cycles = %.1f us at 1.965 GHz per deferred scene" % ((o[0] + o[1] + o[3] + o[4] + o[5] + o[6]) / n,
       (o[0] + o[1] + o[3] + o[4] + o[5] + o[6]) / n / 1965))
