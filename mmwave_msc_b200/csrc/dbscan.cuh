@@ -290,20 +290,28 @@ __device__ inline int dbscan_bits_block(const NbScreened& nbf, int B, int min_sa
             const float xq = qlive ? X[q] : 0.f, yq = qlive ? Y[q] : 0.f, zq = qlive ? Z[q] : 0.f;
             const int b0 = I << 5, bn = min(32, B - b0);
             unsigned tb = 0;
-            for (int r = 0; r < bn; ++r) {
-                const int b = b0 + r;
-                const float yb = Y[b];
-                const float wgt = 1.f - 0.5f * (yb + yq) * rw;
-                const float dx = X[b] - xq, dy = yb - yq, dz = Z[b] - zq;
-                const float d = wgt * (dx * dx + dy * dy + zw * (dz * dz));
-                bool hit = qlive && (d < lo || q == b);
-                const bool unsure = qlive && !(d > hi) && !hit;           // inside the band, or not finite
-                if (__any_sync(kFullMask, unsure)) {
-                    if (unsure) hit = nbf.exact(b, q);
+            // two rows per step: their dependent chains (broadcast loads -> distance -> ballot) overlap
+            for (int r = 0; r < bn; r += 2) {
+                const int ba = b0 + r, bb = r + 1 < bn ? ba + 1 : ba;
+                const float ya = Y[ba], yb = Y[bb];
+                const float wa = 1.f - 0.5f * (ya + yq) * rw, wb = 1.f - 0.5f * (yb + yq) * rw;
+                const float dxa = X[ba] - xq, dya = ya - yq, dza = Z[ba] - zq;
+                const float dxb = X[bb] - xq, dyb = yb - yq, dzb = Z[bb] - zq;
+                const float da = wa * (dxa * dxa + dya * dya + zw * (dza * dza));
+                const float db = wb * (dxb * dxb + dyb * dyb + zw * (dzb * dzb));
+                bool hita = qlive && (da < lo || q == ba), hitb = qlive && (db < lo || q == bb);
+                const bool unsa = qlive && !(da > hi) && !hita, unsb = qlive && !(db > hi) && !hitb;   // in the band / not finite
+                if (__any_sync(kFullMask, unsa || unsb)) {
+                    if (unsa) hita = nbf.exact(ba, q);
+                    if (unsb) hitb = nbf.exact(bb, q);
                 }
-                const unsigned m = __ballot_sync(kFullMask, hit);
-                if (lane == 0) adj[b * W + J] = m;
-                tb |= (hit ? 1u : 0u) << r;
+                const unsigned ma = __ballot_sync(kFullMask, hita), mb = __ballot_sync(kFullMask, hitb);
+                if (lane == 0) {
+                    adj[ba * W + J] = ma;
+                    if (bb != ba) adj[bb * W + J] = mb;
+                }
+                tb |= (hita ? 1u : 0u) << r;
+                if (bb != ba) tb |= (hitb ? 1u : 0u) << (r + 1);
             }
             if (I != J && qlive) adj[q * W + I] = tb;
         }
