@@ -58,6 +58,7 @@ struct mmw_ctx {
     double* d_dt2[2] = {nullptr, nullptr};
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+    int stage_pending = -1;              // staging buffer whose stage_free event is still to be recorded
     cudaEvent_t packed[2] = {nullptr, nullptr}, results_done[2] = {nullptr, nullptr};
     float* d_results[2] = {nullptr, nullptr};
     double* d_export = nullptr;      // [S][192*5 + 2] rows + centroid of mmw_export_track0 (allocated on first use)
@@ -470,7 +471,13 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
             return fail(MMW_ERR_CAPACITY, "more points than n_scenes * max_points_per_frame");
         if (total > 0 && !pts) return fail(MMW_ERR_INVALID, "pts is NULL");
         const int k = (int)(x->stage_idx++ & 1u);
-        // the staging buffer is free once the step kernel that last read it has run
+        // The staging buffer is free once the step kernel that last read it has run.  That event is recorded here, at
+        // the head of the NEXT step, where the stream has to wait for the upload anyway -- not behind the previous
+        // step's last kernel, where it would sit between dense 2 and the result pack and undo their dependent launch.
+        if (x->stage_pending >= 0) {
+            CK(cudaEventRecord(x->stage_free[x->stage_pending], x->stream));
+            x->stage_pending = -1;
+        }
         CK(cudaStreamWaitEvent(x->h2d_stream, x->stage_free[k], 0));
         if (total)
             CK(cudaMemcpyAsync(x->d_pts2[k], pts, sizeof(float) * kRawCols * total, cudaMemcpyHostToDevice,
@@ -501,9 +508,7 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     prof_mark(x, -1);
     int rc = MMW_OK;
     if (flags & MMW_STEP_POSE) rc = mmw_estimate_posture(x);
-    // the staging buffer is free once step_kernel has read it; recorded after the last launch of the step so that no
-    // event sits between two kernels of the chain (it would undo their programmatic dependent launch)
-    if (host_stage >= 0) CK(cudaEventRecord(x->stage_free[host_stage], x->stream));
+    if (host_stage >= 0) x->stage_pending = host_stage;      // recorded at the head of the next step (see above)
     return rc;
 }
 
@@ -923,6 +928,8 @@ __global__ void __launch_bounds__(256) pack_results_kernel(const SceneRec* scene
                                                            const float* keypoints, int S, int tcap, float* out,
                                                            FadeCfg fade) {
     const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    pdl_wait();                          // the step's last kernel (dense 2 or the tracker) has completed
+    pdl_launch_dependents();
     const int nt = scenes[s].n_tracks;
     for (int k = warp; k < tcap; k += nw) {
         float* o = out + ((size_t)s * tcap + k) * MMW_RESULT_FLOATS;
@@ -1040,9 +1047,9 @@ int mmw_pack_results(mmw_ctx* x, float* device_out) {
     if (!x || !device_out) return fail(MMW_ERR_INVALID, "ctx/device_out is NULL");
     CK(cudaSetDevice(x->device));
     const FadeCfg fc{x->cfg.m_x, x->cfg.m_y, x->cfg.m_z, x->cfg.fade_size_max, x->cfg.fade_size_min, x->cfg.fade_weight};
-    pack_results_kernel<<<x->S, 256, 0, x->stream>>>(x->d_scenes, x->d_tracks, x->d_keypoints, x->S, x->tcap,
-                                                              device_out, fc);
-    CK(cudaGetLastError());
+    CK(launch_pdl(pack_results_kernel, dim3(x->S), dim3(256), 0, x->stream, dim3(1, 1, 1),
+                  (const SceneRec*)x->d_scenes, (const TrackRec*)x->d_tracks, (const float*)x->d_keypoints, x->S, x->tcap,
+                  device_out, fc));
     x->launches++;
     return MMW_OK;
 }
@@ -1051,11 +1058,17 @@ int mmw_read_results_async(mmw_ctx* x, float* host_out, int* slot) {
     if (!x || !host_out) return fail(MMW_ERR_INVALID, "ctx/host_out is NULL");
     CK(cudaSetDevice(x->device));
     const int r = (int)(x->result_idx++ & 1u);
-    CK(cudaStreamWaitEvent(x->stream, x->results_done[r], 0));     // previous download of this buffer finished
+    // The previous download of this buffer must have finished.  In a pipelined loop the host has already waited for
+    // it (mmw_wait_results two frames ago), and then no wait is put into the stream: an event between dense 2 and the
+    // pack kernel would undo their programmatic dependent launch.
+    if (cudaEventQuery(x->results_done[r]) != cudaSuccess) {
+        (void)cudaGetLastError();
+        CK(cudaStreamWaitEvent(x->stream, x->results_done[r], 0));
+    }
     const FadeCfg fc{x->cfg.m_x, x->cfg.m_y, x->cfg.m_z, x->cfg.fade_size_max, x->cfg.fade_size_min, x->cfg.fade_weight};
-    pack_results_kernel<<<x->S, 256, 0, x->stream>>>(x->d_scenes, x->d_tracks, x->d_keypoints, x->S, x->tcap,
-                                                              x->d_results[r], fc);
-    CK(cudaGetLastError());
+    CK(launch_pdl(pack_results_kernel, dim3(x->S), dim3(256), 0, x->stream, dim3(1, 1, 1),
+                  (const SceneRec*)x->d_scenes, (const TrackRec*)x->d_tracks, (const float*)x->d_keypoints, x->S, x->tcap,
+                  x->d_results[r], fc));
     x->launches++;
     CK(cudaEventRecord(x->packed[r], x->stream));
     CK(cudaStreamWaitEvent(x->d2h_stream, x->packed[r], 0));

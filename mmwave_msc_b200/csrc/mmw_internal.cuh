@@ -12,7 +12,10 @@ constexpr int kRing = 3;          // max frames in a ring: FB_FRAMES_BATCH + 1 <
 constexpr int kFeatPts = 64;      // points kept per track ring frame (format_single_frame, Utils.py:505-510)
 constexpr int kRawCols = 5;       // x, y, z, doppler, peakVal (sensor frame, fp32)
 constexpr int kKp = 57;           // 19 joints x 3
-constexpr int kStepThreads = 128;
+#ifndef MMW_STEP_THREADS
+#define MMW_STEP_THREADS 128     // threads per scene CTA of the tracker step (profiling builds override it)
+#endif
+constexpr int kStepThreads = MMW_STEP_THREADS;
 constexpr int kStepWarps = kStepThreads / 32;
 constexpr int kMaxTcap = 32;
 

@@ -75,6 +75,31 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// Reduce NV per-lane values across the warp so that lane v (< NV) ends up with the total of value v: at every
+// butterfly level a lane keeps one half of its live values and hands the other half to its partner, so the 5 levels
+// cost about NV + log2 shuffles instead of 5 * NV.  The order of the additions is fixed (deterministic results).
+template <int NV, class Op>
+__device__ __forceinline__ double warp_reduce_to_lane(double (&a)[NV], int lane, Op op) {
+    static_assert(NV >= 1 && NV <= 32, "one value per lane at most");
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; ++k) {
+            if (k < NV) {
+                if (k + o < NV) {
+                    const double keep = up ? a[k + o] : a[k];
+                    const double send = up ? a[k] : a[k + o];
+                    a[k] = op(keep, __shfl_xor_sync(kFull, send, o));
+                } else {
+                    a[k] = op(a[k], __shfl_xor_sync(kFull, a[k], o));
+                }
+            }
+        }
+    }
+    return a[0];
+}
+
 // Push the rows i (ascending) with sel(i) true into a ring frame of capacity `cap` rows.  One warp.
 // Returns the number of selected rows (may exceed cap; only the first cap are stored).
 template <class Sel>
@@ -264,6 +289,9 @@ __device__ __forceinline__ NbScreened load_fused_ring(const StepArgs& a, int s, 
         }                                                                                \
     } while (0)
 
+#ifndef MMW_ASSOC_V2
+#define MMW_ASSOC_V2 1
+#endif
 #ifndef MMW_STEP_MINBLOCKS
 #define MMW_STEP_MINBLOCKS 7
 #endif
@@ -406,6 +434,233 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     __syncthreads();
 
     PHASE_MARK(3);
+#if MMW_ASSOC_V2
+    // ---- 4. gating + association (Tracking.py:553-572, Q14) -------------------------------------------
+    // Besides the decision per point this phase builds, in input order, the index list of every group (group j < T0:
+    // the points gated into track j; then the unassigned points).  Warp w owns a contiguous run of 32-point chunks
+    // and counts its points per group (lane j keeps track j's count); after one barrier every warp knows where its
+    // run starts inside each list, places its indices and pushes the raw rows into the rings (Tracking.py:691, 338)
+    // with one thread per point.  The per-track statistics below then walk a compact list.
+    uint16_t* lst = reinterpret_cast<uint16_t*>(wsall);              // [M]; the warp scratch is idle in phases 4-6
+    int* wtot = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(wsall) + 2 * ((ncap + 3) & ~3));   // [33][warps]
+    const unsigned ltmask = (1u << lane) - 1u;
+    const int nchunk = (M + 31) >> 5, cpw = (nchunk + kStepWarps - 1) / kStepWarps;
+    const int ch0 = warp * cpw, ch1 = min(nchunk, ch0 + cpw);
+    {
+        int cntj = 0, cntu = 0;
+        for (int ch = ch0; ch < ch1; ++ch) {
+            const int i = ch * 32 + lane;
+            int g = 255;
+            if (i < M) {
+                double p[6];
+                load_w(i, p);
+                double best = INFINITY;
+                int bj = -1;
+                for (int j = 0; j < T0; ++j) {
+                    double y[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) y[k] = p[k] - hx[j * 6 + k];
+                    const double* Ci = cinv + j * 36;
+                    double q = 0.0;
+#pragma unroll
+                    for (int b = 0; b < 6; ++b) {
+                        double tb = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) tb += y[k] * Ci[k * 6 + b];
+                        q += tb * y[b];
+                    }
+                    const double d2 = logdet[j] + q;
+                    if (d2 < c.gate && d2 < best) { best = d2; bj = j; }
+                }
+                g = bj < 0 ? T0 : bj;
+                assoc[i] = (uint8_t)g;
+                a.assoc_out[off + i] = bj;
+            }
+            for (int j = 0; j < T0; ++j) {
+                const unsigned b = __ballot_sync(kFull, g == j);
+                if (lane == j) cntj += __popc(b);
+            }
+            cntu += __popc(__ballot_sync(kFull, g == T0));
+        }
+        if (lane < T0) wtot[lane * kStepWarps + warp] = cntj;
+        if (lane == 0) wtot[kMaxTcap * kStepWarps + warp] = cntu;
+    }
+    __syncthreads();
+    // lane j: size and start of track j's list, and where this warp's run begins inside it
+    int totj = 0, startj, runj = 0, U, runu = 0;
+    {
+        if (lane < T0)
+            for (int w = 0; w < kStepWarps; ++w) {
+                const int cw = wtot[lane * kStepWarps + w];
+                totj += cw;
+                if (w < warp) runj += cw;
+            }
+        int incl = totj;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += up;
+        }
+        startj = incl - totj;
+        runj += startj;
+        U = 0;
+        for (int w = 0; w < kStepWarps; ++w) {
+            const int cw = wtot[kMaxTcap * kStepWarps + w];
+            U += cw;
+            if (w < warp) runu += cw;
+        }
+        runu += __shfl_sync(kFull, incl, 31);                         // the unassigned list follows the tracks' lists
+    }
+    const int uphys = sc.ring_n >= c.ring_size ? sc.ring_head : (sc.ring_head + sc.ring_n) % c.ring_size;
+    {
+        // BatchedData.add_frame(unassigned): the oldest frame is dropped when the ring is full
+        float* udst = const_cast<float*>(uring_frame(a, s, uphys));
+        const int ustart = M - U;
+        for (int ch = ch0; ch < ch1; ++ch) {
+            const int i = ch * 32 + lane;
+            const int g = i < M ? (int)assoc[i] : 255;
+            int pos = 0;
+            for (int j = 0; j < T0; ++j) {
+                const unsigned b = __ballot_sync(kFull, g == j);
+                const int basej = __shfl_sync(kFull, runj, j);
+                if (g == j) pos = basej + __popc(b & ltmask);
+                if (lane == j) runj += __popc(b);
+            }
+            {
+                const unsigned b = __ballot_sync(kFull, g == T0);
+                if (g == T0) pos = runu + __popc(b & ltmask);
+                runu += __popc(b);
+            }
+            const int gstart = __shfl_sync(kFull, startj, g < 32 ? g : 0);
+            if (i < M) {
+                lst[pos] = (uint16_t)i;
+                float* dst = nullptr;
+                if (g == T0) {
+                    dst = udst + (size_t)(pos - ustart) * kRawCols;
+                } else if (pos - gstart < kFeatPts) {
+                    // first 64 associated rows in input order are what format_single_frame can see
+                    const TrackRec& t = tr[g];
+                    const int phys = t.ring_n >= c.ring_size ? t.ring_head : (t.ring_head + t.ring_n) % c.ring_size;
+                    dst = a.track_ring + (((size_t)s * tcap + t.slot) * kRing + phys) * (kFeatPts * kRawCols) +
+                          (size_t)(pos - gstart) * kRawCols;
+                }
+                if (dst != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < kRawCols; ++k) dst[k] = craw[i * kRawCols + k];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    PHASE_MARK(4);
+    // ---- 5. per-track association (Tracking.py:648-653, 314-341) ---------------------------------------
+    int ring_rows = 0;
+    for (int g = warp; g < T0; g += kStepWarps) {
+        TrackRec& t = tr[g];
+        const int n = __shfl_sync(kFull, totj, g), start = __shfl_sync(kFull, startj, g);
+        if (n == 0) {
+            if (lane == 0) t.lifetime += dt;                     // update_lifetime(dt) (400-407)
+            continue;
+        }
+        // PointCluster statistics (Tracking.py:120-136): sums in a[0..5]; minima and negated maxima share one array
+        double cen[6], mnv, mxv;
+        {
+            double sa[6], mm[12];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { sa[k] = 0.0; mm[k] = INFINITY; mm[6 + k] = INFINITY; }
+            for (int k0 = lane; k0 < n; k0 += 32) {
+                double w[6];
+                load_w((int)lst[start + k0], w);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    sa[k] += w[k];
+                    mm[k] = fmin(mm[k], w[k]);
+                    mm[6 + k] = fmin(mm[6 + k], -w[k]);
+                }
+            }
+            const double ssum = warp_reduce_to_lane(sa, lane, [](double u, double v) { return u + v; });
+            const double smin = warp_reduce_to_lane(mm, lane, [](double u, double v) { return fmin(u, v); });
+#pragma unroll
+            for (int k = 0; k < 6; ++k) cen[k] = __shfl_sync(kFull, ssum, k) / (double)n;
+            mnv = smin;                                          // lane m < 6: min of column m
+            mxv = -__shfl_sync(kFull, smin, (lane + 6) & 31);    // lane m < 6: max of column m
+        }
+        // dispersion matrix about the centroid (population covariance, _get_D 270-290); entry p lands in lane p
+        double cov;
+        {
+            double acc[21];
+#pragma unroll
+            for (int p = 0; p < 21; ++p) acc[p] = 0.0;
+            for (int k0 = lane; k0 < n; k0 += 32) {
+                double d[6];
+                load_w((int)lst[start + k0], d);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) d[k] -= cen[k];
+                int p = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int q = r; q < 6; ++q) acc[p++] += d[r] * d[q];
+            }
+            cov = warp_reduce_to_lane(acc, lane, [](double u, double v) { return u + v; }) / (double)n;
+        }
+        const int phys = t.ring_n >= c.ring_size ? t.ring_head : (t.ring_head + t.ring_n) % c.ring_size;
+        double n_est = t.n_est;
+        if (c.enable_est) {                                      // _estimate_point_num (232-244)
+            if ((double)n > n_est) n_est = (double)n;
+            else n_est = (1 - c.a_n) * n_est + c.a_n * (double)n;
+        } else {
+            n_est = (double)(n > c.est_pointnum ? n : c.est_pointnum);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (t.ring_n >= c.ring_size) t.ring_head = (t.ring_head + 1) % c.ring_size;
+            else t.ring_n += 1;
+            t.ring_cnt[phys] = n < kFeatPts ? n : kFeatPts;
+            t.lifetime = 0.0;
+            t.point_num = n;
+            t.is_static = sqrt(cen[3] * cen[3] + cen[4] * cen[4] + cen[5] * cen[5]) < c.vel_thres ? 1 : 0;
+            t.n_est = n_est;
+        }
+        if (lane < 6) {                                          // _estimate_measurement_spread (246-268)
+            const int m = lane;
+            double cm = cen[0];
+#pragma unroll
+            for (int k = 1; k < 6; ++k) cm = (m == k) ? cen[k] : cm;
+            t.centroid[m] = cm;
+            t.minv[m] = mnv;
+            t.maxv[m] = mxv;
+            double spread = mxv - mnv;
+            if (n != 1) spread = spread * (double)(n + 1) / (double)(n - 1);
+            spread = fmin(2 * c.spread_lim[m], spread);
+            spread = fmax(c.spread_lim[m], spread);
+            if (spread > t.spread[m]) t.spread[m] = spread;
+            else t.spread[m] = (1.0 - c.a_spr) * t.spread[m] + c.a_spr * spread;
+        }
+        {                                                        // _estimate_group_disp_matrix (292-297)
+            const double al = (double)n / n_est;
+#pragma unroll
+            for (int e0 = 0; e0 < 64; e0 += 32) {
+                const int e = e0 + lane;
+                int r = e / 6, q = e % 6;
+                if (r > q) { const int tmp = r; r = q; q = tmp; }
+                const int p = e < 36 ? r * 6 - (r * (r - 1)) / 2 + (q - r) : 0;
+                const double dv = __shfl_sync(kFull, cov, p);
+                if (e < 36) t.G[e] = (1 - al) * t.G[e] + al * dv;
+            }
+        }
+        if (lane == 0) ring_rows += (n < kFeatPts ? n : kFeatPts);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        if (sc.ring_n >= c.ring_size) sc.ring_head = (sc.ring_head + 1) % c.ring_size;
+        else sc.ring_n += 1;
+        sc.ring_cnt[uphys] = U;
+    }
+
+#else   // MMW_ASSOC_V2 == 0: the first version (three masked passes over all points per track), kept for A/B timing
     // ---- 4. gating + association (Tracking.py:553-572, Q14) -------------------------------------------
     for (int i = tid; i < M; i += kStepThreads) {
         double p[6];
@@ -530,6 +785,8 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         else sc.ring_n += 1;
         sc.ring_cnt[phys] = u;
     }
+
+#endif
 
     PHASE_MARK(5);
     // ---- 6. maintenance (Tracking.py:513-528, Q16): drop timed-out tracks, keep list order -----------
