@@ -115,6 +115,56 @@ struct NbScreened {
     __device__ __forceinline__ Hot hot() const { return Hot{Xf, Yf, Zf, lo, hi, rw, zw, this}; }
 };
 
+// Conservative screen "can any point of this cloud be a core point?" on a 16 x 16 grid over the world (x, y') plane.
+// Two points within eps of each other satisfy dx^2 + dy^2 <= eps / w with w = 1 - range_weight (y1 + y2)/2 >=
+// 1 - range_weight * max y' (Utils.py:242-247; the z term only adds), so with cells at least that wide every
+// neighbour of a point lies in the 3 x 3 block of cells around it: if no block holds min_samples points, no point
+// has min_samples neighbours and DBSCAN labels everything noise -- which is what the steady-state residue of ~70
+// clutter points does in > 99.9 % of the scene-frames (measured with the oracle).  Cells outside the
+// grid are folded onto its border (counts can only grow).  Block-cooperative; hist: kGridCells ints of shared
+// memory, s_red: one int.  Returns the same value in every thread; false means "certainly no core point".
+constexpr int kGridDim = 16, kGridCells = kGridDim * kGridDim;
+__device__ inline bool dbscan_grid_may_have_core(const DevConfig& c, const float* Xf, const float* Yf, int B,
+                                                 int min_samples, int* hist, int* s_red) {
+    if (B < min_samples) return false;                               // a point has at most B neighbours, itself included
+    if (!(c.db_range_weight >= 0.0) || !(c.db_z_weight >= 0.0) || !(c.db_eps > 0.0)) return true;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < kGridCells; e += nt) hist[e] = 0;
+    if (tid == 0) *s_red = 0;
+    __syncthreads();
+    float ym = 0.f;
+    for (int b = tid; b < B; b += nt) ym = fmaxf(ym, Yf[b]);
+    ym = fmaxf(ym, 0.f);                                             // y' > 0 after the scene filter: ordered like its bits
+    const int ymw = __reduce_max_sync(0xffffffffu, __float_as_int(ym));
+    if ((tid & 31) == 0) atomicMax(s_red, ymw);
+    __syncthreads();
+    const float wmin = 1.f - (float)c.db_range_weight * (__int_as_float(*s_red) * 1.0001f);
+    if (!(wmin > 0.05f)) return true;                                // the bound degenerates: take the exact path
+    const float h = 1.01f * sqrtf((float)c.db_eps / wmin);           // 1 % wider than the largest xy reach
+    const float inv_h = 1.f / h;
+    auto cell = [&](float v, float origin) {
+        const int k = (int)floorf(v * inv_h + origin);
+        return k < 0 ? 0 : (k >= kGridDim ? kGridDim - 1 : k);
+    };
+    for (int b = tid; b < B; b += nt)
+        atomicAdd(&hist[cell(Yf[b], 0.f) * kGridDim + cell(Xf[b], 0.5f * kGridDim)], 1);
+    __syncthreads();
+    int cand = 0;
+    for (int b = tid; b < B; b += nt) {
+        const int cx = cell(Xf[b], 0.5f * kGridDim), cy = cell(Yf[b], 0.f);
+        int n = 0;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = cx + dx, y = cy + dy;
+                if (x >= 0 && x < kGridDim && y >= 0 && y < kGridDim) n += hist[y * kGridDim + x];
+            }
+        cand |= n >= min_samples ? 1 : 0;
+    }
+    return __syncthreads_or(cand) != 0;
+}
+
 // par, cl: B ints each (shared).  On return cl[b] is the label of b.
 // Returns the number of clusters (uniform over the block).
 // Sweep over all unordered pairs q < b < B in warp tiles: a warp owns a chunk of 32 consecutive q (one per lane) and

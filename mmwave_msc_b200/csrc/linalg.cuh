@@ -44,7 +44,7 @@ __device__ __forceinline__ double warp_inv6(const double* A, double* Ainv, doubl
         if (p != k) det = -det;
         const double piv = shfl_d(r[k], k);
         det *= piv;
-        r[k] = r[k] / piv;
+        r[k] = div_zero_fast(r[k], piv);            // the identity half of [A | I] is mostly exact zeros
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             if (i == k) continue;

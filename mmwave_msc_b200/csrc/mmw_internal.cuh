@@ -144,6 +144,23 @@ __device__ __forceinline__ void world_yz(const DevConfig& c, double y, double z,
     zw = __dadd_rn(__dadd_rn(__dmul_rn(c.sin_t, y), __dmul_rn(c.cos_t, z)), c.s_height);
 }
 
+// (a + b) mod ring_size for 0 <= a + b < 3 * ring_size (ring positions: ring_size <= kRing): two conditional
+// subtractions instead of an integer division by a run-time value.
+__device__ __forceinline__ int ring_wrap(int v, int ring_size) {
+    v = v >= ring_size ? v - ring_size : v;
+    return v >= ring_size ? v - ring_size : v;
+}
+
+// num / den, correctly rounded like __ddiv_rn, for finite den != 0.  A zero numerator (Doppler bin 0 on a third of
+// the points, the identity columns of a Gauss-Jordan step) sends the whole warp down the slow path of the
+// division routine -- ~70 instructions, 13.5 % of the step kernel's instructions in the ncu capture
+// (profiles/r01_ncu_full_final3.md) -- so it is answered directly: 0 / den = 0 with the sign of num * den.
+__device__ __forceinline__ double div_zero_fast(double num, double den) {
+    const bool z = num == 0.0;
+    const double q = __ddiv_rn(z ? 1.0 : num, den);
+    return z ? (den < 0.0 ? -num : num) : q;
+}
+
 __device__ __forceinline__ void world_from_raw(const DevConfig& c, float fx, float fy, float fz, float fd,
                                                double w[6]) {
     const double x = fx, y = fy, z = fz, d = fd;
@@ -152,9 +169,9 @@ __device__ __forceinline__ void world_from_raw(const DevConfig& c, float fx, flo
     if (r == 0.0) {                       // Utils.py:387-390
         vx = 0.0; vy = d; vz = 0.0;
     } else {                              // Utils.py:400-402: (doppler * coord) / r
-        vx = __ddiv_rn(__dmul_rn(d, x), r);
-        vy = __ddiv_rn(__dmul_rn(d, y), r);
-        vz = __ddiv_rn(__dmul_rn(d, z), r);
+        vx = div_zero_fast(__dmul_rn(d, x), r);
+        vy = div_zero_fast(__dmul_rn(d, y), r);
+        vz = div_zero_fast(__dmul_rn(d, z), r);
     }
     w[0] = x;
     world_yz(c, y, z, w[1], w[2]);

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(128) pose_feature_kernel(PoseFeatArgs a) {
                     for (int e = lane; e < kFeatPts * 2; e += 32) pk[f * kFeatPts * 2 + e] = make_uint4(0, 0, 0, 0);
                 continue;
             }
-            const int phys = (rh + f) % c.ring_size;
+            const int phys = ring_wrap(rh + f, c.ring_size);
             const int cnt = t->ring_cnt[phys];
             const float* src = a.track_ring + (((size_t)s * c.tcap + slot) * kRing + phys) * (kFeatPts * kRawCols);
 #pragma unroll

@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         (void)src; (void)dst;
 #endif
         for (int f = 0; f < sc.ring_n; ++f) {
-            const int phys = (sc.ring_head + f) % c.ring_size;
+            const int phys = ring_wrap(sc.ring_head + f, c.ring_size);
             const char* fr = reinterpret_cast<const char*>(uring_frame(a, s, phys));
             const int lines = (sc.ring_cnt[phys] * kRawCols * 4 + 127) / 128;
             for (int i = tid; i < lines; i += kStepThreads)
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         }
         runu += __shfl_sync(kFull, incl, 31);                         // the unassigned list follows the tracks' lists
     }
-    const int uphys = sc.ring_n >= c.ring_size ? sc.ring_head : (sc.ring_head + sc.ring_n) % c.ring_size;
+    const int uphys = sc.ring_n >= c.ring_size ? sc.ring_head : ring_wrap(sc.ring_head + sc.ring_n, c.ring_size);
     {
         // BatchedData.add_frame(unassigned): the oldest frame is dropped when the ring is full
         float* udst = const_cast<float*>(uring_frame(a, s, uphys));
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
                 } else if (pos - gstart < kFeatPts) {
                     // first 64 associated rows in input order are what format_single_frame can see
                     const TrackRec& t = tr[g];
-                    const int phys = t.ring_n >= c.ring_size ? t.ring_head : (t.ring_head + t.ring_n) % c.ring_size;
+                    const int phys = t.ring_n >= c.ring_size ? t.ring_head : ring_wrap(t.ring_head + t.ring_n, c.ring_size);
                     dst = a.track_ring + (((size_t)s * tcap + t.slot) * kRing + phys) * (kFeatPts * kRawCols) +
                           (size_t)(pos - gstart) * kRawCols;
                 }
@@ -575,12 +575,12 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
                     sa[k] += w[k];
-                    mm[k] = fmin(mm[k], w[k]);
-                    mm[6 + k] = fmin(mm[6 + k], -w[k]);
+                    mm[k] = w[k] < mm[k] ? w[k] : mm[k];             // plain compare-select: no NaNs to honour here
+                    mm[6 + k] = -w[k] < mm[6 + k] ? -w[k] : mm[6 + k];
                 }
             }
             const double ssum = warp_reduce_to_lane(sa, lane, [](double u, double v) { return u + v; });
-            const double smin = warp_reduce_to_lane(mm, lane, [](double u, double v) { return fmin(u, v); });
+            const double smin = warp_reduce_to_lane(mm, lane, [](double u, double v) { return v < u ? v : u; });
 #pragma unroll
             for (int k = 0; k < 6; ++k) cen[k] = __shfl_sync(kFull, ssum, k) / (double)n;
             mnv = smin;                                          // lane m < 6: min of column m
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
             }
             cov = warp_reduce_to_lane(acc, lane, [](double u, double v) { return u + v; }) / (double)n;
         }
-        const int phys = t.ring_n >= c.ring_size ? t.ring_head : (t.ring_head + t.ring_n) % c.ring_size;
+        const int phys = t.ring_n >= c.ring_size ? t.ring_head : ring_wrap(t.ring_head + t.ring_n, c.ring_size);
         double n_est = t.n_est;
         if (c.enable_est) {                                      // _estimate_point_num (232-244)
             if ((double)n > n_est) n_est = (double)n;
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         }
         __syncwarp();
         if (lane == 0) {
-            if (t.ring_n >= c.ring_size) t.ring_head = (t.ring_head + 1) % c.ring_size;
+            if (t.ring_n >= c.ring_size) t.ring_head = ring_wrap(t.ring_head + 1, c.ring_size);
             else t.ring_n += 1;
             t.ring_cnt[phys] = n < kFeatPts ? n : kFeatPts;
             t.lifetime = 0.0;
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     }
     __syncthreads();
     {
-        if (sc.ring_n >= c.ring_size) sc.ring_head = (sc.ring_head + 1) % c.ring_size;
+        if (sc.ring_n >= c.ring_size) sc.ring_head = ring_wrap(sc.ring_head + 1, c.ring_size);
         else sc.ring_n += 1;
         sc.ring_cnt[uphys] = U;
     }
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
             // BatchedData.add_frame(unassigned): drop the oldest frame when the ring is full
             int phys;
             if (sc.ring_n >= c.ring_size) { phys = sc.ring_head; }
-            else { phys = (sc.ring_head + sc.ring_n) % c.ring_size; }
+            else { phys = ring_wrap(sc.ring_head + sc.ring_n, c.ring_size); }
             float* dst = const_cast<float*>(uring_frame(a, s, phys));
             const int u = warp_push_rows(craw, M, dst, ncap, [&](int i) { return assoc[i] == 255; }, lane);
             if (lane == 0) { misc[kU] = u; misc[kUPhys] = phys; }
@@ -731,12 +731,12 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         // ring push (first 64 associated rows in input order are what format_single_frame can see)
         int phys;
         if (t.ring_n >= c.ring_size) { phys = t.ring_head; }
-        else { phys = (t.ring_head + t.ring_n) % c.ring_size; }
+        else { phys = ring_wrap(t.ring_head + t.ring_n, c.ring_size); }
         float* dst = a.track_ring + (((size_t)s * tcap + t.slot) * kRing + phys) * (kFeatPts * kRawCols);
         warp_push_rows(craw, M, dst, kFeatPts, sel, lane);
         __syncwarp();
         if (lane == 0) {
-            if (t.ring_n >= c.ring_size) t.ring_head = (t.ring_head + 1) % c.ring_size;
+            if (t.ring_n >= c.ring_size) t.ring_head = ring_wrap(t.ring_head + 1, c.ring_size);
             else t.ring_n += 1;
             t.ring_cnt[phys] = n < kFeatPts ? n : kFeatPts;
             t.lifetime = 0.0;
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     {
         const int u = misc[kU], phys = misc[kUPhys];
         U = u;
-        if (sc.ring_n >= c.ring_size) sc.ring_head = (sc.ring_head + 1) % c.ring_size;
+        if (sc.ring_n >= c.ring_size) sc.ring_head = ring_wrap(sc.ring_head + 1, c.ring_size);
         else sc.ring_n += 1;
         sc.ring_cnt[phys] = u;
     }
@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     int B = 0;
     int fcnt[kRing], fphys[kRing];
     for (int f = 0; f < kRing; ++f) {
-        fphys[f] = (sc.ring_head + f) % c.ring_size;
+        fphys[f] = ring_wrap(sc.ring_head + f, c.ring_size);
         fcnt[f] = f < sc.ring_n ? sc.ring_cnt[fphys[f]] : 0;
         B += fcnt[f];
     }
@@ -845,7 +845,18 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     } else if (run_db) {
         NbScreened nb = load_fused_ring(a, s, fcnt, fphys, reinterpret_cast<float*>(smem + L.dbf), 3 * ncap);
         PHASE_MARK(11);
-        ncl = dbscan_block(nb, B, c.db_min_samples, par, cl, misc + kScan, a.phase_cycles, a.defer_list != nullptr);
+        // Grid screen first (dbscan.cuh): the residue of a steady scene cannot hold a core point and is all noise.
+        // Whatever the screen lets through is most likely a cluster forming and goes straight to dbscan_big_kernel.
+        const bool screen = a.defer_list != nullptr && 3 * ncap >= kGridCells;
+        if (screen && !dbscan_grid_may_have_core(c, nb.Xf, nb.Yf, B, c.db_min_samples, cl, misc + kScan)) {
+            // (the histogram aliased cl; the screen ends with a barrier, and cl[b] is read back by its writer only)
+            for (int b = tid; b < B; b += kStepThreads) cl[b] = -1;
+            ncl = 0;
+        } else if (screen) {
+            ncl = -1;
+        } else {
+            ncl = dbscan_block(nb, B, c.db_min_samples, par, cl, misc + kScan, a.phase_cycles, a.defer_list != nullptr);
+        }
         PHASE_MARK(12);
         if (ncl < 0) {
             // A cluster forms in this scene (a couple of scenes per frame): components, border labels and the spawn
@@ -973,7 +984,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
         int B = 0;
         int fcnt[kRing], fphys[kRing];
         for (int f = 0; f < kRing; ++f) {
-            fphys[f] = (sc.ring_head + f) % c.ring_size;
+            fphys[f] = ring_wrap(sc.ring_head + f, c.ring_size);
             fcnt[f] = f < sc.ring_n ? sc.ring_cnt[fphys[f]] : 0;
             B += fcnt[f];
         }
