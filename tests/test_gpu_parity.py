@@ -199,6 +199,59 @@ def test_empty_and_ragged_frames():
         compare_frame(bt, recs, offsets, "frame %d" % f, labels=bt.labels())
 
 
+def _raw_from_world(x, yw, zw, doppler, peak, cfg):
+    """Sensor-frame rows whose world coordinates (Utils.py:312-327) are (x, yw, zw)."""
+    th = np.radians(cfg.s_tilt_deg)
+    y = np.cos(th) * yw + np.sin(th) * (zw - cfg.s_height)
+    z = -np.sin(th) * yw + np.cos(th) * (zw - cfg.s_height)
+    return np.stack([x, y, z, doppler, peak], axis=1).astype(np.float32)
+
+
+def test_grid_screen_edge_cases():
+    """The step kernel decides 'no point can be a core point' on a clamped 16 x 16 grid over (x, y') before it counts
+    neighbours (dbscan.cuh).  Clouds built to sit on the edges of that screen -- blobs outside the grid, on cell
+    borders, one point short of min_samples, far range where the range weight widens the reach, range beyond which
+    the weight turns negative -- must give the oracle's labels, spawns and ids."""
+    cfg = default_config()
+    rng = np.random.default_rng(77)
+
+    def blob(n, cx, cy, sx, sy):
+        return _raw_from_world(rng.normal(cx, sx, n), rng.normal(cy, sy, n), rng.uniform(0.6, 1.6, n),
+                               rng.choice([0.0, 0.0626, -0.0626], n), rng.integers(1, 90, n).astype(np.float64), cfg)
+
+    def clutter(n):
+        return _raw_from_world(rng.uniform(-2.5, 2.5, n), rng.uniform(0.5, 4.5, n), rng.uniform(0.1, 2.4, n),
+                               rng.choice([0.0, 0.0626, -0.125], n), rng.integers(1, 60, n).astype(np.float64), cfg)
+
+    h = float(np.sqrt(cfg.db_eps / (1.0 - cfg.db_range_weight * 3.0)))      # about one grid cell at 3 m
+    makers = [
+        lambda f: blob(40, 6.5, 3.0, 0.08, 0.08),                             # beyond the grid in x (folded onto its border)
+        lambda f: blob(40, -7.0, 11.5, 0.08, 0.08),                           # beyond it in x and y
+        lambda f: np.concatenate([blob(20, 0.2, 2.0, 0.03, 0.03), blob(20, 0.95, 2.0, 0.03, 0.03)]),   # 40 points in one
+        #   block of cells but two groups out of each other's reach: screened in, no core point until the ring fuses two frames
+        lambda f: blob(36, 0.0, 30.0, 0.5, 0.5),                              # far range: reach sqrt(eps / 0.1) = 1.7 m
+        lambda f: blob(36, 0.0, 40.0, 2.0, 2.0),                              # range weight negative: everything is a neighbour
+        lambda f: np.concatenate([blob(18, 2 * h - 0.05, 3 * h - 0.05, 0.02, 0.02),
+                                  blob(18, 2 * h + 0.05, 3 * h + 0.05, 0.02, 0.02)]),   # one blob straddling a cell corner
+        lambda f: clutter(20),                                                # never reaches min_samples points at all
+        lambda f: clutter(90),                                                # plenty of points, nowhere dense
+    ]
+    S = len(makers)
+    bt = BatchedTracker(S, config=cfg)
+    oracles = [mo.SceneOracle(oracle_config(cfg)) for _ in range(S)]
+    spawned = np.zeros(S, bool)
+    for f in range(5):
+        parts = [m(f) for m in makers]
+        offsets = np.zeros(S + 1, np.int32); offsets[1:] = np.cumsum([len(p) for p in parts])
+        dt = np.full(S, 0.083)
+        bt.step(np.concatenate(parts), offsets, dt, pose=False, record_labels=True)
+        recs = [o.step(p, 0.083) for o, p in zip(oracles, parts)]
+        compare_frame(bt, recs, offsets, "frame %d" % f, labels=bt.labels())
+        spawned |= np.array([len(r["tracks"]) > 0 for r in recs])
+    assert spawned[[0, 1, 2, 3, 4, 5]].all() and not spawned[[6, 7]].any()    # both outcomes were exercised
+    assert not bt.status().any()
+
+
 # ---- golden traces recorded from the reference's own Tracking.py / Utils.py --------------------------
 @pytest.mark.parametrize("case", golden_cases())
 def test_against_reference_golden_trace(case):
