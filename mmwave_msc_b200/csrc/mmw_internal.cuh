@@ -151,13 +151,16 @@ __device__ __forceinline__ int ring_wrap(int v, int ring_size) {
     return v >= ring_size ? v - ring_size : v;
 }
 
-// num / den, correctly rounded like __ddiv_rn, for finite den != 0.  A zero numerator (Doppler bin 0 on a third of
+// num / den, correctly rounded like __ddiv_rn.  A zero numerator over a finite non-zero denominator (Doppler bin 0 on a third of
 // the points, the identity columns of a Gauss-Jordan step) sends the whole warp down the slow path of the
 // division routine -- ~70 instructions, 13.5 % of the step kernel's instructions in the ncu capture
 // (profiles/r01_ncu_full_final3.md) -- so it is answered directly: 0 / den = 0 with the sign of num * den.
 __device__ __forceinline__ double div_zero_fast(double num, double den) {
-    const bool z = num == 0.0;
-    const double q = __ddiv_rn(z ? 1.0 : num, den);
+    const bool z = num == 0.0 && den != 0.0 && fabs(den) <= 1.7976931348623157e308;   // 0/0, 0/inf, 0/nan: the real thing
+    double nsafe = z ? 1.0 : num;
+    // opaque to the compiler: it would otherwise divide `num` itself (the quotient is unused when z) -- and did
+    asm("" : "+d"(nsafe));
+    const double q = __ddiv_rn(nsafe, den);
     return z ? (den < 0.0 ? -num : num) : q;
 }
 

@@ -811,12 +811,12 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         // _get_Rc (299-312): Rm/N + ((N_est - N)/((N_est - 1) N)) * group_disp_est
         double* Rc = cinv + misc[kOrder + k] * 36;   // the gate matrices are dead by now: reuse as R storage
         const double Nn = (double)t.point_num;
-        const double coef = (t.n_est - Nn) / ((t.n_est - 1.0) * Nn);
+        const double coef = div_zero_fast(t.n_est - Nn, (t.n_est - 1.0) * Nn);     // N_est == N: zero numerator
         for (int e = lane; e < 36; e += 32) {
             const int r = e / 6, q = e % 6;
             double rm = 0.0;
             if (r == q) { const double h = t.spread[r] / 2; rm = h * h; }
-            Rc[e] = rm / Nn + coef * t.G[e];
+            Rc[e] = div_zero_fast(rm, Nn) + coef * t.G[e];                        // rm is zero off the diagonal
         }
         __syncwarp();
         warp_kf_update(t.x, t.P, t.centroid, Rc, t.lifetime == 0.0, c.nudge_thres, c.nudge_gain, ws, lane);
