@@ -56,7 +56,7 @@ __host__ __device__ inline SmemLayout make_layout(int ncap, int tcap) {
 int step_smem_bytes(int ncap, int tcap) { return make_layout(ncap, tcap).total; }
 
 // misc int slots
-enum { kM = 0, kNFree = 1, kU = 2, kUPhys = 3, kScan = 4 /* .. +kStepWarps+1 */, kOrder = 16 /* .. +32 */,
+enum { kM = 0, kNFree = 1, kScan = 4 /* .. +kStepWarps+1 */, kOrder = 16 /* .. +32 */,
        kFree = 48 /* .. +32 */ };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -98,59 +98,6 @@ __device__ __forceinline__ double warp_reduce_to_lane(double (&a)[NV], int lane,
         }
     }
     return a[0];
-}
-
-// Push the rows i (ascending) with sel(i) true into a ring frame of capacity `cap` rows.  One warp.
-// Returns the number of selected rows (may exceed cap; only the first cap are stored).
-template <class Sel>
-__device__ __forceinline__ int warp_push_rows(const float* craw, int M, float* dst, int cap, Sel sel, int lane) {
-    int base = 0;
-    for (int i0 = 0; i0 < M; i0 += 32) {
-        const int i = i0 + lane;
-        const bool f = i < M && sel(i);
-        const unsigned m = __ballot_sync(kFull, f);
-        const int pos = base + __popc(m & ((1u << lane) - 1u));
-        if (f && pos < cap) {
-#pragma unroll
-            for (int k = 0; k < kRawCols; ++k) dst[pos * kRawCols + k] = craw[i * kRawCols + k];
-        }
-        base += __popc(m);
-    }
-    return base;
-}
-
-// PointCluster statistics (Tracking.py:120-136) of the rows selected by sel, from world columns wp[k][i].
-// All lanes return the same values.
-template <class Sel, class LoadW>
-__device__ __forceinline__ int warp_cluster_stats(LoadW load_w, int M, Sel sel, int lane,
-                                                  double cen[6], double mn[6], double mx[6]) {
-    int n = 0;
-    double s[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { s[k] = 0.0; mn[k] = INFINITY; mx[k] = -INFINITY; }
-    for (int i = lane; i < M; i += 32) {
-        if (!sel(i)) continue;
-        ++n;
-        double w[6];
-        load_w(i, w);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const double v = w[k];
-            s[k] += v;
-            mn[k] = fmin(mn[k], v);
-            mx[k] = fmax(mx[k], v);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        s[k] = warp_sum(s[k]);
-        mn[k] = warp_min(mn[k]);
-        mx[k] = warp_max(mx[k]);
-        cen[k] = n > 0 ? s[k] / (double)n : 0.0;
-    }
-    return n;
 }
 
 __device__ __forceinline__ const float* uring_frame(const StepArgs& a, int s, int phys) {
@@ -289,9 +236,6 @@ __device__ __forceinline__ NbScreened load_fused_ring(const StepArgs& a, int s, 
         }                                                                                \
     } while (0)
 
-#ifndef MMW_ASSOC_V2
-#define MMW_ASSOC_V2 1
-#endif
 #ifndef MMW_STEP_MINBLOCKS
 #define MMW_STEP_MINBLOCKS 7
 #endif
@@ -434,7 +378,6 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     __syncthreads();
 
     PHASE_MARK(3);
-#if MMW_ASSOC_V2
     // ---- 4. gating + association (Tracking.py:553-572, Q14) -------------------------------------------
     // Besides the decision per point this phase builds, in input order, the index list of every group (group j < T0:
     // the points gated into track j; then the unassigned points).  Warp w owns a contiguous run of 32-point chunks
@@ -659,134 +602,6 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         else sc.ring_n += 1;
         sc.ring_cnt[uphys] = U;
     }
-
-#else   // MMW_ASSOC_V2 == 0: the first version (three masked passes over all points per track), kept for A/B timing
-    // ---- 4. gating + association (Tracking.py:553-572, Q14) -------------------------------------------
-    for (int i = tid; i < M; i += kStepThreads) {
-        double p[6];
-        load_w(i, p);
-        double best = INFINITY;
-        int bj = -1;
-        for (int j = 0; j < T0; ++j) {
-            double y[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) y[k] = p[k] - hx[j * 6 + k];
-            const double* Ci = cinv + j * 36;
-            double q = 0.0;
-#pragma unroll
-            for (int b = 0; b < 6; ++b) {
-                double tb = 0.0;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) tb += y[k] * Ci[k * 6 + b];
-                q += tb * y[b];
-            }
-            const double d2 = logdet[j] + q;
-            if (d2 < c.gate && d2 < best) { best = d2; bj = j; }
-        }
-        assoc[i] = (uint8_t)(bj < 0 ? 255 : bj);
-        a.assoc_out[off + i] = bj;
-    }
-    __syncthreads();
-
-    PHASE_MARK(4);
-    // ---- 5. per-track association (Tracking.py:648-653, 314-341) + unassigned push (Tracking.py:691) --
-    int U = 0, ring_rows = 0;
-    for (int g = warp; g <= T0; g += kStepWarps) {
-        if (g == T0) {
-            // BatchedData.add_frame(unassigned): drop the oldest frame when the ring is full
-            int phys;
-            if (sc.ring_n >= c.ring_size) { phys = sc.ring_head; }
-            else { phys = ring_wrap(sc.ring_head + sc.ring_n, c.ring_size); }
-            float* dst = const_cast<float*>(uring_frame(a, s, phys));
-            const int u = warp_push_rows(craw, M, dst, ncap, [&](int i) { return assoc[i] == 255; }, lane);
-            if (lane == 0) { misc[kU] = u; misc[kUPhys] = phys; }
-            continue;
-        }
-        TrackRec& t = tr[g];
-        double cen[6], mn[6], mx[6];
-        auto sel = [&](int i) { return assoc[i] == g; };
-        const int n = warp_cluster_stats(load_w, M, sel, lane, cen, mn, mx);
-        if (n == 0) {
-            if (lane == 0) t.lifetime += dt;                     // update_lifetime(dt) (400-407)
-            continue;
-        }
-        // dispersion matrix about the centroid (population covariance, _get_D 270-290)
-        double acc[21];
-#pragma unroll
-        for (int p = 0; p < 21; ++p) acc[p] = 0.0;
-        for (int i = lane; i < M; i += 32) {
-            if (!sel(i)) continue;
-            double d[6];
-            load_w(i, d);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) d[k] -= cen[k];
-            int p = 0;
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int q = r; q < 6; ++q) acc[p++] += d[r] * d[q];
-        }
-#pragma unroll
-        for (int p = 0; p < 21; ++p) acc[p] = warp_sum(acc[p]) / (double)n;
-        // ring push (first 64 associated rows in input order are what format_single_frame can see)
-        int phys;
-        if (t.ring_n >= c.ring_size) { phys = t.ring_head; }
-        else { phys = ring_wrap(t.ring_head + t.ring_n, c.ring_size); }
-        float* dst = a.track_ring + (((size_t)s * tcap + t.slot) * kRing + phys) * (kFeatPts * kRawCols);
-        warp_push_rows(craw, M, dst, kFeatPts, sel, lane);
-        __syncwarp();
-        if (lane == 0) {
-            if (t.ring_n >= c.ring_size) t.ring_head = ring_wrap(t.ring_head + 1, c.ring_size);
-            else t.ring_n += 1;
-            t.ring_cnt[phys] = n < kFeatPts ? n : kFeatPts;
-            t.lifetime = 0.0;
-            t.point_num = n;
-            t.is_static = sqrt(cen[3] * cen[3] + cen[4] * cen[4] + cen[5] * cen[5]) < c.vel_thres ? 1 : 0;
-            if (c.enable_est) {                                  // _estimate_point_num (232-244)
-                if ((double)n > t.n_est) t.n_est = (double)n;
-                else t.n_est = (1 - c.a_n) * t.n_est + c.a_n * (double)n;
-            } else {
-                t.n_est = (double)(n > c.est_pointnum ? n : c.est_pointnum);
-            }
-        }
-        if (lane < 6) {                                          // _estimate_measurement_spread (246-268)
-            const int m = lane;
-            t.centroid[m] = cen[m];
-            t.minv[m] = mn[m];
-            t.maxv[m] = mx[m];
-            double spread = mx[m] - mn[m];
-            if (n != 1) spread = spread * (double)(n + 1) / (double)(n - 1);
-            spread = fmin(2 * c.spread_lim[m], spread);
-            spread = fmax(c.spread_lim[m], spread);
-            if (spread > t.spread[m]) t.spread[m] = spread;
-            else t.spread[m] = (1.0 - c.a_spr) * t.spread[m] + c.a_spr * spread;
-        }
-        __syncwarp();
-        {                                                        // _estimate_group_disp_matrix (292-297)
-            const double al = (double)n / t.n_est;
-            for (int e = lane; e < 36; e += 32) {
-                int r = e / 6, q = e % 6;
-                if (r > q) { const int tmp = r; r = q; q = tmp; }
-                const int p = r * 6 - (r * (r - 1)) / 2 + (q - r);
-                double dv = 0.0;
-#pragma unroll
-                for (int pp = 0; pp < 21; ++pp) dv = (pp == p) ? acc[pp] : dv;
-                t.G[e] = (1 - al) * t.G[e] + al * dv;
-            }
-        }
-        if (lane == 0) ring_rows += (n < kFeatPts ? n : kFeatPts);
-        __syncwarp();
-    }
-    __syncthreads();
-    {
-        const int u = misc[kU], phys = misc[kUPhys];
-        U = u;
-        if (sc.ring_n >= c.ring_size) sc.ring_head = ring_wrap(sc.ring_head + 1, c.ring_size);
-        else sc.ring_n += 1;
-        sc.ring_cnt[phys] = u;
-    }
-
-#endif
 
     PHASE_MARK(5);
     // ---- 6. maintenance (Tracking.py:513-528, Q16): drop timed-out tracks, keep list order -----------
