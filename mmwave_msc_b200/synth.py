@@ -173,6 +173,15 @@ def gen_batch(scene_ids: Sequence[int], n_frames: int, spec: SceneSpec = SceneSp
     return out
 
 
+def raw_from_world(x, yw, zw, doppler, peak, tilt_deg: float = -5.0, height: float = 1.8) -> np.ndarray:
+    """Sensor-frame rows (x, y, z, doppler, peakVal; float32) whose world coordinates under the reference's
+    transform (Utils.py:312-327: rotation about x by the tilt, then + height) are (x, yw, zw)."""
+    th = np.radians(tilt_deg)
+    y = np.cos(th) * np.asarray(yw) + np.sin(th) * (np.asarray(zw) - height)
+    z = -np.sin(th) * np.asarray(yw) + np.cos(th) * (np.asarray(zw) - height)
+    return np.stack([np.asarray(x), y, z, np.asarray(doppler), np.asarray(peak)], axis=1).astype(np.float32)
+
+
 def write_reference_csv(scene: Scene, directory: str, frames_per_file: int = 200) -> None:
     """Write a scene as a reference experiment log (DataLogging.py:60-89 schema:
     ``frame,x,y,z,doppler,peakVal,posix_ms``; files 1.csv, 2.csv ...; frame numbers

@@ -46,6 +46,41 @@ CASES = [
 ]
 
 
+# Clouds built to sit on the edges of the grid screen that the CUDA tracker step puts in front of DBSCAN
+# (mmwave_msc_b200/csrc/dbscan.cuh): the reference's own labels, spawns and ids for them.  (name, seed, builder);
+# a builder returns the world-frame (x, y', z) blobs of one frame as (n, cx, cy, sigma) tuples plus a clutter count.
+SCREEN_CASES = [
+    ("screen_outside_grid", 1, lambda h: ([(40, 6.5, 3.0, 0.08)], 0)),             # beyond the 16 cells in x
+    ("screen_outside_grid_xy", 2, lambda h: ([(40, -7.0, 11.5, 0.08)], 0)),        # ... in x and y
+    ("screen_two_groups", 3, lambda h: ([(20, 0.2, 2.0, 0.03), (20, 0.95, 2.0, 0.03)], 0)),   # one block of cells, out of reach
+    ("screen_far_range", 4, lambda h: ([(36, 0.0, 30.0, 0.5)], 0)),                # range weight 0.1: reach 1.7 m
+    ("screen_negative_weight", 5, lambda h: ([(36, 0.0, 40.0, 2.0)], 0)),          # weight < 0: everything is a neighbour
+    ("screen_cell_corner", 6, lambda h: ([(18, 2 * h - 0.05, 3 * h - 0.05, 0.02), (18, 2 * h + 0.05, 3 * h + 0.05, 0.02)], 0)),
+    ("screen_sparse_clutter", 7, lambda h: ([], 90)),                              # many points, nowhere dense
+    ("screen_blob_in_clutter", 8, lambda h: ([(30, 1.0, 2.5, 0.1)], 60)),          # 30 < min_samples until the ring fuses
+]
+
+
+def screen_case_frames(seed: int, builder, n_frames: int = 5):
+    const, _, _ = rh.load_reference()
+    rng = np.random.default_rng(9000 + seed)
+    h = float(np.sqrt(const.DB_EPS / (1.0 - const.DB_RANGE_WEIGHT * 3.0)))
+    frames = []
+    for _ in range(n_frames):
+        blobs, n_clutter = builder(h)
+        xs, ys, zs = [], [], []
+        for n, cx, cy, s in blobs:
+            xs.append(rng.normal(cx, s, n)); ys.append(np.abs(rng.normal(cy, s, n)) + 1e-3); zs.append(rng.uniform(0.6, 1.6, n))
+        if n_clutter:
+            xs.append(rng.uniform(-2.5, 2.5, n_clutter)); ys.append(rng.uniform(0.5, 4.5, n_clutter))
+            zs.append(rng.uniform(0.1, 2.4, n_clutter))
+        x, yw, zw = np.concatenate(xs), np.concatenate(ys), np.concatenate(zs)
+        n = len(x)
+        frames.append(synth.raw_from_world(x, yw, zw, rng.choice([0.0, 0.0626, -0.0626, 0.1252], n),
+                                           rng.integers(1, 90, n).astype(np.float64), const.S_TILT, const.S_HEIGHT))
+    return frames, np.full(n_frames, 0.083)
+
+
 def known_answers() -> dict:
     const, utils, tracking = rh.load_reference()
     ka = {}
@@ -133,8 +168,23 @@ def track0_export_golden() -> dict:
     return out
 
 
+def screen_traces():
+    for name, seed, builder in SCREEN_CASES:
+        frames, dts = screen_case_frames(seed, builder)
+        recs = rh.run_reference_scene(frames, dts, pose_fn=lambda x: np.zeros((len(x), 57)))
+        d = trace_io.pack(frames, dts, recs)
+        d["max_tracks"] = np.array(4, np.int32)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **d)
+        print(name, "frames", len(frames), "tracks at end", len(recs[-1]["tracks"]), "next id", recs[-1]["next_track_id"],
+              "dbscan runs", int(d["labels_ran"].sum()),
+              "clustered points per run", [int((r["labels"] >= 0).sum()) for r in recs if r["labels"] is not None])
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--screen-only" in sys.argv:
+        screen_traces()
+        return
     if "--export0-only" in sys.argv:
         np.savez_compressed(os.path.join(GOLDEN, "track0_export.npz"), **track0_export_golden())
         return
@@ -149,6 +199,7 @@ def main():
         print(name, "frames", nf, "tracks at end", len(recs[-1]["tracks"]), "next id", recs[-1]["next_track_id"],
               "dbscan runs", int(d["labels_ran"].sum()))
     np.savez_compressed(os.path.join(GOLDEN, "track0_export.npz"), **track0_export_golden())
+    screen_traces()
     if "--deviation" in sys.argv:
         dev = balltree_deviation()
         json.dump(dev, open(os.path.join(GOLDEN, "balltree_deviation.json"), "w"), indent=1)
