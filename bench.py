@@ -370,7 +370,7 @@ def main():
                 ["scene_frames", "N", "M", "U", "Bf", "tracks", "ring_rows", "pose_rows"], cnt)},
         }
         out.update(rooflines(kern, cnt, K, alg, pk, total_ms / K))
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (the reference arm times all host cores)
             n, sec = cpu_port_run(range(50_000, 50_004), 60)
             out["cpu_baseline"] = {"value": n / sec, "unit": UNIT, "cores": 1, "kind": "port",
                                    "sample": "4 C2-shaped scenes x 60 frames, oracle port (numpy float64 + torch-CPU "
