@@ -17,7 +17,7 @@ struct SmemLayout {
     int vel;         // double [3][ncap]: world-frame velocity columns of the compacted frame (sqrt/div: kept);
                      //   positions are recomputed from craw on use (x is the raw x; y', z' cost 4 mul + 3 add)
     int craw;        // float [ncap*5] compacted raw points of this frame
-    int assoc;       // uint8 [ncap]: track index per compacted point, 255 = unassigned
+    int assoc;       // uint8 [ncap]: group of each compacted point = track index, or n_tracks for unassigned
     int dbf;         // float [3][3*ncap]: fp32 world coordinates of the fused ring during DBSCAN; aliases
                      //   vel|craw|assoc, which are dead by then
     int tracks;      // TrackRec [tcap]
