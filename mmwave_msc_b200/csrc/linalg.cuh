@@ -1,5 +1,10 @@
-// Warp-cooperative float64 linear algebra for the 6x6 / 9x9 tracker matrices.
-// One warp owns one track; matrices live in shared memory, lanes split the elements.
+// Float64 linear algebra of the tracker (6x6 / 9x9), laid out for a 128-thread CTA per scene:
+//   * element-parallel steps: thread e owns element e of a 9x9 / 9x6 / 6x6 matrix of track j and the CTA walks the
+//     scene's tracks; consecutive steps are separated by a block barrier at the call site, so all four warps work
+//     on every track instead of one warp per track;
+//   * the 6x6 inverses: one HALF warp per matrix (two tracks per warp), a column of [A | I] per lane, no pivot
+//     search (the gate matrix and the innovation covariance are symmetric positive definite).
+// Every function cites the reference lines it follows; filterpy 1.4.5 semantics are in SURVEY Appendix B.
 #pragma once
 #include "mmw_internal.cuh"
 
@@ -7,176 +12,187 @@ namespace mmw {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// Per-warp scratch (doubles): A 36 | B 36 | K 54 | M1 81 | v 8.  M2 = K R (9x6) reuses A|B once S and S^-1 are dead.
-constexpr int kWsAug = 0, kWsA = 0, kWsB = 36, kWsK = 72, kWsM1 = 126, kWsM2 = 0, kWsV = 207;
-constexpr int kWarpScratch = 216;
+// Per-thread element coordinates, computed once per kernel: e = threadIdx.x.
+struct Elem {
+    int e;          // thread index
+    int i9, j9;     // row / column of element e of a 9x9 matrix (valid for e < 81)
+    int i6, a6;     // row / column of element e of an Rx6 matrix (valid for e < 54; 6x6 for e < 36)
+    __device__ __forceinline__ explicit Elem(int tid) : e(tid), i9(tid / 9), j9(tid % 9), i6(tid / 6), a6(tid % 6) {}
+};
 
-__device__ __forceinline__ double shfl_d(double v, int src) {
-    return __shfl_sync(kFull, v, src);
+// ---- Kalman predict (filterpy KalmanFilter.predict with F = KF_F(dt), Q = KF_Q_DISCR(dt); constants.py:195-215,
+// Tracking.py:372-385):  x = F x;  P = (F P) F' + Q.  State order [p(3) v(3) a(3)]: F couples i with i+3 (dt) and
+// i+6 (dt^2/2), so both products are three-term sums.
+//   pass 1: A = F P          (thread e < 81)
+//   pass 2: P = A F' + Q     (thread e < 81), x = F x (thread e < 9; kf_predict_x evaluated before anything is written)
+__device__ __forceinline__ void kf_predict_pass1(const double* P, double* A, double dt, const Elem& t) {
+    if (t.e < 81) {
+        const double h = 0.5 * (dt * dt);
+        double v = P[t.e];
+        if (t.i9 < 6) v += dt * P[t.e + 27];
+        if (t.i9 < 3) v += h * P[t.e + 54];
+        A[t.e] = v;
+    }
+}
+__device__ __forceinline__ double kf_predict_x(const double* x, double dt, int e) {
+    double xn = x[e];
+    if (e < 6) xn += dt * x[e + 3];
+    if (e < 3) xn += (0.5 * (dt * dt)) * x[e + 6];
+    return xn;
 }
 
-// Inverse and determinant of a 6x6 row-major matrix by Gauss-Jordan elimination with partial
-// pivoting (numpy.linalg.inv / det are LU with partial pivoting: Tracking.py:558-559, filterpy update).
-// Lane l < 12 keeps column l of the augmented matrix [A | I] in six registers; pivot search, row swap and the
-// multipliers travel by warp shuffle, so there is no shared-memory round trip or __syncwarp inside the six
-// elimination steps.  A, Ainv: 36 doubles in shared memory (may not alias).  `aug` is unused (kept for the
-// callers' scratch layout).  Returns det(A); every lane returns the same value.
-__device__ __forceinline__ double warp_inv6(const double* A, double* Ainv, double* /*aug*/, int lane) {
-    const int col = lane < 12 ? lane : 11;          // lanes >= 12 shadow lane 11 (results discarded)
-    double r[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) r[i] = col < 6 ? A[i * 6 + col] : (col - 6 == i ? 1.0 : 0.0);
-    double det = 1.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        // partial pivoting on column k (held by lane k): first row of maximum magnitude, like LAPACK's idamax
-        int p = k;
-        double best = fabs(r[k]);
-#pragma unroll
-        for (int i = k + 1; i < 6; ++i) {
-            const double v = fabs(r[i]);
-            if (v > best) { best = v; p = i; }
-        }
-        p = __shfl_sync(kFull, p, k);
-#pragma unroll
-        for (int i = k + 1; i < 6; ++i)
-            if (p == i) { const double t = r[k]; r[k] = r[i]; r[i] = t; }
-        if (p != k) det = -det;
-        const double piv = shfl_d(r[k], k);
-        det *= piv;
-        r[k] = div_zero_fast(r[k], piv);            // the identity half of [A | I] is mostly exact zeros
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            if (i == k) continue;
-            const double f = shfl_d(r[i], k);       // multiplier = column k's entry of row i (before the update)
-            r[i] -= f * r[k];
-        }
-    }
-    if (lane >= 6 && lane < 12) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) Ainv[i * 6 + (lane - 6)] = r[i];
-    }
-    __syncwarp();
-    return det;
-}
-
-// filterpy KalmanFilter.predict with F = KF_F(dt), Q = KF_Q_DISCR(dt) (constants.py:195-215):
-//   x = F x ;  P = (F P) F' + Q.  x: 9, P: 81 in shared memory; tmp: 81 doubles scratch.
-__device__ __forceinline__ void warp_kf_predict(double* x, double* P, double dt, double q_var, double* tmp,
-                                                int lane) {
-    const double h = 0.5 * (dt * dt);
-    double nx = 0.0;
-    if (lane < 9) {
-        nx = x[lane];
-        if (lane < 6) nx += dt * x[lane + 3];
-        if (lane < 3) nx += h * x[lane + 6];
-    }
-    for (int e = lane; e < 81; e += 32) {
-        const int i = e / 9, j = e % 9;
-        double v = P[e];
-        if (i < 6) v += dt * P[(i + 3) * 9 + j];
-        if (i < 3) v += h * P[(i + 6) * 9 + j];
-        tmp[e] = v;
-    }
-    __syncwarp();
-    if (lane < 9) x[lane] = nx;
-    const double dt2 = dt * dt, dt3 = dt2 * dt, dt4 = dt2 * dt2;
-    for (int e = lane; e < 81; e += 32) {
-        const int i = e / 9, j = e % 9;
-        double v = tmp[e];
-        if (j < 6) v += dt * tmp[i * 9 + j + 3];
-        if (j < 3) v += h * tmp[i * 9 + j + 6];
-        if (i / 3 == j / 3) {   // block_diag(Qw, Qw, Qw): blocks on state indices (0-2), (3-5), (6-8)  (Q10)
-            const int a = i % 3, b = j % 3, s = a + b;   // Qw[a][b] depends on a+b only
+// Q = block_diag(Qw, Qw, Qw) * q_var with Qw = [[dt^4/4, dt^3/2, dt^2/2], [dt^3/2, dt^2, dt], [dt^2/2, dt, 1]] on
+// state indices (0-2), (3-5), (6-8): the block order does not match the state order (Q10) -- reproduced.
+__device__ __forceinline__ void kf_predict_pass2(double* x, double xn, const double* A, double* P, double dt,
+                                                 double q_var, const Elem& t) {
+    if (t.e < 9) x[t.e] = xn;
+    if (t.e < 81) {
+        const double h = 0.5 * (dt * dt);
+        double v = A[t.e];
+        if (t.j9 < 6) v += dt * A[t.e + 3];
+        if (t.j9 < 3) v += h * A[t.e + 6];
+        if (t.i9 / 3 == t.j9 / 3) {
+            const int a = t.i9 % 3, b = t.j9 % 3, s = a + b;   // Qw[a][b] depends on a + b except the middle entry
+            const double dt2 = dt * dt;
             double qv;
-            if (s == 0) qv = 0.25 * dt4;
-            else if (s == 1) qv = 0.5 * dt3;
+            if (s == 0) qv = 0.25 * (dt2 * dt2);
+            else if (s == 1) qv = 0.5 * (dt2 * dt);
             else if (s == 2) qv = (a == 1) ? dt2 : 0.5 * dt2;
             else if (s == 3) qv = dt;
             else qv = 1.0;
             v += qv * q_var;
         }
-        P[e] = v;
+        P[t.e] = v;
     }
-    __syncwarp();
 }
 
-// filterpy KalmanFilter.update, Joseph form, H = [I6 0] (Tracking.py:387-393):
-//   y = z - x[:6]; S = P[:6,:6] + R; K = P[:, :6] S^-1; x += K y;
-//   P = (I-KH) P (I-KH)' + (K R) K'
-// then the x[0] nudge of Tracking.py:396-398 when `nudge` is set.
-// R: 36 doubles (shared).  ws: per-warp scratch of kWarpScratch doubles.
-__device__ __forceinline__ void warp_kf_update(double* x, double* P, const double* z, const double* R, bool nudge,
-                                               double nudge_thres, double nudge_gain, double* ws, int lane) {
-    double* S = ws + kWsA;
-    double* SI = ws + kWsB;
-    double* K = ws + kWsK;
-    double* M1 = ws + kWsM1;
-    double* M2 = ws + kWsM2;
-    double* v = ws + kWsV;
-    for (int e = lane; e < 36; e += 32) S[e] = P[(e / 6) * 9 + (e % 6)] + R[e];
-    if (lane < 6) v[lane] = z[lane] - x[lane];
-    __syncwarp();
-    warp_inv6(S, SI, ws + kWsAug, lane);
-    // K = P[:, :6] SI   (9x6)
-    for (int e = lane; e < 54; e += 32) {
-        const int i = e / 6, a = e % 6;
-        double acc = 0.0;
+// ---- 6x6 inverse + determinant, two matrices per warp -------------------------------------------------------
+// Half h = lane / 16 of the warp works on matrix h; lane c = lane % 16 < 12 keeps column c of [A | I] in six
+// registers.  Gauss-Jordan without row exchanges: A is symmetric positive definite at both call sites (gate matrix
+// P[:6,:6] + Rm + G, Tracking.py:551; innovation covariance H P H' + R, filterpy update), so every pivot is
+// positive.  The reference inverts with LAPACK (partial pivoting); the results agree to rounding (parity tests hold
+// the state to 1e-6 relative and the gate decisions exactly).  Rows are scaled by the pivot's reciprocal; the five
+// multipliers of a step travel by shuffle while the reciprocal is being computed.
+// A: 36 doubles, row-major (shared memory) or nullptr for an idle half.  On return lane c in [6, 12) of the half
+// holds column c - 6 of the inverse in r[0..5]; every lane of the half returns det(A).
+__device__ __forceinline__ double inv6_spd_half(const double* A, int lane, double (&r)[6]) {
+    const int c = lane & 15;
+    const int col = c < 12 ? c : 11;                 // lanes 12..15 shadow lane 11 (results discarded)
 #pragma unroll
-        for (int b = 0; b < 6; ++b) acc += P[i * 9 + b] * SI[b * 6 + a];
-        K[e] = acc;
+    for (int i = 0; i < 6; ++i)
+        r[i] = (A != nullptr && col < 6) ? A[i * 6 + col] : (col - 6 == i ? 1.0 : 0.0);
+    double det = 1.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double piv = __shfl_sync(kFull, r[k], k, 16);
+        double f[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            if (i != k) f[i] = __shfl_sync(kFull, r[i], k, 16);     // column k's entry of row i, before the update
+        det *= piv;
+        const double inv = __drcp_rn(piv);
+        r[k] *= inv;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            if (i != k) r[i] -= f[i] * r[k];
     }
-    __syncwarp();
-    // x += K y
-    if (lane < 9) {
-        double acc = 0.0;
+    return det;
+}
+
+// ---- Mahalanobis gate (TrackBuffer._calc_dist_fun, Tracking.py:545-572) ---------------------------------------
+// Per track the gate needs C^-1, H x and log|det C| (C = P[:6,:6] + Rm + group_disp_est).  They are kept as 28
+// doubles: the upper triangle of C^-1, row-major, with the off-diagonal entries doubled (y' C^-1 y in 21 products
+// instead of 36), then H x, then log|det C|.
+constexpr int kGateWords = 28;
+// After inv6_spd_half: lanes [6, 12) of the half store their column of the inverse, lane 0 the log-determinant.
+__device__ __forceinline__ void gate_pack_half(double* gp, const double (&r)[6], double det, int lane) {
+    const int c = lane & 15;
+    if (c >= 6 && c < 12) {
+        const int cc = c - 6;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) acc += K[lane * 6 + a] * v[a];
-        x[lane] += acc;
+        for (int i = 0; i < 6; ++i)
+            if (i <= cc) gp[i * 6 - (i * (i - 1)) / 2 + (cc - i)] = (i == cc) ? r[i] : 2.0 * r[i];
     }
-    // M1 = (I - K H) P : row i = P[i,:] - sum_{a<6} K[i][a] P[a,:]
-    for (int e = lane; e < 81; e += 32) {
-        const int i = e / 9, j = e % 9;
-        double acc = 0.0;
+    if (c == 0) gp[27] = log(fabs(det));
+}
+// d2 = log|det C| + (w - H x)' C^-1 (w - H x)   (Tracking.py:558-560)
+__device__ __forceinline__ double gate_score(const double* gp, const double (&w)[6]) {
+    double y[6];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const double ikh = (k == i ? 1.0 : 0.0) - (k < 6 ? K[i * 6 + k] : 0.0);
-            acc += ikh * P[k * 9 + j];
-        }
-        M1[e] = acc;
+    for (int k = 0; k < 6; ++k) y[k] = w[k] - gp[21 + k];
+    double q = 0.0;
+    int p = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double tb = gp[p++] * y[r];
+#pragma unroll
+        for (int cc = r + 1; cc < 6; ++cc) tb += gp[p++] * y[cc];
+        q += tb * y[r];
     }
-    __syncwarp();                                   // every lane is done with SI before M2 overwrites A|B
-    // M2 = K R  (9x6)
-    for (int e = lane; e < 54; e += 32) {
-        const int i = e / 6, a = e % 6;
+    return gp[27] + q;
+}
+
+// ---- Kalman update (filterpy KalmanFilter.update, Joseph form, H = [I6 0]; Tracking.py:387-398) --------------
+//   y = z - x[:6];  S = P[:6,:6] + R;  K = P[:, :6] S^-1;  x += K y;
+//   P = (I - K H) P (I - K H)' + (K R) K'
+// as element-parallel steps over a track's scratch:  Sm 36 | R 36  and  M1 81 | K 54 | KR 54.
+// step 1 (e < 36): S = P[:6,:6] + R
+__device__ __forceinline__ void kf_update_S(const double* P, const double* R, double* S, const Elem& t) {
+    if (t.e < 36) S[t.e] = P[t.i6 * 9 + t.a6] + R[t.e];
+}
+// step 3 (e < 54): K = P[:, :6] S^-1
+__device__ __forceinline__ void kf_update_K(const double* P, const double* Sinv, double* K, const Elem& t) {
+    if (t.e < 54) {
         double acc = 0.0;
 #pragma unroll
-        for (int b = 0; b < 6; ++b) acc += K[i * 6 + b] * R[b * 6 + a];
-        M2[e] = acc;
+        for (int b = 0; b < 6; ++b) acc += P[t.i6 * 9 + b] * Sinv[b * 6 + t.a6];
+        K[t.e] = acc;
     }
-    __syncwarp();
-    // P = M1 (I-KH)' + M2 K'
-    for (int e = lane; e < 81; e += 32) {
-        const int i = e / 9, j = e % 9;
+}
+// step 4 (e < 81): M1 = (I - K H) P = P - K P[:6, :]   and (e < 54)  KR = K R
+__device__ __forceinline__ void kf_update_M1_KR(const double* P, const double* K, const double* R, double* M1,
+                                                double* KR, const Elem& t) {
+    if (t.e < 81) {
+        double acc = P[t.e];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc -= K[t.i9 * 6 + a] * P[a * 9 + t.j9];
+        M1[t.e] = acc;
+    }
+    if (t.e < 54) {
         double acc = 0.0;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const double ikh = (k == j ? 1.0 : 0.0) - (k < 6 ? K[j * 6 + k] : 0.0);
-            acc += M1[i * 9 + k] * ikh;
-        }
+        for (int b = 0; b < 6; ++b) acc += K[t.i6 * 6 + b] * R[b * 6 + t.a6];
+        KR[t.e] = acc;
+    }
+}
+// x += K (z - x[:6]), row i < 9: returns the new x[i] (the caller writes it after every lane has read the old x).
+__device__ __forceinline__ double kf_update_x(const double* x, const double* z, const double* K, int i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc += K[i * 6 + a] * (z[a] - x[a]);
+    return acc + x[i];
+}
+// step 5 (e < 81): P = M1 (I - K H)' + KR K' = M1 - M1[:, :6] K' + KR K'
+__device__ __forceinline__ void kf_update_P(const double* M1, const double* K, const double* KR, double* P,
+                                            const Elem& t) {
+    if (t.e < 81) {
+        double acc = M1[t.e];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc -= M1[t.i9 * 9 + a] * K[t.j9 * 6 + a];
         double acc2 = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) acc2 += M2[i * 6 + a] * K[j * 6 + a];
-        P[e] = acc + acc2;
+        for (int a = 0; a < 6; ++a) acc2 += KR[t.i9 * 6 + a] * K[t.j9 * 6 + a];
+        P[t.e] = acc + acc2;
     }
-    __syncwarp();
-    if (nudge && lane == 0) {
-        // `abs(variance.any()) > 0.6` is abs(bool) > 0.6, i.e. true iff z[0] != x[0]  (Q12)
-        const double var = z[0] - x[0];
-        const double truth = (var != 0.0) ? 1.0 : 0.0;
-        if (truth > nudge_thres) x[0] += var * nudge_gain;
-    }
-    __syncwarp();
+}
+// The x[0] nudge of Tracking.py:396-398: `abs(variance.any()) > 0.6` is abs(bool) > 0.6, i.e. true iff
+// z[0] != x[0] (Q12); applied when the track got points this frame.
+__device__ __forceinline__ void kf_update_nudge(double* x, const double* z, bool lifetime_zero, double nudge_thres,
+                                                double nudge_gain) {
+    if (!lifetime_zero) return;
+    const double var = z[0] - x[0];
+    const double truth = (var != 0.0) ? 1.0 : 0.0;
+    if (truth > nudge_thres) x[0] += var * nudge_gain;
 }
 
 }  // namespace mmw

@@ -49,6 +49,7 @@ struct mmw_ctx {
     unsigned long long* d_counters = nullptr;
     unsigned long long* d_phase = nullptr;
     bool phase_clocks = false;
+    int32_t* d_scene_stats = nullptr; // [S][8] per-scene counters of the last step (summed on the device)
     int32_t* d_defer = nullptr;      // [2 + S + S]: counter, the work list of dbscan_big_kernel, pose rows per scene, finished-CTA ticket
     bool fold_pose_index = true;     // pose-row scan inside pose_feature_kernel (S <= 4096) instead of pose_index_kernel
     // input staging (host-input path): double-buffered, copied on a side stream so that the upload of frame k+1
@@ -166,7 +167,7 @@ int mmw_destroy(mmw_ctx* x) {
     cudaSetDevice(x->device);
     if (x->stream) cudaStreamSynchronize(x->stream);
     void* ptrs[] = {x->d_export, x->d_export_valid, x->d_tracks, x->d_scenes, x->d_track_ring, x->d_uring, x->d_keypoints, x->d_default_posture,
-                    x->d_assoc, x->d_labels, x->d_counters, x->d_phase, x->d_defer, x->d_pts2[0], x->d_pts2[1], x->d_offsets2[0],
+                    x->d_assoc, x->d_labels, x->d_counters, x->d_phase, x->d_defer, x->d_scene_stats, x->d_pts2[0], x->d_pts2[1], x->d_offsets2[0],
                     x->d_offsets2[1], x->d_dt2[0], x->d_dt2[1], x->d_results[0], x->d_results[1], x->d_blob, x->d_bn1s,
                     x->d_bn1t, x->d_bn2s, x->d_bn2t, x->d_feats, x->d_row_scene, x->d_row_track, x->d_row_slot,
                     x->d_pose_total, x->d_act2, x->d_act3, x->d_pose_out};
@@ -192,6 +193,7 @@ int mmw_reset(mmw_ctx* x) {
     CK(cudaMemsetAsync(x->d_assoc, 0xff, sizeof(int32_t) * (size_t)x->S * x->ncap, x->stream));
     CK(cudaMemsetAsync(x->d_pose_total, 0, sizeof(int), x->stream));
     CK(cudaMemsetAsync(x->d_defer, 0, sizeof(int32_t) * (2 + 2 * (size_t)x->S), x->stream));
+    CK(cudaMemsetAsync(x->d_scene_stats, 0, sizeof(int32_t) * 8 * (size_t)x->S, x->stream));
     return MMW_OK;
 }
 
@@ -275,7 +277,7 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     const int smem = step_smem_bytes(max_points, max_tracks);
-    if ((size_t)smem > prop.sharedMemPerBlockOptin)
+    if ((size_t)smem > prop.sharedMemPerBlockOptin || (size_t)dbscan_big_smem_bytes(max_points) > prop.sharedMemPerBlockOptin)
         return fail(MMW_ERR_CAPACITY, "max_points/max_tracks need more shared memory than one CTA can have");
     mmw_ctx* x = new (std::nothrow) mmw_ctx();
     if (!x) return fail(MMW_ERR_INVALID, "out of host memory");
@@ -306,12 +308,13 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     ALLOC(x->d_counters, sizeof(unsigned long long) * 8);
     ALLOC(x->d_phase, sizeof(unsigned long long) * (16 + 3 * S + 16));
     ALLOC(x->d_defer, sizeof(int32_t) * (2 + 2 * S));
+    ALLOC(x->d_scene_stats, sizeof(int32_t) * 8 * S);
     {
         const char* env = getenv("MMW_POSE_INDEX_FOLD");
         x->fold_pose_index = S <= 4096 && !(env && env[0] == '0');
     }
     for (int i = 0; i < 2; ++i) {
-        ALLOC(x->d_pts2[i], sizeof(float) * kRawCols * S * max_points);
+        ALLOC(x->d_pts2[i], sizeof(float) * kRawCols * S * max_points + 16);
         ALLOC(x->d_offsets2[i], sizeof(int32_t) * (S + 1));
         ALLOC(x->d_dt2[i], sizeof(double) * S);
         ALLOC(x->d_results[i], sizeof(float) * S * max_tracks * MMW_RESULT_FLOATS);
@@ -376,6 +379,7 @@ int mmw_load_pose_weights(mmw_ctx* x, int variant, const float* blob, size_t n) 
     if (n != off[16]) return fail(MMW_ERR_INVALID, "weight blob has the wrong number of floats for this variant");
     CK(cudaSetDevice(x->device));
     CK(cudaStreamSynchronize(x->stream));
+    x->has_weights = false;              // a failed reload must not leave the old pointers in use
     if (x->d_blob) { cudaFree(x->d_blob); x->d_blob = nullptr; }
     for (float** p : {&x->d_bn1s, &x->d_bn1t, &x->d_bn2s, &x->d_bn2t, &x->d_act2, &x->d_act3})
         if (*p) { cudaFree(*p); *p = nullptr; }
@@ -470,6 +474,9 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
         if (total > (size_t)x->S * x->ncap)
             return fail(MMW_ERR_CAPACITY, "more points than n_scenes * max_points_per_frame");
         if (total > 0 && !pts) return fail(MMW_ERR_INVALID, "pts is NULL");
+        for (int i = 0; i < x->S; ++i)
+            if (offsets[i] < 0 || offsets[i] > offsets[i + 1])
+                return fail(MMW_ERR_INVALID, "offsets must be non-negative and non-decreasing");
         const int k = (int)(x->stage_idx++ & 1u);
         // The staging buffer is free once the step kernel that last read it has run.  That event is recorded here, at
         // the head of the NEXT step, where the stream has to wait for the upload anyway -- not behind the previous
@@ -500,6 +507,7 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     a.defer_done = x->d_defer + 1 + 2 * x->S;
     a.defer_list = x->d_defer + 1;
     a.pose_cnt = x->d_defer + 1 + x->S;
+    a.scene_stats = x->d_scene_stats;
     prof_mark(x, MMW_K_STEP);
     CK(launch_step(a, x->stream));
     prof_mark(x, MMW_K_DBSCAN_BIG);
@@ -663,6 +671,9 @@ static int ring_edit(mmw_ctx* x, int scene, bool clear) {
     CK(cudaMemcpy(&sc, x->d_scenes + scene, sizeof(sc), cudaMemcpyDeviceToHost));
     if (clear) {
         sc.ring_n = 0; sc.ring_head = 0; sc.ring_cnt[0] = sc.ring_cnt[1] = sc.ring_cnt[2] = 0;
+        sc.ring_ph_gone = 1;
+    } else if (!sc.ring_ph_gone) {       // the deque still starts with its initial empty frame: that is what pops
+        sc.ring_ph_gone = 1;
     } else if (sc.ring_n > 0) {          // popleft (Tracking.py:66-71)
         sc.ring_cnt[sc.ring_head] = 0;
         sc.ring_head = (sc.ring_head + 1) % x->dc.ring_size;
@@ -747,66 +758,88 @@ __global__ void __launch_bounds__(kStepThreads) dbscan_stage_kernel(DevConfig c,
     for (int b = threadIdx.x; b < B; b += blockDim.x) labels[off + b] = cl[b];
 }
 
-__global__ void kalman_predict_kernel(double* x, double* P, const double* dt, int n, double q_var) {
-    __shared__ double sx[4][9], sP[4][81], tmp[4][81];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 4 + warp;
-    if (i >= n) return;
-    for (int e = lane; e < 81; e += 32) sP[warp][e] = P[(size_t)i * 81 + e];
-    if (lane < 9) sx[warp][lane] = x[(size_t)i * 9 + lane];
+// One CTA of 128 threads per track: the element-parallel steps of linalg.cuh, as the fused step kernel runs them.
+__global__ void __launch_bounds__(128) kalman_predict_kernel(double* x, double* P, const double* dt, int n, double q_var) {
+    __shared__ double sx[9], sP[81], sA[81];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const Elem el(tid);
+    if (tid < 81) sP[tid] = P[(size_t)i * 81 + tid];
+    if (tid < 9) sx[tid] = x[(size_t)i * 9 + tid];
+    __syncthreads();
+    kf_predict_pass1(sP, sA, dt[i], el);
+    __syncthreads();
+    const double xn = tid < 9 ? kf_predict_x(sx, dt[i], tid) : 0.0;
     __syncwarp();
-    warp_kf_predict(sx[warp], sP[warp], dt[i], q_var, tmp[warp], lane);
-    for (int e = lane; e < 81; e += 32) P[(size_t)i * 81 + e] = sP[warp][e];
-    if (lane < 9) x[(size_t)i * 9 + lane] = sx[warp][lane];
+    kf_predict_pass2(sx, xn, sA, sP, dt[i], q_var, el);
+    __syncthreads();
+    if (tid < 81) P[(size_t)i * 81 + tid] = sP[tid];
+    if (tid < 9) x[(size_t)i * 9 + tid] = sx[tid];
 }
 
-__global__ void kalman_update_kernel(double* x, double* P, const double* z, const double* R, const uint8_t* life0,
-                                     int n, double thres, double gain) {
-    __shared__ double sx[4][9], sP[4][81], sz[4][6], sR[4][36], ws[4][kWarpScratch];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 4 + warp;
-    if (i >= n) return;
-    for (int e = lane; e < 81; e += 32) sP[warp][e] = P[(size_t)i * 81 + e];
-    for (int e = lane; e < 36; e += 32) sR[warp][e] = R[(size_t)i * 36 + e];
-    if (lane < 9) sx[warp][lane] = x[(size_t)i * 9 + lane];
-    if (lane < 6) sz[warp][lane] = z[(size_t)i * 6 + lane];
-    __syncwarp();
-    warp_kf_update(sx[warp], sP[warp], sz[warp], sR[warp], life0[i] != 0, thres, gain, ws[warp], lane);
-    for (int e = lane; e < 81; e += 32) P[(size_t)i * 81 + e] = sP[warp][e];
-    if (lane < 9) x[(size_t)i * 9 + lane] = sx[warp][lane];
+__global__ void __launch_bounds__(128) kalman_update_kernel(double* x, double* P, const double* z, const double* R,
+                                                            const uint8_t* life0, int n, double thres, double gain) {
+    __shared__ double sx[9], sP[81], sz[6], sR[36], sS[36], sM1[81], sK[54], sKR[54];
+    const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Elem el(tid);
+    if (tid < 81) sP[tid] = P[(size_t)i * 81 + tid];
+    if (tid < 36) sR[tid] = R[(size_t)i * 36 + tid];
+    if (tid < 9) sx[tid] = x[(size_t)i * 9 + tid];
+    if (tid < 6) sz[tid] = z[(size_t)i * 6 + tid];
+    __syncthreads();
+    kf_update_S(sP, sR, sS, el);
+    __syncthreads();
+    if (warp == 0) {
+        double r[6];
+        (void)inv6_spd_half(lane < 16 ? sS : nullptr, lane, r);
+        __syncwarp();
+        if (lane >= 6 && lane < 12) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sS[k * 6 + (lane - 6)] = r[k];
+        }
+    }
+    __syncthreads();
+    kf_update_K(sP, sS, sK, el);
+    __syncthreads();
+    kf_update_M1_KR(sP, sK, sR, sM1, sKR, el);
+    if (warp == 3) {
+        const double xv = lane < 9 ? kf_update_x(sx, sz, sK, lane) : 0.0;
+        __syncwarp();
+        if (lane < 9) sx[lane] = xv;
+    }
+    __syncthreads();
+    kf_update_P(sM1, sK, sKR, sP, el);
+    if (tid == 96) kf_update_nudge(sx, sz, life0[i] != 0, thres, gain);
+    __syncthreads();
+    if (tid < 81) P[(size_t)i * 81 + tid] = sP[tid];
+    if (tid < 9) x[(size_t)i * 9 + tid] = sx[tid];
 }
 
 __global__ void __launch_bounds__(128) gate_stage_kernel(const double* pts, int M, const double* hx, const double* C,
                                                          int T, double gate, double* d2, int32_t* assoc) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double* cinv = reinterpret_cast<double*>(smem);          // [T][36]
-    double* logdet = cinv + (size_t)T * 36;                   // [T]
-    double* sC = logdet + T;                                  // [4][36]
-    double* aug = sC + 4 * 36;                                // [4][72]
+    double* gp = reinterpret_cast<double*>(smem);             // [T][kGateWords]
+    double* sC = gp + (size_t)T * kGateWords;                 // [T][36]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = warp; j < T; j += 4) {
-        for (int e = lane; e < 36; e += 32) sC[warp * 36 + e] = C[(size_t)j * 36 + e];
-        __syncwarp();
-        const double det = warp_inv6(sC + warp * 36, cinv + j * 36, aug + warp * 72, lane);
-        if (lane == 0) logdet[j] = log(fabs(det));
+    for (int e = threadIdx.x; e < T * 36; e += blockDim.x) sC[e] = C[e];
+    for (int e = threadIdx.x; e < T * 6; e += blockDim.x) gp[(e / 6) * kGateWords + 21 + e % 6] = hx[e];
+    __syncthreads();
+    for (int j0 = 0; j0 < T; j0 += 8) {
+        const int j = j0 + 2 * warp + (lane >> 4);
+        const bool live = j < T;
+        if (__ballot_sync(kFull, live) == 0u) continue;
+        double r[6];
+        const double det = inv6_spd_half(live ? sC + j * 36 : nullptr, lane, r);
+        if (live) gate_pack_half(gp + j * kGateWords, r, det, lane);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        double w[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w[k] = pts[(size_t)i * 6 + k];
         double best = INFINITY;
         int bj = -1;
         for (int j = 0; j < T; ++j) {
-            double y[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) y[k] = pts[(size_t)i * 6 + k] - hx[j * 6 + k];
-            double q = 0.0;
-#pragma unroll
-            for (int b = 0; b < 6; ++b) {
-                double tb = 0.0;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) tb += y[k] * cinv[j * 36 + k * 6 + b];
-                q += tb * y[b];
-            }
-            const double v = logdet[j] + q;
+            const double v = gate_score(gp + j * kGateWords, w);
             d2[(size_t)i * T + j] = v;
             if (v < gate && v < best) { best = v; bj = j; }
         }
@@ -1150,7 +1183,7 @@ int mmw_kalman_predict(mmw_ctx* x, double* hx, double* hP, const double* dt, int
     CK(cudaMemcpyAsync(dx, hx, (size_t)n * 9 * 8, cudaMemcpyHostToDevice, x->stream));
     CK(cudaMemcpyAsync(dP, hP, (size_t)n * 81 * 8, cudaMemcpyHostToDevice, x->stream));
     CK(cudaMemcpyAsync(ddt, dt, (size_t)n * 8, cudaMemcpyHostToDevice, x->stream));
-    kalman_predict_kernel<<<(n + 3) / 4, 128, 0, x->stream>>>(dx, dP, ddt, n, x->dc.q_var);
+    kalman_predict_kernel<<<n, 128, 0, x->stream>>>(dx, dP, ddt, n, x->dc.q_var);
     CK(cudaGetLastError());
     x->launches++;
     CK(cudaMemcpyAsync(hx, dx, (size_t)n * 9 * 8, cudaMemcpyDeviceToHost, x->stream));
@@ -1176,7 +1209,7 @@ int mmw_kalman_update(mmw_ctx* x, double* hx, double* hP, const double* z, const
     CK(cudaMemcpyAsync(dz, z, (size_t)n * 6 * 8, cudaMemcpyHostToDevice, x->stream));
     CK(cudaMemcpyAsync(dR, R, (size_t)n * 36 * 8, cudaMemcpyHostToDevice, x->stream));
     CK(cudaMemcpyAsync(dl, life0, (size_t)n, cudaMemcpyHostToDevice, x->stream));
-    kalman_update_kernel<<<(n + 3) / 4, 128, 0, x->stream>>>(dx, dP, dz, dR, dl, n, x->dc.nudge_thres,
+    kalman_update_kernel<<<n, 128, 0, x->stream>>>(dx, dP, dz, dR, dl, n, x->dc.nudge_thres,
                                                              x->dc.nudge_gain);
     CK(cudaGetLastError());
     x->launches++;
@@ -1205,7 +1238,7 @@ int mmw_gate(mmw_ctx* x, const double* points, int M, const double* hxv, const d
         CK(cudaMemcpyAsync(dh, hxv, (size_t)T * 6 * 8, cudaMemcpyHostToDevice, x->stream));
         CK(cudaMemcpyAsync(dC, C, (size_t)T * 36 * 8, cudaMemcpyHostToDevice, x->stream));
     }
-    const size_t smem = ((size_t)T * 37 + 4 * 36 + 4 * 72) * 8;
+    const size_t smem = ((size_t)(T ? T : 1) * (kGateWords + 36)) * 8;
     CK(cudaFuncSetAttribute(gate_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gate_stage_kernel<<<1, 128, smem, x->stream>>>(dp, M, dh, dC, T, x->dc.gate, dd, da);
     CK(cudaGetLastError());

@@ -67,7 +67,9 @@ struct SceneRec {
     int32_t last_ran;          // 1 if the last frame ran track()
     int32_t dbscan_n;          // fused points clustered in the last frame, -1 if DBSCAN did not run
     int32_t pose_base;         // first pose row of this scene in the last pose batch
-    int32_t pad[3];
+    int32_t ring_ph_gone;      // 0 while the global ring still holds the deque's initial empty frame (RingBuffer.__init__
+                               //   appends init_val, Utils.py:36-50): it is what batch.pop_frame() pops first
+    int32_t pad[2];
 };
 static_assert(sizeof(SceneRec) == 64, "SceneRec is one 64-byte record");
 
@@ -90,10 +92,11 @@ struct StepArgs {
     int32_t* defer_count;      // device counter of defer_list; dbscan_big_kernel's last CTA zeroes it for the next step
     int32_t* defer_done;       // CTAs of dbscan_big_kernel that have finished (ticket for that reset)
     int32_t* pose_cnt;         // [S] tracks of the scene if the frame ran track(), else 0: the pose-row scan reads this
+    int32_t* scene_stats;      // [S][8] this frame's N, M, U, Bf (if DBSCAN ran), tracks, ring rows written, ran, 0:
+                               //   summed into `counters` by dbscan_big_kernel (one reduction instead of 7 atomics per scene)
     int n_scenes;
     uint32_t flags;
 };
-constexpr int kDeferPoints = 160;     // fused clouds larger than this go to dbscan_big_kernel
 
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------------------
 // The seven kernels of a step run back to back on one stream.  Each is launched with
@@ -134,6 +137,27 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     }
     cfg.attrs = at; cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// cudaFuncSetAttribute is per device and a process may hold contexts on several GPUs: every launcher keeps what it
+// has asked for per device.  smem < 0: only the carve-out preference.
+constexpr int kMaxDevices = 64;
+inline cudaError_t ensure_smem_attr(const void* fn, int* configured /*[kMaxDevices], zero-initialised*/, int smem) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    const int want = smem < 0 ? 1 : smem;
+    if (want > configured[dev]) {
+        if (smem >= 0) {
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+        }
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured[dev] = want;
+    }
+    return cudaSuccess;
 }
 
 // ---- world-frame point from a raw sensor point (Utils.py:379-420) -----------------------------------

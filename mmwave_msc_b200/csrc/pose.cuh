@@ -60,6 +60,7 @@ cudaError_t launch_fc1_simt(const FcArgs& a, int max_rows, cudaStream_t st);
 cudaError_t launch_fc2(const Fc2Args& a, int grid, cudaStream_t st);
 
 int step_smem_bytes(int ncap, int tcap);
+int dbscan_big_smem_bytes(int ncap);
 cudaError_t launch_step(const StepArgs& a, cudaStream_t stream);
 cudaError_t launch_dbscan_big(const StepArgs& a, cudaStream_t stream);
 

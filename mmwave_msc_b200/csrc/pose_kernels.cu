@@ -362,12 +362,9 @@ __global__ void __launch_bounds__(128) fc2_kernel(Fc2Args a) {
 
 cudaError_t launch_fc2(const Fc2Args& a, int grid, cudaStream_t st) {
     const size_t smem = (size_t)kFc2Rows * a.H * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static int configured[kMaxDevices] = {0};
+    cudaError_t e = ensure_smem_attr(reinterpret_cast<const void*>(fc2_kernel), configured, 64 * 1024);
+    if (e != cudaSuccess) return e;
     fc2_kernel<<<grid, 128, smem, st>>>(a);
     return cudaGetLastError();
 }
@@ -379,13 +376,9 @@ cudaError_t launch_pose_index(SceneRec* scenes, int S, int* pose_total, unsigned
 }
 
 cudaError_t launch_pose_features(const PoseFeatArgs& a, int S, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {          // same shared-memory carve-out as its neighbours in the step (no SM reconfiguration)
-        cudaError_t e = cudaFuncSetAttribute(pose_feature_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                             cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static int configured[kMaxDevices] = {0};   // same shared-memory carve-out as its neighbours in the step
+    cudaError_t e = ensure_smem_attr(reinterpret_cast<const void*>(pose_feature_kernel), configured, -1);
+    if (e != cudaSuccess) return e;
     return launch_pdl(pose_feature_kernel, dim3(S), dim3(128), 0, st, dim3(1, 1, 1), a);
 }
 

@@ -1,63 +1,81 @@
-// The fused per-frame tracker step: one CTA per scene runs
+// The fused per-frame tracker step: one CTA of 128 threads per scene runs
 //   Utils.normalize_data (Utils.py:342-434) -> TrackBuffer.track (Tracking.py:664-703)
-// i.e. transform+bounds filter+ordered compaction, Kalman predict, Mahalanobis gating and association,
-// per-track cluster statistics and ring push, track maintenance, Kalman update, push of the unassigned
-// points into the scene's global ring, DBSCAN over the fused ring, and track spawning -- with every
-// intermediate in shared memory / registers.  HBM traffic per scene-frame is the raw points in, the track
-// records in and out, the ring rows written and the fused ring read when DBSCAN runs.
+// i.e. transform + bounds filter + ordered compaction, Kalman predict, Mahalanobis gating and association, per-track
+// cluster statistics and ring push, track maintenance, Kalman update, push of the unassigned points into the scene's
+// global ring and the grid screen that decides whether DBSCAN has anything to find -- with every intermediate in
+// shared memory / registers.  HBM traffic per scene-frame is the raw points in, the track records in and out, the
+// ring rows written and the fused ring read by the screen.
+//
+// How the work is laid out (round 2; profiles/r02_*.md):
+//   * inputs arrive by two bulk copies (cp.async.bulk, 1-D TMA) behind one mbarrier: the scene's contiguous block of
+//     raw points (as the 16-byte aligned window around it) and its track records;
+//   * point phases are thread-per-point, two points per thread per tile of 256 -- transform, filter, gate, list
+//     positions, ring pushes all work from registers; only the world 6-vectors of associated points go to shared
+//     memory, in list order, for the statistics;
+//   * track phases are ELEMENT-parallel (linalg.cuh): thread e owns element e of the 9x9 / 9x6 / 6x6 matrices and
+//     the CTA walks the tracks, so all four warps work whatever the number of tracks; the two 6x6 inverses per
+//     track run two tracks per warp (one half warp each);
+//   * per-track statistics: 39 values (6 sums, 21 products, 6 minima, 6 maxima) x 3 slices of the track's list = 117
+//     threads, each a short FMA chain straight from shared memory, combined in a fixed order (deterministic);
+//   * clusters that form are left to dbscan_big_kernel through a work list; this kernel only runs the grid screen.
 #include "dbscan.cuh"
 #include "linalg.cuh"
 #include "mmw_internal.cuh"
 
 namespace mmw {
 
+constexpr int kTile = 2 * kStepThreads;          // points per tile: two per thread
+constexpr int kChunks = kTile / 32;              // warp chunks of 32 consecutive points in a tile
+constexpr int kBw = 72;                          // doubles of per-track scratch B
+constexpr int kGinv = 40, kHx = kGinv + 21, kNest = 68;   // inside B from the gate matrices to the statistics (below)
+constexpr int kNStat = 39;                       // 6 sums + 21 products + 6 minima + 6 maxima, at B[0..38]
+static_assert(kStepThreads == 128, "the element-parallel track phases are written for 128 threads per scene");
+
+// Dynamic shared memory of step_kernel.
+//   tracks  TrackRec [tcap]
+//   B       double [tcap][72]   gate:   C (0..35) -> statistics totals (0..38) | packed C^-1 (40..60) | H x (61..66)
+//                                       | log|det C| (67)
+//                               update: S -> S^-1 (0..35) | Rc (36..71)
+//   A       double [tcap][81]   F P (predict), (I - K H) P (update)
+//   KK      double [tcap][108]  K (0..53) | K Rc (54..107)
+//   aliases: the list of world 6-vectors of a tile's associated points (kTile x 6 doubles) lies over A|KK between the
+//   gate matrices and the update; the staged raw points lie over KK when a frame is a single tile, in their own
+//   space otherwise (they must survive the tile loop); the DBSCAN screen's scratch lies over A|KK at the end.
 struct SmemLayout {
-    // offsets in bytes into dynamic shared memory (kept under 32 KB at N_cap 256 / T_cap 8: 7 CTAs per SM, so the
-    // 1024 scenes of the C2 workload are resident in a single wave)
-    int vel;         // double [3][ncap]: world-frame velocity columns of the compacted frame (sqrt/div: kept);
-                     //   positions are recomputed from craw on use (x is the raw x; y', z' cost 4 mul + 3 add)
-    int craw;        // float [ncap*5] compacted raw points of this frame
-    int assoc;       // uint8 [ncap]: group of each compacted point = track index, or n_tracks for unassigned
-    int dbf;         // float [3][3*ncap]: fp32 world coordinates of the fused ring during DBSCAN; aliases
-                     //   vel|craw|assoc, which are dead by then
-    int tracks;      // TrackRec [tcap]
-    int cinv;        // double [tcap][36]
-    int hx;          // double [tcap][6]
-    int logdet;      // double [tcap]
-    int ws;          // double [warps][kWarpScratch]
-    int par, cl;     // int [3*ncap] each: alias ws (dead during DBSCAN/spawn) when they fit, else their own space
-    int misc;        // ints
-    int total;
+    int tracks, B, A, KK, stage, misc, total;
 };
+constexpr int kMiscInts = 384;
+// misc int slots (slot 0-1: the mbarrier)
+enum { kT1 = 2, kFreed = 3, kScan = 4 /* 2 ints: dbscan_grid_may_have_core */, kCntK = 8 /* 8 */, kCntU = 16 /* 8 */,
+       kBaseG = 24 /* 2 x 32 */, kBaseU = 88 /* 2 */, kOrder = 96 /* 32 */, kCntG = 128 /* 8 x 32 */ };
 
 __host__ __device__ inline SmemLayout make_layout(int ncap, int tcap) {
     SmemLayout L;
-    const int n4 = (ncap + 3) & ~3;
     int o = 0;
-    L.vel = o;     o += 3 * n4 * 8;
-    L.craw = o;    o += n4 * 5 * 4;
-    L.assoc = o;   o += n4;
-    L.dbf = 0;
-    if (o < 36 * n4) o = 36 * n4;                       // (never: 24 + 20 + 1 = 45 bytes per point)
-    o = (o + 15) & ~15;
     L.tracks = o;  o += tcap * (int)sizeof(TrackRec);
-    L.cinv = o;    o += tcap * 36 * 8;
-    L.hx = o;      o += tcap * 6 * 8;
-    L.logdet = o;  o += ((tcap + 1) & ~1) * 8;
-    L.ws = o;
-    const int wsb = kStepWarps * kWarpScratch * 8, dbb = 2 * 3 * n4 * 4;
-    o += wsb > dbb ? wsb : dbb;
-    L.par = L.ws;  L.cl = L.ws + 3 * n4 * 4;
-    L.misc = o;    o += 128 * 4;
+    L.B = o;       o += tcap * kBw * 8;
+    L.A = o;
+    const int a_bytes = (tcap * 81 * 8 + 15) & ~15;      // KK (bulk-copy destination when it stages the points) stays 16-byte aligned
+    int kk_bytes = tcap * 108 * 8;
+    const int stage_bytes = ((ncap * kRawCols * 4 + 15) & ~15) + 32;
+    const bool single = ncap <= kTile;
+    if (single && kk_bytes < stage_bytes) kk_bytes = stage_bytes;
+    int akk = a_bytes + kk_bytes;
+    const int list_bytes = kTile * 6 * 8;
+    const int screen_bytes = 2 * 3 * ncap * 4 + kGridCells * 4;   // fp32 world x, y' of the fused ring + histogram
+    if (akk < list_bytes) akk = list_bytes;
+    if (akk < screen_bytes) akk = screen_bytes;
+    akk = (akk + 15) & ~15;
+    L.KK = L.A + a_bytes;
+    o += akk;
+    L.stage = single ? L.KK : o;
+    if (!single) o += stage_bytes;
+    L.misc = o;    o += kMiscInts * 4;
     L.total = o;
     return L;
 }
 
 int step_smem_bytes(int ncap, int tcap) { return make_layout(ncap, tcap).total; }
-
-// misc int slots
-enum { kM = 0, kNFree = 1, kScan = 4 /* .. +kStepWarps+1 */, kOrder = 16 /* .. +32 */,
-       kFree = 48 /* .. +32 */ };
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -75,29 +93,31 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// Reduce NV per-lane values across the warp so that lane v (< NV) ends up with the total of value v: at every
-// butterfly level a lane keeps one half of its live values and hands the other half to its partner, so the 5 levels
-// cost about NV + log2 shuffles instead of 5 * NV.  The order of the additions is fixed (deterministic results).
-template <int NV, class Op>
-__device__ __forceinline__ double warp_reduce_to_lane(double (&a)[NV], int lane, Op op) {
-    static_assert(NV >= 1 && NV <= 32, "one value per lane at most");
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int k = 0; k < o; ++k) {
-            if (k < NV) {
-                if (k + o < NV) {
-                    const double keep = up ? a[k + o] : a[k];
-                    const double send = up ? a[k] : a[k + o];
-                    a[k] = op(keep, __shfl_xor_sync(kFull, send, o));
-                } else {
-                    a[k] = op(a[k], __shfl_xor_sync(kFull, a[k], o));
-                }
-            }
-        }
-    }
-    return a[0];
+// ---- mbarrier + bulk copy (1-D TMA) ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sk_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sk_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sk_smem(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void sk_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sk_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SK_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SK_DONE;\n\t"
+        "bra SK_WAIT_LOOP;\n\t"
+        "SK_DONE:\n\t"
+        "}" ::"r"(sk_smem(bar)), "r"(parity) : "memory");
+}
+// bytes: a positive multiple of 16; dst (shared) and src (global) 16-byte aligned
+__device__ __forceinline__ void sk_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                     "r"(sk_smem(dst)), "l"(src), "r"(bytes), "r"(sk_smem(bar))
+                 : "memory");
 }
 
 __device__ __forceinline__ const float* uring_frame(const StepArgs& a, int s, int phys) {
@@ -226,6 +246,7 @@ __device__ __forceinline__ NbScreened load_fused_ring(const StepArgs& a, int s, 
 }
 
 
+
 // Optional per-phase cycle accounting (thread 0 of every CTA, accumulated with one atomic per phase).
 #define PHASE_MARK(idx)                                                                  \
     do {                                                                                 \
@@ -251,82 +272,295 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     const DevConfig& c = a.cfg;
     const int ncap = c.ncap, tcap = c.tcap;
     const SmemLayout L = make_layout(ncap, tcap);
-    double* vel = reinterpret_cast<double*>(smem + L.vel);
-    float* craw = reinterpret_cast<float*>(smem + L.craw);
-    uint8_t* assoc = smem + L.assoc;
-    // world-frame 6-vector of compacted point i: positions recomputed (bit-identical to step 1), velocities stored
-    auto load_w = [&](int i, double (&w)[6]) {
-        w[0] = (double)craw[i * kRawCols + 0];
-        world_yz(c, (double)craw[i * kRawCols + 1], (double)craw[i * kRawCols + 2], w[1], w[2]);
-        w[3] = vel[i]; w[4] = vel[ncap + i]; w[5] = vel[2 * ncap + i];
-    };
-    int* par = reinterpret_cast<int*>(smem + L.par);
-    int* cl = reinterpret_cast<int*>(smem + L.cl);
     TrackRec* tr = reinterpret_cast<TrackRec*>(smem + L.tracks);
-    double* cinv = reinterpret_cast<double*>(smem + L.cinv);
-    double* hx = reinterpret_cast<double*>(smem + L.hx);
-    double* logdet = reinterpret_cast<double*>(smem + L.logdet);
-    double* wsall = reinterpret_cast<double*>(smem + L.ws);
+    double* Bm = reinterpret_cast<double*>(smem + L.B);
+    double* Am = reinterpret_cast<double*>(smem + L.A);
+    double* KKm = reinterpret_cast<double*>(smem + L.KK);
+    double* wl = Am;                                            // list of world 6-vectors (aliases A | KK)
     int* misc = reinterpret_cast<int*>(smem + L.misc);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L.misc);
 
     const int s = blockIdx.x;
     if (s >= a.n_scenes) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* ws = wsall + warp * kWarpScratch;
+    const Elem el(tid);
+    const unsigned ltmask = (1u << lane) - 1u;
 
+    // ---- 0. round trip one: scene record, offsets, dt; then the bulk copies ----------------------------------
+    if (tid == 0) sk_mbar_init(mbar, 1);
     SceneRec sc = a.scenes[s];           // every thread keeps a copy; thread 0 writes it back
     const int off = a.offsets[s];
     int N = a.offsets[s + 1] - off;
-    if (N > ncap) { N = ncap; sc.flags |= MMW_SCENE_POINT_OVERFLOW; }
     const double dt = a.dt[s];
-
-    // Issued first, consumed later: this scene's track records (cp.async -> shared memory, waited for in step 2)
-    // and the ring frames DBSCAN will read (L2 prefetch), so their DRAM latency overlaps the point phase.
+    if (N < 0) N = 0;
+    if (N > ncap) { N = ncap; sc.flags |= MMW_SCENE_POINT_OVERFLOW; }
     const int T0 = sc.n_tracks;
-    {
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.tracks + (size_t)s * tcap);
-        unsigned char* dst = reinterpret_cast<unsigned char*>(tr);
-#ifndef MMW_NO_CPASYNC
-        for (int i = tid; i < T0 * (int)(sizeof(TrackRec) / 16); i += kStepThreads)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i * 16)),
-                         "l"(src + i * 16)
-                         : "memory");
-#else
-        (void)src; (void)dst;
-#endif
-        for (int f = 0; f < sc.ring_n; ++f) {
-            const int phys = ring_wrap(sc.ring_head + f, c.ring_size);
-            const char* fr = reinterpret_cast<const char*>(uring_frame(a, s, phys));
-            const int lines = (sc.ring_cnt[phys] * kRawCols * 4 + 127) / 128;
-            for (int i = tid; i < lines; i += kStepThreads)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(fr + i * 128));
+    __syncthreads();                     // the barrier is initialised
+    const size_t byte0 = (size_t)off * (kRawCols * 4);
+    const size_t win0 = byte0 & ~(size_t)15;
+    const uint32_t win_bytes = (uint32_t)(((byte0 + (size_t)N * (kRawCols * 4) + 15) & ~(size_t)15) - win0);
+    const bool bulk_pts = (reinterpret_cast<uintptr_t>(a.pts) & 15) == 0;       // else: plain loads (below)
+    const float* stagef = reinterpret_cast<const float*>(smem + L.stage + (byte0 - win0));
+    if (tid == 0) {
+        const uint32_t tr_bytes = (uint32_t)T0 * (uint32_t)sizeof(TrackRec);
+        sk_mbar_expect_tx(mbar, tr_bytes + (bulk_pts ? win_bytes : 0u));
+        if (tr_bytes) sk_bulk_g2s(tr, a.tracks + (size_t)s * tcap, tr_bytes, mbar);
+        if (bulk_pts && win_bytes)
+            sk_bulk_g2s(smem + L.stage, reinterpret_cast<const unsigned char*>(a.pts) + win0, win_bytes, mbar);
+    }
+    if (!bulk_pts) {
+        float* st = const_cast<float*>(stagef);
+        for (int i = tid; i < N * kRawCols; i += kStepThreads) st[i] = a.pts[(size_t)off * kRawCols + i];
+    }
+    // the ring frames the screen will read: L2 prefetch, their DRAM latency overlaps everything below
+    for (int f = 0; f < sc.ring_n; ++f) {
+        const int phys = ring_wrap(sc.ring_head + f, c.ring_size);
+        const char* fr = reinterpret_cast<const char*>(uring_frame(a, s, phys));
+        const int lines = (sc.ring_cnt[phys] * kRawCols * 4 + 127) / 128;
+        for (int i = tid; i < lines; i += kStepThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(fr + i * 128));
+    }
+    if (tid < 2 * 32 + 2) misc[kBaseG + tid < kBaseG + 64 ? kBaseG + tid : kBaseU + (tid - 64)] = 0;
+    sk_mbar_wait(mbar, 0);
+    if (!bulk_pts) __syncthreads();
+    PHASE_MARK(1);
+
+    // ---- 1. predict (Tracking.py:591-596, Q9) and gate matrices (Tracking.py:545-551) -----------------------
+    // pass 1: A = F P
+    for (int j = 0; j < T0; ++j) kf_predict_pass1(tr[j].P, Am + j * 81, tr[j].lifetime + dt, el);
+    __syncthreads();
+    // pass 2: P = A F' + Q; x = F x; H x for the gate
+    for (int j = 0; j < T0; ++j) {
+        TrackRec& t = tr[j];
+        const double dte = t.lifetime + dt;
+        const double x_new = tid < 9 ? kf_predict_x(t.x, dte, tid) : 0.0;
+        __syncwarp();                    // warp 0: every lane has read the old x
+        kf_predict_pass2(t.x, x_new, Am + j * 81, t.P, dte, c.q_var, el);
+        if (tid < 6) Bm[j * kBw + kHx + tid] = x_new;
+    }
+    __syncthreads();
+    PHASE_MARK(2);
+    // gate matrix C = P[:6,:6] + Rm + G (get_Rm 361-370)
+    for (int j = 0; j < T0; ++j) {
+        if (tid < 36) {
+            const TrackRec& t = tr[j];
+            double v = t.P[el.i6 * 9 + el.a6];
+            if (el.i6 == el.a6) { const double h = t.spread[el.i6] / 2; v += h * h; }
+            Bm[j * kBw + tid] = v + t.G[tid];
         }
     }
-
-    // ---- 1. load, transform, bounds filter, ordered compaction (Utils.py:379-432) ------------------
-    for (int i = tid; i < N * kRawCols; i += kStepThreads) craw[i] = a.pts[(size_t)off * kRawCols + i];
     __syncthreads();
+    // inverse + log|det| of the gate matrices, two tracks per warp; C^-1 is stored as its upper triangle with the
+    // off-diagonal entries doubled (the quadratic form needs 21 products instead of 36).  The half warp then resets
+    // the track's statistics totals, which take the place of C.
+    for (int j0 = 0; j0 < T0; j0 += 2 * kStepWarps) {
+        const int j = j0 + 2 * warp + (lane >> 4);
+        const bool live = j < T0;
+        if (__ballot_sync(kFull, live) == 0u) continue;
+        double r[6];
+        const double det = inv6_spd_half(live ? Bm + j * kBw : nullptr, lane, r);
+        __syncwarp();
+        if (live) {
+            double* bj = Bm + j * kBw;
+            gate_pack_half(bj + kGinv, r, det, lane);
+            for (int v = lane & 15; v < kNStat; v += 16) bj[v] = v < 27 ? 0.0 : (v < 33 ? INFINITY : -INFINITY);
+        }
+    }
+    __syncthreads();
+    PHASE_MARK(3);
+
+    // ---- 2. tiles of 256 points: transform + filter + compaction (Utils.py:379-432), gating + association
+    //         (Tracking.py:553-572, Q14), list positions, ring pushes (Tracking.py:691, 338), statistics ------------
+    const int uphys = sc.ring_n >= c.ring_size ? sc.ring_head : ring_wrap(sc.ring_head + sc.ring_n, c.ring_size);
+    float* udst = const_cast<float*>(uring_frame(a, s, uphys));
+    // role of this thread in the statistics: value v (0..5 sums of w -- the x column is a sum of lattice values and
+    // therefore exact in any order, which keeps centroid[0] bit-identical to numpy's mean: the pose features sort
+    // on x - centroid[0] against zero pads (Utils.py:505-514) --, 6..26 products d_r d_c (r <= c) of d = w - H x,
+    // 27..32 minima of w, 33..38 maxima of w), slice q of the list
+    const int sv = warp * 10 + lane / 3, sq = lane % 3;
+    const bool s_active = lane < 30 && sv < kNStat;
+    int s_ra = 0, s_rb = 6;
+    if (sv < 6) {
+        s_ra = sv;
+    } else if (sv < 27) {
+        int rem = sv - 6, r = 0;
+        while (rem >= 6 - r) { rem -= 6 - r; ++r; }
+        s_ra = r; s_rb = r + rem;
+    } else {
+        s_ra = (sv - 27) % 6;
+    }
     int M = 0;
-    for (int base = 0; base < N; base += kStepThreads) {
-        const int i = base + tid;
-        float r5[kRawCols];
-        double w[6];
-        bool keep = false;
-        if (i < N) {
+    const int ntiles = (N + kTile - 1) / kTile;
+    for (int tile = 0; tile < ntiles; ++tile) {
+        float raw[2][kRawCols];
+        double w[2][6];
+        unsigned km[2];
 #pragma unroll
-            for (int k = 0; k < kRawCols; ++k) r5[k] = craw[i * kRawCols + k];
-            world_from_raw(c, r5[0], r5[1], r5[2], r5[3], w);
-            keep = (w[2] <= c.z_max) && (w[2] > 0.0) && (w[1] > 0.0);      // Utils.py:423-427
+        for (int r2 = 0; r2 < 2; ++r2) {
+            const int i = tile * kTile + r2 * kStepThreads + tid;
+            bool keep = false;
+            if (i < N) {
+#pragma unroll
+                for (int k = 0; k < kRawCols; ++k) raw[r2][k] = stagef[i * kRawCols + k];
+                world_from_raw(c, raw[r2][0], raw[r2][1], raw[r2][2], raw[r2][3], w[r2]);
+                keep = (w[r2][2] <= c.z_max) && (w[r2][2] > 0.0) && (w[r2][1] > 0.0);      // Utils.py:423-427
+            }
+            km[r2] = __ballot_sync(kFull, keep);
+            if (lane == 0) misc[kCntK + r2 * kStepWarps + warp] = __popc(km[r2]);
         }
-        int tot;
-        const int pos = M + block_rank(keep, &tot, misc + kScan);   // syncs: all rows of this chunk are in registers
-        if (keep) {
+        __syncthreads();
+        PHASE_MARK(4);
+        int pos[2], tile_kept = 0;
+        {
+            int pre0 = 0, pre1 = 0;
 #pragma unroll
-            for (int k = 0; k < kRawCols; ++k) craw[pos * kRawCols + k] = r5[k];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) vel[k * ncap + pos] = w[3 + k];
+            for (int c2 = 0; c2 < kChunks; ++c2) {
+                const int v = misc[kCntK + c2];
+                tile_kept += v;
+                if (c2 < warp) pre0 += v;
+                if (c2 < kStepWarps + warp) pre1 += v;
+            }
+            pos[0] = M + pre0 + __popc(km[0] & ltmask);
+            pos[1] = M + pre1 + __popc(km[1] & ltmask);
         }
-        M += tot;
+        // gate: d2 = log|det C| + y' C^-1 y < gate, arg-min over the gated tracks, ties -> lower index
+        int grp[2];
+#pragma unroll
+        for (int r2 = 0; r2 < 2; ++r2) {
+            grp[r2] = 255;
+            if ((km[r2] >> lane) & 1u) {
+                double best = INFINITY;
+                int bj = -1;
+                for (int j = 0; j < T0; ++j) {
+                    const double d2 = gate_score(Bm + j * kBw + kGinv, w[r2]);
+                    if (d2 < c.gate && d2 < best) { best = d2; bj = j; }
+                }
+                grp[r2] = bj < 0 ? T0 : bj;
+                a.assoc_out[off + pos[r2]] = bj;
+            }
+        }
+        // per chunk and group: count (lane j keeps track j's) and this point's rank inside its group
+        int rk[2] = {0, 0};
+        {
+            int cj[2] = {0, 0};
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2) {
+                for (int j = 0; j < T0; ++j) {
+                    const unsigned b = __ballot_sync(kFull, grp[r2] == j);
+                    if (grp[r2] == j) rk[r2] = __popc(b & ltmask);
+                    if (lane == j) cj[r2] = __popc(b);
+                }
+                const unsigned bu = __ballot_sync(kFull, grp[r2] == T0);
+                if (grp[r2] == T0) rk[r2] = __popc(bu & ltmask);
+                if (lane < T0) misc[kCntG + (r2 * kStepWarps + warp) * 32 + lane] = cj[r2];
+                if (lane == 0) misc[kCntU + r2 * kStepWarps + warp] = __popc(bu);
+            }
+        }
+        __syncthreads();
+        PHASE_MARK(5);
+        // lane j: points of track j in this tile, where this warp's two chunks start inside its list, the number of
+        // points it had before this tile; the tile-local list of track j starts at the exclusive scan over j
+        int tot = 0, preg[2] = {0, 0}, base = 0, start;
+        {
+            if (lane < T0) {
+#pragma unroll
+                for (int c2 = 0; c2 < kChunks; ++c2) {
+                    const int v = misc[kCntG + c2 * 32 + lane];
+                    tot += v;
+                    if (c2 < warp) preg[0] += v;
+                    if (c2 < kStepWarps + warp) preg[1] += v;
+                }
+                base = misc[kBaseG + (tile & 1) * 32 + lane];
+            }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += up;
+            }
+            start = incl - tot;
+        }
+        int ubase = misc[kBaseU + (tile & 1)], utot = 0, preu[2] = {0, 0};
+#pragma unroll
+        for (int c2 = 0; c2 < kChunks; ++c2) {
+            const int v = misc[kCntU + c2];
+            utot += v;
+            if (c2 < warp) preu[0] += v;
+            if (c2 < kStepWarps + warp) preu[1] += v;
+        }
+        if (warp == 0) {                 // running counts for the next tile (double-buffered: others still read these)
+            if (lane < T0) misc[kBaseG + ((tile + 1) & 1) * 32 + lane] = base + tot;
+            if (lane == 0) misc[kBaseU + ((tile + 1) & 1)] = ubase + utot;
+        }
+#pragma unroll
+        for (int r2 = 0; r2 < 2; ++r2) {
+            const int g = grp[r2];
+            const int gs = g < T0 ? g : 0;
+            const int gb = __shfl_sync(kFull, base, gs), gp0 = __shfl_sync(kFull, preg[r2], gs),
+                      gst = __shfl_sync(kFull, start, gs);
+            if (g < T0) {
+                const int lp = gb + gp0 + rk[r2];                // position in the track's cloud of this frame
+                const int tl = gst + gp0 + rk[r2];               // position in the tile's list
+#pragma unroll
+                for (int k = 0; k < 6; ++k) wl[tl * 6 + k] = w[r2][k];
+                if (lp < kFeatPts) {
+                    // first 64 associated rows in input order are what format_single_frame can see
+                    const TrackRec& t = tr[g];
+                    const int phys = t.ring_n >= c.ring_size ? t.ring_head : ring_wrap(t.ring_head + t.ring_n, c.ring_size);
+                    float* dst = a.track_ring + (((size_t)s * tcap + t.slot) * kRing + phys) * (kFeatPts * kRawCols) +
+                                 (size_t)lp * kRawCols;
+#pragma unroll
+                    for (int k = 0; k < kRawCols; ++k) dst[k] = raw[r2][k];
+                }
+            } else if (g == T0) {
+                // BatchedData.add_frame(unassigned): the oldest frame is dropped when the ring is full
+                float* dst = udst + (size_t)(ubase + preu[r2] + rk[r2]) * kRawCols;
+#pragma unroll
+                for (int k = 0; k < kRawCols; ++k) dst[k] = raw[r2][k];
+            }
+        }
+        M += tile_kept;
+        __syncthreads();
+        PHASE_MARK(6);
+        // statistics of this tile's lists (PointCluster, Tracking.py:120-136; _get_D 270-290 about H x instead of the
+        // centroid: E[d d'] - m m' with d = w - H x, m = centroid - H x below the gate radius, so nothing cancels)
+        for (int j = 0; j < T0; ++j) {
+            const int nj = __shfl_sync(kFull, tot, j), st = __shfl_sync(kFull, start, j);
+            if (nj == 0) continue;
+            const double* hxj = Bm + j * kBw + kHx;
+            const bool is_mom = sv < 27, is_max = sv >= 33;
+            double acc = is_mom ? 0.0 : (is_max ? -INFINITY : INFINITY);
+            if (s_active) {
+                if (is_mom) {
+                    const double ha = s_rb < 6 ? hxj[s_ra] : 0.0, hb = s_rb < 6 ? hxj[s_rb] : 0.0;
+                    const int rb = s_rb < 6 ? s_rb : 0;
+                    for (int k = sq; k < nj; k += 3) {
+                        const double* wp = wl + (st + k) * 6;
+                        const double pa = wp[s_ra] - ha;
+                        const double pb = s_rb < 6 ? wp[rb] - hb : 1.0;
+                        acc += pa * pb;
+                    }
+                } else {
+                    for (int k = sq; k < nj; k += 3) {
+                        const double x = wl[(st + k) * 6 + s_ra];
+                        acc = is_max ? (x > acc ? x : acc) : (x < acc ? x : acc);
+                    }
+                }
+            }
+            // the three slices of a value sit in adjacent lanes; fixed order of combination
+            const double a1 = __shfl_down_sync(kFull, acc, 1), a2 = __shfl_down_sync(kFull, acc, 2);
+            if (is_mom) {
+                acc = (acc + a1) + a2;
+            } else if (is_max) {
+                acc = a1 > acc ? a1 : acc; acc = a2 > acc ? a2 : acc;
+            } else {
+                acc = a1 < acc ? a1 : acc; acc = a2 < acc ? a2 : acc;
+            }
+            if (s_active && sq == 0) {
+                double* tv = Bm + j * kBw + sv;
+                const double old = *tv;
+                *tv = sv < 27 ? old + acc : (sv < 33 ? (acc < old ? acc : old) : (acc > old ? acc : old));
+            }
+        }
         __syncthreads();
     }
     for (int i = M + tid; i < N; i += kStepThreads) a.assoc_out[off + i] = -2;
@@ -334,244 +568,52 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     sc.last_M = M;
     sc.dbscan_n = -1;
     if (M == 0) {                        // offline_main.py:55: the frame is skipped entirely (Q23)
-        asm volatile("cp.async.wait_all;" ::: "memory");
         if (tid == 0) {
             sc.last_ran = 0;
             a.scenes[s] = sc;
             a.pose_cnt[s] = 0;
-            atomicAdd(&a.counters[1], (unsigned long long)N);
+            int4* st4 = reinterpret_cast<int4*>(a.scene_stats + (size_t)s * 8);
+            st4[0] = make_int4(N, 0, 0, 0);
+            st4[1] = make_int4(0, 0, 0, 0);
         }
         return;
     }
     sc.last_ran = 1;
+    const int U = misc[kBaseU + (ntiles & 1)];
+    PHASE_MARK(7);
 
-    PHASE_MARK(1);
-    // ---- 2. load this scene's track records -----------------------------------------------------------
-#ifndef MMW_NO_CPASYNC
-    asm volatile("cp.async.wait_all;" ::: "memory");
-#else
-    {
-        const double* src = reinterpret_cast<const double*>(a.tracks + (size_t)s * tcap);
-        double* dst = reinterpret_cast<double*>(tr);
-        for (int i = tid; i < T0 * kTrackWords; i += kStepThreads) dst[i] = src[i];
-    }
-#endif
-    __syncthreads();
-
-    PHASE_MARK(2);
-    // ---- 3. predict (Tracking.py:591-596, Q9) and gate matrices (Tracking.py:545-551) ---------------
-    for (int j = warp; j < T0; j += kStepWarps) {
-        TrackRec& t = tr[j];
-        warp_kf_predict(t.x, t.P, t.lifetime + dt, c.q_var, ws + kWsM1, lane);
-        double* C = ws + kWsA;
-        for (int e = lane; e < 36; e += 32) {
-            const int r = e / 6, q = e % 6;
-            double v = t.P[r * 9 + q];
-            if (r == q) { const double h = t.spread[r] / 2; v += h * h; }   // get_Rm (361-370)
-            C[e] = v + t.G[e];
-        }
-        if (lane < 6) hx[j * 6 + lane] = t.x[lane];
-        __syncwarp();
-        const double det = warp_inv6(C, cinv + j * 36, ws + kWsAug, lane);
-        if (lane == 0) logdet[j] = log(fabs(det));
-    }
-    __syncthreads();
-
-    PHASE_MARK(3);
-    // ---- 4. gating + association (Tracking.py:553-572, Q14) -------------------------------------------
-    // Besides the decision per point this phase builds, in input order, the index list of every group (group j < T0:
-    // the points gated into track j; then the unassigned points).  Warp w owns a contiguous run of 32-point chunks
-    // and counts its points per group (lane j keeps track j's count); after one barrier every warp knows where its
-    // run starts inside each list, places its indices and pushes the raw rows into the rings (Tracking.py:691, 338)
-    // with one thread per point.  The per-track statistics below then walk a compact list.
-    uint16_t* lst = reinterpret_cast<uint16_t*>(wsall);              // [M]; the warp scratch is idle in phases 4-6
-    int* wtot = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(wsall) + 2 * ((ncap + 3) & ~3));   // [33][warps]
-    const unsigned ltmask = (1u << lane) - 1u;
-    const int nchunk = (M + 31) >> 5, cpw = (nchunk + kStepWarps - 1) / kStepWarps;
-    const int ch0 = warp * cpw, ch1 = min(nchunk, ch0 + cpw);
-    {
-        int cntj = 0, cntu = 0;
-        for (int ch = ch0; ch < ch1; ++ch) {
-            const int i = ch * 32 + lane;
-            int g = 255;
-            if (i < M) {
-                double p[6];
-                load_w(i, p);
-                double best = INFINITY;
-                int bj = -1;
-                for (int j = 0; j < T0; ++j) {
-                    double y[6];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) y[k] = p[k] - hx[j * 6 + k];
-                    const double* Ci = cinv + j * 36;
-                    double q = 0.0;
-#pragma unroll
-                    for (int b = 0; b < 6; ++b) {
-                        double tb = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) tb += y[k] * Ci[k * 6 + b];
-                        q += tb * y[b];
-                    }
-                    const double d2 = logdet[j] + q;
-                    if (d2 < c.gate && d2 < best) { best = d2; bj = j; }
-                }
-                g = bj < 0 ? T0 : bj;
-                assoc[i] = (uint8_t)g;
-                a.assoc_out[off + i] = bj;
-            }
-            for (int j = 0; j < T0; ++j) {
-                const unsigned b = __ballot_sync(kFull, g == j);
-                if (lane == j) cntj += __popc(b);
-            }
-            cntu += __popc(__ballot_sync(kFull, g == T0));
-        }
-        if (lane < T0) wtot[lane * kStepWarps + warp] = cntj;
-        if (lane == 0) wtot[kMaxTcap * kStepWarps + warp] = cntu;
-    }
-    __syncthreads();
-    // lane j: size and start of track j's list, and where this warp's run begins inside it
-    int totj = 0, startj, runj = 0, U, runu = 0;
-    {
-        if (lane < T0)
-            for (int w = 0; w < kStepWarps; ++w) {
-                const int cw = wtot[lane * kStepWarps + w];
-                totj += cw;
-                if (w < warp) runj += cw;
-            }
-        int incl = totj;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int up = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += up;
-        }
-        startj = incl - totj;
-        runj += startj;
-        U = 0;
-        for (int w = 0; w < kStepWarps; ++w) {
-            const int cw = wtot[kMaxTcap * kStepWarps + w];
-            U += cw;
-            if (w < warp) runu += cw;
-        }
-        runu += __shfl_sync(kFull, incl, 31);                         // the unassigned list follows the tracks' lists
-    }
-    const int uphys = sc.ring_n >= c.ring_size ? sc.ring_head : ring_wrap(sc.ring_head + sc.ring_n, c.ring_size);
-    {
-        // BatchedData.add_frame(unassigned): the oldest frame is dropped when the ring is full
-        float* udst = const_cast<float*>(uring_frame(a, s, uphys));
-        const int ustart = M - U;
-        for (int ch = ch0; ch < ch1; ++ch) {
-            const int i = ch * 32 + lane;
-            const int g = i < M ? (int)assoc[i] : 255;
-            int pos = 0;
-            for (int j = 0; j < T0; ++j) {
-                const unsigned b = __ballot_sync(kFull, g == j);
-                const int basej = __shfl_sync(kFull, runj, j);
-                if (g == j) pos = basej + __popc(b & ltmask);
-                if (lane == j) runj += __popc(b);
-            }
-            {
-                const unsigned b = __ballot_sync(kFull, g == T0);
-                if (g == T0) pos = runu + __popc(b & ltmask);
-                runu += __popc(b);
-            }
-            const int gstart = __shfl_sync(kFull, startj, g < 32 ? g : 0);
-            if (i < M) {
-                lst[pos] = (uint16_t)i;
-                float* dst = nullptr;
-                if (g == T0) {
-                    dst = udst + (size_t)(pos - ustart) * kRawCols;
-                } else if (pos - gstart < kFeatPts) {
-                    // first 64 associated rows in input order are what format_single_frame can see
-                    const TrackRec& t = tr[g];
-                    const int phys = t.ring_n >= c.ring_size ? t.ring_head : ring_wrap(t.ring_head + t.ring_n, c.ring_size);
-                    dst = a.track_ring + (((size_t)s * tcap + t.slot) * kRing + phys) * (kFeatPts * kRawCols) +
-                          (size_t)(pos - gstart) * kRawCols;
-                }
-                if (dst != nullptr) {
-#pragma unroll
-                    for (int k = 0; k < kRawCols; ++k) dst[k] = craw[i * kRawCols + k];
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    PHASE_MARK(4);
-    // ---- 5. per-track association (Tracking.py:648-653, 314-341) ---------------------------------------
+    // ---- 3. per-track association results (Tracking.py:648-653, 314-341) ------------------------------------
     int ring_rows = 0;
-    for (int g = warp; g < T0; g += kStepWarps) {
-        TrackRec& t = tr[g];
-        const int n = __shfl_sync(kFull, totj, g), start = __shfl_sync(kFull, startj, g);
+    for (int j = 0; j < T0; ++j) {
+        TrackRec& t = tr[j];
+        const int n = misc[kBaseG + (ntiles & 1) * 32 + j];
+        ring_rows += n < kFeatPts ? n : kFeatPts;
         if (n == 0) {
-            if (lane == 0) t.lifetime += dt;                     // update_lifetime(dt) (400-407)
+            if (tid == 0) t.lifetime += dt;                      // update_lifetime(dt) (400-407)
+            if (tid == 96) Bm[j * kBw + kNest] = t.n_est;
             continue;
         }
-        // PointCluster statistics (Tracking.py:120-136): sums in a[0..5]; minima and negated maxima share one array
-        double cen[6], mnv, mxv;
-        {
-            double sa[6], mm[12];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { sa[k] = 0.0; mm[k] = INFINITY; mm[6 + k] = INFINITY; }
-            for (int k0 = lane; k0 < n; k0 += 32) {
-                double w[6];
-                load_w((int)lst[start + k0], w);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    sa[k] += w[k];
-                    mm[k] = w[k] < mm[k] ? w[k] : mm[k];             // plain compare-select: no NaNs to honour here
-                    mm[6 + k] = -w[k] < mm[6 + k] ? -w[k] : mm[6 + k];
-                }
-            }
-            const double ssum = warp_reduce_to_lane(sa, lane, [](double u, double v) { return u + v; });
-            const double smin = warp_reduce_to_lane(mm, lane, [](double u, double v) { return v < u ? v : u; });
-#pragma unroll
-            for (int k = 0; k < 6; ++k) cen[k] = __shfl_sync(kFull, ssum, k) / (double)n;
-            mnv = smin;                                          // lane m < 6: min of column m
-            mxv = -__shfl_sync(kFull, smin, (lane + 6) & 31);    // lane m < 6: max of column m
-        }
-        // dispersion matrix about the centroid (population covariance, _get_D 270-290); entry p lands in lane p
-        double cov;
-        {
-            double acc[21];
-#pragma unroll
-            for (int p = 0; p < 21; ++p) acc[p] = 0.0;
-            for (int k0 = lane; k0 < n; k0 += 32) {
-                double d[6];
-                load_w((int)lst[start + k0], d);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) d[k] -= cen[k];
-                int p = 0;
-#pragma unroll
-                for (int r = 0; r < 6; ++r)
-#pragma unroll
-                    for (int q = r; q < 6; ++q) acc[p++] += d[r] * d[q];
-            }
-            cov = warp_reduce_to_lane(acc, lane, [](double u, double v) { return u + v; }) / (double)n;
-        }
-        const int phys = t.ring_n >= c.ring_size ? t.ring_head : ring_wrap(t.ring_head + t.ring_n, c.ring_size);
+        const double* tv = Bm + j * kBw;
+        const double dn = (double)n;
         double n_est = t.n_est;
         if (c.enable_est) {                                      // _estimate_point_num (232-244)
-            if ((double)n > n_est) n_est = (double)n;
-            else n_est = (1 - c.a_n) * n_est + c.a_n * (double)n;
+            if (dn > n_est) n_est = dn;
+            else n_est = (1 - c.a_n) * n_est + c.a_n * dn;
         } else {
             n_est = (double)(n > c.est_pointnum ? n : c.est_pointnum);
         }
-        __syncwarp();
-        if (lane == 0) {
-            if (t.ring_n >= c.ring_size) t.ring_head = ring_wrap(t.ring_head + 1, c.ring_size);
-            else t.ring_n += 1;
-            t.ring_cnt[phys] = n < kFeatPts ? n : kFeatPts;
-            t.lifetime = 0.0;
-            t.point_num = n;
-            t.is_static = sqrt(cen[3] * cen[3] + cen[4] * cen[4] + cen[5] * cen[5]) < c.vel_thres ? 1 : 0;
-            t.n_est = n_est;
-        }
-        if (lane < 6) {                                          // _estimate_measurement_spread (246-268)
-            const int m = lane;
-            double cm = cen[0];
-#pragma unroll
-            for (int k = 1; k < 6; ++k) cm = (m == k) ? cen[k] : cm;
-            t.centroid[m] = cm;
+        if (tid < 36) {                                          // _estimate_group_disp_matrix (292-297)
+            int r = el.i6, q = el.a6;
+            if (r > q) { const int tmp = r; r = q; q = tmp; }
+            const int p = r * 6 - (r * (r - 1)) / 2 + (q - r);
+            const double mr = tv[r] / dn - tv[kHx + r], mq = tv[q] / dn - tv[kHx + q];
+            const double dv = tv[6 + p] / dn - mr * mq;
+            const double al = dn / n_est;
+            t.G[tid] = (1 - al) * t.G[tid] + al * dv;
+        } else if (tid >= 64 && tid < 70) {                      // centroid, extrema, _estimate_measurement_spread (246-268)
+            const int m = tid - 64;
+            const double mnv = tv[27 + m], mxv = tv[33 + m];
+            t.centroid[m] = tv[m] / dn;
             t.minv[m] = mnv;
             t.maxv[m] = mxv;
             double spread = mxv - mnv;
@@ -580,178 +622,175 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
             spread = fmax(c.spread_lim[m], spread);
             if (spread > t.spread[m]) t.spread[m] = spread;
             else t.spread[m] = (1.0 - c.a_spr) * t.spread[m] + c.a_spr * spread;
-        }
-        {                                                        // _estimate_group_disp_matrix (292-297)
-            const double al = (double)n / n_est;
-#pragma unroll
-            for (int e0 = 0; e0 < 64; e0 += 32) {
-                const int e = e0 + lane;
-                int r = e / 6, q = e % 6;
-                if (r > q) { const int tmp = r; r = q; q = tmp; }
-                const int p = e < 36 ? r * 6 - (r * (r - 1)) / 2 + (q - r) : 0;
-                const double dv = __shfl_sync(kFull, cov, p);
-                if (e < 36) t.G[e] = (1 - al) * t.G[e] + al * dv;
-            }
-        }
-        if (lane == 0) ring_rows += (n < kFeatPts ? n : kFeatPts);
-        __syncwarp();
+        } else if (tid == 96) {
+            const int phys = t.ring_n >= c.ring_size ? t.ring_head : ring_wrap(t.ring_head + t.ring_n, c.ring_size);
+            if (t.ring_n >= c.ring_size) t.ring_head = ring_wrap(t.ring_head + 1, c.ring_size);
+            else t.ring_n += 1;
+            t.ring_cnt[phys] = n < kFeatPts ? n : kFeatPts;
+            t.lifetime = 0.0;
+            t.point_num = n;
+            const double c3 = tv[3] / dn, c4 = tv[4] / dn, c5 = tv[5] / dn;
+            t.is_static = sqrt(c3 * c3 + c4 * c4 + c5 * c5) < c.vel_thres ? 1 : 0;
+            Bm[j * kBw + kNest] = n_est;             // written to the record by the maintenance warp: the
+        }                                                        // threads above still read the old value
     }
-    __syncthreads();
     {
+        if (!sc.ring_ph_gone && sc.ring_n + 1 >= c.ring_size) sc.ring_ph_gone = 1;   // the deque's initial empty frame
         if (sc.ring_n >= c.ring_size) sc.ring_head = ring_wrap(sc.ring_head + 1, c.ring_size);
         else sc.ring_n += 1;
         sc.ring_cnt[uphys] = U;
     }
+    __syncthreads();
+    PHASE_MARK(8);
 
-    PHASE_MARK(5);
-    // ---- 6. maintenance (Tracking.py:513-528, Q16): drop timed-out tracks, keep list order -----------
-    if (tid == 0) {
-        int nk = 0, nf = 0;
-        for (int k = 0; k < T0; ++k) {
-            const double lim = tr[k].is_static ? c.life_sta : c.life_dyn;
-            if (tr[k].lifetime > lim) misc[kFree + nf++] = tr[k].slot;     // INACTIVE: dropped from the list
-            else misc[kOrder + nk++] = k;
+    // ---- 4. maintenance (Tracking.py:513-528, Q16): drop timed-out tracks, keep list order -------------------
+    if (warp == 0) {
+        bool keep = false;
+        unsigned slotbit = 0u;
+        if (lane < T0) {
+            const double lim = tr[lane].is_static ? c.life_sta : c.life_dyn;
+            keep = !(tr[lane].lifetime > lim);                   // dropped tracks are INACTIVE: off the list
+            tr[lane].n_est = Bm[lane * kBw + kNest];
+            if (!keep) slotbit = 1u << tr[lane].slot;
         }
-        misc[kM] = nk;
-        misc[kNFree] = nf;
+        const unsigned kmask = __ballot_sync(kFull, keep);
+        const unsigned freed = __reduce_or_sync(kFull, slotbit);
+        if (keep) misc[kOrder + __popc(kmask & ltmask)] = lane;
+        if (lane == 0) { misc[kT1] = __popc(kmask); misc[kFreed] = (int)freed; }
     }
     __syncthreads();
-    const int T1 = misc[kM];
-    for (int k = 0; k < misc[kNFree]; ++k) sc.slot_mask &= ~(1u << misc[kFree + k]);
+    const int T1 = misc[kT1];
+    sc.slot_mask &= ~(unsigned)misc[kFreed];
+    PHASE_MARK(9);
 
-    PHASE_MARK(6);
-    // ---- 7. update every surviving track (Tracking.py:598-603, 387-398; Q11-Q13) ---------------------
-    for (int k = warp; k < T1; k += kStepWarps) {
-        TrackRec& t = tr[misc[kOrder + k]];
-        // _get_Rc (299-312): Rm/N + ((N_est - N)/((N_est - 1) N)) * group_disp_est
-        double* Rc = cinv + misc[kOrder + k] * 36;   // the gate matrices are dead by now: reuse as R storage
-        const double Nn = (double)t.point_num;
-        const double coef = div_zero_fast(t.n_est - Nn, (t.n_est - 1.0) * Nn);     // N_est == N: zero numerator
-        for (int e = lane; e < 36; e += 32) {
-            const int r = e / 6, q = e % 6;
+    // ---- 5. update every surviving track (Tracking.py:598-603, 387-398; Q11-Q13) ----------------------------
+    // _get_Rc (299-312): Rm/N + ((N_est - N)/((N_est - 1) N)) * group_disp_est;  S = P[:6,:6] + Rc
+    for (int k = 0; k < T1; ++k) {
+        if (tid < 36) {
+            const int j = misc[kOrder + k];
+            const TrackRec& t = tr[j];
+            const double Nn = (double)t.point_num;
+            const double coef = div_zero_fast(t.n_est - Nn, (t.n_est - 1.0) * Nn);     // N_est == N: zero numerator
             double rm = 0.0;
-            if (r == q) { const double h = t.spread[r] / 2; rm = h * h; }
-            Rc[e] = div_zero_fast(rm, Nn) + coef * t.G[e];                        // rm is zero off the diagonal
+            if (el.i6 == el.a6) { const double h = t.spread[el.i6] / 2; rm = (h * h) / Nn; }
+            const double rc = rm + coef * t.G[tid];
+            double* b = Bm + j * kBw;
+            b[36 + tid] = rc;
+            b[tid] = t.P[el.i6 * 9 + el.a6] + rc;
         }
-        __syncwarp();
-        warp_kf_update(t.x, t.P, t.centroid, Rc, t.lifetime == 0.0, c.nudge_thres, c.nudge_gain, ws, lane);
     }
     __syncthreads();
+    for (int k0 = 0; k0 < T1; k0 += 2 * kStepWarps) {
+        const int k = k0 + 2 * warp + (lane >> 4);
+        const bool live = k < T1;
+        if (__ballot_sync(kFull, live) == 0u) continue;
+        const int j = live ? misc[kOrder + k] : 0;
+        double r[6];
+        (void)inv6_spd_half(live ? Bm + j * kBw : nullptr, lane, r);
+        __syncwarp();
+        const int cl16 = lane & 15;
+        if (live && cl16 >= 6 && cl16 < 12) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Bm[j * kBw + i * 6 + (cl16 - 6)] = r[i];
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < T1; ++k) {
+        const int j = misc[kOrder + k];
+        kf_update_K(tr[j].P, Bm + j * kBw, KKm + j * 108, el);
+    }
+    __syncthreads();
+    for (int k = 0; k < T1; ++k) {
+        const int j = misc[kOrder + k];
+        TrackRec& t = tr[j];
+        kf_update_M1_KR(t.P, KKm + j * 108, Bm + j * kBw + 36, Am + j * 81, KKm + j * 108 + 54, el);
+        if (warp == 3) {
+            double xv = 0.0;
+            if (lane < 9) xv = kf_update_x(t.x, t.centroid, KKm + j * 108, lane);
+            __syncwarp();
+            if (lane < 9) t.x[lane] = xv;
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < T1; ++k) {
+        const int j = misc[kOrder + k];
+        TrackRec& t = tr[j];
+        kf_update_P(Am + j * 81, KKm + j * 108, KKm + j * 108 + 54, t.P, el);
+        if (tid == 96) kf_update_nudge(t.x, t.centroid, t.lifetime == 0.0, c.nudge_thres, c.nudge_gain);
+    }
+    __syncthreads();
+    PHASE_MARK(10);
 
-    PHASE_MARK(7);
-    // ---- 8. DBSCAN over the fused global ring (Tracking.py:693-700) -----------------------------------
-    int B = 0;
+    // ---- 6. DBSCAN over the fused global ring (Tracking.py:693-700): the grid screen --------------------------
+    int Bf = 0;
     int fcnt[kRing], fphys[kRing];
     for (int f = 0; f < kRing; ++f) {
         fphys[f] = ring_wrap(sc.ring_head + f, c.ring_size);
         fcnt[f] = f < sc.ring_n ? sc.ring_cnt[fphys[f]] : 0;
-        B += fcnt[f];
+        Bf += fcnt[f];
     }
-    int ncl = 0;
-    const bool run_db = B > 0 && T1 < c.tr_max_tracks;
-    // Big fused clouds (someone walked in: hundreds of points) are rare -- a couple of scenes per frame -- but cost
-    // several times a normal scene-frame and would set this kernel's duration.  They are handed to
-    // dbscan_big_kernel (1024 threads per scene) through a work list; everything else is clustered right here.
-    const bool defer = run_db && a.defer_list != nullptr && B > kDeferPoints;
-    bool deferred_late = false;
-    if (defer) {
-        if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
-        sc.dbscan_n = B;
-    } else if (run_db) {
-        NbScreened nb = load_fused_ring(a, s, fcnt, fphys, reinterpret_cast<float*>(smem + L.dbf), 3 * ncap);
-        PHASE_MARK(11);
-        // Grid screen first (dbscan.cuh): the residue of a steady scene cannot hold a core point and is all noise.
-        // Whatever the screen lets through is most likely a cluster forming and goes straight to dbscan_big_kernel.
-        const bool screen = a.defer_list != nullptr && 3 * ncap >= kGridCells;
-        if (screen && !dbscan_grid_may_have_core(c, nb.Xf, nb.Yf, B, c.db_min_samples, cl, misc + kScan)) {
-            // (the histogram aliased cl; the screen ends with a barrier, and cl[b] is read back by its writer only)
-            for (int b = tid; b < B; b += kStepThreads) cl[b] = -1;
-            ncl = 0;
-        } else if (screen) {
-            ncl = -1;
-        } else {
-            ncl = dbscan_block(nb, B, c.db_min_samples, par, cl, misc + kScan, a.phase_cycles, a.defer_list != nullptr);
-        }
-        PHASE_MARK(12);
-        if (ncl < 0) {
-            // A cluster forms in this scene (a couple of scenes per frame): components, border labels and the spawn
-            // happen in dbscan_big_kernel.  Finishing them here from the bit rows of the core points was measured:
-            // correct, but those CTAs (4 warps sharing an SM with 6 other CTAs) then end 35 us after all others and
-            // the step kernel goes from 72 to 107 us -- the separate 512-thread kernel costs 29 us.
-            if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
-            ncl = 0;
-            deferred_late = true;
-        }
-        sc.dbscan_n = B;
-        if (a.labels_out != nullptr && !deferred_late)
-            for (int b = tid; b < B; b += kStepThreads) a.labels_out[(size_t)s * 3 * ncap + b] = cl[b];
-    }
-
-    PHASE_MARK(8);
-    // ---- 9. spawn one track per cluster, in label order (Tracking.py:576-589, 210-230; Q7, Q20) ------
-    int T2 = T1;
-    if (ncl > 0) {
-        if (T1 + ncl > tcap) { ncl = tcap - T1; sc.flags |= MMW_SCENE_TRACK_OVERFLOW; }
-        // smem record indices not used by survivors, physical slots not in use (all threads compute the same)
-        unsigned used = 0;
-        for (int k = 0; k < T1; ++k) used |= 1u << misc[kOrder + k];
-        int newidx[kMaxTcap], newslot[kMaxTcap];
-        {
-            const unsigned capmask = tcap >= 32 ? 0xffffffffu : ((1u << tcap) - 1u);
-            unsigned fr = ~used & capmask, fs = ~sc.slot_mask & capmask;
-            for (int q = 0; q < ncl; ++q) {
-                newidx[q] = __ffs(fr) - 1; fr &= fr - 1;
-                newslot[q] = __ffs(fs) - 1; fs &= fs - 1;
-                sc.slot_mask |= 1u << newslot[q];
+    const bool run_db = Bf > 0 && T1 < c.tr_max_tracks;
+    if (run_db) {
+        // The residue of a steady scene cannot hold a core point and is all noise (dbscan.cuh): 99.9 % of the
+        // scene-frames.  Whatever the screen lets through is most likely a cluster forming -- a couple of scenes per
+        // frame -- and goes to dbscan_big_kernel (512 threads per scene) through the work list.
+        bool maybe = Bf >= c.db_min_samples;
+        if (maybe) {
+            float* Xf = reinterpret_cast<float*>(smem + L.A);
+            float* Yf = Xf + 3 * ncap;
+            int b0 = 0;
+            for (int f = 0; f < kRing; ++f) {
+                const float* src = uring_frame(a, s, fphys[f]);
+                for (int i = tid; i < fcnt[f]; i += kStepThreads) {
+                    double yw, zw;
+                    world_yz(c, (double)src[i * kRawCols + 1], (double)src[i * kRawCols + 2], yw, zw);
+                    Xf[b0 + i] = src[i * kRawCols + 0];
+                    Yf[b0 + i] = (float)yw;
+                }
+                b0 += fcnt[f];
             }
+            __syncthreads();
+            maybe = dbscan_grid_may_have_core(c, Xf, Yf, Bf, c.db_min_samples, reinterpret_cast<int*>(Yf + 3 * ncap),
+                                              misc + kScan);
         }
-        for (int q = warp; q < ncl; q += kStepWarps) {
-            spawn_track(a, s, tr[newidx[q]], q, newslot[q], sc.next_id + q, cl, fcnt, fphys, lane);
-            if (lane == 0) misc[kOrder + T1 + q] = newidx[q];
+        if (maybe) {
+            if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
+        } else if (a.labels_out != nullptr) {
+            for (int b = tid; b < Bf; b += kStepThreads) a.labels_out[(size_t)s * 3 * ncap + b] = -1;
         }
-        sc.next_id += ncl;
-        T2 = T1 + ncl;
-        sc.ring_n = 0;                   // batch.clear() (Tracking.py:699-700, Q8)
-        sc.ring_head = 0;
-        sc.ring_cnt[0] = sc.ring_cnt[1] = sc.ring_cnt[2] = 0;
+        sc.dbscan_n = Bf;
     }
-    __syncthreads();
+    PHASE_MARK(11);
 
-    PHASE_MARK(9);
     pdl_launch_dependents();             // late on purpose: dbscan_big's CTAs would otherwise sit on 16 SMs for the whole step
-    // ---- 10. write back: track records in list order, scene record, counters ---------------------------
+    // ---- 7. write back: track records in list order, scene record, per-scene counters --------------------------
     {
         double* dstbase = reinterpret_cast<double*>(a.tracks + (size_t)s * tcap);
-        for (int i = tid; i < T2 * kTrackWords; i += kStepThreads) {
-            const int k = i / kTrackWords, wd = i % kTrackWords;
+        for (int i = tid; i < T1 * kTrackWords; i += kStepThreads) {
+            const int k = i / kTrackWords, wd = i - k * kTrackWords;
             dstbase[i] = reinterpret_cast<const double*>(tr + misc[kOrder + k])[wd];
         }
     }
-    // ring rows written by all warps of this CTA
-    if (lane == 0 && ring_rows) atomicAdd(&a.counters[6], (unsigned long long)ring_rows);
     if (tid == 0) {
-        sc.n_tracks = T2;
+        sc.n_tracks = T1;
         a.scenes[s] = sc;
-        a.pose_cnt[s] = T2;
-        atomicAdd(&a.counters[0], 1ull);
-        atomicAdd(&a.counters[1], (unsigned long long)N);
-        atomicAdd(&a.counters[2], (unsigned long long)M);
-        atomicAdd(&a.counters[3], (unsigned long long)U);
-        if (run_db) atomicAdd(&a.counters[4], (unsigned long long)B);
-        atomicAdd(&a.counters[5], (unsigned long long)T2);
+        a.pose_cnt[s] = T1;
+        int4* st4 = reinterpret_cast<int4*>(a.scene_stats + (size_t)s * 8);
+        st4[0] = make_int4(N, M, U, run_db ? Bf : 0);
+        st4[1] = make_int4(T1, ring_rows, 1, 0);
     }
-    PHASE_MARK(10);
-    if (a.phase_cycles != nullptr && threadIdx.x == 0)
-        a.phase_cycles[16 + blockIdx.x] = (unsigned long long)(clock64() - kernel_t0);   // last frame's cycles of this scene
+    PHASE_MARK(12);
     if (a.phase_cycles != nullptr && threadIdx.x == 0) {
+        a.phase_cycles[16 + blockIdx.x] = (unsigned long long)(clock64() - kernel_t0);   // last frame's cycles of this scene
         unsigned long long ns;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
         a.phase_cycles[16 + 2 * gridDim.x + blockIdx.x] = ns;
     }
 }
 
-// DBSCAN + spawn for the scenes the step kernel deferred (fused cloud > kDeferPoints): same device functions, one
-// CTA of 1024 threads per scene, new tracks written straight to the scene's list in global memory.
+// DBSCAN + spawn for the scenes whose fused cloud passed the step kernel's grid screen (a cluster is forming: a
+// couple of scenes per frame): one CTA of 512 threads per scene, new tracks written straight to the scene's list in
+// global memory.  The last CTA also folds the step's per-scene counters into the context's totals.
 constexpr int kBigThreads = 512;
 constexpr int kBitsMaxB = 768;        // adjacency bit matrix of up to 768 x 768 (72 KB of shared memory)
 __host__ __device__ inline int big_bits_cap(int ncap) { return 3 * ncap < kBitsMaxB ? 3 * ncap : kBitsMaxB; }
@@ -842,6 +881,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
             sc.ring_n = 0;               // batch.clear() (Tracking.py:699-700, Q8)
             sc.ring_head = 0;
             sc.ring_cnt[0] = sc.ring_cnt[1] = sc.ring_cnt[2] = 0;
+            sc.ring_ph_gone = 1;
             if (tid == 0) atomicAdd(&a.counters[5], (unsigned long long)ncl);
         }
         __syncthreads();
@@ -849,6 +889,23 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
         __syncthreads();
         stamp(1);
         if (dbg != nullptr && tid == 0) { atomicAdd(&dbg[2], 1ull); atomicAdd(&dbg[7], (unsigned long long)B); }
+    }
+    // this step's counters: every scene left eight ints; the grid's last CTA (idle unless 16 clusters form at once)
+    // sums them -- one reduction and seven atomics per step instead of seven atomics per scene
+    if (blockIdx.x == gridDim.x - 1 && a.scene_stats != nullptr) {
+        unsigned long long acc[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int sidx = tid; sidx < a.n_scenes; sidx += kBigThreads) {
+            const int4 s0 = reinterpret_cast<const int4*>(a.scene_stats)[2 * sidx];
+            const int4 s1 = reinterpret_cast<const int4*>(a.scene_stats)[2 * sidx + 1];
+            acc[0] += (unsigned)s1.z; acc[1] += (unsigned)s0.x; acc[2] += (unsigned)s0.y; acc[3] += (unsigned)s0.z;
+            acc[4] += (unsigned)s0.w; acc[5] += (unsigned)s1.x; acc[6] += (unsigned)s1.y;
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            unsigned v = (unsigned)acc[k];                   // < 2^32 per thread: at most S / 512 scenes of < 2^16 each
+            v = __reduce_add_sync(kFullMask, v);
+            if (lane == 0 && v) atomicAdd(&a.counters[k], (unsigned long long)v);
+        }
     }
     // every CTA read the work-list length when it started; the last one to finish empties the list for the next step
     // (no memset node between the steps)
@@ -862,34 +919,23 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
     }
 }
 
+int dbscan_big_smem_bytes(int ncap) { return big_w6_offset(ncap) + big_bits_cap(ncap) * 6 * 8; }
+
 cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
     const int smem = step_smem_bytes(a.cfg.ncap, a.cfg.tcap);
-    static int configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static int configured[kMaxDevices] = {0};
+    cudaError_t e = ensure_smem_attr(reinterpret_cast<const void*>(step_kernel), configured, smem);
+    if (e != cudaSuccess) return e;
     step_kernel<<<a.n_scenes, kStepThreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_dbscan_big(const StepArgs& a, cudaStream_t stream) {
     if (a.defer_count == nullptr) return cudaSuccess;
-    cudaError_t e;
-    const int big_smem = big_w6_offset(a.cfg.ncap) + big_bits_cap(a.cfg.ncap) * 6 * 8;
-    static int big_configured = 0;
-    if (big_smem > big_configured) {
-        e = cudaFuncSetAttribute(dbscan_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(dbscan_big_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        big_configured = big_smem;
-    }
+    const int big_smem = dbscan_big_smem_bytes(a.cfg.ncap);
+    static int configured[kMaxDevices] = {0};
+    cudaError_t e = ensure_smem_attr(reinterpret_cast<const void*>(dbscan_big_kernel), configured, big_smem);
+    if (e != cudaSuccess) return e;
     return launch_pdl(dbscan_big_kernel, dim3(16), dim3(kBigThreads), big_smem, stream, dim3(1, 1, 1), a);
 }
 

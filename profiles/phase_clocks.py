@@ -10,8 +10,8 @@ from mmwave_msc_b200.batched import BatchedTracker
 
 S, F = 1024, 40
 b = synth.gen_batch(range(S), F)
-names = ["load+filter", "load tracks", "predict+gatemat", "gate", "assoc stats", "maintain", "update", "dbscan",
-         "spawn", "writeback"]
+names = ["load (bulk copies)", "predict", "gate matrices", "transform+filter", "gate+counts", "lists+pushes",
+         "statistics", "assoc results", "maintain", "update", "screen", "writeback"]
 for pose in (False, True):
     bt = BatchedTracker(S)
     if pose:
@@ -22,13 +22,11 @@ for pose in (False, True):
     for f in range(20, 40):
         bt.step(b[f].points, b[f].offsets, b[f].dt, pose=pose)
     pc = bt.phase_clocks(False).astype(float)
-    tot = pc[1:11].sum() + pc[11] + pc[12]
+    tot = pc[1:13].sum()
     print("== pose between steps: %s" % pose)
     for i, n in enumerate(names):
-        print("%-16s %8.0f cyc/scene-frame %5.1f%%" % (n, pc[i + 1] / (S * 20), 100 * pc[i + 1] / tot))
+        print("%-20s %8.0f cyc/scene-frame %5.1f%%" % (n, pc[i + 1] / (S * 20), 100 * pc[i + 1] / tot))
     print("total cycles per scene-frame %.0f" % (tot / (S * 20)))
-    print("  inside dbscan: ring load %.0f, dbscan_block %.0f, tail %.0f  (cyc/scene-frame; tail = pc[8])" % (
-        pc[11] / (S * 20), pc[12] / (S * 20), pc[8] / (S * 20)))
 
 # distribution of per-scene cycles in one frame (the kernel ends when the slowest scene does)
 import ctypes
@@ -68,5 +66,4 @@ pc = bt1.phase_clocks(False).astype(float)
 lab, nf = bt1.labels()
 print("slowest scene %d: fused points %d, clusters %d" % (w, nf[0], lab[0, :max(nf[0], 0)].max() + 1 if nf[0] > 0 else 0))
 for i, nme in enumerate(names):
-    print("   %-16s %8.0f" % (nme, pc[i + 1]))
-print("   ring load %.0f dbscan_block %.0f  [count %.0f | union %.0f | find+rank+relabel %.0f | border = rest]" % (pc[11], pc[12], pc[13], pc[14], pc[15]))
+    print("   %-20s %8.0f" % (nme, pc[i + 1]))
