@@ -115,50 +115,56 @@ struct NbScreened {
     __device__ __forceinline__ Hot hot() const { return Hot{Xf, Yf, Zf, lo, hi, rw, zw, this}; }
 };
 
-// Conservative screen "can any point of this cloud be a core point?" on a 16 x 16 grid over the world (x, y') plane.
-// Two points within eps of each other satisfy dx^2 + dy^2 <= eps / w with w = 1 - range_weight (y1 + y2)/2 >=
-// 1 - range_weight * max y' (Utils.py:242-247; the z term only adds), so with cells at least that wide every
-// neighbour of a point lies in the 3 x 3 block of cells around it: if no block holds min_samples points, no point
-// has min_samples neighbours and DBSCAN labels everything noise -- which is what the steady-state residue of ~70
-// clutter points does in > 99.9 % of the scene-frames (measured with the oracle).  Cells outside the
-// grid are folded onto its border (counts can only grow).  Block-cooperative; hist: kGridCells ints of shared
-// memory, s_red: one int.  Returns the same value in every thread; false means "certainly no core point".
+// Conservative screen "can any point of the fused ring be a core point?" on a fixed 16 x 16 grid over the world
+// (x, y') plane.  Two points within eps of each other satisfy dx^2 + dy^2 <= eps / w with
+// w = 1 - range_weight (y1 + y2)/2 >= 1 - range_weight * ybound for y' <= ybound (Utils.py:242-247; the z term only
+// adds), so with cells at least sqrt(eps / w_min) wide every neighbour of a point lies in the 3 x 3 block of cells
+// around it: if no block around an occupied cell holds min_samples points, no point has min_samples neighbours and
+// DBSCAN labels everything noise -- which is what the steady-state residue of ~70 clutter points does in > 99.9 %
+// of the scene-frames (tests/test_grid_screen_cpu.py).  Cells outside the grid are folded onto its border (counts
+// can only grow).  Because the cells do not depend on the cloud, every ring frame is binned ONCE, when it is pushed
+// (the points are in registers then), and kept as 256 saturating byte counts + a flag byte per frame next to the
+// ring (StepArgs::ring_hist); the screen itself is a sum of three small histograms and 256 box sums -- no point is
+// touched again.  The flag marks a frame with a point beyond ybound (or not finite): then the screen passes.
 constexpr int kGridDim = 16, kGridCells = kGridDim * kGridDim;
-__device__ inline bool dbscan_grid_may_have_core(const DevConfig& c, const float* Xf, const float* Yf, int B,
-                                                 int min_samples, int* hist, int* s_red) {
-    if (B < min_samples) return false;                               // a point has at most B neighbours, itself included
-    if (!(c.db_range_weight >= 0.0) || !(c.db_z_weight >= 0.0) || !(c.db_eps > 0.0)) return true;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int e = tid; e < kGridCells; e += nt) hist[e] = 0;
-    if (tid == 0) *s_red = 0;
-    __syncthreads();
-    float ym = 0.f;
-    for (int b = tid; b < B; b += nt) ym = fmaxf(ym, Yf[b]);
-    ym = fmaxf(ym, 0.f);                                             // y' > 0 after the scene filter: ordered like its bits
-    const int ymw = __reduce_max_sync(0xffffffffu, __float_as_int(ym));
-    if ((tid & 31) == 0) atomicMax(s_red, ymw);
-    __syncthreads();
-    const float wmin = 1.f - (float)c.db_range_weight * (__int_as_float(*s_red) * 1.0001f);
-    if (!(wmin > 0.05f)) return true;                                // the bound degenerates: take the exact path
-    const float h = 1.01f * sqrtf((float)c.db_eps / wmin);           // 1 % wider than the largest xy reach
-    const float inv_h = 1.f / h;
-    auto cell = [&](float v, float origin) {
-        const int k = (int)floorf(v * inv_h + origin);
-        return k < 0 ? 0 : (k >= kGridDim ? kGridDim - 1 : k);
-    };
-    for (int b = tid; b < B; b += nt)
-        atomicAdd(&hist[cell(Yf[b], 0.f) * kGridDim + cell(Xf[b], 0.5f * kGridDim)], 1);
-    __syncthreads();
+
+// Host side: cell size and validity for a configuration (mmw_create).  ybound: 12 m covers every radar profile of
+// the reference (config_cases/*.cfg: <= 8.5 m) and keeps w_min at 0.64 for the default range weight.
+inline void grid_screen_config(double eps, double range_weight, double z_weight, int min_samples, float* inv_h,
+                               float* ybound, int* ok) {
+    *ok = 0; *inv_h = 0.f; *ybound = 0.f;
+    if (!(range_weight >= 0.0) || !(z_weight >= 0.0) || !(eps > 0.0) || min_samples > 255) return;
+    double yb = 12.0;
+    if (range_weight * yb > 0.5) yb = 0.5 / range_weight;              // keep w_min >= 0.5
+    const float wmin = 1.f - (float)range_weight * ((float)yb * 1.0001f);
+    if (!(wmin > 0.05f)) return;
+    const float h = 1.01f * sqrtf((float)eps / wmin);                  // 1 % wider than the largest xy reach
+    *inv_h = 1.f / h;
+    *ybound = (float)yb;
+    *ok = 1;
+}
+
+__device__ __forceinline__ int grid_cell(const DevConfig& c, float x, float yw) {
+    const int kx = (int)floorf(x * c.grid_inv_h + 0.5f * kGridDim), ky = (int)floorf(yw * c.grid_inv_h);
+    const int cx = kx < 0 ? 0 : (kx >= kGridDim ? kGridDim - 1 : kx);
+    const int cy = ky < 0 ? 0 : (ky >= kGridDim ? kGridDim - 1 : ky);
+    return cy * kGridDim + cx;
+}
+
+// sum[cell]: points of the fused ring per cell (shared memory).  Returns the same value in every thread of the
+// block; false means "certainly no core point".  Ends with a block barrier.
+__device__ __forceinline__ bool grid_screen_may_have_core(const uint16_t* sum, int min_samples) {
     int cand = 0;
-    for (int b = tid; b < B; b += nt) {
-        const int cx = cell(Xf[b], 0.5f * kGridDim), cy = cell(Yf[b], 0.f);
+    for (int cell = threadIdx.x; cell < kGridCells; cell += blockDim.x) {
+        if (sum[cell] == 0) continue;
+        const int cx = cell % kGridDim, cy = cell / kGridDim;
         int n = 0;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
                 const int x = cx + dx, y = cy + dy;
-                if (x >= 0 && x < kGridDim && y >= 0 && y < kGridDim) n += hist[y * kGridDim + x];
+                if (x >= 0 && x < kGridDim && y >= 0 && y < kGridDim) n += sum[y * kGridDim + x];
             }
         cand |= n >= min_samples ? 1 : 0;
     }

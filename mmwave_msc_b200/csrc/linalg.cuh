@@ -21,49 +21,48 @@ struct Elem {
 };
 
 // ---- Kalman predict (filterpy KalmanFilter.predict with F = KF_F(dt), Q = KF_Q_DISCR(dt); constants.py:195-215,
-// Tracking.py:372-385):  x = F x;  P = (F P) F' + Q.  State order [p(3) v(3) a(3)]: F couples i with i+3 (dt) and
-// i+6 (dt^2/2), so both products are three-term sums.
-//   pass 1: A = F P          (thread e < 81)
-//   pass 2: P = A F' + Q     (thread e < 81), x = F x (thread e < 9; kf_predict_x evaluated before anything is written)
-__device__ __forceinline__ void kf_predict_pass1(const double* P, double* A, double dt, const Elem& t) {
-    if (t.e < 81) {
-        const double h = 0.5 * (dt * dt);
-        double v = P[t.e];
-        if (t.i9 < 6) v += dt * P[t.e + 27];
-        if (t.i9 < 3) v += h * P[t.e + 54];
-        A[t.e] = v;
-    }
-}
+// Tracking.py:372-385):  x = F x;  P = F P F' + Q.  State order [p(3) v(3) a(3)]: F couples i with i+3 (dt) and
+// i+6 (dt^2/2), so element (i, j) of F P F' is a 3 x 3-term sum over P[i + 3a][j + 3b].  Thread e < 81 computes
+// its element into a register from the OLD P (kf_predict_elem); after a block barrier the values are stored
+// (the caller batches several tracks between the two barriers).
 __device__ __forceinline__ double kf_predict_x(const double* x, double dt, int e) {
     double xn = x[e];
     if (e < 6) xn += dt * x[e + 3];
     if (e < 3) xn += (0.5 * (dt * dt)) * x[e + 6];
     return xn;
 }
-
 // Q = block_diag(Qw, Qw, Qw) * q_var with Qw = [[dt^4/4, dt^3/2, dt^2/2], [dt^3/2, dt^2, dt], [dt^2/2, dt, 1]] on
 // state indices (0-2), (3-5), (6-8): the block order does not match the state order (Q10) -- reproduced.
-__device__ __forceinline__ void kf_predict_pass2(double* x, double xn, const double* A, double* P, double dt,
-                                                 double q_var, const Elem& t) {
-    if (t.e < 9) x[t.e] = xn;
-    if (t.e < 81) {
-        const double h = 0.5 * (dt * dt);
-        double v = A[t.e];
-        if (t.j9 < 6) v += dt * A[t.e + 3];
-        if (t.j9 < 3) v += h * A[t.e + 6];
-        if (t.i9 / 3 == t.j9 / 3) {
-            const int a = t.i9 % 3, b = t.j9 % 3, s = a + b;   // Qw[a][b] depends on a + b except the middle entry
-            const double dt2 = dt * dt;
-            double qv;
-            if (s == 0) qv = 0.25 * (dt2 * dt2);
-            else if (s == 1) qv = 0.5 * (dt2 * dt);
-            else if (s == 2) qv = (a == 1) ? dt2 : 0.5 * dt2;
-            else if (s == 3) qv = dt;
-            else qv = 1.0;
-            v += qv * q_var;
-        }
-        P[t.e] = v;
+__device__ __forceinline__ double kf_predict_elem(const double* P, double dt, double q_var, const Elem& t) {
+    const double h = 0.5 * (dt * dt);
+    const double* p = P + t.e;
+    // rows i, i+3, i+6 of P F'
+    double v0 = p[0], v1 = 0.0, v2 = 0.0;
+    if (t.j9 < 6) v0 += dt * p[3];
+    if (t.j9 < 3) v0 += h * p[6];
+    if (t.i9 < 6) {
+        v1 = p[27];
+        if (t.j9 < 6) v1 += dt * p[30];
+        if (t.j9 < 3) v1 += h * p[33];
     }
+    if (t.i9 < 3) {
+        v2 = p[54];
+        if (t.j9 < 6) v2 += dt * p[57];
+        if (t.j9 < 3) v2 += h * p[60];
+    }
+    double v = v0 + dt * v1 + h * v2;
+    if (t.i9 / 3 == t.j9 / 3) {
+        const int a = t.i9 % 3, b = t.j9 % 3, s = a + b;   // Qw[a][b] depends on a + b except the middle entry
+        const double dt2 = dt * dt;
+        double qv;
+        if (s == 0) qv = 0.25 * (dt2 * dt2);
+        else if (s == 1) qv = 0.5 * (dt2 * dt);
+        else if (s == 2) qv = (a == 1) ? dt2 : 0.5 * dt2;
+        else if (s == 3) qv = dt;
+        else qv = 1.0;
+        v += qv * q_var;
+    }
+    return v;
 }
 
 // ---- 6x6 inverse + determinant, two matrices per warp -------------------------------------------------------
@@ -135,35 +134,28 @@ __device__ __forceinline__ double gate_score(const double* gp, const double (&w)
 // ---- Kalman update (filterpy KalmanFilter.update, Joseph form, H = [I6 0]; Tracking.py:387-398) --------------
 //   y = z - x[:6];  S = P[:6,:6] + R;  K = P[:, :6] S^-1;  x += K y;
 //   P = (I - K H) P (I - K H)' + (K R) K'
-// as element-parallel steps over a track's scratch:  Sm 36 | R 36  and  M1 81 | K 54 | KR 54.
-// step 1 (e < 36): S = P[:6,:6] + R
-__device__ __forceinline__ void kf_update_S(const double* P, const double* R, double* S, const Elem& t) {
-    if (t.e < 36) S[t.e] = P[t.i6 * 9 + t.a6] + R[t.e];
-}
+// as element-parallel steps over a track's scratch:  S 36 | R 36  and  M1 81 | K 54 | KR 54.  The functions return
+// the thread's element; the caller stores it (and batches several tracks per step so that their loads overlap).
 // step 3 (e < 54): K = P[:, :6] S^-1
-__device__ __forceinline__ void kf_update_K(const double* P, const double* Sinv, double* K, const Elem& t) {
-    if (t.e < 54) {
-        double acc = 0.0;
+__device__ __forceinline__ double kf_update_K_elem(const double* P, const double* Sinv, const Elem& t) {
+    double acc = 0.0;
 #pragma unroll
-        for (int b = 0; b < 6; ++b) acc += P[t.i6 * 9 + b] * Sinv[b * 6 + t.a6];
-        K[t.e] = acc;
-    }
+    for (int b = 0; b < 6; ++b) acc += P[t.i6 * 9 + b] * Sinv[b * 6 + t.a6];
+    return acc;
 }
-// step 4 (e < 81): M1 = (I - K H) P = P - K P[:6, :]   and (e < 54)  KR = K R
-__device__ __forceinline__ void kf_update_M1_KR(const double* P, const double* K, const double* R, double* M1,
-                                                double* KR, const Elem& t) {
-    if (t.e < 81) {
-        double acc = P[t.e];
+// step 4 (e < 81): M1 = (I - K H) P = P - K P[:6, :]
+__device__ __forceinline__ double kf_update_M1_elem(const double* P, const double* K, const Elem& t) {
+    double acc = P[t.e];
 #pragma unroll
-        for (int a = 0; a < 6; ++a) acc -= K[t.i9 * 6 + a] * P[a * 9 + t.j9];
-        M1[t.e] = acc;
-    }
-    if (t.e < 54) {
-        double acc = 0.0;
+    for (int a = 0; a < 6; ++a) acc -= K[t.i9 * 6 + a] * P[a * 9 + t.j9];
+    return acc;
+}
+// step 4 (e < 54): KR = K R
+__device__ __forceinline__ double kf_update_KR_elem(const double* K, const double* R, const Elem& t) {
+    double acc = 0.0;
 #pragma unroll
-        for (int b = 0; b < 6; ++b) acc += K[t.i6 * 6 + b] * R[b * 6 + t.a6];
-        KR[t.e] = acc;
-    }
+    for (int b = 0; b < 6; ++b) acc += K[t.i6 * 6 + b] * R[b * 6 + t.a6];
+    return acc;
 }
 // x += K (z - x[:6]), row i < 9: returns the new x[i] (the caller writes it after every lane has read the old x).
 __device__ __forceinline__ double kf_update_x(const double* x, const double* z, const double* K, int i) {
@@ -173,17 +165,14 @@ __device__ __forceinline__ double kf_update_x(const double* x, const double* z, 
     return acc + x[i];
 }
 // step 5 (e < 81): P = M1 (I - K H)' + KR K' = M1 - M1[:, :6] K' + KR K'
-__device__ __forceinline__ void kf_update_P(const double* M1, const double* K, const double* KR, double* P,
-                                            const Elem& t) {
-    if (t.e < 81) {
-        double acc = M1[t.e];
+__device__ __forceinline__ double kf_update_P_elem(const double* M1, const double* K, const double* KR, const Elem& t) {
+    double acc = M1[t.e];
 #pragma unroll
-        for (int a = 0; a < 6; ++a) acc -= M1[t.i9 * 9 + a] * K[t.j9 * 6 + a];
-        double acc2 = 0.0;
+    for (int a = 0; a < 6; ++a) acc -= M1[t.i9 * 9 + a] * K[t.j9 * 6 + a];
+    double acc2 = 0.0;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) acc2 += KR[t.i9 * 6 + a] * K[t.j9 * 6 + a];
-        P[t.e] = acc + acc2;
-    }
+    for (int a = 0; a < 6; ++a) acc2 += KR[t.i9 * 6 + a] * K[t.j9 * 6 + a];
+    return acc + acc2;
 }
 // The x[0] nudge of Tracking.py:396-398: `abs(variance.any()) > 0.6` is abs(bool) > 0.6, i.e. true iff
 // z[0] != x[0] (Q12); applied when the track got points this frame.

@@ -49,6 +49,7 @@ struct mmw_ctx {
     unsigned long long* d_counters = nullptr;
     unsigned long long* d_phase = nullptr;
     bool phase_clocks = false;
+    uint8_t* d_ring_hist = nullptr;   // [S][kRing][kHistBytes] cell histograms of the global ring's frames (grid screen)
     int32_t* d_scene_stats = nullptr; // [S][8] per-scene counters of the last step (summed on the device)
     int32_t* d_defer = nullptr;      // [2 + S + S]: counter, the work list of dbscan_big_kernel, pose rows per scene, finished-CTA ticket
     bool fold_pose_index = true;     // pose-row scan inside pose_feature_kernel (S <= 4096) instead of pose_index_kernel
@@ -127,6 +128,8 @@ static void fill_devconfig(const mmw_config& c, int ncap, int tcap, DevConfig* d
     d->est_pointnum = c.kf_est_pointnum;
     d->ncap = ncap;
     d->tcap = tcap;
+    grid_screen_config(c.db_eps, c.db_range_weight, c.db_z_weight, c.db_min_samples, &d->grid_inv_h, &d->grid_ybound,
+                       &d->grid_ok);
 }
 
 static const float kDefaultPosture[57] = {
@@ -167,7 +170,7 @@ int mmw_destroy(mmw_ctx* x) {
     cudaSetDevice(x->device);
     if (x->stream) cudaStreamSynchronize(x->stream);
     void* ptrs[] = {x->d_export, x->d_export_valid, x->d_tracks, x->d_scenes, x->d_track_ring, x->d_uring, x->d_keypoints, x->d_default_posture,
-                    x->d_assoc, x->d_labels, x->d_counters, x->d_phase, x->d_defer, x->d_scene_stats, x->d_pts2[0], x->d_pts2[1], x->d_offsets2[0],
+                    x->d_assoc, x->d_labels, x->d_counters, x->d_phase, x->d_defer, x->d_scene_stats, x->d_ring_hist, x->d_pts2[0], x->d_pts2[1], x->d_offsets2[0],
                     x->d_offsets2[1], x->d_dt2[0], x->d_dt2[1], x->d_results[0], x->d_results[1], x->d_blob, x->d_bn1s,
                     x->d_bn1t, x->d_bn2s, x->d_bn2t, x->d_feats, x->d_row_scene, x->d_row_track, x->d_row_slot,
                     x->d_pose_total, x->d_act2, x->d_act3, x->d_pose_out};
@@ -194,6 +197,7 @@ int mmw_reset(mmw_ctx* x) {
     CK(cudaMemsetAsync(x->d_pose_total, 0, sizeof(int), x->stream));
     CK(cudaMemsetAsync(x->d_defer, 0, sizeof(int32_t) * (2 + 2 * (size_t)x->S), x->stream));
     CK(cudaMemsetAsync(x->d_scene_stats, 0, sizeof(int32_t) * 8 * (size_t)x->S, x->stream));
+    CK(cudaMemsetAsync(x->d_ring_hist, 0, (size_t)kRing * kHistBytes * x->S, x->stream));
     return MMW_OK;
 }
 
@@ -212,6 +216,7 @@ std::vector<StatePart> state_parts(mmw_ctx* x) {
             {x->d_tracks, sizeof(TrackRec) * S * x->tcap},
             {x->d_track_ring, sizeof(float) * S * x->tcap * kRing * kFeatPts * kRawCols},
             {x->d_uring, sizeof(float) * S * kRing * x->ncap * kRawCols},
+            {x->d_ring_hist, (size_t)kRing * kHistBytes * S},
             {x->d_keypoints, sizeof(float) * S * x->tcap * kKp},
             {x->d_defer + 1 + S, sizeof(int32_t) * S}};                 // pose rows per scene of the last frame
 }
@@ -309,6 +314,7 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     ALLOC(x->d_phase, sizeof(unsigned long long) * (16 + 3 * S + 16));
     ALLOC(x->d_defer, sizeof(int32_t) * (2 + 2 * S));
     ALLOC(x->d_scene_stats, sizeof(int32_t) * 8 * S);
+    ALLOC(x->d_ring_hist, (size_t)kRing * kHistBytes * S);
     {
         const char* env = getenv("MMW_POSE_INDEX_FOLD");
         x->fold_pose_index = S <= 4096 && !(env && env[0] == '0');
@@ -508,6 +514,7 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     a.defer_list = x->d_defer + 1;
     a.pose_cnt = x->d_defer + 1 + x->S;
     a.scene_stats = x->d_scene_stats;
+    a.ring_hist = x->d_ring_hist;
     prof_mark(x, MMW_K_STEP);
     CK(launch_step(a, x->stream));
     prof_mark(x, MMW_K_DBSCAN_BIG);
@@ -760,20 +767,16 @@ __global__ void __launch_bounds__(kStepThreads) dbscan_stage_kernel(DevConfig c,
 
 // One CTA of 128 threads per track: the element-parallel steps of linalg.cuh, as the fused step kernel runs them.
 __global__ void __launch_bounds__(128) kalman_predict_kernel(double* x, double* P, const double* dt, int n, double q_var) {
-    __shared__ double sx[9], sP[81], sA[81];
+    __shared__ double sx[9], sP[81];
     const int i = blockIdx.x, tid = threadIdx.x;
     const Elem el(tid);
     if (tid < 81) sP[tid] = P[(size_t)i * 81 + tid];
     if (tid < 9) sx[tid] = x[(size_t)i * 9 + tid];
     __syncthreads();
-    kf_predict_pass1(sP, sA, dt[i], el);
-    __syncthreads();
+    const double pv = tid < 81 ? kf_predict_elem(sP, dt[i], q_var, el) : 0.0;
     const double xn = tid < 9 ? kf_predict_x(sx, dt[i], tid) : 0.0;
-    __syncwarp();
-    kf_predict_pass2(sx, xn, sA, sP, dt[i], q_var, el);
-    __syncthreads();
-    if (tid < 81) P[(size_t)i * 81 + tid] = sP[tid];
-    if (tid < 9) x[(size_t)i * 9 + tid] = sx[tid];
+    if (tid < 81) P[(size_t)i * 81 + tid] = pv;
+    if (tid < 9) x[(size_t)i * 9 + tid] = xn;
 }
 
 __global__ void __launch_bounds__(128) kalman_update_kernel(double* x, double* P, const double* z, const double* R,
@@ -786,7 +789,7 @@ __global__ void __launch_bounds__(128) kalman_update_kernel(double* x, double* P
     if (tid < 9) sx[tid] = x[(size_t)i * 9 + tid];
     if (tid < 6) sz[tid] = z[(size_t)i * 6 + tid];
     __syncthreads();
-    kf_update_S(sP, sR, sS, el);
+    if (tid < 36) sS[tid] = sP[el.i6 * 9 + el.a6] + sR[tid];          // S = P[:6,:6] + R
     __syncthreads();
     if (warp == 0) {
         double r[6];
@@ -798,16 +801,17 @@ __global__ void __launch_bounds__(128) kalman_update_kernel(double* x, double* P
         }
     }
     __syncthreads();
-    kf_update_K(sP, sS, sK, el);
+    if (tid < 54) sK[tid] = kf_update_K_elem(sP, sS, el);
     __syncthreads();
-    kf_update_M1_KR(sP, sK, sR, sM1, sKR, el);
+    if (tid < 81) sM1[tid] = kf_update_M1_elem(sP, sK, el);
+    if (tid < 54) sKR[tid] = kf_update_KR_elem(sK, sR, el);
     if (warp == 3) {
         const double xv = lane < 9 ? kf_update_x(sx, sz, sK, lane) : 0.0;
         __syncwarp();
         if (lane < 9) sx[lane] = xv;
     }
     __syncthreads();
-    kf_update_P(sM1, sK, sKR, sP, el);
+    if (tid < 81) sP[tid] = kf_update_P_elem(sM1, sK, sKR, el);
     if (tid == 96) kf_update_nudge(sx, sz, life0[i] != 0, thres, gain);
     __syncthreads();
     if (tid < 81) P[(size_t)i * 81 + tid] = sP[tid];

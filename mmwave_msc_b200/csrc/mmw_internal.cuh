@@ -12,6 +12,7 @@ constexpr int kRing = 3;          // max frames in a ring: FB_FRAMES_BATCH + 1 <
 constexpr int kFeatPts = 64;      // points kept per track ring frame (format_single_frame, Utils.py:505-510)
 constexpr int kRawCols = 5;       // x, y, z, doppler, peakVal (sensor frame, fp32)
 constexpr int kKp = 57;           // 19 joints x 3
+constexpr int kHistBytes = 272;   // per ring frame: 256 cell counts of the grid screen (uint8, saturating) + flag + pad
 #ifndef MMW_STEP_THREADS
 #define MMW_STEP_THREADS 128     // threads per scene CTA of the tracker step (profiling builds override it)
 #endif
@@ -29,6 +30,10 @@ struct DevConfig {
     double int_mu, int_std, nudge_thres, nudge_gain;
     int db_min_samples, ring_size, tr_max_tracks, enable_est, est_pointnum;
     int ncap, tcap;
+    // grid screen in front of DBSCAN (dbscan.cuh): fixed 16 x 16 cells over world (x, y'), at least one eps reach wide
+    // for every pair of points with y' <= grid_ybound; grid_ok = 0: degenerate configuration, the screen always passes
+    float grid_inv_h, grid_ybound;
+    int grid_ok;
 };
 
 // One element of a scene's effective_tracks list (ClusterTrack + KalmanState + PointCluster).
@@ -92,6 +97,7 @@ struct StepArgs {
     int32_t* defer_count;      // device counter of defer_list; dbscan_big_kernel's last CTA zeroes it for the next step
     int32_t* defer_done;       // CTAs of dbscan_big_kernel that have finished (ticket for that reset)
     int32_t* pose_cnt;         // [S] tracks of the scene if the frame ran track(), else 0: the pose-row scan reads this
+    uint8_t* ring_hist;        // [S][kRing][kHistBytes] cell histograms of the global ring's frames, by physical slot
     int32_t* scene_stats;      // [S][8] this frame's N, M, U, Bf (if DBSCAN ran), tracks, ring rows written, ran, 0:
                                //   summed into `counters` by dbscan_big_kernel (one reduction instead of 7 atomics per scene)
     int n_scenes;

@@ -4,50 +4,60 @@
 // cluster statistics and ring push, track maintenance, Kalman update, push of the unassigned points into the scene's
 // global ring and the grid screen that decides whether DBSCAN has anything to find -- with every intermediate in
 // shared memory / registers.  HBM traffic per scene-frame is the raw points in, the track records in and out, the
-// ring rows written and the fused ring read by the screen.
+// ring rows written and three 272-byte cell histograms for the screen.
 //
 // How the work is laid out (round 2; profiles/r02_*.md):
-//   * inputs arrive by two bulk copies (cp.async.bulk, 1-D TMA) behind one mbarrier: the scene's contiguous block of
-//     raw points (as the 16-byte aligned window around it) and its track records;
-//   * point phases are thread-per-point, two points per thread per tile of 256 -- transform, filter, gate, list
-//     positions, ring pushes all work from registers; only the world 6-vectors of associated points go to shared
-//     memory, in list order, for the statistics;
+//   * inputs arrive by three bulk copies (cp.async.bulk, 1-D TMA) behind one mbarrier: the scene's contiguous block
+//     of raw points (as the 16-byte aligned window around it), its track records and the ring's cell histograms;
+//   * point phases are thread-per-point, two points per thread per tile of 256, both in flight at once (straight-
+//     line code, two independent float64 chains) -- transform, filter, gate, list positions, ring pushes all work
+//     from registers;
 //   * track phases are ELEMENT-parallel (linalg.cuh): thread e owns element e of the 9x9 / 9x6 / 6x6 matrices and
 //     the CTA walks the tracks, so all four warps work whatever the number of tracks; the two 6x6 inverses per
 //     track run two tracks per warp (one half warp each);
-//   * per-track statistics: 39 values (6 sums, 21 products, 6 minima, 6 maxima) x 3 slices of the track's list = 117
-//     threads, each a short FMA chain straight from shared memory, combined in a fixed order (deterministic);
-//   * clusters that form are left to dbscan_big_kernel through a work list; this kernel only runs the grid screen.
+//   * per-track statistics are a Gram matrix: each associated point leaves the row (d0..d5, x) with d = w - H x in
+//     shared memory, in list order, and one warp per track accumulates [1 d x]' [1 d x] over four points per
+//     DMMA.8x8x4 (float64 tensor-core MMA; fixed summation order, deterministic) -- sums, second moments and the
+//     exact sum of the x lattice values in 1/4 instruction per point; minima / maxima by a second warp;
+//   * the grid screen works on per-frame cell histograms that were filled when the frames were pushed; clusters
+//     that form are left to dbscan_big_kernel through a work list.
 #include "dbscan.cuh"
 #include "linalg.cuh"
 #include "mmw_internal.cuh"
 
 namespace mmw {
 
+#ifndef MMW_KTB
+#define MMW_KTB 1
+#endif
 constexpr int kTile = 2 * kStepThreads;          // points per tile: two per thread
 constexpr int kChunks = kTile / 32;              // warp chunks of 32 consecutive points in a tile
+constexpr int kTB = MMW_KTB;                           // tracks per batch of the element-parallel track phases
+constexpr int kLw = 7;                           // doubles per list row: d0..d5 (w - H x of the point's track), x
 constexpr int kBw = 72;                          // doubles of per-track scratch B
-constexpr int kGinv = 40, kHx = kGinv + 21, kNest = 68;   // inside B from the gate matrices to the statistics (below)
-constexpr int kNStat = 39;                       // 6 sums + 21 products + 6 minima + 6 maxima, at B[0..38]
+// inside B from the gate matrices to the association results: gate form (kGateWords = 28) | new N_est | minima of
+// d (6) | maxima of d (6) | sum d (6), sum x, products d_r d_c (21)
+constexpr int kGp = 0, kHx = kGp + 21, kNest = 28, kMin = 29, kMax = 35, kSum = 41, kSumX = 47, kProd = 48;
+static_assert(kProd + 21 <= kBw, "B holds the statistics totals next to the gate form");
 static_assert(kStepThreads == 128, "the element-parallel track phases are written for 128 threads per scene");
 
 // Dynamic shared memory of step_kernel.
 //   tracks  TrackRec [tcap]
-//   B       double [tcap][72]   gate:   C (0..35) -> statistics totals (0..38) | packed C^-1 (40..60) | H x (61..66)
-//                                       | log|det C| (67)
-//                               update: S -> S^-1 (0..35) | Rc (36..71)
-//   A       double [tcap][81]   F P (predict), (I - K H) P (update)
+//   B       double [tcap][72]   gate..association: see above;  update: S -> S^-1 (0..35) | Rc (36..71)
+//   A       double [tcap][81]   F P (predict), C (gate matrix, first 36), (I - K H) P (update)
 //   KK      double [tcap][108]  K (0..53) | K Rc (54..107)
-//   aliases: the list of world 6-vectors of a tile's associated points (kTile x 6 doubles) lies over A|KK between the
-//   gate matrices and the update; the staged raw points lie over KK when a frame is a single tile, in their own
-//   space otherwise (they must survive the tile loop); the DBSCAN screen's scratch lies over A|KK at the end.
+//   hist    ring frames' cell histograms (3 x 272 bytes), this frame's counts (256 x uint16)
+//   aliases: the list rows of a tile's associated points (kTile x 7 doubles) lie over A|KK between the gate matrices
+//   and the update; the staged raw points lie over KK when a frame is a single tile, in their own space otherwise
+//   (they must survive the tile loop).
 struct SmemLayout {
-    int tracks, B, A, KK, stage, misc, total;
+    int tracks, B, A, KK, stage, hist, hnew, misc, total;
 };
-constexpr int kMiscInts = 384;
+constexpr int kMiscInts = 192;
 // misc int slots (slot 0-1: the mbarrier)
-enum { kT1 = 2, kFreed = 3, kScan = 4 /* 2 ints: dbscan_grid_may_have_core */, kCntK = 8 /* 8 */, kCntU = 16 /* 8 */,
-       kBaseG = 24 /* 2 x 32 */, kBaseU = 88 /* 2 */, kOrder = 96 /* 32 */, kCntG = 128 /* 8 x 32 */ };
+enum { kT1 = 2, kFreed = 3, kFlag = 4, kCntK = 8 /* 8 */, kCntU = 16 /* 8 */, kBaseG = 24 /* 2 x 32 */,
+       kBaseU = 88 /* 2 */, kOrder = 92 /* 32 */, kCntG = 124 /* 8 x 32 bytes = 64 ints */ };
+static_assert(kCntG + 64 <= kMiscInts, "misc layout");
 
 __host__ __device__ inline SmemLayout make_layout(int ncap, int tcap) {
     SmemLayout L;
@@ -61,15 +71,15 @@ __host__ __device__ inline SmemLayout make_layout(int ncap, int tcap) {
     const bool single = ncap <= kTile;
     if (single && kk_bytes < stage_bytes) kk_bytes = stage_bytes;
     int akk = a_bytes + kk_bytes;
-    const int list_bytes = kTile * 6 * 8;
-    const int screen_bytes = 2 * 3 * ncap * 4 + kGridCells * 4;   // fp32 world x, y' of the fused ring + histogram
+    const int list_bytes = kTile * kLw * 8;
     if (akk < list_bytes) akk = list_bytes;
-    if (akk < screen_bytes) akk = screen_bytes;
     akk = (akk + 15) & ~15;
     L.KK = L.A + a_bytes;
     o += akk;
     L.stage = single ? L.KK : o;
     if (!single) o += stage_bytes;
+    L.hist = o;    o += kRing * kHistBytes;
+    L.hnew = o;    o += kGridCells * 2;
     L.misc = o;    o += kMiscInts * 4;
     L.total = o;
     return L;
@@ -118,6 +128,12 @@ __device__ __forceinline__ void sk_bulk_g2s(void* dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                      "r"(sk_smem(dst)), "l"(src), "r"(bytes), "r"(sk_smem(bar))
                  : "memory");
+}
+// D (8x8, float64) += A (8x4) B (4x8): lane L supplies A[L/4][L%4] and B[L%4][L/4], holds D[L/4][2 (L%4) + {0, 1}]
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
 }
 
 __device__ __forceinline__ const float* uring_frame(const StepArgs& a, int s, int phys) {
@@ -250,7 +266,7 @@ __device__ __forceinline__ NbScreened load_fused_ring(const StepArgs& a, int s, 
 // Optional per-phase cycle accounting (thread 0 of every CTA, accumulated with one atomic per phase).
 #define PHASE_MARK(idx)                                                                  \
     do {                                                                                 \
-        if (a.phase_cycles != nullptr && threadIdx.x == 0) {                             \
+        if (dbg_clocks && threadIdx.x == 0) {                                            \
             const long long now__ = clock64();                                           \
             atomicAdd(&a.phase_cycles[idx], (unsigned long long)(now__ - phase_t0));     \
             phase_t0 = now__;                                                            \
@@ -261,9 +277,10 @@ __device__ __forceinline__ NbScreened load_fused_ring(const StepArgs& a, int s, 
 #define MMW_STEP_MINBLOCKS 7
 #endif
 __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(const __grid_constant__ StepArgs a) {
-    long long phase_t0 = clock64();
+    const bool dbg_clocks = a.phase_cycles != nullptr;
+    long long phase_t0 = dbg_clocks ? clock64() : 0;
     const long long kernel_t0 = phase_t0;
-    if (a.phase_cycles != nullptr && threadIdx.x == 0) {
+    if (dbg_clocks && threadIdx.x == 0) {
         unsigned long long ns;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
         a.phase_cycles[16 + gridDim.x + blockIdx.x] = ns;
@@ -276,8 +293,11 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     double* Bm = reinterpret_cast<double*>(smem + L.B);
     double* Am = reinterpret_cast<double*>(smem + L.A);
     double* KKm = reinterpret_cast<double*>(smem + L.KK);
-    double* wl = Am;                                            // list of world 6-vectors (aliases A | KK)
+    double* wl = Am;                                            // list rows (alias A | KK)
+    uint8_t* hist = smem + L.hist;                              // [kRing][kHistBytes] by physical ring slot
+    uint16_t* hnew = reinterpret_cast<uint16_t*>(smem + L.hnew);   // this frame's cell counts, later the fused sums
     int* misc = reinterpret_cast<int*>(smem + L.misc);
+    uint8_t* cntG = reinterpret_cast<uint8_t*>(misc + kCntG);   // [kChunks][32] points per chunk and track
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + L.misc);
 
     const int s = blockIdx.x;
@@ -303,66 +323,74 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     const float* stagef = reinterpret_cast<const float*>(smem + L.stage + (byte0 - win0));
     if (tid == 0) {
         const uint32_t tr_bytes = (uint32_t)T0 * (uint32_t)sizeof(TrackRec);
-        sk_mbar_expect_tx(mbar, tr_bytes + (bulk_pts ? win_bytes : 0u));
+        sk_mbar_expect_tx(mbar, tr_bytes + (bulk_pts ? win_bytes : 0u) + (uint32_t)(kRing * kHistBytes));
         if (tr_bytes) sk_bulk_g2s(tr, a.tracks + (size_t)s * tcap, tr_bytes, mbar);
         if (bulk_pts && win_bytes)
             sk_bulk_g2s(smem + L.stage, reinterpret_cast<const unsigned char*>(a.pts) + win0, win_bytes, mbar);
+        sk_bulk_g2s(hist, a.ring_hist + (size_t)s * (kRing * kHistBytes), kRing * kHistBytes, mbar);
     }
     if (!bulk_pts) {
         float* st = const_cast<float*>(stagef);
         for (int i = tid; i < N * kRawCols; i += kStepThreads) st[i] = a.pts[(size_t)off * kRawCols + i];
     }
-    // the ring frames the screen will read: L2 prefetch, their DRAM latency overlaps everything below
-    for (int f = 0; f < sc.ring_n; ++f) {
-        const int phys = ring_wrap(sc.ring_head + f, c.ring_size);
-        const char* fr = reinterpret_cast<const char*>(uring_frame(a, s, phys));
-        const int lines = (sc.ring_cnt[phys] * kRawCols * 4 + 127) / 128;
-        for (int i = tid; i < lines; i += kStepThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(fr + i * 128));
-    }
-    if (tid < 2 * 32 + 2) misc[kBaseG + tid < kBaseG + 64 ? kBaseG + tid : kBaseU + (tid - 64)] = 0;
+    reinterpret_cast<uint32_t*>(hnew)[tid] = 0u;                 // 256 uint16 counts = 128 words
+    if (tid < 32) misc[kBaseG + tid] = 0;
+    if (tid == 32) { misc[kBaseU] = 0; misc[kFlag] = 0; }
     sk_mbar_wait(mbar, 0);
     if (!bulk_pts) __syncthreads();
     PHASE_MARK(1);
 
     // ---- 1. predict (Tracking.py:591-596, Q9) and gate matrices (Tracking.py:545-551) -----------------------
-    // pass 1: A = F P
-    for (int j = 0; j < T0; ++j) kf_predict_pass1(tr[j].P, Am + j * 81, tr[j].lifetime + dt, el);
-    __syncthreads();
-    // pass 2: P = A F' + Q; x = F x; H x for the gate
-    for (int j = 0; j < T0; ++j) {
-        TrackRec& t = tr[j];
-        const double dte = t.lifetime + dt;
-        const double x_new = tid < 9 ? kf_predict_x(t.x, dte, tid) : 0.0;
-        __syncwarp();                    // warp 0: every lane has read the old x
-        kf_predict_pass2(t.x, x_new, Am + j * 81, t.P, dte, c.q_var, el);
-        if (tid < 6) Bm[j * kBw + kHx + tid] = x_new;
-    }
-    __syncthreads();
-    PHASE_MARK(2);
-    // gate matrix C = P[:6,:6] + Rm + G (get_Rm 361-370)
-    for (int j = 0; j < T0; ++j) {
-        if (tid < 36) {
-            const TrackRec& t = tr[j];
-            double v = t.P[el.i6 * 9 + el.a6];
-            if (el.i6 == el.a6) { const double h = t.spread[el.i6] / 2; v += h * h; }
-            Bm[j * kBw + tid] = v + t.G[tid];
+    // Element-parallel, kTB tracks per batch: every thread computes its element of F P F' + Q for all tracks of
+    // the batch from the old P (independent chains, their loads overlap), one barrier, then the stores: P, x = F x,
+    // H x, and the gate matrix C = P[:6,:6] + Rm + G (get_Rm 361-370) into the track's B block.
+    for (int j0 = 0; j0 < T0; j0 += kTB) {
+        double pv[kTB], xv[kTB];
+#pragma unroll
+        for (int u = 0; u < kTB; ++u) {
+            const int j = j0 + u;
+            pv[u] = 0.0; xv[u] = 0.0;
+            if (j < T0) {
+                const TrackRec& t = tr[j];
+                const double dte = t.lifetime + dt;
+                if (tid < 81) pv[u] = kf_predict_elem(t.P, dte, c.q_var, el);
+                if (tid < 9) xv[u] = kf_predict_x(t.x, dte, tid);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kTB; ++u) {
+            const int j = j0 + u;
+            if (j < T0) {
+                TrackRec& t = tr[j];
+                if (tid < 81) {
+                    t.P[tid] = pv[u];
+                    if (el.i9 < 6 && el.j9 < 6) {
+                        double v = pv[u];
+                        if (el.i9 == el.j9) { const double h = t.spread[el.i9] / 2; v += h * h; }
+                        Bm[j * kBw + kMin + el.i9 * 6 + el.j9] = v + t.G[el.i9 * 6 + el.j9];
+                    }
+                }
+                if (tid < 9) t.x[tid] = xv[u];
+                if (tid < 6) Bm[j * kBw + kHx + tid] = xv[u];
+            }
         }
     }
     __syncthreads();
-    // inverse + log|det| of the gate matrices, two tracks per warp; C^-1 is stored as its upper triangle with the
-    // off-diagonal entries doubled (the quadratic form needs 21 products instead of 36).  The half warp then resets
-    // the track's statistics totals, which take the place of C.
+    PHASE_MARK(2);
+    // inverse + log|det| of the gate matrices, two tracks per warp, kept in the packed gate form (linalg.cuh).  The
+    // half warp then resets the track's statistics totals, which take the place of C.
     for (int j0 = 0; j0 < T0; j0 += 2 * kStepWarps) {
         const int j = j0 + 2 * warp + (lane >> 4);
         const bool live = j < T0;
         if (__ballot_sync(kFull, live) == 0u) continue;
         double r[6];
-        const double det = inv6_spd_half(live ? Bm + j * kBw : nullptr, lane, r);
+        const double det = inv6_spd_half(live ? Bm + j * kBw + kMin : nullptr, lane, r);
         __syncwarp();
         if (live) {
             double* bj = Bm + j * kBw;
-            gate_pack_half(bj + kGinv, r, det, lane);
-            for (int v = lane & 15; v < kNStat; v += 16) bj[v] = v < 27 ? 0.0 : (v < 33 ? INFINITY : -INFINITY);
+            gate_pack_half(bj + kGp, r, det, lane);
+            for (int v = lane & 15; v < 40; v += 16) bj[kMin + v] = v < 6 ? INFINITY : (v < 12 ? -INFINITY : 0.0);
         }
     }
     __syncthreads();
@@ -372,39 +400,26 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     //         (Tracking.py:553-572, Q14), list positions, ring pushes (Tracking.py:691, 338), statistics ------------
     const int uphys = sc.ring_n >= c.ring_size ? sc.ring_head : ring_wrap(sc.ring_head + sc.ring_n, c.ring_size);
     float* udst = const_cast<float*>(uring_frame(a, s, uphys));
-    // role of this thread in the statistics: value v (0..5 sums of w -- the x column is a sum of lattice values and
-    // therefore exact in any order, which keeps centroid[0] bit-identical to numpy's mean: the pose features sort
-    // on x - centroid[0] against zero pads (Utils.py:505-514) --, 6..26 products d_r d_c (r <= c) of d = w - H x,
-    // 27..32 minima of w, 33..38 maxima of w), slice q of the list
-    const int sv = warp * 10 + lane / 3, sq = lane % 3;
-    const bool s_active = lane < 30 && sv < kNStat;
-    int s_ra = 0, s_rb = 6;
-    if (sv < 6) {
-        s_ra = sv;
-    } else if (sv < 27) {
-        int rem = sv - 6, r = 0;
-        while (rem >= 6 - r) { rem -= 6 - r; ++r; }
-        s_ra = r; s_rb = r + rem;
-    } else {
-        s_ra = (sv - 27) % 6;
-    }
     int M = 0;
     const int ntiles = (N + kTile - 1) / kTile;
     for (int tile = 0; tile < ntiles; ++tile) {
+        // both points of the thread in straight-line code: two independent float64 chains in flight
         float raw[2][kRawCols];
         double w[2][6];
+        bool keep[2];
         unsigned km[2];
 #pragma unroll
         for (int r2 = 0; r2 < 2; ++r2) {
             const int i = tile * kTile + r2 * kStepThreads + tid;
-            bool keep = false;
-            if (i < N) {
+            const int ic = i < N ? i : N - 1;                    // lanes past the end redo the last point (discarded)
 #pragma unroll
-                for (int k = 0; k < kRawCols; ++k) raw[r2][k] = stagef[i * kRawCols + k];
-                world_from_raw(c, raw[r2][0], raw[r2][1], raw[r2][2], raw[r2][3], w[r2]);
-                keep = (w[r2][2] <= c.z_max) && (w[r2][2] > 0.0) && (w[r2][1] > 0.0);      // Utils.py:423-427
-            }
-            km[r2] = __ballot_sync(kFull, keep);
+            for (int k = 0; k < kRawCols; ++k) raw[r2][k] = stagef[ic * kRawCols + k];
+            world_from_raw(c, raw[r2][0], raw[r2][1], raw[r2][2], raw[r2][3], w[r2]);
+            keep[r2] = i < N && (w[r2][2] <= c.z_max) && (w[r2][2] > 0.0) && (w[r2][1] > 0.0);   // Utils.py:423-427
+        }
+#pragma unroll
+        for (int r2 = 0; r2 < 2; ++r2) {
+            km[r2] = __ballot_sync(kFull, keep[r2]);
             if (lane == 0) misc[kCntK + r2 * kStepWarps + warp] = __popc(km[r2]);
         }
         __syncthreads();
@@ -424,19 +439,32 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         }
         // gate: d2 = log|det C| + y' C^-1 y < gate, arg-min over the gated tracks, ties -> lower index
         int grp[2];
-#pragma unroll
-        for (int r2 = 0; r2 < 2; ++r2) {
-            grp[r2] = 255;
-            if ((km[r2] >> lane) & 1u) {
-                double best = INFINITY;
-                int bj = -1;
-                for (int j = 0; j < T0; ++j) {
-                    const double d2 = gate_score(Bm + j * kBw + kGinv, w[r2]);
-                    if (d2 < c.gate && d2 < best) { best = d2; bj = j; }
-                }
-                grp[r2] = bj < 0 ? T0 : bj;
-                a.assoc_out[off + pos[r2]] = bj;
+        {
+            double best0 = INFINITY, best1 = INFINITY;
+            int bj0 = -1, bj1 = -1;
+#ifndef MMW_GATE_SEQ
+            for (int j = 0; j < T0; ++j) {
+                const double* gp = Bm + j * kBw + kGp;
+                const double d0 = gate_score(gp, w[0]), d1 = gate_score(gp, w[1]);
+                if (d0 < c.gate && d0 < best0) { best0 = d0; bj0 = j; }
+                if (d1 < c.gate && d1 < best1) { best1 = d1; bj1 = j; }
             }
+#else
+            if (keep[0])
+                for (int j = 0; j < T0; ++j) {
+                    const double d0 = gate_score(Bm + j * kBw + kGp, w[0]);
+                    if (d0 < c.gate && d0 < best0) { best0 = d0; bj0 = j; }
+                }
+            if (keep[1])
+                for (int j = 0; j < T0; ++j) {
+                    const double d1 = gate_score(Bm + j * kBw + kGp, w[1]);
+                    if (d1 < c.gate && d1 < best1) { best1 = d1; bj1 = j; }
+                }
+#endif
+            grp[0] = keep[0] ? (bj0 < 0 ? T0 : bj0) : 255;
+            grp[1] = keep[1] ? (bj1 < 0 ? T0 : bj1) : 255;
+            if (keep[0]) a.assoc_out[off + pos[0]] = bj0;
+            if (keep[1]) a.assoc_out[off + pos[1]] = bj1;
         }
         // per chunk and group: count (lane j keeps track j's) and this point's rank inside its group
         int rk[2] = {0, 0};
@@ -451,7 +479,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
                 }
                 const unsigned bu = __ballot_sync(kFull, grp[r2] == T0);
                 if (grp[r2] == T0) rk[r2] = __popc(bu & ltmask);
-                if (lane < T0) misc[kCntG + (r2 * kStepWarps + warp) * 32 + lane] = cj[r2];
+                if (lane < T0) cntG[(r2 * kStepWarps + warp) * 32 + lane] = (uint8_t)cj[r2];
                 if (lane == 0) misc[kCntU + r2 * kStepWarps + warp] = __popc(bu);
             }
         }
@@ -464,7 +492,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
             if (lane < T0) {
 #pragma unroll
                 for (int c2 = 0; c2 < kChunks; ++c2) {
-                    const int v = misc[kCntG + c2 * 32 + lane];
+                    const int v = cntG[c2 * 32 + lane];
                     tot += v;
                     if (c2 < warp) preg[0] += v;
                     if (c2 < kStepWarps + warp) preg[1] += v;
@@ -499,9 +527,11 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
                       gst = __shfl_sync(kFull, start, gs);
             if (g < T0) {
                 const int lp = gb + gp0 + rk[r2];                // position in the track's cloud of this frame
-                const int tl = gst + gp0 + rk[r2];               // position in the tile's list
+                double* row = wl + (gst + gp0 + rk[r2]) * kLw;   // position in the tile's list
+                const double* hx = Bm + g * kBw + kHx;
 #pragma unroll
-                for (int k = 0; k < 6; ++k) wl[tl * 6 + k] = w[r2][k];
+                for (int k = 0; k < 6; ++k) row[k] = w[r2][k] - hx[k];
+                row[6] = w[r2][0];
                 if (lp < kFeatPts) {
                     // first 64 associated rows in input order are what format_single_frame can see
                     const TrackRec& t = tr[g];
@@ -516,49 +546,72 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
                 float* dst = udst + (size_t)(ubase + preu[r2] + rk[r2]) * kRawCols;
 #pragma unroll
                 for (int k = 0; k < kRawCols; ++k) dst[k] = raw[r2][k];
+                // the frame's cell histogram for the grid screen (dbscan.cuh)
+                const float yw = (float)w[r2][1];
+                if (!(yw <= c.grid_ybound)) misc[kFlag] = 1;
+                const int cell = grid_cell(c, raw[r2][0], yw);
+                atomicAdd(reinterpret_cast<unsigned*>(hnew) + (cell >> 1), (cell & 1) ? 0x10000u : 1u);
             }
         }
         M += tile_kept;
         __syncthreads();
         PHASE_MARK(6);
         // statistics of this tile's lists (PointCluster, Tracking.py:120-136; _get_D 270-290 about H x instead of the
-        // centroid: E[d d'] - m m' with d = w - H x, m = centroid - H x below the gate radius, so nothing cancels)
+        // centroid: E[d d'] - m m' with d = w - H x and m = mean d, below the gate radius, so nothing cancels).
+        // Track j: warp j % 4 accumulates the Gram matrix of the rows [1 d0..d5 x], four points per DMMA, two
+        // accumulator chains; warp (j + 2) % 4 takes the minima / maxima.
         for (int j = 0; j < T0; ++j) {
             const int nj = __shfl_sync(kFull, tot, j), st = __shfl_sync(kFull, start, j);
             if (nj == 0) continue;
-            const double* hxj = Bm + j * kBw + kHx;
-            const bool is_mom = sv < 27, is_max = sv >= 33;
-            double acc = is_mom ? 0.0 : (is_max ? -INFINITY : INFINITY);
-            if (s_active) {
-                if (is_mom) {
-                    const double ha = s_rb < 6 ? hxj[s_ra] : 0.0, hb = s_rb < 6 ? hxj[s_rb] : 0.0;
-                    const int rb = s_rb < 6 ? s_rb : 0;
-                    for (int k = sq; k < nj; k += 3) {
-                        const double* wp = wl + (st + k) * 6;
-                        const double pa = wp[s_ra] - ha;
-                        const double pb = s_rb < 6 ? wp[rb] - hb : 1.0;
-                        acc += pa * pb;
+            const double* rows = wl + st * kLw;
+            double* bj = Bm + j * kBw;
+            if (warp == (j & 3)) {
+                const int pt = lane & 3, comp = lane >> 2;
+                double c0a = 0.0, c1a = 0.0, c0b = 0.0, c1b = 0.0;
+                for (int g0 = 0; g0 < nj; g0 += 8) {
+                    const int k0 = g0 + pt, k1 = g0 + 4 + pt;
+                    double va = 0.0, vb = 0.0;
+                    if (k0 < nj) va = comp ? rows[k0 * kLw + comp - 1] : 1.0;
+                    if (k1 < nj) vb = comp ? rows[k1 * kLw + comp - 1] : 1.0;
+                    dmma_884(c0a, c1a, va, va);
+                    dmma_884(c0b, c1b, vb, vb);
+                }
+                const double cv[2] = {c0a + c0b, c1a + c1b};
+#pragma unroll
+                for (int e2 = 0; e2 < 2; ++e2) {
+                    const int col = 2 * pt + e2;                 // Gram[comp][col]; index 0 = the constant, 7 = x
+                    int idx = -1;
+                    if (comp == 0) { if (col >= 1) idx = kSum + col - 1; }
+                    else if (comp <= 6 && col >= comp && col <= 6) {
+                        const int r = comp - 1, q = col - 1;
+                        idx = kProd + r * 6 - (r * (r - 1)) / 2 + (q - r);
                     }
-                } else {
-                    for (int k = sq; k < nj; k += 3) {
-                        const double x = wl[(st + k) * 6 + s_ra];
-                        acc = is_max ? (x > acc ? x : acc) : (x < acc ? x : acc);
-                    }
+                    if (idx >= 0) bj[idx] += cv[e2];
                 }
             }
-            // the three slices of a value sit in adjacent lanes; fixed order of combination
-            const double a1 = __shfl_down_sync(kFull, acc, 1), a2 = __shfl_down_sync(kFull, acc, 2);
-            if (is_mom) {
-                acc = (acc + a1) + a2;
-            } else if (is_max) {
-                acc = a1 > acc ? a1 : acc; acc = a2 > acc ? a2 : acc;
-            } else {
-                acc = a1 < acc ? a1 : acc; acc = a2 < acc ? a2 : acc;
-            }
-            if (s_active && sq == 0) {
-                double* tv = Bm + j * kBw + sv;
-                const double old = *tv;
-                *tv = sv < 27 ? old + acc : (sv < 33 ? (acc < old ? acc : old) : (acc > old ? acc : old));
+            if (warp == ((j + 2) & 3)) {
+                const int dim = lane >> 2, q = lane & 3;
+                const int col = dim == 0 ? 6 : dim;              // x itself (exact) for dim 0, d_k otherwise
+                double mn = INFINITY, mx = -INFINITY;
+                if (lane < 24) {
+                    for (int k = q; k < nj; k += 4) {
+                        const double v = rows[k * kLw + col];
+                        mn = v < mn ? v : mn;
+                        mx = v > mx ? v : mx;
+                    }
+                }
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const double omn = __shfl_xor_sync(kFull, mn, o), omx = __shfl_xor_sync(kFull, mx, o);
+                    mn = omn < mn ? omn : mn;
+                    mx = omx > mx ? omx : mx;
+                }
+                if (lane < 24 && q == 0) {
+                    const double sh = dim == 0 ? 0.0 : bj[kHx + dim];          // back to world coordinates
+                    mn += sh; mx += sh;
+                    bj[kMin + dim] = mn < bj[kMin + dim] ? mn : bj[kMin + dim];
+                    bj[kMax + dim] = mx > bj[kMax + dim] ? mx : bj[kMax + dim];
+                }
             }
         }
         __syncthreads();
@@ -583,56 +636,84 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     PHASE_MARK(7);
 
     // ---- 3. per-track association results (Tracking.py:648-653, 314-341) ------------------------------------
+    // Roles by thread (the same for every track, kTB tracks per batch: values first, stores after):
+    //   tid < 36      group dispersion entry (_estimate_group_disp_matrix 292-297)
+    //   64 <= tid < 70  centroid, extrema, spread of dimension tid - 64 (_estimate_measurement_spread 246-268)
+    //   tid == 96     ring bookkeeping, lifetime, point count, status, N_est (_estimate_point_num 232-244)
     int ring_rows = 0;
-    for (int j = 0; j < T0; ++j) {
-        TrackRec& t = tr[j];
-        const int n = misc[kBaseG + (ntiles & 1) * 32 + j];
-        ring_rows += n < kFeatPts ? n : kFeatPts;
-        if (n == 0) {
-            if (tid == 0) t.lifetime += dt;                      // update_lifetime(dt) (400-407)
-            if (tid == 96) Bm[j * kBw + kNest] = t.n_est;
-            continue;
+    for (int j0 = 0; j0 < T0; j0 += kTB) {
+        double v0[kTB], v1[kTB], v2[kTB], v3[kTB];
+        int nn[kTB];
+#pragma unroll
+        for (int u = 0; u < kTB; ++u) {
+            const int j = j0 + u;
+            nn[u] = 0; v0[u] = v1[u] = v2[u] = v3[u] = 0.0;
+            if (j >= T0) continue;
+            const TrackRec& t = tr[j];
+            const int n = misc[kBaseG + (ntiles & 1) * 32 + j];
+            nn[u] = n;
+            ring_rows += n < kFeatPts ? n : kFeatPts;
+            if (n == 0) continue;
+            const double* tv = Bm + j * kBw;
+            const double dn = (double)n;
+            if (tid < 36) {
+                double n_est;
+                if (c.enable_est) n_est = dn > t.n_est ? dn : (1 - c.a_n) * t.n_est + c.a_n * dn;
+                else n_est = (double)(n > c.est_pointnum ? n : c.est_pointnum);
+                int r = el.i6, q = el.a6;
+                if (r > q) { const int tmp = r; r = q; q = tmp; }
+                const int p = r * 6 - (r * (r - 1)) / 2 + (q - r);
+                const double rn = 1.0 / dn;
+                const double dv = tv[kProd + p] * rn - (tv[kSum + r] * rn) * (tv[kSum + q] * rn);
+                const double al = dn / n_est;
+                v0[u] = (1 - al) * t.G[tid] + al * dv;
+            } else if (tid >= 64 && tid < 70) {
+                const int m = tid - 64;
+                const double mnv = tv[kMin + m], mxv = tv[kMax + m];
+                // centroid[0]: the x column is a sum of lattice values, exact in any order, so this is numpy's mean to the
+                // bit -- the pose features sort on x - centroid[0] against zero pads (Utils.py:505-514)
+                v0[u] = m == 0 ? tv[kSumX] / dn : tv[kHx + m] + tv[kSum + m] / dn;
+                v1[u] = mnv;
+                v2[u] = mxv;
+                double spread = mxv - mnv;
+                if (n != 1) spread = spread * (double)(n + 1) / (double)(n - 1);
+                spread = fmin(2 * c.spread_lim[m], spread);
+                spread = fmax(c.spread_lim[m], spread);
+                v3[u] = spread > t.spread[m] ? spread : (1.0 - c.a_spr) * t.spread[m] + c.a_spr * spread;
+            } else if (tid == 96) {
+                if (c.enable_est) v0[u] = dn > t.n_est ? dn : (1 - c.a_n) * t.n_est + c.a_n * dn;
+                else v0[u] = (double)(n > c.est_pointnum ? n : c.est_pointnum);
+                const double c3 = tv[kHx + 3] + tv[kSum + 3] / dn, c4 = tv[kHx + 4] + tv[kSum + 4] / dn,
+                             c5 = tv[kHx + 5] + tv[kSum + 5] / dn;
+                v1[u] = sqrt(c3 * c3 + c4 * c4 + c5 * c5) < c.vel_thres ? 1.0 : 0.0;
+            }
         }
-        const double* tv = Bm + j * kBw;
-        const double dn = (double)n;
-        double n_est = t.n_est;
-        if (c.enable_est) {                                      // _estimate_point_num (232-244)
-            if (dn > n_est) n_est = dn;
-            else n_est = (1 - c.a_n) * n_est + c.a_n * dn;
-        } else {
-            n_est = (double)(n > c.est_pointnum ? n : c.est_pointnum);
+#pragma unroll
+        for (int u = 0; u < kTB; ++u) {
+            const int j = j0 + u;
+            if (j >= T0) continue;
+            TrackRec& t = tr[j];
+            const int n = nn[u];
+            if (n == 0) {
+                if (tid == 96) t.lifetime += dt;                 // update_lifetime(dt) (400-407)
+                continue;
+            }
+            if (tid < 36) {
+                t.G[tid] = v0[u];
+            } else if (tid >= 64 && tid < 70) {
+                const int m = tid - 64;
+                t.centroid[m] = v0[u]; t.minv[m] = v1[u]; t.maxv[m] = v2[u]; t.spread[m] = v3[u];
+            } else if (tid == 96) {
+                const int phys = t.ring_n >= c.ring_size ? t.ring_head : ring_wrap(t.ring_head + t.ring_n, c.ring_size);
+                if (t.ring_n >= c.ring_size) t.ring_head = ring_wrap(t.ring_head + 1, c.ring_size);
+                else t.ring_n += 1;
+                t.ring_cnt[phys] = n < kFeatPts ? n : kFeatPts;
+                t.lifetime = 0.0;
+                t.point_num = n;
+                t.is_static = v1[u] != 0.0 ? 1 : 0;
+                t.n_est = v0[u];         // (the dispersion threads computed their own copy from the old value above)
+            }
         }
-        if (tid < 36) {                                          // _estimate_group_disp_matrix (292-297)
-            int r = el.i6, q = el.a6;
-            if (r > q) { const int tmp = r; r = q; q = tmp; }
-            const int p = r * 6 - (r * (r - 1)) / 2 + (q - r);
-            const double mr = tv[r] / dn - tv[kHx + r], mq = tv[q] / dn - tv[kHx + q];
-            const double dv = tv[6 + p] / dn - mr * mq;
-            const double al = dn / n_est;
-            t.G[tid] = (1 - al) * t.G[tid] + al * dv;
-        } else if (tid >= 64 && tid < 70) {                      // centroid, extrema, _estimate_measurement_spread (246-268)
-            const int m = tid - 64;
-            const double mnv = tv[27 + m], mxv = tv[33 + m];
-            t.centroid[m] = tv[m] / dn;
-            t.minv[m] = mnv;
-            t.maxv[m] = mxv;
-            double spread = mxv - mnv;
-            if (n != 1) spread = spread * (double)(n + 1) / (double)(n - 1);
-            spread = fmin(2 * c.spread_lim[m], spread);
-            spread = fmax(c.spread_lim[m], spread);
-            if (spread > t.spread[m]) t.spread[m] = spread;
-            else t.spread[m] = (1.0 - c.a_spr) * t.spread[m] + c.a_spr * spread;
-        } else if (tid == 96) {
-            const int phys = t.ring_n >= c.ring_size ? t.ring_head : ring_wrap(t.ring_head + t.ring_n, c.ring_size);
-            if (t.ring_n >= c.ring_size) t.ring_head = ring_wrap(t.ring_head + 1, c.ring_size);
-            else t.ring_n += 1;
-            t.ring_cnt[phys] = n < kFeatPts ? n : kFeatPts;
-            t.lifetime = 0.0;
-            t.point_num = n;
-            const double c3 = tv[3] / dn, c4 = tv[4] / dn, c5 = tv[5] / dn;
-            t.is_static = sqrt(c3 * c3 + c4 * c4 + c5 * c5) < c.vel_thres ? 1 : 0;
-            Bm[j * kBw + kNest] = n_est;             // written to the record by the maintenance warp: the
-        }                                                        // threads above still read the old value
     }
     {
         if (!sc.ring_ph_gone && sc.ring_n + 1 >= c.ring_size) sc.ring_ph_gone = 1;   // the deque's initial empty frame
@@ -640,22 +721,36 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         else sc.ring_n += 1;
         sc.ring_cnt[uphys] = U;
     }
+    // this frame's cell histogram takes the ring slot of the frame just pushed: saturating bytes, in shared memory
+    // for the screen below and in global memory for the next two frames
+    if (tid <= 64) {
+        unsigned wd;
+        if (tid < 64) {
+            const unsigned lo = reinterpret_cast<const unsigned*>(hnew)[2 * tid], hi = reinterpret_cast<const unsigned*>(hnew)[2 * tid + 1];
+            const unsigned c0 = min(lo & 0xffffu, 255u), c1 = min(lo >> 16, 255u), c2 = min(hi & 0xffffu, 255u),
+                           c3 = min(hi >> 16, 255u);
+            wd = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+        } else {
+            wd = misc[kFlag] ? 1u : 0u;
+        }
+        reinterpret_cast<unsigned*>(hist + uphys * kHistBytes)[tid] = wd;
+        reinterpret_cast<unsigned*>(a.ring_hist + ((size_t)s * kRing + uphys) * kHistBytes)[tid] = wd;
+    }
     __syncthreads();
     PHASE_MARK(8);
 
     // ---- 4. maintenance (Tracking.py:513-528, Q16): drop timed-out tracks, keep list order -------------------
     if (warp == 0) {
-        bool keep = false;
+        bool kp = false;
         unsigned slotbit = 0u;
         if (lane < T0) {
             const double lim = tr[lane].is_static ? c.life_sta : c.life_dyn;
-            keep = !(tr[lane].lifetime > lim);                   // dropped tracks are INACTIVE: off the list
-            tr[lane].n_est = Bm[lane * kBw + kNest];
-            if (!keep) slotbit = 1u << tr[lane].slot;
+            kp = !(tr[lane].lifetime > lim);                     // dropped tracks are INACTIVE: off the list
+            if (!kp) slotbit = 1u << tr[lane].slot;
         }
-        const unsigned kmask = __ballot_sync(kFull, keep);
+        const unsigned kmask = __ballot_sync(kFull, kp);
         const unsigned freed = __reduce_or_sync(kFull, slotbit);
-        if (keep) misc[kOrder + __popc(kmask & ltmask)] = lane;
+        if (kp) misc[kOrder + __popc(kmask & ltmask)] = lane;
         if (lane == 0) { misc[kT1] = __popc(kmask); misc[kFreed] = (int)freed; }
     }
     __syncthreads();
@@ -664,6 +759,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     PHASE_MARK(9);
 
     // ---- 5. update every surviving track (Tracking.py:598-603, 387-398; Q11-Q13) ----------------------------
+    // Element-parallel steps of the Joseph-form update (linalg.cuh), kTB tracks per batch and step.
     // _get_Rc (299-312): Rm/N + ((N_est - N)/((N_est - 1) N)) * group_disp_est;  S = P[:6,:6] + Rc
     for (int k = 0; k < T1; ++k) {
         if (tid < 36) {
@@ -695,39 +791,78 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         }
     }
     __syncthreads();
-    for (int k = 0; k < T1; ++k) {
-        const int j = misc[kOrder + k];
-        kf_update_K(tr[j].P, Bm + j * kBw, KKm + j * 108, el);
+    for (int k0 = 0; k0 < T1; k0 += kTB) {               // K = P[:, :6] S^-1
+        double kv[kTB];
+#pragma unroll
+        for (int u = 0; u < kTB; ++u) {
+            kv[u] = 0.0;
+            if (k0 + u < T1 && tid < 54) {
+                const int j = misc[kOrder + k0 + u];
+                kv[u] = kf_update_K_elem(tr[j].P, Bm + j * kBw, el);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kTB; ++u)
+            if (k0 + u < T1 && tid < 54) KKm[misc[kOrder + k0 + u] * 108 + tid] = kv[u];
     }
     __syncthreads();
-    for (int k = 0; k < T1; ++k) {
-        const int j = misc[kOrder + k];
-        TrackRec& t = tr[j];
-        kf_update_M1_KR(t.P, KKm + j * 108, Bm + j * kBw + 36, Am + j * 81, KKm + j * 108 + 54, el);
-        if (warp == 3) {
-            double xv = 0.0;
-            if (lane < 9) xv = kf_update_x(t.x, t.centroid, KKm + j * 108, lane);
-            __syncwarp();
-            if (lane < 9) t.x[lane] = xv;
+    for (int k0 = 0; k0 < T1; k0 += kTB) {               // M1 = (I - K H) P, K Rc, x += K y
+        double mv[kTB], rv[kTB], xv[kTB];
+#pragma unroll
+        for (int u = 0; u < kTB; ++u) {
+            mv[u] = rv[u] = xv[u] = 0.0;
+            if (k0 + u < T1) {
+                const int j = misc[kOrder + k0 + u];
+                const TrackRec& t = tr[j];
+                const double* K = KKm + j * 108;
+                if (tid < 81) mv[u] = kf_update_M1_elem(t.P, K, el);
+                if (tid < 54) rv[u] = kf_update_KR_elem(K, Bm + j * kBw + 36, el);
+                if (tid >= 96 && tid < 105) xv[u] = kf_update_x(t.x, t.centroid, K, tid - 96);
+            }
+        }
+        __syncwarp();                    // warp 3: every lane has read the old x
+#pragma unroll
+        for (int u = 0; u < kTB; ++u) {
+            if (k0 + u < T1) {
+                const int j = misc[kOrder + k0 + u];
+                if (tid < 81) Am[j * 81 + tid] = mv[u];
+                if (tid < 54) KKm[j * 108 + 54 + tid] = rv[u];
+                if (tid >= 96 && tid < 105) tr[j].x[tid - 96] = xv[u];
+            }
         }
     }
     __syncthreads();
-    for (int k = 0; k < T1; ++k) {
-        const int j = misc[kOrder + k];
-        TrackRec& t = tr[j];
-        kf_update_P(Am + j * 81, KKm + j * 108, KKm + j * 108 + 54, t.P, el);
-        if (tid == 96) kf_update_nudge(t.x, t.centroid, t.lifetime == 0.0, c.nudge_thres, c.nudge_gain);
+    for (int k0 = 0; k0 < T1; k0 += kTB) {               // P = M1 (I - K H)' + (K Rc) K'
+        double pv[kTB];
+#pragma unroll
+        for (int u = 0; u < kTB; ++u) {
+            pv[u] = 0.0;
+            if (k0 + u < T1 && tid < 81) {
+                const int j = misc[kOrder + k0 + u];
+                pv[u] = kf_update_P_elem(Am + j * 81, KKm + j * 108, KKm + j * 108 + 54, el);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kTB; ++u) {
+            if (k0 + u < T1) {
+                TrackRec& t = tr[misc[kOrder + k0 + u]];
+                if (tid < 81) t.P[tid] = pv[u];
+                if (tid == 96) kf_update_nudge(t.x, t.centroid, t.lifetime == 0.0, c.nudge_thres, c.nudge_gain);
+            }
+        }
     }
-    __syncthreads();
     PHASE_MARK(10);
 
     // ---- 6. DBSCAN over the fused global ring (Tracking.py:693-700): the grid screen --------------------------
     int Bf = 0;
-    int fcnt[kRing], fphys[kRing];
+    int fphys[kRing];
+    bool fl = false;
     for (int f = 0; f < kRing; ++f) {
         fphys[f] = ring_wrap(sc.ring_head + f, c.ring_size);
-        fcnt[f] = f < sc.ring_n ? sc.ring_cnt[fphys[f]] : 0;
-        Bf += fcnt[f];
+        if (f < sc.ring_n) {
+            Bf += sc.ring_cnt[fphys[f]];
+            fl = fl || hist[fphys[f] * kHistBytes + kGridCells] != 0;
+        }
     }
     const bool run_db = Bf > 0 && T1 < c.tr_max_tracks;
     if (run_db) {
@@ -735,23 +870,16 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         // scene-frames.  Whatever the screen lets through is most likely a cluster forming -- a couple of scenes per
         // frame -- and goes to dbscan_big_kernel (512 threads per scene) through the work list.
         bool maybe = Bf >= c.db_min_samples;
-        if (maybe) {
-            float* Xf = reinterpret_cast<float*>(smem + L.A);
-            float* Yf = Xf + 3 * ncap;
-            int b0 = 0;
-            for (int f = 0; f < kRing; ++f) {
-                const float* src = uring_frame(a, s, fphys[f]);
-                for (int i = tid; i < fcnt[f]; i += kStepThreads) {
-                    double yw, zw;
-                    world_yz(c, (double)src[i * kRawCols + 1], (double)src[i * kRawCols + 2], yw, zw);
-                    Xf[b0 + i] = src[i * kRawCols + 0];
-                    Yf[b0 + i] = (float)yw;
-                }
-                b0 += fcnt[f];
+        if (maybe && c.grid_ok && !fl) {
+            // (the counts of this frame were packed before the barrier that followed the association results)
+            for (int cell = tid; cell < kGridCells; cell += kStepThreads) {
+                int n = 0;
+                for (int f = 0; f < kRing; ++f)
+                    if (f < sc.ring_n) n += hist[fphys[f] * kHistBytes + cell];
+                hnew[cell] = (uint16_t)n;
             }
             __syncthreads();
-            maybe = dbscan_grid_may_have_core(c, Xf, Yf, Bf, c.db_min_samples, reinterpret_cast<int*>(Yf + 3 * ncap),
-                                              misc + kScan);
+            maybe = grid_screen_may_have_core(hnew, c.db_min_samples);
         }
         if (maybe) {
             if (tid == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = s;
@@ -760,6 +888,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         }
         sc.dbscan_n = Bf;
     }
+    __syncthreads();                     // the update's last step has written P
     PHASE_MARK(11);
 
     pdl_launch_dependents();             // late on purpose: dbscan_big's CTAs would otherwise sit on 16 SMs for the whole step
@@ -780,7 +909,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         st4[1] = make_int4(T1, ring_rows, 1, 0);
     }
     PHASE_MARK(12);
-    if (a.phase_cycles != nullptr && threadIdx.x == 0) {
+    if (dbg_clocks && threadIdx.x == 0) {
         a.phase_cycles[16 + blockIdx.x] = (unsigned long long)(clock64() - kernel_t0);   // last frame's cycles of this scene
         unsigned long long ns;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));

@@ -1,11 +1,12 @@
-"""The grid screen in front of DBSCAN in the tracker step (mmwave_msc_b200/csrc/dbscan.cuh,
-dbscan_grid_may_have_core), restated in numpy with the kernel's fp32 arithmetic and held against the oracle's exact
-eps-neighbourhoods (Utils.py:222-247 through oracle.mmw_oracle.pair_distance_matrix).
+"""The grid screen in front of DBSCAN in the tracker step (mmwave_msc_b200/csrc/dbscan.cuh: grid_screen_config,
+grid_cell, grid_screen_may_have_core; the per-frame histograms are filled in step_kernel.cu when a frame is pushed),
+restated in numpy with the kernel's fp32 arithmetic and held against the oracle's exact eps-neighbourhoods
+(Utils.py:222-247 through oracle.mmw_oracle.pair_distance_matrix).
 
 What must hold for the CUDA path to stay bit-exact: whenever the screen answers "no point can be a core point", no
-point of the cloud has min_samples neighbours -- for clouds inside the grid, outside it, at ranges where the range
-weight widens the reach, and where it turns negative.  What makes it worth having: on the residue clouds of steady
-scenes it answers "no" almost always.  (The device code itself is compared with the oracle in
+point of the cloud has min_samples neighbours -- for clouds inside the grid, outside it, beyond the range bound the
+cells were sized for, and where the range weight turns negative.  What makes it worth having: on the residue clouds of
+steady scenes it answers "no" almost always.  (The device code itself is compared with the oracle in
 test_gpu_parity.py::test_grid_screen_edge_cases and by every sequence test.)"""
 import numpy as np
 
@@ -15,25 +16,39 @@ from oracle import mmw_oracle as mo
 GRID = 16
 
 
+def grid_config(cfg: mo.OracleConfig):
+    """grid_screen_config: (inv_h, ybound, ok) in fp32 like the host code."""
+    f32 = np.float32
+    if not (cfg.db_range_weight >= 0.0) or not (cfg.db_z_weight >= 0.0) or not (cfg.db_eps > 0.0) \
+            or cfg.db_min_samples > 255:
+        return f32(0), f32(0), False
+    yb = 12.0
+    if cfg.db_range_weight * yb > 0.5:
+        yb = 0.5 / cfg.db_range_weight
+    wmin = f32(1) - f32(cfg.db_range_weight) * (f32(yb) * f32(1.0001))
+    if not (wmin > f32(0.05)):
+        return f32(0), f32(0), False
+    h = f32(1.01) * np.sqrt(f32(cfg.db_eps) / wmin, dtype=f32)
+    return f32(1) / h, f32(yb), True
+
+
 def screen_may_have_core(world: np.ndarray, cfg: mo.OracleConfig) -> bool:
-    """dbscan_grid_may_have_core: world = (B, >=2) float64 world-frame points (x, y', ...)."""
+    """The step kernel's screen: world = (B, >=2) float64 world-frame points (x, y', ...) of the fused ring."""
     B = len(world)
     if B < cfg.db_min_samples:
         return False
-    if not (cfg.db_range_weight >= 0.0) or not (cfg.db_z_weight >= 0.0) or not (cfg.db_eps > 0.0):
+    inv_h, ybound, ok = grid_config(cfg)
+    if not ok:
         return True
     f32 = np.float32
-    X, Y = world[:, 0].astype(f32), world[:, 1].astype(f32)          # the kernel keeps the fused ring in fp32
-    ym = max(f32(Y.max()), f32(0))
-    wmin = f32(1) - f32(cfg.db_range_weight) * (ym * f32(1.0001))
-    if not (wmin > f32(0.05)):
+    X, Y = world[:, 0].astype(f32), world[:, 1].astype(f32)          # raw x is fp32; y' is rounded to fp32 for the cell
+    if not np.all(Y <= ybound):                                       # the frame's flag byte: the screen passes
         return True
-    h = f32(1.01) * np.sqrt(f32(cfg.db_eps) / wmin, dtype=f32)
-    inv_h = f32(1) / h
     cx = np.clip(np.floor(X * inv_h + f32(0.5 * GRID)).astype(np.int64), 0, GRID - 1)
-    cy = np.clip(np.floor(Y * inv_h + f32(0)).astype(np.int64), 0, GRID - 1)
+    cy = np.clip(np.floor(Y * inv_h).astype(np.int64), 0, GRID - 1)
     hist = np.zeros((GRID + 2, GRID + 2), np.int64)                   # one ring of empty cells instead of bounds checks
     np.add.at(hist, (cy + 1, cx + 1), 1)
+    hist = np.minimum(hist, 3 * 255)                                  # three frames of saturating byte counts
     block = sum(hist[cy + 1 + dy, cx + 1 + dx] for dy in (-1, 0, 1) for dx in (-1, 0, 1))
     return bool((block >= cfg.db_min_samples).any())
 
@@ -118,7 +133,7 @@ def test_screen_degenerate_configurations_fall_back():
     pts = np.zeros((40, 3)); pts[:, 1] = 1.0
     assert screen_may_have_core(pts, cfg)                             # 40 coincident points
     assert not screen_may_have_core(pts[:cfg.db_min_samples - 1], cfg)
-    far = pts.copy(); far[:, 1] = 34.0                                # 1 - 0.03 * 34 < 0: no bound on the reach
+    far = pts.copy(); far[:, 1] = 34.0                                # beyond the range bound (1 - 0.03 * 34 < 0: no reach bound)
     far[:, 0] = np.linspace(-50, 50, 40)
     assert screen_may_have_core(far, cfg)
     assert has_core_point(far, cfg)                                   # ... and indeed: with a negative weight all are neighbours
