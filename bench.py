@@ -130,35 +130,217 @@ def _cpu_worker(args):
     return cpu_port_run(*args)
 
 
+def reference_run(scene_ids, n_frames):
+    """The reference ITSELF (unmodified Utils.normalize_data / TrackBuffer.track / estimate_posture from
+    oracle/_ref/src -- staged by oracle/make_ref.py -- or /root/reference/src), driven by the loop body of
+    offline_main.py:45-60: sklearn DBSCAN as shipped (BallTree), default argsort.  filterpy is the restatement of
+    oracle/filterpy_shim, the Keras model a torch-CPU fp32 module behind .predict (neither library is installed).
+    Returns scene-frames, seconds."""
+    from mmwave_msc_b200 import pose_weights as pw, synth
+    from oracle import mmw_oracle as mo, ref_harness as rh
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+    const, utils, tracking = rh.load_reference()
+    W = pw.make_pose_weights(pw.VARIANT_3D)
+
+    class Model:
+        def predict(self, x):
+            return mo.pose_forward(W, np.asarray(x, np.float32), np.float32)
+
+    scenes = [synth.gen_scene(s, n_frames) for s in scene_ids]
+    dets = [[rh.detobj_from_raw(fr) for fr in sc.frames] for sc in scenes]
+    model = Model()
+    devnull = open(os.devnull, "w")
+    out, sys.stdout = sys.stdout, devnull          # the reference prints on malformed points (Utils.py:398)
+    try:
+        t0 = time.perf_counter()
+        n = 0
+        for sc, dd in zip(scenes, dets):
+            tb, batch = tracking.TrackBuffer(), tracking.BatchedData()
+            for det, dt in zip(dd, sc.dts()):
+                tb.dt = float(dt)
+                eff = utils.normalize_data(det)
+                if eff.shape[0] != 0:
+                    tb.track(eff, batch)
+                    tb.estimate_posture(model)
+                n += 1
+        sec = time.perf_counter() - t0
+    finally:
+        sys.stdout = out
+    return n, sec
+
+
+def _ref_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    return reference_run(*args)
+
+
 def reference_arm(args, rank, world):
-    """--impl reference: the CPU implementation of the path (oracle port; the reference itself is pure Python
-    that cannot travel to this box) on all host cores, independent scenes per process."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, independent scenes per
+    process (the reference is single-threaded).  Uses the staged unmodified reference (kind "reference"); without it
+    the oracle port (kind "port", ~10x faster than the real thing)."""
     if rank != 0:
         return
     import multiprocessing as mp
+    from oracle import make_ref
+    real = bool(make_ref.staged_dir())
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     frames = 30
-    per_proc = 2
+    per_proc = 1 if real else 2
     vals = []
     for step in range(args.warmup + args.steps):
-        jobs = [([10_000 + step * 1000 + p * per_proc + i for i in range(per_proc)], frames, True) for p in range(procs)]
-        t0 = time.perf_counter()
+        jobs = [([10_000 + step * 1000 + p * per_proc + i for i in range(per_proc)], frames) for p in range(procs)]
         with mp.get_context("fork").Pool(procs) as pool:
-            res = pool.map(_cpu_worker, jobs)
+            res = pool.map(_ref_worker if real else _cpu_worker_pose, jobs)
         wall = max(r[1] for r in res)
         if step >= args.warmup:
             vals.append(sum(r[0] for r in res) / wall)
     v = float(np.mean(vals)) if vals else 0.0
-    sample = "%d processes x %d scenes x %d frames per step (C2-shaped scenes, pose CNN in torch-CPU fp32)" % (
-        procs, per_proc, frames)
+    impl = ("the unmodified reference (Utils.normalize_data, TrackBuffer.track, estimate_posture; offline_main.py "
+            "loop body) with the filterpy restatement and a torch-CPU fp32 pose net behind .predict"
+            if real else "oracle port (numpy float64 + torch-CPU fp32 pose net)")
+    sample = "%d processes x %d scene(s) x %d frames per step (C2-shaped scenes), %s" % (procs, per_proc, frames, impl)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * procs * per_proc * frames / v if v else None,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "reference" if real else "port",
+                         "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def _cpu_worker_pose(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    return cpu_port_run(args[0], args[1], True)
+
+
+# --------------------------------------------------------------------------------------------------
+def _tile_batches(batches, reps):
+    """The same scenes `reps` times side by side (scene s + k * S is scene s again): a throughput workload of
+    reps * S scenes from S generated ones."""
+    out = []
+    for b in batches:
+        n = b.points.shape[0]
+        pts = np.tile(b.points, (reps, 1))
+        off = np.concatenate([b.offsets[:-1] + k * n for k in range(reps)] + [np.array([reps * n], np.int32)])
+        out.append((pts, off.astype(np.int32), np.tile(b.dt, reps)))
+    return out
+
+
+def _timed_device_steps(bt, host_batches, prime, warm, K, flush, local):
+    """Device-resident inputs, L2 flushed before every timed step, CUDA events on the library's stream."""
+    import torch
+    stream = torch.cuda.ExternalStream(bt.stream, device=local)
+    ms = []
+    for f, (pts, off, dt) in enumerate(host_batches[:prime + warm + K]):
+        p, o, d = torch.from_numpy(pts).cuda(), torch.from_numpy(off).cuda(), torch.from_numpy(dt).cuda()
+        timed = f >= prime + warm
+        with torch.cuda.stream(stream):
+            if timed:
+                flush.fill_(f & 0xff)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            bt.step_device(p.data_ptr(), o.data_ptr(), d.data_ptr(), p.shape[0], pose=True)
+            if timed:
+                e1.record(stream)
+                e1.synchronize()
+                ms.append(e0.elapsed_time(e1))
+        bt.sync()
+    return np.array(ms)
+
+
+def other_configs(batches, weights3d, flush, local):
+    """The BASELINE.json configurations that are not the headline workload, on ONE GPU (same timing protocol):
+    C3 dense 8.5 m (1000 points/frame, 10 targets, TR_MAX_TRACKS = 10), C4 pose regression alone (65 536 maps,
+    2-D net), C5 all 8192 scenes on one GPU.  C1 (one scene) is `latency.p50_ms_single_scene_*`."""
+    from mmwave_msc_b200 import _lib, pose_weights as pw, synth
+    from mmwave_msc_b200.batched import BatchedTracker, default_config
+    from oracle import mmw_oracle as mo
+    PRIME, WARM, K = 12, 3, 8
+    out = {}
+    # C3
+    gen = synth.gen_batch(range(200_000, 200_256), PRIME + WARM + K, synth.SceneSpec.dense())
+    tiled = _tile_batches(gen, 4)
+    bt = BatchedTracker(1024, max_points=1024, max_tracks=16, device=local, config=default_config(tr_max_tracks=10))
+    bt.load_pose_weights(weights3d)
+    ms = _timed_device_steps(bt, tiled, PRIME, WARM, K, flush, local)
+    _, nt = bt.tracks()
+    out["C3"] = {"what": "dense 8.5 m config: 1024 scenes (256 generated x 4), 1000 points/frame, 10 targets, "
+                         "TR_MAX_TRACKS = 10, full path incl. pose", "scenes": 1024,
+                 "points_per_scene_frame": float(np.mean([t[0].shape[0] for t in tiled]) / 1024),
+                 "tracks_per_scene": float(nt.mean()), "ms_per_step": float(ms.mean()),
+                 "scene_frames_per_s": float(1024 / (ms.mean() / 1e3))}
+    bt.close()
+    # C5 on one GPU: the headline run's own scenes, eight times side by side
+    tiled = _tile_batches(batches[:PRIME + WARM + K], 8)
+    bt = BatchedTracker(8192, max_points=256, max_tracks=8, device=local)
+    bt.load_pose_weights(weights3d)
+    ms = _timed_device_steps(bt, tiled, PRIME, WARM, K, flush, local)
+    out["C5_one_gpu"] = {"what": "8192 scenes on ONE GPU (the 1024 generated scenes x 8), full path incl. pose",
+                         "scenes": 8192, "ms_per_step": float(ms.mean()),
+                         "scene_frames_per_s": float(8192 / (ms.mean() / 1e3))}
+    # C4 on the same context size: 65 536 feature maps through the 2-D net
+    bt.close()
+    N = 65536
+    rng = np.random.default_rng(4)
+    k = rng.integers(20, 65, size=N)
+    rows = np.zeros((N, 64, 5), np.float32)
+    rows[:, :, :3] = rng.normal([0, 0, 1.0], [0.15, 0.15, 0.4], size=(N, 64, 3))
+    rows[:, :, 3] = rng.normal(0, 0.3, size=(N, 64))
+    rows[:, :, 4] = (np.floor(rng.gamma(0.5, 54.0, size=(N, 64))) + 1 - 27.0187) / 70.351
+    rows[np.arange(64)[None, :] >= k[:, None]] = 0.0                    # zero pads after the real rows
+    order = np.argsort(rows[:, :, 0], axis=1, kind="stable")
+    feats = np.take_along_axis(rows, order[:, :, None], axis=1).reshape(N, 8, 8, 5)
+    W2 = pw.make_pose_weights(pw.VARIANT_2D)
+    bt = BatchedTracker(8192, max_tracks=8, device=local, config=default_config(frames_batch=0))
+    bt.load_pose_weights(W2, pw.VARIANT_2D)
+    got = bt.pose(feats)
+    err = float(np.abs(got[:256] - mo.pose_forward(W2, feats[:256], np.float64)).max())
+    _lib.check(bt.lib.mmw_profile(bt._h, 1))
+    for _ in range(5):
+        bt.pose(feats)
+    kms = np.zeros(8); calls = np.zeros(8, np.uint64)
+    _lib.check(bt.lib.mmw_get_kernel_ms(bt._h, _lib.ptr(kms), _lib.ptr(calls)))
+    _lib.check(bt.lib.mmw_profile(bt._h, 0))
+    per = {n: float(kms[i] / calls[i]) for i, n in enumerate(_lib.KERNEL_NAMES) if calls[i]}
+    total = sum(per.values())
+    out["C4"] = {"what": "MARS-style pose regression alone: 65 536 8x8x5 maps -> 57 (define_CNN, tcgen05 path), device "
+                         "time of the pose kernels (CUDA events around every launch)", "rows": N, "kernel_ms": per,
+                 "pose_ms": total, "maps_per_s": N / (total / 1e3),
+                 "algorithmic_tflops": 2837504.0 * N / (total / 1e3) / 1e12,
+                 "max_joint_err_m_vs_fp64_oracle_256_rows": err}
+    bt.close()
+    return out
+
+
+def replay_check(world, S, n_frames_done, weights, gathered, per_scene, local, pose_calls):
+    """a scene's results do not depend on which GPU ran it.  Rank 0 re-runs the first scenes of rank 1's
+    shard from frame 0 through the same sequence of calls in a context of its own and compares the records with
+    the ones rank 1 contributed to the gather -- bitwise."""
+    from mmwave_msc_b200 import _lib, synth
+    from mmwave_msc_b200.batched import BatchedTracker
+    import torch
+    n_check = min(32, S)
+    ids = list(range(S, S + n_check))                     # global scene ids of rank 1's first scenes
+    batches = synth.gen_batch(ids, n_frames_done)
+    bt = BatchedTracker(n_check, max_points=256, max_tracks=8, device=local)
+    bt.load_pose_weights(weights)
+    for f, b in enumerate(batches):
+        bt.step(b.points, b.offsets, b.dt, pose=pose_calls[f])
+    out = torch.empty(n_check * per_scene, dtype=torch.float32, device="cuda")
+    bt.pack_results(out.data_ptr())
+    bt.sync()
+    mine = out.cpu().numpy().view(np.uint32)
+    theirs = gathered[S * per_scene:(S + n_check) * per_scene].cpu().numpy().view(np.uint32)
+    bt.close()
+    return {"scenes_compared": n_check, "of_rank": 1, "frames": n_frames_done,
+            "bitwise_identical": bool(np.array_equal(mine, theirs)),
+            "mismatching_words": int((mine != theirs).sum())}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -182,8 +364,8 @@ def main():
         reference_arm(args, rank, world)
         return
 
-    # the contract is ONE JSON line on stdout: keep NCCL's own banner/debug output off stdout
-    os.environ["NCCL_DEBUG"] = os.environ.get("MMW_NCCL_DEBUG", "WARN")
+    # the contract is ONE JSON line on stdout: NCCL's own debug output (whatever level the caller asked for) goes
+    # to stderr, not to stdout
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
@@ -346,6 +528,10 @@ def main():
         gathered = sharding.gather_results(res_dev, world * S, bt.tcap * _lib.RESULT_FLOATS)
         torch.cuda.synchronize()
         assert gathered.numel() == world * res_dev.numel()
+        # own shard comes back unchanged; another rank's scenes re-run here give the same bits
+        assert torch.equal(gathered[rank * res_dev.numel():(rank + 1) * res_dev.numel()], res_dev)
+        identity = (replay_check(world, S, n_frames, weights, gathered, bt.tcap * _lib.RESULT_FLOATS, local,
+                                 [True] * n_frames) if rank == 0 else None)
 
     if rank == 0:
         pk = peaks()
@@ -370,20 +556,39 @@ def main():
                 ["scene_frames", "N", "M", "U", "Bf", "tracks", "ring_rows", "pose_rows"], cnt)},
         }
         out.update(rooflines(kern, cnt, K, alg, pk, total_ms / K))
+        if world > 1:
+            out["multi_gpu_identity"] = identity
+        else:
+            bt.close()
+            del dev
+            out["configs"] = other_configs(batches, weights, flush, local)
+            out["configs"]["C1"] = {"what": "one scene (what a live 12 Hz sensor sees): host enqueue -> results in host "
+                                            "memory, nothing overlapped",
+                                    "p50_ms_per_frame": latency.get("p50_ms_single_scene_host_enqueue_to_results")}
         if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (the reference arm times all host cores)
-            n, sec = cpu_port_run(range(50_000, 50_004), 60)
-            out["cpu_baseline"] = {"value": n / sec, "unit": UNIT, "cores": 1, "kind": "port",
-                                   "sample": "4 C2-shaped scenes x 60 frames, oracle port (numpy float64 + torch-CPU "
-                                             "fp32 pose net), one thread"}
+            from oracle import make_ref
+            if make_ref.staged_dir():
+                n, sec = reference_run(range(50_000, 50_004), 60)
+                out["cpu_baseline"] = {"value": n / sec, "unit": UNIT, "cores": 1, "kind": "reference",
+                                       "sample": "4 C2-shaped scenes x 60 frames through the unmodified reference "
+                                                 "(oracle/_ref: Utils.normalize_data, TrackBuffer.track, "
+                                                 "estimate_posture; filterpy restatement, torch-CPU fp32 pose net "
+                                                 "behind .predict), one thread"}
+            else:
+                n, sec = cpu_port_run(range(50_000, 50_004), 60)
+                out["cpu_baseline"] = {"value": n / sec, "unit": UNIT, "cores": 1, "kind": "port",
+                                       "sample": "4 C2-shaped scenes x 60 frames, oracle port (numpy float64 + "
+                                                 "torch-CPU fp32 pose net), one thread"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of each kernel from the committed ncu --set full capture (profiles/r01_traffic.json,
-    written by profiles/summarize_ncu.py --traffic), or {} when absent."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per launch of each kernel from the committed ncu --set full capture (profiles/r02_traffic.json,
+    written by profiles/summarize_ncu.py --traffic), or {} when absent.  STATIC: measured once under the profiler for
+    this build, not in this run (a run under ncu is never a bench value)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         return json.load(open(p))
     except Exception:
@@ -399,7 +604,8 @@ def issue_roofline(step_ms, traffic):
     peak = 148 * 4 * 1.965e9            # warp instructions per second at the maximum SM clock
     ach = wi / (step_ms / 1e3)
     return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": ach / peak,
-            "warp_insts_per_launch": wi}
+            "warp_insts_per_launch": wi,
+            "warp_insts_src": "static: ncu smsp__inst_executed.sum of the committed capture (profiles/r02_traffic.json)"}
 
 
 def rooflines(kern, cnt, K, alg_bytes, pk, step_ms):
@@ -425,6 +631,7 @@ def rooflines(kern, cnt, K, alg_bytes, pk, step_ms):
             a = step_bytes / (st / 1e3) / 1e9
             out["roofline_step"] = {"kernel": "step_kernel", "bound": "hbm", "achieved": a, "peak": pk["hbm_gbs"],
                                     "unit": "GB/s", "frac": a / pk["hbm_gbs"], "traffic": traffic.get("step_kernel"),
+                                    "traffic_src": "static: ncu dram bytes of the committed capture (profiles/r02_traffic.json)",
                                     "algorithmic_bytes_per_launch": step_bytes, "peak_src": pk["src"],
                                     # what actually bounds it: warp-instruction issue (ncu smsp__inst_executed.sum of the
                                     # committed capture / (SMs x 4 schedulers x SM clock))

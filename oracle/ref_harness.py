@@ -28,6 +28,10 @@ from typing import Dict, List, Optional
 import numpy as np
 
 REF_SRC = os.environ.get("MMW_REFERENCE_SRC", "/root/reference/src")
+if not os.path.isfile(os.path.join(REF_SRC, "Tracking.py")):      # GPU box: the copy staged by oracle/make_ref.py
+    _staged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "src")
+    if os.path.isfile(os.path.join(_staged, "Tracking.py")):
+        REF_SRC = _staged
 _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "filterpy_shim")
 
 
