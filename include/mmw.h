@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MMW_ABI_VERSION 2
+#define MMW_ABI_VERSION 3
 
 typedef enum mmw_status {
     MMW_OK = 0,
@@ -70,6 +70,12 @@ typedef struct mmw_config {
     double fade_size_max;          /* V_SCREEN_FADE_SIZE_MAX :50 */
     double fade_size_min;          /* V_SCREEN_FADE_SIZE_MIN :51 */
     double fade_weight;            /* V_SCREEN_FADE_WEIGHT :52 */
+    /* Unit of the Doppler column of every point row: doppler [m/s] = row[3] * doppler_res, multiplied in float64 on
+     * the device.  The sensor reports dopplerIdx (int16) and the reference forms doppler = dopplerIdx *
+     * dopplerResolutionMps in float64 (ReadDataIWR1443.py:163-165) -- a value fp32 cannot hold.  With doppler_res =
+     * dopplerResolutionMps the rows carry the index (exact in fp32) and the product is the reference's, bit for bit.
+     * 1.0 (default; 0 is read as 1.0): rows carry m/s directly (exact for values that are fp32-representable). */
+    double doppler_res;
 } mmw_config;
 
 /* Fills *cfg with the reference's default constants. */
@@ -105,6 +111,10 @@ int mmw_abi_version(void);
 
 /* Resets every scene to the state of a fresh TrackBuffer() + BatchedData() (Tracking.py:504-511, 38-41). */
 int mmw_reset(mmw_ctx* ctx);
+
+/* Changes mmw_config::doppler_res of a live context (takes effect with the next call; rows already in the rings are
+ * re-read in the new unit, so change it only while they hold none -- e.g. before the first frame). */
+int mmw_set_doppler_resolution(mmw_ctx* ctx, double doppler_res);
 
 /* Checkpoint / resume of the tracker state of all scenes (track records, rings, keypoints, id counters): what a
  * replay needs to continue bit-identically in this or another context created with the same n_scenes,

@@ -142,6 +142,7 @@ class TrackBuffer:
         self.t = time.time()
         self._bt: Optional[BatchedTracker] = None
         self._model_key = None
+        self._doppler_seen = False          # a frame with a non-zero Doppler value went to the device
 
     # ------------------------------------------------------------------------------------------------
     def _ctx(self, n_points: int) -> BatchedTracker:
@@ -167,6 +168,13 @@ class TrackBuffer:
                             "(the device tracker works from the sensor rows it carries)")
         world = np.asarray(pointcloud)
         bt = self._ctx(raw.shape[0])
+        res = float(getattr(pointcloud, "doppler_res", 1.0))
+        if bt.cfg.doppler_res != res:       # unit of the rows' Doppler column (Utils._doppler_units)
+            if self._doppler_seen:
+                raise ValueError("the Doppler resolution of the input changed mid-sequence (%r -> %r): set "
+                                 "constants.DOPPLER_RESOLUTION" % (bt.cfg.doppler_res, res))
+            bt.set_doppler_resolution(res)
+        self._doppler_seen = self._doppler_seen or bool(np.any(raw[:, 3] != 0))
         if batch._external_add:
             raise NotImplementedError("frames added to the global ring by the caller are not mirrored on the device")
         for op in batch._pending:                       # preprocessing.py:263-264 pops the ring between frames

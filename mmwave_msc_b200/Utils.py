@@ -24,15 +24,18 @@ from .batched import BatchedTracker, config_from_constants
 
 class WorldPoints(np.ndarray):
     """(M, 8) float64 array returned by normalize_data that remembers the fp32 sensor rows it came from, which
-    is what the device tracker consumes (rings are stored as raw rows, SURVEY/DESIGN 'data layout')."""
+    is what the device tracker consumes (rings are stored as raw rows, SURVEY/DESIGN 'data layout'), and the unit
+    of their Doppler column."""
 
-    def __new__(cls, world: np.ndarray, raw: np.ndarray):
+    def __new__(cls, world: np.ndarray, raw: np.ndarray, doppler_res: float = 1.0):
         obj = np.asarray(world, dtype=np.float64).view(cls)
         obj.raw = raw
+        obj.doppler_res = doppler_res
         return obj
 
     def __array_finalize__(self, obj):
         self.raw = None          # any derived view/copy loses the tag
+        self.doppler_res = 1.0
 
 
 _stage_ctx: Optional[BatchedTracker] = None
@@ -50,17 +53,48 @@ def _stage(min_points: int = 0) -> BatchedTracker:
     return _stage_ctx
 
 
+def _doppler_units(d: np.ndarray):
+    """Doppler column of the device rows and its unit.  The sensor reports dopplerIdx and the reference forms
+    doppler = dopplerIdx * dopplerResolutionMps in float64 (ReadDataIWR1443.py:163-165; DataLogging.py writes that
+    value to the CSV logs) -- not representable in fp32.  The device therefore takes the INDEX (exact in fp32) and
+    multiplies by the resolution in float64.  The resolution is ``constants.DOPPLER_RESOLUTION`` when set; else, if
+    the values are fp32-representable they are passed as they are (unit 1.0); else it is inferred from the data once
+    (every value must be an exact integer multiple) and kept in ``constants.DOPPLER_RESOLUTION``."""
+    res = getattr(const, "DOPPLER_RESOLUTION", None)
+    if res is None:
+        d32 = d.astype(np.float32)
+        if np.array_equal(d32.astype(np.float64), d):
+            return d32, 1.0
+        nz = np.abs(d[d != 0])
+        for k in range(1, 65):
+            r = float(nz.min()) / k
+            if np.array_equal(np.rint(d / r) * r, d):
+                res = const.DOPPLER_RESOLUTION = r
+                break
+        else:
+            raise ValueError("doppler values are neither fp32-representable nor integer multiples of one resolution: "
+                             "set constants.DOPPLER_RESOLUTION to the sensor's dopplerResolutionMps")
+    idx = np.rint(d / res)
+    if not np.array_equal(idx * res, d) or (len(idx) and np.abs(idx).max() >= 2 ** 24):
+        raise ValueError("doppler values are not integer multiples of constants.DOPPLER_RESOLUTION = %r" % res)
+    return idx.astype(np.float32), float(res)
+
+
 def normalize_data(detObj) -> np.ndarray:
     """Sensor dict {x, y, z, doppler, peakVal} -> (M, 8) [x y z vx vy vz doppler peakVal] in the room frame,
     restricted to the scene bounds (same contract as the reference)."""
     raw = np.stack([np.asarray(detObj[k], dtype=np.float64) for k in ("x", "y", "z", "doppler", "peakVal")], axis=1)
     raw32 = raw.astype(np.float32)
-    if not np.array_equal(raw32.astype(np.float64), raw):
-        raise ValueError("sensor values must be representable in float32 (they are int16/2^Q lattice values)")
+    if not np.array_equal(raw32[:, [0, 1, 2, 4]].astype(np.float64), raw[:, [0, 1, 2, 4]]):
+        raise ValueError("x, y, z, peakVal must be representable in float32 (they are int16 / 2^Q lattice values)")
+    raw32[:, 3], res = _doppler_units(raw[:, 3])
     if raw32.shape[0] == 0:
-        return WorldPoints(np.empty((0, 8)), raw32)
-    world, keep = _stage().preprocess(raw32)
-    return WorldPoints(world[keep], np.ascontiguousarray(raw32[keep]))
+        return WorldPoints(np.empty((0, 8)), raw32, res)
+    st = _stage()
+    if st.cfg.doppler_res != res:
+        st.set_doppler_resolution(res)
+    world, keep = st.preprocess(raw32)
+    return WorldPoints(world[keep], np.ascontiguousarray(raw32[keep]), res)
 
 
 def altered_EuclideanDist(p1, p2) -> float:

@@ -14,7 +14,7 @@ MMW_POSE_2D, MMW_POSE_3D = 0, 1
 STEP_POSE, STEP_DEVICE_INPUT, STEP_RECORD_LABELS = 0x1, 0x2, 0x4
 SCENE_POINT_OVERFLOW, SCENE_TRACK_OVERFLOW = 0x1, 0x2
 RESULT_FLOATS = 72
-ABI_VERSION = 2            # MMW_ABI_VERSION of include/mmw.h this binding was written against
+ABI_VERSION = 3            # MMW_ABI_VERSION of include/mmw.h this binding was written against
 KERNEL_NAMES = ["step", "pose_index", "pose_features", "conv", "fc1", "fc2", "dbscan_big", "k7"]
 
 
@@ -39,6 +39,7 @@ class Config(C.Structure):
         ("default_posture", C.c_float * 57), ("reserved1", C.c_float),
         ("m_x", C.c_double), ("m_y", C.c_double), ("m_z", C.c_double),
         ("fade_size_max", C.c_double), ("fade_size_min", C.c_double), ("fade_weight", C.c_double),
+        ("doppler_res", C.c_double),
     ]
 
 
@@ -74,6 +75,7 @@ SIGNATURES = {
     "mmw_create": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_p)]),
     "mmw_destroy": (C.c_int, [_p]),
     "mmw_reset": (C.c_int, [_p]),
+    "mmw_set_doppler_resolution": (C.c_int, [_p, C.c_double]),
     "mmw_state_size": (C.c_size_t, [_p]),
     "mmw_state_dump": (C.c_int, [_p, _p, C.c_size_t]),
     "mmw_state_restore": (C.c_int, [_p, _p, C.c_size_t]),

@@ -53,7 +53,8 @@ def config_from_constants(const) -> _lib.Config:
         m_x=float(getattr(const, "M_X", 0.32)), m_y=float(getattr(const, "M_Y", -0.6)),
         m_z=float(getattr(const, "M_Z", 1.3)), fade_size_max=float(getattr(const, "V_SCREEN_FADE_SIZE_MAX", 0.3)),
         fade_size_min=float(getattr(const, "V_SCREEN_FADE_SIZE_MIN", 0.2)),
-        fade_weight=float(getattr(const, "V_SCREEN_FADE_WEIGHT", 0.08)))
+        fade_weight=float(getattr(const, "V_SCREEN_FADE_WEIGHT", 0.08)),
+        doppler_res=float(getattr(const, "DOPPLER_RESOLUTION", None) or 1.0))
 
 
 class BatchedTracker:
@@ -85,6 +86,12 @@ class BatchedTracker:
 
     def reset(self):
         _lib.check(self.lib.mmw_reset(self._h))
+
+    def set_doppler_resolution(self, doppler_res: float):
+        """Unit of the Doppler column of the point rows: doppler [m/s] = row[3] * doppler_res in float64 on the device
+        (mmw_config::doppler_res).  With the sensor's dopplerResolutionMps the rows carry dopplerIdx."""
+        _lib.check(self.lib.mmw_set_doppler_resolution(self._h, float(doppler_res)))
+        self.cfg.doppler_res = float(doppler_res)
 
     @property
     def stream(self) -> int:

@@ -16,6 +16,10 @@ V_SCREEN_FADE_SIZE_MAX = 0.3
 V_SCREEN_FADE_SIZE_MIN = 0.2
 V_SCREEN_FADE_WEIGHT = 0.08
 
+# Doppler resolution of the radar profile [m/s per index] (dopplerResolutionMps, ReadDataIWR1443.py:249-257).  Not a
+# constant of the reference (it derives it from the .cfg it uploads); None = take it from the data (Utils._doppler_units)
+DOPPLER_RESOLUTION = None
+
 # sensor pose (constants.py:41-42)
 S_HEIGHT = 1.8
 S_TILT = -5

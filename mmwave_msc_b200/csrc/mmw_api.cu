@@ -121,6 +121,7 @@ static void fill_devconfig(const mmw_config& c, int ncap, int tcap, DevConfig* d
     d->int_std = c.intensity_std;
     d->nudge_thres = c.x_nudge_thres;
     d->nudge_gain = c.x_nudge_gain;
+    d->doppler_res = c.doppler_res != 0.0 ? c.doppler_res : 1.0;
     d->db_min_samples = c.db_min_samples;
     d->ring_size = c.frames_batch + 1;
     d->tr_max_tracks = c.tr_max_tracks;
@@ -162,6 +163,7 @@ int mmw_default_config(mmw_config* c) {
     std::memcpy(c->default_posture, kDefaultPosture, sizeof(kDefaultPosture));
     c->m_x = 0.32; c->m_y = -0.6; c->m_z = 1.3;
     c->fade_size_max = 0.3; c->fade_size_min = 0.2; c->fade_weight = 0.08;
+    c->doppler_res = 1.0;
     return MMW_OK;
 }
 
@@ -351,6 +353,14 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     if (rc != MMW_OK) { mmw_destroy(x); return rc; }
     cudaStreamSynchronize(x->stream);
     *out = x;
+    return MMW_OK;
+}
+
+int mmw_set_doppler_resolution(mmw_ctx* x, double doppler_res) {
+    if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
+    if (!(doppler_res > 0.0) || !std::isfinite(doppler_res)) return fail(MMW_ERR_INVALID, "doppler_res must be positive and finite");
+    x->cfg.doppler_res = doppler_res;
+    x->dc.doppler_res = doppler_res;
     return MMW_OK;
 }
 
@@ -737,7 +747,7 @@ __global__ void preprocess_kernel(DevConfig c, const float* pts, size_t n, doubl
     double* o = world + i * 8;
 #pragma unroll
     for (int k = 0; k < 6; ++k) o[k] = w[k];
-    o[6] = (double)p[3];
+    o[6] = __dmul_rn((double)p[3], c.doppler_res);
     o[7] = (double)p[4];
     keep[i] = ((w[2] <= c.z_max) && (w[2] > 0.0) && (w[1] > 0.0)) ? 1 : 0;
 }
@@ -915,7 +925,7 @@ __global__ void __launch_bounds__(256) tlv_decode_kernel(const uint8_t* bytes, c
         o[j * kRawCols + 0] = (float)((double)rd_i16(b + 6) / scale);
         o[j * kRawCols + 1] = (float)((double)rd_i16(b + 8) / scale);
         o[j * kRawCols + 2] = (float)((double)rd_i16(b + 10) / scale);
-        o[j * kRawCols + 3] = (float)((double)dop * doppler_res);
+        o[j * kRawCols + 3] = (float)((double)dop * doppler_res);        // doppler_res: in units of the context's (1 = the index)
         o[j * kRawCols + 4] = (float)rd_i16(b + 4);
     }
 }
@@ -951,7 +961,7 @@ __global__ void __launch_bounds__(kFeatPts) export_track0_kernel(DevConfig c, co
                 v[0] = __dsub_rn((double)r[0], cx);
                 v[1] = __dsub_rn(yw, cy);
                 v[2] = zw;
-                v[3] = (double)r[3];
+                v[3] = __dmul_rn((double)r[3], c.doppler_res);
                 v[4] = (double)r[4];
             }
         }
@@ -1041,7 +1051,7 @@ int mmw_decode_tlv(mmw_ctx* x, const uint8_t* packets, const int64_t* packet_off
         TLV_CK(cudaMemcpyAsync(d_poff, point_offsets, sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice, x->stream));
         const long long threads = 32LL * n;
         tlv_decode_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, x->stream>>>(
-            d_bytes, d_off, n, d_poff, num_doppler_bins / 2 - 1, doppler_res, d_pts);
+            d_bytes, d_off, n, d_poff, num_doppler_bins / 2 - 1, doppler_res / x->dc.doppler_res, d_pts);
         TLV_CK(cudaGetLastError());
         x->launches++;
         TLV_CK(cudaMemcpyAsync(points, d_pts, sizeof(float) * kRawCols * total, cudaMemcpyDeviceToHost, x->stream));

@@ -28,6 +28,7 @@ struct DevConfig {
     double q_var, p_init, g_init, a_n, a_spr;
     double spread_lim[6];
     double int_mu, int_std, nudge_thres, nudge_gain;
+    double doppler_res;        // doppler [m/s] = row[3] * doppler_res (float64 product, ReadDataIWR1443.py:163-165)
     int db_min_samples, ring_size, tr_max_tracks, enable_est, est_pointnum;
     int ncap, tcap;
     // grid screen in front of DBSCAN (dbscan.cuh): fixed 16 x 16 cells over world (x, y'), at least one eps reach wide
@@ -196,7 +197,7 @@ __device__ __forceinline__ double div_zero_fast(double num, double den) {
 
 __device__ __forceinline__ void world_from_raw(const DevConfig& c, float fx, float fy, float fz, float fd,
                                                double w[6]) {
-    const double x = fx, y = fy, z = fz, d = fd;
+    const double x = fx, y = fy, z = fz, d = __dmul_rn((double)fd, c.doppler_res);
     const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
     double vx, vy, vz;
     if (r == 0.0) {                       // Utils.py:387-390

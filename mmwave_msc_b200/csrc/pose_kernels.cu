@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) pose_feature_kernel(PoseFeatArgs a) {
                     v[0] = (float)key;
                     v[1] = (float)__dsub_rn(yw, cy);
                     v[2] = (float)zw;
-                    v[3] = d;
+                    v[3] = (float)__dmul_rn((double)d, c.doppler_res);
                     v[4] = (float)__ddiv_rn(__dsub_rn((double)p, c.int_mu), c.int_std);
                 }
                 keys[warp][i] = key;

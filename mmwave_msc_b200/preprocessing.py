@@ -20,7 +20,7 @@ from typing import Dict, Iterable, List, Optional, Sequence
 import numpy as np
 
 from . import constants as const
-from .Utils import OfflineManager
+from .Utils import OfflineManager, _doppler_units
 from .batched import BatchedTracker, config_from_constants
 
 
@@ -62,6 +62,7 @@ def preprocess_dataset_batched(experiment_dirs: Sequence[str],
                         config=config_from_constants(const))
     first_iter = [True] * E
     t_prev = [0.0] * E
+    doppler_seen = False
     while True:
         live = [e for e in range(E) if not readers[e].is_finished()]
         if not live:
@@ -84,8 +85,15 @@ def preprocess_dataset_batched(experiment_dirs: Sequence[str],
                 t_prev[e] = det["posix"][0] / 1000
                 raw = np.stack([np.asarray(det[k], np.float64) for k in ("x", "y", "z", "doppler", "peakVal")], axis=1)
                 raw32 = raw.astype(np.float32)
-                if not np.array_equal(raw32.astype(np.float64), raw):
-                    raise ValueError("sensor values must be representable in float32 (int16/2^Q lattice values)")
+                if not np.array_equal(raw32[:, [0, 1, 2, 4]].astype(np.float64), raw[:, [0, 1, 2, 4]]):
+                    raise ValueError("x, y, z, peakVal must be representable in float32 (int16/2^Q lattice values)")
+                raw32[:, 3], res = _doppler_units(raw[:, 3])        # the index; the device multiplies in float64
+                if bt.cfg.doppler_res != res:
+                    if doppler_seen:
+                        raise ValueError("Doppler resolution differs between experiments/frames: set "
+                                         "constants.DOPPLER_RESOLUTION")
+                    bt.set_doppler_resolution(res)
+                doppler_seen = doppler_seen or bool(np.any(raw32[:, 3] != 0))
                 clouds[e] = raw32
                 stepped[e] = True
             else:

@@ -180,8 +180,44 @@ def screen_traces():
               "clustered points per run", [int((r["labels"] >= 0).sum()) for r in recs if r["labels"] is not None])
 
 
+DOPPLER_RES_12HZ = 0.0626302709636043     # dopplerResolutionMps of config_cases/iwr1443sdk2_4m_12hz.cfg (the reference's parser)
+
+
+def extra_traces():
+    """(1) Doppler as the sensor reports it: rows carry dopplerIdx, the reference sees dopplerIdx * dopplerResolutionMps
+    in float64 (ReadDataIWR1443.py:163-165) -- values fp32 cannot hold.  (2) a frame without data among the first
+    tracked frames: the dataset builder pops the global ring (preprocessing.py:262-264) while it still holds the
+    deque's initial empty frame, so the pop removes that and not the first real frame."""
+    sc = synth.gen_scene(31, 60)
+    idx_frames = []
+    for fr in sc.frames:
+        r = np.asarray(fr, np.float32).copy()
+        r[:, 3] = np.rint(r[:, 3].astype(np.float64) / 0.0626).astype(np.float32)
+        idx_frames.append(r)
+    g = {"frames": idx_frames, "doppler_res": DOPPLER_RES_12HZ}
+    recs = rh.run_reference_scene(trace_io.reference_frames(g), sc.dts(), pose_fn=lambda x: np.zeros((len(x), 57)))
+    d = trace_io.pack(idx_frames, sc.dts(), recs, doppler_res=DOPPLER_RES_12HZ)
+    d["max_tracks"] = np.array(4, np.int32)
+    np.savez_compressed(os.path.join(GOLDEN, "c1_s31_doppler_idx.npz"), **d)
+    print("c1_s31_doppler_idx tracks at end", len(recs[-1]["tracks"]), "next id", recs[-1]["next_track_id"])
+
+    # a blob of 22 points per frame: no cluster until two frames are fused (min_samples = 35)
+    frames, dts = screen_case_frames(21, lambda h: ([(22, 1.0, 2.5, 0.08)], 40), n_frames=7)
+    missing = [False, True, False, False, True, False, False]
+    frames = [np.zeros((0, 5), np.float32) if m else f for f, m in zip(frames, missing)]
+    recs = rh.run_reference_scene(frames, dts, pose_fn=lambda x: np.zeros((len(x), 57)), missing=missing)
+    d = trace_io.pack(frames, dts, recs, missing=missing)
+    d["max_tracks"] = np.array(4, np.int32)
+    np.savez_compressed(os.path.join(GOLDEN, "ring_pop_placeholder.npz"), **d)
+    print("ring_pop_placeholder: ring per frame", [r["ring_counts"].tolist() for r in recs], "tracks",
+          [len(r["tracks"]) for r in recs])
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--extra-only" in sys.argv:
+        extra_traces()
+        return
     if "--screen-only" in sys.argv:
         screen_traces()
         return
@@ -200,6 +236,7 @@ def main():
               "dbscan runs", int(d["labels_ran"].sum()))
     np.savez_compressed(os.path.join(GOLDEN, "track0_export.npz"), **track0_export_golden())
     screen_traces()
+    extra_traces()
     if "--deviation" in sys.argv:
         dev = balltree_deviation()
         json.dump(dev, open(os.path.join(GOLDEN, "balltree_deviation.json"), "w"), indent=1)

@@ -129,11 +129,14 @@ class _ModelAdapter:
 
 def run_reference_scene(frames: List[np.ndarray], dts: np.ndarray, pose_fn=None,
                         dbscan_algorithm: str = "brute", stable_sort: bool = True,
-                        max_tracks: Optional[int] = None, export0: bool = False) -> List[dict]:
+                        max_tracks: Optional[int] = None, export0: bool = False,
+                        missing: Optional[List[bool]] = None) -> List[dict]:
     """Run the offline_main.py loop body (offline_main.py:45-60) on one scene.
 
     Returns one record per frame with the decisions and states after the frame.
     Track ids are the value of ``next_track_id`` at spawn (Tracking.py:587-588).
+    ``missing[f]``: the frame has no sensor data -- the dataset builder's loop then calls ``batch.pop_frame()``
+    instead of the loop body (preprocessing.py:177-264); ``frames[f]`` is ignored.
     """
     const, utils, tracking = load_reference()
     out: List[dict] = []
@@ -153,6 +156,10 @@ def run_reference_scene(frames: List[np.ndarray], dts: np.ndarray, pose_fn=None,
         tb._calc_dist_fun = calc_spy
         for f, raw in enumerate(frames):
             tb.dt = float(dts[f])
+            gone = missing is not None and bool(missing[f])
+            if gone:
+                batch.pop_frame()                                # preprocessing.py:262-264
+                raw = np.zeros((0, 5))
             eff = utils.normalize_data(detobj_from_raw(raw))
             rec = {"M": int(eff.shape[0]), "world": eff.copy()}
             n_lab0, n_as0 = len(pr.labels_log), len(assoc_log)

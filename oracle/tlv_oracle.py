@@ -1,11 +1,15 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's UART TLV decoder for one framed packet
 (ReadDataIWR1443.py:88-201, class ReadIWR14xx.read after the magic-word search).
 
-PARITY UNPINNED.  The reference decoder cannot run in this image: it stores ``np.matmul(bytes, [1, 256])`` (0..65535)
-into ``int16`` arrays and evaluates ``int16_array - 65535``, both of which raise OverflowError under numpy >= 2 (NEP 50;
-probed with numpy 2.3.5: "Python integer 40000 out of bounds for int16"), and its module imports ``serial``.  What
-follows restates the arithmetic the reference performs under its pinned numpy 1.26.3 (requirements.txt:8), where those
-assignments wrap modulo 2^16 (C cast) and ``int16 - 65535`` is computed in int32 and wrapped on assignment:
+PARITY PINNED (under a numpy-1.x casting shim).  The reference decoder cannot run as it is in this image: it stores
+``np.matmul(bytes, [1, 256])`` (0..65535) into ``int16`` arrays and evaluates ``int16_array - 65535`` for every frame
+(even when the mask that selects its operand is empty), both of which raise OverflowError under numpy >= 2 (NEP 50;
+probed with numpy 2.3.5), and its module imports ``serial``.  ``oracle/gen_tlv_golden.py`` runs ``ReadIWR14xx.read()``
+unmodified with a stub ``serial`` and a proxy ``np`` whose int16 arrays restore exactly those two numpy-1.26
+behaviours (requirements.txt:8: C-cast wrap on assignment; value-based promotion of ``int16 - 65535`` to int32), over
+the reference's own three radar profiles parsed by its own ``__parseConfigFile``.  The 27 packets and what the
+reference returned for them are ``tests/golden/tlv/reference_tlv.npz``; ``tests/test_tlv.py`` holds this restatement to
+them bit for bit (float64) and the CUDA decoder to both.  What the restatement says:
 
 * header, little endian: magic 8 B | version 4 | totalPacketLen 4 | platform 4 | frameNumber 4 | timeCpuCycles 4 |
   numDetectedObj 4 | numTLVs 4  (ReadDataIWR1443.py:90-98; no subFrameNumber: SDK 1 layout, :101-103)
@@ -19,7 +23,9 @@ assignments wrap modulo 2^16 (C cast) and ``int16 - 65535`` is computed in int32
 * doppler = dopplerIdx * dopplerResolutionMps, x, y, z = int16 / 2**xyzQFormat (:176-184), float64
 
 The device decoder emits float32 rows [x, y, z, doppler, peakVal] -- the tracker's input format; x, y, z, peakVal are
-exact, doppler is the float64 product rounded to float32 (the same value the synthetic generator stores).
+exact; the Doppler column is in units of the context's mmw_config::doppler_res: with doppler_res =
+dopplerResolutionMps it is dopplerIdx itself and the device forms the float64 product the reference forms; with the
+default unit 1.0 it is that product rounded to float32 (the value the synthetic generator stores).
 """
 from __future__ import annotations
 

@@ -17,9 +17,14 @@ def _pad3(a):
     return out
 
 
-def pack(frames: List[np.ndarray], dts: np.ndarray, recs: List[dict], feature_every: int = 7) -> Dict[str, np.ndarray]:
+def pack(frames: List[np.ndarray], dts: np.ndarray, recs: List[dict], feature_every: int = 7,
+         doppler_res: float = 1.0, missing=None) -> Dict[str, np.ndarray]:
+    """``frames``: fp32 rows as the device takes them -- Doppler column in units of ``doppler_res`` (the reference was
+    run on row[3] * doppler_res in float64).  ``missing``: frames without sensor data (the global ring is popped)."""
     F = len(recs)
     d: Dict[str, np.ndarray] = {}
+    d["doppler_res"] = np.array(doppler_res, np.float64)
+    d["missing"] = np.zeros(F, bool) if missing is None else np.asarray(missing, bool)
     d["raw"] = np.concatenate(frames, axis=0).astype(np.float32)
     d["raw_off"] = np.cumsum([0] + [len(f) for f in frames]).astype(np.int64)
     d["dts"] = np.asarray(dts, np.float64)
@@ -76,4 +81,17 @@ def unpack(d) -> dict:
             k = featmap[f]
             r["features"] = np.asarray(d["feats"][d["feat_off"][k]:d["feat_off"][k + 1]], np.float64)
         recs.append(r)
-    return {"frames": frames, "dts": np.asarray(d["dts"], np.float64), "recs": recs}
+    files = getattr(d, "files", d)
+    return {"frames": frames, "dts": np.asarray(d["dts"], np.float64), "recs": recs,
+            "doppler_res": float(d["doppler_res"]) if "doppler_res" in files else 1.0,
+            "missing": np.asarray(d["missing"], bool) if "missing" in files else np.zeros(F, bool)}
+
+
+def reference_frames(g: dict) -> List[np.ndarray]:
+    """The float64 rows the reference saw: Doppler column in m/s."""
+    out = []
+    for fr in g["frames"]:
+        r = np.asarray(fr, np.float64).copy()
+        r[:, 3] = r[:, 3] * g["doppler_res"]
+        out.append(r)
+    return out

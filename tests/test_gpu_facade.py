@@ -90,6 +90,33 @@ def test_apply_dbscan_and_opaque_model():
         np.testing.assert_array_equal(trk.keypoints, np.arange(57, dtype=np.float32) + k)
 
 
+def test_facade_takes_float64_doppler_of_a_real_radar_profile(monkeypatch):
+    """detObj as the reference's reader produces it: doppler = dopplerIdx * dopplerResolutionMps in float64
+    (ReadDataIWR1443.py:163-165), not fp32-representable.  The facade recovers the index, the device multiplies in
+    float64: decisions and states equal the reference's own trace (tests/golden/c1_s31_doppler_idx.npz)."""
+    import os
+    from conftest import GOLDEN
+    from oracle import trace_io
+    from mmwave_msc_b200 import Tracking, Utils, constants
+    g = trace_io.unpack(np.load(os.path.join(GOLDEN, "c1_s31_doppler_idx.npz")))
+    monkeypatch.setattr(constants, "DOPPLER_RESOLUTION", None)
+    monkeypatch.setattr(Utils, "_stage_ctx", None)
+    tb, batch = Tracking.TrackBuffer(), Tracking.BatchedData()
+    for f, (fr, dt, rec) in enumerate(zip(trace_io.reference_frames(g), g["dts"], g["recs"])):
+        det = {k: fr[:, i].tolist() for i, k in enumerate(("x", "y", "z", "doppler", "peakVal"))}
+        tb.dt = float(dt)
+        eff = Utils.normalize_data(det)
+        assert eff.shape[0] == rec["M"]
+        assert np.isin(np.asarray(eff)[:, 6], fr[:, 3]).all()        # Doppler column: the float64 input values, exactly
+        if eff.shape[0]:
+            tb.track(eff, batch)
+        assert [t.id for t in tb.effective_tracks] == [t["id"] for t in rec["tracks"]], "frame %d" % f
+        for trk, t in zip(tb.effective_tracks, rec["tracks"]):
+            np.testing.assert_allclose(trk.state.x[:, 0], t["x"], rtol=1e-6, atol=1e-9, err_msg="frame %d" % f)
+    assert constants.DOPPLER_RESOLUTION == g["doppler_res"] and len(tb.effective_tracks) >= 1
+    assert not np.array_equal(fr[:, 3].astype(np.float32).astype(np.float64), fr[:, 3])   # fp32 could not hold them
+
+
 def test_replay_of_reference_csv_log(tmp_path):
     """offline_main.py's control flow over a CSV log in the reference's format, vs the oracle fed by the same reader."""
     from mmwave_msc_b200 import Tracking, Utils, replay

@@ -259,11 +259,14 @@ def test_against_reference_golden_trace(case):
     g = trace_io.unpack(d)
     mt = int(d["max_tracks"])
     dense = max(len(f) for f in g["frames"]) > 256
+    # rows as the sensor reports them: the Doppler column in units of doppler_res (c1_s31_doppler_idx: the index)
     bt = BatchedTracker(1, max_points=1024 if dense else 256, max_tracks=16 if dense else 8,
-                        config=default_config(tr_max_tracks=mt))
+                        config=default_config(tr_max_tracks=mt, doppler_res=g["doppler_res"]))
     bt.load_pose_weights(pw.make_pose_weights(pw.VARIANT_3D))
     for f, (fr, dt, rec) in enumerate(zip(g["frames"], g["dts"], g["recs"])):
         offsets = np.array([0, len(fr)], np.int32)
+        if g["missing"][f]:
+            bt.ring_pop(0)                               # a frame without data (preprocessing.py:262-264)
         want_pose = rec["features"] is not None
         bt.step(fr, offsets, np.array([dt]), pose=want_pose, record_labels=True)
         compare_frame(bt, [rec], offsets, "%s frame %d" % (case, f), labels=bt.labels(),

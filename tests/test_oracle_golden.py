@@ -86,7 +86,12 @@ def test_track0_export_matches_reference(name):
 
 def _run_oracle(g, max_tracks):
     so = mo.SceneOracle(mo.OracleConfig(tr_max_tracks=max_tracks))
-    return [so.step(fr, dt) for fr, dt in zip(g["frames"], g["dts"])]
+    out = []
+    for fr, dt, gone in zip(trace_io.reference_frames(g), g["dts"], g["missing"]):
+        if gone:
+            so.ring.pop()                                # preprocessing.py:262-264
+        out.append(so.step(fr, dt))
+    return out
 
 
 @pytest.mark.parametrize("case", golden_cases())

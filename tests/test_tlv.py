@@ -1,6 +1,10 @@
-"""UART TLV packets -> point rows.  PARITY UNPINNED (oracle/tlv_oracle.py header): the reference
-decoder needs numpy 1.26 and cannot run here, so these tests hold the CUDA decoder to the restated oracle and the
-oracle to hand-computed vectors of the reference's documented arithmetic (ReadDataIWR1443.py:88-201)."""
+"""UART TLV packets -> point rows.  The oracle (oracle/tlv_oracle.py) is pinned to the reference's
+own decoder: tests/golden/tlv/reference_tlv.npz holds what `ReadIWR14xx.read()` (ReadDataIWR1443.py:27-201, run
+unmodified by oracle/gen_tlv_golden.py under a shim that restores the two numpy-1.26 int16 casting behaviours it relies
+on) returns for 27 packets over the reference's three radar profiles -- negative coordinates, the Doppler wrap quirk,
+peakVal beyond int16, wrong TLV type, no objects, an incomplete packet.  The CUDA decoder is held to those vectors and
+to the oracle on arbitrary words."""
+import os
 import struct
 
 import numpy as np
@@ -35,6 +39,50 @@ def test_oracle_known_vectors():
     assert tlv.decode_packet(tlv.encode_packet(9, np.ones((3, 5)), Q, RES, tlv_type=2), BINS, RES)[0] == 0
     assert tlv.decode_packet(b"\x00" + pkt[1:], BINS, RES)[0] == 0
     assert tlv.decode_packet(pkt[:-3], BINS, RES)[0] == 0
+
+
+def _reference_vectors():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tlv", "reference_tlv.npz"))
+    po, ro = g["packet_offsets"], g["row_offsets"]
+    for i in range(len(po) - 1):
+        yield (bytes(g["packet_bytes"][po[i]:po[i + 1]]), float(g["params"][i, 0]), float(g["params"][i, 1]),
+               int(g["ok"][i]), int(g["frame"][i]), g["rows"][ro[i]:ro[i + 1]])
+
+
+def test_oracle_matches_reference_decoder_vectors():
+    n_ok = 0
+    for pkt, bins, res, ok, frame, rows in _reference_vectors():
+        wok, wframe, wrows = tlv.decode_packet(pkt, bins, res)
+        assert (wok, wframe) == (ok, frame)
+        if ok:
+            np.testing.assert_array_equal(wrows, rows)            # float64, bit for bit
+            n_ok += 1
+        else:
+            assert wrows is None
+    assert n_ok == 18
+
+
+@pytest.mark.gpu
+def test_device_decoder_matches_reference_decoder_vectors():
+    """Context whose Doppler unit is the profile's dopplerResolutionMps: the rows carry dopplerIdx and
+    row[3] * doppler_res in float64 is the reference's doppler value bit for bit; x, y, z, peakVal are exact."""
+    from mmwave_msc_b200.batched import BatchedTracker, default_config
+    vecs = list(_reference_vectors())
+    for res in sorted({v[2] for v in vecs}):
+        sel = [v for v in vecs if v[2] == res]
+        bt = BatchedTracker(1, config=default_config(doppler_res=res))
+        pts, off, frames, ok = bt.decode_tlv([v[0] for v in sel], sel[0][1], res)
+        for i, (pkt, bins, _, wok, wframe, rows) in enumerate(sel):
+            assert bool(ok[i]) == bool(wok) and int(frames[i]) == wframe
+            got = pts[off[i]:off[i + 1]].astype(np.float64)
+            if wok:
+                np.testing.assert_array_equal(got[:, [0, 1, 2, 4]], rows[:, [0, 1, 2, 4]])
+                np.testing.assert_array_equal(got[:, 3] * res, rows[:, 3])
+                world, _ = bt.preprocess(pts[off[i]:off[i + 1]])   # ... and on the device
+                np.testing.assert_array_equal(world[:, 6], rows[:, 3])
+            else:
+                assert len(got) == 0
+        bt.close()
 
 
 def test_oracle_round_trip_of_synthetic_frames():
