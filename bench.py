@@ -360,6 +360,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner with
+    # printf whatever NCCL_DEBUG_FILE says): from here on file descriptor 1 IS stderr, and the JSON line goes to the
+    # saved original at the end.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _print = print
+
+    def emit(*a, **k):
+        _print(*a, file=real_stdout, **k)
+        real_stdout.flush()
+
+    globals()["print"] = emit
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
@@ -532,6 +545,15 @@ def main():
         assert torch.equal(gathered[rank * res_dev.numel():(rank + 1) * res_dev.numel()], res_dev)
         identity = (replay_check(world, S, n_frames, weights, gathered, bt.tcap * _lib.RESULT_FLOATS, local,
                                  [True] * n_frames) if rank == 0 else None)
+        # the same gather through the C ABI (mmw_gather_nccl: one ncclAllGather on the library's stream)
+        ng = sharding.NcclGather(bt)
+        via_abi = ng.gather()
+        bt.sync()
+        same = bool(torch.equal(via_abi, gathered))
+        ng.close()
+        if identity is not None:
+            identity["mmw_gather_nccl_equals_torch_all_gather"] = same
+        assert same, "mmw_gather_nccl and torch.distributed all_gather disagree"
 
     if rank == 0:
         pk = peaks()

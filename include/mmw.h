@@ -284,6 +284,21 @@ int mmw_export_track0(mmw_ctx* ctx, double* rows, int32_t* valid, double* centro
 #define MMW_RESULT_FLOATS 72
 int mmw_pack_results(mmw_ctx* ctx, float* device_out);
 
+/* The one collective of the path: scenes are sharded over the GPUs of a box with no traffic in
+ * the hot loop; the packed result records of all ranks are gathered with ONE ncclAllGather over NVLink/NVSwitch.
+ *   nccl_comm      : an ncclComm_t whose ranks each own one context of the same n_scenes / max_tracks
+ *   device_out_all : DEVICE buffer of nranks * S * max_tracks * MMW_RESULT_FLOATS fp32; rank r's records land in block
+ *                    r.  This rank's records are packed straight into its own block (no staging copy) and the
+ *                    all-gather runs in place on the context's stream; asynchronous.
+ * libnccl.so.2 is bound at run time (dlopen: the copy the process already loaded, e.g. PyTorch's); the call fails
+ * with MMW_ERR_STATE when there is none.  mmw_nccl_* are conveniences for a host without an NCCL binding of its own:
+ * rank 0 calls mmw_nccl_unique_id (128 bytes), ships the bytes to the others by any means, every rank calls
+ * mmw_nccl_comm_init. */
+int mmw_gather_nccl(mmw_ctx* ctx, void* nccl_comm, int nranks, float* device_out_all);
+int mmw_nccl_unique_id(void* id128);
+int mmw_nccl_comm_init(mmw_ctx* ctx, const void* id128, int nranks, int rank, void** nccl_comm_out);
+int mmw_nccl_comm_destroy(void* nccl_comm);
+
 /* Pipelined result read-back for the hot loop: packs the results of the frames queued so far (same layout as
  * mmw_pack_results) and downloads them into host_out (pinned memory recommended; S * max_tracks *
  * MMW_RESULT_FLOATS fp32) on a side stream, without blocking the host.  *slot receives the id (0/1) to pass to

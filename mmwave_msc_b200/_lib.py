@@ -104,6 +104,10 @@ SIGNATURES = {
     "mmw_decode_tlv": (C.c_int, [_p, _p, _p, C.c_int, C.c_double, C.c_double, _p, C.c_size_t, _p, _p, _p]),
     "mmw_export_track0": (C.c_int, [_p, _p, _p, _p]),
     "mmw_pack_results": (C.c_int, [_p, _p]),
+    "mmw_gather_nccl": (C.c_int, [_p, _p, C.c_int, _p]),
+    "mmw_nccl_unique_id": (C.c_int, [_p]),
+    "mmw_nccl_comm_init": (C.c_int, [_p, _p, C.c_int, C.c_int, C.POINTER(_p)]),
+    "mmw_nccl_comm_destroy": (C.c_int, [_p]),
     "mmw_read_results_async": (C.c_int, [_p, _p, C.POINTER(C.c_int)]),
     "mmw_wait_results": (C.c_int, [_p, C.c_int]),
     "mmw_get_counters": (C.c_int, [_p, _p, C.c_int]),

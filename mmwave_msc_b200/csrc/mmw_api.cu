@@ -1,6 +1,7 @@
 // C ABI of libmmw.so (include/mmw.h): context management, the per-frame step, readback, and the
 // stage-level entry points.  No torch types, no exceptions across the boundary, no CPU fallback.
 #include <climits>
+#include <dlfcn.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1098,6 +1099,94 @@ int mmw_pack_results(mmw_ctx* x, float* device_out) {
                   (const SceneRec*)x->d_scenes, (const TrackRec*)x->d_tracks, (const float*)x->d_keypoints, x->S, x->tcap,
                   device_out, fc));
     x->launches++;
+    return MMW_OK;
+}
+
+// ---- NCCL, bound at run time ---------------------------------------------------------------------------------
+namespace {
+struct NcclId128 { char b[128]; };          // ncclUniqueId (passed by value to ncclCommInitRank)
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*CommUserRank)(void*, int*) = nullptr;
+    int (*CommCount)(void*, int*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int /* ncclDataType_t */, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // the copy this process already uses
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+        if (h) {
+            api.lib = h;
+            *(void**)&api.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+            *(void**)&api.CommInitRank = dlsym(h, "ncclCommInitRank");
+            *(void**)&api.CommDestroy = dlsym(h, "ncclCommDestroy");
+            *(void**)&api.CommUserRank = dlsym(h, "ncclCommUserRank");
+            *(void**)&api.CommCount = dlsym(h, "ncclCommCount");
+            *(void**)&api.AllGather = dlsym(h, "ncclAllGather");
+            *(void**)&api.GetErrorString = dlsym(h, "ncclGetErrorString");
+            if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.CommUserRank || !api.CommCount ||
+                !api.AllGather)
+                api.lib = nullptr;
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+int nccl_fail(NcclApi* a, const char* what, int rc) {
+    return fail(MMW_ERR_CUDA, std::string(what) + ": " + (a->GetErrorString ? a->GetErrorString(rc) : "NCCL error"));
+}
+}  // namespace
+
+int mmw_nccl_unique_id(void* id128) {
+    if (!id128) return fail(MMW_ERR_INVALID, "id128 is NULL");
+    NcclApi* a = nccl_api();
+    if (!a) return fail(MMW_ERR_STATE, "libnccl.so.2 is not available in this process");
+    const int rc = a->GetUniqueId(id128);
+    return rc == 0 ? MMW_OK : nccl_fail(a, "ncclGetUniqueId", rc);
+}
+
+int mmw_nccl_comm_init(mmw_ctx* x, const void* id128, int nranks, int rank, void** comm_out) {
+    if (!x || !id128 || !comm_out) return fail(MMW_ERR_INVALID, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(MMW_ERR_INVALID, "bad nranks/rank");
+    NcclApi* a = nccl_api();
+    if (!a) return fail(MMW_ERR_STATE, "libnccl.so.2 is not available in this process");
+    CK(cudaSetDevice(x->device));
+    NcclId128 id;
+    std::memcpy(id.b, id128, sizeof(id.b));
+    void* comm = nullptr;
+    const int rc = a->CommInitRank(&comm, nranks, id, rank);
+    if (rc != 0) return nccl_fail(a, "ncclCommInitRank", rc);
+    *comm_out = comm;
+    return MMW_OK;
+}
+
+int mmw_nccl_comm_destroy(void* comm) {
+    if (!comm) return MMW_OK;
+    NcclApi* a = nccl_api();
+    if (!a) return fail(MMW_ERR_STATE, "libnccl.so.2 is not available in this process");
+    const int rc = a->CommDestroy(comm);
+    return rc == 0 ? MMW_OK : nccl_fail(a, "ncclCommDestroy", rc);
+}
+
+int mmw_gather_nccl(mmw_ctx* x, void* comm, int nranks, float* device_out_all) {
+    if (!x || !comm || !device_out_all) return fail(MMW_ERR_INVALID, "NULL argument");
+    NcclApi* a = nccl_api();
+    if (!a) return fail(MMW_ERR_STATE, "libnccl.so.2 is not available in this process");
+    int rank = -1, count = 0, rc;
+    if ((rc = a->CommUserRank(comm, &rank)) != 0) return nccl_fail(a, "ncclCommUserRank", rc);
+    if ((rc = a->CommCount(comm, &count)) != 0) return nccl_fail(a, "ncclCommCount", rc);
+    if (count != nranks) return fail(MMW_ERR_INVALID, "nranks does not match the communicator");
+    const size_t per_rank = (size_t)x->S * x->tcap * MMW_RESULT_FLOATS;
+    int prc = mmw_pack_results(x, device_out_all + per_rank * rank);      // straight into this rank's block
+    if (prc != MMW_OK) return prc;
+    rc = a->AllGather(device_out_all + per_rank * rank, device_out_all, per_rank, /* ncclFloat32 */ 7, comm, x->stream);
+    if (rc != 0) return nccl_fail(a, "ncclAllGather", rc);
     return MMW_OK;
 }
 
