@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, golden_cases
-from helpers import KEYPOINT_ATOL, compare_frame, oracle_config
+from helpers import KEYPOINT_ATOL, STATE_ATOL, STATE_RTOL, compare_frame, oracle_config
 from mmwave_msc_b200 import _lib, pose_weights as pw, synth
 from mmwave_msc_b200.batched import BatchedTracker, default_config
 from oracle import mmw_oracle as mo, trace_io
@@ -315,6 +315,78 @@ def test_full_size_c2_permutation_and_determinism():
 
 
 # ---- pipelined host path: side-stream upload + asynchronous packed-result download -----------------
+def _tiled(batches, reps):
+    """reps copies of the generated scenes side by side: scene s + k * S is scene s again."""
+    out = []
+    for b in batches:
+        n = b.points.shape[0]
+        off = np.concatenate([b.offsets[:-1] + k * n for k in range(reps)] + [np.array([reps * n], np.int32)])
+        out.append((np.tile(b.points, (reps, 1)), off.astype(np.int32), np.tile(b.dt, reps)))
+    return out
+
+
+def _spot_check_against_oracle(bt, tiled, gen_batches, S_gen, pick, ocfg, W, every=4):
+    """Scenes `pick` of the big batch (each a copy of generated scene pick % S_gen) against the oracle, every few
+    frames: track count, ids, association of every point, Kalman state; keypoints at the end."""
+    oracles = {s: mo.SceneOracle(ocfg, pose_weights=W) for s in pick}
+    F = len(tiled)
+    for f, (pts, off, dt) in enumerate(tiled):
+        bt.step(pts, off, dt, pose=W is not None)
+        b = gen_batches[f]
+        recs = {s: oracles[s].step(b.points[b.offsets[s % S_gen]:b.offsets[s % S_gen + 1]], b.dt[s % S_gen]) for s in pick}
+        if f % every and f != F - 1:
+            continue
+        tr, nt = bt.tracks()
+        assoc = bt.point_assoc()
+        for s in pick:
+            r = recs[s]
+            ctx = "frame %d scene %d" % (f, s)
+            assert nt[s] == len(r["tracks"]), ctx
+            np.testing.assert_array_equal(assoc[off[s]:off[s] + r["M"]], r["assoc"], err_msg=ctx)
+            for k, t in enumerate(r["tracks"]):
+                assert tr[s, k]["id"] == t["id"] and tr[s, k]["point_num"] == t["point_num"], ctx
+                np.testing.assert_allclose(tr[s, k]["x"], t["x"], rtol=STATE_RTOL, atol=STATE_ATOL, err_msg=ctx)
+                np.testing.assert_allclose(tr[s, k]["P"], t["P"], rtol=STATE_RTOL, atol=STATE_ATOL, err_msg=ctx)
+                if W is not None and f == F - 1:
+                    np.testing.assert_allclose(tr[s, k]["keypoints"], t["keypoints"], rtol=0, atol=KEYPOINT_ATOL,
+                                               err_msg=ctx)
+    return nt
+
+
+def test_full_size_c5_8192_scenes_on_one_gpu_oracle_spot_checks():
+    """BASELINE config C5 on one GPU: 8192 scenes in one context (the pose-row scan takes its separate kernel above
+    4096 scenes), 36 scenes spread over the batch against the oracle for 20 frames, and the eight copies of every
+    generated scene agree bit for bit."""
+    S_gen, reps, F = 1024, 8, 20
+    gen = synth.gen_batch(list(range(3000, 3000 + S_gen)), F)
+    tiled = _tiled(gen, reps)
+    W = pw.make_pose_weights(pw.VARIANT_3D)
+    bt = BatchedTracker(S_gen * reps)
+    bt.load_pose_weights(W)
+    pick = sorted(set(int(x) for x in np.random.default_rng(5).integers(0, S_gen * reps, 34)) | {0, 8191})
+    nt = _spot_check_against_oracle(bt, tiled, gen, S_gen, pick, mo.OracleConfig(), W)
+    assert not bt.status().any() and nt.sum() > S_gen * reps
+    tr, nt = bt.tracks()
+    tr = tr.reshape(reps, S_gen, -1)
+    for k in range(1, reps):
+        assert tr[0].tobytes() == tr[k].tobytes()
+    bt.close()
+
+
+def test_full_size_c3_dense_1024_scenes_oracle_spot_checks():
+    """BASELINE config C3 at 1024 scenes: 1000 points per frame, 10 targets, TR_MAX_TRACKS = 10 (fused clouds of up to
+    3000 points: the large-cloud DBSCAN path), 12 scenes against the oracle for 10 frames."""
+    S_gen, reps, F = 256, 4, 10
+    gen = synth.gen_batch(list(range(5000, 5000 + S_gen)), F, synth.SceneSpec.dense())
+    tiled = _tiled(gen, reps)
+    cfg = default_config(tr_max_tracks=10)
+    bt = BatchedTracker(S_gen * reps, max_points=1024, max_tracks=16, config=cfg)
+    pick = sorted(set(int(x) for x in np.random.default_rng(7).integers(0, S_gen * reps, 10)) | {0, 1023})
+    nt = _spot_check_against_oracle(bt, tiled, gen, S_gen, pick, oracle_config(cfg), None, every=3)
+    assert not bt.status().any() and nt.mean() > 3
+    bt.close()
+
+
 def test_pipelined_results_match_blocking_readback():
     import torch
     S, F = 64, 10
