@@ -91,6 +91,11 @@ typedef struct mmw_ctx mmw_ctx;
 #define MMW_STEP_POSE          0x1u   /* run estimate_posture after track (offline_main.py:60) */
 #define MMW_STEP_DEVICE_INPUT  0x2u   /* pts/offsets/dt are device pointers (already resident in HBM) */
 #define MMW_STEP_RECORD_LABELS 0x4u   /* keep the DBSCAN labels of this frame for mmw_get_labels */
+#define MMW_STEP_PIPELINE      0x8u   /* throughput mode (with MMW_STEP_POSE): the pose network of this frame runs on a
+                                         second stream and overlaps the tracker of the NEXT frame -- keypoints never feed
+                                         back into tracking (Tracking.py:705-734).  The frame's packed result records
+                                         are produced as part of the step; fetch them with mmw_read_results_async right
+                                         after the call.  Results are bit-identical to the serial mode. */
 
 /* per-scene status bits (mmw_get_status) */
 #define MMW_SCENE_POINT_OVERFLOW 0x1u /* a frame had more points than max_points_per_frame (extra points dropped) */

@@ -111,8 +111,10 @@ class BatchedTracker:
 
     # -- the hot path -----------------------------------------------------------------------------
     def step(self, points: np.ndarray, offsets: np.ndarray, dt: np.ndarray, pose: bool = True,
-             record_labels: bool = False):
-        """Host inputs: points (sum N, 5) float32, offsets (S+1,) int32, dt (S,) float64."""
+             record_labels: bool = False, pipeline: bool = False):
+        """Host inputs: points (sum N, 5) float32, offsets (S+1,) int32, dt (S,) float64.
+        ``pipeline`` (throughput mode, MMW_STEP_PIPELINE): this frame's pose network overlaps the next frame's tracker;
+        fetch the frame's results with read_results_async() right after the call."""
         points = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 5)
         offsets = np.ascontiguousarray(offsets, dtype=np.int32)
         dt = np.ascontiguousarray(dt, dtype=np.float64)
@@ -120,13 +122,15 @@ class BatchedTracker:
             raise ValueError("offsets must have S+1 entries and dt S entries")
         if int(offsets[-1]) != points.shape[0]:
             raise ValueError("offsets[-1] must equal the number of point rows")
-        flags = (_lib.STEP_POSE if pose else 0) | (_lib.STEP_RECORD_LABELS if record_labels else 0)
+        flags = ((_lib.STEP_POSE if pose else 0) | (_lib.STEP_RECORD_LABELS if record_labels else 0) |
+                 (_lib.STEP_PIPELINE if pipeline else 0))
         self._n_last = points.shape[0]
         _lib.check(self.lib.mmw_step(self._h, _lib.ptr(points), _lib.ptr(offsets), _lib.ptr(dt), flags))
 
-    def step_device(self, points_ptr: int, offsets_ptr: int, dt_ptr: int, n_points: int, pose: bool = True):
+    def step_device(self, points_ptr: int, offsets_ptr: int, dt_ptr: int, n_points: int, pose: bool = True,
+                    pipeline: bool = False):
         """Inputs already resident in HBM (device pointers, same layouts as ``step``)."""
-        flags = _lib.STEP_DEVICE_INPUT | (_lib.STEP_POSE if pose else 0)
+        flags = _lib.STEP_DEVICE_INPUT | (_lib.STEP_POSE if pose else 0) | (_lib.STEP_PIPELINE if pipeline else 0)
         self._n_last = int(n_points)
         _lib.check(self.lib.mmw_step(self._h, C.c_void_p(points_ptr), C.c_void_p(offsets_ptr), C.c_void_p(dt_ptr),
                                      flags))

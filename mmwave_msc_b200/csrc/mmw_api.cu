@@ -60,6 +60,14 @@ struct mmw_ctx {
     int32_t* d_offsets2[2] = {nullptr, nullptr};
     double* d_dt2[2] = {nullptr, nullptr};
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    // throughput mode (MMW_STEP_PIPELINE): pose network on its own stream, its inputs double-buffered
+    cudaStream_t pose_stream = nullptr;
+    cudaEvent_t feat_done[2] = {nullptr, nullptr}, packt_done[2] = {nullptr, nullptr}, pose_done[2] = {nullptr, nullptr};
+    int32_t *d_row_scene2 = nullptr, *d_row_track2 = nullptr, *d_row_slot2 = nullptr;
+    int* d_pose_total2 = nullptr;
+    unsigned pipe_idx = 0;           // pipelined steps so far
+    int pipe_r = -1;                 // result buffer the last step filled itself (-1: the last step was serial)
+    bool pose_pending = false;       // the pose stream has work the main stream has not waited for
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
     int stage_pending = -1;              // staging buffer whose stage_free event is still to be recorded
     cudaEvent_t packed[2] = {nullptr, nullptr}, results_done[2] = {nullptr, nullptr};
@@ -90,6 +98,22 @@ struct mmw_ctx {
     double kernel_ms[MMW_N_KERNELS] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t kernel_calls[MMW_N_KERNELS] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+// Everything queued so far on both compute streams has completed (the pose stream only runs in throughput mode).
+static cudaError_t sync_main(mmw_ctx* x) {
+    if (x->pose_pending) {
+        cudaError_t e = cudaStreamSynchronize(x->pose_stream);
+        if (e != cudaSuccess) return e;
+        x->pose_pending = false;
+    }
+    return cudaStreamSynchronize(x->stream);
+}
+// Serial-mode work is about to be queued on the main stream: it must come after whatever the pose stream still runs.
+static cudaError_t join_pose(mmw_ctx* x) {
+    if (!x->pose_pending) return cudaSuccess;
+    x->pose_pending = false;
+    return cudaStreamWaitEvent(x->stream, x->pose_done[(x->pipe_idx + 1) & 1], 0);     // the last pipelined step's
+}
 
 static void prof_mark(mmw_ctx* x, int next_kernel) {
     if (!x->profiling) return;
@@ -176,15 +200,18 @@ int mmw_destroy(mmw_ctx* x) {
                     x->d_assoc, x->d_labels, x->d_counters, x->d_phase, x->d_defer, x->d_scene_stats, x->d_ring_hist, x->d_pts2[0], x->d_pts2[1], x->d_offsets2[0],
                     x->d_offsets2[1], x->d_dt2[0], x->d_dt2[1], x->d_results[0], x->d_results[1], x->d_blob, x->d_bn1s,
                     x->d_bn1t, x->d_bn2s, x->d_bn2t, x->d_feats, x->d_row_scene, x->d_row_track, x->d_row_slot,
-                    x->d_pose_total, x->d_act2, x->d_act3, x->d_pose_out};
+                    x->d_pose_total, x->d_act2, x->d_act3, x->d_pose_out, x->d_row_scene2, x->d_row_track2, x->d_row_slot2,
+                    x->d_pose_total2};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     pose_tc_free(&x->tc);
     for (int i = 0; i < 2; ++i)
-        for (cudaEvent_t e : {x->h2d_done[i], x->stage_free[i], x->packed[i], x->results_done[i]})
+        for (cudaEvent_t e : {x->h2d_done[i], x->stage_free[i], x->packed[i], x->results_done[i], x->feat_done[i],
+                              x->packt_done[i], x->pose_done[i]})
             if (e) cudaEventDestroy(e);
     if (x->h2d_stream) cudaStreamDestroy(x->h2d_stream);
     if (x->d2h_stream) cudaStreamDestroy(x->d2h_stream);
+    if (x->pose_stream) { cudaStreamSynchronize(x->pose_stream); cudaStreamDestroy(x->pose_stream); }
     if (x->stream) cudaStreamDestroy(x->stream);
     delete x;
     return MMW_OK;
@@ -193,11 +220,14 @@ int mmw_destroy(mmw_ctx* x) {
 int mmw_reset(mmw_ctx* x) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(x->device));
+    if (x->pose_stream) CK(join_pose(x));
+    x->pipe_r = -1;
     CK(cudaMemsetAsync(x->d_scenes, 0, sizeof(SceneRec) * x->S, x->stream));
     CK(cudaMemsetAsync(x->d_tracks, 0, sizeof(TrackRec) * (size_t)x->S * x->tcap, x->stream));
     CK(cudaMemsetAsync(x->d_counters, 0, sizeof(unsigned long long) * 8, x->stream));
     CK(cudaMemsetAsync(x->d_assoc, 0xff, sizeof(int32_t) * (size_t)x->S * x->ncap, x->stream));
     CK(cudaMemsetAsync(x->d_pose_total, 0, sizeof(int), x->stream));
+    CK(cudaMemsetAsync(x->d_pose_total2, 0, sizeof(int), x->stream));
     CK(cudaMemsetAsync(x->d_defer, 0, sizeof(int32_t) * (2 + 2 * (size_t)x->S), x->stream));
     CK(cudaMemsetAsync(x->d_scene_stats, 0, sizeof(int32_t) * 8 * (size_t)x->S, x->stream));
     CK(cudaMemsetAsync(x->d_ring_hist, 0, (size_t)kRing * kHistBytes * x->S, x->stream));
@@ -237,7 +267,7 @@ int mmw_state_dump(mmw_ctx* x, void* host_blob, size_t bytes) {
     const size_t need = mmw_state_size(x);
     if (bytes < need) return fail(MMW_ERR_CAPACITY, "state blob buffer is smaller than mmw_state_size()");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     StateHeader h{kStateMagic, MMW_ABI_VERSION, x->S, x->ncap, x->tcap, x->dc.ring_size, (uint64_t)need};
     unsigned char* o = static_cast<unsigned char*>(host_blob);
     std::memcpy(o, &h, sizeof(h));
@@ -330,12 +360,16 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
         if (cudaEventCreateWithFlags(&x->h2d_done[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&x->stage_free[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&x->packed[i], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&x->results_done[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&x->results_done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x->feat_done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x->packt_done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x->pose_done[i], cudaEventDisableTiming) != cudaSuccess) {
             mmw_destroy(x);
             return fail(MMW_ERR_CUDA, "cudaEventCreate failed");
         }
     }
     if (cudaStreamCreateWithFlags(&x->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&x->pose_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&x->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
         mmw_destroy(x);
         return fail(MMW_ERR_CUDA, "cudaStreamCreate failed");
@@ -345,6 +379,10 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     ALLOC(x->d_row_scene, sizeof(int32_t) * x->pose_cap);
     ALLOC(x->d_row_track, sizeof(int32_t) * x->pose_cap);
     ALLOC(x->d_row_slot, sizeof(int32_t) * x->pose_cap);
+    ALLOC(x->d_row_scene2, sizeof(int32_t) * x->pose_cap);
+    ALLOC(x->d_row_track2, sizeof(int32_t) * x->pose_cap);
+    ALLOC(x->d_row_slot2, sizeof(int32_t) * x->pose_cap);
+    ALLOC(x->d_pose_total2, sizeof(int));
     ALLOC(x->d_feats, sizeof(float) * (size_t)x->pose_cap * kRing * kFeatPts * kRawCols);
     ALLOC(x->d_pose_out, sizeof(float) * (size_t)x->pose_cap * kKp);
 #undef ALLOC
@@ -352,7 +390,7 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     cudaMemset(x->d_keypoints, 0, sizeof(float) * S * max_tracks * kKp);
     int rc = mmw_reset(x);
     if (rc != MMW_OK) { mmw_destroy(x); return rc; }
-    cudaStreamSynchronize(x->stream);
+    sync_main(x);
     *out = x;
     return MMW_OK;
 }
@@ -369,7 +407,7 @@ int mmw_sync(mmw_ctx* x) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(x->device));
     CK(cudaStreamSynchronize(x->h2d_stream));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     CK(cudaStreamSynchronize(x->d2h_stream));
     return MMW_OK;
 }
@@ -395,7 +433,7 @@ int mmw_load_pose_weights(mmw_ctx* x, int variant, const float* blob, size_t n) 
     for (int i = 0; i < 16; ++i) off[i + 1] = off[i] + sz[i];
     if (n != off[16]) return fail(MMW_ERR_INVALID, "weight blob has the wrong number of floats for this variant");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     x->has_weights = false;              // a failed reload must not leave the old pointers in use
     if (x->d_blob) { cudaFree(x->d_blob); x->d_blob = nullptr; }
     for (float** p : {&x->d_bn1s, &x->d_bn1t, &x->d_bn2s, &x->d_bn2t, &x->d_act2, &x->d_act3})
@@ -474,6 +512,15 @@ static int run_pose_net(mmw_ctx* x, float* keypoints_by_slot, int max_rows) {
     return MMW_OK;
 }
 
+// Throughput mode, the part of a step after the tracker (MMW_STEP_PIPELINE).  Frame k, buffers b = k & 1:
+//   main stream : [step k][dbscan_big k] (queued by the caller)  wait pose(k-2)  [features k -> inputs b]  ev feat[b]
+//                 wait pose(k-1)  [pack_tracks k -> results b]  ev packt[b]                    ... then frame k+1
+//   pose stream : wait feat[b]  [conv1][conv2][dense 1]  wait packt[b]  [dense 2 -> keypoints, results b]  ev pose[b]
+// so the tracker of frame k+1 runs under the convolutions / dense 1 of frame k.  The pose stream is serial, hence
+// "pose(k-1) done" implies every earlier frame's pose work is done (its activations are single-buffered).
+static int pipeline_pose(mmw_ctx* x);
+static int launch_pack_tracks(mmw_ctx* x, float* results);
+
 int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double* dt, uint32_t flags) {
     if (!x || !offsets || !dt) return fail(MMW_ERR_INVALID, "ctx/offsets/dt is NULL");
     if ((flags & MMW_STEP_POSE) && !x->has_weights)
@@ -526,6 +573,15 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     a.pose_cnt = x->d_defer + 1 + x->S;
     a.scene_stats = x->d_scene_stats;
     a.ring_hist = x->d_ring_hist;
+    const bool pipelined = (flags & MMW_STEP_PIPELINE) != 0;
+    if (pipelined) {
+        if (!(flags & MMW_STEP_POSE) || !(x->use_tc && x->tc.ready))
+            return fail(MMW_ERR_STATE, "MMW_STEP_PIPELINE needs MMW_STEP_POSE and the tensor-core pose path");
+        if (flags & MMW_STEP_RECORD_LABELS) return fail(MMW_ERR_INVALID, "MMW_STEP_PIPELINE cannot record labels");
+    } else {
+        CK(join_pose(x));
+        x->pipe_r = -1;
+    }
     prof_mark(x, MMW_K_STEP);
     CK(launch_step(a, x->stream));
     prof_mark(x, MMW_K_DBSCAN_BIG);
@@ -533,7 +589,8 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     x->launches += 2;          // step_kernel + dbscan_big_kernel
     prof_mark(x, -1);
     int rc = MMW_OK;
-    if (flags & MMW_STEP_POSE) rc = mmw_estimate_posture(x);
+    if (pipelined) rc = pipeline_pose(x);
+    else if (flags & MMW_STEP_POSE) rc = mmw_estimate_posture(x);
     if (host_stage >= 0) x->stage_pending = host_stage;      // recorded at the head of the next step (see above)
     return rc;
 }
@@ -542,6 +599,7 @@ int mmw_estimate_posture(mmw_ctx* x) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     if (!x->has_weights) return fail(MMW_ERR_STATE, "estimate_posture needs mmw_load_pose_weights first");
     CK(cudaSetDevice(x->device));
+    CK(join_pose(x));
     if (!x->fold_pose_index) {
         prof_mark(x, MMW_K_POSE_INDEX);
         CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
@@ -560,6 +618,7 @@ int mmw_estimate_posture(mmw_ctx* x) {
 int mmw_pose_features_only(mmw_ctx* x) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(x->device));
+    CK(join_pose(x));
     if (!x->fold_pose_index) {
         CK(launch_pose_index(x->d_scenes, x->S, x->d_pose_total, x->d_counters, x->stream));
         x->launches++;
@@ -577,7 +636,7 @@ int mmw_set_keypoints(mmw_ctx* x, int scene, int track_index, const float* kp57)
     if (scene < 0 || scene >= x->S || track_index < 0 || track_index >= x->tcap)
         return fail(MMW_ERR_INVALID, "scene/track out of range");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     TrackRec t;
     CK(cudaMemcpy(&t, x->d_tracks + (size_t)scene * x->tcap + track_index, sizeof(t), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(x->d_keypoints + ((size_t)scene * x->tcap + t.slot) * kKp, kp57, sizeof(float) * kKp,
@@ -589,7 +648,7 @@ int mmw_set_keypoints(mmw_ctx* x, int scene, int track_index, const float* kp57)
 int mmw_get_tracks(mmw_ctx* x, mmw_track_out* tracks, int32_t* n_tracks) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     std::vector<SceneRec> sc(x->S);
     CK(cudaMemcpy(sc.data(), x->d_scenes, sizeof(SceneRec) * x->S, cudaMemcpyDeviceToHost));
     if (n_tracks)
@@ -625,7 +684,7 @@ int mmw_get_scene_summary(mmw_ctx* x, int32_t* n_tracks, int32_t* next_id, int32
     CK(cudaSetDevice(x->device));
     std::vector<SceneRec> sc(x->S);
     CK(cudaMemcpyAsync(sc.data(), x->d_scenes, sizeof(SceneRec) * x->S, cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     for (int s = 0; s < x->S; ++s) {
         if (n_tracks) n_tracks[s] = sc[s].n_tracks;
         if (next_id) next_id[s] = sc[s].next_id;
@@ -639,14 +698,14 @@ int mmw_get_point_assoc(mmw_ctx* x, int32_t* assoc, size_t n) {
     if (n > (size_t)x->S * x->ncap) return fail(MMW_ERR_CAPACITY, "n exceeds n_scenes * max_points_per_frame");
     CK(cudaSetDevice(x->device));
     CK(cudaMemcpyAsync(assoc, x->d_assoc, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     return MMW_OK;
 }
 
 int mmw_get_labels(mmw_ctx* x, int32_t* labels, int32_t* n_fused) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     if (labels)
         CK(cudaMemcpy(labels, x->d_labels, sizeof(int32_t) * (size_t)x->S * 3 * x->ncap, cudaMemcpyDeviceToHost));
     if (n_fused) {
@@ -660,7 +719,7 @@ int mmw_get_labels(mmw_ctx* x, int32_t* labels, int32_t* n_fused) {
 int mmw_get_status(mmw_ctx* x, uint32_t* flags) {
     if (!x || !flags) return fail(MMW_ERR_INVALID, "ctx/flags is NULL");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     std::vector<SceneRec> sc(x->S);
     CK(cudaMemcpy(sc.data(), x->d_scenes, sizeof(SceneRec) * x->S, cudaMemcpyDeviceToHost));
     for (int s = 0; s < x->S; ++s) flags[s] = sc[s].flags;
@@ -670,7 +729,7 @@ int mmw_get_status(mmw_ctx* x, uint32_t* flags) {
 int mmw_get_ring_counts(mmw_ctx* x, int32_t* counts) {
     if (!x || !counts) return fail(MMW_ERR_INVALID, "ctx/counts is NULL");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     std::vector<SceneRec> sc(x->S);
     CK(cudaMemcpy(sc.data(), x->d_scenes, sizeof(SceneRec) * x->S, cudaMemcpyDeviceToHost));
     for (int s = 0; s < x->S; ++s)
@@ -684,7 +743,7 @@ static int ring_edit(mmw_ctx* x, int scene, bool clear) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     if (scene < 0 || scene >= x->S) return fail(MMW_ERR_INVALID, "scene out of range");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     SceneRec sc;
     CK(cudaMemcpy(&sc, x->d_scenes + scene, sizeof(sc), cudaMemcpyDeviceToHost));
     if (clear) {
@@ -707,7 +766,7 @@ int mmw_get_pose_rows(mmw_ctx* x, int32_t* n_rows, int32_t* scene_idx, int32_t* 
                       size_t cap_floats) {
     if (!x || !n_rows) return fail(MMW_ERR_INVALID, "ctx/n_rows is NULL");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     int n = 0;
     CK(cudaMemcpy(&n, x->d_pose_total, sizeof(int), cudaMemcpyDeviceToHost));
     *n_rows = n;
@@ -724,7 +783,7 @@ int mmw_get_pose_rows(mmw_ctx* x, int32_t* n_rows, int32_t* scene_idx, int32_t* 
 int mmw_get_counters(mmw_ctx* x, uint64_t out[8], int reset) {
     if (!x || !out) return fail(MMW_ERR_INVALID, "ctx/out is NULL");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     unsigned long long h[8];
     CK(cudaMemcpy(h, x->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 8; ++i) out[i] = h[i];
@@ -862,17 +921,6 @@ __global__ void __launch_bounds__(128) gate_stage_kernel(const double* pts, int 
     }
 }
 
-struct FadeCfg { double m_x, m_y, m_z, smax, smin, weight; };
-
-// calc_projection_points (Utils.py:180-219): where the line from the point to the sensitive object (M_X, M_Y, M_Z)
-// crosses the window plane y = 0.
-__device__ __forceinline__ void projection_point(const FadeCfg& f, double xo, double yo, double zo, double& xp,
-                                                 double& zp) {
-    const double xd = xo - f.m_x, yd = yo - f.m_y, zd = zo - f.m_z;
-    xp = (xd == 0.0) ? xo : (-f.m_y / (yd / xd)) + f.m_x;
-    zp = (zd == 0.0) ? zo : (-f.m_y / (yd / zd)) + f.m_z;
-}
-
 // ---- UART TLV packets -> fp32 point rows (ReadDataIWR1443.py:88-201) ------------------------------------
 constexpr int kTlvHeader = 36;
 __device__ __forceinline__ uint32_t rd_u32(const uint8_t* p) {
@@ -1005,9 +1053,102 @@ __global__ void __launch_bounds__(256) pack_results_kernel(const SceneRec* scene
     }
 }
 
+// Throughput mode: the tracker's half of the packed result records of a frame -- id, track count, state x, the
+// keypoints the track has NOW (the pose network's dense 2 overwrites them for every track that gets a pose row this
+// frame), and x[0], x[1] as two float64 in fields 68..71 for dense 2's fade square.  Records of tracks without a pose
+// row this frame (scenes whose frame was skipped) are finished here.
+__global__ void __launch_bounds__(256) pack_tracks_kernel(const SceneRec* scenes, const TrackRec* tracks,
+                                                          const float* keypoints, int tcap, float* out, FadeCfg fade) {
+    const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nt = scenes[s].n_tracks;
+    const bool ran = scenes[s].last_ran != 0;
+    for (int k = warp; k < tcap; k += nw) {
+        float* o = out + ((size_t)s * tcap + k) * MMW_RESULT_FLOATS;
+        if (k >= nt) {
+            for (int e = lane; e < MMW_RESULT_FLOATS; e += 32) o[e] = e == 0 ? -1.f : (e == 1 ? (float)nt : 0.f);
+            continue;
+        }
+        const TrackRec* t = tracks + (size_t)s * tcap + k;
+        const float* kp = keypoints + ((size_t)s * tcap + t->slot) * kKp;
+        for (int e = lane; e < 68; e += 32) {
+            float v;
+            if (e == 0) v = (float)t->id;
+            else if (e == 1) v = (float)nt;
+            else if (e < 11) v = (float)t->x[e - 2];
+            else v = kp[e - 11];
+            o[e] = v;
+        }
+        if (lane == 0) {
+            if (ran) {
+                reinterpret_cast<double*>(o + 68)[0] = t->x[0];
+                reinterpret_cast<double*>(o + 68)[1] = t->x[1];
+            } else {
+                write_fade_square(fade, t->x[0], t->x[1], kp, o);
+            }
+        }
+    }
+}
+
 }  // namespace mmw
 
 extern "C" {
+
+static FadeCfg fade_cfg(const mmw_ctx* x) {
+    return FadeCfg{x->cfg.m_x, x->cfg.m_y, x->cfg.m_z, x->cfg.fade_size_max, x->cfg.fade_size_min, x->cfg.fade_weight};
+}
+
+static int launch_pack_tracks(mmw_ctx* x, float* results) {
+    pack_tracks_kernel<<<x->S, 256, 0, x->stream>>>(x->d_scenes, x->d_tracks, x->d_keypoints, x->tcap, results, fade_cfg(x));
+    CK(cudaGetLastError());
+    x->launches++;
+    return MMW_OK;
+}
+
+static int pipeline_pose(mmw_ctx* x) {
+    const int b = (int)(x->pipe_idx & 1u);
+    cudaStream_t T = x->stream, P = x->pose_stream;
+    int32_t *row_scene = b ? x->d_row_scene2 : x->d_row_scene, *row_track = b ? x->d_row_track2 : x->d_row_track,
+            *row_slot = b ? x->d_row_slot2 : x->d_row_slot;
+    int* pose_total = b ? x->d_pose_total2 : x->d_pose_total;
+    if (x->pipe_idx >= 2) CK(cudaStreamWaitEvent(T, x->pose_done[b], 0));              // frame k-2: inputs b are free
+    if (!x->fold_pose_index) {
+        CK(launch_pose_index(x->d_scenes, x->S, pose_total, x->d_counters, T));
+        x->launches++;
+    }
+    PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, pose_tc_input(&x->tc, b), row_scene,
+                    row_track, row_slot, x->fold_pose_index ? x->d_defer + 1 + x->S : nullptr, pose_total, x->d_counters,
+                    x->S};
+    CK(launch_pose_features(fa, x->S, T));
+    x->launches++;
+    CK(cudaEventRecord(x->feat_done[b], T));
+    // the result records of this frame: buffer b must have been downloaded (frame k-2), and the keypoints the tracker
+    // side copies are final once frame k-1's pose network is done
+    if (cudaEventQuery(x->results_done[b]) != cudaSuccess) {
+        (void)cudaGetLastError();
+        CK(cudaStreamWaitEvent(T, x->results_done[b], 0));
+    }
+    if (x->pipe_idx >= 1 && x->pose_pending) CK(cudaStreamWaitEvent(T, x->pose_done[b ^ 1], 0));
+    int rc = launch_pack_tracks(x, x->d_results[b]);
+    if (rc != MMW_OK) return rc;
+    CK(cudaEventRecord(x->packt_done[b], T));
+    // pose stream
+    CK(cudaStreamWaitEvent(P, x->feat_done[b], 0));
+    PoseTcRun r{pose_total, x->b1, x->b2, x->d_bn1s, x->d_bn1t, x->bd1, x->d_bn2s, x->d_bn2t, x->bd2, x->d_pose_out,
+                x->d_keypoints, row_scene, row_slot, x->tcap, x->d_results[b], row_track, fade_cfg(x)};
+    int nl = 0;
+    if (pose_tc_conv(&x->tc, r, P, &nl, b) != 0) return fail(MMW_ERR_CUDA, std::string("tensor-core conv: ") + pose_tc_error());
+    x->launches += nl;
+    if (pose_tc_fc1(&x->tc, r, x->pose_cap, P, &nl) != 0) return fail(MMW_ERR_CUDA, std::string("tensor-core dense 1: ") + pose_tc_error());
+    x->launches += nl;
+    CK(cudaStreamWaitEvent(P, x->packt_done[b], 0));
+    if (pose_tc_fc2(&x->tc, r, x->pose_cap, P, &nl) != 0) return fail(MMW_ERR_CUDA, std::string("tensor-core dense 2: ") + pose_tc_error());
+    x->launches += nl;
+    CK(cudaEventRecord(x->pose_done[b], P));
+    x->pose_pending = true;
+    x->pipe_r = b;
+    x->pipe_idx++;
+    return MMW_OK;
+}
 
 int mmw_decode_tlv(mmw_ctx* x, const uint8_t* packets, const int64_t* packet_offsets, int n, double num_doppler_bins,
                    double doppler_res, float* points, size_t max_points_total, int32_t* point_offsets,
@@ -1036,7 +1177,7 @@ int mmw_decode_tlv(mmw_ctx* x, const uint8_t* packets, const int64_t* packet_off
     std::vector<int32_t> cnt(n);
     TLV_CK(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, x->stream));
     TLV_CK(cudaMemcpyAsync(frame_numbers, d_fr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, x->stream));
-    TLV_CK(cudaStreamSynchronize(x->stream));
+    TLV_CK(sync_main(x));
     x->launches++;
     size_t total = 0;
     for (int i = 0; i < n; ++i) {
@@ -1056,7 +1197,7 @@ int mmw_decode_tlv(mmw_ctx* x, const uint8_t* packets, const int64_t* packet_off
         TLV_CK(cudaGetLastError());
         x->launches++;
         TLV_CK(cudaMemcpyAsync(points, d_pts, sizeof(float) * kRawCols * total, cudaMemcpyDeviceToHost, x->stream));
-        TLV_CK(cudaStreamSynchronize(x->stream));
+        TLV_CK(sync_main(x));
     }
 #undef TLV_CK
     cleanup();
@@ -1078,7 +1219,7 @@ int mmw_export_track0(mmw_ctx* x, double* rows, int32_t* valid, double* centroid
     std::vector<double> h(per * x->S);
     CK(cudaMemcpyAsync(valid, x->d_export_valid, sizeof(int32_t) * x->S, cudaMemcpyDeviceToHost, x->stream));
     CK(cudaMemcpyAsync(h.data(), x->d_export, sizeof(double) * per * x->S, cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     for (int s = 0; s < x->S; ++s) {                               // blocks of invalid scenes are undefined on the device
         double* r = rows + (size_t)s * kExportRows * kRawCols;
         if (valid[s]) std::memcpy(r, h.data() + per * s, sizeof(double) * kExportRows * kRawCols);
@@ -1094,6 +1235,7 @@ int mmw_export_track0(mmw_ctx* x, double* rows, int32_t* valid, double* centroid
 int mmw_pack_results(mmw_ctx* x, float* device_out) {
     if (!x || !device_out) return fail(MMW_ERR_INVALID, "ctx/device_out is NULL");
     CK(cudaSetDevice(x->device));
+    CK(join_pose(x));
     const FadeCfg fc{x->cfg.m_x, x->cfg.m_y, x->cfg.m_z, x->cfg.fade_size_max, x->cfg.fade_size_min, x->cfg.fade_weight};
     CK(launch_pdl(pack_results_kernel, dim3(x->S), dim3(256), 0, x->stream, dim3(1, 1, 1),
                   (const SceneRec*)x->d_scenes, (const TrackRec*)x->d_tracks, (const float*)x->d_keypoints, x->S, x->tcap,
@@ -1193,6 +1335,18 @@ int mmw_gather_nccl(mmw_ctx* x, void* comm, int nranks, float* device_out_all) {
 int mmw_read_results_async(mmw_ctx* x, float* host_out, int* slot) {
     if (!x || !host_out) return fail(MMW_ERR_INVALID, "ctx/host_out is NULL");
     CK(cudaSetDevice(x->device));
+    if (x->pipe_r >= 0) {
+        // throughput mode: the last step produced its own records in d_results[pipe_r]; they are complete when that
+        // frame's dense 2 is
+        const int r = x->pipe_r;
+        CK(cudaStreamWaitEvent(x->d2h_stream, x->pose_done[r], 0));
+        CK(cudaMemcpyAsync(host_out, x->d_results[r], sizeof(float) * (size_t)x->S * x->tcap * MMW_RESULT_FLOATS,
+                           cudaMemcpyDeviceToHost, x->d2h_stream));
+        CK(cudaEventRecord(x->results_done[r], x->d2h_stream));
+        if (slot) *slot = r;
+        return MMW_OK;
+    }
+    CK(join_pose(x));
     const int r = (int)(x->result_idx++ & 1u);
     // The previous download of this buffer must have finished.  In a pipelined loop the host has already waited for
     // it (mmw_wait_results two frames ago), and then no wait is put into the stream: an event between dense 2 and the
@@ -1236,7 +1390,7 @@ int mmw_preprocess(mmw_ctx* x, const float* pts, size_t n, double* world, uint8_
     x->launches++;
     CK(cudaMemcpyAsync(world, dw, n * 8 * sizeof(double), cudaMemcpyDeviceToHost, x->stream));
     CK(cudaMemcpyAsync(keep, dk, n, cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     cudaFree(dp); cudaFree(dw); cudaFree(dk);
     return MMW_OK;
 }
@@ -1270,7 +1424,7 @@ int mmw_dbscan(mmw_ctx* x, const double* xyz, const int32_t* offsets, int n_clou
     CK(cudaGetLastError());
     x->launches++;
     CK(cudaMemcpyAsync(labels, dl, total * sizeof(int32_t), cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     cudaFree(dx); cudaFree(doff); cudaFree(dl);
     return MMW_OK;
 }
@@ -1291,7 +1445,7 @@ int mmw_kalman_predict(mmw_ctx* x, double* hx, double* hP, const double* dt, int
     x->launches++;
     CK(cudaMemcpyAsync(hx, dx, (size_t)n * 9 * 8, cudaMemcpyDeviceToHost, x->stream));
     CK(cudaMemcpyAsync(hP, dP, (size_t)n * 81 * 8, cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     cudaFree(dx); cudaFree(dP); cudaFree(ddt);
     return MMW_OK;
 }
@@ -1318,7 +1472,7 @@ int mmw_kalman_update(mmw_ctx* x, double* hx, double* hP, const double* z, const
     x->launches++;
     CK(cudaMemcpyAsync(hx, dx, (size_t)n * 9 * 8, cudaMemcpyDeviceToHost, x->stream));
     CK(cudaMemcpyAsync(hP, dP, (size_t)n * 81 * 8, cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     cudaFree(dx); cudaFree(dP); cudaFree(dz); cudaFree(dR); cudaFree(dl);
     return MMW_OK;
 }
@@ -1348,7 +1502,7 @@ int mmw_gate(mmw_ctx* x, const double* points, int M, const double* hxv, const d
     x->launches++;
     if (T) CK(cudaMemcpyAsync(d2, dd, (size_t)M * T * 8, cudaMemcpyDeviceToHost, x->stream));
     CK(cudaMemcpyAsync(assoc, da, (size_t)M * 4, cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     cudaFree(dp); cudaFree(da); cudaFree(dh); cudaFree(dC); cudaFree(dd);
     return MMW_OK;
 }
@@ -1359,10 +1513,11 @@ int mmw_pose(mmw_ctx* x, const float* feats, int n, float* keypoints) {
     if (n > x->pose_cap) return fail(MMW_ERR_CAPACITY, "n exceeds n_scenes * max_tracks");
     if (n == 0) return MMW_OK;
     CK(cudaSetDevice(x->device));
+    CK(join_pose(x));
     const size_t per = (size_t)x->dc.ring_size * kFeatPts * kRawCols;
     CK(cudaMemcpyAsync(x->d_feats, feats, sizeof(float) * per * n, cudaMemcpyHostToDevice, x->stream));
     CK(cudaMemcpyAsync(x->d_pose_total, &n, sizeof(int), cudaMemcpyHostToDevice, x->stream));
-    CK(cudaStreamSynchronize(x->stream));     // &n is a stack variable
+    CK(sync_main(x));     // &n is a stack variable
     if (x->use_tc && x->tc.ready) {
         if (pose_tc_pack_input(&x->tc, x->d_feats, x->d_pose_total, x->stream) != 0)
             return fail(MMW_ERR_CUDA, std::string("tensor-core input pack: ") + pose_tc_error());
@@ -1371,14 +1526,14 @@ int mmw_pose(mmw_ctx* x, const float* feats, int n, float* keypoints) {
     int rc = run_pose_net(x, nullptr, n);
     if (rc != MMW_OK) return rc;
     CK(cudaMemcpyAsync(keypoints, x->d_pose_out, sizeof(float) * kKp * n, cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     return MMW_OK;
 }
 
 int mmw_profile(mmw_ctx* x, int enable) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     for (auto& m : x->marks) cudaEventDestroy(m.first);
     x->marks.clear();
     for (int i = 0; i < MMW_N_KERNELS; ++i) { x->kernel_ms[i] = 0; x->kernel_calls[i] = 0; }
@@ -1389,7 +1544,7 @@ int mmw_profile(mmw_ctx* x, int enable) {
 int mmw_get_kernel_ms(mmw_ctx* x, double* total_ms, uint64_t* calls) {
     if (!x || !total_ms || !calls) return fail(MMW_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     for (size_t i = 0; i + 1 < x->marks.size(); ++i) {
         const int k = x->marks[i].second;
         if (k < 0 || k >= MMW_N_KERNELS) continue;
@@ -1408,7 +1563,7 @@ int mmw_get_kernel_ms(mmw_ctx* x, double* total_ms, uint64_t* calls) {
 int mmw_scene_cycles(mmw_ctx* x, uint64_t* out /*[S]*/) {
     if (!x || !out) return fail(MMW_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     CK(cudaMemcpy(out, x->d_phase + 16, sizeof(unsigned long long) * 3 * x->S, cudaMemcpyDeviceToHost));
     return MMW_OK;
 }
@@ -1416,7 +1571,7 @@ int mmw_scene_cycles(mmw_ctx* x, uint64_t* out /*[S]*/) {
 int mmw_dbscan_big_clocks(mmw_ctx* x, uint64_t* out8 /*[16]*/) {
     if (!x || !out8) return fail(MMW_ERR_INVALID, "NULL argument");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     unsigned long long h[16];
     CK(cudaMemcpy(h, x->d_phase + 16 + 3 * x->S, sizeof(h), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 16; ++i) out8[i] = h[i];
@@ -1427,7 +1582,7 @@ int mmw_dbscan_big_clocks(mmw_ctx* x, uint64_t* out8 /*[16]*/) {
 int mmw_phase_clocks(mmw_ctx* x, int enable, uint64_t* out16) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(x->device));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(sync_main(x));
     if (out16) {
         unsigned long long h[16];
         CK(cudaMemcpy(h, x->d_phase, sizeof(h), cudaMemcpyDeviceToHost));

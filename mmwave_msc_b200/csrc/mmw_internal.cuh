@@ -214,6 +214,26 @@ __device__ __forceinline__ void world_from_raw(const DevConfig& c, float fx, flo
     w[5] = __dadd_rn(__dmul_rn(c.sin_t, vy), __dmul_rn(c.cos_t, vz));
 }
 
+struct FadeCfg { double m_x, m_y, m_z, smax, smin, weight; };
+
+// calc_projection_points (Utils.py:180-219): where the line from the point to the sensitive object (M_X, M_Y, M_Z)
+// crosses the window plane y = 0.
+__device__ __forceinline__ void projection_point(const FadeCfg& f, double xo, double yo, double zo, double& xp,
+                                                 double& zp) {
+    const double xd = xo - f.m_x, yd = yo - f.m_y, zd = zo - f.m_z;
+    xp = (xd == 0.0) ? xo : (-f.m_y / (yd / xd)) + f.m_x;
+    zp = (zd == 0.0) ? zo : (-f.m_y / (yd / zd)) + f.m_z;
+}
+
+// Fade square of a packed result record (calc_fade_square, Visualizer.py:14-29), float64 like the reference: rec[2..10]
+// = state x, kp = the track's 57 keypoints; writes rec[68..71].
+__device__ __forceinline__ void write_fade_square(const FadeCfg& fade, double x0, double x1, const float* kp, float* rec) {
+    double cx, cz;
+    projection_point(fade, x0 + (double)kp[3], x1 + (double)kp[41], (double)kp[22], cx, cz);
+    const double size = fmax(fade.smin, fmin(fade.smax, fade.smax - (x1 + (double)kp[12]) * fade.weight));
+    rec[68] = (float)cx; rec[69] = (float)cz; rec[70] = (float)size; rec[71] = 0.f;
+}
+
 // altered_EuclideanDist(p, q) <= eps (Utils.py:242-247, compared as sklearn's radius query does)
 __device__ __forceinline__ bool eps_neighbour(const DevConfig& c, double x1, double y1, double z1, double x2,
                                               double y2, double z2, double eps) {

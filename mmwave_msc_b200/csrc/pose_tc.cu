@@ -405,6 +405,9 @@ struct GemmTcArgs {
     const int32_t *row_scene, *row_slot;
     int K, N, tcap;
     int dbg;                             // timing experiments only (MMW_GEMM_DBG): 1 = no TMA loads, 2 = no MMAs
+    float* results = nullptr;            // MODE 1, throughput mode: packed result records to finish (pose_tc.cuh)
+    const int32_t* row_track = nullptr;
+    FadeCfg fade = {0, 0, 0, 0, 0, 0};
 };
 
 constexpr int kGemmThreads = 192;
@@ -550,6 +553,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                 for (int r = q; r < nrow; r += 4) {
                     float* kp = a.keypoints + ((size_t)a.row_scene[m0 + r] * a.tcap + a.row_slot[m0 + r]) * kKp;
                     for (int n = lane; n < kKp; n += 32) kp[n] = stg[r * kKp + n];
+                }
+            }
+            if (a.results) {
+                for (int r = q; r < nrow; r += 4) {
+                    float* rec = a.results + ((size_t)a.row_scene[m0 + r] * a.tcap + a.row_track[m0 + r]) * MMW_RESULT_FLOATS;
+                    for (int n = lane; n < kKp; n += 32) rec[11 + n] = stg[r * kKp + n];
+                    if (lane == 0) {     // the tracker side left x[0], x[1] as two doubles in rec[68..71]
+                        const double x0 = reinterpret_cast<const double*>(rec + 68)[0], x1 = reinterpret_cast<const double*>(rec + 68)[1];
+                        write_fade_square(a.fade, x0, x1, stg + r * kKp, rec);
+                    }
                 }
             }
         }
@@ -799,7 +812,7 @@ __global__ void pack_input_kernel(const float* __restrict__ feats, __nv_bfloat16
 // ---- host side ---------------------------------------------------------------------------------------
 struct TcImpl {
     int D = 0, taps = 0, Kf = 0, H = 0, rows_cap = 0, rows_pad = 0;
-    __nv_bfloat16 *in_p = nullptr, *act1_p = nullptr;                 // packed activations
+    __nv_bfloat16 *in_p = nullptr, *in_p2 = nullptr, *act1_p = nullptr;   // packed activations (input double-buffered)
     __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr;                   // dense-1 operand [rows_pad][Kf]
     __nv_bfloat16 *h_hi = nullptr, *h_lo = nullptr;                   // dense-2 operand [rows_pad][H]
     __nv_bfloat16 *w1b = nullptr, *w2b = nullptr;                     // conv B matrices [taps][NOUT][CK]
@@ -914,7 +927,8 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
     im->rows_pad = (rows_cap + 127) / 128 * 128;
     t->D = D; t->K = im->Kf; t->H = im->H; t->rows_cap = rows_cap;
     const size_t R = im->rows_pad, P = (size_t)D * 64;
-    bool ok = dev_alloc(&im->in_p, R * P * 16 * 2, true) && dev_alloc(&im->act1_p, R * P * 32 * 2, true) &&
+    bool ok = dev_alloc(&im->in_p, R * P * 16 * 2, true) && dev_alloc(&im->in_p2, R * P * 16 * 2, true) &&
+              dev_alloc(&im->act1_p, R * P * 32 * 2, true) &&
               dev_alloc(&im->a_hi, R * im->Kf * 2, true) && dev_alloc(&im->a_lo, R * im->Kf * 2, true) &&
               dev_alloc(&im->h_hi, R * im->H * 2, true) && dev_alloc(&im->h_lo, R * im->H * 2, true);
     { const char* env = getenv("MMW_GEMM_DBG"); im->dbg = env ? atoi(env) : 0; }
@@ -1001,9 +1015,9 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
     return 0;
 }
 
-__nv_bfloat16* pose_tc_input(PoseTc* t) {
+__nv_bfloat16* pose_tc_input(PoseTc* t, int buf) {
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
-    return im ? im->in_p : nullptr;
+    return im ? (buf ? im->in_p2 : im->in_p) : nullptr;
 }
 
 static int check_launch(const char* what) {
@@ -1019,10 +1033,10 @@ int pose_tc_pack_input(PoseTc* t, const float* feats, const int* n_rows, cudaStr
     return check_launch("pack_input_kernel");
 }
 
-int pose_tc_conv(PoseTc* t, const PoseTcRun& r, cudaStream_t st, int* n_launches) {
+int pose_tc_conv(PoseTc* t, const PoseTcRun& r, cudaStream_t st, int* n_launches, int buf) {
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
-    ConvTcArgs c1{r.n_rows, r.b1, nullptr, nullptr, im->in_p, im->act1_p, nullptr, im->D, im->taps, im->dbg};
+    ConvTcArgs c1{r.n_rows, r.b1, nullptr, nullptr, buf ? im->in_p2 : im->in_p, im->act1_p, nullptr, im->D, im->taps, im->dbg};
     const dim3 one(1, 1, 1);
     cudaError_t le;
     if (im->D == 3)
@@ -1083,7 +1097,7 @@ int pose_tc_fc2(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
     GemmTcArgs g{r.n_rows, r.bd2, nullptr, nullptr, nullptr, nullptr, r.out, r.keypoints, r.row_scene, r.row_slot,
-                 im->H, 64, r.tcap, im->dbg};
+                 im->H, 64, r.tcap, im->dbg, r.results, r.row_track, r.fade};
     const cudaError_t le = launch_pdl(gemm_tc_kernel<64, 4, 1>, dim3(1, (max_rows + 127) / 128), dim3(kGemmThreads),
                                       gemm_smem_bytes<64, 4>(), st, dim3(1, 1, 1), im->m_hh, im->m_hl, im->m_w2h,
                                       im->m_w2l, g);
@@ -1095,7 +1109,7 @@ int pose_tc_fc2(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
 void pose_tc_free(PoseTc* t) {
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (im) {
-        for (void* p : {(void*)im->in_p, (void*)im->act1_p, (void*)im->a_hi, (void*)im->a_lo, (void*)im->h_hi,
+        for (void* p : {(void*)im->in_p, (void*)im->in_p2, (void*)im->act1_p, (void*)im->a_hi, (void*)im->a_lo, (void*)im->h_hi,
                         (void*)im->h_lo, (void*)im->w1b, (void*)im->w2b, (void*)im->wd1_hi, (void*)im->wd1_lo,
                         (void*)im->wd2_hi, (void*)im->wd2_lo})
             if (p) cudaFree(p);

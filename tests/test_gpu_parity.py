@@ -449,6 +449,41 @@ def _run_with_env(env, S=48, F=14):
                 os.environ[k] = v
 
 
+def test_throughput_mode_results_are_bit_identical_to_serial_mode():
+    """MMW_STEP_PIPELINE: the pose network of frame k on its own stream under the tracker of frame k + 1.  The packed
+    records fetched per frame equal the serial mode's bit for bit -- also for scenes whose frame is skipped (their
+    tracks get no pose row) and across a switch back to the serial mode; the final track records agree too."""
+    S, F = 48, 30
+    batches = synth.gen_batch(list(range(700, 700 + S)), F)
+    W = pw.make_pose_weights(pw.VARIANT_3D)
+    n = S * 8 * _lib.RESULT_FLOATS
+    a, b = BatchedTracker(S), BatchedTracker(S)
+    a.load_pose_weights(W); b.load_pose_weights(W)
+    rng = np.random.default_rng(3)
+    out_a = [np.zeros(n, np.float32) for _ in range(F)]
+    out_b = [np.zeros(n, np.float32) for _ in range(F)]
+    slots = []
+    for f, bt in enumerate(batches):
+        pts, off, dt = bt.points, bt.offsets, bt.dt
+        if f in (9, 10, 17):                                     # a few scenes lose their frame (Q23)
+            drop = rng.choice(S, 5, replace=False)
+            parts = [pts[off[s]:off[s + 1]] if s not in drop else pts[:0] for s in range(S)]
+            pts = np.concatenate(parts); off = np.zeros(S + 1, np.int32); off[1:] = np.cumsum([len(p) for p in parts])
+        serial_here = f in (20, 21)                              # mode switch in the middle of the sequence
+        a.step(pts, off, dt, pose=True)
+        a.wait_results(a.read_results_async(out_a[f]))
+        b.step(pts, off, dt, pose=True, pipeline=not serial_here)
+        slots.append(b.read_results_async(out_b[f]))
+        if f >= 1:
+            b.wait_results(slots[f - 1])
+    b.wait_results(slots[-1])
+    for f in range(F):
+        assert out_a[f].tobytes() == out_b[f].tobytes(), "frame %d" % f
+    ta, na = a.tracks()
+    tb, nb = b.tracks()
+    assert na.sum() > S and np.array_equal(na, nb) and ta.tobytes() == tb.tobytes()
+
+
 def test_pose_row_scan_folded_vs_separate_kernel():
     """The pose-row scan inside pose_feature_kernel (default, S <= 4096) and pose_index_kernel (S > 4096) lay the
     rows out identically."""
