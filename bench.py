@@ -46,31 +46,81 @@ def peaks():
 
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and clock-event (throttle) reasons DURING the timed regions (B200_PROFILING.md recipe).
+    Sampled through NVML in a thread of this process every 5 ms: the same counters `nvidia-smi --query-gpu=clocks.sm,
+    clocks.max.sm,power.draw,clocks_event_reasons.*` prints, without a second process polling the driver -- the
+    nvidia-smi loop stalled the launch path for milliseconds at a time, which is a third of a 5 ms timed window.
+    Falls back to that loop when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows, self.samples = [], []
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except Exception:
+                pass
+        return self.gpu
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE,
+                                          "-i", str(self._physical_index()), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+                rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1)
+            n = self.nvml
+            bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+            reasons = sorted(k for k, b in bits.items() if any(s[2] & b for s in self.samples))
+            sm = [s[0] for s in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max,
+                    "power_w_max": max((s[1] for s in self.samples), default=None), "samples": len(sm),
+                    "reasons": reasons, "source": "NVML (in-process, every 5 ms)"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -80,7 +130,6 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
@@ -89,11 +138,12 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[5:9]):
+            for nm, v in zip(self.NAMES, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi -lms 20"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -220,6 +270,42 @@ def _cpu_worker_pose(args):
 
 
 # --------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa_node(local):
+    """Best effort: run this rank (and place its pinned buffers, first touch) on the cores of the NUMA node its GPU
+    hangs off.  Returns a description for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return {"numa_node": None, "why": "the platform reports no NUMA node for %s" % bus}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "why": "no allowed core on that node"}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cores": len(cpus), "gpu": bus}
+    except Exception as e:                      # never fatal: it is an optimisation
+        return {"numa_node": None, "why": "%s: %s" % (type(e).__name__, e)}
+
+
+DOPPLER_RES = 0.0626       # Doppler bin of the 12 Hz profile the synthetic generator quantises to (synth.py)
+
+
+def lattice_rows(points):
+    """The generator's fp32 rows as the sensor's lattice: (fp32 rows with the Doppler column as the index, int16 rows
+    x, y, z in Q9, dopplerIdx, peakVal).  The context multiplies the index by mmw_config::doppler_res in float64."""
+    p = points.astype(np.float64)
+    q = np.stack([np.rint(p[:, 0] * 512), np.rint(p[:, 1] * 512), np.rint(p[:, 2] * 512), np.rint(p[:, 3] / DOPPLER_RES),
+                  np.rint(p[:, 4])], axis=1)
+    f32 = np.stack([q[:, 0] / 512, q[:, 1] / 512, q[:, 2] / 512, q[:, 3], q[:, 4]], axis=1).astype(np.float32)
+    return np.ascontiguousarray(f32), np.ascontiguousarray(q.astype(np.int16))
+
+
 def _tile_batches(batches, reps):
     """The same scenes `reps` times side by side (scene s + k * S is scene s again): a throughput workload of
     reps * S scenes from S generated ones."""
@@ -278,7 +364,8 @@ def other_configs(batches, weights3d, flush, local):
     bt.close()
     # C5 on one GPU: the headline run's own scenes, eight times side by side
     tiled = _tile_batches(batches[:PRIME + WARM + K], 8)
-    bt = BatchedTracker(8192, max_points=256, max_tracks=8, device=local)
+    bt = BatchedTracker(8192, max_points=256, max_tracks=8, device=local,
+                        config=default_config(doppler_res=DOPPLER_RES, xyz_q_format=9))
     bt.load_pose_weights(weights3d)
     ms = _timed_device_steps(bt, tiled, PRIME, WARM, K, flush, local)
     out["C5_one_gpu"] = {"what": "8192 scenes on ONE GPU (the 1024 generated scenes x 8), full path incl. pose",
@@ -327,11 +414,13 @@ def replay_check(world, S, n_frames_done, weights, gathered, per_scene, local, p
     import torch
     n_check = min(32, S)
     ids = list(range(S, S + n_check))                     # global scene ids of rank 1's first scenes
+    from mmwave_msc_b200.batched import default_config
     batches = synth.gen_batch(ids, n_frames_done)
-    bt = BatchedTracker(n_check, max_points=256, max_tracks=8, device=local)
+    bt = BatchedTracker(n_check, max_points=256, max_tracks=8, device=local,
+                        config=default_config(doppler_res=DOPPLER_RES, xyz_q_format=9))
     bt.load_pose_weights(weights)
     for f, b in enumerate(batches):
-        bt.step(b.points, b.offsets, b.dt, pose=pose_calls[f])
+        bt.step(lattice_rows(b.points)[1], b.offsets, b.dt, pose=pose_calls[f])        # int16 rows, serial mode
     out = torch.empty(n_check * per_scene, dtype=torch.float32, device="cuda")
     bt.pack_results(out.data_ptr())
     bt.sync()
@@ -388,16 +477,26 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     S = args.scenes
     W_, K = args.warmup, args.steps
     LAT_FRAMES = 12
-    n_frames = PRIME_FRAMES + 3 * (W_ + K) + K + LAT_FRAMES   # device-timed, throughput-mode, e2e, latency and per-kernel profile passes
+    E2E_REPS = 5               # the end-to-end window of K steps is ~5 ms: measured this many times, median reported
+    n_frames = PRIME_FRAMES + 2 * (W_ + K) + (W_ + E2E_REPS * K) + K + LAT_FRAMES   # device-timed, throughput-mode, e2e, latency, per-kernel profile
     ids = sharding.shard_scene_ids(world * S, world, rank)      # contiguous block of scenes per GPU
     batches = synth.gen_batch(ids, n_frames)
+    # the sensor's lattice: fp32 rows for the device-resident passes, int16 rows (10 bytes per point) for the end-to-end
+    # pass; the Doppler column is the index, the context multiplies by the resolution in float64
+    rows16 = []
+    for b in batches:
+        b.points, r16 = lattice_rows(b.points)
+        rows16.append(r16)
 
-    bt = BatchedTracker(S, max_points=256, max_tracks=8, device=local)
+    from mmwave_msc_b200.batched import default_config
+    bt = BatchedTracker(S, max_points=256, max_tracks=8, device=local,
+                        config=default_config(doppler_res=DOPPLER_RES, xyz_q_format=9))
     weights = pw.make_pose_weights(pw.VARIANT_3D)
     bt.load_pose_weights(weights)
     bt.set_dense_path(args.dense_path == "tc")
@@ -451,23 +550,27 @@ def main():
     total_ms_max = float(t.item())
     value = world * S * K / (total_ms_max / 1e3)
 
-    # ---- throughput mode (MMW_STEP_PIPELINE): the pose network of frame k under the tracker of frame k + 1; K steps
-    # back to back, device-resident inputs, one pair of CUDA events around all of them (the second after the main
-    # stream has joined the pose stream).  No explicit L2 flush between these steps -- it would serialise the two
-    # streams; every step streams its ~430 MB working set (track state + pose scratch) through the 126 MB L2.
+    # ---- throughput mode (MMW_STEP_PIPELINE): the pose network of frame k on a second stream under the tracker of
+    # frame k + 1 (results bit-identical to the serial mode); K steps back to back, device-resident inputs, one pair of
+    # CUDA events around all of them (the second after the main stream has joined the pose stream), max over ranks.
+    # No explicit L2 flush here -- a fill on either stream would serialise them: every step reads a frame that has never
+    # been read before from its own buffer and streams ~150 MB of state, activations and weights through the 126 MB L2.
+    # Reported next to the headline `value`, which stays the serial, flushed, per-step protocol.
     res_dev0 = torch.empty(S * bt.tcap * _lib.RESULT_FLOATS, dtype=torch.float32, device="cuda")
     for _ in range(W_):
         p, o, d = dev[f]
         bt.step_device(p.data_ptr(), o.data_ptr(), d.data_ptr(), p.shape[0], pose=True, pipeline=True); f += 1
     barrier(); bt.sync()
     t_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    barrier()
     t_ev[0].record(stream)
-    for _ in range(K):
+    for k in range(K):
         p, o, d = dev[f]
         bt.step_device(p.data_ptr(), o.data_ptr(), d.data_ptr(), p.shape[0], pose=True, pipeline=True); f += 1
     bt.pack_results(res_dev0.data_ptr())          # serial-mode call: the main stream waits for the pose stream first
     t_ev[1].record(stream)
     barrier(); bt.sync()
+    bt.counters(reset=True)
     tp_ms = torch.tensor([t_ev[0].elapsed_time(t_ev[1])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tp_ms, op=dist.ReduceOp.MAX)
@@ -475,50 +578,41 @@ def main():
 
     # ---- end-to-end pass through the public API: pinned host inputs, result read back every step ----------
     res_dev = torch.empty(S * bt.tcap * _lib.RESULT_FLOATS, dtype=torch.float32, device="cuda")
-    res_host = torch.empty(S * bt.tcap * _lib.RESULT_FLOATS, dtype=torch.float32).pin_memory()
-    pinned = []
-    for b in batches[f:f + W_ + K]:
-        pp = torch.from_numpy(b.points).pin_memory()
-        po = torch.from_numpy(b.offsets).pin_memory()
-        pd = torch.from_numpy(b.dt).pin_memory()
-        pinned.append((pp.numpy(), po.numpy(), pd.numpy()))
+    per_frame = S * bt.tcap * _lib.RESULT_FLOATS
 
-    # The public API pipelines by itself: step() uploads from pinned memory on a side stream into double-buffered
-    # staging, runs the tracker on the main stream and (throughput mode) the pose network on a second one,
-    # read_results_async() downloads the frame's records on a third; the host only waits for the results of the
-    # PREVIOUS frame, so upload(k+1) / tracker(k+1) / pose(k) / download(k-1) overlap.  Every frame's inputs cross PCIe inside
-    # the timed region and every frame's results land in host memory.
-    res_hosts = [torch.empty(S * bt.tcap * _lib.RESULT_FLOATS, dtype=torch.float32).pin_memory() for _ in range(2)]
-    res_np = [r.numpy() for r in res_hosts]
-    res_host = res_hosts[0]
+    # The public API for a replay of many scenes is mmw_run_frames (BatchedTracker.run_frames): the loop of
+    # offline_main.py:40-62 in C over pinned host buffers -- int16 sensor rows up, packed result records down, every
+    # frame's bytes crossing PCIe inside the timed region; uploads on one side stream into double-buffered staging, the
+    # tracker on the main stream, the pose network on a second one (throughput mode), downloads on a third, so
+    # upload(k+1) / tracker(k+1) / pose(k) / download(k-1) overlap.
+    def pinned_block(lo, hi):
+        rows = torch.from_numpy(np.concatenate(rows16[lo:hi])).pin_memory()
+        fro = np.cumsum([0] + [len(r) for r in rows16[lo:hi]]).astype(np.int64)
+        offs = torch.from_numpy(np.stack([b.offsets for b in batches[lo:hi]])).pin_memory()
+        dts = torch.from_numpy(np.stack([b.dt for b in batches[lo:hi]])).pin_memory()
+        res = torch.empty((hi - lo, per_frame), dtype=torch.float32).pin_memory()
+        return rows.numpy(), fro, offs.numpy(), dts.numpy(), res.numpy()
 
-    def run_e2e(lo, hi):
-        nbytes, prev = 0, None
-        for i in range(lo, hi):
-            p, o, d = pinned[i]
-            bt.step(p, o, d, pose=True, pipeline=True)
-            slot = bt.read_results_async(res_np[i & 1])
-            if prev is not None:
-                bt.wait_results(prev)
-            prev = slot
-            nbytes += p.nbytes + o.nbytes + d.nbytes
-        if prev is not None:
-            bt.wait_results(prev)
-        return nbytes
-
-    run_e2e(0, W_)
-    barrier()
-    t0 = time.perf_counter()
-    h2d = run_e2e(W_, W_ + K)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()           # sampled every 20 ms across the device-timed pass and the end-to-end pass
-    clocks["window"] = "device-timed pass + end-to-end pass (both under load)"
-    f += W_ + K
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * S * K / float(t.item())
+    warm_blk = pinned_block(f, f + W_)
+    time_blks = [pinned_block(f + W_ + r * K, f + W_ + (r + 1) * K) for r in range(E2E_REPS)]
+    bt.run_frames(*warm_blk)
+    e2e_reps = []
+    for blk in time_blks:              # consecutive frames of the same sequences: every window is K new frames
+        barrier()
+        t0 = time.perf_counter()
+        bt.run_frames(*blk)
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_reps.append(float(t.item()))
+    time_blk = time_blks[-1]
+    h2d = time_blk[0].nbytes + time_blk[2].nbytes + time_blk[3].nbytes
+    res_np = [time_blk[4][0], time_blk[4][1]]
+    clocks = sampler.stop()           # sampled across the device-timed passes and the end-to-end pass
+    clocks["window"] = "device-timed passes + end-to-end pass (all under load)"
+    f += W_ + E2E_REPS * K
+    e2e_value = world * S * K / float(np.median(e2e_reps))
 
     # ---- per-frame latency, host enqueue -> results in host memory, NOT pipelined -------------
     lat = []
@@ -589,17 +683,24 @@ def main():
             "config": {"workload": WORKLOAD, "scenes_per_gpu": S, "max_points": 256, "max_tracks": 8,
                        "pose_net": "define_CNN_3D", "pose_dtype": "fp32 (CUDA-core) / bf16x3 split on tcgen05, fp32 accumulate",
                        "dense_path": args.dense_path, "prime_frames": PRIME_FRAMES,
+                       "mode": "serial mode: one stream, every kernel of a frame before the next frame's first (what a live "
+                               "sensor gets); `throughput_mode` and `e2e` overlap the pose network with the next frame's tracker",
                        "l2": ("NOT flushed (diagnostic run)" if args.no_l2_flush else
                               "flushed between timed steps (256 MiB fill); per-step CUDA events on the library stream, "
                               "flush excluded"), "parallelism": "scenes sharded %d/GPU, no collective in the hot loop" % S},
             "throughput_mode": {"value": world * S * K / (tp_ms / 1e3), "unit": UNIT, "ms_per_step": tp_ms / K,
-                                "what": "MMW_STEP_PIPELINE: pose network of frame k on a second stream under the tracker "
-                                        "of frame k+1 (results bit-identical to the serial mode), device-resident inputs, "
-                                        "K steps inside one pair of CUDA events, max over ranks",
-                                "l2": "no explicit flush (it would serialise the streams): each step streams its ~430 MB "
-                                      "working set through the 126 MB L2"},
+                                "what": "MMW_STEP_PIPELINE: pose network of frame k on a second (high-priority) stream under "
+                                        "the tracker of frame k+1, results bit-identical to the serial mode; device-resident "
+                                        "inputs, K steps inside one pair of CUDA events, max over ranks",
+                                "l2": "no explicit flush (a fill on either stream would serialise them): every step reads a "
+                                      "frame never read before and streams ~150 MB through the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // K),
-                    "d2h_bytes_per_step": int(res_host.numel() * 4)},
+                    "d2h_bytes_per_step": int(per_frame * 4),
+                    "api": "mmw_run_frames (BatchedTracker.run_frames): int16 sensor rows from pinned host memory, "
+                           "throughput mode, packed result records of every frame back in pinned host memory",
+                    "host": numa,
+                    "windows": {"reps": E2E_REPS, "steps_each": K, "value_is": "median over the windows of (steps / max-over-ranks "
+                                "wall time)", "scene_frames_per_s": [world * S * K / t for t in e2e_reps]}},
             "gpu_launches": int(launches),
             "latency": latency,
             "clocks": clocks,

@@ -58,7 +58,8 @@ typedef struct mmw_config {
     double kf_a_spr;               /* KF_A_SPR :104 */
     double kf_spread_lim[6];       /* KF_SPREAD_LIM :103 */
     int32_t kf_est_pointnum;       /* KF_EST_POINTNUM :102 */
-    int32_t reserved0;
+    int32_t xyz_q_format;          /* Q format of int16 point rows (MMW_STEP_INPUT_I16): metres = value / 2^Q; the
+                                      xWR14xx demo reports it per frame (ReadDataIWR1443.py:126-128), usually 9 */
     double intensity_mu;           /* INTENSITY_MU :108 */
     double intensity_std;          /* INTENSITY_STD :109 */
     double x_nudge_thres;          /* 0.6, Tracking.py:397 */
@@ -91,6 +92,9 @@ typedef struct mmw_ctx mmw_ctx;
 #define MMW_STEP_POSE          0x1u   /* run estimate_posture after track (offline_main.py:60) */
 #define MMW_STEP_DEVICE_INPUT  0x2u   /* pts/offsets/dt are device pointers (already resident in HBM) */
 #define MMW_STEP_RECORD_LABELS 0x4u   /* keep the DBSCAN labels of this frame for mmw_get_labels */
+#define MMW_STEP_INPUT_I16     0x10u  /* pts is int16 [sum N, 5] = x, y, z (Q format mmw_config::xyz_q_format), dopplerIdx,
+                                         peakVal -- the sensor's own lattice, 10 bytes per point instead of 20; converted on
+                                         the device (exact: x = value / 2^Q, doppler = dopplerIdx * doppler_res in float64) */
 #define MMW_STEP_PIPELINE      0x8u   /* throughput mode (with MMW_STEP_POSE): the pose network of this frame runs on a
                                          second stream and overlaps the tracker of the NEXT frame -- keypoints never feed
                                          back into tracking (Tracking.py:705-734).  The frame's packed result records
@@ -313,6 +317,16 @@ int mmw_nccl_comm_destroy(void* nccl_comm);
  * mmw_step or mmw_sync. */
 int mmw_read_results_async(mmw_ctx* ctx, float* host_out, int* slot);
 int mmw_wait_results(mmw_ctx* ctx, int slot);
+
+/* The replay loop of offline_main.py:40-62 for all scenes of the context, n_frames frames back to back from HOST
+ * buffers (pinned memory recommended), in C: frame f takes its rows at pts + frame_row_offsets[f] rows (fp32 rows, or
+ * int16 rows with MMW_STEP_INPUT_I16), its own CSR offsets at offsets + f * (S + 1) (each starting at 0) and dt + f * S,
+ * and leaves its packed result records (layout of mmw_pack_results) at results + f * S * max_tracks *
+ * MMW_RESULT_FLOATS.  flags as for mmw_step (MMW_STEP_POSE | MMW_STEP_PIPELINE for the throughput mode).  The upload
+ * of frame f+1, the kernels of frame f and the download of frame f-1 overlap; returns when every frame's results
+ * are in host memory. */
+int mmw_run_frames(mmw_ctx* ctx, int n_frames, const void* pts, const int64_t* frame_row_offsets, const int32_t* offsets,
+                   const double* dt, float* results, uint32_t flags);
 
 /* Counters accumulated on the device since the last call (algorithmic-bytes bookkeeping):
  * out[0]=frames stepped (scene-frames that ran), [1]=sum N, [2]=sum M, [3]=sum U (unassigned pushed),

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MMW_LIB", os.path.join(_HERE, "libmmw.so"))   # MMW_LIB: alternative build (profiling experiments)
 
 MMW_POSE_2D, MMW_POSE_3D = 0, 1
-STEP_POSE, STEP_DEVICE_INPUT, STEP_RECORD_LABELS, STEP_PIPELINE = 0x1, 0x2, 0x4, 0x8
+STEP_POSE, STEP_DEVICE_INPUT, STEP_RECORD_LABELS, STEP_PIPELINE, STEP_INPUT_I16 = 0x1, 0x2, 0x4, 0x8, 0x10
 SCENE_POINT_OVERFLOW, SCENE_TRACK_OVERFLOW = 0x1, 0x2
 RESULT_FLOATS = 72
 ABI_VERSION = 3            # MMW_ABI_VERSION of include/mmw.h this binding was written against
@@ -33,7 +33,7 @@ class Config(C.Structure):
         ("tr_vel_thres", C.c_double), ("tr_gate", C.c_double),
         ("kf_q_var", C.c_double), ("kf_p_init", C.c_double), ("kf_group_disp_init", C.c_double),
         ("kf_a_n", C.c_double), ("kf_a_spr", C.c_double), ("kf_spread_lim", C.c_double * 6),
-        ("kf_est_pointnum", C.c_int32), ("reserved0", C.c_int32),
+        ("kf_est_pointnum", C.c_int32), ("xyz_q_format", C.c_int32),
         ("intensity_mu", C.c_double), ("intensity_std", C.c_double),
         ("x_nudge_thres", C.c_double), ("x_nudge_gain", C.c_double),
         ("default_posture", C.c_float * 57), ("reserved1", C.c_float),
@@ -110,6 +110,7 @@ SIGNATURES = {
     "mmw_nccl_comm_destroy": (C.c_int, [_p]),
     "mmw_read_results_async": (C.c_int, [_p, _p, C.POINTER(C.c_int)]),
     "mmw_wait_results": (C.c_int, [_p, C.c_int]),
+    "mmw_run_frames": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _p, C.c_uint32]),
     "mmw_get_counters": (C.c_int, [_p, _p, C.c_int]),
     "mmw_set_dense_path": (C.c_int, [_p, C.c_int]),
     "mmw_profile": (C.c_int, [_p, C.c_int]),

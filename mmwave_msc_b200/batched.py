@@ -115,7 +115,8 @@ class BatchedTracker:
         """Host inputs: points (sum N, 5) float32, offsets (S+1,) int32, dt (S,) float64.
         ``pipeline`` (throughput mode, MMW_STEP_PIPELINE): this frame's pose network overlaps the next frame's tracker;
         fetch the frame's results with read_results_async() right after the call."""
-        points = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 5)
+        i16 = getattr(points, "dtype", None) == np.int16         # the sensor's lattice: x, y, z, dopplerIdx, peakVal
+        points = np.ascontiguousarray(points, dtype=np.int16 if i16 else np.float32).reshape(-1, 5)
         offsets = np.ascontiguousarray(offsets, dtype=np.int32)
         dt = np.ascontiguousarray(dt, dtype=np.float64)
         if offsets.shape != (self.S + 1,) or dt.shape != (self.S,):
@@ -123,7 +124,7 @@ class BatchedTracker:
         if int(offsets[-1]) != points.shape[0]:
             raise ValueError("offsets[-1] must equal the number of point rows")
         flags = ((_lib.STEP_POSE if pose else 0) | (_lib.STEP_RECORD_LABELS if record_labels else 0) |
-                 (_lib.STEP_PIPELINE if pipeline else 0))
+                 (_lib.STEP_PIPELINE if pipeline else 0) | (_lib.STEP_INPUT_I16 if i16 else 0))
         self._n_last = points.shape[0]
         _lib.check(self.lib.mmw_step(self._h, _lib.ptr(points), _lib.ptr(offsets), _lib.ptr(dt), flags))
 
@@ -134,6 +135,24 @@ class BatchedTracker:
         self._n_last = int(n_points)
         _lib.check(self.lib.mmw_step(self._h, C.c_void_p(points_ptr), C.c_void_p(offsets_ptr), C.c_void_p(dt_ptr),
                                      flags))
+
+    def run_frames(self, points: np.ndarray, frame_row_offsets: np.ndarray, offsets: np.ndarray, dt: np.ndarray,
+                   results: np.ndarray, pose: bool = True, pipeline: bool = True):
+        """F frames back to back from host buffers, the loop in C (mmw_run_frames): points (rows, 5) float32 or int16,
+        frame_row_offsets (F+1,) int64, offsets (F, S+1) int32 (each frame's own, starting at 0), dt (F, S) float64,
+        results (F, S * max_tracks * 72) float32 filled with every frame's packed records.  Blocking."""
+        i16 = points.dtype == np.int16
+        F = len(frame_row_offsets) - 1
+        for a, dt_, shp in ((points, np.int16 if i16 else np.float32, None), (frame_row_offsets, np.int64, (F + 1,)),
+                            (offsets, np.int32, (F, self.S + 1)), (dt, np.float64, (F, self.S)),
+                            (results, np.float32, (F, self.S * self.tcap * _lib.RESULT_FLOATS))):
+            if a.dtype != dt_ or not a.flags["C_CONTIGUOUS"] or (shp is not None and a.shape != shp):
+                raise ValueError("run_frames: wrong dtype / shape / layout of an argument")
+        flags = ((_lib.STEP_POSE if pose else 0) | (_lib.STEP_PIPELINE if pipeline else 0) |
+                 (_lib.STEP_INPUT_I16 if i16 else 0))
+        _lib.check(self.lib.mmw_run_frames(self._h, F, _lib.ptr(points), _lib.ptr(frame_row_offsets), _lib.ptr(offsets),
+                                           _lib.ptr(dt), _lib.ptr(results), flags))
+        self._n_last = int(frame_row_offsets[-1] - frame_row_offsets[-2]) if F else 0
 
     def estimate_posture(self):
         """TrackBuffer.estimate_posture alone (needs load_pose_weights first)."""

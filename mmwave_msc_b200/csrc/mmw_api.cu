@@ -147,6 +147,7 @@ static void fill_devconfig(const mmw_config& c, int ncap, int tcap, DevConfig* d
     d->nudge_thres = c.x_nudge_thres;
     d->nudge_gain = c.x_nudge_gain;
     d->doppler_res = c.doppler_res != 0.0 ? c.doppler_res : 1.0;
+    d->xyz_scale = (float)std::ldexp(1.0, -(c.xyz_q_format));
     d->db_min_samples = c.db_min_samples;
     d->ring_size = c.frames_batch + 1;
     d->tr_max_tracks = c.tr_max_tracks;
@@ -189,6 +190,7 @@ int mmw_default_config(mmw_config* c) {
     c->m_x = 0.32; c->m_y = -0.6; c->m_z = 1.3;
     c->fade_size_max = 0.3; c->fade_size_min = 0.2; c->fade_weight = 0.08;
     c->doppler_res = 1.0;
+    c->xyz_q_format = 9;
     return MMW_OK;
 }
 
@@ -306,6 +308,7 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
         return fail(MMW_ERR_INVALID, "n_scenes >= 1, max_points >= 1, 1 <= max_tracks <= 32 required");
     if (cfg->frames_batch < 0 || cfg->frames_batch > kRing - 1)
         return fail(MMW_ERR_INVALID, "frames_batch must be 0..2");
+    if (cfg->xyz_q_format < 0 || cfg->xyz_q_format > 15) return fail(MMW_ERR_INVALID, "xyz_q_format must be 0..15");
     if (cfg->db_min_samples < 1 || cfg->tr_max_tracks < 0)
         return fail(MMW_ERR_INVALID, "db_min_samples >= 1 and tr_max_tracks >= 0 required");
     int ndev = 0;
@@ -368,8 +371,11 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
             return fail(MMW_ERR_CUDA, "cudaEventCreate failed");
         }
     }
+    // the pose network is the critical path of the throughput mode: its CTAs are scheduled ahead of the tracker's
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithFlags(&x->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&x->pose_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&x->pose_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithFlags(&x->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
         mmw_destroy(x);
         return fail(MMW_ERR_CUDA, "cudaStreamCreate failed");
@@ -551,8 +557,8 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
         }
         CK(cudaStreamWaitEvent(x->h2d_stream, x->stage_free[k], 0));
         if (total)
-            CK(cudaMemcpyAsync(x->d_pts2[k], pts, sizeof(float) * kRawCols * total, cudaMemcpyHostToDevice,
-                               x->h2d_stream));
+            CK(cudaMemcpyAsync(x->d_pts2[k], pts, ((flags & MMW_STEP_INPUT_I16) ? sizeof(int16_t) : sizeof(float)) * kRawCols * total,
+                               cudaMemcpyHostToDevice, x->h2d_stream));
         CK(cudaMemcpyAsync(x->d_offsets2[k], offsets, sizeof(int32_t) * (x->S + 1), cudaMemcpyHostToDevice,
                            x->h2d_stream));
         CK(cudaMemcpyAsync(x->d_dt2[k], dt, sizeof(double) * x->S, cudaMemcpyHostToDevice, x->h2d_stream));
@@ -1367,6 +1373,38 @@ int mmw_read_results_async(mmw_ctx* x, float* host_out, int* slot) {
     CK(cudaEventRecord(x->results_done[r], x->d2h_stream));
     if (slot) *slot = r;
     return MMW_OK;
+}
+
+int mmw_run_frames(mmw_ctx* x, int n_frames, const void* pts, const int64_t* frame_row_offsets, const int32_t* offsets,
+                   const double* dt, float* results, uint32_t flags) {
+    if (!x || !frame_row_offsets || !offsets || !dt || !results) return fail(MMW_ERR_INVALID, "NULL argument");
+    if (n_frames < 0) return fail(MMW_ERR_INVALID, "n_frames must not be negative");
+    if (flags & (MMW_STEP_DEVICE_INPUT | MMW_STEP_RECORD_LABELS))
+        return fail(MMW_ERR_INVALID, "mmw_run_frames takes host buffers and does not record labels");
+    const size_t row_bytes = (flags & MMW_STEP_INPUT_I16) ? sizeof(int16_t) * kRawCols : sizeof(float) * kRawCols;
+    const size_t per_frame = (size_t)x->S * x->tcap * MMW_RESULT_FLOATS;
+    // Every frame has its own host buffers, so the host never has to wait for a frame's results before queueing the
+    // next one -- the device-side buffers (input staging, pose inputs, result records) are handed over by stream
+    // events.  The host only keeps the queue bounded: at most kAhead frames in flight.  (Waiting for frame f-1 before
+    // queueing f+1 would put the upload of f+1 behind the download of f-1 and leave the pose stream idle for a
+    // third of every frame.)
+    constexpr int kAhead = 4;
+    cudaEvent_t done[kAhead] = {nullptr, nullptr, nullptr, nullptr};
+    CK(cudaSetDevice(x->device));
+    for (int i = 0; i < kAhead; ++i) CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    int rc = MMW_OK;
+    for (int f = 0; f < n_frames && rc == MMW_OK; ++f) {
+        if (f >= kAhead && cudaEventSynchronize(done[f % kAhead]) != cudaSuccess) { rc = fail(MMW_ERR_CUDA, "cudaEventSynchronize failed"); break; }
+        const unsigned char* p = static_cast<const unsigned char*>(pts) + (size_t)frame_row_offsets[f] * row_bytes;
+        rc = mmw_step(x, reinterpret_cast<const float*>(p), offsets + (size_t)f * (x->S + 1), dt + (size_t)f * x->S, flags);
+        if (rc != MMW_OK) break;
+        rc = mmw_read_results_async(x, results + (size_t)f * per_frame, nullptr);
+        if (rc != MMW_OK) break;
+        if (cudaEventRecord(done[f % kAhead], x->d2h_stream) != cudaSuccess) rc = fail(MMW_ERR_CUDA, "cudaEventRecord failed");
+    }
+    if (cudaStreamSynchronize(x->d2h_stream) != cudaSuccess && rc == MMW_OK) rc = fail(MMW_ERR_CUDA, "cudaStreamSynchronize failed");
+    for (int i = 0; i < kAhead; ++i) cudaEventDestroy(done[i]);
+    return rc;
 }
 
 int mmw_wait_results(mmw_ctx* x, int slot) {

@@ -28,6 +28,7 @@ struct DevConfig {
     double q_var, p_init, g_init, a_n, a_spr;
     double spread_lim[6];
     double int_mu, int_std, nudge_thres, nudge_gain;
+    float xyz_scale;           // 2^-Q of int16 point rows (MMW_STEP_INPUT_I16)
     double doppler_res;        // doppler [m/s] = row[3] * doppler_res (float64 product, ReadDataIWR1443.py:163-165)
     int db_min_samples, ring_size, tr_max_tracks, enable_est, est_pointnum;
     int ncap, tcap;
@@ -81,7 +82,7 @@ static_assert(sizeof(SceneRec) == 64, "SceneRec is one 64-byte record");
 
 struct StepArgs {
     DevConfig cfg;
-    const float* pts;          // [sum N, 5]
+    const float* pts;          // [sum N, 5] fp32 rows; int16 rows when flags has MMW_STEP_INPUT_I16
     const int32_t* offsets;    // [S+1]
     const double* dt;          // [S]
     TrackRec* tracks;          // [S][tcap]

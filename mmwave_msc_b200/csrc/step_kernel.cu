@@ -316,11 +316,15 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     if (N > ncap) { N = ncap; sc.flags |= MMW_SCENE_POINT_OVERFLOW; }
     const int T0 = sc.n_tracks;
     __syncthreads();                     // the barrier is initialised
-    const size_t byte0 = (size_t)off * (kRawCols * 4);
+    const bool i16 = (a.flags & MMW_STEP_INPUT_I16) != 0;             // the sensor's int16 lattice, 10 bytes per point
+    const int row_bytes = i16 ? kRawCols * 2 : kRawCols * 4;
+    const size_t byte0 = (size_t)off * row_bytes;
     const size_t win0 = byte0 & ~(size_t)15;
-    const uint32_t win_bytes = (uint32_t)(((byte0 + (size_t)N * (kRawCols * 4) + 15) & ~(size_t)15) - win0);
+    const uint32_t win_bytes = (uint32_t)(((byte0 + (size_t)N * row_bytes + 15) & ~(size_t)15) - win0);
     const bool bulk_pts = (reinterpret_cast<uintptr_t>(a.pts) & 15) == 0;       // else: plain loads (below)
-    const float* stagef = reinterpret_cast<const float*>(smem + L.stage + (byte0 - win0));
+    const unsigned char* stageb = smem + L.stage + (byte0 - win0);
+    const float* stagef = reinterpret_cast<const float*>(stageb);
+    const int16_t* stageh = reinterpret_cast<const int16_t*>(stageb);
     if (tid == 0) {
         const uint32_t tr_bytes = (uint32_t)T0 * (uint32_t)sizeof(TrackRec);
         sk_mbar_expect_tx(mbar, tr_bytes + (bulk_pts ? win_bytes : 0u) + (uint32_t)(kRing * kHistBytes));
@@ -330,8 +334,14 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         sk_bulk_g2s(hist, a.ring_hist + (size_t)s * (kRing * kHistBytes), kRing * kHistBytes, mbar);
     }
     if (!bulk_pts) {
-        float* st = const_cast<float*>(stagef);
-        for (int i = tid; i < N * kRawCols; i += kStepThreads) st[i] = a.pts[(size_t)off * kRawCols + i];
+        if (i16) {
+            int16_t* st = const_cast<int16_t*>(stageh);
+            const int16_t* src = reinterpret_cast<const int16_t*>(a.pts) + (size_t)off * kRawCols;
+            for (int i = tid; i < N * kRawCols; i += kStepThreads) st[i] = src[i];
+        } else {
+            float* st = const_cast<float*>(stagef);
+            for (int i = tid; i < N * kRawCols; i += kStepThreads) st[i] = a.pts[(size_t)off * kRawCols + i];
+        }
     }
     reinterpret_cast<uint32_t*>(hnew)[tid] = 0u;                 // 256 uint16 counts = 128 words
     if (tid < 32) misc[kBaseG + tid] = 0;
@@ -412,8 +422,14 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
         for (int r2 = 0; r2 < 2; ++r2) {
             const int i = tile * kTile + r2 * kStepThreads + tid;
             const int ic = i < N ? i : N - 1;                    // lanes past the end redo the last point (discarded)
+            if (i16) {                   // value / 2^Q is exact in fp32; the Doppler column is the index
+                const int16_t* p = stageh + ic * kRawCols;
+                raw[r2][0] = (float)p[0] * c.xyz_scale; raw[r2][1] = (float)p[1] * c.xyz_scale;
+                raw[r2][2] = (float)p[2] * c.xyz_scale; raw[r2][3] = (float)p[3]; raw[r2][4] = (float)p[4];
+            } else {
 #pragma unroll
-            for (int k = 0; k < kRawCols; ++k) raw[r2][k] = stagef[ic * kRawCols + k];
+                for (int k = 0; k < kRawCols; ++k) raw[r2][k] = stagef[ic * kRawCols + k];
+            }
             world_from_raw(c, raw[r2][0], raw[r2][1], raw[r2][2], raw[r2][3], w[r2]);
             keep[r2] = i < N && (w[r2][2] <= c.z_max) && (w[r2][2] > 0.0) && (w[r2][1] > 0.0);   // Utils.py:423-427
         }

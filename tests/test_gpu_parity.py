@@ -484,6 +484,51 @@ def test_throughput_mode_results_are_bit_identical_to_serial_mode():
     assert na.sum() > S and np.array_equal(na, nb) and ta.tobytes() == tb.tobytes()
 
 
+def test_int16_lattice_input_and_run_frames_equal_the_fp32_path():
+    """MMW_STEP_INPUT_I16: rows as the sensor reports them (int16 x, y, z in Q9, dopplerIdx, peakVal; 10 bytes per
+    point) give bit for bit what the fp32 rows of the same lattice values give; mmw_run_frames (the replay loop in C,
+    throughput mode) gives what stepping frame by frame gives."""
+    S, F, RES = 24, 16, 0.0626302709636043
+    batches = synth.gen_batch(list(range(900, 900 + S)), F)
+    W = pw.make_pose_weights(pw.VARIANT_3D)
+    cfg = default_config(doppler_res=RES, xyz_q_format=9)
+    f32, i16 = [], []
+    for b in batches:
+        p = b.points.astype(np.float64)
+        q = np.stack([np.rint(p[:, 0] * 512), np.rint(p[:, 1] * 512), np.rint(p[:, 2] * 512), np.rint(p[:, 3] / 0.0626),
+                      p[:, 4]], axis=1)
+        assert np.array_equal(q[:, :3] / 512, p[:, :3]) and np.abs(q).max() < 32768
+        i16.append(np.ascontiguousarray(q.astype(np.int16)))
+        f32.append(np.ascontiguousarray(np.stack([q[:, 0] / 512, q[:, 1] / 512, q[:, 2] / 512, q[:, 3], q[:, 4]], 1).astype(np.float32)))
+    n = S * 8 * _lib.RESULT_FLOATS
+    a, b_, c_ = BatchedTracker(S, config=cfg), BatchedTracker(S, config=cfg), BatchedTracker(S, config=cfg)
+    for t in (a, b_, c_):
+        t.load_pose_weights(W)
+    ra, rb = np.zeros((F, n), np.float32), np.zeros((F, n), np.float32)
+    for f, bt in enumerate(batches):
+        a.step(f32[f], bt.offsets, bt.dt, pose=True)
+        a.wait_results(a.read_results_async(ra[f]))
+        b_.step(i16[f], bt.offsets, bt.dt, pose=True)
+        b_.wait_results(b_.read_results_async(rb[f]))
+    assert ra.tobytes() == rb.tobytes()
+    ta, na = a.tracks(); tb, nb = b_.tracks()
+    assert na.sum() > S and ta.tobytes() == tb.tobytes()
+    rc = np.zeros((F, n), np.float32)
+    rows = np.concatenate(i16)
+    fro = np.cumsum([0] + [len(x) for x in i16]).astype(np.int64)
+    c_.run_frames(rows, fro, np.stack([bt.offsets for bt in batches]), np.stack([bt.dt for bt in batches]), rc)
+    assert rc.tobytes() == ra.tobytes()
+    # ... and against the oracle on the float64 values the lattice stands for
+    so = mo.SceneOracle(pose_weights=W)
+    for f, bt in enumerate(batches):
+        fr = f32[f][bt.offsets[3]:bt.offsets[4]].astype(np.float64)
+        fr[:, 3] *= RES
+        rec = so.step(fr, bt.dt[3])
+    assert [t["id"] for t in rec["tracks"]] == [int(x) for x in ta[3]["id"][:na[3]]]
+    for k, t in enumerate(rec["tracks"]):
+        np.testing.assert_allclose(ta[3, k]["x"], t["x"], rtol=STATE_RTOL, atol=STATE_ATOL)
+
+
 def test_pose_row_scan_folded_vs_separate_kernel():
     """The pose-row scan inside pose_feature_kernel (default, S <= 4096) and pose_index_kernel (S > 4096) lay the
     rows out identically."""
