@@ -51,6 +51,8 @@ struct mmw_ctx {
     unsigned long long* d_phase = nullptr;
     bool phase_clocks = false;
     uint8_t* d_ring_hist = nullptr;   // [S][kRing][kHistBytes] cell histograms of the global ring's frames (grid screen)
+    int32_t* h_defer_hint = nullptr;  // pinned + mapped: work-list length of the last finished step (sizes dbscan_big's grid)
+    int32_t* d_defer_hint = nullptr;  //   its device alias
     int32_t* d_scene_stats = nullptr; // [S][8] per-scene counters of the last step (summed on the device)
     int32_t* d_defer = nullptr;      // [2 + S + S]: counter, the work list of dbscan_big_kernel, pose rows per scene, finished-CTA ticket
     bool fold_pose_index = true;     // pose-row scan inside pose_feature_kernel (S <= 4096) instead of pose_index_kernel
@@ -207,6 +209,7 @@ int mmw_destroy(mmw_ctx* x) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     pose_tc_free(&x->tc);
+    if (x->h_defer_hint) cudaFreeHost(x->h_defer_hint);
     for (int i = 0; i < 2; ++i)
         for (cudaEvent_t e : {x->h2d_done[i], x->stage_free[i], x->packed[i], x->results_done[i], x->feat_done[i],
                               x->packt_done[i], x->pose_done[i]})
@@ -350,6 +353,13 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
     ALLOC(x->d_phase, sizeof(unsigned long long) * (16 + 3 * S + 16));
     ALLOC(x->d_defer, sizeof(int32_t) * (2 + 2 * S));
     ALLOC(x->d_scene_stats, sizeof(int32_t) * 8 * S);
+    if (cudaHostAlloc((void**)&x->h_defer_hint, sizeof(int32_t), cudaHostAllocMapped) == cudaSuccess) {
+        *x->h_defer_hint = 0;
+        if (cudaHostGetDevicePointer((void**)&x->d_defer_hint, x->h_defer_hint, 0) != cudaSuccess) x->d_defer_hint = nullptr;
+    } else {
+        (void)cudaGetLastError();
+        x->h_defer_hint = nullptr;
+    }
     ALLOC(x->d_ring_hist, (size_t)kRing * kHistBytes * S);
     {
         const char* env = getenv("MMW_POSE_INDEX_FOLD");
@@ -578,6 +588,7 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     a.defer_list = x->d_defer + 1;
     a.pose_cnt = x->d_defer + 1 + x->S;
     a.scene_stats = x->d_scene_stats;
+    a.defer_hint = x->d_defer_hint;
     a.ring_hist = x->d_ring_hist;
     const bool pipelined = (flags & MMW_STEP_PIPELINE) != 0;
     if (pipelined) {
@@ -591,7 +602,8 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     prof_mark(x, MMW_K_STEP);
     CK(launch_step(a, x->stream));
     prof_mark(x, MMW_K_DBSCAN_BIG);
-    CK(launch_dbscan_big(a, x->stream));
+    // one CTA per deferred scene of the last step the device has reported, within [16, 148]
+    CK(launch_dbscan_big(a, x->stream, x->h_defer_hint ? *(volatile int32_t*)x->h_defer_hint : 16));
     x->launches += 2;          // step_kernel + dbscan_big_kernel
     prof_mark(x, -1);
     int rc = MMW_OK;

@@ -98,6 +98,8 @@ struct StepArgs {
     int32_t* defer_list;       // [S] scenes whose DBSCAN + spawn is left to dbscan_big_kernel, or nullptr
     int32_t* defer_count;      // device counter of defer_list; dbscan_big_kernel's last CTA zeroes it for the next step
     int32_t* defer_done;       // CTAs of dbscan_big_kernel that have finished (ticket for that reset)
+    int32_t* defer_hint;       // mapped host word: the work-list length of this step, read by the host (without any
+                               //   synchronisation) to size dbscan_big_kernel's grid of the NEXT steps; or nullptr
     int32_t* pose_cnt;         // [S] tracks of the scene if the frame ran track(), else 0: the pose-row scan reads this
     uint8_t* ring_hist;        // [S][kRing][kHistBytes] cell histograms of the global ring's frames, by physical slot
     int32_t* scene_stats;      // [S][8] this frame's N, M, U, Bf (if DBSCAN ran), tracks, ring rows written, ran, 0:

@@ -62,6 +62,6 @@ cudaError_t launch_fc2(const Fc2Args& a, int grid, cudaStream_t st);
 int step_smem_bytes(int ncap, int tcap);
 int dbscan_big_smem_bytes(int ncap);
 cudaError_t launch_step(const StepArgs& a, cudaStream_t stream);
-cudaError_t launch_dbscan_big(const StepArgs& a, cudaStream_t stream);
+cudaError_t launch_dbscan_big(const StepArgs& a, cudaStream_t stream, int grid = 16);
 
 }  // namespace mmw

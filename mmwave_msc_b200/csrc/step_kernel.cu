@@ -1058,6 +1058,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
     if (tid == 0) {
         __threadfence();
         if (atomicAdd(a.defer_done, 1) == (int)gridDim.x - 1) {
+            if (a.defer_hint != nullptr) *a.defer_hint = n_defer;     // zero-copy write to pinned host memory
             *a.defer_count = 0;
             *a.defer_done = 0;
         }
@@ -1075,13 +1076,17 @@ cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_dbscan_big(const StepArgs& a, cudaStream_t stream) {
+// grid: 16 CTAs cover the couple of scenes per frame in which a cluster forms (C2); dense configurations keep every
+// scene's DBSCAN busy (untracked targets stay in the residue) and get one CTA per SM -- chosen by the caller from the
+// work-list length of an earlier step (StepArgs::defer_hint), which only affects speed, never results.
+cudaError_t launch_dbscan_big(const StepArgs& a, cudaStream_t stream, int grid) {
     if (a.defer_count == nullptr) return cudaSuccess;
     const int big_smem = dbscan_big_smem_bytes(a.cfg.ncap);
     static int configured[kMaxDevices] = {0};
     cudaError_t e = ensure_smem_attr(reinterpret_cast<const void*>(dbscan_big_kernel), configured, big_smem);
     if (e != cudaSuccess) return e;
-    return launch_pdl(dbscan_big_kernel, dim3(16), dim3(kBigThreads), big_smem, stream, dim3(1, 1, 1), a);
+    return launch_pdl(dbscan_big_kernel, dim3(grid < 16 ? 16 : (grid > 148 ? 148 : grid)), dim3(kBigThreads), big_smem, stream,
+                      dim3(1, 1, 1), a);
 }
 
 }  // namespace mmw
