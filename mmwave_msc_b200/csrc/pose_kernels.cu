@@ -49,12 +49,15 @@ __global__ void __launch_bounds__(1024) pose_index_kernel(SceneRec* scenes, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// One warp per track.  Feature rows are relative to the CURRENT centroid for every ring frame (Q21),
-// intensity is normalised before padding so pads stay exactly 0, rows are sorted by x with the canonical
-// stable (x, row index) order, frames absent from the ring stay zero.
-__global__ void __launch_bounds__(128) pose_feature_kernel(PoseFeatArgs a) {
-    __shared__ double keys[4][kFeatPts];
-    __shared__ float vals[4][kFeatPts][kRawCols];
+// One warp per (track, ring frame): the 3 frames of a track are independent, so a scene with two tracks keeps six
+// warps busy at once instead of two warps walking three frames each (round 1: 21 us of dependent round trips for
+// 27 MB of traffic).  Feature rows are relative to the CURRENT centroid for every ring frame (Q21), intensity is
+// normalised before padding so pads stay exactly 0, rows are sorted by x with the canonical stable (x, row index)
+// order, frames absent from the ring stay zero.  Each lane owns points lane and lane + 32 of the frame: their values
+// stay in registers, only the 64 sort keys go through shared memory, and both ranks come out of one pass over them.
+constexpr int kFeatWarps = 6;
+__global__ void __launch_bounds__(kFeatWarps * 32, 7) pose_feature_kernel(PoseFeatArgs a) {
+    __shared__ __align__(16) double keys[kFeatWarps][kFeatPts];
     const int s = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_wait();                          // the tracker kernels have completed
@@ -64,14 +67,16 @@ __global__ void __launch_bounds__(128) pose_feature_kernel(PoseFeatArgs a) {
     if (a.pose_cnt != nullptr) {
         // exclusive scan value of this scene: every CTA adds up the (at most S) counts in front of it; the order of
         // the integer additions does not matter, so the row layout is the same as pose_index_kernel's
-        __shared__ int wpart[4];
+        __shared__ int wpart[kFeatWarps];
         int part = 0;
-        for (int i = threadIdx.x; i < s; i += 128) part += __ldg(a.pose_cnt + i);
+        for (int i = threadIdx.x; i < s; i += kFeatWarps * 32) part += __ldg(a.pose_cnt + i);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) wpart[warp] = part;
         __syncthreads();
-        pose_base = wpart[0] + wpart[1] + wpart[2] + wpart[3];
+        pose_base = 0;
+#pragma unroll
+        for (int w = 0; w < kFeatWarps; ++w) pose_base += wpart[w];
         if (threadIdx.x == 0) {
             if (s == a.n_scenes - 1) {
                 const int total = pose_base + (sc.last_ran ? sc.n_tracks : 0);
@@ -83,80 +88,84 @@ __global__ void __launch_bounds__(128) pose_feature_kernel(PoseFeatArgs a) {
     if (!sc.last_ran) return;
     const DevConfig& c = a.cfg;
     const int nfr = c.ring_size;
-    for (int k = warp; k < sc.n_tracks; k += 4) {
+    const int items = sc.n_tracks * nfr;
+    for (int item = warp; item < items; item += kFeatWarps) {
+        const int k = item / nfr, f = item - k * nfr;
         const TrackRec* t = a.tracks + (size_t)s * c.tcap + k;
         const int row = pose_base + k;
-        const double cx = t->centroid[0], cy = t->centroid[1];
         const int slot = t->slot, rn = t->ring_n, rh = t->ring_head;
-        if (lane == 0) {
+        if (f == 0 && lane == 0) {
             a.row_scene[row] = s;
             a.row_track[row] = k;
             a.row_slot[row] = slot;
         }
-        float* out = a.feats + (size_t)row * nfr * kFeatPts * kRawCols;
+        float* out = a.feats + ((size_t)row * nfr + f) * (kFeatPts * kRawCols);
         uint4* pk = a.packed ? reinterpret_cast<uint4*>(a.packed + (size_t)row * nfr * kFeatPts * 16) : nullptr;
-        for (int f = 0; f < nfr; ++f) {
-            if (f >= rn) {
-                for (int e = lane; e < kFeatPts * kRawCols; e += 32) out[f * kFeatPts * kRawCols + e] = 0.f;
-                if (pk)
-                    for (int e = lane; e < kFeatPts * 2; e += 32) pk[f * kFeatPts * 2 + e] = make_uint4(0, 0, 0, 0);
-                continue;
-            }
-            const int phys = ring_wrap(rh + f, c.ring_size);
-            const int cnt = t->ring_cnt[phys];
-            const float* src = a.track_ring + (((size_t)s * c.tcap + slot) * kRing + phys) * (kFeatPts * kRawCols);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = lane + 32 * h;
-                double key = 0.0;
-                float v[kRawCols] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                if (i < cnt) {
-                    const float x = src[i * kRawCols + 0], y = src[i * kRawCols + 1], z = src[i * kRawCols + 2];
-                    const float d = src[i * kRawCols + 3], p = src[i * kRawCols + 4];
-                    double yw, zw;
-                    world_yz(c, (double)y, (double)z, yw, zw);
-                    key = __dsub_rn((double)x, cx);
-                    v[0] = (float)key;
-                    v[1] = (float)__dsub_rn(yw, cy);
-                    v[2] = (float)zw;
-                    v[3] = (float)__dmul_rn((double)d, c.doppler_res);
-                    v[4] = (float)__ddiv_rn(__dsub_rn((double)p, c.int_mu), c.int_std);
-                }
-                keys[warp][i] = key;
-#pragma unroll
-                for (int q = 0; q < kRawCols; ++q) vals[warp][i][q] = v[q];
-            }
-            __syncwarp();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = lane + 32 * h;
-                const double key = keys[warp][i];
-                int rank = 0;
-                for (int q = 0; q < kFeatPts; ++q) {
-                    const double kq = keys[warp][q];
-                    rank += (kq < key || (kq == key && q < i)) ? 1 : 0;
-                }
-#pragma unroll
-                for (int q = 0; q < kRawCols; ++q)
-                    out[(f * kFeatPts + rank) * kRawCols + q] = vals[warp][i][q];
-                if (pk) {
-                    __align__(16) __nv_bfloat16 pv[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) pv[q] = __float2bfloat16_rn(0.f);
-#pragma unroll
-                    for (int q = 0; q < kRawCols; ++q) {
-                        const float x = vals[warp][i][q];
-                        pv[q] = __float2bfloat16_rn(x);
-                        pv[8 + q] = __float2bfloat16_rn(x - __bfloat162float(pv[q]));
-                    }
-                    // slab order of the tensor-core convs: [row][d = f][w][chunk][h][8]  (pose_tc.cu)
-                    const int ph = rank >> 3, pw_ = rank & 7;
-                    pk[((f * 8 + pw_) * 2 + 0) * 8 + ph] = reinterpret_cast<const uint4*>(pv)[0];
-                    pk[((f * 8 + pw_) * 2 + 1) * 8 + ph] = reinterpret_cast<const uint4*>(pv)[1];
-                }
-            }
-            __syncwarp();
+        if (f >= rn) {
+            for (int e = lane; e < kFeatPts * kRawCols; e += 32) out[e] = 0.f;
+            if (pk)
+                for (int e = lane; e < kFeatPts * 2; e += 32) pk[f * kFeatPts * 2 + e] = make_uint4(0, 0, 0, 0);
+            continue;
         }
+        const double cx = t->centroid[0], cy = t->centroid[1];
+        const int phys = ring_wrap(rh + f, c.ring_size);
+        const int cnt = t->ring_cnt[phys];
+        const float* src = a.track_ring + (((size_t)s * c.tcap + slot) * kRing + phys) * (kFeatPts * kRawCols);
+        float v[2][kRawCols];
+        double key[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            key[h] = 0.0;
+#pragma unroll
+            for (int q = 0; q < kRawCols; ++q) v[h][q] = 0.f;
+            if (i < cnt) {
+                const float x = src[i * kRawCols + 0], y = src[i * kRawCols + 1], z = src[i * kRawCols + 2];
+                const float d = src[i * kRawCols + 3], p = src[i * kRawCols + 4];
+                double yw, zw;
+                world_yz(c, (double)y, (double)z, yw, zw);
+                key[h] = __dsub_rn((double)x, cx);
+                v[h][0] = (float)key[h];
+                v[h][1] = (float)__dsub_rn(yw, cy);
+                v[h][2] = (float)zw;
+                v[h][3] = (float)__dmul_rn((double)d, c.doppler_res);
+                v[h][4] = (float)__ddiv_rn(__dsub_rn((double)p, c.int_mu), c.int_std);
+            }
+            keys[warp][i] = key[h];
+        }
+        __syncwarp();
+        int rank[2] = {0, 0};
+        const double2* k2 = reinterpret_cast<const double2*>(keys[warp]);
+#pragma unroll 8
+        for (int q2 = 0; q2 < kFeatPts / 2; ++q2) {
+            const double2 kq = k2[q2];                   // broadcast read: keys 2 q2 and 2 q2 + 1
+            const int q = 2 * q2;
+            rank[0] += (kq.x < key[0] || (kq.x == key[0] && q < lane)) ? 1 : 0;
+            rank[0] += (kq.y < key[0] || (kq.y == key[0] && q + 1 < lane)) ? 1 : 0;
+            rank[1] += (kq.x < key[1] || (kq.x == key[1] && q < lane + 32)) ? 1 : 0;
+            rank[1] += (kq.y < key[1] || (kq.y == key[1] && q + 1 < lane + 32)) ? 1 : 0;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int q = 0; q < kRawCols; ++q) out[rank[h] * kRawCols + q] = v[h][q];
+            if (pk) {
+                __align__(16) __nv_bfloat16 pv[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) pv[q] = __float2bfloat16_rn(0.f);
+#pragma unroll
+                for (int q = 0; q < kRawCols; ++q) {
+                    const float x = v[h][q];
+                    pv[q] = __float2bfloat16_rn(x);
+                    pv[8 + q] = __float2bfloat16_rn(x - __bfloat162float(pv[q]));
+                }
+                // slab order of the tensor-core convs: [row][d = f][w][chunk][h][8]  (pose_tc.cu)
+                const int ph = rank[h] >> 3, pw_ = rank[h] & 7;
+                pk[((f * 8 + pw_) * 2 + 0) * 8 + ph] = reinterpret_cast<const uint4*>(pv)[0];
+                pk[((f * 8 + pw_) * 2 + 1) * 8 + ph] = reinterpret_cast<const uint4*>(pv)[1];
+            }
+        }
+        __syncwarp();                    // the keys are reused by this warp's next item
     }
 }
 
@@ -379,7 +388,7 @@ cudaError_t launch_pose_features(const PoseFeatArgs& a, int S, cudaStream_t st) 
     static int configured[kMaxDevices] = {0};   // same shared-memory carve-out as its neighbours in the step
     cudaError_t e = ensure_smem_attr(reinterpret_cast<const void*>(pose_feature_kernel), configured, -1);
     if (e != cudaSuccess) return e;
-    return launch_pdl(pose_feature_kernel, dim3(S), dim3(128), 0, st, dim3(1, 1, 1), a);
+    return launch_pdl(pose_feature_kernel, dim3(S), dim3(kFeatWarps * 32), 0, st, dim3(1, 1, 1), a);
 }
 
 }  // namespace mmw

@@ -412,11 +412,57 @@ struct GemmTcArgs {
 
 constexpr int kGemmThreads = 192;
 constexpr int kBK = 64;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+
+// Tail of dense 2: the 57 outputs of the tile's rows are staged row-major in shared memory (stg); 128 epilogue threads
+// (et = 0..127, warp quadrant q) write them out coalesced, scatter them to the tracks' keypoint slots and, in
+// throughput mode, finish the packed result records of the frame.
+__device__ __forceinline__ void gemm_store_keypoints(const GemmTcArgs& a, const float* stg, int m0, int rows, int q,
+                                                     int lane, int et) {
+    const int nrow = min(128, rows - m0);
+    float* o = a.out + (size_t)m0 * kKp;                               // rows m0.. are contiguous in out
+    for (int i = et; i < nrow * kKp; i += 128) o[i] = stg[i];
+    if (a.keypoints) {
+        for (int r = q; r < nrow; r += 4) {
+            float* kp = a.keypoints + ((size_t)a.row_scene[m0 + r] * a.tcap + a.row_slot[m0 + r]) * kKp;
+            for (int n = lane; n < kKp; n += 32) kp[n] = stg[r * kKp + n];
+        }
+    }
+    if (a.results) {
+        for (int r = q; r < nrow; r += 4) {
+            float* rec = a.results + ((size_t)a.row_scene[m0 + r] * a.tcap + a.row_track[m0 + r]) * MMW_RESULT_FLOATS;
+            for (int n = lane; n < kKp; n += 32) rec[11 + n] = stg[r * kKp + n];
+            if (lane == 0) {     // the tracker side left x[0], x[1] as two doubles in rec[68..71]
+                const double x0 = reinterpret_cast<const double*>(rec + 68)[0], x1 = reinterpret_cast<const double*>(rec + 68)[1];
+                write_fade_square(a.fade, x0, x1, stg + r * kKp, rec);
+            }
+        }
+    }
+}
 template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() { return STAGES * (2 * 128 * kBK * 2 + 2 * BN * kBK * 2) + 1024 + 256 + 3 * BN * 4; }
 
 // MODE 0: out = split(BN(relu(acc + bias)))      MODE 1: out = acc + bias (first 57 columns), scattered to tracks
-template <int BN, int STAGES, int MODE>
+// KS > 1 (MODE 1, dense 2): split K over a cluster of KS CTAs (blockIdx.x = cluster rank = K slice).  Dense 2 has only
+// ceil(rows / 128) row tiles -- 16 CTAs at C2 -- and each of them streamed 1.1 MB of operands through ONE SM's L2 port
+// (14 us of main loop for 0.34 GFLOP).  With the split, KS times as many SMs pull a KS-th each; the partial
+// accumulators go TMEM -> registers -> the leader's shared memory (st.shared::cluster into the idle pipeline stages)
+// and the leader adds them in rank order: the sum of a row does not depend on where the row sits in the batch.
+template <int BN, int STAGES, int MODE, int KS = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl,
@@ -439,7 +485,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = a.K / kBK;
+    static_assert(KS == 1 || MODE == 1, "the K split is written for dense 2");
+    const int ks = KS > 1 ? (int)blockIdx.x : 0;         // cluster rank (cluster = (KS, 1, 1), gridDim.x = KS)
+    const int nkb = a.K / kBK / KS, kb0 = ks * nkb;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah) : "memory");
@@ -467,7 +515,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                 unsigned char* st = smem + s * STAGE_BYTES;
                 if (a.dbg & 1) { mbar_arrive(&full[s]); continue; }
                 mbar_expect_tx(&full[s], STAGE_BYTES);
-                const int k0 = kb * kBK;
+                const int k0 = (kb0 + kb) * kBK;
                 tma_load_2d(st, &map_ah, &full[s], k0, m0);
                 tma_load_2d(st + A_BYTES, &map_al, &full[s], k0, m0);
                 tma_load_2d(st + 2 * A_BYTES, &map_wh, &full[s], k0, n0);
@@ -497,6 +545,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
             }
             umma_commit(tmem_full);
         }
+    } else if (KS > 1) {
+        // accumulators of this K slice into registers; the exchange follows below, outside the role branches
     } else {
         const int q = warp & 3;
         // bias / BatchNorm constants of this column tile into shared memory while the main loop runs
@@ -545,26 +595,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         }
         if (MODE == 1) {
             asm volatile("bar.sync 1, 128;" ::: "memory");                     // the four epilogue warps
-            const float* stg = reinterpret_cast<const float*>(smem);
-            const int nrow = min(BM, rows - m0), et = threadIdx.x - 64;
-            float* o = a.out + (size_t)m0 * kKp;                               // rows m0.. are contiguous in out
-            for (int i = et; i < nrow * kKp; i += 128) o[i] = stg[i];
-            if (a.keypoints) {
-                for (int r = q; r < nrow; r += 4) {
-                    float* kp = a.keypoints + ((size_t)a.row_scene[m0 + r] * a.tcap + a.row_slot[m0 + r]) * kKp;
-                    for (int n = lane; n < kKp; n += 32) kp[n] = stg[r * kKp + n];
+            gemm_store_keypoints(a, reinterpret_cast<const float*>(smem), m0, rows, q, lane, threadIdx.x - 64);
+        }
+    }
+    if (KS > 1) {
+        static_assert(KS == 1 || BN == 64, "split epilogue: 64 accumulator columns per row");
+        static_assert(KS == 1 || 32768 + (KS - 1) * 32768 <= STAGES * STAGE_BYTES, "partials fit in the pipeline stages");
+        const int q = warp & 3, r = q * 32 + lane;           // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+        uint32_t v0[32], v1[32];
+        if (warp >= 2) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16), v0);
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + 32u, v1);
+            tc_fence_before();
+        }
+        // every CTA of the cluster has finished its MMAs: the leader's pipeline stages are free to receive the partials
+        cluster_sync_all();
+        // partials in the leader: [rank - 1][column group of 4][row][4] floats from byte 32768 on (a warp's 32 rows of
+        // one column group are 512 contiguous bytes); the first 32 KB stay free for the coalesced output staging
+        float* part = reinterpret_cast<float*>(smem + 32768);
+        if (warp >= 2 && ks != 0) {
+            const uint32_t base = mapa_shared(smem_u32(part + (size_t)(ks - 1) * 8192 + r * 4), 0);
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+                const uint32_t* v = g < 8 ? v0 : v1;
+                const int j = (g & 7) * 4;
+                asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(g * 2048)),
+                             "r"(v[j]), "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
+                             : "memory");
+            }
+        }
+        cluster_sync_all();
+        if (warp >= 2 && ks == 0) {
+            float* stg = reinterpret_cast<float*>(smem);
+            const float4* p4 = reinterpret_cast<const float4*>(part);
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+                const uint32_t* v = g < 8 ? v0 : v1;
+                const int j = (g & 7) * 4;
+                float acc[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                __uint_as_float(v[j + 3])};
+#pragma unroll
+                for (int o = 0; o < KS - 1; ++o) {                       // fixed order: rank 1, 2, ...
+                    const float4 t = p4[(size_t)o * 2048 + g * 128 + r];
+                    acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int n = g * 4 + e;
+                    if (n < kKp) stg[r * kKp + n] = acc[e] + __ldg(a.bias + n);
                 }
             }
-            if (a.results) {
-                for (int r = q; r < nrow; r += 4) {
-                    float* rec = a.results + ((size_t)a.row_scene[m0 + r] * a.tcap + a.row_track[m0 + r]) * MMW_RESULT_FLOATS;
-                    for (int n = lane; n < kKp; n += 32) rec[11 + n] = stg[r * kKp + n];
-                    if (lane == 0) {     // the tracker side left x[0], x[1] as two doubles in rec[68..71]
-                        const double x0 = reinterpret_cast<const double*>(rec + 68)[0], x1 = reinterpret_cast<const double*>(rec + 68)[1];
-                        write_fade_square(a.fade, x0, x1, stg + r * kKp, rec);
-                    }
-                }
-            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");                     // the four epilogue warps
+            gemm_store_keypoints(a, stg, m0, rows, q, lane, threadIdx.x - 64);
         }
     }
     tc_fence_before();
@@ -586,20 +670,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
 //   * the leader's elected thread issues every MMA; tcgen05.commit multicasts the "stage free" / "accumulator
 //     ready" arrivals to the barriers of both CTAs
 //   * each CTA's epilogue warps read the CTA's own TMEM (its 128 rows x BN columns)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
 // dst in this CTA's shared memory, completion bytes on `bar_cluster` (a shared::cluster address, the leader's barrier)
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
     asm volatile(
@@ -1010,6 +1080,7 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
         if (verbose) fprintf(stderr, "[mmw] dense 1: %s\n", im->pair ? "cta_group::2 pair kernel" : "single-CTA kernel");
     }
     set_smem((const void*)gemm_tc_kernel<64, 4, 1>, gemm_smem_bytes<64, 4>());
+    set_smem((const void*)gemm_tc_kernel<64, 4, 1, 4>, gemm_smem_bytes<64, 4>());
     if (e != cudaSuccess) { g_tc_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
     t->ready = true;
     return 0;
@@ -1098,9 +1169,16 @@ int pose_tc_fc2(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
     GemmTcArgs g{r.n_rows, r.bd2, nullptr, nullptr, nullptr, nullptr, r.out, r.keypoints, r.row_scene, r.row_slot,
                  im->H, 64, r.tcap, im->dbg, r.results, r.row_track, r.fade};
-    const cudaError_t le = launch_pdl(gemm_tc_kernel<64, 4, 1>, dim3(1, (max_rows + 127) / 128), dim3(kGemmThreads),
-                                      gemm_smem_bytes<64, 4>(), st, dim3(1, 1, 1), im->m_hh, im->m_hl, im->m_w2h,
-                                      im->m_w2l, g);
+    // K split over a cluster of 4 CTAs per row tile whenever the K blocks divide (1536 / 64 = 24, 512 / 64 = 8);
+    // MMW_FC2_SPLIT=0 keeps the single-CTA kernel (the comparison point)
+    static const bool split = [] { const char* e = getenv("MMW_FC2_SPLIT"); return !e || atoi(e) != 0; }();
+    cudaError_t le;
+    if (split && (im->H / kBK) % 4 == 0)
+        le = launch_pdl(gemm_tc_kernel<64, 4, 1, 4>, dim3(4, (max_rows + 127) / 128), dim3(kGemmThreads),
+                        gemm_smem_bytes<64, 4>(), st, dim3(4, 1, 1), im->m_hh, im->m_hl, im->m_w2h, im->m_w2l, g);
+    else
+        le = launch_pdl(gemm_tc_kernel<64, 4, 1>, dim3(1, (max_rows + 127) / 128), dim3(kGemmThreads),
+                        gemm_smem_bytes<64, 4>(), st, dim3(1, 1, 1), im->m_hh, im->m_hl, im->m_w2h, im->m_w2l, g);
     if (le != cudaSuccess) { g_tc_err = std::string("dense 2 launch: ") + cudaGetErrorString(le); return -1; }
     if (n_launches) *n_launches = 1;
     return 0;

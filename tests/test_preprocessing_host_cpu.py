@@ -5,6 +5,8 @@ without a GPU.  (The same driver against the real device context: tests/test_gpu
 import copy
 import os
 
+import types
+
 import numpy as np
 import pytest
 
@@ -21,7 +23,11 @@ class _OracleTracker:
         self.scenes = [mo.SceneOracle() for _ in range(n_scenes)]
         self.ran = [False] * n_scenes
         self.log = []
+        self.cfg = types.SimpleNamespace(doppler_res=1.0)
         _OracleTracker.instances.append(self)
+
+    def set_doppler_resolution(self, res):
+        self.cfg.doppler_res = float(res)
 
     def ring_pop(self, scene):
         self.log.append(("pop", scene))
@@ -30,7 +36,8 @@ class _OracleTracker:
     def step(self, points, offsets, dt, pose=True, record_labels=False):
         assert not pose
         for s, o in enumerate(self.scenes):
-            raw = points[offsets[s]:offsets[s + 1]]
+            raw = np.asarray(points[offsets[s]:offsets[s + 1]], np.float64).copy()
+            raw[:, 3] *= self.cfg.doppler_res            # the rows carry the Doppler index (the device multiplies in float64)
             self.ran[s] = False
             if len(raw):
                 self.ran[s] = bool(o.step(raw, dt[s])["ran"])
