@@ -340,6 +340,29 @@ def _timed_device_steps(bt, host_batches, prime, warm, K, flush, local):
     return np.array(ms)
 
 
+def _timed_device_pipeline(bt, host_batches, warm, K, local):
+    """Throughput mode (MMW_STEP_PIPELINE) on a context that has already been primed: device-resident inputs, K steps
+    on frames never read before inside one pair of CUDA events (the second after the streams have joined)."""
+    import torch
+    from mmwave_msc_b200 import _lib
+    stream = torch.cuda.ExternalStream(bt.stream, device=local)
+    dev = [(torch.from_numpy(p).cuda(), torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda())
+           for p, o, d in host_batches[:warm + K]]
+    res = torch.empty(bt.S * bt.tcap * _lib.RESULT_FLOATS, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    for p, o, d in dev[:warm]:
+        bt.step_device(p.data_ptr(), o.data_ptr(), d.data_ptr(), p.shape[0], pose=True, pipeline=True)
+    bt.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for p, o, d in dev[warm:]:
+        bt.step_device(p.data_ptr(), o.data_ptr(), d.data_ptr(), p.shape[0], pose=True, pipeline=True)
+    bt.pack_results(res.data_ptr())               # serial-mode call: the main stream waits for the pose stream first
+    e1.record(stream)
+    bt.sync()
+    return e0.elapsed_time(e1) / K
+
+
 def other_configs(batches, weights3d, flush, local):
     """The BASELINE.json configurations that are not the headline workload, on ONE GPU (same timing protocol):
     C3 dense 8.5 m (1000 points/frame, 10 targets, TR_MAX_TRACKS = 10), C4 pose regression alone (65 536 maps,
@@ -350,27 +373,31 @@ def other_configs(batches, weights3d, flush, local):
     PRIME, WARM, K = 12, 3, 8
     out = {}
     # C3
-    gen = synth.gen_batch(range(200_000, 200_256), PRIME + WARM + K, synth.SceneSpec.dense())
+    gen = synth.gen_batch(range(200_000, 200_256), PRIME + 2 * (WARM + K), synth.SceneSpec.dense())
     tiled = _tile_batches(gen, 4)
     bt = BatchedTracker(1024, max_points=1024, max_tracks=16, device=local, config=default_config(tr_max_tracks=10))
     bt.load_pose_weights(weights3d)
     ms = _timed_device_steps(bt, tiled, PRIME, WARM, K, flush, local)
     _, nt = bt.tracks()
+    tp = _timed_device_pipeline(bt, tiled[PRIME + WARM + K:], WARM, K, local)
     out["C3"] = {"what": "dense 8.5 m config: 1024 scenes (256 generated x 4), 1000 points/frame, 10 targets, "
                          "TR_MAX_TRACKS = 10, full path incl. pose", "scenes": 1024,
                  "points_per_scene_frame": float(np.mean([t[0].shape[0] for t in tiled]) / 1024),
                  "tracks_per_scene": float(nt.mean()), "ms_per_step": float(ms.mean()),
-                 "scene_frames_per_s": float(1024 / (ms.mean() / 1e3))}
+                 "scene_frames_per_s": float(1024 / (ms.mean() / 1e3)),
+                 "throughput_mode": {"ms_per_step": tp, "scene_frames_per_s": float(1024 / (tp / 1e3))}}
     bt.close()
     # C5 on one GPU: the headline run's own scenes, eight times side by side
-    tiled = _tile_batches(batches[:PRIME + WARM + K], 8)
+    tiled = _tile_batches(batches[:PRIME + 2 * (WARM + K)], 8)
     bt = BatchedTracker(8192, max_points=256, max_tracks=8, device=local,
                         config=default_config(doppler_res=DOPPLER_RES, xyz_q_format=9))
     bt.load_pose_weights(weights3d)
     ms = _timed_device_steps(bt, tiled, PRIME, WARM, K, flush, local)
+    tp = _timed_device_pipeline(bt, tiled[PRIME + WARM + K:], WARM, K, local)
     out["C5_one_gpu"] = {"what": "8192 scenes on ONE GPU (the 1024 generated scenes x 8), full path incl. pose",
                          "scenes": 8192, "ms_per_step": float(ms.mean()),
-                         "scene_frames_per_s": float(8192 / (ms.mean() / 1e3))}
+                         "scene_frames_per_s": float(8192 / (ms.mean() / 1e3)),
+                         "throughput_mode": {"ms_per_step": tp, "scene_frames_per_s": float(8192 / (tp / 1e3))}}
     # C4 on the same context size: 65 536 feature maps through the 2-D net
     bt.close()
     N = 65536

@@ -65,6 +65,8 @@ struct mmw_ctx {
     // throughput mode (MMW_STEP_PIPELINE): pose network on its own stream, its inputs double-buffered
     cudaStream_t pose_stream = nullptr;
     cudaEvent_t feat_done[2] = {nullptr, nullptr}, packt_done[2] = {nullptr, nullptr}, pose_done[2] = {nullptr, nullptr};
+    cudaEvent_t conv_done[2] = {nullptr, nullptr};   // the convolutions of a pipelined frame have run (gate of the next tracker step)
+    int pipe_gate = 0;               // MMW_PIPE_GATE: 1 = the tracker of frame k+1 starts when the convolutions of frame k are done
     int32_t *d_row_scene2 = nullptr, *d_row_track2 = nullptr, *d_row_slot2 = nullptr;
     int* d_pose_total2 = nullptr;
     unsigned pipe_idx = 0;           // pipelined steps so far
@@ -212,7 +214,7 @@ int mmw_destroy(mmw_ctx* x) {
     if (x->h_defer_hint) cudaFreeHost(x->h_defer_hint);
     for (int i = 0; i < 2; ++i)
         for (cudaEvent_t e : {x->h2d_done[i], x->stage_free[i], x->packed[i], x->results_done[i], x->feat_done[i],
-                              x->packt_done[i], x->pose_done[i]})
+                              x->packt_done[i], x->pose_done[i], x->conv_done[i]})
             if (e) cudaEventDestroy(e);
     if (x->h2d_stream) cudaStreamDestroy(x->h2d_stream);
     if (x->d2h_stream) cudaStreamDestroy(x->d2h_stream);
@@ -376,11 +378,13 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
             cudaEventCreateWithFlags(&x->results_done[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&x->feat_done[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&x->packt_done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&x->conv_done[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&x->pose_done[i], cudaEventDisableTiming) != cudaSuccess) {
             mmw_destroy(x);
             return fail(MMW_ERR_CUDA, "cudaEventCreate failed");
         }
     }
+    { const char* env = getenv("MMW_PIPE_GATE"); x->pipe_gate = env ? atoi(env) : 0; }
     // the pose network is the critical path of the throughput mode: its CTAs are scheduled ahead of the tracker's
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -595,6 +599,10 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
         if (!(flags & MMW_STEP_POSE) || !(x->use_tc && x->tc.ready))
             return fail(MMW_ERR_STATE, "MMW_STEP_PIPELINE needs MMW_STEP_POSE and the tensor-core pose path");
         if (flags & MMW_STEP_RECORD_LABELS) return fail(MMW_ERR_INVALID, "MMW_STEP_PIPELINE cannot record labels");
+        // The persistent convolution kernels need (almost) whole SMs: tracker CTAs that are resident when one of them
+        // starts delay its slowest CTA by up to a tracker CTA's lifetime.  With the gate the tracker of the next frame
+        // starts once the previous frame's convolutions have run, under dense 1 / dense 2, which leave room.
+        if (x->pipe_gate && x->pose_pending) CK(cudaStreamWaitEvent(x->stream, x->conv_done[(x->pipe_idx + 1) & 1], 0));
     } else {
         CK(join_pose(x));
         x->pipe_r = -1;
@@ -1156,6 +1164,7 @@ static int pipeline_pose(mmw_ctx* x) {
     int nl = 0;
     if (pose_tc_conv(&x->tc, r, P, &nl, b) != 0) return fail(MMW_ERR_CUDA, std::string("tensor-core conv: ") + pose_tc_error());
     x->launches += nl;
+    if (x->pipe_gate) CK(cudaEventRecord(x->conv_done[b], P));     // (an event between two kernels undoes their dependent launch)
     if (pose_tc_fc1(&x->tc, r, x->pose_cap, P, &nl) != 0) return fail(MMW_ERR_CUDA, std::string("tensor-core dense 1: ") + pose_tc_error());
     x->launches += nl;
     CK(cudaStreamWaitEvent(P, x->packt_done[b], 0));

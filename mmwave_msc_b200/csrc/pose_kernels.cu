@@ -6,6 +6,8 @@
 // The CUDA-core fp32 kernels in this file are the reference-exact path; the tensor-core (tcgen05) GEMM for the
 // dense contraction lives in pose_tc.cu and replaces fc1 when enabled.
 #include "mmw_internal.cuh"
+#include <cstdlib>
+
 #include "pose.cuh"
 
 namespace mmw {
@@ -57,14 +59,17 @@ __global__ void __launch_bounds__(1024) pose_index_kernel(SceneRec* scenes, int 
 // stay in registers, only the 64 sort keys go through shared memory, and both ranks come out of one pass over them.
 constexpr int kFeatWarps = 6;
 __global__ void __launch_bounds__(kFeatWarps * 32, 7) pose_feature_kernel(PoseFeatArgs a) {
-    __shared__ __align__(16) double keys[kFeatWarps][kFeatPts];
+    __shared__ __align__(16) long long keys[kFeatWarps][kFeatPts];     // order-preserving integer images of the sort keys
+    __shared__ __align__(16) float srow[kFeatWarps][kFeatPts * kRawCols];
+    __shared__ __align__(16) uint4 spk[kFeatWarps][kFeatPts * 2];
     const int s = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_wait();                          // the tracker kernels have completed
     pdl_launch_dependents();
     const SceneRec sc = a.scenes[s];
     int pose_base = sc.pose_base;
-    if (a.pose_cnt != nullptr) {
+    if (a.dbg & 1) pose_base = 2 * s;
+    else if (a.pose_cnt != nullptr) {
         // exclusive scan value of this scene: every CTA adds up the (at most S) counts in front of it; the order of
         // the integer additions does not matter, so the row layout is the same as pose_index_kernel's
         __shared__ int wpart[kFeatWarps];
@@ -111,44 +116,73 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 7) pose_feature_kernel(PoseFe
         const int phys = ring_wrap(rh + f, c.ring_size);
         const int cnt = t->ring_cnt[phys];
         const float* src = a.track_ring + (((size_t)s * c.tcap + slot) * kRing + phys) * (kFeatPts * kRawCols);
+        float* so = srow[warp];
+        {   // the frame's 64 raw rows (1280 contiguous bytes) as 80 float4 loads, not 10 strided scalar loads per lane
+            const float4* g4 = reinterpret_cast<const float4*>(src);
+            float4* s4 = reinterpret_cast<float4*>(so);
+            if (!(a.dbg & 8))
+                for (int e = lane; e < kFeatPts * kRawCols / 4; e += 32) s4[e] = __ldg(g4 + e);
+        }
+        __syncwarp();
         float v[2][kRawCols];
-        double key[2];
+        long long mkey[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int i = lane + 32 * h;
-            key[h] = 0.0;
+            double key = 0.0;
 #pragma unroll
             for (int q = 0; q < kRawCols; ++q) v[h][q] = 0.f;
             if (i < cnt) {
-                const float x = src[i * kRawCols + 0], y = src[i * kRawCols + 1], z = src[i * kRawCols + 2];
-                const float d = src[i * kRawCols + 3], p = src[i * kRawCols + 4];
+                const float x = so[i * kRawCols + 0], y = so[i * kRawCols + 1], z = so[i * kRawCols + 2];
+                const float d = so[i * kRawCols + 3], p = so[i * kRawCols + 4];
                 double yw, zw;
                 world_yz(c, (double)y, (double)z, yw, zw);
-                key[h] = __dsub_rn((double)x, cx);
-                v[h][0] = (float)key[h];
+                key = __dsub_rn((double)x, cx);
+                v[h][0] = (float)key;
                 v[h][1] = (float)__dsub_rn(yw, cy);
                 v[h][2] = (float)zw;
                 v[h][3] = (float)__dmul_rn((double)d, c.doppler_res);
                 v[h][4] = (float)__ddiv_rn(__dsub_rn((double)p, c.int_mu), c.int_std);
             }
-            keys[warp][i] = key[h];
+            const long long b = __double_as_longlong(__dadd_rn(key, 0.0));
+            mkey[h] = b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+            keys[warp][i] = mkey[h];
         }
         __syncwarp();
+        // Stable rank of (key, index).  Float64 compares (DSETP) issue at a fraction of the integer rate on this part
+        // and the 4096 compares per frame were two thirds of the kernel's time (profiles/r02_feat_probe.txt), so the
+        // keys are compared as integers: a finite double maps to an int64 with the same order (-0.0 was folded into
+        // +0.0 above), and "kq < k  or  (kq == k and q < i)" is "mq < m + (q < i)".
         int rank[2] = {0, 0};
-        const double2* k2 = reinterpret_cast<const double2*>(keys[warp]);
+        const long long lt0 = mkey[0], le0 = mkey[0] + 1, lt1 = mkey[1], le1 = mkey[1] + 1;
+        const longlong2* k2 = reinterpret_cast<const longlong2*>(keys[warp]);
+        const int nq2 = (a.dbg & 4) ? 1 : kFeatPts / 4;
 #pragma unroll 8
-        for (int q2 = 0; q2 < kFeatPts / 2; ++q2) {
-            const double2 kq = k2[q2];                   // broadcast read: keys 2 q2 and 2 q2 + 1
+        for (int q2 = 0; q2 < nq2; ++q2) {               // q = 2 q2, 2 q2 + 1 < 32: below every index of the second point
+            const longlong2 kq = k2[q2];                 // broadcast read
             const int q = 2 * q2;
-            rank[0] += (kq.x < key[0] || (kq.x == key[0] && q < lane)) ? 1 : 0;
-            rank[0] += (kq.y < key[0] || (kq.y == key[0] && q + 1 < lane)) ? 1 : 0;
-            rank[1] += (kq.x < key[1] || (kq.x == key[1] && q < lane + 32)) ? 1 : 0;
-            rank[1] += (kq.y < key[1] || (kq.y == key[1] && q + 1 < lane + 32)) ? 1 : 0;
+            rank[0] += kq.x < (q < lane ? le0 : lt0) ? 1 : 0;
+            rank[0] += kq.y < (q + 1 < lane ? le0 : lt0) ? 1 : 0;
+            rank[1] += kq.x < le1 ? 1 : 0;
+            rank[1] += kq.y < le1 ? 1 : 0;
         }
+#pragma unroll 8
+        for (int q2 = 0; q2 < nq2; ++q2) {               // q = 32 + 2 q2 ...: above every index of the first point
+            const longlong2 kq = k2[kFeatPts / 4 + q2];
+            const int q = 2 * q2;
+            rank[0] += kq.x < lt0 ? 1 : 0;
+            rank[0] += kq.y < lt0 ? 1 : 0;
+            rank[1] += kq.x < (q < lane ? le1 : lt1) ? 1 : 0;
+            rank[1] += kq.y < (q + 1 < lane ? le1 : lt1) ? 1 : 0;
+        }
+        // the sorted frame is put together in shared memory and leaves as whole 16-byte vectors: a row is 20 bytes,
+        // written from registers it cost 14 store instructions of 32 scattered sectors each (the L2 request rate, not
+        // the bytes, bounded the kernel)
+        uint4* sp = spk[warp];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int q = 0; q < kRawCols; ++q) out[rank[h] * kRawCols + q] = v[h][q];
+            for (int q = 0; q < kRawCols; ++q) so[rank[h] * kRawCols + q] = v[h][q];
             if (pk) {
                 __align__(16) __nv_bfloat16 pv[16];
 #pragma unroll
@@ -161,8 +195,18 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 7) pose_feature_kernel(PoseFe
                 }
                 // slab order of the tensor-core convs: [row][d = f][w][chunk][h][8]  (pose_tc.cu)
                 const int ph = rank[h] >> 3, pw_ = rank[h] & 7;
-                pk[((f * 8 + pw_) * 2 + 0) * 8 + ph] = reinterpret_cast<const uint4*>(pv)[0];
-                pk[((f * 8 + pw_) * 2 + 1) * 8 + ph] = reinterpret_cast<const uint4*>(pv)[1];
+                sp[(pw_ * 2 + 0) * 8 + ph] = reinterpret_cast<const uint4*>(pv)[0];
+                sp[(pw_ * 2 + 1) * 8 + ph] = reinterpret_cast<const uint4*>(pv)[1];
+            }
+        }
+        __syncwarp();
+        if (!(a.dbg & 2)) {
+            float4* o4 = reinterpret_cast<float4*>(out);
+            const float4* s4 = reinterpret_cast<const float4*>(so);
+            for (int e = lane; e < kFeatPts * kRawCols / 4; e += 32) o4[e] = s4[e];
+            if (pk) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pk[f * kFeatPts * 2 + e * 32 + lane] = sp[e * 32 + lane];
             }
         }
         __syncwarp();                    // the keys are reused by this warp's next item
@@ -388,7 +432,10 @@ cudaError_t launch_pose_features(const PoseFeatArgs& a, int S, cudaStream_t st) 
     static int configured[kMaxDevices] = {0};   // same shared-memory carve-out as its neighbours in the step
     cudaError_t e = ensure_smem_attr(reinterpret_cast<const void*>(pose_feature_kernel), configured, -1);
     if (e != cudaSuccess) return e;
-    return launch_pdl(pose_feature_kernel, dim3(S), dim3(kFeatWarps * 32), 0, st, dim3(1, 1, 1), a);
+    static const int dbg = [] { const char* env = getenv("MMW_FEAT_DBG"); return env ? atoi(env) : 0; }();
+    PoseFeatArgs b = a;
+    b.dbg = dbg;
+    return launch_pdl(pose_feature_kernel, dim3(S), dim3(kFeatWarps * 32), 0, st, dim3(1, 1, 1), b);
 }
 
 }  // namespace mmw

@@ -1173,7 +1173,7 @@ int pose_tc_fc2(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
     // MMW_FC2_SPLIT=0 keeps the single-CTA kernel (the comparison point)
     static const bool split = [] { const char* e = getenv("MMW_FC2_SPLIT"); return !e || atoi(e) != 0; }();
     cudaError_t le;
-    if (split && (im->H / kBK) % 4 == 0)
+    if (split && (im->H / kBK) % 4 == 0 && (max_rows + 127) / 128 <= 128)      // large batches fill the SMs without it
         le = launch_pdl(gemm_tc_kernel<64, 4, 1, 4>, dim3(4, (max_rows + 127) / 128), dim3(kGemmThreads),
                         gemm_smem_bytes<64, 4>(), st, dim3(4, 1, 1), im->m_hh, im->m_hl, im->m_w2h, im->m_w2l, g);
     else
