@@ -22,7 +22,7 @@ struct PoseFeatArgs {
     int* pose_total;
     unsigned long long* counters;
     int n_scenes;
-    int dbg = 0;           // timing experiments only (MMW_FEAT_DBG): 1 = no row scan, 2 = no stores, 4 = no rank loop, 8 = no ring loads
+    int dbg = 0;           // timing experiments only (MMW_FEAT_DBG): 1 = no row scan, 2 = no stores, 4 = no rank loop, 8 = no ring loads; 16 = always the exact (float64-order) sort, the fast lattice path off
 };
 
 struct ConvArgs {

@@ -126,6 +126,19 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 7) pose_feature_kernel(PoseFe
         __syncwarp();
         float v[2][kRawCols];
         long long mkey[2];
+        // Fast path of the sort (taken when every x of the frame is a multiple of 2^-16 below 128 m -- the sensor's
+        // Q-format lattice -- and |cx| < 2^30): there fl(x - cx) is STRICTLY monotone in x (two lattice values differ by
+        // >= 2^-16, the rounding moves a difference by < 2^-22), and a pad (key 0.0) sorts like a point at cx.  So the
+        // order of (key, index) is the order of the 32-bit word  (2 x 2^16 [pads: the odd or even integer at cx] + 2^25)
+        // << 6 | index, all different: one integer compare per pair instead of a 64-bit compare with a tie rule.
+        int kx[2];
+        bool lattice = fabs(cx) < 1073741824.0;
+        {
+            const double cs = cx * 65536.0, fl = floor(cs);
+            const int kpad = cs >= 8388608.0 ? (1 << 24) + 1 : (cs <= -8388608.0 ? -(1 << 24) - 1
+                             : 2 * (int)fl + (cs != fl ? 1 : 0));
+            kx[0] = kx[1] = kpad;
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int i = lane + 32 * h;
@@ -133,6 +146,11 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 7) pose_feature_kernel(PoseFe
 #pragma unroll
             for (int q = 0; q < kRawCols; ++q) v[h][q] = 0.f;
             if (i < cnt) {
+                {
+                    const float xs = so[i * kRawCols + 0] * 65536.f;
+                    lattice = lattice && fabsf(xs) < 8388608.f && xs == rintf(xs);
+                    kx[h] = 2 * (int)xs;
+                }
                 const float x = so[i * kRawCols + 0], y = so[i * kRawCols + 1], z = so[i * kRawCols + 2];
                 const float d = so[i * kRawCols + 3], p = so[i * kRawCols + 4];
                 double yw, zw;
@@ -146,14 +164,33 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 7) pose_feature_kernel(PoseFe
             }
             const long long b = __double_as_longlong(__dadd_rn(key, 0.0));
             mkey[h] = b ^ ((b >> 63) & 0x7fffffffffffffffLL);
-            keys[warp][i] = mkey[h];
+        }
+        const bool fast = __all_sync(0xffffffffu, lattice) && !(a.dbg & 16);
+        if (!fast) {
+            keys[warp][lane] = mkey[0];
+            keys[warp][lane + 32] = mkey[1];
+        } else {
+            unsigned* k32 = reinterpret_cast<unsigned*>(keys[warp]);
+            k32[lane] = ((unsigned)(kx[0] + (1 << 25)) << 6) | (unsigned)lane;
+            k32[lane + 32] = ((unsigned)(kx[1] + (1 << 25)) << 6) | (unsigned)(lane + 32);
         }
         __syncwarp();
+        int rank[2] = {0, 0};
+        if (fast) {
+            const unsigned c0 = ((unsigned)(kx[0] + (1 << 25)) << 6) | (unsigned)lane;
+            const unsigned c1 = ((unsigned)(kx[1] + (1 << 25)) << 6) | (unsigned)(lane + 32);
+            const uint4* k4 = reinterpret_cast<const uint4*>(keys[warp]);
+#pragma unroll
+            for (int q4 = 0; q4 < kFeatPts / 4; ++q4) {
+                const uint4 kq = k4[q4];                 // broadcast read
+                rank[0] += (kq.x < c0) + (kq.y < c0) + (kq.z < c0) + (kq.w < c0);
+                rank[1] += (kq.x < c1) + (kq.y < c1) + (kq.z < c1) + (kq.w < c1);
+            }
+        } else {
         // Stable rank of (key, index).  Float64 compares (DSETP) issue at a fraction of the integer rate on this part
         // and the 4096 compares per frame were two thirds of the kernel's time (profiles/r02_feat_probe.txt), so the
         // keys are compared as integers: a finite double maps to an int64 with the same order (-0.0 was folded into
         // +0.0 above), and "kq < k  or  (kq == k and q < i)" is "mq < m + (q < i)".
-        int rank[2] = {0, 0};
         const long long lt0 = mkey[0], le0 = mkey[0] + 1, lt1 = mkey[1], le1 = mkey[1] + 1;
         const longlong2* k2 = reinterpret_cast<const longlong2*>(keys[warp]);
         const int nq2 = (a.dbg & 4) ? 1 : kFeatPts / 4;
@@ -174,6 +211,7 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 7) pose_feature_kernel(PoseFe
             rank[0] += kq.y < lt0 ? 1 : 0;
             rank[1] += kq.x < (q < lane ? le1 : lt1) ? 1 : 0;
             rank[1] += kq.y < (q + 1 < lane ? le1 : lt1) ? 1 : 0;
+        }
         }
         // the sorted frame is put together in shared memory and leaves as whole 16-byte vectors: a row is 20 bytes,
         // written from registers it cost 14 store instructions of 32 scattered sectors each (the L2 request rate, not
@@ -432,7 +470,8 @@ cudaError_t launch_pose_features(const PoseFeatArgs& a, int S, cudaStream_t st) 
     static int configured[kMaxDevices] = {0};   // same shared-memory carve-out as its neighbours in the step
     cudaError_t e = ensure_smem_attr(reinterpret_cast<const void*>(pose_feature_kernel), configured, -1);
     if (e != cudaSuccess) return e;
-    static const int dbg = [] { const char* env = getenv("MMW_FEAT_DBG"); return env ? atoi(env) : 0; }();
+    const char* env = getenv("MMW_FEAT_DBG");              // read at every launch: a test switches paths in one process
+    const int dbg = env ? atoi(env) : 0;
     PoseFeatArgs b = a;
     b.dbg = dbg;
     return launch_pdl(pose_feature_kernel, dim3(S), dim3(kFeatWarps * 32), 0, st, dim3(1, 1, 1), b);

@@ -157,6 +157,50 @@ def test_sequences_default_config_with_pose():
     _run_sequence(list(range(12)), 45, synth.SceneSpec(), default_config(), weights=W)
 
 
+def test_feature_sort_lattice_fast_path_and_exact_path(monkeypatch):
+    """pose_feature_kernel ranks the 64 rows of a frame by (x - cx, index).  On the sensor's lattice (x a multiple of
+    2^-16) it compares 32-bit integer images of x; otherwise the order-preserving int64 images of the float64 keys.
+    Both must give the reference's order: the exact path on off-lattice inputs against the oracle, and both paths
+    bit-identical on lattice inputs."""
+    W = pw.make_pose_weights(pw.VARIANT_3D)
+    ids, nf = [3, 4, 9, 11], 16
+    # (1) off-lattice x (fp32 values that are not multiples of 2^-16): the exact path, checked against the oracle
+    batches = synth.gen_batch(ids, nf, synth.SceneSpec())
+    rng = np.random.default_rng(17)
+    for b in batches:
+        b.points[:, 0] = (b.points[:, 0].astype(np.float64) + rng.uniform(-3e-6, 3e-6, len(b.points))).astype(np.float32)
+    assert (np.rint(batches[3].points[:, 0].astype(np.float64) * 65536) != batches[3].points[:, 0].astype(np.float64) * 65536).any()
+    cfg = default_config()
+    oracles = [mo.SceneOracle(oracle_config(cfg), pose_weights=W, pose_dtype=np.float64) for _ in ids]
+    bt = BatchedTracker(len(ids), config=cfg)
+    bt.load_pose_weights(W)
+    for f, b in enumerate(batches):
+        bt.step(b.points, b.offsets, b.dt, pose=True, record_labels=True)
+        recs = [o.step(b.points[b.offsets[s]:b.offsets[s + 1]], b.dt[s]) for s, o in enumerate(oracles)]
+        compare_frame(bt, recs, b.offsets, "off-lattice frame %d" % f, labels=bt.labels(), check_keypoints=True,
+                      pose_rows=bt.pose_rows())
+    bt.close()
+    # (2) lattice inputs: fast path == exact path, bit for bit (feature maps and keypoints)
+    batches = synth.gen_batch(ids, nf, synth.SceneSpec())
+    runs = []
+    for dbg in ("0", "16"):
+        monkeypatch.setenv("MMW_FEAT_DBG", dbg)
+        bt = BatchedTracker(len(ids), config=cfg)
+        bt.load_pose_weights(W)
+        out = []
+        for b in batches:
+            bt.step(b.points, b.offsets, b.dt, pose=True)
+            si, ti, feats = bt.pose_rows()
+            out.append((si.copy(), ti.copy(), feats.copy(), bt.tracks()[0].tobytes()))
+        runs.append(out)
+        bt.close()
+    monkeypatch.delenv("MMW_FEAT_DBG")
+    assert sum(len(o[0]) for o in runs[0]) > 3 * nf
+    for a, b in zip(*runs):
+        for u, v in zip(a, b):
+            assert u == v if isinstance(u, bytes) else np.array_equal(u, v)
+
+
 def test_sequences_churn_tracks_time_out_and_ids_reissued():
     spec = synth.SceneSpec(clutter_frac=0.02, leave_prob=0.5, enter_prob=0.5, clutter_box=(2.2, 2.5, 4.2, 4.5),
                            people_min=2, people_max=4)
