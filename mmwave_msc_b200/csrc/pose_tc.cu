@@ -428,23 +428,31 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     return r;
 }
 
-// Tail of dense 2: the 57 outputs of the tile's rows are staged row-major in shared memory (stg); 128 epilogue threads
-// (et = 0..127, warp quadrant q) write them out coalesced, scatter them to the tracks' keypoint slots and, in
-// throughput mode, finish the packed result records of the frame.
-__device__ __forceinline__ void gemm_store_keypoints(const GemmTcArgs& a, const float* stg, int m0, int rows, int q,
-                                                     int lane, int et) {
-    const int nrow = min(128, rows - m0);
-    float* o = a.out + (size_t)m0 * kKp;                               // rows m0.. are contiguous in out
+// Tail of dense 2: the 57 outputs of `nrow` consecutive rows starting at row0 are staged row-major in shared memory
+// (stg); 128 epilogue threads (et = 0..127, warp quadrant q) write them out coalesced, scatter them to the tracks'
+// keypoint slots and, in throughput mode, finish the packed result records of the frame.  The rows' scene / slot /
+// track indices were copied to shared memory (maps: [3][128]) while the main loop ran -- read in the loops below,
+// every row would pay an L2 round trip before its stores (32 rows per warp: most of the epilogue's time).
+__device__ __forceinline__ void gemm_load_row_maps(const GemmTcArgs& a, int* maps, int row0, int nrow, int et) {
+    for (int i = et; i < nrow; i += 128) {
+        maps[i] = a.keypoints || a.results ? __ldg(a.row_scene + row0 + i) : 0;
+        maps[128 + i] = a.keypoints ? __ldg(a.row_slot + row0 + i) : 0;
+        maps[256 + i] = a.results ? __ldg(a.row_track + row0 + i) : 0;
+    }
+}
+__device__ __forceinline__ void gemm_store_keypoints(const GemmTcArgs& a, const float* stg, const int* maps, int row0,
+                                                     int nrow, int q, int lane, int et) {
+    float* o = a.out + (size_t)row0 * kKp;                             // rows row0.. are contiguous in out
     for (int i = et; i < nrow * kKp; i += 128) o[i] = stg[i];
     if (a.keypoints) {
         for (int r = q; r < nrow; r += 4) {
-            float* kp = a.keypoints + ((size_t)a.row_scene[m0 + r] * a.tcap + a.row_slot[m0 + r]) * kKp;
+            float* kp = a.keypoints + ((size_t)maps[r] * a.tcap + maps[128 + r]) * kKp;
             for (int n = lane; n < kKp; n += 32) kp[n] = stg[r * kKp + n];
         }
     }
     if (a.results) {
         for (int r = q; r < nrow; r += 4) {
-            float* rec = a.results + ((size_t)a.row_scene[m0 + r] * a.tcap + a.row_track[m0 + r]) * MMW_RESULT_FLOATS;
+            float* rec = a.results + ((size_t)maps[r] * a.tcap + maps[256 + r]) * MMW_RESULT_FLOATS;
             for (int n = lane; n < kKp; n += 32) rec[11 + n] = stg[r * kKp + n];
             if (lane == 0) {     // the tracker side left x[0], x[1] as two doubles in rec[68..71]
                 const double x0 = reinterpret_cast<const double*>(rec + 68)[0], x1 = reinterpret_cast<const double*>(rec + 68)[1];
@@ -453,8 +461,9 @@ __device__ __forceinline__ void gemm_store_keypoints(const GemmTcArgs& a, const 
         }
     }
 }
+
 template <int BN, int STAGES>
-constexpr int gemm_smem_bytes() { return STAGES * (2 * 128 * kBK * 2 + 2 * BN * kBK * 2) + 1024 + 256 + 3 * BN * 4; }
+constexpr int gemm_smem_bytes() { return STAGES * (2 * 128 * kBK * 2 + 2 * BN * kBK * 2) + 1024 + 256 + (3 * BN * 4 > 1536 ? 3 * BN * 4 : 1536); }
 
 // MODE 0: out = split(BN(relu(acc + bias)))      MODE 1: out = acc + bias (first 57 columns), scattered to tracks
 // KS > 1 (MODE 1, dense 2): split K over a cluster of KS CTAs (blockIdx.x = cluster rank = K slice).  Dense 2 has only
@@ -558,6 +567,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
                 sconst[2 * BN + i] = __ldg(a.bn_shift + n0 + i);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
+        } else {
+            gemm_load_row_maps(a, reinterpret_cast<int*>(sconst), m0, min(BM, rows - m0), threadIdx.x - 64);
         }
         mbar_wait(tmem_full, 0);
         tc_fence_after();
@@ -595,60 +606,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         }
         if (MODE == 1) {
             asm volatile("bar.sync 1, 128;" ::: "memory");                     // the four epilogue warps
-            gemm_store_keypoints(a, reinterpret_cast<const float*>(smem), m0, rows, q, lane, threadIdx.x - 64);
+            gemm_store_keypoints(a, reinterpret_cast<const float*>(smem), reinterpret_cast<const int*>(sconst), m0,
+                                 min(BM, rows - m0), q, lane, threadIdx.x - 64);
         }
     }
     if (KS > 1) {
-        static_assert(KS == 1 || BN == 64, "split epilogue: 64 accumulator columns per row");
-        static_assert(KS == 1 || 32768 + (KS - 1) * 32768 <= STAGES * STAGE_BYTES, "partials fit in the pipeline stages");
-        const int q = warp & 3, r = q * 32 + lane;           // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+        // Reduce-scatter by row quadrant: the 32 rows TMEM lane quadrant q holds (epilogue warp with warp % 4 == q)
+        // are finished by CTA q of the cluster -- every CTA sends three quadrants of its partial accumulator away,
+        // receives three partials of its own quadrant, adds the four in rank order (the sum of a row does not depend on
+        // where the row sits in the batch) and writes out 32 rows, so the epilogue is spread over the four SMs too.
+        static_assert(KS == 1 || (KS == 4 && BN == 64), "split epilogue: 4 CTAs, 4 row quadrants, 64 columns");
+        static_assert(KS == 1 || 32768 + 4 * 8192 <= STAGES * STAGE_BYTES, "partials fit in the pipeline stages");
+        const int q = warp & 3;                               // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+        const int row0 = m0 + 32 * ks, nrow = max(0, min(32, rows - row0));
+        int* maps = reinterpret_cast<int*>(tmem_slot + 2);
         uint32_t v0[32], v1[32];
         if (warp >= 2) {
+            gemm_load_row_maps(a, maps, row0, nrow, threadIdx.x - 64);
             mbar_wait(tmem_full, 0);
             tc_fence_after();
             tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16), v0);
             tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + 32u, v1);
             tc_fence_before();
         }
-        // every CTA of the cluster has finished its MMAs: the leader's pipeline stages are free to receive the partials
+        // every CTA of the cluster has finished its MMAs: the pipeline stages of all four are free to receive partials
         cluster_sync_all();
-        // partials in the leader: [rank - 1][column group of 4][row][4] floats from byte 32768 on (a warp's 32 rows of
-        // one column group are 512 contiguous bytes); the first 32 KB stay free for the coalesced output staging
+        // partials in the receiver: [source rank][column group of 4][row of the quadrant][4] floats from byte 32768 on
+        // (a warp's 32 rows of one column group are 512 contiguous bytes); the bytes below stay free for the output staging
         float* part = reinterpret_cast<float*>(smem + 32768);
-        if (warp >= 2 && ks != 0) {
-            const uint32_t base = mapa_shared(smem_u32(part + (size_t)(ks - 1) * 8192 + r * 4), 0);
+        if (warp >= 2 && q != ks) {
+            const uint32_t base = mapa_shared(smem_u32(part + (size_t)ks * 2048 + lane * 4), (uint32_t)q);
 #pragma unroll
             for (int g = 0; g < 16; ++g) {
                 const uint32_t* v = g < 8 ? v0 : v1;
                 const int j = (g & 7) * 4;
-                asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(g * 2048)),
+                asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(g * 512)),
                              "r"(v[j]), "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
                              : "memory");
             }
         }
         cluster_sync_all();
-        if (warp >= 2 && ks == 0) {
+        if (warp >= 2) {
             float* stg = reinterpret_cast<float*>(smem);
-            const float4* p4 = reinterpret_cast<const float4*>(part);
+            if (q == ks) {
+                const float4* p4 = reinterpret_cast<const float4*>(part);
 #pragma unroll
-            for (int g = 0; g < 16; ++g) {
-                const uint32_t* v = g < 8 ? v0 : v1;
-                const int j = (g & 7) * 4;
-                float acc[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                __uint_as_float(v[j + 3])};
+                for (int g = 0; g < 16; ++g) {
+                    const uint32_t* v = g < 8 ? v0 : v1;
+                    const int j = (g & 7) * 4;
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int o = 0; o < KS - 1; ++o) {                       // fixed order: rank 1, 2, ...
-                    const float4 t = p4[(size_t)o * 2048 + g * 128 + r];
-                    acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w;
-                }
+                    for (int o = 0; o < KS; ++o) {                   // fixed order: K slice 0, 1, 2, 3
+                        if (o == ks) {
+                            acc[0] += __uint_as_float(v[j]); acc[1] += __uint_as_float(v[j + 1]);
+                            acc[2] += __uint_as_float(v[j + 2]); acc[3] += __uint_as_float(v[j + 3]);
+                        } else {
+                            const float4 t = p4[(size_t)o * 512 + g * 32 + lane];
+                            acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w;
+                        }
+                    }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int n = g * 4 + e;
-                    if (n < kKp) stg[r * kKp + n] = acc[e] + __ldg(a.bias + n);
+                    for (int e = 0; e < 4; ++e) {
+                        const int n = g * 4 + e;
+                        if (n < kKp) stg[lane * kKp + n] = acc[e] + __ldg(a.bias + n);
+                    }
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");                     // the four epilogue warps
-            gemm_store_keypoints(a, stg, m0, rows, q, lane, threadIdx.x - 64);
+            gemm_store_keypoints(a, stg, maps, row0, nrow, q, lane, threadIdx.x - 64);
         }
     }
     tc_fence_before();
