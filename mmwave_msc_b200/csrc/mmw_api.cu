@@ -53,6 +53,8 @@ struct mmw_ctx {
     uint8_t* d_ring_hist = nullptr;   // [S][kRing][kHistBytes] cell histograms of the global ring's frames (grid screen)
     int32_t* h_defer_hint = nullptr;  // pinned + mapped: work-list length of the last finished step (sizes dbscan_big's grid)
     int32_t* d_defer_hint = nullptr;  //   its device alias
+    int32_t* h_rows_hint = nullptr;   // pinned + mapped: pose rows of the last finished feature kernel (tile shape of dense 1)
+    int32_t* d_rows_hint = nullptr;
     int32_t* d_scene_stats = nullptr; // [S][8] per-scene counters of the last step (summed on the device)
     int32_t* d_defer = nullptr;      // [2 + S + S]: counter, the work list of dbscan_big_kernel, pose rows per scene, finished-CTA ticket
     bool fold_pose_index = true;     // pose-row scan inside pose_feature_kernel (S <= 4096) instead of pose_index_kernel
@@ -212,6 +214,7 @@ int mmw_destroy(mmw_ctx* x) {
         if (p) cudaFree(p);
     pose_tc_free(&x->tc);
     if (x->h_defer_hint) cudaFreeHost(x->h_defer_hint);
+    if (x->h_rows_hint) cudaFreeHost(x->h_rows_hint);
     for (int i = 0; i < 2; ++i)
         for (cudaEvent_t e : {x->h2d_done[i], x->stage_free[i], x->packed[i], x->results_done[i], x->feat_done[i],
                               x->packt_done[i], x->pose_done[i], x->conv_done[i]})
@@ -362,6 +365,13 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
         (void)cudaGetLastError();
         x->h_defer_hint = nullptr;
     }
+    if (cudaHostAlloc((void**)&x->h_rows_hint, sizeof(int32_t), cudaHostAllocMapped) == cudaSuccess) {
+        *x->h_rows_hint = 0;
+        if (cudaHostGetDevicePointer((void**)&x->d_rows_hint, x->h_rows_hint, 0) != cudaSuccess) x->d_rows_hint = nullptr;
+    } else {
+        (void)cudaGetLastError();
+        x->h_rows_hint = nullptr;
+    }
     ALLOC(x->d_ring_hist, (size_t)kRing * kHistBytes * S);
     {
         const char* env = getenv("MMW_POSE_INDEX_FOLD");
@@ -502,7 +512,7 @@ static int run_pose_net(mmw_ctx* x, float* keypoints_by_slot, int max_rows) {
             return fail(MMW_ERR_CUDA, std::string("tensor-core conv: ") + pose_tc_error());
         x->launches += nl;
         prof_mark(x, MMW_K_FC1);
-        if (pose_tc_fc1(&x->tc, r, max_rows, x->stream, &nl) != 0)
+        if (pose_tc_fc1(&x->tc, r, max_rows, x->stream, &nl, x->h_rows_hint ? *(volatile int32_t*)x->h_rows_hint : 0) != 0)
             return fail(MMW_ERR_CUDA, std::string("tensor-core dense 1: ") + pose_tc_error());
         x->launches += nl;
         prof_mark(x, MMW_K_FC2);
@@ -635,6 +645,7 @@ int mmw_estimate_posture(mmw_ctx* x) {
                     (x->use_tc && x->tc.ready) ? pose_tc_input(&x->tc) : nullptr, x->d_row_scene, x->d_row_track,
                     x->d_row_slot, x->fold_pose_index ? x->d_defer + 1 + x->S : nullptr, x->d_pose_total, x->d_counters,
                     x->S};
+    fa.rows_hint = x->d_rows_hint;
     prof_mark(x, MMW_K_POSE_FEATURES);
     CK(launch_pose_features(fa, x->S, x->stream));
     x->launches++;
@@ -1144,6 +1155,7 @@ static int pipeline_pose(mmw_ctx* x) {
     PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, pose_tc_input(&x->tc, b), row_scene,
                     row_track, row_slot, x->fold_pose_index ? x->d_defer + 1 + x->S : nullptr, pose_total, x->d_counters,
                     x->S};
+    fa.rows_hint = x->d_rows_hint;
     CK(launch_pose_features(fa, x->S, T));
     x->launches++;
     CK(cudaEventRecord(x->feat_done[b], T));
@@ -1165,7 +1177,7 @@ static int pipeline_pose(mmw_ctx* x) {
     if (pose_tc_conv(&x->tc, r, P, &nl, b) != 0) return fail(MMW_ERR_CUDA, std::string("tensor-core conv: ") + pose_tc_error());
     x->launches += nl;
     if (x->pipe_gate) CK(cudaEventRecord(x->conv_done[b], P));     // (an event between two kernels undoes their dependent launch)
-    if (pose_tc_fc1(&x->tc, r, x->pose_cap, P, &nl) != 0) return fail(MMW_ERR_CUDA, std::string("tensor-core dense 1: ") + pose_tc_error());
+    if (pose_tc_fc1(&x->tc, r, x->pose_cap, P, &nl, x->h_rows_hint ? *(volatile int32_t*)x->h_rows_hint : 0) != 0) return fail(MMW_ERR_CUDA, std::string("tensor-core dense 1: ") + pose_tc_error());
     x->launches += nl;
     CK(cudaStreamWaitEvent(P, x->packt_done[b], 0));
     if (pose_tc_fc2(&x->tc, r, x->pose_cap, P, &nl) != 0) return fail(MMW_ERR_CUDA, std::string("tensor-core dense 2: ") + pose_tc_error());

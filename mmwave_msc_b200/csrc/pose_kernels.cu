@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kFeatWarps * 32, 7) pose_feature_kernel(PoseFe
             if (s == a.n_scenes - 1) {
                 const int total = pose_base + (sc.last_ran ? sc.n_tracks : 0);
                 *a.pose_total = total;
+                if (a.rows_hint != nullptr) *a.rows_hint = total;        // zero-copy write to pinned host memory
                 atomicAdd(&a.counters[7], (unsigned long long)total);
             }
         }

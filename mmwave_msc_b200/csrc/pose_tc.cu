@@ -913,6 +913,10 @@ struct TcImpl {
     __nv_bfloat16 *w1b = nullptr, *w2b = nullptr;                     // conv B matrices [taps][NOUT][CK]
     __nv_bfloat16 *wd1_hi = nullptr, *wd1_lo = nullptr, *wd2_hi = nullptr, *wd2_lo = nullptr;
     CUtensorMap m_w1b, m_w2b, m_ah, m_al, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l, m_w1h_half, m_w1l_half;
+    CUtensorMap m_w1h_half256, m_w1l_half256;                         // W halves of 128 rows: the wide (N = 256) pair kernel
+    bool wide_ok = false;                                             // N = 192 is the default and N = 256 is available too
+    bool wide_always = false;                                         // MMW_FC1_WIDE=2 (tests)
+    int pair_slots = 74;                                              // CTA pairs that run at once (SMs / 2)
     int dbg = 0;
     int pair = 0;                                                     // dense 1 on CTA pairs (cta_group::2): stages, 0 = off
 };
@@ -1103,6 +1107,24 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
             if (n > 0) { im->pair = c.stages; break; }
         }
         if (verbose) fprintf(stderr, "[mmw] dense 1: %s\n", im->pair ? "cta_group::2 pair kernel" : "single-CTA kernel");
+        // 256 x 192 tiles need ceil(rows / 256) * 8 CTA pairs: one wave up to 2304 rows (74 pairs on 148 SMs), two
+        // beyond -- twice the time for one row more.  256 x 256 tiles (6 per row block, 4/3 of the time each) stay in one
+        // wave up to 3072 rows; the launcher takes whichever is cheaper for the row count of an earlier frame.
+        {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            im->pair_slots = sms / 2;
+        }
+        const char* wenv = getenv("MMW_FC1_WIDE");
+        if (n192 && im->pair == 3 && im->H % 256 == 0 && !(wenv && atoi(wenv) == 0) &&
+            clusters((const void*)gemm_tc_pair_kernel<256, 3>, gemm_pair_smem_bytes<256, 3>()) > 0 &&
+            make_map_2d(&im->m_w1h_half256, im->wd1_hi, im->H, im->Kf, 128, 64) == 0 &&
+            make_map_2d(&im->m_w1l_half256, im->wd1_lo, im->H, im->Kf, 128, 64) == 0)
+        {
+            im->wide_ok = true;
+            im->wide_always = wenv && atoi(wenv) == 2;
+        }
     }
     set_smem((const void*)gemm_tc_kernel<64, 4, 1>, gemm_smem_bytes<64, 4>());
     set_smem((const void*)gemm_tc_kernel<64, 4, 1, 4>, gemm_smem_bytes<64, 4>());
@@ -1154,7 +1176,7 @@ int pose_tc_conv(PoseTc* t, const PoseTcRun& r, cudaStream_t st, int* n_launches
     return 0;
 }
 
-int pose_tc_fc1(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, int* n_launches) {
+int pose_tc_fc1(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, int* n_launches, int rows_hint) {
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
     GemmTcArgs g{r.n_rows, r.bd1, r.bn2_scale, r.bn2_shift, im->h_hi, im->h_lo, nullptr, nullptr, nullptr, nullptr,
@@ -1165,7 +1187,16 @@ int pose_tc_fc1(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
     if (im->pair) {
         const bool n192 = im->H % 192 == 0;
         const dim3 grid((((max_rows + 127) / 128) + 1) & ~1, im->H / (n192 ? 192 : 256)), blk(kGemmThreads), cl(2, 1, 1);
-        if (n192 && im->pair == 3)
+        bool wide = im->wide_ok && im->wide_always;
+        if (im->wide_ok && !wide && rows_hint > 0) {
+            const int mt = (rows_hint + 255) / 256, P = im->pair_slots;
+            const int w192 = (mt * (im->H / 192) + P - 1) / P, w256 = (mt * (im->H / 256) + P - 1) / P;
+            wide = 4 * w256 < 3 * w192;                      // a 256-wide tile takes 4/3 of a 192-wide one
+        }
+        if (wide)
+            le = launch_pdl(gemm_tc_pair_kernel<256, 3>, dim3(grid.x, im->H / 256), blk, gemm_pair_smem_bytes<256, 3>(), st,
+                            cl, im->m_ah, im->m_al, im->m_w1h_half256, im->m_w1l_half256, g);
+        else if (n192 && im->pair == 3)
             le = launch_pdl(gemm_tc_pair_kernel<192, 3>, grid, blk, gemm_pair_smem_bytes<192, 3>(), st, cl, im->m_ah,
                             im->m_al, im->m_w1h_half, im->m_w1l_half, g);
         else if (n192)
