@@ -470,6 +470,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense-path", default="tc", choices=["tc", "simt"])
     ap.add_argument("--no-l2-flush", action="store_true", help="diagnostic only: keep L2 warm between timed steps")
+    ap.add_argument("--e2e-full-records", action="store_true",
+                    help="end-to-end pass downloads all S * max_tracks records per frame instead of the live ones")
     ap.add_argument("--e2e-reps", type=int, default=5, help="end-to-end windows of K steps (the median is reported)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -633,20 +635,27 @@ def main():
     offs_all = torch.from_numpy(np.stack([b.offsets for b in batches[lo_all:hi_all]] + [batches[hi_all - 1].offsets] * guard)).pin_memory().numpy()
     dts_all = torch.from_numpy(np.stack([b.dt for b in batches[lo_all:hi_all]] + [batches[hi_all - 1].dt] * guard)).pin_memory().numpy()
     res_all = torch.empty((n_all + guard, per_frame), dtype=torch.float32).pin_memory().numpy()
+    cnt_all = torch.zeros(n_all + guard, dtype=torch.int32).pin_memory().numpy()
 
     def pinned_block(lo, hi):
         a, b = lo - lo_all, hi - lo_all
         return (rows_all[fro_all[a]:fro_all[b]], (fro_all[a:b + 1] - fro_all[a]).astype(np.int64), offs_all[a:b], dts_all[a:b],
-                res_all[a:b])
+                res_all[a:b], cnt_all[a:b])
+
+    def run_block(blk):                # live records only (mmw_run_frames_compact) unless --e2e-full-records
+        if args.e2e_full_records:
+            bt.run_frames(*blk[:5])
+        else:
+            bt.run_frames(*blk[:5], n_records=blk[5])
 
     warm_blk = pinned_block(f, f + W_)
     time_blks = [pinned_block(f + W_ + r * K, f + W_ + (r + 1) * K) for r in range(E2E_REPS)]
-    bt.run_frames(*warm_blk)
+    run_block(warm_blk)
     e2e_reps = []
     for blk in time_blks:              # consecutive frames of the same sequences: every window is K new frames
         barrier()
         t0 = time.perf_counter()
-        bt.run_frames(*blk)
+        run_block(blk)
         barrier()
         t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -655,6 +664,7 @@ def main():
     time_blk = time_blks[-1]
     h2d = time_blk[0].nbytes + time_blk[2].nbytes + time_blk[3].nbytes
     res_np = [time_blk[4][0], time_blk[4][1]]
+    d2h = int(per_frame * 4) if args.e2e_full_records else int(time_blk[5].mean() * _lib.RESULT_FLOATS * 4 + 4)
     clocks = sampler.stop()           # sampled across the device-timed passes and the end-to-end pass
     clocks["window"] = "device-timed passes + end-to-end pass (all under load)"
     f += W_ + E2E_REPS * K
@@ -738,9 +748,12 @@ def main():
                                 "l2": "no explicit flush (a fill on either stream would serialise them): every step reads a "
                                       "frame never read before and streams ~150 MB through the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // K),
-                    "d2h_bytes_per_step": int(per_frame * 4),
-                    "api": "mmw_run_frames (BatchedTracker.run_frames): int16 sensor rows from pinned host memory, "
-                           "throughput mode, packed result records of every frame back in pinned host memory",
+                    "d2h_bytes_per_step": d2h,
+                    "api": ("mmw_run_frames" if args.e2e_full_records else "mmw_run_frames_compact") +
+                           " (BatchedTracker.run_frames): int16 sensor rows from pinned host memory, throughput mode, " +
+                           ("packed result records of every track slot" if args.e2e_full_records else
+                            "packed result records of the live tracks (~2 of 8 slots per scene) + their count") +
+                           ", every frame, back in pinned host memory",
                     "host": numa,
                     "windows": {"reps": E2E_REPS, "steps_each": K, "value_is": "median over the windows of (steps / max-over-ranks "
                                 "wall time)", "scene_frames_per_s": [world * S * K / t for t in e2e_reps]}},

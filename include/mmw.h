@@ -328,6 +328,16 @@ int mmw_wait_results(mmw_ctx* ctx, int slot);
 int mmw_run_frames(mmw_ctx* ctx, int n_frames, const void* pts, const int64_t* frame_row_offsets, const int32_t* offsets,
                    const double* dt, float* results, uint32_t flags);
 
+/* mmw_run_frames that sends back only the records of LIVE tracks (a scene holds ~2 of its max_tracks slots: a quarter of
+ * the bytes).  Frame f leaves n_records[f] records at results + f * S * max_tracks * MMW_RESULT_FLOATS (the same frame
+ * stride as mmw_run_frames, only the head of each frame's block is written), in (scene, list index) order; field [71]
+ * of a record is its scene index, field [1] the scene's track count, the other fields as in mmw_pack_results.  Scenes
+ * without tracks leave no record.  The records are written by a kernel straight into the host buffer, so `results`
+ * and `n_records` must be pinned, device-mapped host memory (cudaHostAlloc / cudaHostRegister, e.g. torch
+ * pin_memory()); MMW_ERR_INVALID otherwise. */
+int mmw_run_frames_compact(mmw_ctx* ctx, int n_frames, const void* pts, const int64_t* frame_row_offsets,
+                           const int32_t* offsets, const double* dt, float* results, int32_t* n_records, uint32_t flags);
+
 /* Counters accumulated on the device since the last call (algorithmic-bytes bookkeeping):
  * out[0]=frames stepped (scene-frames that ran), [1]=sum N, [2]=sum M, [3]=sum U (unassigned pushed),
  * [4]=sum fused points clustered, [5]=sum tracks after the frame, [6]=sum min(A_j,64) ring rows written,

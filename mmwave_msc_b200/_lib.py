@@ -111,6 +111,7 @@ SIGNATURES = {
     "mmw_read_results_async": (C.c_int, [_p, _p, C.POINTER(C.c_int)]),
     "mmw_wait_results": (C.c_int, [_p, C.c_int]),
     "mmw_run_frames": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _p, C.c_uint32]),
+    "mmw_run_frames_compact": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _p, _p, C.c_uint32]),
     "mmw_get_counters": (C.c_int, [_p, _p, C.c_int]),
     "mmw_set_dense_path": (C.c_int, [_p, C.c_int]),
     "mmw_profile": (C.c_int, [_p, C.c_int]),

@@ -137,10 +137,13 @@ class BatchedTracker:
                                      flags))
 
     def run_frames(self, points: np.ndarray, frame_row_offsets: np.ndarray, offsets: np.ndarray, dt: np.ndarray,
-                   results: np.ndarray, pose: bool = True, pipeline: bool = True):
+                   results: np.ndarray, pose: bool = True, pipeline: bool = True, n_records: Optional[np.ndarray] = None):
         """F frames back to back from host buffers, the loop in C (mmw_run_frames): points (rows, 5) float32 or int16,
         frame_row_offsets (F+1,) int64, offsets (F, S+1) int32 (each frame's own, starting at 0), dt (F, S) float64,
-        results (F, S * max_tracks * 72) float32 filled with every frame's packed records.  Blocking."""
+        results (F, S * max_tracks * 72) float32 filled with every frame's packed records.  Blocking.
+        With ``n_records`` ((F,) int32; it and ``results`` in pinned memory) only the live tracks' records come back
+        (mmw_run_frames_compact): frame f's first n_records[f] records, field 71 = scene index; see
+        ``expand_compact_results``."""
         i16 = points.dtype == np.int16
         F = len(frame_row_offsets) - 1
         for a, dt_, shp in ((points, np.int16 if i16 else np.float32, None), (frame_row_offsets, np.int64, (F + 1,)),
@@ -150,9 +153,33 @@ class BatchedTracker:
                 raise ValueError("run_frames: wrong dtype / shape / layout of an argument")
         flags = ((_lib.STEP_POSE if pose else 0) | (_lib.STEP_PIPELINE if pipeline else 0) |
                  (_lib.STEP_INPUT_I16 if i16 else 0))
-        _lib.check(self.lib.mmw_run_frames(self._h, F, _lib.ptr(points), _lib.ptr(frame_row_offsets), _lib.ptr(offsets),
-                                           _lib.ptr(dt), _lib.ptr(results), flags))
+        if n_records is not None:
+            if n_records.dtype != np.int32 or n_records.shape != (F,) or not n_records.flags["C_CONTIGUOUS"]:
+                raise ValueError("run_frames: n_records must be a contiguous int32 array with one entry per frame")
+            _lib.check(self.lib.mmw_run_frames_compact(self._h, F, _lib.ptr(points), _lib.ptr(frame_row_offsets),
+                                                       _lib.ptr(offsets), _lib.ptr(dt), _lib.ptr(results),
+                                                       _lib.ptr(n_records), flags))
+        else:
+            _lib.check(self.lib.mmw_run_frames(self._h, F, _lib.ptr(points), _lib.ptr(frame_row_offsets),
+                                               _lib.ptr(offsets), _lib.ptr(dt), _lib.ptr(results), flags))
         self._n_last = int(frame_row_offsets[-1] - frame_row_offsets[-2]) if F else 0
+
+    def expand_compact_results(self, frame_block: np.ndarray, n: int) -> np.ndarray:
+        """The full (S, max_tracks, 72) record array of a frame from its compact block (run_frames with n_records):
+        empty slots get id -1 and the scene's track count, like mmw_pack_results writes them."""
+        R = _lib.RESULT_FLOATS
+        rec = np.asarray(frame_block[:n * R], np.float32).reshape(n, R)
+        out = np.zeros((self.S, self.tcap, R), np.float32)
+        out[:, :, 0] = -1.0
+        if n:
+            scene = rec[:, R - 1].astype(np.int64)
+            first = np.r_[True, scene[1:] != scene[:-1]]
+            start = np.maximum.accumulate(np.where(first, np.arange(n), 0))
+            k = np.arange(n) - start
+            out[scene, k] = rec
+            out[scene, k, R - 1] = 0.0
+            out[scene, :, 1] = rec[:, 1][:, None]
+        return out
 
     def estimate_posture(self):
         """TrackBuffer.estimate_posture alone (needs load_pose_weights first)."""

@@ -1126,6 +1126,35 @@ __global__ void __launch_bounds__(256) pack_tracks_kernel(const SceneRec* scenes
     }
 }
 
+// Live records of a frame, compacted in (scene, list index) order, written straight into mapped host memory
+// (mmw_run_frames_compact): CTA s adds up the track counts of the scenes before it (field [1] of a scene's first record),
+// its warps copy the scene's live records as 16-byte vectors and stamp the scene index into field [71]; the last scene's
+// CTA publishes the frame's record count.
+__global__ void __launch_bounds__(128) compact_results_kernel(const float* __restrict__ rec, int S, int tcap,
+                                                              float* __restrict__ host_out, int32_t* __restrict__ host_count) {
+    const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int wpart[4];
+    const size_t scene_stride = (size_t)tcap * MMW_RESULT_FLOATS;
+    int part = 0;
+    for (int i = threadIdx.x; i < s; i += 128) part += (int)__ldg(rec + (size_t)i * scene_stride + 1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) wpart[warp] = part;
+    __syncthreads();
+    const int base = wpart[0] + wpart[1] + wpart[2] + wpart[3];
+    const int nt = (int)rec[(size_t)s * scene_stride + 1];
+    if (s == S - 1 && threadIdx.x == 0) *host_count = base + nt;
+    for (int k = warp; k < nt; k += 4) {
+        const float4* src = reinterpret_cast<const float4*>(rec + (size_t)s * scene_stride + (size_t)k * MMW_RESULT_FLOATS);
+        float4* dst = reinterpret_cast<float4*>(host_out + (size_t)(base + k) * MMW_RESULT_FLOATS);
+        if (lane < MMW_RESULT_FLOATS / 4) {
+            float4 v = src[lane];
+            if (lane == MMW_RESULT_FLOATS / 4 - 1) v.w = (float)s;
+            dst[lane] = v;
+        }
+    }
+}
+
 }  // namespace mmw
 
 extern "C" {
@@ -1371,16 +1400,36 @@ int mmw_gather_nccl(mmw_ctx* x, void* comm, int nranks, float* device_out_all) {
     return MMW_OK;
 }
 
+// The download of a frame's records on the d2h stream: all of them by a copy, or (dev_out != nullptr: the device
+// alias of mapped host memory) only the live ones by compact_results_kernel.
+static int queue_download(mmw_ctx* x, int r, float* host_out, float* dev_out, int32_t* dev_count) {
+    if (dev_out != nullptr) {
+        compact_results_kernel<<<x->S, 128, 0, x->d2h_stream>>>(x->d_results[r], x->S, x->tcap, dev_out, dev_count);
+        CK(cudaGetLastError());
+        x->launches++;
+    } else {
+        CK(cudaMemcpyAsync(host_out, x->d_results[r], sizeof(float) * (size_t)x->S * x->tcap * MMW_RESULT_FLOATS,
+                           cudaMemcpyDeviceToHost, x->d2h_stream));
+    }
+    return MMW_OK;
+}
+
+static int read_results_impl(mmw_ctx* x, float* host_out, int* slot, float* dev_out, int32_t* dev_count);
+
 int mmw_read_results_async(mmw_ctx* x, float* host_out, int* slot) {
     if (!x || !host_out) return fail(MMW_ERR_INVALID, "ctx/host_out is NULL");
+    return read_results_impl(x, host_out, slot, nullptr, nullptr);
+}
+
+static int read_results_impl(mmw_ctx* x, float* host_out, int* slot, float* dev_out, int32_t* dev_count) {
     CK(cudaSetDevice(x->device));
     if (x->pipe_r >= 0) {
         // throughput mode: the last step produced its own records in d_results[pipe_r]; they are complete when that
         // frame's dense 2 is
         const int r = x->pipe_r;
         CK(cudaStreamWaitEvent(x->d2h_stream, x->pose_done[r], 0));
-        CK(cudaMemcpyAsync(host_out, x->d_results[r], sizeof(float) * (size_t)x->S * x->tcap * MMW_RESULT_FLOATS,
-                           cudaMemcpyDeviceToHost, x->d2h_stream));
+        const int rc = queue_download(x, r, host_out, dev_out, dev_count);
+        if (rc != MMW_OK) return rc;
         CK(cudaEventRecord(x->results_done[r], x->d2h_stream));
         if (slot) *slot = r;
         return MMW_OK;
@@ -1401,15 +1450,29 @@ int mmw_read_results_async(mmw_ctx* x, float* host_out, int* slot) {
     x->launches++;
     CK(cudaEventRecord(x->packed[r], x->stream));
     CK(cudaStreamWaitEvent(x->d2h_stream, x->packed[r], 0));
-    CK(cudaMemcpyAsync(host_out, x->d_results[r], sizeof(float) * (size_t)x->S * x->tcap * MMW_RESULT_FLOATS,
-                       cudaMemcpyDeviceToHost, x->d2h_stream));
+    const int rc = queue_download(x, r, host_out, dev_out, dev_count);
+    if (rc != MMW_OK) return rc;
     CK(cudaEventRecord(x->results_done[r], x->d2h_stream));
     if (slot) *slot = r;
     return MMW_OK;
 }
 
+static int run_frames_impl(mmw_ctx* x, int n_frames, const void* pts, const int64_t* frame_row_offsets, const int32_t* offsets,
+                           const double* dt, float* results, int32_t* n_records, bool compact, uint32_t flags);
+
 int mmw_run_frames(mmw_ctx* x, int n_frames, const void* pts, const int64_t* frame_row_offsets, const int32_t* offsets,
                    const double* dt, float* results, uint32_t flags) {
+    return run_frames_impl(x, n_frames, pts, frame_row_offsets, offsets, dt, results, nullptr, false, flags);
+}
+
+int mmw_run_frames_compact(mmw_ctx* x, int n_frames, const void* pts, const int64_t* frame_row_offsets,
+                           const int32_t* offsets, const double* dt, float* results, int32_t* n_records, uint32_t flags) {
+    if (!n_records) return fail(MMW_ERR_INVALID, "n_records is NULL");
+    return run_frames_impl(x, n_frames, pts, frame_row_offsets, offsets, dt, results, n_records, true, flags);
+}
+
+static int run_frames_impl(mmw_ctx* x, int n_frames, const void* pts, const int64_t* frame_row_offsets, const int32_t* offsets,
+                           const double* dt, float* results, int32_t* n_records, bool compact, uint32_t flags) {
     if (!x || !frame_row_offsets || !offsets || !dt || !results) return fail(MMW_ERR_INVALID, "NULL argument");
     if (n_frames < 0) return fail(MMW_ERR_INVALID, "n_frames must not be negative");
     if (flags & (MMW_STEP_DEVICE_INPUT | MMW_STEP_RECORD_LABELS))
@@ -1424,6 +1487,16 @@ int mmw_run_frames(mmw_ctx* x, int n_frames, const void* pts, const int64_t* fra
     constexpr int kAhead = 4;
     cudaEvent_t done[kAhead] = {nullptr, nullptr, nullptr, nullptr};
     CK(cudaSetDevice(x->device));
+    float* dev_results = nullptr;
+    int32_t* dev_counts = nullptr;
+    if (compact && n_frames > 0) {
+        // the kernel writes the host buffers itself: they must be pinned and mapped into the device's address space
+        if (cudaHostGetDevicePointer((void**)&dev_results, results, 0) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&dev_counts, n_records, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(MMW_ERR_INVALID, "mmw_run_frames_compact needs results and n_records in pinned (device-mapped) host memory");
+        }
+    }
     for (int i = 0; i < kAhead; ++i) CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
     int rc = MMW_OK;
     for (int f = 0; f < n_frames && rc == MMW_OK; ++f) {
@@ -1431,7 +1504,8 @@ int mmw_run_frames(mmw_ctx* x, int n_frames, const void* pts, const int64_t* fra
         const unsigned char* p = static_cast<const unsigned char*>(pts) + (size_t)frame_row_offsets[f] * row_bytes;
         rc = mmw_step(x, reinterpret_cast<const float*>(p), offsets + (size_t)f * (x->S + 1), dt + (size_t)f * x->S, flags);
         if (rc != MMW_OK) break;
-        rc = mmw_read_results_async(x, results + (size_t)f * per_frame, nullptr);
+        rc = read_results_impl(x, results + (size_t)f * per_frame, nullptr, compact ? dev_results + (size_t)f * per_frame : nullptr,
+                               compact ? dev_counts + f : nullptr);
         if (rc != MMW_OK) break;
         if (cudaEventRecord(done[f % kAhead], x->d2h_stream) != cudaSuccess) rc = fail(MMW_ERR_CUDA, "cudaEventRecord failed");
     }

@@ -562,6 +562,26 @@ def test_int16_lattice_input_and_run_frames_equal_the_fp32_path():
     fro = np.cumsum([0] + [len(x) for x in i16]).astype(np.int64)
     c_.run_frames(rows, fro, np.stack([bt.offsets for bt in batches]), np.stack([bt.dt for bt in batches]), rc)
     assert rc.tobytes() == ra.tobytes()
+    # mmw_run_frames_compact: only the live tracks' records come back (written by a kernel into pinned host memory);
+    # expanded again they are the full records, bit for bit -- in throughput mode and in serial mode
+    import torch
+    for pipeline in (True, False):
+        d_ = BatchedTracker(S, config=cfg)
+        d_.load_pose_weights(W)
+        rd = torch.zeros((F, n), dtype=torch.float32).pin_memory().numpy()
+        cnt = torch.zeros(F, dtype=torch.int32).pin_memory().numpy()
+        d_.run_frames(rows, fro, np.stack([bt.offsets for bt in batches]), np.stack([bt.dt for bt in batches]), rd,
+                      pipeline=pipeline, n_records=cnt)
+        assert cnt[-1] == na.sum() and (cnt[2:] > 0).all()
+        for f in range(F):
+            full = d_.expand_compact_results(rd[f], int(cnt[f]))
+            assert full.tobytes() == ra[f].tobytes(), "frame %d" % f
+        d_.close()
+    with pytest.raises(_lib.MmwError):         # pageable host memory is refused, not silently staged
+        e_ = BatchedTracker(S, config=cfg)
+        e_.load_pose_weights(W)
+        e_.run_frames(rows, fro, np.stack([bt.offsets for bt in batches]), np.stack([bt.dt for bt in batches]),
+                      np.zeros((F, n), np.float32), n_records=np.zeros(F, np.int32))
     # ... and against the oracle on the float64 values the lattice stands for
     so = mo.SceneOracle(pose_weights=W)
     for f, bt in enumerate(batches):
