@@ -64,6 +64,14 @@ struct mmw_ctx {
     int32_t* d_offsets2[2] = {nullptr, nullptr};
     double* d_dt2[2] = {nullptr, nullptr};
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    // mmw_run_frames: the inputs of kGroup consecutive frames go up in ONE copy per array (a 2 MB copy runs at 15 GB/s
+    // on a link that gives 24 GB/s at 8 MB: per-copy cost, not bandwidth), double-buffered by group
+    void* d_ptsG[2] = {nullptr, nullptr};
+    size_t ptsG_cap = 0;
+    int32_t* d_offG[2] = {nullptr, nullptr};
+    double* d_dtG[2] = {nullptr, nullptr};
+    cudaEvent_t h2dG_done[2] = {nullptr, nullptr}, stageG_free[2] = {nullptr, nullptr};
+    long long dev_row0 = 0;          // StepArgs::pts_row0 of the next MMW_STEP_DEVICE_INPUT step (reset by it)
     // throughput mode (MMW_STEP_PIPELINE): pose network on its own stream, its inputs double-buffered
     cudaStream_t pose_stream = nullptr;
     cudaEvent_t feat_done[2] = {nullptr, nullptr}, packt_done[2] = {nullptr, nullptr}, pose_done[2] = {nullptr, nullptr};
@@ -215,6 +223,13 @@ int mmw_destroy(mmw_ctx* x) {
     pose_tc_free(&x->tc);
     if (x->h_defer_hint) cudaFreeHost(x->h_defer_hint);
     if (x->h_rows_hint) cudaFreeHost(x->h_rows_hint);
+    for (int i = 0; i < 2; ++i) {
+        if (x->d_ptsG[i]) cudaFree(x->d_ptsG[i]);
+        if (x->d_offG[i]) cudaFree(x->d_offG[i]);
+        if (x->d_dtG[i]) cudaFree(x->d_dtG[i]);
+        if (x->h2dG_done[i]) cudaEventDestroy(x->h2dG_done[i]);
+        if (x->stageG_free[i]) cudaEventDestroy(x->stageG_free[i]);
+    }
     for (int i = 0; i < 2; ++i)
         for (cudaEvent_t e : {x->h2d_done[i], x->stage_free[i], x->packed[i], x->results_done[i], x->feat_done[i],
                               x->packt_done[i], x->pose_done[i], x->conv_done[i]})
@@ -562,6 +577,8 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     if (flags & MMW_STEP_DEVICE_INPUT) {
         if (!pts) return fail(MMW_ERR_INVALID, "pts is NULL");
         a.pts = pts; a.offsets = offsets; a.dt = dt;
+        a.pts_row0 = x->dev_row0;
+        x->dev_row0 = 0;
     } else {
         const size_t total = (size_t)offsets[x->S];
         if (offsets[0] != 0) return fail(MMW_ERR_INVALID, "offsets[0] must be 0");
@@ -1484,8 +1501,11 @@ static int run_frames_impl(mmw_ctx* x, int n_frames, const void* pts, const int6
     // events.  The host only keeps the queue bounded: at most kAhead frames in flight.  (Waiting for frame f-1 before
     // queueing f+1 would put the upload of f+1 behind the download of f-1 and leave the pose stream idle for a
     // third of every frame.)
-    constexpr int kAhead = 4;
-    cudaEvent_t done[kAhead] = {nullptr, nullptr, nullptr, nullptr};
+    constexpr int kAheadMax = 8;
+    // timing experiments only: MMW_RUN_AHEAD = frames in flight (default 4), MMW_RUN_NODL = 1 leaves the results on the device
+    static const int kAhead = [] { const char* e = getenv("MMW_RUN_AHEAD"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > kAheadMax ? kAheadMax : v); }();
+    static const bool no_download = [] { const char* e = getenv("MMW_RUN_NODL"); return e && atoi(e) != 0; }();
+    cudaEvent_t done[kAheadMax] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     CK(cudaSetDevice(x->device));
     float* dev_results = nullptr;
     int32_t* dev_counts = nullptr;
@@ -1498,19 +1518,84 @@ static int run_frames_impl(mmw_ctx* x, int n_frames, const void* pts, const int6
         }
     }
     for (int i = 0; i < kAhead; ++i) CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-    int rc = MMW_OK;
+    // ---- input staging by groups of kGroup frames -----------------------------------------------------------
+    constexpr int kGroup = 4;
+    const int n_groups = (n_frames + kGroup - 1) / kGroup;
+    {
+        size_t need = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            const int f0 = g * kGroup, f1 = f0 + kGroup < n_frames ? f0 + kGroup : n_frames;
+            if (frame_row_offsets[f1] < frame_row_offsets[f0]) return fail(MMW_ERR_INVALID, "frame_row_offsets must not decrease");
+            const size_t b = (size_t)(frame_row_offsets[f1] - frame_row_offsets[f0]) * row_bytes;
+            if (b > need) need = b;
+        }
+        // sized for full frames once (no re-allocation -- and no device synchronisation -- when a later call brings more points)
+        const size_t cap_all = (size_t)kGroup * x->S * x->ncap * kRawCols * sizeof(float);
+        if (need < cap_all) need = cap_all;
+        need += 64;                      // the step kernel copies 16-byte aligned windows around a scene's rows
+        if (need > x->ptsG_cap || !x->d_offG[0]) {
+            CK(sync_main(x));
+            for (int i = 0; i < 2; ++i) {
+                if (x->d_ptsG[i]) { cudaFree(x->d_ptsG[i]); x->d_ptsG[i] = nullptr; }
+                CK(cudaMalloc(&x->d_ptsG[i], need));
+                if (!x->d_offG[i]) {
+                    CK(cudaMalloc((void**)&x->d_offG[i], sizeof(int32_t) * kGroup * (x->S + 1)));
+                    CK(cudaMalloc((void**)&x->d_dtG[i], sizeof(double) * kGroup * x->S));
+                    CK(cudaEventCreateWithFlags(&x->h2dG_done[i], cudaEventDisableTiming));
+                    CK(cudaEventCreateWithFlags(&x->stageG_free[i], cudaEventDisableTiming));
+                }
+            }
+            x->ptsG_cap = need;
+        }
+    }
+    auto upload_group = [&](int g) -> int {
+        const int k = g & 1, f0 = g * kGroup, f1 = f0 + kGroup < n_frames ? f0 + kGroup : n_frames;
+        const size_t bytes = (size_t)(frame_row_offsets[f1] - frame_row_offsets[f0]) * row_bytes;
+        CK(cudaStreamWaitEvent(x->h2d_stream, x->stageG_free[k], 0));        // the group two back has been consumed
+        if (bytes) {
+            if (!pts) return fail(MMW_ERR_INVALID, "pts is NULL");
+            CK(cudaMemcpyAsync(x->d_ptsG[k], static_cast<const unsigned char*>(pts) + (size_t)frame_row_offsets[f0] * row_bytes,
+                               bytes, cudaMemcpyHostToDevice, x->h2d_stream));
+        }
+        CK(cudaMemcpyAsync(x->d_offG[k], offsets + (size_t)f0 * (x->S + 1), sizeof(int32_t) * (size_t)(f1 - f0) * (x->S + 1),
+                           cudaMemcpyHostToDevice, x->h2d_stream));
+        CK(cudaMemcpyAsync(x->d_dtG[k], dt + (size_t)f0 * x->S, sizeof(double) * (size_t)(f1 - f0) * x->S,
+                           cudaMemcpyHostToDevice, x->h2d_stream));
+        CK(cudaEventRecord(x->h2dG_done[k], x->h2d_stream));
+        return MMW_OK;
+    };
+    int rc = n_groups > 0 ? upload_group(0) : MMW_OK;
     for (int f = 0; f < n_frames && rc == MMW_OK; ++f) {
+        const int g = f / kGroup, k = g & 1, f0 = g * kGroup;
+        if (f == f0) {
+            if (g + 1 < n_groups && (rc = upload_group(g + 1)) != MMW_OK) break;    // goes up under this group's kernels
+            if (cudaStreamWaitEvent(x->stream, x->h2dG_done[k], 0) != cudaSuccess) { rc = fail(MMW_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
+        }
         if (f >= kAhead && cudaEventSynchronize(done[f % kAhead]) != cudaSuccess) { rc = fail(MMW_ERR_CUDA, "cudaEventSynchronize failed"); break; }
-        const unsigned char* p = static_cast<const unsigned char*>(pts) + (size_t)frame_row_offsets[f] * row_bytes;
-        rc = mmw_step(x, reinterpret_cast<const float*>(p), offsets + (size_t)f * (x->S + 1), dt + (size_t)f * x->S, flags);
+        const int32_t* off = offsets + (size_t)f * (x->S + 1);
+        {
+            const size_t total = (size_t)off[x->S];
+            bool ok = off[0] == 0 && total <= (size_t)x->S * x->ncap &&
+                      total <= (size_t)(frame_row_offsets[f + 1] - frame_row_offsets[f]);
+            for (int i = 0; i < x->S && ok; ++i) ok = off[i] >= 0 && off[i] <= off[i + 1];
+            if (!ok) { rc = fail(MMW_ERR_INVALID, "mmw_run_frames: bad offsets (each frame: 0 = offsets[0] <= ... <= offsets[S] <= its rows, <= S * max_points)"); break; }
+        }
+        x->dev_row0 = frame_row_offsets[f] - frame_row_offsets[f0];
+        rc = mmw_step(x, static_cast<const float*>(x->d_ptsG[k]), x->d_offG[k] + (size_t)(f - f0) * (x->S + 1),
+                      x->d_dtG[k] + (size_t)(f - f0) * x->S, flags | MMW_STEP_DEVICE_INPUT);
         if (rc != MMW_OK) break;
-        rc = read_results_impl(x, results + (size_t)f * per_frame, nullptr, compact ? dev_results + (size_t)f * per_frame : nullptr,
-                               compact ? dev_counts + f : nullptr);
+        x->h_offsets.assign(off, off + x->S + 1);
+        if ((f + 1 == n_frames || (f + 1) % kGroup == 0) &&
+            cudaEventRecord(x->stageG_free[k], x->stream) != cudaSuccess) { rc = fail(MMW_ERR_CUDA, "cudaEventRecord failed"); break; }
+        if (!no_download)
+            rc = read_results_impl(x, results + (size_t)f * per_frame, nullptr, compact ? dev_results + (size_t)f * per_frame : nullptr,
+                                   compact ? dev_counts + f : nullptr);
         if (rc != MMW_OK) break;
-        if (cudaEventRecord(done[f % kAhead], x->d2h_stream) != cudaSuccess) rc = fail(MMW_ERR_CUDA, "cudaEventRecord failed");
+        if (cudaEventRecord(done[f % kAhead], no_download ? x->stream : x->d2h_stream) != cudaSuccess) rc = fail(MMW_ERR_CUDA, "cudaEventRecord failed");
     }
     if (cudaStreamSynchronize(x->d2h_stream) != cudaSuccess && rc == MMW_OK) rc = fail(MMW_ERR_CUDA, "cudaStreamSynchronize failed");
     for (int i = 0; i < kAhead; ++i) cudaEventDestroy(done[i]);
+    if (no_download && sync_main(x) != cudaSuccess && rc == MMW_OK) rc = fail(MMW_ERR_CUDA, "synchronisation failed");
     return rc;
 }
 

@@ -106,6 +106,8 @@ struct StepArgs {
                                //   summed into `counters` by dbscan_big_kernel (one reduction instead of 7 atomics per scene)
     int n_scenes;
     uint32_t flags;
+    long long pts_row0 = 0;    // row of `pts` at which this frame starts (offsets are relative to it): lets several frames
+                               //   share one 16-byte aligned upload (mmw_run_frames)
 };
 
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------------------

@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     __syncthreads();                     // the barrier is initialised
     const bool i16 = (a.flags & MMW_STEP_INPUT_I16) != 0;             // the sensor's int16 lattice, 10 bytes per point
     const int row_bytes = i16 ? kRawCols * 2 : kRawCols * 4;
-    const size_t byte0 = (size_t)off * row_bytes;
+    const size_t byte0 = (size_t)(a.pts_row0 + off) * row_bytes;
     const size_t win0 = byte0 & ~(size_t)15;
     const uint32_t win_bytes = (uint32_t)(((byte0 + (size_t)N * row_bytes + 15) & ~(size_t)15) - win0);
     const bool bulk_pts = (reinterpret_cast<uintptr_t>(a.pts) & 15) == 0;       // else: plain loads (below)
@@ -336,11 +336,11 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     if (!bulk_pts) {
         if (i16) {
             int16_t* st = const_cast<int16_t*>(stageh);
-            const int16_t* src = reinterpret_cast<const int16_t*>(a.pts) + (size_t)off * kRawCols;
+            const int16_t* src = reinterpret_cast<const int16_t*>(a.pts) + (size_t)(a.pts_row0 + off) * kRawCols;
             for (int i = tid; i < N * kRawCols; i += kStepThreads) st[i] = src[i];
         } else {
             float* st = const_cast<float*>(stagef);
-            for (int i = tid; i < N * kRawCols; i += kStepThreads) st[i] = a.pts[(size_t)off * kRawCols + i];
+            for (int i = tid; i < N * kRawCols; i += kStepThreads) st[i] = a.pts[(size_t)(a.pts_row0 + off) * kRawCols + i];
         }
     }
     reinterpret_cast<uint32_t*>(hnew)[tid] = 0u;                 // 256 uint16 counts = 128 words

@@ -532,7 +532,7 @@ def test_int16_lattice_input_and_run_frames_equal_the_fp32_path():
     """MMW_STEP_INPUT_I16: rows as the sensor reports them (int16 x, y, z in Q9, dopplerIdx, peakVal; 10 bytes per
     point) give bit for bit what the fp32 rows of the same lattice values give; mmw_run_frames (the replay loop in C,
     throughput mode) gives what stepping frame by frame gives."""
-    S, F, RES = 24, 16, 0.0626302709636043
+    S, F, RES = 24, 18, 0.0626302709636043      # 18 frames: run_frames uploads them in groups of 4 + a group of 2
     batches = synth.gen_batch(list(range(900, 900 + S)), F)
     W = pw.make_pose_weights(pw.VARIANT_3D)
     cfg = default_config(doppler_res=RES, xyz_q_format=9)
