@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MMW_ABI_VERSION 3
+#define MMW_ABI_VERSION 4
 
 typedef enum mmw_status {
     MMW_OK = 0,

@@ -14,7 +14,7 @@ MMW_POSE_2D, MMW_POSE_3D = 0, 1
 STEP_POSE, STEP_DEVICE_INPUT, STEP_RECORD_LABELS, STEP_PIPELINE, STEP_INPUT_I16 = 0x1, 0x2, 0x4, 0x8, 0x10
 SCENE_POINT_OVERFLOW, SCENE_TRACK_OVERFLOW = 0x1, 0x2
 RESULT_FLOATS = 72
-ABI_VERSION = 3            # MMW_ABI_VERSION of include/mmw.h this binding was written against
+ABI_VERSION = 4            # MMW_ABI_VERSION of include/mmw.h this binding was written against
 KERNEL_NAMES = ["step", "pose_index", "pose_features", "conv", "fc1", "fc2", "dbscan_big", "k7"]
 
 
