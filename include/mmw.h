@@ -264,8 +264,8 @@ int mmw_pose(mmw_ctx* ctx, const float* feats, int n, float* keypoints);
  *   packets, packet_offsets[n+1]  concatenated packet bytes and their boundaries (host)
  *   points [max_points_total][5]  x y z doppler peakVal (host); point_offsets[n+1]; frame_numbers[n];
  *   data_ok[n] = the reference's dataOK (0: no object, other TLV type, truncated or bad magic -> no points)
- * PARITY UNPINNED: the reference decoder cannot run under numpy >= 2; the oracle
- * (oracle/tlv_oracle.py) restates it.  Synchronous. */
+ * Pinned to the reference's own ReadIWR14xx.read() run under a numpy-1.x int16 casting shim (27 packets,
+ * tests/golden/tlv/reference_tlv.npz).  Synchronous. */
 int mmw_decode_tlv(mmw_ctx* ctx, const uint8_t* packets, const int64_t* packet_offsets, int n_packets,
                    double num_doppler_bins, double doppler_res, float* points, size_t max_points_total,
                    int32_t* point_offsets, int32_t* frame_numbers, int32_t* data_ok);
