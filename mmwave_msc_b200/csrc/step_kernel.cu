@@ -227,6 +227,108 @@ __device__ __forceinline__ void spawn_track(const StepArgs& a, int s, TrackRec& 
     for (int e = lane; e < kKp; e += 32) kp[e] = a.default_posture[e];
 }
 
+// The same for the bit-matrix path of dbscan_big_kernel, by the whole CTA (16 warps) instead of one warp per cluster: the
+// cluster's points are spread over all threads (fused clouds of <= 768 points: at most two per thread), sums / minima /
+// maxima are reduced per warp by shuffles and across warps in warp order (fixed order: deterministic), the first 64
+// cluster rows in fused order get their ring positions from per-chunk ballot counts, and the record's fields are
+// written by different threads at once.  `red` is shared scratch of at least 16 * 20 + 32 + 20 doubles.
+__device__ __forceinline__ void spawn_track_block(const StepArgs& a, int s, TrackRec& t, int q, int slot, int track_id,
+                                                  const int* cl, int B, const float* rawc, const double* w6, double* red) {
+    const DevConfig& c = a.cfg;
+    const int tcap = c.tcap, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const unsigned ltmask = (1u << lane) - 1u;
+    double* wred = red;                                   // [nwarps][20]: n, sums (6), minima (6), maxima (6)
+    int* ccnt = reinterpret_cast<int*>(red + nwarps * 20);   // [<= 32] in-cluster points per chunk of 32
+    double* fin = red + nwarps * 20 + 16;                 // [20] totals
+    const int nchunks = (B + 31) >> 5;
+    int n = 0;
+    double sacc[6], mn[6], mx[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { sacc[k] = 0.0; mn[k] = INFINITY; mx[k] = -INFINITY; }
+    unsigned mask[2] = {0u, 0u};
+    for (int j = 0, ch = warp; ch < nchunks; ch += nwarps, ++j) {
+        const int b = ch * 32 + lane;
+        const bool in = b < B && cl[b] == q;
+        if (in) {
+            ++n;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const double w = w6[(size_t)b * 6 + k];
+                sacc[k] += w; mn[k] = fmin(mn[k], w); mx[k] = fmax(mx[k], w);
+            }
+        }
+        const unsigned m = __ballot_sync(kFull, in);
+        if (j < 2) mask[j] = m;
+        if (lane == 0) ccnt[ch] = __popc(m);
+    }
+    if (__any_sync(kFull, n > 0)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { sacc[k] = warp_sum(sacc[k]); mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
+    }
+    if (lane == 0) {
+        double* w = wred + warp * 20;
+        w[0] = (double)n;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { w[1 + k] = sacc[k]; w[7 + k] = mn[k]; w[13 + k] = mx[k]; }
+    }
+    __syncthreads();
+    if (warp == 0 && lane < 19) {                        // across the warps, in warp order
+        double v = wred[lane];
+        for (int w = 1; w < nwarps; ++w) {
+            const double o = wred[w * 20 + lane];
+            v = lane < 7 ? v + o : (lane < 13 ? fmin(v, o) : fmax(v, o));
+        }
+        fin[lane] = v;
+    }
+    // ring = the first 64 cluster rows in fused order (ClusterTrack.__init__ -> BatchedData of the cluster's points)
+    float* dst = a.track_ring + (((size_t)s * tcap + slot) * kRing + 0) * (kFeatPts * kRawCols);
+    for (int j = 0, ch = warp; ch < nchunks && j < 2; ch += nwarps, ++j) {
+        const int b = ch * 32 + lane;
+        if ((mask[j] >> lane) & 1u) {
+            int before = 0;
+            for (int c2 = 0; c2 < ch; ++c2) before += ccnt[c2];
+            const int pos = before + __popc(mask[j] & ltmask);
+            if (pos < kFeatPts) {
+#pragma unroll
+                for (int k = 0; k < kRawCols; ++k) dst[pos * kRawCols + k] = rawc[(size_t)b * kRawCols + k];
+            }
+        }
+    }
+    __syncthreads();
+    const int ntot = (int)fin[0];
+    const double cen = tid < 6 ? fin[1 + tid] / (double)ntot : 0.0;
+    if (tid < 81) t.P[tid] = (tid / 9 == tid % 9) ? c.p_init : 0.0;
+    else if (tid >= 96 && tid < 132) { const int e = tid - 96; t.G[e] = (e / 6 == e % 6) ? c.g_init : 0.0; }
+    else if (tid >= 160 && tid < 163) t.x[6 + tid - 160] = 0.0;
+    else if (tid >= 192 && tid < 192 + kKp)               // keypoints = MODEL_DEFAULT_POSTURE until the first inference (Q25)
+        a.keypoints[((size_t)s * tcap + slot) * kKp + (tid - 192)] = a.default_posture[tid - 192];
+    if (tid < 6) {
+        t.x[tid] = cen;
+        t.centroid[tid] = cen;
+        t.minv[tid] = fin[7 + tid];
+        t.maxv[tid] = fin[13 + tid];
+        t.spread[tid] = 0.0;
+    }
+    if (tid == 32) {
+        const double c3 = fin[4] / (double)ntot, c4 = fin[5] / (double)ntot, c5 = fin[6] / (double)ntot;
+        t.n_est = 0.0;
+        t.lifetime = 0.0;
+        t.id = track_id;
+        t.point_num = ntot;
+        t.is_static = sqrt(c3 * c3 + c4 * c4 + c5 * c5) < c.vel_thres ? 1 : 0;
+        t.slot = slot;
+        t.ring_n = 1;
+        t.ring_head = 0;
+        t.ring_cnt[0] = ntot < kFeatPts ? ntot : kFeatPts;
+        t.ring_cnt[1] = 0;
+        t.ring_cnt[2] = 0;
+        t.pad[0] = t.pad[1] = t.pad[2] = 0;
+    }
+    __syncthreads();                     // `red` is reused by the next cluster
+}
+
 // fp32 world coordinates of the fused ring (oldest frame first) into shared memory + the screened predicate over
 // them (dbscan.cuh).  Block-cooperative; ends with __syncthreads().
 __device__ __forceinline__ NbScreened load_fused_ring(const StepArgs& a, int s, const int* fcnt, const int* fphys,
@@ -239,24 +341,29 @@ __device__ __forceinline__ NbScreened load_fused_ring(const StepArgs& a, int s, 
     const float band = 1e-3f * (float)c.db_eps + 1e-4f;
     nb.lo = (float)c.db_eps - band;
     nb.hi = (float)c.db_eps + band;
+    static_assert(kRing == 3, "the flattened ring load below is written for three frames");
     int b0 = 0;
     for (int f = 0; f < kRing; ++f) {
-        const float* src = uring_frame(a, s, fphys[f]);
-        nb.frame[f] = src;
+        nb.frame[f] = uring_frame(a, s, fphys[f]);
         nb.start[f] = b0;
-        for (int i = threadIdx.x; i < fcnt[f]; i += blockDim.x) {
-            const float x = src[i * kRawCols + 0], y = src[i * kRawCols + 1], z = src[i * kRawCols + 2];
-            double yw, zw;
-            world_yz(c, (double)y, (double)z, yw, zw);
-            Xf[b0 + i] = x; Yf[b0 + i] = (float)yw; Zf[b0 + i] = (float)zw;
-            if (rawc != nullptr) {
-                float* r = rawc + (size_t)(b0 + i) * kRawCols;
-                r[0] = x; r[1] = y; r[2] = z; r[3] = src[i * kRawCols + 3]; r[4] = src[i * kRawCols + 4];
-            }
-        }
         b0 += fcnt[f];
     }
     nb.start[kRing] = b0;
+    // one pass over the fused cloud: the loads of the three frames are independent (a loop per frame paid three round
+    // trips to HBM one after the other)
+    for (int b = threadIdx.x; b < b0; b += blockDim.x) {
+        const int f = b >= nb.start[2] ? 2 : (b >= nb.start[1] ? 1 : 0);
+        const float* src = nb.frame[f];
+        const int i = b - nb.start[f];
+        const float x = src[i * kRawCols + 0], y = src[i * kRawCols + 1], z = src[i * kRawCols + 2];
+        double yw, zw;
+        world_yz(c, (double)y, (double)z, yw, zw);
+        Xf[b] = x; Yf[b] = (float)yw; Zf[b] = (float)zw;
+        if (rawc != nullptr) {
+            float* r = rawc + (size_t)b * kRawCols;
+            r[0] = x; r[1] = y; r[2] = z; r[3] = src[i * kRawCols + 3]; r[4] = src[i * kRawCols + 4];
+        }
+    }
     __syncthreads();
     return nb;
 }
@@ -1018,9 +1125,17 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
                     }
                 __syncthreads();
             }
-            for (int q = warp; q < ncl; q += kBigThreads / 32)
-                spawn_track(a, s, a.tracks[(size_t)s * tcap + T1 + q], q, newslot[q], sc.next_id + q, cl, fcnt, fphys,
-                            lane, bits ? rawc : nullptr, bits ? w6 : nullptr);
+            if (bits) {
+                // the adjacency matrix is dead by now: its first bytes serve as the reduction scratch
+                double* red = reinterpret_cast<double*>(adj);
+                for (int q = 0; q < ncl; ++q)
+                    spawn_track_block(a, s, a.tracks[(size_t)s * tcap + T1 + q], q, newslot[q], sc.next_id + q, cl, B, rawc,
+                                      w6, red);
+            } else {
+                for (int q = warp; q < ncl; q += kBigThreads / 32)
+                    spawn_track(a, s, a.tracks[(size_t)s * tcap + T1 + q], q, newslot[q], sc.next_id + q, cl, fcnt, fphys,
+                                lane, nullptr, nullptr);
+            }
             sc.next_id += ncl;
             sc.n_tracks = T1 + ncl;
             sc.ring_n = 0;               // batch.clear() (Tracking.py:699-700, Q8)
