@@ -1,5 +1,6 @@
 // C ABI of libmmw.so (include/mmw.h): context management, the per-frame step, readback, and the
 // stage-level entry points.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <algorithm>
 #include <climits>
 #include <dlfcn.h>
 #include <cmath>
@@ -79,6 +80,9 @@ struct mmw_ctx {
     int pipe_gate = 0;               // MMW_PIPE_GATE: 1 = the tracker of frame k+1 starts when the convolutions of frame k are done
     int32_t *d_row_scene2 = nullptr, *d_row_track2 = nullptr, *d_row_slot2 = nullptr;
     int* d_pose_total2 = nullptr;
+    int32_t* d_pose_extra = nullptr; // [2] rows dbscan_big_kernel appended for the tracks it spawned (fused steps), by input buffer
+    bool feat_late = true;           // MMW_FEAT_LATE=0: the feature kernel waits for dbscan_big_kernel and lays out every row (round 1)
+    int rows_buf = 0;                // row maps / pose_total of the last feature launch (0 / 1)
     unsigned pipe_idx = 0;           // pipelined steps so far
     int pipe_r = -1;                 // result buffer the last step filled itself (-1: the last step was serial)
     bool pose_pending = false;       // the pose stream has work the main stream has not waited for
@@ -217,7 +221,7 @@ int mmw_destroy(mmw_ctx* x) {
                     x->d_offsets2[1], x->d_dt2[0], x->d_dt2[1], x->d_results[0], x->d_results[1], x->d_blob, x->d_bn1s,
                     x->d_bn1t, x->d_bn2s, x->d_bn2t, x->d_feats, x->d_row_scene, x->d_row_track, x->d_row_slot,
                     x->d_pose_total, x->d_act2, x->d_act3, x->d_pose_out, x->d_row_scene2, x->d_row_track2, x->d_row_slot2,
-                    x->d_pose_total2};
+                    x->d_pose_total2, x->d_pose_extra};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     pose_tc_free(&x->tc);
@@ -253,6 +257,7 @@ int mmw_reset(mmw_ctx* x) {
     CK(cudaMemsetAsync(x->d_assoc, 0xff, sizeof(int32_t) * (size_t)x->S * x->ncap, x->stream));
     CK(cudaMemsetAsync(x->d_pose_total, 0, sizeof(int), x->stream));
     CK(cudaMemsetAsync(x->d_pose_total2, 0, sizeof(int), x->stream));
+    CK(cudaMemsetAsync(x->d_pose_extra, 0, 2 * sizeof(int32_t), x->stream));
     CK(cudaMemsetAsync(x->d_defer, 0, sizeof(int32_t) * (2 + 2 * (size_t)x->S), x->stream));
     CK(cudaMemsetAsync(x->d_scene_stats, 0, sizeof(int32_t) * 8 * (size_t)x->S, x->stream));
     CK(cudaMemsetAsync(x->d_ring_hist, 0, (size_t)kRing * kHistBytes * x->S, x->stream));
@@ -420,6 +425,8 @@ int mmw_create(const mmw_config* cfg, int device, int n_scenes, int max_points, 
         return fail(MMW_ERR_CUDA, "cudaStreamCreate failed");
     }
     ALLOC(x->d_pose_total, sizeof(int));
+    ALLOC(x->d_pose_extra, 2 * sizeof(int32_t));
+    { const char* env = getenv("MMW_FEAT_LATE"); x->feat_late = !(env && atoi(env) == 0); }
     x->pose_cap = n_scenes * max_tracks;
     ALLOC(x->d_row_scene, sizeof(int32_t) * x->pose_cap);
     ALLOC(x->d_row_track, sizeof(int32_t) * x->pose_cap);
@@ -563,7 +570,8 @@ static int run_pose_net(mmw_ctx* x, float* keypoints_by_slot, int max_rows) {
 //   pose stream : wait feat[b]  [conv1][conv2][dense 1]  wait packt[b]  [dense 2 -> keypoints, results b]  ev pose[b]
 // so the tracker of frame k+1 runs under the convolutions / dense 1 of frame k.  The pose stream is serial, hence
 // "pose(k-1) done" implies every earlier frame's pose work is done (its activations are single-buffered).
-static int pipeline_pose(mmw_ctx* x);
+static int pipeline_pose(mmw_ctx* x, bool late);
+static int estimate_posture_impl(mmw_ctx* x, bool late);
 static int launch_pack_tracks(mmw_ctx* x, float* results);
 
 int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double* dt, uint32_t flags) {
@@ -622,6 +630,20 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     a.defer_hint = x->d_defer_hint;
     a.ring_hist = x->d_ring_hist;
     const bool pipelined = (flags & MMW_STEP_PIPELINE) != 0;
+    // fused steps on the tensor-core pose path: the feature kernel does not wait for dbscan_big_kernel, which appends
+    // the rows of the tracks it spawns itself (StepArgs::nr_*)
+    // (serial mode only: in throughput mode, where the pose network of the previous frame holds most SMs, it measured 2 %
+    // slower -- 0.2324 against 0.2274 ms per step -- and 1.7 % faster in serial mode, 0.2419 against 0.2461)
+    const bool late = x->feat_late && !pipelined && (flags & MMW_STEP_POSE) && x->fold_pose_index && x->use_tc && x->tc.ready;
+    if (late) {
+        const int b = pipelined ? (int)(x->pipe_idx & 1u) : 0;
+        a.nr_feats = x->d_feats;
+        a.nr_packed = pose_tc_input(&x->tc, b);
+        a.nr_row_scene = b ? x->d_row_scene2 : x->d_row_scene;
+        a.nr_row_track = b ? x->d_row_track2 : x->d_row_track;
+        a.nr_row_slot = b ? x->d_row_slot2 : x->d_row_slot;
+        a.nr_extra = x->d_pose_extra + b;
+    }
     if (pipelined) {
         if (!(flags & MMW_STEP_POSE) || !(x->use_tc && x->tc.ready))
             return fail(MMW_ERR_STATE, "MMW_STEP_PIPELINE needs MMW_STEP_POSE and the tensor-core pose path");
@@ -630,6 +652,11 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
         // starts delay its slowest CTA by up to a tracker CTA's lifetime.  With the gate the tracker of the next frame
         // starts once the previous frame's convolutions have run, under dense 1 / dense 2, which leave room.
         if (x->pipe_gate && x->pose_pending) CK(cudaStreamWaitEvent(x->stream, x->conv_done[(x->pipe_idx + 1) & 1], 0));
+        // frame k-2 used the same pose inputs / row maps (buffer k & 1): its pose network must be done before
+        // dbscan_big_kernel appends rows and the feature kernel fills them.  Queued in front of the tracker kernels (not
+        // between dbscan_big_kernel and the feature kernel, whose dependent launch it would undo); already satisfied in
+        // steady state, the previous frame's pack_tracks waited for the same event.
+        if (x->pipe_idx >= 2) CK(cudaStreamWaitEvent(x->stream, x->pose_done[x->pipe_idx & 1u], 0));
     } else {
         CK(join_pose(x));
         x->pipe_r = -1;
@@ -642,13 +669,15 @@ int mmw_step(mmw_ctx* x, const float* pts, const int32_t* offsets, const double*
     x->launches += 2;          // step_kernel + dbscan_big_kernel
     prof_mark(x, -1);
     int rc = MMW_OK;
-    if (pipelined) rc = pipeline_pose(x);
-    else if (flags & MMW_STEP_POSE) rc = mmw_estimate_posture(x);
+    if (pipelined) rc = pipeline_pose(x, late);
+    else if (flags & MMW_STEP_POSE) rc = estimate_posture_impl(x, late);
     if (host_stage >= 0) x->stage_pending = host_stage;      // recorded at the head of the next step (see above)
     return rc;
 }
 
-int mmw_estimate_posture(mmw_ctx* x) {
+int mmw_estimate_posture(mmw_ctx* x) { return estimate_posture_impl(x, false); }
+
+static int estimate_posture_impl(mmw_ctx* x, bool late) {
     if (!x) return fail(MMW_ERR_INVALID, "ctx is NULL");
     if (!x->has_weights) return fail(MMW_ERR_STATE, "estimate_posture needs mmw_load_pose_weights first");
     CK(cudaSetDevice(x->device));
@@ -663,6 +692,8 @@ int mmw_estimate_posture(mmw_ctx* x) {
                     x->d_row_slot, x->fold_pose_index ? x->d_defer + 1 + x->S : nullptr, x->d_pose_total, x->d_counters,
                     x->S};
     fa.rows_hint = x->d_rows_hint;
+    fa.late_extra = late ? x->d_pose_extra : nullptr;
+    x->rows_buf = 0;
     prof_mark(x, MMW_K_POSE_FEATURES);
     CK(launch_pose_features(fa, x->S, x->stream));
     x->launches++;
@@ -680,6 +711,7 @@ int mmw_pose_features_only(mmw_ctx* x) {
     PoseFeatArgs fa{x->dc, x->d_scenes, x->d_tracks, x->d_track_ring, x->d_feats, nullptr, x->d_row_scene,
                     x->d_row_track, x->d_row_slot, x->fold_pose_index ? x->d_defer + 1 + x->S : nullptr, x->d_pose_total,
                     x->d_counters, x->S};
+    x->rows_buf = 0;
     CK(launch_pose_features(fa, x->S, x->stream));
     x->launches++;
     return MMW_OK;
@@ -821,15 +853,29 @@ int mmw_get_pose_rows(mmw_ctx* x, int32_t* n_rows, int32_t* scene_idx, int32_t* 
     if (!x || !n_rows) return fail(MMW_ERR_INVALID, "ctx/n_rows is NULL");
     CK(cudaSetDevice(x->device));
     CK(sync_main(x));
+    const int b = x->rows_buf;
     int n = 0;
-    CK(cudaMemcpy(&n, x->d_pose_total, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&n, b ? x->d_pose_total2 : x->d_pose_total, sizeof(int), cudaMemcpyDeviceToHost));
     *n_rows = n;
-    if (scene_idx) CK(cudaMemcpy(scene_idx, x->d_row_scene, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
-    if (track_idx) CK(cudaMemcpy(track_idx, x->d_row_track, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    if (n == 0 || (!scene_idx && !track_idx && !feats)) return MMW_OK;
+    // Rows come back in (scene, list index) order.  On the device the rows of tracks spawned this frame lie behind all
+    // others (dbscan_big_kernel appends them, in the order its CTAs get there).
+    std::vector<int32_t> hs(n), ht(n);
+    CK(cudaMemcpy(hs.data(), b ? x->d_row_scene2 : x->d_row_scene, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ht.data(), b ? x->d_row_track2 : x->d_row_track, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int p, int q) { return hs[p] != hs[q] ? hs[p] < hs[q] : ht[p] < ht[q]; });
+    for (int i = 0; i < n; ++i) {
+        if (scene_idx) scene_idx[i] = hs[order[i]];
+        if (track_idx) track_idx[i] = ht[order[i]];
+    }
     if (feats) {
         const size_t per = (size_t)x->dc.ring_size * kFeatPts * kRawCols;
         if (cap_floats < per * n) return fail(MMW_ERR_CAPACITY, "feats buffer too small");
-        CK(cudaMemcpy(feats, x->d_feats, sizeof(float) * per * n, cudaMemcpyDeviceToHost));
+        std::vector<float> hf(per * n);
+        CK(cudaMemcpy(hf.data(), x->d_feats, sizeof(float) * per * n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i) std::memcpy(feats + per * i, hf.data() + per * order[i], sizeof(float) * per);
     }
     return MMW_OK;
 }
@@ -1187,13 +1233,12 @@ static int launch_pack_tracks(mmw_ctx* x, float* results) {
     return MMW_OK;
 }
 
-static int pipeline_pose(mmw_ctx* x) {
+static int pipeline_pose(mmw_ctx* x, bool late) {
     const int b = (int)(x->pipe_idx & 1u);
     cudaStream_t T = x->stream, P = x->pose_stream;
     int32_t *row_scene = b ? x->d_row_scene2 : x->d_row_scene, *row_track = b ? x->d_row_track2 : x->d_row_track,
             *row_slot = b ? x->d_row_slot2 : x->d_row_slot;
     int* pose_total = b ? x->d_pose_total2 : x->d_pose_total;
-    if (x->pipe_idx >= 2) CK(cudaStreamWaitEvent(T, x->pose_done[b], 0));              // frame k-2: inputs b are free
     if (!x->fold_pose_index) {
         CK(launch_pose_index(x->d_scenes, x->S, pose_total, x->d_counters, T));
         x->launches++;
@@ -1202,6 +1247,8 @@ static int pipeline_pose(mmw_ctx* x) {
                     row_track, row_slot, x->fold_pose_index ? x->d_defer + 1 + x->S : nullptr, pose_total, x->d_counters,
                     x->S};
     fa.rows_hint = x->d_rows_hint;
+    fa.late_extra = late ? x->d_pose_extra + b : nullptr;
+    x->rows_buf = b;
     CK(launch_pose_features(fa, x->S, T));
     x->launches++;
     CK(cudaEventRecord(x->feat_done[b], T));

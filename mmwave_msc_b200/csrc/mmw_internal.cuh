@@ -106,6 +106,14 @@ struct StepArgs {
                                //   summed into `counters` by dbscan_big_kernel (one reduction instead of 7 atomics per scene)
     int n_scenes;
     uint32_t flags;
+    // Pose rows of the tracks dbscan_big_kernel spawns (fused MMW_STEP_POSE steps, S <= 4096): the feature kernel lays
+    // out the rows of the tracks that existed when step_kernel finished and does not wait for dbscan_big_kernel at all;
+    // that kernel computes the feature maps of its new tracks itself and appends them behind (nr_extra counts them).
+    // nr_extra == nullptr: the feature kernel runs after dbscan_big_kernel and lays out every track.
+    float* nr_feats = nullptr;
+    void* nr_packed = nullptr;         // __nv_bfloat16 packed conv-1 input, or nullptr
+    int32_t *nr_row_scene = nullptr, *nr_row_track = nullptr, *nr_row_slot = nullptr;
+    int32_t* nr_extra = nullptr;
     long long pts_row0 = 0;    // row of `pts` at which this frame starts (offsets are relative to it): lets several frames
                                //   share one 16-byte aligned upload (mmw_run_frames)
 };

@@ -23,6 +23,8 @@ struct PoseFeatArgs {
     unsigned long long* counters;
     int n_scenes;
     int dbg = 0;           // timing experiments only (MMW_FEAT_DBG): 1 = no row scan, 2 = no stores, 4 = no rank loop, 8 = no ring loads; 16 = always the exact (float64-order) sort, the fast lattice path off
+    const int32_t* late_extra = nullptr;   // non-null: rows only for the tracks step_kernel left (pose_cnt); no wait for
+                           //   dbscan_big_kernel except by the thread that publishes pose_total = those rows + *late_extra
     int* rows_hint = nullptr;   // mapped host word that receives the row total (the launcher of dense 1 picks its tile shape from it)
 };
 

@@ -24,6 +24,7 @@
 #include "dbscan.cuh"
 #include "linalg.cuh"
 #include "mmw_internal.cuh"
+#include "pose_feat.cuh"
 
 namespace mmw {
 
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(kStepThreads, MMW_STEP_MINBLOCKS) step_kernel(
     const int s = blockIdx.x;
     if (s >= a.n_scenes) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (s == 0 && tid == 0 && a.nr_extra != nullptr) *a.nr_extra = 0;      // rows dbscan_big_kernel will append this frame
     const Elem el(tid);
     const unsigned ltmask = (1u << lane) - 1u;
 
@@ -1048,6 +1050,7 @@ constexpr int kBitsMaxB = 768;        // adjacency bit matrix of up to 768 x 768
 __host__ __device__ inline int big_bits_cap(int ncap) { return 3 * ncap < kBitsMaxB ? 3 * ncap : kBitsMaxB; }
 // shared-memory layout of dbscan_big_kernel: Xf|Yf|Zf, par, cl, scan, adj, cm, ws, raw rows, (8-byte aligned) w6
 constexpr int kBigWsWords = 4 + kMaxCompMasks;    // per-word scratch rows of dbscan_bits_block
+__host__ __device__ inline int big_adj_offset(int ncap) { return 36 * ncap + 2 * 3 * ncap * 4 + 64 * 4; }
 __host__ __device__ inline int big_w6_offset(int ncap) {
     const int cap = big_bits_cap(ncap), w = (cap + 31) / 32;
     const int o = 36 * ncap + 2 * 3 * ncap * 4 + 64 * 4 + (cap * w + (1 + kBigWsWords) * w) * 4 + cap * kRawCols * 4;
@@ -1136,6 +1139,44 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
                     spawn_track(a, s, a.tracks[(size_t)s * tcap + T1 + q], q, newslot[q], sc.next_id + q, cl, fcnt, fphys,
                                 lane, nullptr, nullptr);
             }
+            if (a.nr_extra != nullptr) {
+                // Pose rows of the new tracks, behind the rows of all tracks that existed when step_kernel finished (the
+                // feature kernel lays those out, concurrently): R0 = sum of pose_cnt, which this kernel leaves alone
+                __shared__ int s_part[kBigThreads / 32], s_row0;
+                __syncthreads();                                     // the spawns' global writes are visible to the CTA
+                int part = 0;
+                for (int i = tid; i < a.n_scenes; i += kBigThreads) part += a.pose_cnt[i];
+                part = __reduce_add_sync(kFullMask, part);
+                if (lane == 0) s_part[warp] = part;
+                __syncthreads();
+                if (tid == 0) {
+                    int r0 = 0;
+                    for (int w = 0; w < kBigThreads / 32; ++w) r0 += s_part[w];
+                    s_row0 = r0 + atomicAdd(a.nr_extra, ncl);
+                }
+                __syncthreads();
+                const int nfr = c.ring_size;
+                unsigned char* scratch = smem + ((big_adj_offset(ncap) + 15) & ~15) + warp * kFeatItemBytes;
+                long long* fkeys = reinterpret_cast<long long*>(scratch);
+                float* fso = reinterpret_cast<float*>(scratch + kFeatPts * 8);
+                uint4* fsp = reinterpret_cast<uint4*>(scratch + kFeatPts * 8 + kFeatPts * kRawCols * 4);
+                for (int item = warp; item < ncl * nfr; item += kBigThreads / 32) {
+                    const int q = item / nfr, f = item - q * nfr, row = s_row0 + q, slot = newslot[q];
+                    const TrackRec* t = a.tracks + (size_t)s * tcap + T1 + q;
+                    if (f == 0 && lane == 0) {
+                        a.nr_row_scene[row] = s; a.nr_row_track[row] = T1 + q; a.nr_row_slot[row] = slot;
+                    }
+                    // a fresh track's ring holds one frame: the first 64 cluster rows (spawn_track*); the others are zero
+                    const float* src = f == 0 ? a.track_ring + ((size_t)s * tcap + slot) * kRing * (kFeatPts * kRawCols) : nullptr;
+                    const int cnt = f == 0 ? __ldcg(&t->ring_cnt[0]) : 0;
+                    float* out = a.nr_feats + ((size_t)row * nfr + f) * (kFeatPts * kRawCols);
+                    uint4* pk = a.nr_packed != nullptr
+                                    ? reinterpret_cast<uint4*>(static_cast<unsigned char*>(a.nr_packed) + (size_t)row * nfr * kFeatPts * 32)
+                                    : nullptr;
+                    pose_feature_item<false>(c, src, cnt, __ldcg(&t->centroid[0]), __ldcg(&t->centroid[1]), f, out, pk, fkeys,
+                                             fso, fsp, lane, 0);
+                }
+            }
             sc.next_id += ncl;
             sc.n_tracks = T1 + ncl;
             sc.ring_n = 0;               // batch.clear() (Tracking.py:699-700, Q8)
@@ -1145,7 +1186,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
             if (tid == 0) atomicAdd(&a.counters[5], (unsigned long long)ncl);
         }
         __syncthreads();
-        if (tid == 0) { a.scenes[s] = sc; a.pose_cnt[s] = sc.n_tracks; }
+        if (tid == 0) { a.scenes[s] = sc; if (a.nr_extra == nullptr) a.pose_cnt[s] = sc.n_tracks; }
         __syncthreads();
         stamp(1);
         if (dbg != nullptr && tid == 0) { atomicAdd(&dbg[2], 1ull); atomicAdd(&dbg[7], (unsigned long long)B); }
@@ -1180,7 +1221,13 @@ __global__ void __launch_bounds__(kBigThreads, 1) dbscan_big_kernel(const __grid
     }
 }
 
-int dbscan_big_smem_bytes(int ncap) { return big_w6_offset(ncap) + big_bits_cap(ncap) * 6 * 8; }
+// after DBSCAN and the spawns, everything from the adjacency matrix on is scratch for the new tracks' feature maps
+// (one kFeatItemBytes block per warp)
+int dbscan_big_smem_bytes(int ncap) {
+    const int a = big_w6_offset(ncap) + big_bits_cap(ncap) * 6 * 8;
+    const int b = ((big_adj_offset(ncap) + 15) & ~15) + (kBigThreads / 32) * kFeatItemBytes;
+    return a > b ? a : b;
+}
 
 cudaError_t launch_step(const StepArgs& a, cudaStream_t stream) {
     const int smem = step_smem_bytes(a.cfg.ncap, a.cfg.tcap);
