@@ -848,7 +848,7 @@ def rooflines(kern, cnt, K, alg_bytes, pk, step_ms):
         g = kern.get("fc1", None)
         if g:
             a = fc1_flops / (g / 1e3) / 1e12
-            out["roofline_fc1"] = {"kernel": "gemm_tc_pair_kernel<192,3> (dense 1, tcgen05 cta_group::2)", "bound": "tensor",
+            out["roofline_fc1"] = {"kernel": "gemm_tc_pair_kernel<176|192|256,3> (dense 1, tcgen05 cta_group::2; tile width picked from the row count)", "bound": "tensor",
                                    "achieved": a,
                                    "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": a / pk["bf16_tflops"],
                                    "traffic": traffic.get("gemm_tc_kernel_dense1"),

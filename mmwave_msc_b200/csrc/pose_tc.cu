@@ -836,7 +836,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
         const int q = warp & 3;
         // bias / BatchNorm constants of this column tile into shared memory while the main loop runs
         float* sconst = reinterpret_cast<float*>(tmem_slot + 2);
-        for (int i = threadIdx.x - 64; i < BN; i += 128) {
+        // (BN need not divide N: the last column tile of the 176-wide variant is 128 wide, its missing W rows come in
+        // as zeros from the tensor map's out-of-bounds fill and its missing columns are not stored)
+        const int ncols = min(BN, a.N - n0);
+        for (int i = threadIdx.x - 64; i < ncols; i += 128) {
             sconst[i] = __ldg(a.bias + n0 + i);
             sconst[BN + i] = __ldg(a.bn_scale + n0 + i);
             sconst[2 * BN + i] = __ldg(a.bn_shift + n0 + i);
@@ -847,10 +850,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
         if (threadIdx.x == 64) mark(4);
         const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             if (row >= rows) continue;
+            const int nv4 = min(32, ncols - c0) >> 3;             // 16-byte vectors of this block that exist (8 columns each)
             __align__(16) __nv_bfloat16 hi[32], lo[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -862,8 +866,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
             uint4* ol = reinterpret_cast<uint4*>(a.out_lo + (size_t)row * a.N + n0 + c0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                oh[i] = reinterpret_cast<const uint4*>(hi)[i];
-                ol[i] = reinterpret_cast<const uint4*>(lo)[i];
+                if (i < nv4) {
+                    oh[i] = reinterpret_cast<const uint4*>(hi)[i];
+                    ol[i] = reinterpret_cast<const uint4*>(lo)[i];
+                }
             }
         }
     }
@@ -914,6 +920,9 @@ struct TcImpl {
     __nv_bfloat16 *wd1_hi = nullptr, *wd1_lo = nullptr, *wd2_hi = nullptr, *wd2_lo = nullptr;
     CUtensorMap m_w1b, m_w2b, m_ah, m_al, m_w1h, m_w1l, m_hh, m_hl, m_w2h, m_w2l, m_w1h_half, m_w1l_half;
     CUtensorMap m_w1h_half256, m_w1l_half256;                         // W halves of 128 rows: the wide (N = 256) pair kernel
+    CUtensorMap m_w1h_half176, m_w1l_half176;                         // W halves of 88 rows: the narrow (N = 176) pair kernel
+    bool narrow_ok = false;                                           // 9 column tiles of 176: 72 tiles up to 2048 rows
+    int force_bn = 0;                                                 // MMW_FC1_BN = 176 / 192 / 256 (tests)
     bool wide_ok = false;                                             // N = 192 is the default and N = 256 is available too
     bool wide_always = false;                                         // MMW_FC1_WIDE=2 (tests)
     int pair_slots = 74;                                              // CTA pairs that run at once (SMs / 2)
@@ -1125,6 +1134,12 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
             im->wide_ok = true;
             im->wide_always = wenv && atoi(wenv) == 2;
         }
+        if (n192 && im->pair == 3 && !(wenv && atoi(wenv) == 0) &&
+            clusters((const void*)gemm_tc_pair_kernel<176, 3>, gemm_pair_smem_bytes<176, 3>()) > 0 &&
+            make_map_2d(&im->m_w1h_half176, im->wd1_hi, im->H, im->Kf, 88, 64) == 0 &&
+            make_map_2d(&im->m_w1l_half176, im->wd1_lo, im->H, im->Kf, 88, 64) == 0)
+            im->narrow_ok = true;
+        { const char* benv = getenv("MMW_FC1_BN"); im->force_bn = benv ? atoi(benv) : 0; }
     }
     set_smem((const void*)gemm_tc_kernel<64, 4, 1>, gemm_smem_bytes<64, 4>());
     set_smem((const void*)gemm_tc_kernel<64, 4, 1, 4>, gemm_smem_bytes<64, 4>());
@@ -1187,13 +1202,22 @@ int pose_tc_fc1(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
     if (im->pair) {
         const bool n192 = im->H % 192 == 0;
         const dim3 grid((((max_rows + 127) / 128) + 1) & ~1, im->H / (n192 ? 192 : 256)), blk(kGemmThreads), cl(2, 1, 1);
-        bool wide = im->wide_ok && im->wide_always;
-        if (im->wide_ok && !wide && rows_hint > 0) {
+        bool wide = im->wide_ok && im->wide_always, narrow = false;
+        if (!wide && rows_hint > 0 && n192) {
+            // cost of a launch = waves of CTA pairs x tile width; 176 (9 column tiles), 192 (8) or 256 (6) columns
             const int mt = (rows_hint + 255) / 256, P = im->pair_slots;
-            const int w192 = (mt * (im->H / 192) + P - 1) / P, w256 = (mt * (im->H / 256) + P - 1) / P;
-            wide = 4 * w256 < 3 * w192;                      // a 256-wide tile takes 4/3 of a 192-wide one
+            auto cost = [&](int bn) { return ((mt * ((im->H + bn - 1) / bn) + P - 1) / P) * bn; };
+            int best = cost(192);
+            if (im->wide_ok && cost(256) < best) { best = cost(256); wide = true; }
+            if (im->narrow_ok && cost(176) < best) { wide = false; narrow = true; }
         }
-        if (wide)
+        if (im->force_bn == 256 && im->wide_ok) { wide = true; narrow = false; }
+        if (im->force_bn == 176 && im->narrow_ok) { wide = false; narrow = true; }
+        if (im->force_bn == 192) wide = narrow = false;
+        if (narrow)
+            le = launch_pdl(gemm_tc_pair_kernel<176, 3>, dim3(grid.x, (im->H + 175) / 176), blk, gemm_pair_smem_bytes<176, 3>(),
+                            st, cl, im->m_ah, im->m_al, im->m_w1h_half176, im->m_w1l_half176, g);
+        else if (wide)
             le = launch_pdl(gemm_tc_pair_kernel<256, 3>, dim3(grid.x, im->H / 256), blk, gemm_pair_smem_bytes<256, 3>(), st,
                             cl, im->m_ah, im->m_al, im->m_w1h_half256, im->m_w1l_half256, g);
         else if (n192 && im->pair == 3)

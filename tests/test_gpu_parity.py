@@ -619,20 +619,21 @@ def test_dense1_cta_pair_vs_single_cta_kernel():
 
 # ---- checkpoint / resume -----------------------------------------------------------------------------------
 def test_dense1_wide_tiles_equal_narrow_tiles(monkeypatch):
-    """Dense 1 picks 256 x 192 or 256 x 256 tiles from the row count of an earlier frame (whichever needs fewer waves
-    of CTA pairs: 2305 rows would otherwise take twice as long as 2304).  The choice must never change a bit."""
+    """Dense 1 picks 256 x 176, 256 x 192 or 256 x 256 tiles from the row count of an earlier frame (whichever needs the
+    least waves-times-width on 74 CTA pairs: 72 tiles of 176 columns up to 2048 rows; 2305 rows in 192-wide tiles would
+    take twice as long as 2304).  The choice must never change a bit."""
     rng = np.random.default_rng(11)
     W = pw.make_pose_weights(pw.VARIANT_3D)
     feats = rng.normal(0, 0.4, size=(700, 3, 8, 8, 5)).astype(np.float32)
     outs = []
-    for mode in ("0", "2"):                   # never / always the wide kernel
-        monkeypatch.setenv("MMW_FC1_WIDE", mode)
+    for bn in ("192", "256", "176"):          # 8, 6 or 9 column tiles (the last of the 9 is 128 wide)
+        monkeypatch.setenv("MMW_FC1_BN", bn)
         bt = BatchedTracker(128, max_tracks=8)
         bt.load_pose_weights(W)
         outs.append(bt.pose(feats).copy())
         bt.close()
-    monkeypatch.delenv("MMW_FC1_WIDE")
-    assert np.array_equal(outs[0], outs[1])
+    monkeypatch.delenv("MMW_FC1_BN")
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     assert np.abs(outs[0]).mean() > 0.05
 
 
