@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """What separates the end-to-end loop (mmw_run_frames on pinned host buffers) from the device-resident throughput mode:
-one variant per process (environment knobs are read once).  VARIANT = resident | full | compact | nodl"""
+one variant per process (environment knobs are read once).  VARIANT = resident | resident_serial | full | compact | compact_serial | full_serial"""
 import os
 import sys
 import time
@@ -37,7 +37,7 @@ D = pin(np.stack([b.dt for b in batches[lo:hi]]))
 res = pin(np.zeros((hi - lo + 4, n), np.float32))
 cnt = pin(np.zeros(hi - lo + 4, np.int32))
 dev = [(torch.from_numpy(f32[f]).cuda(), torch.from_numpy(batches[f].offsets).cuda(), torch.from_numpy(batches[f].dt).cuda())
-       for f in range(lo, hi)] if variant == "resident" else None
+       for f in range(lo, hi)] if variant.startswith("resident") else None
 stream = torch.cuda.ExternalStream(bt.stream, device=0)
 rd = torch.empty(n, dtype=torch.float32, device="cuda")
 out = []
@@ -45,14 +45,15 @@ for rep in range(REPS + 1):
     a, b = rep * K, (rep + 1) * K
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    if variant == "resident":
+    if variant.startswith("resident"):
         for p, o, d in dev[a:b]:
-            bt.step_device(p.data_ptr(), o.data_ptr(), d.data_ptr(), p.shape[0], pose=True, pipeline=True)
+            bt.step_device(p.data_ptr(), o.data_ptr(), d.data_ptr(), p.shape[0], pose=True, pipeline=not variant.endswith("_serial"))
         bt.pack_results(rd.data_ptr())
         bt.sync()
     else:
         blk = (R[fro[a]:fro[b]], (fro[a:b + 1] - fro[a]).astype(np.int64), O[a:b], D[a:b], res[a:b])
-        bt.run_frames(*blk, n_records=cnt[a:b] if variant in ("compact",) else None)
+        bt.run_frames(*blk, n_records=cnt[a:b] if variant.startswith("compact") else None,
+                      pipeline=not variant.endswith("_serial"))
     torch.cuda.synchronize()
     out.append((time.perf_counter() - t0) / K * 1e6)
 print("%-10s AHEAD=%s NODL=%s : us per frame %s (first = warm-up)" % (variant, os.environ.get("MMW_RUN_AHEAD", "4"),
