@@ -175,9 +175,16 @@ __device__ __forceinline__ uint64_t make_desc_interleaved(uint32_t saddr, uint32
 //
 // CK   = K' per tap = 2 * padded input channels (hi | lo): 16 for conv1, 32 for conv2
 // NOUT = MMA N     = 2 * output channels: 32 for conv1, 64 for conv2
-template <int CK, int NOUT, int MODE, int D>
+// KD  = taps in depth.  KD == D == 3: define_CNN_3D.  D == 1, KD == 1: define_CNN, one 8 x 8 map per slab (80 of the 128
+// MMA rows of a tile used, the per-sample hand-over paid for every map).  D == 3, KD == 1: define_CNN again, but THREE
+// consecutive samples ride as the three depth planes of one slab -- their packed inputs and outputs are contiguous in
+// exactly the 3-D layout, the depth taps are simply not issued (9 taps, the d padding planes stay unused) -- 240 of 256
+// MMA rows used and a third of the hand-overs: the C4 configuration's convolutions went from 0.83 ms to the figure in
+// DESIGN.md.  Samples past the row count in the last triple are staged as zeros and not stored.
+template <int CK, int NOUT, int MODE, int D, int KD = D>
 __global__ void __launch_bounds__(kSlabThreads, 1)
 conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) {
+    constexpr bool TRIPLE = D == 3 && KD == 1;
     constexpr int NCH = CK / 8;                      // 16-byte chunks per position
     constexpr int ATOM = NCH * 128;                  // bytes of one 8-row atom
     constexpr int SLAB_BYTES = kSlabAtoms * ATOM;
@@ -185,8 +192,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
     constexpr int B_TAP = NOUT * CK * 2;
     constexpr int COUT = NOUT / 2;
     constexpr uint32_t TCOLS = 4 * NOUT;             // 2 accumulator buffers x 2 M tiles
-    constexpr int taps = D == 3 ? 27 : 9;
-    constexpr int MT = D == 3 ? 2 : 1;               // M tiles of 128 rows per sample
+    constexpr int taps = KD == 3 ? 27 : 9;
+    constexpr int MT = D == 3 ? 2 : 1;               // M tiles of 128 rows per sample (or triple of samples)
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -229,7 +236,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
     // everything above overlapped the previous kernel's tail (PDL); its activations and the row count are read below
     pdl_wait();
     pdl_launch_dependents();
-    const int rows = *a.n_rows;
+    const int n_samples = *a.n_rows;
+    const int rows = TRIPLE ? (n_samples + 2) / 3 : n_samples;        // slabs to process
 
     if (warp < 4) {
         // ===== producers: global -> registers (one sample ahead) -> the three h-shifted slabs of the sample =====
@@ -247,7 +255,10 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
         auto load_row = [&](int row, uint4 (&r)[ITEMS]) {
             const uint4* src = reinterpret_cast<const uint4*>(a.in) + (size_t)row * (D * 64 * NCH);
 #pragma unroll
-            for (int j = 0; j < ITEMS; ++j) r[j] = __ldg(src + tid + 128 * j);
+            for (int j = 0; j < ITEMS; ++j) {
+                const bool there = !TRIPLE || row * 3 + (tid + 128 * j) / (64 * NCH) < n_samples;
+                r[j] = there ? __ldg(src + tid + 128 * j) : make_uint4(0, 0, 0, 0);
+            }
         };
         if ((int)blockIdx.x < rows && !(a.dbg & 8)) load_row(blockIdx.x, cur);
         int u = 0;
@@ -300,11 +311,11 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
                         tc_fence_after();
                         const uint64_t da0 = da00 + (uint64_t)((slot * SLAB_BYTES) >> 4);
 #pragma unroll
-                        for (int kdi = 0; kdi < (D == 3 ? 3 : 1); ++kdi) {
+                        for (int kdi = 0; kdi < (KD == 3 ? 3 : 1); ++kdi) {
 #pragma unroll
                             for (int kwi = 0; kwi < 3; ++kwi) {
-                                const int kd = D == 3 ? kdi - 1 : 0, kw = kwi - 1;
-                                const int tap = D == 3 ? (kdi * 3 + c) * 3 + kwi : c * 3 + kwi;
+                                const int kd = KD == 3 ? kdi - 1 : 0, kw = kwi - 1;
+                                const int tap = KD == 3 ? (kdi * 3 + c) * 3 + kwi : c * 3 + kwi;
                                 const bool first = c == 0 && kdi == 0 && kwi == 0;
                                 const int aoff = ((1 + kd) * 10 + kw) * ATOM;        // whole atoms: tap = tile shift
 #pragma unroll
@@ -356,6 +367,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
                 const int aidx = mt * 16 + (m >> 3), hh = m & 7;
                 const int d = aidx / 10, w2 = aidx % 10;
                 if (d >= D || w2 < 1 || w2 > 8 || (a.dbg & 32)) continue;       // padding columns / junk rows
+                if (TRIPLE && row * 3 + d >= n_samples) continue;               // past the last sample
                 __align__(16) __nv_bfloat16 hi[COUT], lo[COUT];
 #pragma unroll
                 for (int c = 0; c < COUT; ++c) {
@@ -1071,6 +1083,8 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
     set_smem((const void*)conv_slab_kernel<32, 64, 1, 3>, conv_smem_bytes_tc<32, 64>(27));
     set_smem((const void*)conv_slab_kernel<16, 32, 0, 1>, conv_smem_bytes_tc<16, 32>(9));
     set_smem((const void*)conv_slab_kernel<32, 64, 1, 1>, conv_smem_bytes_tc<32, 64>(9));
+    set_smem((const void*)conv_slab_kernel<16, 32, 0, 3, 1>, conv_smem_bytes_tc<16, 32>(9));
+    set_smem((const void*)conv_slab_kernel<32, 64, 1, 3, 1>, conv_smem_bytes_tc<32, 64>(9));
     set_smem((const void*)gemm_tc_kernel<256, 2, 0>, gemm_smem_bytes<256, 2>());
     set_smem((const void*)gemm_tc_kernel<192, 2, 0>, gemm_smem_bytes<192, 2>());
     {
@@ -1169,11 +1183,16 @@ int pose_tc_pack_input(PoseTc* t, const float* feats, const int* n_rows, cudaStr
 int pose_tc_conv(PoseTc* t, const PoseTcRun& r, cudaStream_t st, int* n_launches, int buf) {
     TcImpl* im = reinterpret_cast<TcImpl*>(t->impl);
     if (!im || !t->ready) { g_tc_err = "tensor-core path not initialised"; return -1; }
+    // 2-D net: three samples per slab unless MMW_CONV2D_TRIPLE=0 (the comparison point)
+    static const bool triple = [] { const char* e = getenv("MMW_CONV2D_TRIPLE"); return !(e && atoi(e) == 0); }();
     ConvTcArgs c1{r.n_rows, r.b1, nullptr, nullptr, buf ? im->in_p2 : im->in_p, im->act1_p, nullptr, im->D, im->taps, im->dbg};
     const dim3 one(1, 1, 1);
     cudaError_t le;
     if (im->D == 3)
         le = launch_pdl(conv_slab_kernel<16, 32, 0, 3>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<16, 32>(27), st, one,
+                        im->m_w1b, c1);
+    else if (triple)
+        le = launch_pdl(conv_slab_kernel<16, 32, 0, 3, 1>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<16, 32>(9), st, one,
                         im->m_w1b, c1);
     else
         le = launch_pdl(conv_slab_kernel<16, 32, 0, 1>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<16, 32>(9), st, one,
@@ -1182,6 +1201,9 @@ int pose_tc_conv(PoseTc* t, const PoseTcRun& r, cudaStream_t st, int* n_launches
     ConvTcArgs c2{r.n_rows, r.b2, r.bn1_scale, r.bn1_shift, im->act1_p, im->a_hi, im->a_lo, im->D, im->taps, im->dbg};
     if (im->D == 3)
         le = launch_pdl(conv_slab_kernel<32, 64, 1, 3>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<32, 64>(27), st, one,
+                        im->m_w2b, c2);
+    else if (triple)
+        le = launch_pdl(conv_slab_kernel<32, 64, 1, 3, 1>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<32, 64>(9), st, one,
                         im->m_w2b, c2);
     else
         le = launch_pdl(conv_slab_kernel<32, 64, 1, 1>, dim3(148), dim3(kSlabThreads), conv_smem_bytes_tc<32, 64>(9), st, one,
