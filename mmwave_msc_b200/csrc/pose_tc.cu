@@ -1227,7 +1227,9 @@ int pose_tc_fc1(PoseTc* t, const PoseTcRun& r, int max_rows, cudaStream_t st, in
         bool wide = im->wide_ok && im->wide_always, narrow = false;
         if (!wide && rows_hint > 0 && n192) {
             // cost of a launch = waves of CTA pairs x tile width; 176 (9 column tiles), 192 (8) or 256 (6) columns
-            const int mt = (rows_hint + 255) / 256, P = im->pair_slots;
+            // (the hint is a frame or two old and the row count drifts by a few rows per frame: plan for 48 more -- one row
+            // past a tile-count edge costs a whole second wave)
+            const int mt = (rows_hint + 48 + 255) / 256, P = im->pair_slots;
             auto cost = [&](int bn) { return ((mt * ((im->H + bn - 1) / bn) + P - 1) / P) * bn; };
             int best = cost(192);
             if (im->wide_ok && cost(256) < best) { best = cost(256); wide = true; }
