@@ -155,9 +155,15 @@ constexpr int kSlabAtoms = 1 + 5 * 10 + 3;         // one guard atom in front, t
 template <int CK>
 __host__ __device__ constexpr int slab_ring() { return CK == 16 ? 8 : 4; }
 
+// Weights of one tap in shared memory.  Conv 1 (CK = 16: ONE K16 MMA per tap holds a_hi and a_lo): [N = 2 cout][K16] with
+// the (w_lo, a_lo) block zero.  Conv 2 (CK = 32: a K16 MMA for a_hi and one for a_lo): the a_hi MMA multiplies by
+// [w_hi ; w_lo] (N = 64), the a_lo MMA only by w_hi (N = 32, accumulating into the first 32 columns) -- no zero block, 3 KB
+// instead of 4 KB per tap and 5 KB instead of 6 KB of operand reads for every second MMA.
+template <int CK, int NOUT>
+__host__ __device__ constexpr int conv_b_tap_bytes() { return CK == 32 ? (NOUT + NOUT / 2) * 32 : NOUT * CK * 2; }
 template <int CK, int NOUT>
 constexpr int conv_smem_bytes_tc(int taps) {
-    return taps * NOUT * CK * 2 + slab_ring<CK>() * kSlabAtoms * (CK / 8) * 128 + 1024 + 1024;
+    return taps * conv_b_tap_bytes<CK, NOUT>() + slab_ring<CK>() * kSlabAtoms * (CK / 8) * 128 + 1024 + 1024;
 }
 
 __device__ __forceinline__ uint64_t make_desc_interleaved(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -189,7 +195,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
     constexpr int ATOM = NCH * 128;                  // bytes of one 8-row atom
     constexpr int SLAB_BYTES = kSlabAtoms * ATOM;
     constexpr int NSLAB = slab_ring<CK>();
-    constexpr int B_TAP = NOUT * CK * 2;
+    constexpr int B_TAP = conv_b_tap_bytes<CK, NOUT>();
+    constexpr int B_ROWS = CK == 32 ? NOUT + NOUT / 2 : NOUT;        // rows of the weight tensor per tap
     constexpr int COUT = NOUT / 2;
     constexpr uint32_t TCOLS = 4 * NOUT;             // 2 accumulator buffers x 2 M tiles
     constexpr int taps = KD == 3 ? 27 : 9;
@@ -226,7 +233,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // the layer's weights do not depend on the previous kernel: fetch them before the PDL wait below
         mbar_expect_tx(bfull, taps * B_TAP);
-        for (int t = 0; t < taps; ++t) tma_load_2d(sB + t * B_TAP, &map_b, bfull, 0, t * NOUT);
+        for (int t = 0; t < taps; ++t) tma_load_2d(sB + t * B_TAP, &map_b, bfull, 0, t * B_ROWS);
     }
     if (warp == 4) tmem_alloc<TCOLS>(tmem_slot);
     tc_fence_before();
@@ -295,7 +302,8 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
         if (lane == 0) {
             if (mt < MT) {
                 constexpr uint32_t idesc = make_idesc(NOUT);
-                const uint64_t db0 = make_desc<CK * 2>(smem_u32(sB));
+                constexpr uint32_t idesc_lo = make_idesc(NOUT / 2);                    // conv 2, a_lo chunk: N = cout
+                const uint64_t db0 = make_desc<32>(smem_u32(sB));                      // weight rows are one K16 wide
                 const uint64_t da00 = make_desc_interleaved(smem_u32(slab) + (uint32_t)((1 + mt * 16) * ATOM), 128, ATOM);
                 mbar_wait(bfull, 0);
                 int n = 0, u = 0;
@@ -321,7 +329,7 @@ conv_slab_kernel(const __grid_constant__ CUtensorMap map_b, const ConvTcArgs a) 
 #pragma unroll
                                 for (int kk = 0; kk < CK / 16; ++kk)
                                     if (!(a.dbg & 16)) umma_bf16(tmem_d, da0 + (uint64_t)((aoff + kk * 256) >> 4),
-                                              db0 + (uint64_t)((tap * B_TAP + kk * 32) >> 4), idesc,
+                                              db0 + (uint64_t)((tap * B_TAP + kk * NOUT * 32) >> 4), kk == 0 ? idesc : idesc_lo,
                                               (first && kk == 0) ? 0u : 1u);
                             }
                         }
@@ -1026,6 +1034,21 @@ static std::vector<uint16_t> conv_b(const float* w, int taps, int cin, int cinp,
     return b;
 }
 
+// Conv 2 B operand: [taps][3 cout][cin] (one K16 per row): rows 0..cout-1 w_hi, cout..2cout-1 w_lo (both for the a_hi
+// chunk), 2cout..3cout-1 w_hi again (for the a_lo chunk).  cin must be 16.
+static std::vector<uint16_t> conv_b2(const float* w, int taps, int cin, int cout) {
+    std::vector<uint16_t> b((size_t)taps * 3 * cout * cin, 0);
+    for (int t = 0; t < taps; ++t)
+        for (int r = 0; r < 3 * cout; ++r)
+            for (int ci = 0; ci < cin; ++ci) {
+                const int co = r % cout;
+                const float wv = w[((size_t)t * cin + ci) * cout + co];
+                const uint16_t hi = f2bf(wv), lo = f2bf(wv - bf2f(hi));
+                b[((size_t)t * 3 * cout + r) * cin + ci] = (r >= cout && r < 2 * cout) ? lo : hi;
+            }
+    return b;
+}
+
 // Dense weight [K][N] (Keras in,out) -> K-major [Npad][K] hi / lo.
 static void dense_b(const float* w, int K, int N, int Npad, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
     hi.assign((size_t)Npad * K, 0);
@@ -1055,14 +1078,14 @@ int pose_tc_init(PoseTc* t, const float* blob, const size_t* off, int D, int row
     if (!ok) { g_tc_err = "cudaMalloc failed (activations)"; return -1; }
     std::vector<uint16_t> hi, lo;
     ok = upload(&im->w1b, conv_b(blob + off[0], im->taps, 5, 8, 16)) &&
-         upload(&im->w2b, conv_b(blob + off[2], im->taps, 16, 16, 32));
+         upload(&im->w2b, conv_b2(blob + off[2], im->taps, 16, 32));
     dense_b(blob + off[8], im->Kf, im->H, im->H, hi, lo);
     ok = ok && upload(&im->wd1_hi, hi) && upload(&im->wd1_lo, lo);
     dense_b(blob + off[14], im->H, kKp, 64, hi, lo);
     ok = ok && upload(&im->wd2_hi, hi) && upload(&im->wd2_lo, lo);
     if (!ok) { g_tc_err = "cudaMalloc/cudaMemcpy failed (weights)"; return -1; }
     if (make_map_2d(&im->m_w1b, im->w1b, (uint64_t)im->taps * 32, 16, 32, 16) ||
-        make_map_2d(&im->m_w2b, im->w2b, (uint64_t)im->taps * 64, 32, 64, 32) ||
+        make_map_2d(&im->m_w2b, im->w2b, (uint64_t)im->taps * 96, 16, 96, 16) ||
         make_map_2d(&im->m_ah, im->a_hi, R, im->Kf, 128, 64) || make_map_2d(&im->m_al, im->a_lo, R, im->Kf, 128, 64) ||
         make_map_2d(&im->m_w1h, im->wd1_hi, im->H, im->Kf, im->H % 192 == 0 ? 192 : 256, 64) ||
         make_map_2d(&im->m_w1l, im->wd1_lo, im->H, im->Kf, im->H % 192 == 0 ? 192 : 256, 64) ||
